@@ -1,0 +1,73 @@
+"""CPU: the oracle restatement vs the golden vectors produced by the REAL reference (oracle/make_golden.py).
+
+At generation time the oracle matched the reference bit for bit; here (possibly on another CPU, where MKL may
+pick other GEMM kernels) the elementwise stages must still be bit-exact and the GEMM-fed ones within 1e-6.
+"""
+import pytest
+import torch
+
+from oracle import neurad_oracle as O
+from oracle.convert import to_oracle_cfg
+from tests.helpers import cfg_from_meta, load_golden
+
+CASES = ["nff_static.npz", "nff_actors.npz", "nff_sharp.npz"]
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_oracle_matches_reference_golden(name):
+    meta, g = load_golden(name)
+    cfg = to_oracle_cfg(cfg_from_meta(meta))
+    p, r, ref = g["param"], g["ray"], g["ref"]
+    with torch.no_grad():
+        out = O.nff_outputs(p, cfg, r["origins"], r["directions"], r["pixel_area"], r["times"], r["sensor_idx"],
+                            r["is_lidar"], want_trace=True)
+        inten, drop = O.decode_lidar(p, out["features"])
+    tr = out.pop("trace")
+    got = {**out, **tr, "intensity": inten, "ray_drop_logits": drop}
+    # integer / index work: bit-exact
+    for k in ("inds_1", "inds_2", "actor_id_main", "actor_id_0", "actor_id_1"):
+        assert torch.equal(got[k], ref[k]), k
+    # initial bins are pure elementwise fp32: bit-exact
+    for k in ("bins_s_0", "bins_e_0"):
+        assert torch.equal(got[k], ref[k]), k
+    for k in ("features", "depth", "accumulation", "prop_depth_0", "prop_depth_1", "prop_weights_0", "prop_weights_1",
+              "bins_s_1", "bins_e_1", "bins_s_2", "bins_e_2", "sdf", "alpha", "field_feature", "intensity",
+              "ray_drop_logits"):
+        torch.testing.assert_close(got[k], ref[k], rtol=1e-6, atol=1e-6, msg=lambda m, k=k: f"{k}: {m}")
+
+
+def test_hash_encode_matches_reference_golden():
+    meta, g = load_golden("nff_static.npz")
+    cfg = to_oracle_cfg(cfg_from_meta(meta))
+    p, ref = g["param"], g["ref"]
+    out = O.hash_encode(ref["hash_in"], p["field.hashgrid.static_grid.hash_table"],
+                        p["field.hashgrid.static_grid.scalings"], cfg.main.static.table_size)
+    assert torch.equal(out, ref["hash_out"])
+
+
+def test_density_fn_closure_quirk_is_pinned():
+    """neurad.py:248: late-binding closure -> both proposal rounds evaluate proposal_fields[1].  If the oracle used
+    proposal_fields[0] for round 0 the golden weights could not match (they are random, distinct tables)."""
+    meta, g = load_golden("nff_static.npz")
+    p = g["param"]
+    assert not torch.equal(p["proposal_fields.0.hashgrid.static_grid.hash_table"],
+                           p["proposal_fields.1.hashgrid.static_grid.hash_table"])
+    assert O.density_fn_field_index(0, 2) == 1 and O.density_fn_field_index(1, 2) == 1
+
+
+def test_raygen_matches_reference_golden():
+    meta, g = load_golden("raygen.npz")
+    for cam in ("cam0", "cam3"):
+        c = g[cam]
+        h, w = (int(v) for v in c["hw"])
+        ys, xs = torch.meshgrid(torch.arange(h), torch.arange(w), indexing="ij")
+        coords = torch.stack([ys, xs], -1) + 0.5  # cameras.py:296-330 (pixel_offset 0.5)
+        fx, fy, cx, cy = (float(v) for v in c["intr"])
+        o = O.generate_rays_pinhole(c["c2w"], fx, fy, cx, cy, h, w, coords, float(c["time"]), c["velocity"],
+                                    float(c["rs"][0]), float(c["rs"][1]))
+        for k in ("origins", "directions", "pixel_area", "times"):
+            assert torch.equal(o[k], c[k]), (cam, k)
+    li = g["lidar"]
+    o = O.generate_rays_lidar_points(li["l2w"], li["points"], float(li["time"]), li["velocity"])
+    for k in ("origins", "directions", "pixel_area", "times"):
+        assert torch.equal(o[k], li[k]), k
