@@ -1,0 +1,206 @@
+/* b200nerf.h -- C ABI of libb200nerf.so, the sm_100a backend of NeuRAD's volumetric-rendering hot path.
+ *
+ * The reference (georghess/neurad-studio) has no FFI of its own: its backend seam is the string flag
+ * `NeuRADModelConfig.implementation` (nerfstudio/models/neurad.py:146) that selects tiny-cuda-nn or torch
+ * inside HashEncoding / SHEncoding / MLP, and the module-level plugin API Field / Sampler / Renderer /
+ * Model.get_nff_outputs.  This header is the C boundary a third backend ("b200") binds: every entry point
+ * names the reference interface it replaces.  Conventions:
+ *
+ *   - The caller (PyTorch) owns every buffer.  All `const float*` / `float*` arguments are DEVICE pointers to
+ *     contiguous fp32 arrays unless the name ends in `_host`.  Index outputs are int32.
+ *   - `stream` is a `cudaStream_t` passed as `void*` (NULL = the legacy default stream).
+ *   - Every function returns 0 on success and a negative code on failure; `b200nerf_last_error()` returns a
+ *     thread-local message.  The library never aborts and has no CPU fallback.
+ *   - A `b200nerf_ctx` is bound to one device; several contexts (one per GPU) may coexist in one process.
+ *     One host thread drives one context at a time (same contract as the reference's single-threaded model).
+ *   - Large tables (hash grids, embeddings) are referenced zero-copy and must outlive their use; small tensors
+ *     (MLP weights, decoders, actor trajectories) are repacked into library-owned device memory by the
+ *     `b200nerf_set_*` calls, so call those again after the parameters change.
+ *   - No allocation happens inside `*_fwd` calls.
+ */
+#ifndef B200NERF_H_
+#define B200NERF_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200NERF_VERSION 100
+#define B200NERF_MAX_LEVELS 16
+
+enum {
+  B200NERF_OK = 0,
+  B200NERF_ERR_INVALID = -1,     /* bad argument / unsupported configuration */
+  B200NERF_ERR_CUDA = -2,        /* CUDA runtime error (message has the cudaError string) */
+  B200NERF_ERR_STATE = -3,       /* a required b200nerf_set_* call is missing */
+  B200NERF_ERR_UNSUPPORTED = -4  /* valid in the reference, not implemented here yet */
+};
+
+typedef struct b200nerf_ctx b200nerf_ctx;
+
+/* field selector: NeuRADModel.field / NeuRADModel.proposal_fields[0|1] (neurad.py:180-184, 236-247) */
+enum { B200NERF_FIELD_MAIN = 0, B200NERF_FIELD_PROP0 = 1, B200NERF_FIELD_PROP1 = 2 };
+
+/* HashEncoding hyper-parameters + its `scalings` buffer (field_components/encodings.py:326-352). */
+typedef struct {
+  int32_t num_levels;
+  int32_t features_per_level;
+  int32_t log2_hashmap_size;
+  float scalings[B200NERF_MAX_LEVELS];
+} b200nerf_grid_desc;
+
+const char* b200nerf_last_error(void);
+int b200nerf_version(void);
+
+int b200nerf_create(int device_ordinal, b200nerf_ctx** out);
+int b200nerf_destroy(b200nerf_ctx* ctx);
+
+/* ---- parameters --------------------------------------------------------------------------------------- */
+
+/* NeuRADHashEncoding of one field (field_components/neurad_encoding.py:85-131): the static grid
+ * `static_grid.hash_table` [L*T, F] and, in torch mode, one 3-D grid per actor `actor_grids[i].hash_table`.
+ * `actor_tables_host` is a HOST array of `n_actors` device pointers (NULL when n_actors == 0).
+ * `static_scale` = scene_box.aabb.max() (neurad.py:182); `actor_scale` = ActorSettings.actor_scale. */
+int b200nerf_set_field_grids(b200nerf_ctx* ctx, int field, const b200nerf_grid_desc* static_desc,
+                             const float* static_table, const b200nerf_grid_desc* actor_desc,
+                             const float* const* actor_tables_host, int n_actors, float static_scale,
+                             float actor_scale);
+
+/* NeuRADProposalField.density_decoder = nn.Linear(L*F, 1, bias=False) (fields/neurad_field.py:201). */
+int b200nerf_set_proposal_decoder(b200nerf_ctx* ctx, int field, const float* weight, int in_dim);
+
+/* NeuRADField.mlp_geo (in->hidden->1+nff), mlp_feature (nff+16 ->hidden->hidden->nff) as nn.Linear [out,in]
+ * weights + biases (fields/neurad_field.py:98-117, field_components/mlp.py:142-157), and the SDF slope
+ * `beta = |sdf_to_density.beta| + beta_min` (model_components/utils.py:24-41). */
+int b200nerf_set_main_mlps(b200nerf_ctx* ctx, const float* geo_w0, const float* geo_b0, const float* geo_w1,
+                           const float* geo_b1, const float* feat_w0, const float* feat_b0, const float* feat_w1,
+                           const float* feat_b1, const float* feat_w2, const float* feat_b2, float beta);
+
+/* NeuRADModel.lidar_decoder: MLP 48->32->32->2 (neurad.py:217-224). */
+int b200nerf_set_lidar_decoder(b200nerf_ctx* ctx, const float* w0, const float* b0, const float* w1,
+                               const float* b1, const float* w2, const float* b2);
+
+/* NeuRADModel.appearance_embedding [num_embeds, dim] with temporal interpolation (neurad.py:187-196,
+ * 423-441).  Zero-copy. */
+int b200nerf_set_appearance(b200nerf_ctx* ctx, const float* embedding, int num_embeds, int dim,
+                            int embeds_per_sensor, float duration);
+
+/* DynamicActors buffers/parameters (model_components/dynamic_actors.py:109-170): unique_timestamps [T],
+ * actor_rotations_6d [T,A,6], actor_positions [T,A,3], actor_present_at_time [T,A] (uint8), actor_sizes
+ * [A,3]; `padding_host` = actor_bbox_padding (3 floats, host).  n_actors == 0 disables the actor branch. */
+int b200nerf_set_actors(b200nerf_ctx* ctx, int n_actors, int n_times, const float* timestamps,
+                        const float* rotations_6d, const float* positions, const uint8_t* present,
+                        const float* sizes, const float* padding_host);
+
+/* SamplingSettings + ProposalNetworkSampler / PDFSampler constants (neurad.py:101-117,
+ * ray_samplers.py:255-376, 569-666).  `u1_host` / `u2_host` are PDFSampler's eval-mode quantiles
+ * `linspace(0, 1-1/nb, nb) + 1/(2nb)` for nb = n_prop1+1 and nb = n_nerf+1 (computed by the caller with
+ * torch.linspace so they are bit-identical to the reference's).  `density_field_of_round[i]` selects which
+ * proposal field round i evaluates: the reference's `density_fns` closures bind late (neurad.py:248), so
+ * BOTH rounds evaluate proposal_fields[1]; pass {B200NERF_FIELD_PROP1, B200NERF_FIELD_PROP1} for drop-in
+ * behaviour. */
+int b200nerf_set_sampling(b200nerf_ctx* ctx, int n_prop0, int n_prop1, int n_nerf, float power_lambda,
+                          float power_scaling, float sky_distance, float histogram_padding,
+                          const float* u1_host, const float* u2_host, const int* density_field_of_round,
+                          float camera_area_scale);
+
+/* ---- the fused path: NeuRADModel.get_nff_outputs (neurad.py:368-421), eval mode ------------------------ */
+
+/* A flat RayBundle (cameras/rays.py:252-275).  Optional members may be NULL. */
+typedef struct {
+  const float* origins;      /* [N,3] */
+  const float* directions;   /* [N,3] */
+  const float* pixel_area;   /* [N]   (unscaled; camera rays are scaled by camera_area_scale in-kernel,
+                                       NeuRADModel._scale_pixel_area neurad.py:702-709) */
+  const float* times;        /* [N]   */
+  const float* nears;        /* [N] or NULL -> 0 (neurad.py:449) */
+  const float* fars;         /* [N] or NULL -> 1e6, clamped to sky_distance (neurad.py:445-448) */
+  const int64_t* sensor_idx; /* [N] or NULL -> fallback sensor 0 (metadata["sensor_idxs"], neurad.py:424-427) */
+  const uint8_t* is_lidar;   /* [N] or NULL -> all camera rays (metadata["is_lidar"]) */
+} b200nerf_rays;
+
+typedef struct {
+  float* features;       /* [N, nff_out_dim + appearance_dim] rendered features ++ appearance embedding */
+  float* depth;          /* [N] */
+  float* accumulation;   /* [N] */
+  float* prop_depth_0;   /* [N] */
+  float* prop_depth_1;   /* [N] */
+  float* intensity;      /* [N] or NULL: sigmoid(lidar_decoder(features)[0]) (neurad.py:350-357) */
+  float* ray_drop_logit; /* [N] or NULL */
+} b200nerf_outputs;
+
+/* Optional per-stage dump used by the parity tests (any member may be NULL). */
+typedef struct {
+  float* prop_weights_0; /* [N, n_prop0] */
+  float* prop_weights_1; /* [N, n_prop1] */
+  float* bins_s_1;       /* [N, n_prop1+1] spacing-domain bin edges after resampling round 1 */
+  float* bins_e_1;       /* [N, n_prop1+1] euclidean */
+  float* bins_s_2;       /* [N, n_nerf+1] */
+  float* bins_e_2;       /* [N, n_nerf+1] */
+  int32_t* inds_1;       /* [N, n_prop1+1] searchsorted(cdf, u, right) */
+  int32_t* inds_2;       /* [N, n_nerf+1] */
+  float* sdf;            /* [N, n_nerf] */
+  float* alpha;          /* [N, n_nerf] */
+  float* field_feature;  /* [N, n_nerf, nff_out_dim] */
+  float* weights;        /* [N, n_nerf] (after the sky top-up) */
+  int32_t* actor_id_0;   /* [N, n_prop0] actor index per sample or -1 */
+  int32_t* actor_id_1;   /* [N, n_prop1] */
+  int32_t* actor_id_main;/* [N, n_nerf] */
+} b200nerf_trace;
+
+int b200nerf_nff_render_fwd(b200nerf_ctx* ctx, const b200nerf_rays* rays, int64_t n_rays,
+                            const b200nerf_outputs* out, const b200nerf_trace* trace, void* stream);
+
+/* ---- stage-level operators (the reference's per-module API) -------------------------------------------- */
+
+/* HashEncoding.forward / pytorch_fwd (encodings.py:425-471): x [P,3] in [0,1] -> out [P, L*F].
+ * `indices` (optional) receives the 8 hashed table rows per level, [P, L, 8], in the reference's corner
+ * order hashed_0..hashed_7 (encodings.py:436-443). */
+int b200nerf_hashgrid_fwd(b200nerf_ctx* ctx, const b200nerf_grid_desc* desc, const float* table, const float* x,
+                          float* out, int32_t* indices, int64_t n_points, void* stream);
+
+/* SHEncoding(levels=4).forward (encodings.py:797-805, utils/math.py:31-94): dirs [P,3] -> [P,16]. */
+int b200nerf_sh4_fwd(b200nerf_ctx* ctx, const float* dirs, float* out, int64_t n_points, void* stream);
+
+/* PDFSampler.generate_ray_samples, eval mode, include_original=False (ray_samplers.py:280-361):
+ * weights [N,S], existing spacing bins [N,S+1], quantiles u [S_new+1] (device) -> new spacing bins
+ * [N,S_new+1]; optional cdf [N,S+1] and searchsorted indices [N,S_new+1]. */
+int b200nerf_pdf_resample(b200nerf_ctx* ctx, const float* weights, const float* bins, const float* u, int n_rays,
+                          int s_old, int s_new, float histogram_padding, float* new_bins, float* cdf,
+                          int32_t* inds, void* stream);
+
+/* RaySamples.get_weights (cameras/rays.py:188-210): deltas, densities [N,S] -> weights [N,S]. */
+int b200nerf_density_to_weights(b200nerf_ctx* ctx, const float* deltas, const float* densities, int n_rays,
+                                int s, float* weights, void* stream);
+
+/* nerfacc.render_weight_from_alpha on dense [N,S] (call site neurad.py:717). */
+int b200nerf_alpha_to_weights(b200nerf_ctx* ctx, const float* alphas, int n_rays, int s, float* weights,
+                              void* stream);
+
+/* ---- ray generation ------------------------------------------------------------------------------------- */
+
+/* Cameras.generate_rays for one PERSPECTIVE camera without distortion, top-to-bottom rolling shutter
+ * (cameras/cameras.py:633-667, 793-798, 898-969), over the pixel grid rows row0, row0+row_step, ... and
+ * columns col0, col0+col_step, ... (pixel centres at +0.5).  NeuRAD renders at [step//2::step] with step =
+ * rgb_upsample_factor (neurad.py:641-646), so generating only those pixels removes the reference's 9x waste.
+ * `c2w_host` is 12 floats (3x4 row major), `velocity_host` 3 floats (may be NULL: no rolling shutter).
+ * Outputs: origins/directions [n_rows*n_cols,3], pixel_area/times [n_rows*n_cols]. */
+int b200nerf_raygen_pinhole(b200nerf_ctx* ctx, const float* c2w_host, float fx, float fy, float cx, float cy,
+                            int height, int width, int row0, int row_step, int n_rows, int col0, int col_step,
+                            int n_cols, float time, const float* velocity_host, float rolling_shutter_time,
+                            float time_to_center_pixel, float* origins, float* directions, float* pixel_area,
+                            float* times, void* stream);
+
+/* Lidars._generate_rays_from_points, assume_ego_compensated=True (cameras/lidars.py:399-460): points [P,
+ * point_stride] = (x,y,z,intensity,dt,...) in the lidar frame -> rays; `distance` (optional) = the range. */
+int b200nerf_raygen_lidar_points(b200nerf_ctx* ctx, const float* l2w_host, const float* points, int point_stride,
+                                 int64_t n_points, float scan_time, const float* velocity_host, float h_div,
+                                 float v_div, float* origins, float* directions, float* pixel_area, float* times,
+                                 float* distance, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200NERF_H_ */

@@ -1,0 +1,312 @@
+"""Host side of the sm_100a NeuRAD backend: owns a `b200nerf_ctx`, feeds it torch CUDA tensors by pointer and
+launches the kernels on torch's current stream.  PyTorch is plumbing here (device memory, streams); all compute
+is in libb200nerf.so.  There is no CPU path: constructing a `B200Backend` without a CUDA device raises.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Dict, Optional, Sequence
+
+import torch
+
+from . import lib as _lib
+from .config import HashGridSettings, NeuRADConfig
+from .lib import FIELD_MAIN, FIELD_PROP0, FIELD_PROP1, GridDesc, Outputs, Rays, Trace, TRACE_FIELDS
+
+
+def pdf_quantiles(num_samples: int) -> torch.Tensor:
+    """PDFSampler's eval-mode `u` (ray_samplers.py:332-336), evaluated with torch.linspace exactly like the
+    reference so the searchsorted inputs are bit-identical."""
+    num_bins = num_samples + 1
+    u = torch.linspace(0.0, 1.0 - (1.0 / num_bins), steps=num_bins)
+    return u + 1.0 / (2 * num_bins)
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def grid_desc(g: HashGridSettings, scalings: Optional[torch.Tensor] = None) -> GridDesc:
+    d = GridDesc()
+    d.num_levels, d.features_per_level, d.log2_hashmap_size = g.num_levels, g.hashgrid_dim, g.log2_hashmap_size
+    sc = (scalings if scalings is not None else g.scalings()).detach().cpu().float().tolist()
+    if len(sc) != g.num_levels:
+        raise ValueError("scalings buffer does not match num_levels")
+    for i, v in enumerate(sc):
+        d.scalings[i] = v
+    return d
+
+
+class B200Backend:
+    """One context per CUDA device.  `load_params` takes tensors under the reference's state_dict names."""
+
+    def __init__(self, device: Optional[torch.device] = None):
+        if not torch.cuda.is_available():
+            raise RuntimeError("neurad_studio_b200 requires a CUDA (sm_100a) device; there is no CPU fallback")
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        if self.device.type != "cuda":
+            raise RuntimeError("neurad_studio_b200 runs on CUDA devices only")
+        self.lib = _lib.load()
+        h = ctypes.c_void_p()
+        _lib.check(self.lib, self.lib.b200nerf_create(self.device.index or 0, ctypes.byref(h)))
+        self._h = h
+        self._keep: Dict[str, object] = {}  # tensors the library references zero-copy
+        self.cfg: Optional[NeuRADConfig] = None
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            self.lib.b200nerf_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------------------------------ helpers
+    def _dev(self, t: torch.Tensor, dtype=torch.float32) -> torch.Tensor:
+        if t.device != self.device or t.dtype != dtype or not t.is_contiguous():
+            t = t.detach().to(device=self.device, dtype=dtype).contiguous()
+        return t
+
+    def _check(self, rc: int):
+        _lib.check(self.lib, rc)
+
+    @property
+    def _stream(self):
+        return ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    # --------------------------------------------------------------------------------------- parameters
+    def load_params(self, cfg: NeuRADConfig, params: Dict[str, torch.Tensor], density_field_of_round: Sequence[int] = (FIELD_PROP1, FIELD_PROP1)):
+        """Bind a full parameter set.  `density_field_of_round` defaults to the reference's effective behaviour:
+        both proposal rounds evaluate proposal_fields[1] (late-binding closures at models/neurad.py:248)."""
+        self.cfg = cfg
+        p = params
+        n_act = cfg.n_actors
+        prefixes = {FIELD_MAIN: "field", FIELD_PROP0: "proposal_fields.0", FIELD_PROP1: "proposal_fields.1"}
+        gcfgs = {FIELD_MAIN: cfg.grid, FIELD_PROP0: cfg.proposal_grid_1, FIELD_PROP1: cfg.proposal_grid_2}
+        static_scale = float(p["static_scale"]) if "static_scale" in p else float(cfg.static_scale)
+        for f, pre in prefixes.items():
+            g = gcfgs[f]
+            tab = self._dev(p[f"{pre}.hashgrid.static_grid.hash_table"])
+            self._keep[f"{pre}.static"] = tab
+            sd = grid_desc(g.static, p.get(f"{pre}.hashgrid.static_grid.scalings"))
+            ad, arr = None, None
+            if n_act > 0:
+                tabs = [self._dev(p[f"{pre}.hashgrid.actor_grids.{a}.hash_table"]) for a in range(n_act)]
+                self._keep[f"{pre}.actors"] = tabs
+                arr = (ctypes.c_void_p * n_act)(*[t.data_ptr() for t in tabs])
+                ad = grid_desc(g.actor, p.get(f"{pre}.hashgrid.actor_grids.0.scalings"))
+            if f != FIELD_MAIN:
+                w = self._dev(p[f"{pre}.density_decoder.weight"]).reshape(-1)
+                self._check(self.lib.b200nerf_set_proposal_decoder(self._h, f, _ptr(w), w.numel()))
+            self._check(
+                self.lib.b200nerf_set_field_grids(
+                    self._h, f, ctypes.byref(sd), _ptr(tab), ctypes.byref(ad) if ad is not None else None,
+                    arr, n_act, static_scale, float(g.actor_scale),
+                )
+            )
+        names = ["field.mlp_geo.layers.0", "field.mlp_geo.layers.1", "field.mlp_feature.layers.0",
+                 "field.mlp_feature.layers.1", "field.mlp_feature.layers.2"]
+        ts = []
+        for nme in names:
+            ts += [self._dev(p[nme + ".weight"]), self._dev(p[nme + ".bias"])]
+        beta = float(p["field.sdf_to_density.beta"].abs().item() + 0.0001)  # model_components/utils.py:38-41
+        self._check(self.lib.b200nerf_set_main_mlps(self._h, *[_ptr(t) for t in ts], beta))
+        if "lidar_decoder.layers.0.weight" in p:
+            ts = []
+            for i in range(3):
+                ts += [self._dev(p[f"lidar_decoder.layers.{i}.weight"]), self._dev(p[f"lidar_decoder.layers.{i}.bias"])]
+            self._check(self.lib.b200nerf_set_lidar_decoder(self._h, *[_ptr(t) for t in ts]))
+        emb = self._dev(p["appearance_embedding.weight"])
+        self._keep["appearance"] = emb
+        self._check(
+            self.lib.b200nerf_set_appearance(self._h, _ptr(emb), emb.shape[0], emb.shape[1], cfg.embeds_per_sensor, float(cfg.duration))
+        )
+        if n_act > 0:
+            ts_ = self._dev(p["dynamic_actors.unique_timestamps"])
+            rot = self._dev(p["dynamic_actors.actor_rotations_6d"])
+            pos = self._dev(p["dynamic_actors.actor_positions"])
+            pres = self._dev(p["dynamic_actors.actor_present_at_time"], torch.uint8)
+            sizes = self._dev(p["dynamic_actors.actor_sizes"])
+            pad = p.get("dynamic_actors.actor_padding")
+            pad = list(cfg.actor_bbox_padding) if pad is None else pad.detach().cpu().tolist()
+            cpad = (ctypes.c_float * 3)(*pad)
+            self._check(
+                self.lib.b200nerf_set_actors(self._h, n_act, ts_.shape[0], _ptr(ts_), _ptr(rot), _ptr(pos), _ptr(pres), _ptr(sizes), cpad)
+            )
+        else:
+            self._check(self.lib.b200nerf_set_actors(self._h, 0, 0, None, None, None, None, None, None))
+        sp = cfg.sampling
+        u1, u2 = pdf_quantiles(sp.num_proposal_samples[1]), pdf_quantiles(sp.num_nerf_samples)
+        cu1 = (ctypes.c_float * u1.numel())(*u1.tolist())
+        cu2 = (ctypes.c_float * u2.numel())(*u2.tolist())
+        rounds = (ctypes.c_int * 2)(*density_field_of_round)
+        self._check(
+            self.lib.b200nerf_set_sampling(
+                self._h, sp.num_proposal_samples[0], sp.num_proposal_samples[1], sp.num_nerf_samples,
+                sp.power_lambda, sp.power_scaling, sp.sky_distance, sp.histogram_padding, cu1, cu2, rounds,
+                float(cfg.rgb_upsample_factor**2),
+            )
+        )
+
+    # ------------------------------------------------------------------------------------------ fused path
+    def render(self, rays: Dict[str, torch.Tensor], want_trace: bool = False, want_intensity: bool = False,
+               out: Optional[Dict[str, torch.Tensor]] = None) -> Dict[str, torch.Tensor]:
+        """NeuRADModel.get_nff_outputs (models/neurad.py:368-421) for a flat ray batch.
+
+        rays: origins [N,3], directions [N,3], pixel_area [N,1]|[N], times [N,1]|[N] and optionally nears, fars,
+        sensor_idx (int64), is_lidar (bool/uint8).  Returns features [N,48], depth/accumulation/prop_depth_i [N,1].
+        `out` may supply pre-allocated output tensors (e.g. a slice of an all-gather buffer)."""
+        cfg = self.cfg
+        if cfg is None:
+            raise RuntimeError("load_params() must be called before render()")
+        o = self._dev(rays["origins"])
+        n = o.shape[0]
+        r = Rays()
+        hold = [o]
+
+        def put(name, key, dtype=torch.float32, required=False):
+            t = rays.get(key)
+            if t is None:
+                if required:
+                    raise KeyError(key)
+                setattr(r, name, None)
+                return
+            t = self._dev(t.reshape(n, -1) if name in ("origins", "directions") else t.reshape(-1), dtype)
+            hold.append(t)
+            setattr(r, name, t.data_ptr())
+
+        r.origins = o.data_ptr()
+        put("directions", "directions", required=True)
+        put("pixel_area", "pixel_area", required=True)
+        put("times", "times", required=True)
+        put("nears", "nears")
+        put("fars", "fars")
+        put("sensor_idx", "sensor_idx", torch.int64)
+        put("is_lidar", "is_lidar", torch.uint8)
+        fdim = cfg.feature_dim
+        res = out if out is not None else {}
+        shapes = {"features": (n, fdim), "depth": (n, 1), "accumulation": (n, 1), "prop_depth_0": (n, 1), "prop_depth_1": (n, 1)}
+        if want_intensity:
+            shapes.update({"intensity": (n, 1), "ray_drop_logits": (n, 1)})
+        for k, shp in shapes.items():
+            if k not in res:
+                res[k] = torch.empty(shp, device=self.device, dtype=torch.float32)
+            elif not (res[k].is_contiguous() and res[k].device == self.device and res[k].dtype == torch.float32 and res[k].numel() == shp[0] * shp[1]):
+                raise ValueError(f"pre-allocated output {k} has the wrong layout")
+        oo = Outputs()
+        for k in ("features", "depth", "accumulation", "prop_depth_0", "prop_depth_1"):
+            setattr(oo, k, res[k].data_ptr())
+        oo.intensity = res["intensity"].data_ptr() if want_intensity else None
+        oo.ray_drop_logit = res["ray_drop_logits"].data_ptr() if want_intensity else None
+        tr = None
+        if want_trace:
+            S0, S1 = cfg.sampling.num_proposal_samples
+            S2 = cfg.sampling.num_nerf_samples
+            f32, i32 = torch.float32, torch.int32
+            tshapes = {
+                "prop_weights_0": ((n, S0), f32), "prop_weights_1": ((n, S1), f32),
+                "bins_s_1": ((n, S1 + 1), f32), "bins_e_1": ((n, S1 + 1), f32),
+                "bins_s_2": ((n, S2 + 1), f32), "bins_e_2": ((n, S2 + 1), f32),
+                "inds_1": ((n, S1 + 1), i32), "inds_2": ((n, S2 + 1), i32),
+                "sdf": ((n, S2), f32), "alpha": ((n, S2), f32), "field_feature": ((n, S2, cfg.nff_out_dim), f32),
+                "weights": ((n, S2), f32),
+                "actor_id_0": ((n, S0), i32), "actor_id_1": ((n, S1), i32), "actor_id_main": ((n, S2), i32),
+            }
+            tr = Trace()
+            for k in TRACE_FIELDS:
+                shp, dt = tshapes[k]
+                res[k] = torch.empty(shp, device=self.device, dtype=dt)
+                setattr(tr, k, res[k].data_ptr())
+        self._check(
+            self.lib.b200nerf_nff_render_fwd(self._h, ctypes.byref(r), n, ctypes.byref(oo), ctypes.byref(tr) if tr is not None else None, self._stream)
+        )
+        return res
+
+    # --------------------------------------------------------------------------------------- stage operators
+    def hashgrid_fwd(self, g: HashGridSettings, table: torch.Tensor, x: torch.Tensor, scalings: Optional[torch.Tensor] = None, want_indices: bool = False):
+        """HashEncoding.forward (encodings.py:425-471): x [...,3] -> [..., L*F] (+ hashed rows [..., L, 8])."""
+        d = grid_desc(g, scalings)
+        table = self._dev(table)
+        xs = self._dev(x).reshape(-1, 3)
+        n = xs.shape[0]
+        out = torch.empty(n, g.num_levels * g.hashgrid_dim, device=self.device)
+        idx = torch.empty(n, g.num_levels, 8, device=self.device, dtype=torch.int32) if want_indices else None
+        self._check(self.lib.b200nerf_hashgrid_fwd(self._h, ctypes.byref(d), _ptr(table), _ptr(xs), _ptr(out), _ptr(idx), n, self._stream))
+        out = out.reshape(*x.shape[:-1], -1)
+        return (out, idx.reshape(*x.shape[:-1], g.num_levels, 8)) if want_indices else out
+
+    def sh4_fwd(self, dirs: torch.Tensor) -> torch.Tensor:
+        """SHEncoding(levels=4).forward (encodings.py:797-805)."""
+        d = self._dev(dirs).reshape(-1, 3)
+        out = torch.empty(d.shape[0], 16, device=self.device)
+        self._check(self.lib.b200nerf_sh4_fwd(self._h, _ptr(d), _ptr(out), d.shape[0], self._stream))
+        return out.reshape(*dirs.shape[:-1], 16)
+
+    def pdf_resample(self, weights: torch.Tensor, bins: torch.Tensor, num_samples: int, histogram_padding: float = 0.01):
+        """PDFSampler (eval, include_original=False): weights [N,S], spacing bins [N,S+1] ->
+        (new bins [N,S_new+1], cdf [N,S+1], searchsorted indices [N,S_new+1] int32)."""
+        w, b = self._dev(weights), self._dev(bins)
+        n, s = w.shape
+        u = pdf_quantiles(num_samples).to(self.device)
+        nb = torch.empty(n, num_samples + 1, device=self.device)
+        cdf = torch.empty(n, s + 1, device=self.device)
+        inds = torch.empty(n, num_samples + 1, device=self.device, dtype=torch.int32)
+        self._check(self.lib.b200nerf_pdf_resample(self._h, _ptr(w), _ptr(b), _ptr(u), n, s, num_samples, histogram_padding, _ptr(nb), _ptr(cdf), _ptr(inds), self._stream))
+        return nb, cdf, inds
+
+    def density_to_weights(self, deltas: torch.Tensor, densities: torch.Tensor) -> torch.Tensor:
+        """RaySamples.get_weights (cameras/rays.py:188-210) on [N,S]."""
+        d, s = self._dev(deltas), self._dev(densities)
+        out = torch.empty_like(d)
+        self._check(self.lib.b200nerf_density_to_weights(self._h, _ptr(d), _ptr(s), d.shape[0], d.shape[1], _ptr(out), self._stream))
+        return out
+
+    def alpha_to_weights(self, alphas: torch.Tensor) -> torch.Tensor:
+        """nerfacc.render_weight_from_alpha, dense [N,S] (call site models/neurad.py:717)."""
+        a = self._dev(alphas)
+        out = torch.empty_like(a)
+        self._check(self.lib.b200nerf_alpha_to_weights(self._h, _ptr(a), a.shape[0], a.shape[1], _ptr(out), self._stream))
+        return out
+
+    # ------------------------------------------------------------------------------------------- ray generation
+    def raygen_pinhole(self, cam, row0: int = 0, row_step: int = 1, col0: int = 0, col_step: int = 1) -> Dict[str, torch.Tensor]:
+        """Cameras.generate_rays for one pinhole camera (scene.PinholeCamera) over a strided pixel grid."""
+        n_rows = len(range(row0, cam.height, row_step))
+        n_cols = len(range(col0, cam.width, col_step))
+        n = n_rows * n_cols
+        o = torch.empty(n, 3, device=self.device)
+        d = torch.empty(n, 3, device=self.device)
+        a = torch.empty(n, 1, device=self.device)
+        t = torch.empty(n, 1, device=self.device)
+        c2w = (ctypes.c_float * 12)(*cam.c2w.reshape(-1).tolist())
+        vel = (ctypes.c_float * 3)(*cam.velocity.tolist()) if cam.velocity is not None else None
+        self._check(
+            self.lib.b200nerf_raygen_pinhole(
+                self._h, c2w, cam.fx, cam.fy, cam.cx, cam.cy, cam.height, cam.width, row0, row_step, n_rows, col0,
+                col_step, n_cols, cam.time, vel, cam.rolling_shutter_time, cam.time_to_center_pixel, _ptr(o), _ptr(d),
+                _ptr(a), _ptr(t), self._stream,
+            )
+        )
+        return {"origins": o, "directions": d, "pixel_area": a, "times": t, "shape": (n_rows, n_cols)}
+
+    def raygen_lidar_points(self, scan, points: Optional[torch.Tensor] = None) -> Dict[str, torch.Tensor]:
+        """Lidars.generate_rays(points=...) for one scan (scene.LidarScan)."""
+        pts = self._dev(scan.points if points is None else points)
+        n = pts.shape[0]
+        o = torch.empty(n, 3, device=self.device)
+        d = torch.empty(n, 3, device=self.device)
+        a = torch.empty(n, 1, device=self.device)
+        t = torch.empty(n, 1, device=self.device)
+        dist = torch.empty(n, 1, device=self.device)
+        l2w = (ctypes.c_float * 12)(*scan.l2w.reshape(-1).tolist())
+        vel = (ctypes.c_float * 3)(*scan.velocity.tolist()) if scan.velocity is not None else None
+        self._check(
+            self.lib.b200nerf_raygen_lidar_points(
+                self._h, l2w, _ptr(pts), pts.shape[1], n, scan.time, vel, 3.0e-3, 1.5e-3, _ptr(o), _ptr(d), _ptr(a),
+                _ptr(t), _ptr(dist), self._stream,
+            )
+        )
+        return {"origins": o, "directions": d, "pixel_area": a, "times": t, "directions_norm": dist, "did_return": dist < 1e3}

@@ -1,0 +1,717 @@
+// b200nerf.cu -- kernels + C ABI of libb200nerf.so (sm_100a).  See include/b200nerf.h for the contract.
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/b200nerf.h"
+#include "nff_device.h"
+
+using namespace nff;
+
+// ------------------------------------------------------------------------------------------- error plumbing
+static thread_local std::string g_err;
+static int fail(int code, const std::string& msg) {
+  g_err = msg;
+  return code;
+}
+#define CUDA_TRY(expr)                                                                                   \
+  do {                                                                                                   \
+    cudaError_t e_ = (expr);                                                                             \
+    if (e_ != cudaSuccess)                                                                               \
+      return fail(B200NERF_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e_));                \
+  } while (0)
+#define REQUIRE(cond, msg) \
+  do {                     \
+    if (!(cond)) return fail(B200NERF_ERR_INVALID, std::string(msg)); \
+  } while (0)
+
+struct b200nerf_ctx {
+  int device = 0;
+  int sm_count = 0;
+  FieldGrids fields[3]{};
+  bool have_field[3] = {false, false, false};
+  const float** d_actor_tables[3] = {nullptr, nullptr, nullptr};
+  float* d_decoder[3] = {nullptr, nullptr, nullptr};
+  float* d_main_mlp = nullptr;
+  bool have_main_mlp = false;
+  float beta = 0.f;
+  float* d_lidar_mlp = nullptr;
+  bool have_lidar = false;
+  Appearance app{};
+  bool have_app = false;
+  Actors actors{};
+  float *d_act_times = nullptr, *d_act_kf = nullptr, *d_act_bounds = nullptr, *d_act_radii = nullptr;
+  uint8_t* d_act_present = nullptr;
+  Sampling samp{};
+  bool have_samp = false;
+  float *d_u1 = nullptr, *d_u2 = nullptr;
+  int n_prop0 = 0, n_prop1 = 0, n_nerf = 0;
+};
+
+namespace {
+struct DeviceGuard {
+  int prev = 0;
+  explicit DeviceGuard(int dev) {
+    cudaGetDevice(&prev);
+    if (prev != dev) cudaSetDevice(dev);
+  }
+  ~DeviceGuard() { cudaSetDevice(prev); }
+};
+
+int make_grid(const b200nerf_grid_desc* d, const float* table, Grid* g) {
+  REQUIRE(d != nullptr, "grid descriptor is NULL");
+  REQUIRE(d->num_levels >= 1 && d->num_levels <= kMaxLevels, "num_levels must be in [1,16]");
+  REQUIRE(d->log2_hashmap_size >= 1 && d->log2_hashmap_size <= 30, "log2_hashmap_size out of range");
+  g->table = table;
+  g->T = 1u << d->log2_hashmap_size;
+  g->mask = g->T - 1u;
+  g->L = d->num_levels;
+  g->F = d->features_per_level;
+  for (int i = 0; i < kMaxLevels; ++i) g->res[i] = i < d->num_levels ? d->scalings[i] : 0.f;
+  return 0;
+}
+}  // namespace
+
+// =================================================================================================== kernels
+
+template <int WARPS>
+__global__ void __launch_bounds__(WARPS * 32) nff_render_kernel(const __grid_constant__ RenderParams P) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float* mlp = reinterpret_cast<float*>(smem_raw);
+  constexpr int kMlpBytes = (kMainMlpFloats * 4 + 15) / 16 * 16;
+  WarpShared* ws = reinterpret_cast<WarpShared*>(smem_raw + kMlpBytes) + (threadIdx.x >> 5);
+  for (int i = threadIdx.x; i < kMainMlpFloats; i += WARPS * 32) mlp[i] = P.main_mlp[i];
+  __syncthreads();
+  const int64_t stride = (int64_t)gridDim.x * WARPS;
+  for (int64_t ray = (int64_t)blockIdx.x * WARPS + (threadIdx.x >> 5); ray < P.n_rays; ray += stride)
+    render_ray(P, *ws, mlp, ray);
+}
+
+// NeuRADModel.decode_features, lidar half (models/neurad.py:350-357): one thread per ray.
+__global__ void lidar_decode_kernel(const float* __restrict__ mlp, const float* __restrict__ feats, int fdim,
+                                    int64_t n, float* __restrict__ intensity, float* __restrict__ drop) {
+  __shared__ __align__(16) float w[kLidarMlpFloats];
+  for (int i = threadIdx.x; i < kLidarMlpFloats; i += blockDim.x) w[i] = mlp[i];
+  __syncthreads();
+  int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n) return;
+  float x[kNff + kApp];
+#pragma unroll
+  for (int i = 0; i < kNff + kApp; ++i) x[i] = i < fdim ? feats[r * fdim + i] : 0.f;
+  float h[kHidden], h2[kHidden], o[2];
+  dense<kNff + kApp, kHidden, kHidden, true>(w + kOffLidW0, w + kOffLidB0, x, h);
+  dense<kHidden, kHidden, kHidden, true>(w + kOffLidW1, w + kOffLidB1, h, h2);
+  dense<kHidden, 2, kLidOutP, false>(w + kOffLidW2, w + kOffLidB2, h2, o);
+  if (intensity) intensity[r] = 1.0f / (1.0f + expf(-o[0]));
+  if (drop) drop[r] = o[1];
+}
+
+// HashEncoding.forward (encodings.py:425-471), generic L / F: one thread per (point, level).
+__global__ void hashgrid_fwd_kernel(Grid g, const float* __restrict__ x, float* __restrict__ out,
+                                    int32_t* __restrict__ indices, int64_t n_points) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_points * g.L) return;
+  int64_t p = i / g.L;
+  int l = (int)(i % g.L);
+  Cell c = grid_cell(x[3 * p], x[3 * p + 1], x[3 * p + 2], g.res[l]);
+  uint32_t r[8];
+  cell_rows(c, g.mask, r);
+  if (indices) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) indices[(p * g.L + l) * 8 + k] = (int32_t)(r[k] + (uint32_t)l * g.T);
+  }
+  const float* base = g.table + (size_t)l * g.T * g.F;
+  for (int f = 0; f < g.F; ++f) {
+    float v[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v[k] = __ldg(base + (size_t)r[k] * g.F + f);
+    out[p * g.L * g.F + l * g.F + f] = trilerp(v, c);
+  }
+}
+
+__global__ void sh4_fwd_kernel(const float* __restrict__ dirs, float* __restrict__ out, int64_t n) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  // SHEncoding receives get_normalized_directions(d) = (d+1)/2 from the field; as a stand-alone operator it is
+  // the polynomial of utils/math.py:31-94 applied to its input as is.
+  float x = dirs[3 * i], y = dirs[3 * i + 1], z = dirs[3 * i + 2];
+  float c[16];
+  sh4_poly(x, y, z, c);
+#pragma unroll
+  for (int k = 0; k < 16; ++k) out[16 * i + k] = c[k];
+}
+
+// PDFSampler (ray_samplers.py:309-361), generic S: one warp per ray, cdf in shared memory.
+__global__ void pdf_resample_kernel(const float* __restrict__ weights, const float* __restrict__ bins,
+                                    const float* __restrict__ u, int n_rays, int S, int S_new, float hist_pad,
+                                    float* __restrict__ new_bins, float* __restrict__ cdf_out,
+                                    int32_t* __restrict__ inds) {
+  extern __shared__ float sm[];
+  const int warp = threadIdx.x >> 5, ln = threadIdx.x & 31;
+  float* cdf = sm + warp * (S + 1);
+  int ray = blockIdx.x * (blockDim.x >> 5) + warp;
+  if (ray >= n_rays) return;
+  const float* w = weights + (size_t)ray * S;
+  const float* b = bins + (size_t)ray * (S + 1);
+  float part = 0.f;
+  for (int s = ln; s < S; s += 32) part += __fadd_rn(w[s], hist_pad);
+  float tot = warp_sum(part);
+  float padding = fmaxf(__fsub_rn(1e-5f, tot), 0.f);
+  float pad_each = __fdiv_rn(padding, (float)S);
+  tot = __fadd_rn(tot, padding);
+  float carry = 0.f;
+  for (int s0 = 0; s0 < S; s0 += 32) {
+    int s = s0 + ln;
+    float pdf = s < S ? __fdiv_rn(__fadd_rn(__fadd_rn(w[s], hist_pad), pad_each), tot) : 0.f;
+    float incl = warp_scan_add(pdf) + carry;
+    carry = __shfl_sync(0xffffffffu, incl, 31);
+    if (s < S) cdf[s + 1] = fminf(1.f, incl);
+  }
+  if (ln == 0) cdf[0] = 0.f;
+  __syncwarp();
+  if (cdf_out)
+    for (int s = ln; s <= S; s += 32) cdf_out[(size_t)ray * (S + 1) + s] = cdf[s];
+  for (int i = ln; i <= S_new; i += 32) {
+    float uu = u[i];
+    int lo = 0, hi = S + 1;
+    while (lo < hi) {
+      int mid = (lo + hi) >> 1;
+      if (cdf[mid] <= uu) lo = mid + 1; else hi = mid;
+    }
+    int below = min(max(lo - 1, 0), S), above = min(lo, S);
+    float c0 = cdf[below], c1 = cdf[above];
+    float t = nan_to_num(__fdiv_rn(__fsub_rn(uu, c0), __fsub_rn(c1, c0)));
+    t = fminf(fmaxf(t, 0.f), 1.f);
+    new_bins[(size_t)ray * (S_new + 1) + i] = __fadd_rn(b[below], __fmul_rn(t, __fsub_rn(b[above], b[below])));
+    if (inds) inds[(size_t)ray * (S_new + 1) + i] = lo;
+  }
+}
+
+// RaySamples.get_weights (rays.py:188-210) / nerfacc.render_weight_from_alpha: one warp per ray, generic S.
+template <bool FROM_ALPHA>
+__global__ void weights_kernel(const float* __restrict__ a, const float* __restrict__ b, int n_rays, int S,
+                               float* __restrict__ out) {
+  const int warp = threadIdx.x >> 5, ln = threadIdx.x & 31;
+  int ray = blockIdx.x * (blockDim.x >> 5) + warp;
+  if (ray >= n_rays) return;
+  float carry = FROM_ALPHA ? 1.f : 0.f;
+  for (int s0 = 0; s0 < S; s0 += 32) {
+    int s = s0 + ln;
+    size_t idx = (size_t)ray * S + s;
+    if (FROM_ALPHA) {
+      float al = s < S ? a[idx] : 0.f;
+      float incl = warp_scan_mul(1.f - al) * carry;
+      float prev = __shfl_up_sync(0xffffffffu, incl, 1);
+      float T = ln == 0 ? carry : prev;
+      carry = __shfl_sync(0xffffffffu, incl, 31);
+      if (s < S) out[idx] = al * T;
+    } else {
+      float dd = s < S ? __fmul_rn(a[idx], b[idx]) : 0.f;
+      float incl = warp_scan_add(dd);
+      float prev = __shfl_up_sync(0xffffffffu, incl, 1);
+      float excl = carry + (ln == 0 ? 0.f : prev);
+      carry += __shfl_sync(0xffffffffu, incl, 31);
+      if (s < S) out[idx] = nan_to_num((1.f - expf(-dd)) * expf(-excl));
+    }
+  }
+}
+
+// Per-keyframe Gram-Schmidt of the 6-D rotations (utils/poses.py:107-114) + actor_bounds / radii
+// (dynamic_actors.py:107-108, neurad_encoding.py:227).
+__global__ void actors_prep_kernel(int n_times, int n_actors, const float* __restrict__ rot6, const float* __restrict__ pos,
+                                   const float* __restrict__ sizes, float p0, float p1, float p2,
+                                   float* __restrict__ kf, float* __restrict__ bounds, float* __restrict__ radii) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n_times * n_actors) {
+    float a1[3] = {rot6[6 * i], rot6[6 * i + 1], rot6[6 * i + 2]};
+    float a2[3] = {rot6[6 * i + 3], rot6[6 * i + 4], rot6[6 * i + 5]};
+    normalize3(a1);
+    float dt = fadd(fadd(fmul(a1[0], a2[0]), fmul(a1[1], a2[1])), fmul(a1[2], a2[2]));
+    a2[0] = fsub(a2[0], fmul(dt, a1[0]));
+    a2[1] = fsub(a2[1], fmul(dt, a1[1]));
+    a2[2] = fsub(a2[2], fmul(dt, a1[2]));
+    normalize3(a2);
+    float* o = kf + 9 * (size_t)i;
+    o[0] = a1[0]; o[1] = a1[1]; o[2] = a1[2];
+    o[3] = a2[0]; o[4] = a2[1]; o[5] = a2[2];
+    o[6] = pos[3 * i]; o[7] = pos[3 * i + 1]; o[8] = pos[3 * i + 2];
+  }
+  if (i < n_actors) {
+    float b0 = fadd(fmul(sizes[3 * i], 0.5f), p0), b1 = fadd(fmul(sizes[3 * i + 1], 0.5f), p1),
+          b2 = fadd(fmul(sizes[3 * i + 2], 0.5f), p2);
+    bounds[3 * i] = b0; bounds[3 * i + 1] = b1; bounds[3 * i + 2] = b2;
+    radii[i] = fsqrt(fadd(fadd(fmul(b0, b0), fmul(b1, b1)), fmul(b2, b2)));
+  }
+}
+
+// Repack nn.Linear [out,in] weights into the transposed, padded [in][outp] layout the kernels read.
+__global__ void pack_linear_kernel(const float* __restrict__ w, const float* __restrict__ b, int out_f, int in_f,
+                                   int outp, float* __restrict__ dst_w, float* __restrict__ dst_b) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < in_f * outp) {
+    int k = i / outp, o = i % outp;
+    dst_w[i] = o < out_f ? w[o * in_f + k] : 0.f;
+  }
+  if (i < outp) dst_b[i] = (i < out_f && b) ? b[i] : 0.f;
+}
+
+// Cameras._generate_rays_from_coords, pinhole + rolling shutter (cameras/cameras.py:633-667,793-798,898-969)
+struct PinholeArgs {
+  float c2w[12];
+  float fx, fy, cx, cy;
+  int height, width, row0, row_step, n_rows, col0, col_step, n_cols;
+  float time, vel[3], rs_time, ttc;
+  int has_vel;
+};
+__device__ __forceinline__ void cam_dir(const PinholeArgs& a, float u, float v, float out[3], float* norm) {
+  // direction (u, -v, -1) rotated by c2w: sum over columns of dir_j * R[i][j]  (cameras.py:902-904)
+  float dx = u, dy = -v, dz = -1.0f;
+  float r[3];
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+    r[i] = fadd(fadd(fmul(dx, a.c2w[4 * i + 0]), fmul(dy, a.c2w[4 * i + 1])), fmul(dz, a.c2w[4 * i + 2]));
+  float n = fsqrt(fadd(fadd(fmul(r[0], r[0]), fmul(r[1], r[1])), fmul(r[2], r[2])));
+  n = fmaxf(n, 8.8817841970012523e-16f);  // camera_utils.py:30 (_EPS = 4 * float64 eps, cast to fp32)
+  out[0] = fdiv(r[0], n); out[1] = fdiv(r[1], n); out[2] = fdiv(r[2], n);
+  *norm = n;
+}
+__global__ void raygen_pinhole_kernel(PinholeArgs a, float* __restrict__ origins, float* __restrict__ dirs,
+                                      float* __restrict__ area, float* __restrict__ times) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (int64_t)a.n_rows * a.n_cols) return;
+  int r = (int)(i / a.n_cols), c = (int)(i % a.n_cols);
+  float y = (float)(a.row0 + r * a.row_step) + 0.5f, x = (float)(a.col0 + c * a.col_step) + 0.5f;
+  float u0 = fdiv(fsub(x, a.cx), a.fx), v0 = fdiv(fsub(y, a.cy), a.fy);
+  float u1 = fdiv(fadd(fsub(x, a.cx), 1.0f), a.fx), v1 = fdiv(fadd(fsub(y, a.cy), 1.0f), a.fy);
+  float d0[3], dxo[3], dyo[3], n0, n1;
+  cam_dir(a, u0, v0, d0, &n0);
+  cam_dir(a, u1, v0, dxo, &n1);
+  cam_dir(a, u0, v1, dyo, &n1);
+  float ex[3], ey[3];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    ex[k] = fsub(d0[k], dxo[k]);
+    ey[k] = fsub(d0[k], dyo[k]);
+  }
+  float dx = fsqrt(fadd(fadd(fmul(ex[0], ex[0]), fmul(ex[1], ex[1])), fmul(ex[2], ex[2])));
+  float dy = fsqrt(fadd(fadd(fmul(ey[0], ey[0]), fmul(ey[1], ey[1])), fmul(ey[2], ey[2])));
+  float o[3] = {a.c2w[3], a.c2w[7], a.c2w[11]};
+  float t = a.time;
+  if (a.has_vel) {
+    float toff = fadd(fmul(fsub(fdiv(y, (float)a.height), 0.5f), a.rs_time), a.ttc);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) o[k] = fadd(o[k], fmul(a.vel[k], toff));
+    t = fadd(t, toff);
+  }
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    origins[3 * i + k] = o[k];
+    dirs[3 * i + k] = d0[k];
+  }
+  area[i] = fmul(dx, dy);
+  times[i] = t;
+}
+
+// Lidars._generate_rays_from_points (cameras/lidars.py:399-460)
+struct LidarArgs {
+  float l2w[12];
+  float scan_time, vel[3], h_div, v_div;
+  int has_vel, stride;
+};
+__global__ void raygen_lidar_kernel(LidarArgs a, const float* __restrict__ pts, int64_t n, float* __restrict__ origins,
+                                    float* __restrict__ dirs, float* __restrict__ area, float* __restrict__ times,
+                                    float* __restrict__ distance) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float* p = pts + i * a.stride;
+  float px = p[0], py = p[1], pz = p[2], dt = a.stride >= 5 ? p[4] : 0.f;
+  float pw[3], o[3];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    pw[k] = fadd(fadd(fadd(fmul(a.l2w[4 * k], px), fmul(a.l2w[4 * k + 1], py)), fmul(a.l2w[4 * k + 2], pz)), a.l2w[4 * k + 3]);
+    o[k] = a.l2w[4 * k + 3];
+    if (a.has_vel) o[k] = fadd(o[k], fmul(dt, a.vel[k]));
+  }
+  float d[3] = {fsub(pw[0], o[0]), fsub(pw[1], o[1]), fsub(pw[2], o[2])};
+  float nrm = fsqrt(fadd(fadd(fmul(d[0], d[0]), fmul(d[1], d[1])), fmul(d[2], d[2])));
+  nrm = fmaxf(nrm, 8.8817841970012523e-16f);
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    origins[3 * i + k] = o[k];
+    dirs[3 * i + k] = fdiv(d[k], nrm);
+  }
+  area[i] = fmul(a.h_div, a.v_div);
+  times[i] = fadd(a.scan_time, dt);
+  if (distance) distance[i] = nrm;
+}
+
+// ===================================================================================================== C ABI
+extern "C" {
+
+const char* b200nerf_last_error(void) { return g_err.c_str(); }
+int b200nerf_version(void) { return B200NERF_VERSION; }
+
+int b200nerf_create(int device_ordinal, b200nerf_ctx** out) {
+  REQUIRE(out != nullptr, "out is NULL");
+  int n = 0;
+  CUDA_TRY(cudaGetDeviceCount(&n));
+  REQUIRE(device_ordinal >= 0 && device_ordinal < n, "device ordinal out of range");
+  DeviceGuard g(device_ordinal);
+  cudaDeviceProp prop;
+  CUDA_TRY(cudaGetDeviceProperties(&prop, device_ordinal));
+  if (prop.major < 10)
+    return fail(B200NERF_ERR_UNSUPPORTED, "libb200nerf is built for sm_100a only (found sm_" +
+                                              std::to_string(prop.major) + std::to_string(prop.minor) + ")");
+  b200nerf_ctx* c = new (std::nothrow) b200nerf_ctx();
+  REQUIRE(c != nullptr, "out of host memory");
+  c->device = device_ordinal;
+  c->sm_count = prop.multiProcessorCount;
+  CUDA_TRY(cudaFuncSetAttribute(nff_render_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)((kMainMlpFloats * 4 + 15) / 16 * 16 + 4 * sizeof(WarpShared))));
+  *out = c;
+  return 0;
+}
+
+int b200nerf_destroy(b200nerf_ctx* c) {
+  if (!c) return 0;
+  DeviceGuard g(c->device);
+  for (int i = 0; i < 3; ++i) {
+    cudaFree((void*)c->d_actor_tables[i]);
+    cudaFree(c->d_decoder[i]);
+  }
+  cudaFree(c->d_main_mlp);
+  cudaFree(c->d_lidar_mlp);
+  cudaFree(c->d_act_times);
+  cudaFree(c->d_act_kf);
+  cudaFree(c->d_act_bounds);
+  cudaFree(c->d_act_radii);
+  cudaFree(c->d_act_present);
+  cudaFree(c->d_u1);
+  cudaFree(c->d_u2);
+  delete c;
+  return 0;
+}
+
+int b200nerf_set_field_grids(b200nerf_ctx* c, int field, const b200nerf_grid_desc* sd, const float* stable,
+                             const b200nerf_grid_desc* ad, const float* const* atabs_host, int n_actors,
+                             float static_scale, float actor_scale) {
+  REQUIRE(c, "ctx is NULL");
+  REQUIRE(field >= 0 && field < 3, "field selector out of range");
+  REQUIRE(stable != nullptr, "static table is NULL");
+  DeviceGuard g(c->device);
+  FieldGrids fg{};
+  if (int e = make_grid(sd, stable, &fg.stat)) return e;
+  const int wantL = field == B200NERF_FIELD_MAIN ? 8 : 6, wantF = field == B200NERF_FIELD_MAIN ? 4 : 1;
+  if (fg.stat.L != wantL || fg.stat.F != wantF)
+    return fail(B200NERF_ERR_UNSUPPORTED,
+                "fused kernel is specialised for NeuRAD's grid shapes (main: 8 levels x 4 features, proposal: 6 x 1)");
+  if (n_actors > 0) {
+    REQUIRE(ad && atabs_host, "actor grid descriptor / tables missing");
+    if (int e = make_grid(ad, nullptr, &fg.act)) return e;
+    if (fg.act.L != 4 || fg.act.F != wantF)
+      return fail(B200NERF_ERR_UNSUPPORTED, "actor grids must have 4 levels and the static grid's feature width");
+    cudaFree((void*)c->d_actor_tables[field]);
+    c->d_actor_tables[field] = nullptr;
+    CUDA_TRY(cudaMalloc((void**)&c->d_actor_tables[field], sizeof(float*) * n_actors));
+    CUDA_TRY(cudaMemcpy((void*)c->d_actor_tables[field], atabs_host, sizeof(float*) * n_actors, cudaMemcpyHostToDevice));
+    fg.actor_tables = c->d_actor_tables[field];
+  }
+  fg.static_scale = static_scale;
+  fg.actor_scale = actor_scale;
+  fg.decoder = c->d_decoder[field];
+  c->fields[field] = fg;
+  c->have_field[field] = true;
+  return 0;
+}
+
+int b200nerf_set_proposal_decoder(b200nerf_ctx* c, int field, const float* weight, int in_dim) {
+  REQUIRE(c, "ctx is NULL");
+  REQUIRE(field == B200NERF_FIELD_PROP0 || field == B200NERF_FIELD_PROP1, "decoder belongs to a proposal field");
+  REQUIRE(weight && in_dim == 6, "density_decoder must be Linear(6, 1)");
+  DeviceGuard g(c->device);
+  if (!c->d_decoder[field]) CUDA_TRY(cudaMalloc((void**)&c->d_decoder[field], sizeof(float) * 8));
+  CUDA_TRY(cudaMemcpy(c->d_decoder[field], weight, sizeof(float) * in_dim, cudaMemcpyDeviceToDevice));
+  c->fields[field].decoder = c->d_decoder[field];
+  return 0;
+}
+
+static int pack(const float* w, const float* b, int out_f, int in_f, int outp, float* dw, float* db) {
+  int n = in_f * outp > outp ? in_f * outp : outp;
+  pack_linear_kernel<<<(n + 255) / 256, 256>>>(w, b, out_f, in_f, outp, dw, db);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(B200NERF_ERR_CUDA, std::string("pack_linear: ") + cudaGetErrorString(e));
+  return 0;
+}
+
+int b200nerf_set_main_mlps(b200nerf_ctx* c, const float* gw0, const float* gb0, const float* gw1, const float* gb1,
+                           const float* fw0, const float* fb0, const float* fw1, const float* fb1, const float* fw2,
+                           const float* fb2, float beta) {
+  REQUIRE(c, "ctx is NULL");
+  REQUIRE(gw0 && gb0 && gw1 && gb1 && fw0 && fb0 && fw1 && fb1 && fw2 && fb2, "NULL MLP tensor");
+  DeviceGuard g(c->device);
+  if (!c->d_main_mlp) CUDA_TRY(cudaMalloc((void**)&c->d_main_mlp, sizeof(float) * kMainMlpFloats));
+  float* m = c->d_main_mlp;
+  if (int e = pack(gw0, gb0, kHidden, kGeoIn, kHidden, m + kOffGeoW0, m + kOffGeoB0)) return e;
+  if (int e = pack(gw1, gb1, kNff + 1, kHidden, kGeoOutP, m + kOffGeoW1, m + kOffGeoB1)) return e;
+  if (int e = pack(fw0, fb0, kHidden, kNff + kSh, kHidden, m + kOffFeatW0, m + kOffFeatB0)) return e;
+  if (int e = pack(fw1, fb1, kHidden, kHidden, kHidden, m + kOffFeatW1, m + kOffFeatB1)) return e;
+  if (int e = pack(fw2, fb2, kNff, kHidden, kNff, m + kOffFeatW2, m + kOffFeatB2)) return e;
+  CUDA_TRY(cudaDeviceSynchronize());
+  c->beta = beta;
+  c->have_main_mlp = true;
+  return 0;
+}
+
+int b200nerf_set_lidar_decoder(b200nerf_ctx* c, const float* w0, const float* b0, const float* w1, const float* b1,
+                               const float* w2, const float* b2) {
+  REQUIRE(c, "ctx is NULL");
+  REQUIRE(w0 && b0 && w1 && b1 && w2 && b2, "NULL MLP tensor");
+  DeviceGuard g(c->device);
+  if (!c->d_lidar_mlp) CUDA_TRY(cudaMalloc((void**)&c->d_lidar_mlp, sizeof(float) * kLidarMlpFloats));
+  float* m = c->d_lidar_mlp;
+  if (int e = pack(w0, b0, kHidden, kNff + kApp, kHidden, m + kOffLidW0, m + kOffLidB0)) return e;
+  if (int e = pack(w1, b1, kHidden, kHidden, kHidden, m + kOffLidW1, m + kOffLidB1)) return e;
+  if (int e = pack(w2, b2, 2, kHidden, kLidOutP, m + kOffLidW2, m + kOffLidB2)) return e;
+  CUDA_TRY(cudaDeviceSynchronize());
+  c->have_lidar = true;
+  return 0;
+}
+
+int b200nerf_set_appearance(b200nerf_ctx* c, const float* emb, int num_embeds, int dim, int eps, float duration) {
+  REQUIRE(c, "ctx is NULL");
+  REQUIRE(dim >= 0 && dim <= kApp, "appearance_dim must be <= 16");
+  REQUIRE(dim == 0 || (emb && num_embeds > 0 && eps > 0 && duration > 0.f), "bad appearance embedding");
+  c->app.emb = emb;
+  c->app.num_embeds = num_embeds;
+  c->app.dim = dim;
+  c->app.eps = eps;
+  c->app.duration = duration;
+  c->have_app = true;
+  return 0;
+}
+
+int b200nerf_set_actors(b200nerf_ctx* c, int n_actors, int n_times, const float* timestamps, const float* rot6,
+                        const float* pos, const uint8_t* present, const float* sizes, const float* padding_host) {
+  REQUIRE(c, "ctx is NULL");
+  DeviceGuard g(c->device);
+  cudaFree(c->d_act_times); cudaFree(c->d_act_kf); cudaFree(c->d_act_bounds); cudaFree(c->d_act_radii);
+  cudaFree(c->d_act_present);
+  c->d_act_times = c->d_act_kf = c->d_act_bounds = c->d_act_radii = nullptr;
+  c->d_act_present = nullptr;
+  c->actors = Actors{};
+  if (n_actors <= 0) return 0;
+  REQUIRE(n_times >= 1 && timestamps && rot6 && pos && present && sizes && padding_host, "NULL actor tensor");
+  size_t ta = (size_t)n_times * n_actors;
+  CUDA_TRY(cudaMalloc((void**)&c->d_act_times, sizeof(float) * n_times));
+  CUDA_TRY(cudaMalloc((void**)&c->d_act_kf, sizeof(float) * 9 * ta));
+  CUDA_TRY(cudaMalloc((void**)&c->d_act_bounds, sizeof(float) * 3 * n_actors));
+  CUDA_TRY(cudaMalloc((void**)&c->d_act_radii, sizeof(float) * n_actors));
+  CUDA_TRY(cudaMalloc((void**)&c->d_act_present, ta));
+  CUDA_TRY(cudaMemcpy(c->d_act_times, timestamps, sizeof(float) * n_times, cudaMemcpyDeviceToDevice));
+  CUDA_TRY(cudaMemcpy(c->d_act_present, present, ta, cudaMemcpyDeviceToDevice));
+  int n = (int)(ta > (size_t)n_actors ? ta : n_actors);
+  actors_prep_kernel<<<(n + 127) / 128, 128>>>(n_times, n_actors, rot6, pos, sizes, padding_host[0], padding_host[1],
+                                               padding_host[2], c->d_act_kf, c->d_act_bounds, c->d_act_radii);
+  CUDA_TRY(cudaGetLastError());
+  CUDA_TRY(cudaDeviceSynchronize());
+  c->actors.n_actors = n_actors;
+  c->actors.n_times = n_times;
+  c->actors.times = c->d_act_times;
+  c->actors.keyframes = c->d_act_kf;
+  c->actors.present = c->d_act_present;
+  c->actors.bounds = c->d_act_bounds;
+  c->actors.radii = c->d_act_radii;
+  return 0;
+}
+
+int b200nerf_set_sampling(b200nerf_ctx* c, int n_prop0, int n_prop1, int n_nerf, float lam, float scaling, float sky,
+                          float hist_pad, const float* u1_host, const float* u2_host, const int* field_of_round,
+                          float camera_area_scale) {
+  REQUIRE(c, "ctx is NULL");
+  if (n_prop0 != kS0 || n_prop1 != kS1 || n_nerf != kS2)
+    return fail(B200NERF_ERR_UNSUPPORTED, "fused kernel is specialised for NeuRAD's 128/64/32 samples per ray");
+  REQUIRE(u1_host && u2_host && field_of_round, "NULL sampling table");
+  REQUIRE(lam != 0.f && lam != 1.f, "power_lambda 0 / 1 (log / identity spacing) is not supported");
+  for (int i = 0; i < 2; ++i)
+    REQUIRE(field_of_round[i] == B200NERF_FIELD_PROP0 || field_of_round[i] == B200NERF_FIELD_PROP1,
+            "density_field_of_round entries must name a proposal field");
+  DeviceGuard g(c->device);
+  if (!c->d_u1) CUDA_TRY(cudaMalloc((void**)&c->d_u1, sizeof(float) * (kS1 + 1)));
+  if (!c->d_u2) CUDA_TRY(cudaMalloc((void**)&c->d_u2, sizeof(float) * (kS2 + 1)));
+  CUDA_TRY(cudaMemcpy(c->d_u1, u1_host, sizeof(float) * (kS1 + 1), cudaMemcpyHostToDevice));
+  CUDA_TRY(cudaMemcpy(c->d_u2, u2_host, sizeof(float) * (kS2 + 1), cudaMemcpyHostToDevice));
+  Sampling s{};
+  s.lam = lam;
+  s.scaling = scaling;
+  s.sky_distance = sky;
+  s.hist_pad = hist_pad;
+  s.cam_area_scale = camera_area_scale;
+  double lam1 = lam - 1.0 < 0 ? -(lam - 1.0) : (lam - 1.0);
+  s.lam_1 = (float)lam1;
+  s.ratio = (float)(lam1 / (double)lam);
+  s.u1 = c->d_u1;
+  s.u2 = c->d_u2;
+  s.field_of_round[0] = field_of_round[0];
+  s.field_of_round[1] = field_of_round[1];
+  c->samp = s;
+  c->n_prop0 = n_prop0; c->n_prop1 = n_prop1; c->n_nerf = n_nerf;
+  c->have_samp = true;
+  return 0;
+}
+
+int b200nerf_nff_render_fwd(b200nerf_ctx* c, const b200nerf_rays* rays, int64_t n_rays, const b200nerf_outputs* out,
+                            const b200nerf_trace* trace, void* stream) {
+  REQUIRE(c && rays && out, "NULL argument");
+  REQUIRE(n_rays >= 0, "negative ray count");
+  if (!(c->have_field[0] && c->have_main_mlp && c->have_samp && c->have_app))
+    return fail(B200NERF_ERR_STATE, "set_field_grids(MAIN), set_main_mlps, set_sampling and set_appearance are required");
+  for (int i = 0; i < 2; ++i) {
+    int f = c->samp.field_of_round[i];
+    if (!c->have_field[f] || !c->fields[f].decoder)
+      return fail(B200NERF_ERR_STATE, "proposal field used by a sampling round has no grids / decoder set");
+    if (c->actors.n_actors > 0 && !c->fields[f].actor_tables)
+      return fail(B200NERF_ERR_STATE, "actors are set but a proposal field has no actor grids");
+  }
+  if (c->actors.n_actors > 0 && !c->fields[0].actor_tables)
+    return fail(B200NERF_ERR_STATE, "actors are set but the main field has no actor grids");
+  if (n_rays == 0) return 0;
+  REQUIRE(rays->origins && rays->directions && rays->pixel_area && rays->times, "NULL ray tensor");
+  REQUIRE(out->features && out->depth && out->accumulation && out->prop_depth_0 && out->prop_depth_1, "NULL output tensor");
+  if ((out->intensity || out->ray_drop_logit) && !c->have_lidar)
+    return fail(B200NERF_ERR_STATE, "intensity requested but set_lidar_decoder was not called");
+  DeviceGuard g(c->device);
+  RenderParams P{};
+  for (int i = 0; i < 3; ++i) P.fields[i] = c->fields[i];
+  P.main_mlp = c->d_main_mlp;
+  P.lidar_mlp = c->d_lidar_mlp;
+  P.beta = c->beta;
+  P.nff_dim = kNff;
+  P.actors = c->actors;
+  P.samp = c->samp;
+  P.app = c->app;
+  P.rays = *rays;
+  P.out = *out;
+  if (trace) P.trace = *trace;
+  P.n_rays = n_rays;
+  constexpr int WARPS = 4;
+  const size_t smem = (kMainMlpFloats * 4 + 15) / 16 * 16 + WARPS * sizeof(WarpShared);
+  int64_t blocks_needed = (n_rays + WARPS - 1) / WARPS;
+  int64_t max_blocks = (int64_t)c->sm_count * 4;
+  int blocks = (int)(blocks_needed < max_blocks ? blocks_needed : max_blocks);
+  cudaStream_t st = (cudaStream_t)stream;
+  nff_render_kernel<WARPS><<<blocks, WARPS * 32, smem, st>>>(P);
+  CUDA_TRY(cudaGetLastError());
+  if (out->intensity || out->ray_drop_logit) {
+    int fdim = kNff + c->app.dim;
+    lidar_decode_kernel<<<(unsigned)((n_rays + 127) / 128), 128, 0, st>>>(c->d_lidar_mlp, out->features, fdim, n_rays,
+                                                                          out->intensity, out->ray_drop_logit);
+    CUDA_TRY(cudaGetLastError());
+  }
+  return 0;
+}
+
+int b200nerf_hashgrid_fwd(b200nerf_ctx* c, const b200nerf_grid_desc* desc, const float* table, const float* x,
+                          float* out, int32_t* indices, int64_t n_points, void* stream) {
+  REQUIRE(c && desc && table && x && out, "NULL argument");
+  REQUIRE(desc->features_per_level >= 1 && desc->features_per_level <= 8, "features_per_level must be in [1,8]");
+  if (n_points == 0) return 0;
+  DeviceGuard g(c->device);
+  Grid gr{};
+  if (int e = make_grid(desc, table, &gr)) return e;
+  int64_t n = n_points * gr.L;
+  hashgrid_fwd_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(gr, x, out, indices, n_points);
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+int b200nerf_sh4_fwd(b200nerf_ctx* c, const float* dirs, float* out, int64_t n, void* stream) {
+  REQUIRE(c && dirs && out, "NULL argument");
+  if (n == 0) return 0;
+  DeviceGuard g(c->device);
+  sh4_fwd_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(dirs, out, n);
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+int b200nerf_pdf_resample(b200nerf_ctx* c, const float* weights, const float* bins, const float* u, int n_rays,
+                          int s_old, int s_new, float hist_pad, float* new_bins, float* cdf, int32_t* inds,
+                          void* stream) {
+  REQUIRE(c && weights && bins && u && new_bins, "NULL argument");
+  REQUIRE(s_old >= 1 && s_old <= 2048 && s_new >= 1, "sample counts out of range");
+  if (n_rays == 0) return 0;
+  DeviceGuard g(c->device);
+  const int warps = 4;
+  size_t smem = sizeof(float) * warps * (s_old + 1);
+  pdf_resample_kernel<<<(n_rays + warps - 1) / warps, warps * 32, smem, (cudaStream_t)stream>>>(
+      weights, bins, u, n_rays, s_old, s_new, hist_pad, new_bins, cdf, inds);
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+int b200nerf_density_to_weights(b200nerf_ctx* c, const float* deltas, const float* densities, int n_rays, int s,
+                                float* weights, void* stream) {
+  REQUIRE(c && deltas && densities && weights, "NULL argument");
+  if (n_rays == 0) return 0;
+  DeviceGuard g(c->device);
+  weights_kernel<false><<<(n_rays + 3) / 4, 128, 0, (cudaStream_t)stream>>>(deltas, densities, n_rays, s, weights);
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+int b200nerf_alpha_to_weights(b200nerf_ctx* c, const float* alphas, int n_rays, int s, float* weights, void* stream) {
+  REQUIRE(c && alphas && weights, "NULL argument");
+  if (n_rays == 0) return 0;
+  DeviceGuard g(c->device);
+  weights_kernel<true><<<(n_rays + 3) / 4, 128, 0, (cudaStream_t)stream>>>(alphas, nullptr, n_rays, s, weights);
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+int b200nerf_raygen_pinhole(b200nerf_ctx* c, const float* c2w_host, float fx, float fy, float cx, float cy, int height,
+                            int width, int row0, int row_step, int n_rows, int col0, int col_step, int n_cols,
+                            float time, const float* velocity_host, float rs_time, float ttc, float* origins,
+                            float* directions, float* pixel_area, float* times, void* stream) {
+  REQUIRE(c && c2w_host && origins && directions && pixel_area && times, "NULL argument");
+  REQUIRE(n_rows >= 0 && n_cols >= 0 && row_step >= 1 && col_step >= 1, "bad pixel grid");
+  if (n_rows == 0 || n_cols == 0) return 0;
+  DeviceGuard g(c->device);
+  PinholeArgs a{};
+  memcpy(a.c2w, c2w_host, sizeof(float) * 12);
+  a.fx = fx; a.fy = fy; a.cx = cx; a.cy = cy;
+  a.height = height; a.width = width;
+  a.row0 = row0; a.row_step = row_step; a.n_rows = n_rows;
+  a.col0 = col0; a.col_step = col_step; a.n_cols = n_cols;
+  a.time = time; a.rs_time = rs_time; a.ttc = ttc;
+  a.has_vel = velocity_host != nullptr;
+  if (velocity_host) memcpy(a.vel, velocity_host, sizeof(float) * 3);
+  int64_t n = (int64_t)n_rows * n_cols;
+  raygen_pinhole_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(a, origins, directions,
+                                                                                        pixel_area, times);
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+int b200nerf_raygen_lidar_points(b200nerf_ctx* c, const float* l2w_host, const float* points, int point_stride,
+                                 int64_t n_points, float scan_time, const float* velocity_host, float h_div,
+                                 float v_div, float* origins, float* directions, float* pixel_area, float* times,
+                                 float* distance, void* stream) {
+  REQUIRE(c && l2w_host && points && origins && directions && pixel_area && times, "NULL argument");
+  REQUIRE(point_stride >= 3, "points need at least x,y,z");
+  if (n_points == 0) return 0;
+  DeviceGuard g(c->device);
+  LidarArgs a{};
+  memcpy(a.l2w, l2w_host, sizeof(float) * 12);
+  a.scan_time = scan_time; a.h_div = h_div; a.v_div = v_div; a.stride = point_stride;
+  a.has_vel = velocity_host != nullptr;
+  if (velocity_host) memcpy(a.vel, velocity_host, sizeof(float) * 3);
+  raygen_lidar_kernel<<<(unsigned)((n_points + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      a, points, n_points, origins, directions, pixel_area, times, distance);
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+}  // extern "C"

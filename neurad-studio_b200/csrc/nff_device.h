@@ -1,0 +1,630 @@
+// nff_device.h -- device-side implementation of NeuRAD's neural-feature-field forward path.
+//
+// One warp renders one ray end to end: power-spaced initial bins -> proposal round 0 (128 samples) -> PDF
+// resample -> proposal round 1 (64) -> PDF resample -> main field (32 samples, one per lane: hash grid, geo MLP,
+// SH, feature MLP, sigmoid-SDF alpha) -> transmittance scan -> composite.  Bins / cdf live in shared memory,
+// everything else in registers; nothing but the per-ray outputs goes back to HBM.
+//
+// Each function names the reference code it reproduces (paths relative to nerfstudio/).  Where the reference
+// evaluates separate elementwise torch kernels, the same single-rounding fp32 ops are used via simt::fmul/fadd/..
+// (no FMA contraction), so grid cells, hash rows and bin edges agree with the reference bit for bit given
+// identical inputs; only transcendental functions and dot-product orders differ (<= a few ulp).
+#pragma once
+#include "nff_params.h"
+#include "simt.h"
+
+namespace nff {
+using namespace simt;
+
+// ------------------------------------------------------------------------------------------------ helpers
+NFF_D float nan_to_num(float v) {  // torch.nan_to_num defaults: nan->0, +-inf -> +-FLT_MAX
+  if (v != v) return 0.0f;
+  if (v > 3.4028234663852886e38f) return 3.4028234663852886e38f;
+  if (v < -3.4028234663852886e38f) return -3.4028234663852886e38f;
+  return v;
+}
+NFF_D float warp_sum(float v) {
+#pragma unroll
+  for (int m = 16; m >= 1; m >>= 1) v += shfl_xor(v, m);
+  return v;
+}
+NFF_D float warp_scan_add(float v) {  // inclusive
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    float n = shfl_up(v, d);
+    if (lane() >= d) v += n;
+  }
+  return v;
+}
+NFF_D float warp_scan_mul(float v) {  // inclusive
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    float n = shfl_up(v, d);
+    if (lane() >= d) v *= n;
+  }
+  return v;
+}
+
+// ------------------------------------------------------------------------------ power-law sample spacing
+// utils/math.py:541-579 (power_fn / inv_power_fn, general branch) as used by PowerSampler
+// (model_components/ray_samplers.py:838-852).  x**lam with lam == -1 is torch's reciprocal fast path.
+NFF_D float pow_lam(float t, float e) { return e == -1.0f ? frcp(t) : powf(t, e); }
+NFF_D float spacing_fn(float x, const Sampling& s) {
+  float t = fadd(fdiv(fmul(x, s.scaling), s.lam_1), 1.0f);
+  return fmul(s.ratio, fsub(pow_lam(t, s.lam), 1.0f));
+}
+NFF_D float spacing_fn_inv(float y, const Sampling& s) {
+  float t = fadd(fdiv(fmul(y, s.lam), s.lam_1), 1.0f);
+  t = fmaxf(t, 1e-10f);
+  float r = fmul(fsub(pow_lam(t, s.lam == -1.0f ? -1.0f : 1.0f / s.lam), 1.0f), s.lam_1);
+  return fdiv(r, s.scaling);
+}
+// spacing_to_euclidean_fn (ray_samplers.py:119-120)
+NFF_D float to_euclid(float u, float s_near, float s_far, const Sampling& s) {
+  return spacing_fn_inv(fadd(fmul(u, s_far), fmul(fsub(1.0f, u), s_near)), s);
+}
+// torch.linspace(0, 1, n+1)[i] (symmetric evaluation of aten's linspace kernel)
+NFF_D float linspace01(int i, int n) {
+  float step = fdiv(1.0f, (float)n);
+  return i < (n + 1) / 2 ? fmul(step, (float)i) : fsub(1.0f, fmul(step, (float)(n - i)));
+}
+
+// ------------------------------------------------------------------------------------ gaussian + contraction
+struct Gauss {
+  float x, y, z, std;
+};
+// Frustums.get_fast_isotropic_gaussian, num_multisamples = 1 (cameras/rays.py:109-124)
+NFF_D Gauss sample_gaussian(const float o[3], const float d[3], float area, float start, float end) {
+  float md = fdiv(fsub(end, start), 2.0f);
+  float t = fadd(start, md);
+  Gauss g;
+  g.x = fadd(o[0], fmul(d[0], t));
+  g.y = fadd(o[1], fmul(d[1], t));
+  g.z = fadd(o[2], fmul(d[2], t));
+  float cs = fmul(area, fmul(t, t));
+  g.std = powf(fmul(cs, md), 0.33333334f);
+  return g;
+}
+// ScaledSceneContraction(order=inf) on a GaussiansStd (field_components/spatial_distortions.py:103-114,132-136)
+NFF_D Gauss contract(Gauss g, float scale) {
+  float x = fdiv(g.x, scale), y = fdiv(g.y, scale), z = fdiv(g.z, scale), sd = fdiv(g.std, scale);
+  float mag = fmaxf(fmaxf(fabsf(x), fabsf(y)), fabsf(z));
+  if (!(mag < 1.0f)) {
+    float cm = fmaxf(mag, 1.0f);
+    float a = fsub(2.0f, frcp(cm));
+    x = fmul(a, fdiv(x, cm));
+    y = fmul(a, fdiv(y, cm));
+    z = fmul(a, fdiv(z, cm));
+    float q = fdiv(powf(fsub(fmul(2.0f, cm), 1.0f), 0.33333334f), cm);
+    sd = fmul(sd, fmul(q, q));
+  }
+  Gauss r;
+  r.x = fmul(fadd(x, 2.0f), 0.25f);
+  r.y = fmul(fadd(y, 2.0f), 0.25f);
+  r.z = fmul(fadd(z, 2.0f), 0.25f);
+  r.std = fmul(sd, 0.25f);
+  return r;
+}
+
+// -------------------------------------------------------------------------------------------- hash grid
+// HashEncoding.hash_fn + pytorch_fwd (field_components/encodings.py:406-466): per level p = x*res;
+// c = ceil(p), f = floor(p); rows = ((i*1) ^ (j*2654435761) ^ (k*805459861)) mod T (+ level*T); trilinear blend
+// with weight (p - f) on the ceil corner.  int64 products mod 2^k == uint32 wrap-around products mod 2^k.
+struct Cell {
+  uint32_t hx[2], hy[2], hz[2];  // [0] = floor, [1] = ceil, already multiplied by the primes
+  float ox, oy, oz;
+};
+NFF_D Cell grid_cell(float x, float y, float z, float res) {
+  float px = fmul(x, res), py = fmul(y, res), pz = fmul(z, res);
+  float fx = floorf(px), fy = floorf(py), fz = floorf(pz);
+  Cell c;
+  c.hx[0] = (uint32_t)(int32_t)fx;
+  c.hx[1] = (uint32_t)(int32_t)ceilf(px);
+  c.hy[0] = (uint32_t)(int32_t)fy * 2654435761u;
+  c.hy[1] = (uint32_t)(int32_t)ceilf(py) * 2654435761u;
+  c.hz[0] = (uint32_t)(int32_t)fz * 805459861u;
+  c.hz[1] = (uint32_t)(int32_t)ceilf(pz) * 805459861u;
+  c.ox = fsub(px, fx);
+  c.oy = fsub(py, fy);
+  c.oz = fsub(pz, fz);
+  return c;
+}
+// corner order of the reference: hashed_0..7 = ccc, cfc, ffc, fcc, ccf, cff, fff, fcf  (x,y,z; c=ceil f=floor)
+NFF_D void cell_rows(const Cell& c, uint32_t mask, uint32_t r[8]) {
+  r[0] = (c.hx[1] ^ c.hy[1] ^ c.hz[1]) & mask;
+  r[1] = (c.hx[1] ^ c.hy[0] ^ c.hz[1]) & mask;
+  r[2] = (c.hx[0] ^ c.hy[0] ^ c.hz[1]) & mask;
+  r[3] = (c.hx[0] ^ c.hy[1] ^ c.hz[1]) & mask;
+  r[4] = (c.hx[1] ^ c.hy[1] ^ c.hz[0]) & mask;
+  r[5] = (c.hx[1] ^ c.hy[0] ^ c.hz[0]) & mask;
+  r[6] = (c.hx[0] ^ c.hy[0] ^ c.hz[0]) & mask;
+  r[7] = (c.hx[0] ^ c.hy[1] ^ c.hz[0]) & mask;
+}
+NFF_D float blend(float a, float wa, float b, float wb) { return fadd(fmul(a, wa), fmul(b, wb)); }
+NFF_D float trilerp(const float f[8], const Cell& c) {
+  float ix = fsub(1.0f, c.ox), iy = fsub(1.0f, c.oy), iz = fsub(1.0f, c.oz);
+  float f03 = blend(f[0], c.ox, f[3], ix);
+  float f12 = blend(f[1], c.ox, f[2], ix);
+  float f56 = blend(f[5], c.ox, f[6], ix);
+  float f47 = blend(f[4], c.ox, f[7], ix);
+  float f0312 = blend(f03, c.oy, f12, iy);
+  float f4756 = blend(f47, c.oy, f56, iy);
+  return blend(f0312, c.oz, f4756, iz);
+}
+
+// One grid, all levels, F = 1: out[l] = interp * 1/max(1, 2*res_l*std)  (neurad_encoding.py:297-304)
+template <int L>
+NFF_D void encode_f1(const float* NFF_RESTRICT table, uint32_t mask, uint32_t T, const float* res, Gauss g,
+                     float* out) {
+#pragma unroll
+  for (int l = 0; l < L; ++l) {
+    Cell c = grid_cell(g.x, g.y, g.z, res[l]);
+    uint32_t r[8];
+    cell_rows(c, mask, r);
+    const float* base = table + (size_t)l * T;
+    float f[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) f[k] = ldg(base + r[k]);
+    float w = frcp(fmaxf(fmul(fmul(res[l], 2.0f), g.std), 1.0f));
+    out[l] = fmul(trilerp(f, c), w);
+  }
+}
+// F = 4 (16-byte rows, one LDG.128 per corner)
+template <int L>
+NFF_D void encode_f4(const float* NFF_RESTRICT table, uint32_t mask, uint32_t T, const float* res, Gauss g,
+                     float* out) {
+#pragma unroll
+  for (int l = 0; l < L; ++l) {
+    Cell c = grid_cell(g.x, g.y, g.z, res[l]);
+    uint32_t r[8];
+    cell_rows(c, mask, r);
+    const float4* base = reinterpret_cast<const float4*>(table) + (size_t)l * T;
+    float4 v[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v[k] = ldg(base + r[k]);
+    float w = frcp(fmaxf(fmul(fmul(res[l], 2.0f), g.std), 1.0f));
+    float f[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) f[k] = v[k].x;
+    out[4 * l + 0] = fmul(trilerp(f, c), w);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) f[k] = v[k].y;
+    out[4 * l + 1] = fmul(trilerp(f, c), w);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) f[k] = v[k].z;
+    out[4 * l + 2] = fmul(trilerp(f, c), w);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) f[k] = v[k].w;
+    out[4 * l + 3] = fmul(trilerp(f, c), w);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ actors
+// Per-warp shared state.  One warp == one ray.
+struct WarpShared {
+  float cdf[kS0 + 4];
+  float bins_a[kS0 + 4];
+  float bins_b[kS1 + 4];
+  float w2b[kMaxCand][12];  // world->box [R^T | -R^T t], row major 3x4
+  float bnd[kMaxCand][3];
+  int32_t cand_id[kMaxCand];
+  int32_t n_cand;
+  int32_t overflow;
+  float feat_t[32][33];
+};
+
+NFF_D void normalize3(float v[3]) {  // F.normalize: v / max(|v|, 1e-12)
+  float n = fsqrt(fadd(fadd(fmul(v[0], v[0]), fmul(v[1], v[1])), fmul(v[2], v[2])));
+  n = fmaxf(n, 1e-12f);
+  v[0] = fdiv(v[0], n);
+  v[1] = fdiv(v[1], n);
+  v[2] = fdiv(v[2], n);
+}
+
+// DynamicActors.get_boxes2world (model_components/dynamic_actors.py:251-268) = interpolate_trajectories_6d
+// (utils/poses.py:90-150) + rotation_6d_to_matrix (cameras/camera_utils.py:422-443) + pose inverse
+// (utils/poses.py:42-55), followed by the ray-line culling of NeuRADHashEncoding._get_actor_indices
+// (field_components/neurad_encoding.py:225-240).  Lanes stride over actors; survivors are compacted, in
+// increasing actor order, into the warp's candidate list.
+NFF_D void actor_candidates(const Actors& A, float time, const float o[3], const float d[3], WarpShared& ws) {
+  if (lane() == 0) {
+    ws.n_cand = 0;
+    ws.overflow = 0;
+  }
+  syncwarp();
+  if (A.n_actors == 0) return;
+  // torch.searchsorted(pose_times, t) (left): first index with times[idx] >= t
+  int lo = 0, hi = A.n_times;
+  while (lo < hi) {
+    int mid = (lo + hi) >> 1;
+    if (ldg(A.times + mid) < time) lo = mid + 1; else hi = mid;
+  }
+  int right = lo, left = right - 1 < 0 ? 0 : right - 1;
+  if (right > A.n_times - 1) right = A.n_times - 1;
+  float tl = ldg(A.times + left), tr = ldg(A.times + right);
+  float frac = fdiv(fsub(time, tl), fadd(fsub(tr, tl), 1e-6f));
+  frac = fminf(fmaxf(frac, 0.0f), 1.0f);
+  for (int base = 0; base < A.n_actors; base += 32) {
+    int a = base + lane();
+    bool keep = false;
+    float R[9], t[3];
+    if (a < A.n_actors) {
+      const float* kl = A.keyframes + ((size_t)left * A.n_actors + a) * 9;
+      const float* kr = A.keyframes + ((size_t)right * A.n_actors + a) * 9;
+      float p[9];
+#pragma unroll
+      for (int i = 0; i < 9; ++i) {
+        float l_ = ldg(kl + i), r_ = ldg(kr + i);
+        p[i] = fadd(l_, fmul(fsub(r_, l_), frac));
+      }
+      bool valid = (A.present[(size_t)left * A.n_actors + a] | A.present[(size_t)right * A.n_actors + a]) != 0;
+      float b1[3] = {p[0], p[1], p[2]};
+      normalize3(b1);
+      float dt = fadd(fadd(fmul(b1[0], p[3]), fmul(b1[1], p[4])), fmul(b1[2], p[5]));
+      float b2[3] = {fsub(p[3], fmul(dt, b1[0])), fsub(p[4], fmul(dt, b1[1])), fsub(p[5], fmul(dt, b1[2]))};
+      normalize3(b2);
+      float b3[3] = {fsub(fmul(b1[1], b2[2]), fmul(b1[2], b2[1])), fsub(fmul(b1[2], b2[0]), fmul(b1[0], b2[2])),
+                     fsub(fmul(b1[0], b2[1]), fmul(b1[1], b2[0]))};
+      // boxes2world rotation has rows b1,b2,b3; world2box rotation is its transpose
+      R[0] = b1[0]; R[1] = b2[0]; R[2] = b3[0];
+      R[3] = b1[1]; R[4] = b2[1]; R[5] = b3[1];
+      R[6] = b1[2]; R[7] = b2[2]; R[8] = b3[2];
+      t[0] = -fadd(fadd(fmul(R[0], p[6]), fmul(R[1], p[7])), fmul(R[2], p[8]));
+      t[1] = -fadd(fadd(fmul(R[3], p[6]), fmul(R[4], p[7])), fmul(R[5], p[8]));
+      t[2] = -fadd(fadd(fmul(R[6], p[6]), fmul(R[7], p[7])), fmul(R[8], p[8]));
+      // distance from the box centre to the ray line (|d| == 1 up to rounding; the reference renormalises the
+      // first->last sample chord, same direction)
+      float v[3] = {fsub(p[6], o[0]), fsub(p[7], o[1]), fsub(p[8], o[2])};
+      float cx = fsub(fmul(v[1], d[2]), fmul(v[2], d[1]));
+      float cy = fsub(fmul(v[2], d[0]), fmul(v[0], d[2]));
+      float cz = fsub(fmul(v[0], d[1]), fmul(v[1], d[0]));
+      float dist = fsqrt(fadd(fadd(fmul(cx, cx), fmul(cy, cy)), fmul(cz, cz)));
+      // the cull is conservative (a point inside the box is within |bounds| of the centre); 1e-3 relative slack
+      // makes the chord-vs-direction rounding difference irrelevant
+      keep = valid && dist < ldg(A.radii + a) * 1.001f;
+    }
+    unsigned m = vote_ballot(keep);
+    int slot = ws.n_cand + popc(m & ((1u << lane()) - 1u));
+    if (keep) {
+      if (slot < kMaxCand) {
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+          ws.w2b[slot][4 * i + 0] = R[3 * i + 0];
+          ws.w2b[slot][4 * i + 1] = R[3 * i + 1];
+          ws.w2b[slot][4 * i + 2] = R[3 * i + 2];
+          ws.w2b[slot][4 * i + 3] = t[i];
+          ws.bnd[slot][i] = ldg(A.bounds + 3 * a + i);
+        }
+        ws.cand_id[slot] = a;
+      } else {
+        ws.overflow = 1;
+      }
+    }
+    syncwarp();
+    if (lane() == 0) {
+      int n = ws.n_cand + popc(m);
+      ws.n_cand = n > kMaxCand ? kMaxCand : n;
+    }
+    syncwarp();
+  }
+}
+
+// The per-sample part of _get_actor_indices (neurad_encoding.py:241-254): is the sample mean inside a padded
+// box?  Returns the candidate slot (highest actor index wins, matching the reference's sequential index_put on
+// CPU) or -1; `pb` receives the position in the box frame.
+NFF_D int actor_of_sample(const WarpShared& ws, const Gauss& g, float pb[3]) {
+  int hit = -1;
+  int n = ws.n_cand;
+  for (int c = 0; c < n; ++c) {
+    const float* M = ws.w2b[c];
+    float q0 = fadd(fadd(fadd(fmul(M[0], g.x), fmul(M[1], g.y)), fmul(M[2], g.z)), M[3]);
+    float q1 = fadd(fadd(fadd(fmul(M[4], g.x), fmul(M[5], g.y)), fmul(M[6], g.z)), M[7]);
+    float q2 = fadd(fadd(fadd(fmul(M[8], g.x), fmul(M[9], g.y)), fmul(M[10], g.z)), M[11]);
+    if (fabsf(q0) < ws.bnd[c][0] && fabsf(q1) < ws.bnd[c][1] && fabsf(q2) < ws.bnd[c][2]) {
+      hit = c;
+      pb[0] = q0; pb[1] = q1; pb[2] = q2;
+    }
+  }
+  return hit;
+}
+
+// ------------------------------------------------------------------------------------- proposal density
+// NeuRADProposalField.get_density (fields/neurad_field.py:208-213) for one sample:
+// NeuRADHashEncoding.forward (static grid, or the containing actor's grid zero-padded) -> Linear(6,1) -> exp.
+NFF_D float proposal_density(const FieldGrids& fg, const WarpShared& ws, const Gauss& g, int* actor_id) {
+  float pb[3];
+  int c = actor_of_sample(ws, g, pb);
+  float feat[6];
+#pragma unroll
+  for (int i = 0; i < 6; ++i) feat[i] = 0.0f;
+  if (c >= 0) {
+    Gauss ga = {pb[0], pb[1], pb[2], g.std};
+    ga = contract(ga, fg.actor_scale);
+    const float* tab = fg.actor_tables[ws.cand_id[c]];
+    encode_f1<4>(tab, fg.act.mask, fg.act.T, fg.act.res, ga, feat);
+    *actor_id = ws.cand_id[c];
+  } else {
+    Gauss gs = contract(g, fg.static_scale);
+    encode_f1<6>(fg.stat.table, fg.stat.mask, fg.stat.T, fg.stat.res, gs, feat);
+    *actor_id = -1;
+  }
+  float acc = 0.0f;
+#pragma unroll
+  for (int i = 0; i < 6; ++i) acc = fmaf(feat[i], ldg(fg.decoder + i), acc);
+  return expf(acc);
+}
+
+// ----------------------------------------------------------------------------------------------- MLPs
+// y = W x + b with W stored transposed [IN][OUTP] in shared memory: every lane owns one sample (row); a weight
+// quad is one broadcast LDS.128 feeding 4 FFMAs.
+template <int IN, int OUT, int OUTP, bool RELU>
+NFF_D void dense(const float* NFF_RESTRICT W, const float* NFF_RESTRICT B, const float* x, float* y) {
+  float acc[OUTP];
+#pragma unroll
+  for (int o = 0; o < OUTP; ++o) acc[o] = o < OUT ? B[o] : 0.0f;
+#pragma unroll
+  for (int k = 0; k < IN; ++k) {
+    const float xk = x[k];
+#pragma unroll
+    for (int o4 = 0; o4 < OUTP / 4; ++o4) {
+      const float4 w = *reinterpret_cast<const float4*>(W + k * OUTP + 4 * o4);
+      acc[4 * o4 + 0] = fmaf(xk, w.x, acc[4 * o4 + 0]);
+      acc[4 * o4 + 1] = fmaf(xk, w.y, acc[4 * o4 + 1]);
+      acc[4 * o4 + 2] = fmaf(xk, w.z, acc[4 * o4 + 2]);
+      acc[4 * o4 + 3] = fmaf(xk, w.w, acc[4 * o4 + 3]);
+    }
+  }
+#pragma unroll
+  for (int o = 0; o < OUT; ++o) y[o] = RELU ? fmaxf(acc[o], 0.0f) : acc[o];
+}
+
+// components_from_spherical_harmonics(levels=4) (utils/math.py:31-94) on (d+1)/2 (fields/base_field.py:136-142)
+NFF_D void sh4_poly(float x, float y, float z, float* c) {
+  float xx = x * x, yy = y * y, zz = z * z;
+  c[0] = 0.28209479177387814f;
+  c[1] = 0.4886025119029199f * y;
+  c[2] = 0.4886025119029199f * z;
+  c[3] = 0.4886025119029199f * x;
+  c[4] = 1.0925484305920792f * x * y;
+  c[5] = 1.0925484305920792f * y * z;
+  c[6] = 0.9461746957575601f * zz - 0.31539156525251999f;
+  c[7] = 1.0925484305920792f * x * z;
+  c[8] = 0.5462742152960396f * (xx - yy);
+  c[9] = 0.5900435899266435f * y * (3.0f * xx - yy);
+  c[10] = 2.890611442640554f * x * y * z;
+  c[11] = 0.4570457994644658f * y * (5.0f * zz - 1.0f);
+  c[12] = 0.3731763325901154f * z * (5.0f * zz - 3.0f);
+  c[13] = 0.4570457994644658f * x * (5.0f * zz - 1.0f);
+  c[14] = 1.445305721320277f * z * (xx - yy);
+  c[15] = 0.5900435899266435f * x * (xx - 3.0f * yy);
+}
+NFF_D void sh4(float dx, float dy, float dz, float* c) {
+  sh4_poly(fmul(fadd(dx, 1.0f), 0.5f), fmul(fadd(dy, 1.0f), 0.5f), fmul(fadd(dz, 1.0f), 0.5f), c);
+}
+
+// --------------------------------------------------------------------------------- proposal round + resample
+// One proposal round for the warp's ray: densities (NeuRADProposalField.get_density) -> RaySamples.get_weights
+// (cameras/rays.py:188-210) -> prop depth (render_depth_simple, models/neurad.py:727-734) -> PDFSampler
+// (ray_samplers.py:309-361) producing S_NEW+1 new spacing-domain edges.
+// EdgeFn(i) returns the i-th spacing edge of the current level.
+template <int S, int S_NEW, class EdgeFn>
+NFF_D void proposal_round(const RenderParams& P, const FieldGrids& fg, WarpShared& ws, EdgeFn edge, const float o[3],
+                          const float d[3], float area, float s_near, float s_far, const float* NFF_RESTRICT u_tab,
+                          float* bins_out, int64_t ray, float* prop_depth, float* tr_w, int32_t* tr_aid,
+                          float* tr_bins_s, float* tr_bins_e, int32_t* tr_inds) {
+  constexpr int J = S / 32;
+  const Sampling& sp = P.samp;
+  float w[J];
+  float carry = 0.0f, depth_acc = 0.0f;
+#pragma unroll
+  for (int j = 0; j < J; ++j) {
+    const int s = j * 32 + lane();
+    float e0 = to_euclid(edge(s), s_near, s_far, sp);
+    float e1 = to_euclid(edge(s + 1), s_near, s_far, sp);
+    Gauss g = sample_gaussian(o, d, area, e0, e1);
+    int aid;
+    float dens = proposal_density(fg, ws, g, &aid);
+    float dd = fmul(fsub(e1, e0), dens);
+    float incl = warp_scan_add(dd);
+    float prev = shfl_up(incl, 1);
+    float excl = carry + (lane() == 0 ? 0.0f : prev);
+    carry += shfl(incl, 31);
+    float alpha = fsub(1.0f, expf(-dd));
+    float T = expf(-excl);
+    float wj = nan_to_num(fmul(alpha, T));
+    w[j] = wj;
+    depth_acc = fadd(depth_acc, fmul(wj, fmul(fadd(e0, e1), 0.5f)));
+    if (tr_w) tr_w[ray * S + s] = wj;
+    if (tr_aid) tr_aid[ray * S + s] = aid;
+  }
+  *prop_depth = warp_sum(depth_acc);
+
+  // PDFSampler: histogram padding, normalise, cdf
+  float part = 0.0f;
+#pragma unroll
+  for (int j = 0; j < J; ++j) {
+    w[j] = fadd(w[j], sp.hist_pad);
+    part += w[j];
+  }
+  float tot = warp_sum(part);
+  float padding = fmaxf(fsub(1e-5f, tot), 0.0f);
+  float pad_each = fdiv(padding, (float)S);
+  tot = fadd(tot, padding);
+  carry = 0.0f;
+#pragma unroll
+  for (int j = 0; j < J; ++j) {
+    float pdf = fdiv(fadd(w[j], pad_each), tot);
+    float incl = warp_scan_add(pdf) + carry;
+    carry = shfl(incl, 31);
+    ws.cdf[j * 32 + lane() + 1] = fminf(1.0f, incl);
+  }
+  if (lane() == 0) ws.cdf[0] = 0.0f;
+  syncwarp();
+  // inverse-cdf sampling: inds = searchsorted(cdf, u, side="right")
+  for (int i = lane(); i <= S_NEW; i += 32) {
+    float u = ldg(u_tab + i);
+    int lo = 0, hi = S + 1;
+    while (lo < hi) {
+      int mid = (lo + hi) >> 1;
+      if (ws.cdf[mid] <= u) lo = mid + 1; else hi = mid;
+    }
+    int below = lo - 1 < 0 ? 0 : (lo - 1 > S ? S : lo - 1);
+    int above = lo > S ? S : lo;
+    float c0 = ws.cdf[below], c1 = ws.cdf[above];
+    float b0 = edge(below), b1 = edge(above);
+    float t = nan_to_num(fdiv(fsub(u, c0), fsub(c1, c0)));
+    t = fminf(fmaxf(t, 0.0f), 1.0f);
+    float nb = fadd(b0, fmul(t, fsub(b1, b0)));
+    bins_out[i] = nb;
+    if (tr_inds) tr_inds[ray * (S_NEW + 1) + i] = lo;
+    if (tr_bins_s) tr_bins_s[ray * (S_NEW + 1) + i] = nb;
+    if (tr_bins_e) tr_bins_e[ray * (S_NEW + 1) + i] = to_euclid(nb, s_near, s_far, sp);
+  }
+  syncwarp();
+}
+
+// --------------------------------------------------------------------------------------- the whole ray
+// NeuRADModel.get_nff_outputs (models/neurad.py:368-421), eval mode.  `mlp` points at the packed main-field
+// weights in shared memory.
+NFF_D void render_ray(const RenderParams& P, WarpShared& ws, const float* NFF_RESTRICT mlp, int64_t ray) {
+  const Sampling& sp = P.samp;
+  const int ln = lane();
+  float o[3], d[3];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    o[i] = ldg(P.rays.origins + 3 * ray + i);
+    d[i] = ldg(P.rays.directions + 3 * ray + i);
+  }
+  const bool lidar = P.rays.is_lidar ? P.rays.is_lidar[ray] != 0 : false;
+  // _scale_pixel_area (neurad.py:702-709)
+  float area = fmul(ldg(P.rays.pixel_area + ray), lidar ? 1.0f : sp.cam_area_scale);
+  const float time = ldg(P.rays.times + ray);
+  // _get_ray_samples (neurad.py:443-449)
+  float far_ = P.rays.fars ? ldg(P.rays.fars + ray) : 1.0e6f;
+  far_ = fminf(far_, sp.sky_distance);
+  float near_ = P.rays.nears ? ldg(P.rays.nears + ray) : 0.0f;
+  const float s_near = spacing_fn(near_, sp), s_far = spacing_fn(far_, sp);
+
+  actor_candidates(P.actors, time, o, d, ws);
+
+  float prop_depth_0, prop_depth_1;
+  {
+    const FieldGrids& fg = P.fields[sp.field_of_round[0]];
+    auto edge0 = [](int i) { return linspace01(i, kS0); };
+    proposal_round<kS0, kS1>(P, fg, ws, edge0, o, d, area, s_near, s_far, sp.u1, ws.bins_b, ray, &prop_depth_0,
+                             P.trace.prop_weights_0, P.trace.actor_id_0, P.trace.bins_s_1, P.trace.bins_e_1,
+                             P.trace.inds_1);
+  }
+  {
+    const FieldGrids& fg = P.fields[sp.field_of_round[1]];
+    const float* bb = ws.bins_b;
+    auto edge1 = [bb](int i) { return bb[i]; };
+    proposal_round<kS1, kS2>(P, fg, ws, edge1, o, d, area, s_near, s_far, sp.u2, ws.bins_a, ray, &prop_depth_1,
+                             P.trace.prop_weights_1, P.trace.actor_id_1, P.trace.bins_s_2, P.trace.bins_e_2,
+                             P.trace.inds_2);
+  }
+
+  // ---- main field: one sample per lane (fields/neurad_field.py:128-152) ----
+  float e0 = to_euclid(ws.bins_a[ln], s_near, s_far, sp);
+  float e1 = to_euclid(ws.bins_a[ln + 1], s_near, s_far, sp);
+  if (ln == kS2 - 1) e1 = fadd(e1, fsub(sp.sky_distance, e1));  // sky sample (neurad.py:451-455)
+  Gauss g = sample_gaussian(o, d, area, e0, e1);
+  const FieldGrids& fm = P.fields[B200NERF_FIELD_MAIN];
+  float x[kNff + kSh];  // first the 32 grid features, later [geo_embedding | sh]
+  float dir[3] = {d[0], d[1], d[2]};
+  int aid = -1;
+  {
+    float pb[3];
+    int c = actor_of_sample(ws, g, pb);
+    if (c >= 0) {
+      aid = ws.cand_id[c];
+      Gauss ga = {pb[0], pb[1], pb[2], g.std};
+      ga = contract(ga, fm.actor_scale);
+#pragma unroll
+      for (int i = 16; i < 32; ++i) x[i] = 0.0f;  // F.pad(actor_features, (0, 32-16))
+      encode_f4<4>(fm.actor_tables[aid], fm.act.mask, fm.act.T, fm.act.res, ga, x);
+      // direction into the box frame, renormalised with +EPS (neurad_encoding.py:203-209)
+      const float* M = ws.w2b[c];
+      float q0 = fadd(fadd(fmul(M[0], d[0]), fmul(M[1], d[1])), fmul(M[2], d[2]));
+      float q1 = fadd(fadd(fmul(M[4], d[0]), fmul(M[5], d[1])), fmul(M[6], d[2]));
+      float q2 = fadd(fadd(fmul(M[8], d[0]), fmul(M[9], d[1])), fmul(M[10], d[2]));
+      float n = fadd(fsqrt(fadd(fadd(fmul(q0, q0), fmul(q1, q1)), fmul(q2, q2))), 1.0e-7f);
+      dir[0] = fdiv(q0, n); dir[1] = fdiv(q1, n); dir[2] = fdiv(q2, n);
+    } else {
+      Gauss gs = contract(g, fm.static_scale);
+      encode_f4<8>(fm.stat.table, fm.stat.mask, fm.stat.T, fm.stat.res, gs, x);
+    }
+  }
+  float h[kHidden];
+  dense<kGeoIn, kHidden, kHidden, true>(mlp + kOffGeoW0, mlp + kOffGeoB0, x, h);
+  float go[kNff + 1];
+  dense<kHidden, kNff + 1, kGeoOutP, false>(mlp + kOffGeoW1, mlp + kOffGeoB1, h, go);
+  const float sdf = go[0];
+#pragma unroll
+  for (int i = 0; i < kNff; ++i) x[i] = go[i + 1];  // geo_embedding
+  sh4(dir[0], dir[1], dir[2], x + kNff);
+  dense<kNff + kSh, kHidden, kHidden, true>(mlp + kOffFeatW0, mlp + kOffFeatB0, x, h);
+  float h2[kHidden];
+  dense<kHidden, kHidden, kHidden, true>(mlp + kOffFeatW1, mlp + kOffFeatB1, h, h2);
+  dense<kHidden, kNff, kNff, false>(mlp + kOffFeatW2, mlp + kOffFeatB2, h2, h);
+  float feat[kNff];
+#pragma unroll
+  for (int i = 0; i < kNff; ++i) feat[i] = x[i] + h[i];  // residual (neurad_field.py:141)
+  // SigmoidDensity (model_components/utils.py:29-41): alpha = sigmoid(-sdf * beta)
+  const float alpha = frcp(fadd(1.0f, expf(fmul(sdf, P.beta))));
+
+  // nerfacc.render_weight_from_alpha (neurad.py:717): w_i = alpha_i * prod_{j<i} (1 - alpha_j)
+  float incl = warp_scan_mul(fsub(1.0f, alpha));
+  float prevT = shfl_up(incl, 1);
+  float T = ln == 0 ? 1.0f : prevT;
+  float w = fmul(alpha, T);
+  const float acc = warp_sum(w);  // AccumulationRenderer (renderers.py:349)
+  // depth over the non-sky samples (neurad.py:388-389, 727-734)
+  float dterm = ln < kS2 - 1 ? fmul(w, fmul(fadd(e0, e1), 0.5f)) : 0.0f;
+  const float depth = warp_sum(dterm);
+  if (ln == kS2 - 1) w = fadd(fadd(w, 1.0f), -acc);  // remaining accumulation onto the sky sample (neurad.py:381)
+
+  if (P.trace.sdf) P.trace.sdf[ray * kS2 + ln] = sdf;
+  if (P.trace.alpha) P.trace.alpha[ray * kS2 + ln] = alpha;
+  if (P.trace.weights) P.trace.weights[ray * kS2 + ln] = w;
+  if (P.trace.actor_id_main) P.trace.actor_id_main[ray * kS2 + ln] = aid;
+  if (P.trace.field_feature) {
+#pragma unroll
+    for (int i = 0; i < kNff; ++i) P.trace.field_feature[(ray * kS2 + ln) * kNff + i] = feat[i];
+  }
+
+  // FeatureRenderer: sum_s w_s * feat_s (renderers.py:85) via a padded shared-memory transpose
+#pragma unroll
+  for (int i = 0; i < kNff; ++i) ws.feat_t[ln][i] = fmul(feat[i], w);
+  syncwarp();
+  float fsum = 0.0f;
+#pragma unroll
+  for (int s = 0; s < kS2; ++s) fsum = fadd(fsum, ws.feat_t[s][ln]);
+  syncwarp();
+
+  const int fdim = P.nff_dim + P.app.dim;
+  float* fo = P.out.features + ray * fdim;
+  fo[ln] = fsum;
+  // _get_appearance_embedding, temporal branch (neurad.py:423-441)
+  float app = 0.0f;
+  if (ln < P.app.dim) {
+    float sens = P.rays.sensor_idx ? (float)P.rays.sensor_idx[ray] : 0.0f;
+    float eps_ = (float)P.app.eps;
+    float tidx = fmul(fdiv(time, P.app.duration), eps_);
+    float before = fminf(fmaxf(floorf(tidx), 0.0f), eps_ - 1.0f);
+    float after = fminf(fmaxf(fadd(before, 1.0f), 0.0f), eps_ - 1.0f);
+    float ratio = fsub(tidx, before);
+    int ib = (int)fadd(before, fmul(sens, eps_)), ia = (int)fadd(after, fmul(sens, eps_));
+    float eb = ldg(P.app.emb + (size_t)ib * P.app.dim + ln), ea = ldg(P.app.emb + (size_t)ia * P.app.dim + ln);
+    app = fadd(fmul(eb, fsub(1.0f, ratio)), fmul(ea, ratio));
+    fo[P.nff_dim + ln] = app;
+  }
+  if (ln == 0) {
+    P.out.depth[ray] = depth;
+    P.out.accumulation[ray] = acc;
+    P.out.prop_depth_0[ray] = prop_depth_0;
+    P.out.prop_depth_1[ray] = prop_depth_1;
+  }
+}
+
+}  // namespace nff

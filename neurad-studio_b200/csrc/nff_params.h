@@ -1,0 +1,99 @@
+// nff_params.h -- plain-old-data parameter blocks handed to the kernels (by value, in the kernel parameter
+// space) plus compile-time limits.  Shared between the CUDA build and the test-only host emulation.
+#pragma once
+#include <stdint.h>
+
+#include "../../include/b200nerf.h"
+
+namespace nff {
+
+constexpr int kMaxLevels = 16;     // per grid (HashEncoding default is 16 levels)
+constexpr int kMaxCand = 32;       // actor candidates per ray (ray line passes within the box's bounding sphere)
+constexpr int kS0 = 128;           // proposal samples, round 0   (SamplingSettings.num_proposal_samples[0])
+constexpr int kS1 = 64;            // proposal samples, round 1
+constexpr int kS2 = 32;            // nerf samples == warp width: one sample per lane in the shading phase
+constexpr int kGeoIn = 32;         // main grid: 8 levels x 4 features
+constexpr int kHidden = 32;
+constexpr int kNff = 32;           // nff_out_dim
+constexpr int kSh = 16;            // SH degree-4 basis
+constexpr int kApp = 16;           // appearance_dim (max supported)
+constexpr int kFeatOut = 64;       // max nff_out_dim + appearance_dim
+
+// packed, transposed ([in][out_padded]) MLP weights of the main field, in floats
+constexpr int kGeoOutP = 36;  // 33 padded to a multiple of 4
+constexpr int kOffGeoW0 = 0;                                  // [32][32]
+constexpr int kOffGeoB0 = kOffGeoW0 + kGeoIn * kHidden;       // [32]
+constexpr int kOffGeoW1 = kOffGeoB0 + kHidden;                // [32][36]
+constexpr int kOffGeoB1 = kOffGeoW1 + kHidden * kGeoOutP;     // [36]
+constexpr int kOffFeatW0 = kOffGeoB1 + kGeoOutP;              // [48][32]
+constexpr int kOffFeatB0 = kOffFeatW0 + (kNff + kSh) * kHidden;
+constexpr int kOffFeatW1 = kOffFeatB0 + kHidden;              // [32][32]
+constexpr int kOffFeatB1 = kOffFeatW1 + kHidden * kHidden;
+constexpr int kOffFeatW2 = kOffFeatB1 + kHidden;              // [32][32]
+constexpr int kOffFeatB2 = kOffFeatW2 + kHidden * kNff;
+constexpr int kMainMlpFloats = kOffFeatB2 + kNff;             // 5828 floats = 23.3 KB
+// lidar decoder 48->32->32->2(4)
+constexpr int kLidOutP = 4;
+constexpr int kOffLidW0 = 0;                                   // [48][32]
+constexpr int kOffLidB0 = kOffLidW0 + (kNff + kApp) * kHidden;
+constexpr int kOffLidW1 = kOffLidB0 + kHidden;                 // [32][32]
+constexpr int kOffLidB1 = kOffLidW1 + kHidden * kHidden;
+constexpr int kOffLidW2 = kOffLidB1 + kHidden;                 // [32][4]
+constexpr int kOffLidB2 = kOffLidW2 + kHidden * kLidOutP;
+constexpr int kLidarMlpFloats = kOffLidB2 + kLidOutP;
+
+struct Grid {
+  const float* table;  // [L*T, F]
+  uint32_t mask;       // T-1
+  uint32_t T;
+  int32_t L, F;
+  float res[kMaxLevels];
+};
+
+struct FieldGrids {
+  Grid stat;
+  Grid act;                          // .table unused; per-actor tables below
+  const float* const* actor_tables;  // device array [n_actors]
+  float static_scale, actor_scale;
+  const float* decoder;              // proposal fields: density_decoder.weight [L*F]; main: nullptr
+};
+
+struct Actors {
+  int32_t n_actors, n_times;
+  const float* times;      // [T]
+  const float* keyframes;  // [T,A,9]: per-keyframe Gram-Schmidt'ed (a1,a2) + position (poses.py:107-114)
+  const uint8_t* present;  // [T,A]
+  const float* bounds;     // [A,3] = size/2 + padding
+  const float* radii;      // [A]   = |bounds|
+};
+
+struct Sampling {
+  float lam, scaling, sky_distance, hist_pad, cam_area_scale;
+  float lam_1, ratio;  // |lam-1|, lam_1/lam
+  const float* u1;     // [kS1+1]
+  const float* u2;     // [kS2+1]
+  int32_t field_of_round[2];
+};
+
+struct Appearance {
+  const float* emb;
+  int32_t num_embeds, dim, eps;
+  float duration;
+};
+
+struct RenderParams {
+  FieldGrids fields[3];
+  const float* main_mlp;   // packed (kMainMlpFloats)
+  const float* lidar_mlp;  // packed (kLidarMlpFloats) or nullptr
+  float beta;
+  int32_t nff_dim;
+  Actors actors;
+  Sampling samp;
+  Appearance app;
+  b200nerf_rays rays;
+  b200nerf_outputs out;
+  b200nerf_trace trace;
+  int64_t n_rays;
+};
+
+}  // namespace nff

@@ -1,0 +1,154 @@
+// TEST SCAFFOLDING ONLY -- runs the device code of neurad-studio_b200/csrc/nff_device.h on the host.
+//
+// Each "warp" is 32 std::threads executing nff::render_ray in lock-step at warp collectives (see csrc/simt.h), so
+// the exact kernel logic (scans, ballots, binary searches, actor culling, MLPs) can be checked against the oracle
+// on a machine without a GPU.  Never linked into libb200nerf.so; the product has no CPU path.
+#include <cstdlib>
+#include <thread>
+#include <vector>
+
+#include "../../neurad-studio_b200/csrc/nff_device.h"
+
+using namespace nff;
+
+static void pack_linear(const float* w, const float* b, int out_f, int in_f, int outp, float* dw, float* db) {
+  for (int k = 0; k < in_f; ++k)
+    for (int o = 0; o < outp; ++o) dw[k * outp + o] = o < out_f ? w[o * in_f + k] : 0.f;
+  for (int o = 0; o < outp; ++o) db[o] = (o < out_f && b) ? b[o] : 0.f;
+}
+
+extern "C" {
+
+// ptrs / ints / floats layouts are documented in tests/host_emul/emul.py
+int emul_render(const void* const* ptrs, const int* ints, const float* floats, long long n_rays) {
+  RenderParams P{};
+  std::vector<float> kf, bounds, radii;
+  int pi = 0, ii = 0, fi = 0;
+  const int n_actors = ints[ii++];
+  const int n_times = ints[ii++];
+  for (int f = 0; f < 3; ++f) {
+    FieldGrids& fg = P.fields[f];
+    Grid* gs[2] = {&fg.stat, &fg.act};
+    for (int k = 0; k < 2; ++k) {
+      Grid& g = *gs[k];
+      g.L = ints[ii++];
+      g.F = ints[ii++];
+      int log2T = ints[ii++];
+      g.T = 1u << log2T;
+      g.mask = g.T - 1u;
+      for (int l = 0; l < kMaxLevels; ++l) g.res[l] = floats[fi++];
+    }
+    fg.stat.table = (const float*)ptrs[pi++];
+    fg.actor_tables = (const float* const*)ptrs[pi++];
+    fg.decoder = (const float*)ptrs[pi++];
+    fg.static_scale = floats[fi++];
+    fg.actor_scale = floats[fi++];
+  }
+  std::vector<float> mlp(kMainMlpFloats);
+  const float* t[10];
+  for (int k = 0; k < 10; ++k) t[k] = (const float*)ptrs[pi++];
+  pack_linear(t[0], t[1], kHidden, kGeoIn, kHidden, &mlp[kOffGeoW0], &mlp[kOffGeoB0]);
+  pack_linear(t[2], t[3], kNff + 1, kHidden, kGeoOutP, &mlp[kOffGeoW1], &mlp[kOffGeoB1]);
+  pack_linear(t[4], t[5], kHidden, kNff + kSh, kHidden, &mlp[kOffFeatW0], &mlp[kOffFeatB0]);
+  pack_linear(t[6], t[7], kHidden, kHidden, kHidden, &mlp[kOffFeatW1], &mlp[kOffFeatB1]);
+  pack_linear(t[8], t[9], kNff, kHidden, kNff, &mlp[kOffFeatW2], &mlp[kOffFeatB2]);
+  P.beta = floats[fi++];
+  P.nff_dim = kNff;
+  // actors
+  const float* a_times = (const float*)ptrs[pi++];
+  const float* a_rot6 = (const float*)ptrs[pi++];
+  const float* a_pos = (const float*)ptrs[pi++];
+  const uint8_t* a_present = (const uint8_t*)ptrs[pi++];
+  const float* a_sizes = (const float*)ptrs[pi++];
+  float pad[3] = {floats[fi], floats[fi + 1], floats[fi + 2]};
+  fi += 3;
+  if (n_actors > 0) {
+    kf.resize((size_t)9 * n_times * n_actors);
+    bounds.resize(3 * n_actors);
+    radii.resize(n_actors);
+    for (int i = 0; i < n_times * n_actors; ++i) {
+      float a1[3] = {a_rot6[6 * i], a_rot6[6 * i + 1], a_rot6[6 * i + 2]};
+      float a2[3] = {a_rot6[6 * i + 3], a_rot6[6 * i + 4], a_rot6[6 * i + 5]};
+      normalize3(a1);
+      float dt = fadd(fadd(fmul(a1[0], a2[0]), fmul(a1[1], a2[1])), fmul(a1[2], a2[2]));
+      for (int k = 0; k < 3; ++k) a2[k] = fsub(a2[k], fmul(dt, a1[k]));
+      normalize3(a2);
+      float* o = &kf[9 * (size_t)i];
+      for (int k = 0; k < 3; ++k) { o[k] = a1[k]; o[3 + k] = a2[k]; o[6 + k] = a_pos[3 * i + k]; }
+    }
+    for (int i = 0; i < n_actors; ++i) {
+      float b[3];
+      for (int k = 0; k < 3; ++k) b[k] = bounds[3 * i + k] = fadd(fmul(a_sizes[3 * i + k], 0.5f), pad[k]);
+      radii[i] = fsqrt(fadd(fadd(fmul(b[0], b[0]), fmul(b[1], b[1])), fmul(b[2], b[2])));
+    }
+    P.actors = Actors{n_actors, n_times, a_times, kf.data(), a_present, bounds.data(), radii.data()};
+  }
+  // sampling
+  Sampling& s = P.samp;
+  s.lam = floats[fi++]; s.scaling = floats[fi++]; s.sky_distance = floats[fi++]; s.hist_pad = floats[fi++];
+  s.cam_area_scale = floats[fi++];
+  double lam1 = std::fabs((double)s.lam - 1.0);
+  s.lam_1 = (float)lam1;
+  s.ratio = (float)(lam1 / (double)s.lam);
+  s.u1 = (const float*)ptrs[pi++];
+  s.u2 = (const float*)ptrs[pi++];
+  s.field_of_round[0] = ints[ii++];
+  s.field_of_round[1] = ints[ii++];
+  // appearance
+  P.app.emb = (const float*)ptrs[pi++];
+  P.app.num_embeds = ints[ii++];
+  P.app.dim = ints[ii++];
+  P.app.eps = ints[ii++];
+  P.app.duration = floats[fi++];
+  // rays
+  P.rays.origins = (const float*)ptrs[pi++];
+  P.rays.directions = (const float*)ptrs[pi++];
+  P.rays.pixel_area = (const float*)ptrs[pi++];
+  P.rays.times = (const float*)ptrs[pi++];
+  P.rays.nears = (const float*)ptrs[pi++];
+  P.rays.fars = (const float*)ptrs[pi++];
+  P.rays.sensor_idx = (const int64_t*)ptrs[pi++];
+  P.rays.is_lidar = (const uint8_t*)ptrs[pi++];
+  // outputs
+  P.out.features = (float*)ptrs[pi++];
+  P.out.depth = (float*)ptrs[pi++];
+  P.out.accumulation = (float*)ptrs[pi++];
+  P.out.prop_depth_0 = (float*)ptrs[pi++];
+  P.out.prop_depth_1 = (float*)ptrs[pi++];
+  // trace
+  P.trace.prop_weights_0 = (float*)ptrs[pi++];
+  P.trace.prop_weights_1 = (float*)ptrs[pi++];
+  P.trace.bins_s_1 = (float*)ptrs[pi++];
+  P.trace.bins_e_1 = (float*)ptrs[pi++];
+  P.trace.bins_s_2 = (float*)ptrs[pi++];
+  P.trace.bins_e_2 = (float*)ptrs[pi++];
+  P.trace.inds_1 = (int32_t*)ptrs[pi++];
+  P.trace.inds_2 = (int32_t*)ptrs[pi++];
+  P.trace.sdf = (float*)ptrs[pi++];
+  P.trace.alpha = (float*)ptrs[pi++];
+  P.trace.field_feature = (float*)ptrs[pi++];
+  P.trace.weights = (float*)ptrs[pi++];
+  P.trace.actor_id_0 = (int32_t*)ptrs[pi++];
+  P.trace.actor_id_1 = (int32_t*)ptrs[pi++];
+  P.trace.actor_id_main = (int32_t*)ptrs[pi++];
+  P.n_rays = n_rays;
+
+  // one emulated warp (32 threads) per hardware thread group; rays are distributed round-robin
+  unsigned hw = std::thread::hardware_concurrency();
+  int n_warps = hw >= 64 ? 2 : 1;
+  if (n_warps > n_rays) n_warps = (int)n_rays;
+  if (n_warps < 1) return 0;
+  std::vector<simt::EmuWarp> warps(n_warps);
+  std::vector<WarpShared> shared(n_warps);
+  std::vector<std::thread> threads;
+  for (int w = 0; w < n_warps; ++w)
+    for (int l = 0; l < 32; ++l)
+      threads.emplace_back([&, w, l]() {
+        simt::t_lane = l;
+        simt::t_warp = &warps[w];
+        for (long long r = w; r < n_rays; r += n_warps) render_ray(P, shared[w], mlp.data(), r);
+      });
+  for (auto& th : threads) th.join();
+  return 0;
+}
+}
