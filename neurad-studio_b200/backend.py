@@ -272,15 +272,24 @@ class B200Backend:
         return out
 
     # ------------------------------------------------------------------------------------------- ray generation
-    def raygen_pinhole(self, cam, row0: int = 0, row_step: int = 1, col0: int = 0, col_step: int = 1) -> Dict[str, torch.Tensor]:
-        """Cameras.generate_rays for one pinhole camera (scene.PinholeCamera) over a strided pixel grid."""
+    def _ray_buffers(self, n: int, out: Optional[Dict[str, torch.Tensor]]):
+        if out is None:
+            return (torch.empty(n, 3, device=self.device), torch.empty(n, 3, device=self.device),
+                    torch.empty(n, 1, device=self.device), torch.empty(n, 1, device=self.device))
+        bufs = tuple(out[k] for k in ("origins", "directions", "pixel_area", "times"))
+        for b, w in zip(bufs, (3, 3, 1, 1)):
+            if not (b.is_contiguous() and b.device == self.device and b.dtype == torch.float32 and b.numel() == n * w):
+                raise ValueError("pre-allocated ray buffer has the wrong layout")
+        return bufs
+
+    def raygen_pinhole(self, cam, row0: int = 0, row_step: int = 1, col0: int = 0, col_step: int = 1,
+                       out: Optional[Dict[str, torch.Tensor]] = None) -> Dict[str, torch.Tensor]:
+        """Cameras.generate_rays for one pinhole camera (scene.PinholeCamera) over a strided pixel grid.
+        `out` may hold pre-allocated (slices of) origins/directions/pixel_area/times buffers."""
         n_rows = len(range(row0, cam.height, row_step))
         n_cols = len(range(col0, cam.width, col_step))
         n = n_rows * n_cols
-        o = torch.empty(n, 3, device=self.device)
-        d = torch.empty(n, 3, device=self.device)
-        a = torch.empty(n, 1, device=self.device)
-        t = torch.empty(n, 1, device=self.device)
+        o, d, a, t = self._ray_buffers(n, out)
         c2w = (ctypes.c_float * 12)(*cam.c2w.reshape(-1).tolist())
         vel = (ctypes.c_float * 3)(*cam.velocity.tolist()) if cam.velocity is not None else None
         self._check(
@@ -292,14 +301,12 @@ class B200Backend:
         )
         return {"origins": o, "directions": d, "pixel_area": a, "times": t, "shape": (n_rows, n_cols)}
 
-    def raygen_lidar_points(self, scan, points: Optional[torch.Tensor] = None) -> Dict[str, torch.Tensor]:
+    def raygen_lidar_points(self, scan, points: Optional[torch.Tensor] = None,
+                            out: Optional[Dict[str, torch.Tensor]] = None) -> Dict[str, torch.Tensor]:
         """Lidars.generate_rays(points=...) for one scan (scene.LidarScan)."""
         pts = self._dev(scan.points if points is None else points)
         n = pts.shape[0]
-        o = torch.empty(n, 3, device=self.device)
-        d = torch.empty(n, 3, device=self.device)
-        a = torch.empty(n, 1, device=self.device)
-        t = torch.empty(n, 1, device=self.device)
+        o, d, a, t = self._ray_buffers(n, out)
         dist = torch.empty(n, 1, device=self.device)
         l2w = (ctypes.c_float * 12)(*scan.l2w.reshape(-1).tolist())
         vel = (ctypes.c_float * 3)(*scan.velocity.tolist()) if scan.velocity is not None else None

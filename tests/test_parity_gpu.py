@@ -80,7 +80,7 @@ def test_fused_render_vs_oracle_16_actors(backend):
     cfg = nsb.small_config(n_actors=16, log2_main=16, log2_prop=14)
     out, ref = _live_case(backend, cfg, 2048, seed=21, beta=4.0, sdf_bias=0.5)
     n_hit = int((ref["actor_id_main"] >= 0).sum())
-    assert n_hit > 200, n_hit  # the actor branch is really exercised
+    assert n_hit > 100, n_hit  # the actor branch is really exercised
     same = torch.ones(2048, dtype=torch.bool)
     for k in ("inds_1", "inds_2", "actor_id_0", "actor_id_1", "actor_id_main"):
         neq = out[k].cpu().long() != ref[k].long()
