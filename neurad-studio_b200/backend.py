@@ -174,7 +174,7 @@ class B200Backend:
                     raise KeyError(key)
                 setattr(r, name, None)
                 return
-            t = self._dev(t.reshape(n, -1) if name in ("origins", "directions") else t.reshape(-1), dtype)
+            t = self._dev(t.reshape(n, 3) if name in ("origins", "directions") else t.reshape(-1), dtype)
             hold.append(t)
             setattr(r, name, t.data_ptr())
 

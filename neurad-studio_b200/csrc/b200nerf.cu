@@ -77,9 +77,10 @@ int make_grid(const b200nerf_grid_desc* d, const float* table, Grid* g) {
 }  // namespace
 
 // =================================================================================================== kernels
+constexpr int kRenderWarps = 8;  // warps (= rays in flight) per CTA; 2 CTAs/SM -> 16 warps/SM at <=128 registers
 
 template <int WARPS>
-__global__ void __launch_bounds__(WARPS * 32) nff_render_kernel(const __grid_constant__ RenderParams P) {
+__global__ void __launch_bounds__(WARPS * 32, 16 / WARPS) nff_render_kernel(const __grid_constant__ RenderParams P) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float* mlp = reinterpret_cast<float*>(smem_raw);
   constexpr int kMlpBytes = (kMainMlpFloats * 4 + 15) / 16 * 16;
@@ -370,8 +371,8 @@ int b200nerf_create(int device_ordinal, b200nerf_ctx** out) {
   REQUIRE(c != nullptr, "out of host memory");
   c->device = device_ordinal;
   c->sm_count = prop.multiProcessorCount;
-  CUDA_TRY(cudaFuncSetAttribute(nff_render_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                (int)((kMainMlpFloats * 4 + 15) / 16 * 16 + 4 * sizeof(WarpShared))));
+  CUDA_TRY(cudaFuncSetAttribute(nff_render_kernel<kRenderWarps>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)((kMainMlpFloats * 4 + 15) / 16 * 16 + kRenderWarps * sizeof(WarpShared))));
   *out = c;
   return 0;
 }
@@ -597,10 +598,10 @@ int b200nerf_nff_render_fwd(b200nerf_ctx* c, const b200nerf_rays* rays, int64_t 
   P.out = *out;
   if (trace) P.trace = *trace;
   P.n_rays = n_rays;
-  constexpr int WARPS = 4;
+  constexpr int WARPS = kRenderWarps;
   const size_t smem = (kMainMlpFloats * 4 + 15) / 16 * 16 + WARPS * sizeof(WarpShared);
   int64_t blocks_needed = (n_rays + WARPS - 1) / WARPS;
-  int64_t max_blocks = (int64_t)c->sm_count * 4;
+  int64_t max_blocks = (int64_t)c->sm_count * (16 / WARPS);  // persistent: resident CTAs only, grid-stride over rays
   int blocks = (int)(blocks_needed < max_blocks ? blocks_needed : max_blocks);
   cudaStream_t st = (cudaStream_t)stream;
   nff_render_kernel<WARPS><<<blocks, WARPS * 32, smem, st>>>(P);
@@ -616,9 +617,10 @@ int b200nerf_nff_render_fwd(b200nerf_ctx* c, const b200nerf_rays* rays, int64_t 
 
 int b200nerf_hashgrid_fwd(b200nerf_ctx* c, const b200nerf_grid_desc* desc, const float* table, const float* x,
                           float* out, int32_t* indices, int64_t n_points, void* stream) {
-  REQUIRE(c && desc && table && x && out, "NULL argument");
+  REQUIRE(c && desc, "NULL argument");
   REQUIRE(desc->features_per_level >= 1 && desc->features_per_level <= 8, "features_per_level must be in [1,8]");
   if (n_points == 0) return 0;
+  REQUIRE(table && x && out, "NULL argument");
   DeviceGuard g(c->device);
   Grid gr{};
   if (int e = make_grid(desc, table, &gr)) return e;
@@ -629,8 +631,9 @@ int b200nerf_hashgrid_fwd(b200nerf_ctx* c, const b200nerf_grid_desc* desc, const
 }
 
 int b200nerf_sh4_fwd(b200nerf_ctx* c, const float* dirs, float* out, int64_t n, void* stream) {
-  REQUIRE(c && dirs && out, "NULL argument");
+  REQUIRE(c, "NULL argument");
   if (n == 0) return 0;
+  REQUIRE(dirs && out, "NULL argument");
   DeviceGuard g(c->device);
   sh4_fwd_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(dirs, out, n);
   CUDA_TRY(cudaGetLastError());

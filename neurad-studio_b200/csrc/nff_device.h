@@ -118,12 +118,14 @@ NFF_D Cell grid_cell(float x, float y, float z, float res) {
   float px = fmul(x, res), py = fmul(y, res), pz = fmul(z, res);
   float fx = floorf(px), fy = floorf(py), fz = floorf(pz);
   Cell c;
-  c.hx[0] = (uint32_t)(int32_t)fx;
-  c.hx[1] = (uint32_t)(int32_t)ceilf(px);
-  c.hy[0] = (uint32_t)(int32_t)fy * 2654435761u;
-  c.hy[1] = (uint32_t)(int32_t)ceilf(py) * 2654435761u;
-  c.hz[0] = (uint32_t)(int32_t)fz * 805459861u;
-  c.hz[1] = (uint32_t)(int32_t)ceilf(pz) * 805459861u;
+  // ceil(p) == floor(p) + (p != floor(p)) for finite p
+  const uint32_t ix = (uint32_t)(int32_t)fx, iy = (uint32_t)(int32_t)fy, iz = (uint32_t)(int32_t)fz;
+  c.hx[0] = ix;
+  c.hx[1] = ix + (px != fx ? 1u : 0u);
+  c.hy[0] = iy * 2654435761u;
+  c.hy[1] = (iy + (py != fy ? 1u : 0u)) * 2654435761u;
+  c.hz[0] = iz * 805459861u;
+  c.hz[1] = (iz + (pz != fz ? 1u : 0u)) * 805459861u;
   c.ox = fsub(px, fx);
   c.oy = fsub(py, fy);
   c.oz = fsub(pz, fz);
@@ -152,50 +154,54 @@ NFF_D float trilerp(const float f[8], const Cell& c) {
   return blend(f0312, c.oz, f4756, iz);
 }
 
-// One grid, all levels, F = 1: out[l] = interp * 1/max(1, 2*res_l*std)  (neurad_encoding.py:297-304)
-template <int L>
-NFF_D void encode_f1(const float* NFF_RESTRICT table, uint32_t mask, uint32_t T, const float* res, Gauss g,
-                     float* out) {
-#pragma unroll
+// One grid, all levels, F = 1, fused with the proposal field's Linear(L,1) decoder:
+//   sum_l dec[l] * interp_l * 1/max(1, 2*res_l*std)      (neurad_encoding.py:297-304, neurad_field.py:201,211)
+// The level loop stays rolled (one copy of the ~90-instruction body) so the kernel fits the instruction cache.
+NFF_D float encode_f1_dot(const float* NFF_RESTRICT table, const Grid& gr, int L, Gauss g,
+                          const float* NFF_RESTRICT dec) {
+  float acc = 0.0f;
+#pragma unroll 1
   for (int l = 0; l < L; ++l) {
-    Cell c = grid_cell(g.x, g.y, g.z, res[l]);
+    const float res = gr.res[l];
+    Cell c = grid_cell(g.x, g.y, g.z, res);
     uint32_t r[8];
-    cell_rows(c, mask, r);
-    const float* base = table + (size_t)l * T;
+    cell_rows(c, gr.mask, r);
+    const float* base = table + (size_t)l * gr.T;
     float f[8];
 #pragma unroll
     for (int k = 0; k < 8; ++k) f[k] = ldg(base + r[k]);
-    float w = frcp(fmaxf(fmul(fmul(res[l], 2.0f), g.std), 1.0f));
-    out[l] = fmul(trilerp(f, c), w);
+    float w = frcp(fmaxf(fmul(fmul(res, 2.0f), g.std), 1.0f));
+    acc = fmaf(fmul(trilerp(f, c), w), ldg(dec + l), acc);
   }
+  return acc;
 }
-// F = 4 (16-byte rows, one LDG.128 per corner)
-template <int L>
-NFF_D void encode_f4(const float* NFF_RESTRICT table, uint32_t mask, uint32_t T, const float* res, Gauss g,
-                     float* out) {
-#pragma unroll
+// F = 4 (16-byte rows, one LDG.128 per corner); writes feature 4l+f of this lane's sample to panel[4l+f][lane].
+NFF_D void encode_f4_panel(const float* NFF_RESTRICT table, const Grid& gr, int L, Gauss g, float (*panel)[33]) {
+  const int ln = lane();
+#pragma unroll 1
   for (int l = 0; l < L; ++l) {
-    Cell c = grid_cell(g.x, g.y, g.z, res[l]);
+    const float res = gr.res[l];
+    Cell c = grid_cell(g.x, g.y, g.z, res);
     uint32_t r[8];
-    cell_rows(c, mask, r);
-    const float4* base = reinterpret_cast<const float4*>(table) + (size_t)l * T;
+    cell_rows(c, gr.mask, r);
+    const float4* base = reinterpret_cast<const float4*>(table) + (size_t)l * gr.T;
     float4 v[8];
 #pragma unroll
     for (int k = 0; k < 8; ++k) v[k] = ldg(base + r[k]);
-    float w = frcp(fmaxf(fmul(fmul(res[l], 2.0f), g.std), 1.0f));
+    float w = frcp(fmaxf(fmul(fmul(res, 2.0f), g.std), 1.0f));
     float f[8];
 #pragma unroll
     for (int k = 0; k < 8; ++k) f[k] = v[k].x;
-    out[4 * l + 0] = fmul(trilerp(f, c), w);
+    panel[4 * l + 0][ln] = fmul(trilerp(f, c), w);
 #pragma unroll
     for (int k = 0; k < 8; ++k) f[k] = v[k].y;
-    out[4 * l + 1] = fmul(trilerp(f, c), w);
+    panel[4 * l + 1][ln] = fmul(trilerp(f, c), w);
 #pragma unroll
     for (int k = 0; k < 8; ++k) f[k] = v[k].z;
-    out[4 * l + 2] = fmul(trilerp(f, c), w);
+    panel[4 * l + 2][ln] = fmul(trilerp(f, c), w);
 #pragma unroll
     for (int k = 0; k < 8; ++k) f[k] = v[k].w;
-    out[4 * l + 3] = fmul(trilerp(f, c), w);
+    panel[4 * l + 3][ln] = fmul(trilerp(f, c), w);
   }
 }
 
@@ -210,7 +216,7 @@ struct WarpShared {
   int32_t cand_id[kMaxCand];
   int32_t n_cand;
   int32_t overflow;
-  float feat_t[32][33];
+  float act[kNff + kSh][33];  // per-lane (column) activations of the current MLP layer; also the composite transpose
 };
 
 NFF_D void normalize3(float v[3]) {  // F.normalize: v / max(|v|, 1e-12)
@@ -334,23 +340,18 @@ NFF_D int actor_of_sample(const WarpShared& ws, const Gauss& g, float pb[3]) {
 NFF_D float proposal_density(const FieldGrids& fg, const WarpShared& ws, const Gauss& g, int* actor_id) {
   float pb[3];
   int c = actor_of_sample(ws, g, pb);
-  float feat[6];
-#pragma unroll
-  for (int i = 0; i < 6; ++i) feat[i] = 0.0f;
+  float acc;
   if (c >= 0) {
     Gauss ga = {pb[0], pb[1], pb[2], g.std};
     ga = contract(ga, fg.actor_scale);
-    const float* tab = fg.actor_tables[ws.cand_id[c]];
-    encode_f1<4>(tab, fg.act.mask, fg.act.T, fg.act.res, ga, feat);
+    // actor features occupy the first 4 of the 6 decoder inputs; the zero padding contributes nothing
+    acc = encode_f1_dot(fg.actor_tables[ws.cand_id[c]], fg.act, 4, ga, fg.decoder);
     *actor_id = ws.cand_id[c];
   } else {
     Gauss gs = contract(g, fg.static_scale);
-    encode_f1<6>(fg.stat.table, fg.stat.mask, fg.stat.T, fg.stat.res, gs, feat);
+    acc = encode_f1_dot(fg.stat.table, fg.stat, 6, gs, fg.decoder);
     *actor_id = -1;
   }
-  float acc = 0.0f;
-#pragma unroll
-  for (int i = 0; i < 6; ++i) acc = fmaf(feat[i], ldg(fg.decoder + i), acc);
   return expf(acc);
 }
 
@@ -376,6 +377,28 @@ NFF_D void dense(const float* NFF_RESTRICT W, const float* NFF_RESTRICT B, const
   }
 #pragma unroll
   for (int o = 0; o < OUT; ++o) y[o] = RELU ? fmaxf(acc[o], 0.0f) : acc[o];
+}
+
+// Same product, but the input row lives in the warp's shared-memory panel act[k][lane] and the k-loop stays rolled:
+// keeps the kernel small enough for the instruction cache (the fully unrolled form is ~27k SASS instructions and
+// stalls 40% of the time on instruction fetch, profiles/r01_ncu_render_v1.txt).
+template <int IN, int OUT, int OUTP>
+NFF_D void dense_panel(const float* NFF_RESTRICT W, const float* NFF_RESTRICT B, const float (*act)[33], float* acc) {
+  const int ln = lane();
+#pragma unroll
+  for (int o = 0; o < OUTP; ++o) acc[o] = o < OUT ? B[o] : 0.0f;
+#pragma unroll 2
+  for (int k = 0; k < IN; ++k) {
+    const float xk = act[k][ln];
+#pragma unroll
+    for (int o4 = 0; o4 < OUTP / 4; ++o4) {
+      const float4 w = *reinterpret_cast<const float4*>(W + k * OUTP + 4 * o4);
+      acc[4 * o4 + 0] = fmaf(xk, w.x, acc[4 * o4 + 0]);
+      acc[4 * o4 + 1] = fmaf(xk, w.y, acc[4 * o4 + 1]);
+      acc[4 * o4 + 2] = fmaf(xk, w.z, acc[4 * o4 + 2]);
+      acc[4 * o4 + 3] = fmaf(xk, w.w, acc[4 * o4 + 3]);
+    }
+  }
 }
 
 // components_from_spherical_harmonics(levels=4) (utils/math.py:31-94) on (d+1)/2 (fields/base_field.py:136-142)
@@ -405,64 +428,68 @@ NFF_D void sh4(float dx, float dy, float dz, float* c) {
 // --------------------------------------------------------------------------------- proposal round + resample
 // One proposal round for the warp's ray: densities (NeuRADProposalField.get_density) -> RaySamples.get_weights
 // (cameras/rays.py:188-210) -> prop depth (render_depth_simple, models/neurad.py:727-734) -> PDFSampler
-// (ray_samplers.py:309-361) producing S_NEW+1 new spacing-domain edges.
-// EdgeFn(i) returns the i-th spacing edge of the current level.
-template <int S, int S_NEW, class EdgeFn>
-NFF_D void proposal_round(const RenderParams& P, const FieldGrids& fg, WarpShared& ws, EdgeFn edge, const float o[3],
-                          const float d[3], float area, float s_near, float s_far, const float* NFF_RESTRICT u_tab,
-                          float* bins_out, int64_t ray, float* prop_depth, float* tr_w, int32_t* tr_aid,
-                          float* tr_bins_s, float* tr_bins_e, int32_t* tr_inds) {
-  constexpr int J = S / 32;
+// (ray_samplers.py:309-361) producing S_new+1 new spacing-domain edges.  `bins_in` holds the S+1 spacing edges of
+// the current level, `bins_out` receives the new ones (both in shared memory).  Chunks of 32 samples are a rolled
+// loop; per-sample weights are parked in ws.cdf[] between the two passes.
+struct RoundIO {
+  int S, S_new;
+  const float* u_tab;
+  const float* bins_in;
+  float* bins_out;
+  float* tr_w;
+  int32_t* tr_aid;
+  float* tr_bins_s;
+  float* tr_bins_e;
+  int32_t* tr_inds;
+};
+NFF_D float proposal_round(const RenderParams& P, const FieldGrids& fg, WarpShared& ws, const RoundIO& io,
+                           const float o[3], const float d[3], float area, float s_near, float s_far, int64_t ray) {
   const Sampling& sp = P.samp;
-  float w[J];
-  float carry = 0.0f, depth_acc = 0.0f;
-#pragma unroll
-  for (int j = 0; j < J; ++j) {
-    const int s = j * 32 + lane();
-    float e0 = to_euclid(edge(s), s_near, s_far, sp);
-    float e1 = to_euclid(edge(s + 1), s_near, s_far, sp);
+  const int S = io.S, S_new = io.S_new, ln = lane();
+  float carry = 0.0f, depth_acc = 0.0f, part = 0.0f;
+#pragma unroll 1
+  for (int s0 = 0; s0 < S; s0 += 32) {
+    const int s = s0 + ln;
+    float e0 = to_euclid(io.bins_in[s], s_near, s_far, sp);
+    float e1 = to_euclid(io.bins_in[s + 1], s_near, s_far, sp);
     Gauss g = sample_gaussian(o, d, area, e0, e1);
     int aid;
     float dens = proposal_density(fg, ws, g, &aid);
     float dd = fmul(fsub(e1, e0), dens);
     float incl = warp_scan_add(dd);
     float prev = shfl_up(incl, 1);
-    float excl = carry + (lane() == 0 ? 0.0f : prev);
+    float excl = carry + (ln == 0 ? 0.0f : prev);
     carry += shfl(incl, 31);
     float alpha = fsub(1.0f, expf(-dd));
     float T = expf(-excl);
     float wj = nan_to_num(fmul(alpha, T));
-    w[j] = wj;
     depth_acc = fadd(depth_acc, fmul(wj, fmul(fadd(e0, e1), 0.5f)));
-    if (tr_w) tr_w[ray * S + s] = wj;
-    if (tr_aid) tr_aid[ray * S + s] = aid;
+    if (io.tr_w) io.tr_w[ray * S + s] = wj;
+    if (io.tr_aid) io.tr_aid[ray * S + s] = aid;
+    wj = fadd(wj, sp.hist_pad);  // PDFSampler: histogram padding
+    ws.cdf[s + 1] = wj;
+    part += wj;
   }
-  *prop_depth = warp_sum(depth_acc);
-
-  // PDFSampler: histogram padding, normalise, cdf
-  float part = 0.0f;
-#pragma unroll
-  for (int j = 0; j < J; ++j) {
-    w[j] = fadd(w[j], sp.hist_pad);
-    part += w[j];
-  }
+  const float prop_depth = warp_sum(depth_acc);
   float tot = warp_sum(part);
-  float padding = fmaxf(fsub(1e-5f, tot), 0.0f);
-  float pad_each = fdiv(padding, (float)S);
+  const float padding = fmaxf(fsub(1e-5f, tot), 0.0f);
+  const float pad_each = fdiv(padding, (float)S);
   tot = fadd(tot, padding);
   carry = 0.0f;
-#pragma unroll
-  for (int j = 0; j < J; ++j) {
-    float pdf = fdiv(fadd(w[j], pad_each), tot);
+#pragma unroll 1
+  for (int s0 = 0; s0 < S; s0 += 32) {
+    const int s = s0 + ln;
+    float pdf = fdiv(fadd(ws.cdf[s + 1], pad_each), tot);
     float incl = warp_scan_add(pdf) + carry;
     carry = shfl(incl, 31);
-    ws.cdf[j * 32 + lane() + 1] = fminf(1.0f, incl);
+    ws.cdf[s + 1] = fminf(1.0f, incl);
   }
-  if (lane() == 0) ws.cdf[0] = 0.0f;
+  if (ln == 0) ws.cdf[0] = 0.0f;
   syncwarp();
   // inverse-cdf sampling: inds = searchsorted(cdf, u, side="right")
-  for (int i = lane(); i <= S_NEW; i += 32) {
-    float u = ldg(u_tab + i);
+#pragma unroll 1
+  for (int i = ln; i <= S_new; i += 32) {
+    float u = ldg(io.u_tab + i);
     int lo = 0, hi = S + 1;
     while (lo < hi) {
       int mid = (lo + hi) >> 1;
@@ -471,16 +498,17 @@ NFF_D void proposal_round(const RenderParams& P, const FieldGrids& fg, WarpShare
     int below = lo - 1 < 0 ? 0 : (lo - 1 > S ? S : lo - 1);
     int above = lo > S ? S : lo;
     float c0 = ws.cdf[below], c1 = ws.cdf[above];
-    float b0 = edge(below), b1 = edge(above);
+    float b0 = io.bins_in[below], b1 = io.bins_in[above];
     float t = nan_to_num(fdiv(fsub(u, c0), fsub(c1, c0)));
     t = fminf(fmaxf(t, 0.0f), 1.0f);
     float nb = fadd(b0, fmul(t, fsub(b1, b0)));
-    bins_out[i] = nb;
-    if (tr_inds) tr_inds[ray * (S_NEW + 1) + i] = lo;
-    if (tr_bins_s) tr_bins_s[ray * (S_NEW + 1) + i] = nb;
-    if (tr_bins_e) tr_bins_e[ray * (S_NEW + 1) + i] = to_euclid(nb, s_near, s_far, sp);
+    io.bins_out[i] = nb;
+    if (io.tr_inds) io.tr_inds[ray * (S_new + 1) + i] = lo;
+    if (io.tr_bins_s) io.tr_bins_s[ray * (S_new + 1) + i] = nb;
+    if (io.tr_bins_e) io.tr_bins_e[ray * (S_new + 1) + i] = to_euclid(nb, s_near, s_far, sp);
   }
   syncwarp();
+  return prop_depth;
 }
 
 // --------------------------------------------------------------------------------------- the whole ray
@@ -507,22 +535,26 @@ NFF_D void render_ray(const RenderParams& P, WarpShared& ws, const float* NFF_RE
 
   actor_candidates(P.actors, time, o, d, ws);
 
-  float prop_depth_0, prop_depth_1;
-  {
-    const FieldGrids& fg = P.fields[sp.field_of_round[0]];
-    auto edge0 = [](int i) { return linspace01(i, kS0); };
-    proposal_round<kS0, kS1>(P, fg, ws, edge0, o, d, area, s_near, s_far, sp.u1, ws.bins_b, ray, &prop_depth_0,
-                             P.trace.prop_weights_0, P.trace.actor_id_0, P.trace.bins_s_1, P.trace.bins_e_1,
-                             P.trace.inds_1);
+  // level-0 spacing bins: torch.linspace(0, 1, S0+1) (ray_samplers.py:102)
+  for (int i = ln; i <= kS0; i += 32) ws.bins_a[i] = linspace01(i, kS0);
+  syncwarp();
+  float prop_depth[2];
+#pragma unroll 1
+  for (int rd = 0; rd < 2; ++rd) {
+    RoundIO io;
+    io.S = rd == 0 ? kS0 : kS1;
+    io.S_new = rd == 0 ? kS1 : kS2;
+    io.u_tab = rd == 0 ? sp.u1 : sp.u2;
+    io.bins_in = rd == 0 ? ws.bins_a : ws.bins_b;
+    io.bins_out = rd == 0 ? ws.bins_b : ws.bins_a;
+    io.tr_w = rd == 0 ? P.trace.prop_weights_0 : P.trace.prop_weights_1;
+    io.tr_aid = rd == 0 ? P.trace.actor_id_0 : P.trace.actor_id_1;
+    io.tr_bins_s = rd == 0 ? P.trace.bins_s_1 : P.trace.bins_s_2;
+    io.tr_bins_e = rd == 0 ? P.trace.bins_e_1 : P.trace.bins_e_2;
+    io.tr_inds = rd == 0 ? P.trace.inds_1 : P.trace.inds_2;
+    prop_depth[rd] = proposal_round(P, P.fields[sp.field_of_round[rd]], ws, io, o, d, area, s_near, s_far, ray);
   }
-  {
-    const FieldGrids& fg = P.fields[sp.field_of_round[1]];
-    const float* bb = ws.bins_b;
-    auto edge1 = [bb](int i) { return bb[i]; };
-    proposal_round<kS1, kS2>(P, fg, ws, edge1, o, d, area, s_near, s_far, sp.u2, ws.bins_a, ray, &prop_depth_1,
-                             P.trace.prop_weights_1, P.trace.actor_id_1, P.trace.bins_s_2, P.trace.bins_e_2,
-                             P.trace.inds_2);
-  }
+  const float prop_depth_0 = prop_depth[0], prop_depth_1 = prop_depth[1];
 
   // ---- main field: one sample per lane (fields/neurad_field.py:128-152) ----
   float e0 = to_euclid(ws.bins_a[ln], s_near, s_far, sp);
@@ -530,7 +562,6 @@ NFF_D void render_ray(const RenderParams& P, WarpShared& ws, const float* NFF_RE
   if (ln == kS2 - 1) e1 = fadd(e1, fsub(sp.sky_distance, e1));  // sky sample (neurad.py:451-455)
   Gauss g = sample_gaussian(o, d, area, e0, e1);
   const FieldGrids& fm = P.fields[B200NERF_FIELD_MAIN];
-  float x[kNff + kSh];  // first the 32 grid features, later [geo_embedding | sh]
   float dir[3] = {d[0], d[1], d[2]};
   int aid = -1;
   {
@@ -541,8 +572,8 @@ NFF_D void render_ray(const RenderParams& P, WarpShared& ws, const float* NFF_RE
       Gauss ga = {pb[0], pb[1], pb[2], g.std};
       ga = contract(ga, fm.actor_scale);
 #pragma unroll
-      for (int i = 16; i < 32; ++i) x[i] = 0.0f;  // F.pad(actor_features, (0, 32-16))
-      encode_f4<4>(fm.actor_tables[aid], fm.act.mask, fm.act.T, fm.act.res, ga, x);
+      for (int i = 16; i < 32; ++i) ws.act[i][ln] = 0.0f;  // F.pad(actor_features, (0, 32-16))
+      encode_f4_panel(fm.actor_tables[aid], fm.act, 4, ga, ws.act);
       // direction into the box frame, renormalised with +EPS (neurad_encoding.py:203-209)
       const float* M = ws.w2b[c];
       float q0 = fadd(fadd(fmul(M[0], d[0]), fmul(M[1], d[1])), fmul(M[2], d[2]));
@@ -552,24 +583,38 @@ NFF_D void render_ray(const RenderParams& P, WarpShared& ws, const float* NFF_RE
       dir[0] = fdiv(q0, n); dir[1] = fdiv(q1, n); dir[2] = fdiv(q2, n);
     } else {
       Gauss gs = contract(g, fm.static_scale);
-      encode_f4<8>(fm.stat.table, fm.stat.mask, fm.stat.T, fm.stat.res, gs, x);
+      encode_f4_panel(fm.stat.table, fm.stat, 8, gs, ws.act);
     }
   }
-  float h[kHidden];
-  dense<kGeoIn, kHidden, kHidden, true>(mlp + kOffGeoW0, mlp + kOffGeoB0, x, h);
-  float go[kNff + 1];
-  dense<kHidden, kNff + 1, kGeoOutP, false>(mlp + kOffGeoW1, mlp + kOffGeoB1, h, go);
-  const float sdf = go[0];
+  // MLPs: activations go through the warp's shared panel (column = lane), accumulators stay in registers
+  float mac[kGeoOutP];
+  dense_panel<kGeoIn, kHidden, kHidden>(mlp + kOffGeoW0, mlp + kOffGeoB0, ws.act, mac);
 #pragma unroll
-  for (int i = 0; i < kNff; ++i) x[i] = go[i + 1];  // geo_embedding
-  sh4(dir[0], dir[1], dir[2], x + kNff);
-  dense<kNff + kSh, kHidden, kHidden, true>(mlp + kOffFeatW0, mlp + kOffFeatB0, x, h);
-  float h2[kHidden];
-  dense<kHidden, kHidden, kHidden, true>(mlp + kOffFeatW1, mlp + kOffFeatB1, h, h2);
-  dense<kHidden, kNff, kNff, false>(mlp + kOffFeatW2, mlp + kOffFeatB2, h2, h);
+  for (int i = 0; i < kHidden; ++i) ws.act[i][ln] = fmaxf(mac[i], 0.0f);
+  dense_panel<kHidden, kNff + 1, kGeoOutP>(mlp + kOffGeoW1, mlp + kOffGeoB1, ws.act, mac);
+  const float sdf = mac[0];
+  float geo[kNff];  // geo_embedding, kept for the residual
+#pragma unroll
+  for (int i = 0; i < kNff; ++i) {
+    geo[i] = mac[i + 1];
+    ws.act[i][ln] = geo[i];
+  }
+  {
+    float shv[kSh];
+    sh4(dir[0], dir[1], dir[2], shv);
+#pragma unroll
+    for (int i = 0; i < kSh; ++i) ws.act[kNff + i][ln] = shv[i];
+  }
+  dense_panel<kNff + kSh, kHidden, kHidden>(mlp + kOffFeatW0, mlp + kOffFeatB0, ws.act, mac);
+#pragma unroll
+  for (int i = 0; i < kHidden; ++i) ws.act[i][ln] = fmaxf(mac[i], 0.0f);
+  dense_panel<kHidden, kHidden, kHidden>(mlp + kOffFeatW1, mlp + kOffFeatB1, ws.act, mac);
+#pragma unroll
+  for (int i = 0; i < kHidden; ++i) ws.act[i][ln] = fmaxf(mac[i], 0.0f);
+  dense_panel<kHidden, kNff, kNff>(mlp + kOffFeatW2, mlp + kOffFeatB2, ws.act, mac);
   float feat[kNff];
 #pragma unroll
-  for (int i = 0; i < kNff; ++i) feat[i] = x[i] + h[i];  // residual (neurad_field.py:141)
+  for (int i = 0; i < kNff; ++i) feat[i] = geo[i] + mac[i];  // residual (neurad_field.py:141)
   // SigmoidDensity (model_components/utils.py:29-41): alpha = sigmoid(-sdf * beta)
   const float alpha = frcp(fadd(1.0f, expf(fmul(sdf, P.beta))));
 
@@ -595,11 +640,11 @@ NFF_D void render_ray(const RenderParams& P, WarpShared& ws, const float* NFF_RE
 
   // FeatureRenderer: sum_s w_s * feat_s (renderers.py:85) via a padded shared-memory transpose
 #pragma unroll
-  for (int i = 0; i < kNff; ++i) ws.feat_t[ln][i] = fmul(feat[i], w);
+  for (int i = 0; i < kNff; ++i) ws.act[i][ln] = fmul(feat[i], w);
   syncwarp();
   float fsum = 0.0f;
-#pragma unroll
-  for (int s = 0; s < kS2; ++s) fsum = fadd(fsum, ws.feat_t[s][ln]);
+#pragma unroll 8
+  for (int s = 0; s < kS2; ++s) fsum = fadd(fsum, ws.act[ln][s]);
   syncwarp();
 
   const int fdim = P.nff_dim + P.app.dim;
