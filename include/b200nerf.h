@@ -164,6 +164,19 @@ int b200nerf_hashgrid_fwd(b200nerf_ctx* ctx, const b200nerf_grid_desc* desc, con
 /* SHEncoding(levels=4).forward (encodings.py:797-805, utils/math.py:31-94): dirs [P,3] -> [P,16]. */
 int b200nerf_sh4_fwd(b200nerf_ctx* ctx, const float* dirs, float* out, int64_t n_points, void* stream);
 
+/* MLP.forward (field_components/mlp.py:142-183; the tcnn FullyFusedMLP role, mlp.py:103-113) for NeuRAD's tiny
+ * MLPs on the tcgen05 tensor cores with the 3xTF32 split (fp32-level accuracy): x [n_rows, in_dim] -> y [n_rows,
+ * out_dims[n_layers-1]]; ReLU between layers, none at the output.  `weights_host` / `biases_host` are HOST arrays
+ * of `n_layers` device pointers in nn.Linear layout ([out,in] / [out]; biases_host or its entries may be NULL).
+ * Limits: 1..3 layers, every width <= 48. */
+int b200nerf_mlp_fwd(b200nerf_ctx* ctx, const float* x, int64_t n_rows, int in_dim, int n_layers,
+                     const float* const* weights_host, const float* const* biases_host, const int* out_dims_host,
+                     float* y, void* stream);
+
+/* Synchronises with the device and reports (then clears) the device-side failure flag that kernels raise instead
+ * of hanging, e.g. when a tensor-core completion barrier times out.  0 = healthy. */
+int b200nerf_check_status(b200nerf_ctx* ctx);
+
 /* PDFSampler.generate_ray_samples, eval mode, include_original=False (ray_samplers.py:280-361):
  * weights [N,S], existing spacing bins [N,S+1], quantiles u [S_new+1] (device) -> new spacing bins
  * [N,S_new+1]; optional cdf [N,S+1] and searchsorted indices [N,S_new+1]. */

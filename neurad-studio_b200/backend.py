@@ -232,6 +232,9 @@ class B200Backend:
         table = self._dev(table)
         xs = self._dev(x).reshape(-1, 3)
         n = xs.shape[0]
+        if n == 0:
+            out = torch.empty(*x.shape[:-1], g.num_levels * g.hashgrid_dim, device=self.device)
+            return (out, torch.empty(*x.shape[:-1], g.num_levels, 8, device=self.device, dtype=torch.int32)) if want_indices else out
         out = torch.empty(n, g.num_levels * g.hashgrid_dim, device=self.device)
         idx = torch.empty(n, g.num_levels, 8, device=self.device, dtype=torch.int32) if want_indices else None
         self._check(self.lib.b200nerf_hashgrid_fwd(self._h, ctypes.byref(d), _ptr(table), _ptr(xs), _ptr(out), _ptr(idx), n, self._stream))
@@ -244,6 +247,25 @@ class B200Backend:
         out = torch.empty(d.shape[0], 16, device=self.device)
         self._check(self.lib.b200nerf_sh4_fwd(self._h, _ptr(d), _ptr(out), d.shape[0], self._stream))
         return out.reshape(*dirs.shape[:-1], 16)
+
+    def mlp_fwd(self, x: torch.Tensor, weights: Sequence[torch.Tensor], biases: Optional[Sequence[Optional[torch.Tensor]]] = None) -> torch.Tensor:
+        """MLP.forward (field_components/mlp.py:142-183) on the tcgen05 tensor cores (3xTF32): ReLU hidden
+        activations, no output activation.  weights[i] is nn.Linear's [out_i, in_i]."""
+        xs = self._dev(x).reshape(-1, x.shape[-1])
+        ws = [self._dev(w) for w in weights]
+        bs = [None if (biases is None or b is None) else self._dev(b) for b in (biases if biases is not None else [None] * len(ws))]
+        n, nl = xs.shape[0], len(ws)
+        out_dims = [w.shape[0] for w in ws]
+        y = torch.empty(n, out_dims[-1], device=self.device)
+        cw = (ctypes.c_void_p * nl)(*[w.data_ptr() for w in ws])
+        cb = (ctypes.c_void_p * nl)(*[(b.data_ptr() if b is not None else None) for b in bs])
+        co = (ctypes.c_int * nl)(*out_dims)
+        self._check(self.lib.b200nerf_mlp_fwd(self._h, _ptr(xs), n, xs.shape[1], nl, cw, cb, co, _ptr(y), self._stream))
+        return y.reshape(*x.shape[:-1], out_dims[-1])
+
+    def check_status(self):
+        """Raise if a kernel set the device-side failure flag (synchronises)."""
+        self._check(self.lib.b200nerf_check_status(self._h))
 
     def pdf_resample(self, weights: torch.Tensor, bins: torch.Tensor, num_samples: int, histogram_padding: float = 0.01):
         """PDFSampler (eval, include_original=False): weights [N,S], spacing bins [N,S+1] ->

@@ -9,6 +9,7 @@
 
 #include "../../include/b200nerf.h"
 #include "nff_device.h"
+#include "tc_mlp.cuh"
 
 using namespace nff;
 
@@ -49,6 +50,7 @@ struct b200nerf_ctx {
   Sampling samp{};
   bool have_samp = false;
   float *d_u1 = nullptr, *d_u2 = nullptr;
+  int* d_status = nullptr;
   int n_prop0 = 0, n_prop1 = 0, n_nerf = 0;
 };
 
@@ -260,6 +262,83 @@ __global__ void pack_linear_kernel(const float* __restrict__ w, const float* __r
   if (i < outp) dst_b[i] = (i < out_f && b) ? b[i] : 0.f;
 }
 
+
+// MLP.forward (field_components/mlp.py:142-183) for NeuRAD's tiny MLPs on the tensor cores: up to 3 Linear layers,
+// ReLU between them, in/out widths <= 48.  One CTA = one 128-row tile at a time (grid-stride), activations in TMEM,
+// weights in shared memory (see tc_mlp.cuh).
+struct MlpArgs {
+  const float* w[3];
+  const float* b[3];
+  int n_layers, in_dim;
+  int k_real[3], n_real[3], k_pad[3], n_pad[3];
+  int smem_off[3];  // float offsets of each layer's (hi) tile; lo follows at +n_pad*k_pad
+  int bias_off;
+};
+constexpr int kTcKMax = 48, kTcNMax = 48;
+__global__ void __launch_bounds__(128) mlp_tc_kernel(const MlpArgs a, const float* __restrict__ x, float* __restrict__ y,
+                                                     int64_t n_rows, int* __restrict__ status) {
+  extern __shared__ __align__(128) float sm_mlp[];
+  __shared__ uint32_t tmem_base_s;
+  __shared__ __align__(8) uint64_t bar;
+  using Cols = tc::TileCols<kTcKMax, kTcNMax>;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  for (int l = 0; l < a.n_layers; ++l) {
+    float* hi = sm_mlp + a.smem_off[l];
+    tc::stage_b_tile(hi, hi + a.n_pad[l] * a.k_pad[l], a.w[l], a.n_real[l], a.k_real[l], a.n_pad[l], a.k_pad[l], tid, 128);
+    for (int i = tid; i < kTcNMax; i += 128) sm_mlp[a.bias_off + l * kTcNMax + i] = (i < a.n_real[l] && a.b[l]) ? a.b[l][i] : 0.f;
+  }
+  tc::fence_async_smem();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
+  if (warp == 0) tc::tmem_alloc(&tmem_base_s, 256);
+  if (tid == 0) tc::mbar_init(&bar, 1);
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+  const uint32_t tmem_base = tmem_base_s;
+  const uint32_t lane_base = tmem_base + ((uint32_t)(32 * (warp & 3)) << 16);
+  uint32_t parity = 0;
+  const int out_dim = a.n_real[a.n_layers - 1];
+  for (int64_t tile = blockIdx.x; tile * 128 < n_rows; tile += gridDim.x) {
+    const int64_t row = tile * 128 + tid;
+    float v[kTcKMax];
+#pragma unroll
+    for (int k = 0; k < kTcKMax; ++k) v[k] = (row < n_rows && k < a.in_dim) ? x[row * a.in_dim + k] : 0.f;
+    for (int l = 0; l < a.n_layers; ++l) {
+      tc::store_a<kTcKMax>(lane_base, 0, v, a.k_pad[l]);
+      tc::wait_st();
+      tc::fence_before_sync();
+      __syncthreads();
+      if (tid == 0) {
+        tc::fence_after_sync();
+        const float* hi = sm_mlp + a.smem_off[l];
+        tc::issue_layer<kTcKMax>(tmem_base, Cols::d, hi, hi + a.n_pad[l] * a.k_pad[l], a.k_pad[l], a.n_pad[l], &bar);
+      }
+      if (!tc::mbar_wait(&bar, parity)) atomicExch(status, 1);
+      parity ^= 1u;
+      tc::fence_after_sync();
+      uint32_t d[kTcNMax];
+      tc::tmem_ld16(lane_base + Cols::d, d);
+      if (a.n_pad[l] > 16) tc::tmem_ld16(lane_base + Cols::d + 16, d + 16);
+      if (a.n_pad[l] > 32) tc::tmem_ld16(lane_base + Cols::d + 32, d + 32);
+      tc::wait_ld();
+      const float* bias = sm_mlp + a.bias_off + l * kTcNMax;
+      const bool last = l == a.n_layers - 1;
+#pragma unroll
+      for (int k = 0; k < kTcNMax; ++k) {
+        float o = k < a.n_pad[l] ? __uint_as_float(d[k]) + bias[k] : 0.f;
+        v[k] = last ? o : fmaxf(o, 0.f);
+      }
+    }
+    if (row < n_rows) {
+#pragma unroll
+      for (int k = 0; k < kTcNMax; ++k)
+        if (k < out_dim) y[row * out_dim + k] = v[k];
+    }
+  }
+  tc::fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tc::tmem_dealloc(tmem_base, 256);
+}
+
 // Cameras._generate_rays_from_coords, pinhole + rolling shutter (cameras/cameras.py:633-667,793-798,898-969)
 struct PinholeArgs {
   float c2w[12];
@@ -393,6 +472,7 @@ int b200nerf_destroy(b200nerf_ctx* c) {
   cudaFree(c->d_act_present);
   cudaFree(c->d_u1);
   cudaFree(c->d_u2);
+  cudaFree(c->d_status);
   delete c;
   return 0;
 }
@@ -611,6 +691,65 @@ int b200nerf_nff_render_fwd(b200nerf_ctx* c, const b200nerf_rays* rays, int64_t 
     lidar_decode_kernel<<<(unsigned)((n_rays + 127) / 128), 128, 0, st>>>(c->d_lidar_mlp, out->features, fdim, n_rays,
                                                                           out->intensity, out->ray_drop_logit);
     CUDA_TRY(cudaGetLastError());
+  }
+  return 0;
+}
+
+
+int b200nerf_mlp_fwd(b200nerf_ctx* c, const float* x, int64_t n_rows, int in_dim, int n_layers,
+                     const float* const* weights_host, const float* const* biases_host, const int* out_dims_host,
+                     float* y, void* stream) {
+  REQUIRE(c && weights_host && out_dims_host, "NULL argument");
+  REQUIRE(n_layers >= 1 && n_layers <= 3, "MLP depth must be 1..3 Linear layers");
+  REQUIRE(in_dim >= 1 && in_dim <= kTcKMax, "in_dim must be <= 48");
+  if (n_rows == 0) return 0;
+  REQUIRE(x && y, "NULL argument");
+  DeviceGuard g(c->device);
+  MlpArgs a{};
+  a.n_layers = n_layers;
+  a.in_dim = in_dim;
+  int k = in_dim, off = 0;
+  for (int l = 0; l < n_layers; ++l) {
+    int n = out_dims_host[l];
+    REQUIRE(n >= 1 && n <= kTcNMax, "layer widths must be <= 48");
+    REQUIRE(weights_host[l] != nullptr, "NULL weight");
+    a.w[l] = weights_host[l];
+    a.b[l] = biases_host ? biases_host[l] : nullptr;
+    a.k_real[l] = k;
+    a.n_real[l] = n;
+    a.k_pad[l] = (k + 7) / 8 * 8;
+    a.n_pad[l] = (n + 15) / 16 * 16;
+    a.smem_off[l] = off;
+    off += 2 * a.n_pad[l] * a.k_pad[l];
+    k = n;
+  }
+  a.bias_off = off;
+  size_t smem = sizeof(float) * (off + 3 * kTcNMax);
+  static bool attr_set = false;
+  if (!attr_set) {
+    CUDA_TRY(cudaFuncSetAttribute(mlp_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+    attr_set = true;
+  }
+  if (!c->d_status) {
+    CUDA_TRY(cudaMalloc((void**)&c->d_status, sizeof(int)));
+    CUDA_TRY(cudaMemset(c->d_status, 0, sizeof(int)));
+  }
+  int64_t tiles = (n_rows + 127) / 128;
+  int grid = (int)(tiles < (int64_t)c->sm_count * 2 ? tiles : (int64_t)c->sm_count * 2);
+  mlp_tc_kernel<<<grid, 128, smem, (cudaStream_t)stream>>>(a, x, y, n_rows, c->d_status);
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+int b200nerf_check_status(b200nerf_ctx* c) {
+  REQUIRE(c, "ctx is NULL");
+  if (!c->d_status) return 0;
+  DeviceGuard g(c->device);
+  int st = 0;
+  CUDA_TRY(cudaMemcpy(&st, c->d_status, sizeof(int), cudaMemcpyDeviceToHost));
+  if (st != 0) {
+    cudaMemset(c->d_status, 0, sizeof(int));
+    return fail(B200NERF_ERR_CUDA, "device-side failure flag set (tensor-core pipeline timed out, code " + std::to_string(st) + ")");
   }
   return 0;
 }

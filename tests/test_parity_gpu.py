@@ -288,3 +288,41 @@ def test_errors_are_loud(backend):
     fresh.load_params(cfg, scene.make_params(cfg))
     empty = {k: v[:0] for k, v in rays.items()}
     assert fresh.render(empty)["features"].shape[0] == 0
+
+
+# ---------------------------------------------------------------------------------------- tensor-core MLP (tcgen05)
+@pytest.mark.parametrize("dims", [(32, 32, 33), (48, 32, 32, 32), (48, 32, 32, 2), (32, 32), (40, 24, 17)])
+@pytest.mark.parametrize("n_rows", [1000, 128 * 300 + 5])
+def test_mlp_fwd_tensor_core_vs_fp32(backend, dims, n_rows):
+    """MLP.forward on tcgen05 with the 3xTF32 split vs a plain fp32 (float64-accumulated) reference of the same op:
+    NeuRAD's three MLP shapes (mlp_geo 32-32-33, mlp_feature 48-32-32-32, lidar_decoder 48-32-32-2)."""
+    gen = torch.Generator().manual_seed(sum(dims) + n_rows)
+    x = torch.randn(n_rows, dims[0], generator=gen)
+    ws, bs = [], []
+    for i in range(len(dims) - 1):
+        bound = 1.0 / dims[i] ** 0.5
+        ws.append((torch.rand(dims[i + 1], dims[i], generator=gen) * 2 - 1) * bound * 3)
+        bs.append((torch.rand(dims[i + 1], generator=gen) * 2 - 1) * bound)
+    y = backend.mlp_fwd(x, ws, bs)
+    backend.check_status()
+    h = x.double()
+    for i, (w, b) in enumerate(zip(ws, bs)):
+        h = h @ w.double().T + b.double()
+        if i < len(ws) - 1:
+            h = torch.relu(h)
+    err = rel_to_max(y, h.float())
+    assert err < 2e-6, err  # fp32-level: plain TF32 would be ~5e-4
+    # and against the oracle's torch fp32 MLP
+    p = {}
+    for i, (w, b) in enumerate(zip(ws, bs)):
+        p[f"m.layers.{i}.weight"], p[f"m.layers.{i}.bias"] = w, b
+    assert rel_to_max(y, O.mlp_forward(p, "m", len(ws), x)) < 2e-6
+
+
+def test_mlp_fwd_no_bias_and_empty(backend):
+    w = torch.randn(1, 6) * 0.4  # NeuRADProposalField.density_decoder = Linear(6, 1, bias=False)
+    x = torch.randn(777, 6)
+    y = backend.mlp_fwd(x, [w], None)
+    backend.check_status()
+    assert rel_to_max(y, x @ w.T) < 2e-6
+    assert backend.mlp_fwd(torch.zeros(0, 6), [w], None).shape == (0, 1)
