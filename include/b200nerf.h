@@ -173,6 +173,10 @@ int b200nerf_mlp_fwd(b200nerf_ctx* ctx, const float* x, int64_t n_rows, int in_d
                      const float* const* weights_host, const float* const* biases_host, const int* out_dims_host,
                      float* y, void* stream);
 
+/* Numerics mode of the main-field MLPs inside b200nerf_nff_render_fwd: 1 (default) = tcgen05 tensor cores with
+ * the 3xTF32 split (fp32-level accuracy, |err| ~1e-6 relative), 0 = CUDA-core fp32 FFMA. */
+int b200nerf_set_mlp_mode(b200nerf_ctx* ctx, int mode);
+
 /* Synchronises with the device and reports (then clears) the device-side failure flag that kernels raise instead
  * of hanging, e.g. when a tensor-core completion barrier times out.  0 = healthy. */
 int b200nerf_check_status(b200nerf_ctx* ctx);

@@ -263,6 +263,10 @@ class B200Backend:
         self._check(self.lib.b200nerf_mlp_fwd(self._h, _ptr(xs), n, xs.shape[1], nl, cw, cb, co, _ptr(y), self._stream))
         return y.reshape(*x.shape[:-1], out_dims[-1])
 
+    def set_mlp_mode(self, mode: str):
+        """'tc' (default): main-field MLPs on the tcgen05 tensor cores (3xTF32); 'ffma': CUDA-core fp32."""
+        self._check(self.lib.b200nerf_set_mlp_mode(self._h, {"ffma": 0, "tc": 1}[mode]))
+
     def check_status(self):
         """Raise if a kernel set the device-side failure flag (synchronises)."""
         self._check(self.lib.b200nerf_check_status(self._h))

@@ -9,7 +9,6 @@
 
 #include "../../include/b200nerf.h"
 #include "nff_device.h"
-#include "tc_mlp.cuh"
 
 using namespace nff;
 
@@ -38,6 +37,8 @@ struct b200nerf_ctx {
   const float** d_actor_tables[3] = {nullptr, nullptr, nullptr};
   float* d_decoder[3] = {nullptr, nullptr, nullptr};
   float* d_main_mlp = nullptr;
+  float* d_main_mlp_nn = nullptr;
+  int mlp_mode = 1;  // 1 = tcgen05 tensor cores (3xTF32), 0 = CUDA-core fp32 FFMA
   bool have_main_mlp = false;
   float beta = 0.f;
   float* d_lidar_mlp = nullptr;
@@ -81,17 +82,59 @@ int make_grid(const b200nerf_grid_desc* d, const float* table, Grid* g) {
 // =================================================================================================== kernels
 constexpr int kRenderWarps = 8;  // warps (= rays in flight) per CTA; 2 CTAs/SM -> 16 warps/SM at <=128 registers
 
+// CUDA-core MLP variant (exact fp32 FFMA): the reference/fallback numerics mode.
 template <int WARPS>
 __global__ void __launch_bounds__(WARPS * 32, 16 / WARPS) nff_render_kernel(const __grid_constant__ RenderParams P) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  float* mlp = reinterpret_cast<float*>(smem_raw);
+  float* mlp_s = reinterpret_cast<float*>(smem_raw);
   constexpr int kMlpBytes = (kMainMlpFloats * 4 + 15) / 16 * 16;
   WarpShared* ws = reinterpret_cast<WarpShared*>(smem_raw + kMlpBytes) + (threadIdx.x >> 5);
-  for (int i = threadIdx.x; i < kMainMlpFloats; i += WARPS * 32) mlp[i] = P.main_mlp[i];
+  for (int i = threadIdx.x; i < kMainMlpFloats; i += WARPS * 32) mlp_s[i] = P.main_mlp[i];
   __syncthreads();
+  MlpFfma mlp{mlp_s};
   const int64_t stride = (int64_t)gridDim.x * WARPS;
   for (int64_t ray = (int64_t)blockIdx.x * WARPS + (threadIdx.x >> 5); ray < P.n_rays; ray += stride)
-    render_ray(P, *ws, mlp, ray);
+    render_ray(P, *ws, mlp, ray, true);
+}
+
+// Tensor-core MLP variant (tcgen05 + TMEM, 3xTF32): each group of 4 warps forms one 128-row tile.
+using WarpSharedTc = WarpSharedT<kNff>;
+template <int WARPS>
+__global__ void __launch_bounds__(WARPS * 32, 16 / WARPS) nff_render_tc_kernel(const __grid_constant__ RenderParams P) {
+  static_assert(WARPS % 4 == 0 && WARPS <= 16, "warp groups of 4");
+  extern __shared__ __align__(128) unsigned char smem_tc[];
+  unsigned char* smem_raw = smem_tc;
+  TcShared* tcs = reinterpret_cast<TcShared*>(smem_raw);
+  constexpr int kTcBytes = (sizeof(TcShared) + 127) / 128 * 128;
+  const int warp = threadIdx.x >> 5, group = warp >> 2;
+  WarpSharedTc* ws = reinterpret_cast<WarpSharedTc*>(smem_raw + kTcBytes) + warp;
+  tc_stage_weights(*tcs, P.main_mlp_nn, threadIdx.x, WARPS * 32);
+  tc::fence_async_smem();
+  constexpr uint32_t kCols = kTcTileCols * (WARPS / 4);
+  if (warp == 0) tc::tmem_alloc(&tcs->tmem_base, kCols);
+  if (threadIdx.x == 0)
+    for (int g = 0; g < WARPS / 4; ++g) tc::mbar_init(&tcs->bar[g], 1);
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+  MlpTc mlp;
+  mlp.t = tcs;
+  mlp.tile_base = tcs->tmem_base + (uint32_t)(group * kTcTileCols);
+  mlp.lane_base = mlp.tile_base + ((uint32_t)(32 * (warp & 3)) << 16);
+  mlp.bar = &tcs->bar[group];
+  mlp.parity = 0;
+  mlp.bar_id = 1 + group;
+  mlp.issuer = (threadIdx.x & 127) == 0;
+  mlp.status = P.status;
+  const int64_t stride = (int64_t)gridDim.x * WARPS;
+  for (int64_t base = (int64_t)blockIdx.x * WARPS; base < P.n_rays; base += stride) {
+    const int64_t ray = base + warp;
+    const bool active = ray < P.n_rays;
+    render_ray(P, *ws, mlp, active ? ray : P.n_rays - 1, active);
+  }
+  tc::fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tc::tmem_dealloc(tcs->tmem_base, kCols);
 }
 
 // NeuRADModel.decode_features, lidar half (models/neurad.py:350-357): one thread per ray.
@@ -452,6 +495,10 @@ int b200nerf_create(int device_ordinal, b200nerf_ctx** out) {
   c->sm_count = prop.multiProcessorCount;
   CUDA_TRY(cudaFuncSetAttribute(nff_render_kernel<kRenderWarps>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 (int)((kMainMlpFloats * 4 + 15) / 16 * 16 + kRenderWarps * sizeof(WarpShared))));
+  CUDA_TRY(cudaFuncSetAttribute(nff_render_tc_kernel<kRenderWarps>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)((sizeof(TcShared) + 127) / 128 * 128 + kRenderWarps * sizeof(WarpSharedTc))));
+  CUDA_TRY(cudaMalloc((void**)&c->d_status, sizeof(int)));
+  CUDA_TRY(cudaMemset(c->d_status, 0, sizeof(int)));
   *out = c;
   return 0;
 }
@@ -464,6 +511,7 @@ int b200nerf_destroy(b200nerf_ctx* c) {
     cudaFree(c->d_decoder[i]);
   }
   cudaFree(c->d_main_mlp);
+  cudaFree(c->d_main_mlp_nn);
   cudaFree(c->d_lidar_mlp);
   cudaFree(c->d_act_times);
   cudaFree(c->d_act_kf);
@@ -541,6 +589,16 @@ int b200nerf_set_main_mlps(b200nerf_ctx* c, const float* gw0, const float* gb0, 
   if (int e = pack(fw0, fb0, kHidden, kNff + kSh, kHidden, m + kOffFeatW0, m + kOffFeatB0)) return e;
   if (int e = pack(fw1, fb1, kHidden, kHidden, kHidden, m + kOffFeatW1, m + kOffFeatB1)) return e;
   if (int e = pack(fw2, fb2, kNff, kHidden, kNff, m + kOffFeatW2, m + kOffFeatB2)) return e;
+  if (!c->d_main_mlp_nn) CUDA_TRY(cudaMalloc((void**)&c->d_main_mlp_nn, sizeof(float) * kNnMlpFloats));
+  {
+    float* n = c->d_main_mlp_nn;
+    const float* src[10] = {gw0, gb0, gw1, gb1, fw0, fb0, fw1, fb1, fw2, fb2};
+    const int off[10] = {kNnGeoW0, kNnGeoB0, kNnGeoW1, kNnGeoB1, kNnFeatW0, kNnFeatB0, kNnFeatW1, kNnFeatB1, kNnFeatW2, kNnFeatB2};
+    const int cnt[10] = {kHidden * kGeoIn, kHidden, (kNff + 1) * kHidden, kNff + 1, kHidden * (kNff + kSh), kHidden,
+                         kHidden * kHidden, kHidden, kNff * kHidden, kNff};
+    for (int i = 0; i < 10; ++i)
+      CUDA_TRY(cudaMemcpy(n + off[i], src[i], sizeof(float) * cnt[i], cudaMemcpyDeviceToDevice));
+  }
   CUDA_TRY(cudaDeviceSynchronize());
   c->beta = beta;
   c->have_main_mlp = true;
@@ -668,6 +726,8 @@ int b200nerf_nff_render_fwd(b200nerf_ctx* c, const b200nerf_rays* rays, int64_t 
   RenderParams P{};
   for (int i = 0; i < 3; ++i) P.fields[i] = c->fields[i];
   P.main_mlp = c->d_main_mlp;
+  P.main_mlp_nn = c->d_main_mlp_nn;
+  P.status = c->d_status;
   P.lidar_mlp = c->d_lidar_mlp;
   P.beta = c->beta;
   P.nff_dim = kNff;
@@ -679,12 +739,17 @@ int b200nerf_nff_render_fwd(b200nerf_ctx* c, const b200nerf_rays* rays, int64_t 
   if (trace) P.trace = *trace;
   P.n_rays = n_rays;
   constexpr int WARPS = kRenderWarps;
-  const size_t smem = (kMainMlpFloats * 4 + 15) / 16 * 16 + WARPS * sizeof(WarpShared);
   int64_t blocks_needed = (n_rays + WARPS - 1) / WARPS;
   int64_t max_blocks = (int64_t)c->sm_count * (16 / WARPS);  // persistent: resident CTAs only, grid-stride over rays
   int blocks = (int)(blocks_needed < max_blocks ? blocks_needed : max_blocks);
   cudaStream_t st = (cudaStream_t)stream;
-  nff_render_kernel<WARPS><<<blocks, WARPS * 32, smem, st>>>(P);
+  if (c->mlp_mode == 1) {
+    const size_t smem = (sizeof(TcShared) + 127) / 128 * 128 + WARPS * sizeof(WarpSharedTc);
+    nff_render_tc_kernel<WARPS><<<blocks, WARPS * 32, smem, st>>>(P);
+  } else {
+    const size_t smem = (kMainMlpFloats * 4 + 15) / 16 * 16 + WARPS * sizeof(WarpShared);
+    nff_render_kernel<WARPS><<<blocks, WARPS * 32, smem, st>>>(P);
+  }
   CUDA_TRY(cudaGetLastError());
   if (out->intensity || out->ray_drop_logit) {
     int fdim = kNff + c->app.dim;
@@ -730,14 +795,17 @@ int b200nerf_mlp_fwd(b200nerf_ctx* c, const float* x, int64_t n_rows, int in_dim
     CUDA_TRY(cudaFuncSetAttribute(mlp_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
     attr_set = true;
   }
-  if (!c->d_status) {
-    CUDA_TRY(cudaMalloc((void**)&c->d_status, sizeof(int)));
-    CUDA_TRY(cudaMemset(c->d_status, 0, sizeof(int)));
-  }
   int64_t tiles = (n_rows + 127) / 128;
   int grid = (int)(tiles < (int64_t)c->sm_count * 2 ? tiles : (int64_t)c->sm_count * 2);
   mlp_tc_kernel<<<grid, 128, smem, (cudaStream_t)stream>>>(a, x, y, n_rows, c->d_status);
   CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+int b200nerf_set_mlp_mode(b200nerf_ctx* c, int mode) {
+  REQUIRE(c, "ctx is NULL");
+  REQUIRE(mode == 0 || mode == 1, "mlp mode: 0 = CUDA-core fp32 FFMA, 1 = tcgen05 3xTF32");
+  c->mlp_mode = mode;
   return 0;
 }
 

@@ -207,7 +207,8 @@ NFF_D void encode_f4_panel(const float* NFF_RESTRICT table, const Grid& gr, int 
 
 // ------------------------------------------------------------------------------------------------ actors
 // Per-warp shared state.  One warp == one ray.
-struct WarpShared {
+template <int ACT_ROWS>
+struct WarpSharedT {
   float cdf[kS0 + 4];
   float bins_a[kS0 + 4];
   float bins_b[kS1 + 4];
@@ -216,8 +217,9 @@ struct WarpShared {
   int32_t cand_id[kMaxCand];
   int32_t n_cand;
   int32_t overflow;
-  float act[kNff + kSh][33];  // per-lane (column) activations of the current MLP layer; also the composite transpose
+  float act[ACT_ROWS][33];  // per-lane (column) grid features / MLP activations; also the composite transpose
 };
+using WarpShared = WarpSharedT<kNff + kSh>;  // CUDA-core MLP path (and the host emulation)
 
 NFF_D void normalize3(float v[3]) {  // F.normalize: v / max(|v|, 1e-12)
   float n = fsqrt(fadd(fadd(fmul(v[0], v[0]), fmul(v[1], v[1])), fmul(v[2], v[2])));
@@ -232,7 +234,8 @@ NFF_D void normalize3(float v[3]) {  // F.normalize: v / max(|v|, 1e-12)
 // (utils/poses.py:42-55), followed by the ray-line culling of NeuRADHashEncoding._get_actor_indices
 // (field_components/neurad_encoding.py:225-240).  Lanes stride over actors; survivors are compacted, in
 // increasing actor order, into the warp's candidate list.
-NFF_D void actor_candidates(const Actors& A, float time, const float o[3], const float d[3], WarpShared& ws) {
+template <class WS>
+NFF_D void actor_candidates(const Actors& A, float time, const float o[3], const float d[3], WS& ws) {
   if (lane() == 0) {
     ws.n_cand = 0;
     ws.overflow = 0;
@@ -318,7 +321,8 @@ NFF_D void actor_candidates(const Actors& A, float time, const float o[3], const
 // The per-sample part of _get_actor_indices (neurad_encoding.py:241-254): is the sample mean inside a padded
 // box?  Returns the candidate slot (highest actor index wins, matching the reference's sequential index_put on
 // CPU) or -1; `pb` receives the position in the box frame.
-NFF_D int actor_of_sample(const WarpShared& ws, const Gauss& g, float pb[3]) {
+template <class WS>
+NFF_D int actor_of_sample(const WS& ws, const Gauss& g, float pb[3]) {
   int hit = -1;
   int n = ws.n_cand;
   for (int c = 0; c < n; ++c) {
@@ -337,7 +341,8 @@ NFF_D int actor_of_sample(const WarpShared& ws, const Gauss& g, float pb[3]) {
 // ------------------------------------------------------------------------------------- proposal density
 // NeuRADProposalField.get_density (fields/neurad_field.py:208-213) for one sample:
 // NeuRADHashEncoding.forward (static grid, or the containing actor's grid zero-padded) -> Linear(6,1) -> exp.
-NFF_D float proposal_density(const FieldGrids& fg, const WarpShared& ws, const Gauss& g, int* actor_id) {
+template <class WS>
+NFF_D float proposal_density(const FieldGrids& fg, const WS& ws, const Gauss& g, int* actor_id) {
   float pb[3];
   int c = actor_of_sample(ws, g, pb);
   float acc;
@@ -442,7 +447,8 @@ struct RoundIO {
   float* tr_bins_e;
   int32_t* tr_inds;
 };
-NFF_D float proposal_round(const RenderParams& P, const FieldGrids& fg, WarpShared& ws, const RoundIO& io,
+template <class WS>
+NFF_D float proposal_round(const RenderParams& P, const FieldGrids& fg, WS& ws, const RoundIO& io,
                            const float o[3], const float d[3], float area, float s_near, float s_far, int64_t ray) {
   const Sampling& sp = P.samp;
   const int S = io.S, S_new = io.S_new, ln = lane();
@@ -511,10 +517,154 @@ NFF_D float proposal_round(const RenderParams& P, const FieldGrids& fg, WarpShar
   return prop_depth;
 }
 
+// ------------------------------------------------------------------------------------ main-field MLP policies
+// NeuRADField.forward after the grid lookup (fields/neurad_field.py:138-142): mlp_geo -> (sdf | geo_embedding),
+// SH(dir), feature = geo_embedding + mlp_feature([geo_embedding, sh]).  Input: this lane's 32 grid features in
+// ws.act[0..31][lane].
+//
+// CUDA-core path: fp32 FFMA, weights transposed in shared memory (exact-fp32 reference mode; also what the host
+// emulation runs).
+struct MlpFfma {
+  const float* w;  // packed (nff_params.h), in shared memory
+  template <class WS>
+  NFF_D void run(WS& ws, const float dir[3], float& sdf, float* feat) const {
+    const int ln = lane();
+    const float* mlp = w;
+    float mac[kGeoOutP];
+    dense_panel<kGeoIn, kHidden, kHidden>(mlp + kOffGeoW0, mlp + kOffGeoB0, ws.act, mac);
+#pragma unroll
+    for (int i = 0; i < kHidden; ++i) ws.act[i][ln] = fmaxf(mac[i], 0.0f);
+    dense_panel<kHidden, kNff + 1, kGeoOutP>(mlp + kOffGeoW1, mlp + kOffGeoB1, ws.act, mac);
+    sdf = mac[0];
+    float geo[kNff];  // geo_embedding, kept for the residual
+#pragma unroll
+    for (int i = 0; i < kNff; ++i) {
+      geo[i] = mac[i + 1];
+      ws.act[i][ln] = geo[i];
+    }
+    {
+      float shv[kSh];
+      sh4(dir[0], dir[1], dir[2], shv);
+#pragma unroll
+      for (int i = 0; i < kSh; ++i) ws.act[kNff + i][ln] = shv[i];
+    }
+    dense_panel<kNff + kSh, kHidden, kHidden>(mlp + kOffFeatW0, mlp + kOffFeatB0, ws.act, mac);
+#pragma unroll
+    for (int i = 0; i < kHidden; ++i) ws.act[i][ln] = fmaxf(mac[i], 0.0f);
+    dense_panel<kHidden, kHidden, kHidden>(mlp + kOffFeatW1, mlp + kOffFeatB1, ws.act, mac);
+#pragma unroll
+    for (int i = 0; i < kHidden; ++i) ws.act[i][ln] = fmaxf(mac[i], 0.0f);
+    dense_panel<kHidden, kNff, kNff>(mlp + kOffFeatW2, mlp + kOffFeatB2, ws.act, mac);
+#pragma unroll
+    for (int i = 0; i < kNff; ++i) feat[i] = geo[i] + mac[i];  // residual (neurad_field.py:141)
+  }
+};
+
+#if defined(__CUDACC__)
+}  // namespace nff
+#include "tc_mlp.cuh"
+namespace nff {
+// Tensor-core path: a tile = the 4 warps (4 rays x 32 samples = 128 rows) of one warp group; activations live in
+// TMEM (columns [A_hi 48 | A_lo 48 | D 32] per tile), weights are tcgen05 B tiles in shared memory, every layer is
+// 3 x (K/8) tcgen05.mma (3xTF32 split, fp32-level accuracy) issued by the group's first thread.  The sdf neuron
+// (row 0 of mlp_geo's last layer) is one 32-term dot product on the CUDA cores so that all tensor-core layers have
+// N = 32 and a tile needs only 128 TMEM columns.
+constexpr int kTcLayers = 5;
+constexpr int kTcTileCols = 128;
+struct TcShared {
+  float b[2 * 32 * (32 + 32 + 48 + 32 + 32)];  // hi|lo B tiles of the 5 layers (45 KB)
+  float bias[kTcLayers][32];
+  float w_sdf[32];
+  float b_sdf;
+  uint32_t tmem_base;
+  uint64_t bar[4];
+};
+NFF_D constexpr int tc_layer_k(int l) { return l == 2 ? 48 : 32; }
+NFF_D constexpr int tc_layer_off(int l) { return l == 0 ? 0 : l == 1 ? 2048 : l == 2 ? 4096 : l == 3 ? 7168 : 9216; }
+
+// cooperative (whole CTA): build the B tiles from the nn.Linear-layout weights in global memory
+NFF_D void tc_stage_weights(TcShared& t, const float* NFF_RESTRICT nn, int tid, int nthreads) {
+  const int w_off[kTcLayers] = {kNnGeoW0, kNnGeoW1 + kHidden /* rows 1..32 */, kNnFeatW0, kNnFeatW1, kNnFeatW2};
+  const int b_off[kTcLayers] = {kNnGeoB0, kNnGeoB1 + 1, kNnFeatB0, kNnFeatB1, kNnFeatB2};
+#pragma unroll
+  for (int l = 0; l < kTcLayers; ++l) {
+    const int K = tc_layer_k(l);
+    float* hi = t.b + tc_layer_off(l);
+    tc::stage_b_tile(hi, hi + 32 * K, nn + w_off[l], 32, K, 32, K, tid, nthreads);
+    for (int i = tid; i < 32; i += nthreads) t.bias[l][i] = nn[b_off[l] + i];
+  }
+  for (int i = tid; i < 32; i += nthreads) t.w_sdf[i] = nn[kNnGeoW1 + i];
+  if (tid == 0) t.b_sdf = nn[kNnGeoB1];
+}
+
+struct MlpTc {
+  const TcShared* t;
+  uint32_t tile_base;  // TMEM address of the tile's first column (lane 0)
+  uint32_t lane_base;  // same, at this warp's lane quarter
+  uint64_t* bar;
+  uint32_t parity;
+  int bar_id;
+  bool issuer;
+  int* status;
+
+  // store K activations of this thread's row, run layer l on the tensor cores, fetch the 32 outputs
+  template <int K>
+  NFF_D void layer(int l, const float* x, float* out) {
+    tc::store_a<48>(lane_base, 0, x, K);
+    tc::wait_st();
+    tc::fence_before_sync();
+    asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
+    if (issuer) {
+      tc::fence_after_sync();
+      const float* hi = t->b + tc_layer_off(l);
+      tc::issue_layer<48>(tile_base, 96, hi, hi + 32 * K, K, 32, bar);
+    }
+    if (!tc::mbar_wait(bar, parity) && status) atomicExch(status, 2);
+    parity ^= 1u;
+    tc::fence_after_sync();
+    uint32_t d[32];
+    tc::tmem_ld16(lane_base + 96, d);
+    tc::tmem_ld16(lane_base + 112, d + 16);
+    tc::wait_ld();
+#pragma unroll
+    for (int i = 0; i < 32; ++i) out[i] = __uint_as_float(d[i]) + t->bias[l][i];
+  }
+
+  template <class WS>
+  NFF_D void run(WS& ws, const float dir[3], float& sdf, float* feat) {
+    const int ln = lane();
+    float x[kNff + kSh], h[kHidden];
+#pragma unroll
+    for (int i = 0; i < kGeoIn; ++i) x[i] = ws.act[i][ln];
+    layer<32>(0, x, h);
+    float s = t->b_sdf;
+#pragma unroll
+    for (int i = 0; i < kHidden; ++i) {
+      h[i] = fmaxf(h[i], 0.0f);
+      s = fmaf(h[i], t->w_sdf[i], s);
+    }
+    sdf = s;
+    layer<32>(1, h, x);  // x[0..31] = geo_embedding (kept for the residual)
+    sh4(dir[0], dir[1], dir[2], x + kNff);
+    layer<48>(2, x, h);
+#pragma unroll
+    for (int i = 0; i < kHidden; ++i) h[i] = fmaxf(h[i], 0.0f);
+    float h2[kHidden];
+    layer<32>(3, h, h2);
+#pragma unroll
+    for (int i = 0; i < kHidden; ++i) h2[i] = fmaxf(h2[i], 0.0f);
+    layer<32>(4, h2, h);
+#pragma unroll
+    for (int i = 0; i < kNff; ++i) feat[i] = x[i] + h[i];
+  }
+};
+#endif  // __CUDACC__
+
 // --------------------------------------------------------------------------------------- the whole ray
-// NeuRADModel.get_nff_outputs (models/neurad.py:368-421), eval mode.  `mlp` points at the packed main-field
-// weights in shared memory.
-NFF_D void render_ray(const RenderParams& P, WarpShared& ws, const float* NFF_RESTRICT mlp, int64_t ray) {
+// NeuRADModel.get_nff_outputs (models/neurad.py:368-421), eval mode.  `active == false` renders a (clamped, valid)
+// ray without storing anything: warps of a tensor-core tile must all take part in the tile's barriers.
+template <class WS, class Mlp>
+NFF_D void render_ray(const RenderParams& P, WS& ws, Mlp& mlp, int64_t ray, bool active) {
   const Sampling& sp = P.samp;
   const int ln = lane();
   float o[3], d[3];
@@ -547,11 +697,11 @@ NFF_D void render_ray(const RenderParams& P, WarpShared& ws, const float* NFF_RE
     io.u_tab = rd == 0 ? sp.u1 : sp.u2;
     io.bins_in = rd == 0 ? ws.bins_a : ws.bins_b;
     io.bins_out = rd == 0 ? ws.bins_b : ws.bins_a;
-    io.tr_w = rd == 0 ? P.trace.prop_weights_0 : P.trace.prop_weights_1;
-    io.tr_aid = rd == 0 ? P.trace.actor_id_0 : P.trace.actor_id_1;
-    io.tr_bins_s = rd == 0 ? P.trace.bins_s_1 : P.trace.bins_s_2;
-    io.tr_bins_e = rd == 0 ? P.trace.bins_e_1 : P.trace.bins_e_2;
-    io.tr_inds = rd == 0 ? P.trace.inds_1 : P.trace.inds_2;
+    io.tr_w = !active ? nullptr : rd == 0 ? P.trace.prop_weights_0 : P.trace.prop_weights_1;
+    io.tr_aid = !active ? nullptr : rd == 0 ? P.trace.actor_id_0 : P.trace.actor_id_1;
+    io.tr_bins_s = !active ? nullptr : rd == 0 ? P.trace.bins_s_1 : P.trace.bins_s_2;
+    io.tr_bins_e = !active ? nullptr : rd == 0 ? P.trace.bins_e_1 : P.trace.bins_e_2;
+    io.tr_inds = !active ? nullptr : rd == 0 ? P.trace.inds_1 : P.trace.inds_2;
     prop_depth[rd] = proposal_round(P, P.fields[sp.field_of_round[rd]], ws, io, o, d, area, s_near, s_far, ray);
   }
   const float prop_depth_0 = prop_depth[0], prop_depth_1 = prop_depth[1];
@@ -586,35 +736,9 @@ NFF_D void render_ray(const RenderParams& P, WarpShared& ws, const float* NFF_RE
       encode_f4_panel(fm.stat.table, fm.stat, 8, gs, ws.act);
     }
   }
-  // MLPs: activations go through the warp's shared panel (column = lane), accumulators stay in registers
-  float mac[kGeoOutP];
-  dense_panel<kGeoIn, kHidden, kHidden>(mlp + kOffGeoW0, mlp + kOffGeoB0, ws.act, mac);
-#pragma unroll
-  for (int i = 0; i < kHidden; ++i) ws.act[i][ln] = fmaxf(mac[i], 0.0f);
-  dense_panel<kHidden, kNff + 1, kGeoOutP>(mlp + kOffGeoW1, mlp + kOffGeoB1, ws.act, mac);
-  const float sdf = mac[0];
-  float geo[kNff];  // geo_embedding, kept for the residual
-#pragma unroll
-  for (int i = 0; i < kNff; ++i) {
-    geo[i] = mac[i + 1];
-    ws.act[i][ln] = geo[i];
-  }
-  {
-    float shv[kSh];
-    sh4(dir[0], dir[1], dir[2], shv);
-#pragma unroll
-    for (int i = 0; i < kSh; ++i) ws.act[kNff + i][ln] = shv[i];
-  }
-  dense_panel<kNff + kSh, kHidden, kHidden>(mlp + kOffFeatW0, mlp + kOffFeatB0, ws.act, mac);
-#pragma unroll
-  for (int i = 0; i < kHidden; ++i) ws.act[i][ln] = fmaxf(mac[i], 0.0f);
-  dense_panel<kHidden, kHidden, kHidden>(mlp + kOffFeatW1, mlp + kOffFeatB1, ws.act, mac);
-#pragma unroll
-  for (int i = 0; i < kHidden; ++i) ws.act[i][ln] = fmaxf(mac[i], 0.0f);
-  dense_panel<kHidden, kNff, kNff>(mlp + kOffFeatW2, mlp + kOffFeatB2, ws.act, mac);
-  float feat[kNff];
-#pragma unroll
-  for (int i = 0; i < kNff; ++i) feat[i] = geo[i] + mac[i];  // residual (neurad_field.py:141)
+  syncwarp();
+  float sdf, feat[kNff];
+  mlp.run(ws, dir, sdf, feat);
   // SigmoidDensity (model_components/utils.py:29-41): alpha = sigmoid(-sdf * beta)
   const float alpha = frcp(fadd(1.0f, expf(fmul(sdf, P.beta))));
 
@@ -629,11 +753,11 @@ NFF_D void render_ray(const RenderParams& P, WarpShared& ws, const float* NFF_RE
   const float depth = warp_sum(dterm);
   if (ln == kS2 - 1) w = fadd(fadd(w, 1.0f), -acc);  // remaining accumulation onto the sky sample (neurad.py:381)
 
-  if (P.trace.sdf) P.trace.sdf[ray * kS2 + ln] = sdf;
-  if (P.trace.alpha) P.trace.alpha[ray * kS2 + ln] = alpha;
-  if (P.trace.weights) P.trace.weights[ray * kS2 + ln] = w;
-  if (P.trace.actor_id_main) P.trace.actor_id_main[ray * kS2 + ln] = aid;
-  if (P.trace.field_feature) {
+  if (active && P.trace.sdf) P.trace.sdf[ray * kS2 + ln] = sdf;
+  if (active && P.trace.alpha) P.trace.alpha[ray * kS2 + ln] = alpha;
+  if (active && P.trace.weights) P.trace.weights[ray * kS2 + ln] = w;
+  if (active && P.trace.actor_id_main) P.trace.actor_id_main[ray * kS2 + ln] = aid;
+  if (active && P.trace.field_feature) {
 #pragma unroll
     for (int i = 0; i < kNff; ++i) P.trace.field_feature[(ray * kS2 + ln) * kNff + i] = feat[i];
   }
@@ -647,6 +771,7 @@ NFF_D void render_ray(const RenderParams& P, WarpShared& ws, const float* NFF_RE
   for (int s = 0; s < kS2; ++s) fsum = fadd(fsum, ws.act[ln][s]);
   syncwarp();
 
+  if (!active) return;
   const int fdim = P.nff_dim + P.app.dim;
   float* fo = P.out.features + ray * fdim;
   fo[ln] = fsum;

@@ -42,6 +42,19 @@ constexpr int kOffLidW2 = kOffLidB1 + kHidden;                 // [32][4]
 constexpr int kOffLidB2 = kOffLidW2 + kHidden * kLidOutP;
 constexpr int kLidarMlpFloats = kOffLidB2 + kLidOutP;
 
+// main-field MLP in nn.Linear ([out,in]) layout, the source for the tensor-core B tiles
+constexpr int kNnGeoW0 = 0;
+constexpr int kNnGeoB0 = kNnGeoW0 + kHidden * kGeoIn;
+constexpr int kNnGeoW1 = kNnGeoB0 + kHidden;          // [33][32]: row 0 = sdf, rows 1..32 = geo_embedding
+constexpr int kNnGeoB1 = kNnGeoW1 + (kNff + 1) * kHidden;
+constexpr int kNnFeatW0 = kNnGeoB1 + (kNff + 1);      // [32][48]
+constexpr int kNnFeatB0 = kNnFeatW0 + kHidden * (kNff + kSh);
+constexpr int kNnFeatW1 = kNnFeatB0 + kHidden;
+constexpr int kNnFeatB1 = kNnFeatW1 + kHidden * kHidden;
+constexpr int kNnFeatW2 = kNnFeatB1 + kHidden;
+constexpr int kNnFeatB2 = kNnFeatW2 + kNff * kHidden;
+constexpr int kNnMlpFloats = kNnFeatB2 + kNff;
+
 struct Grid {
   const float* table;  // [L*T, F]
   uint32_t mask;       // T-1
@@ -84,7 +97,9 @@ struct Appearance {
 struct RenderParams {
   FieldGrids fields[3];
   const float* main_mlp;   // packed (kMainMlpFloats)
+  const float* main_mlp_nn;  // nn.Linear layout (kNnMlpFloats), source of the tensor-core B tiles
   const float* lidar_mlp;  // packed (kLidarMlpFloats) or nullptr
+  int* status;             // device-side failure flag (tensor-core barrier timeout)
   float beta;
   int32_t nff_dim;
   Actors actors;

@@ -62,6 +62,7 @@ SIGNATURES = {
     "b200nerf_mlp_fwd": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int, POINTER(c_void_p), POINTER(c_void_p),
                                  POINTER(c_int), c_void_p, c_void_p]),
     "b200nerf_check_status": (c_int, [c_void_p]),
+    "b200nerf_set_mlp_mode": (c_int, [c_void_p, c_int]),
     "b200nerf_pdf_resample": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_void_p,
                                       c_void_p, c_void_p, c_void_p]),
     "b200nerf_density_to_weights": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p]),

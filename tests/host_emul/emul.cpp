@@ -146,7 +146,8 @@ int emul_render(const void* const* ptrs, const int* ints, const float* floats, l
       threads.emplace_back([&, w, l]() {
         simt::t_lane = l;
         simt::t_warp = &warps[w];
-        for (long long r = w; r < n_rays; r += n_warps) render_ray(P, shared[w], mlp.data(), r);
+        MlpFfma pol{mlp.data()};
+        for (long long r = w; r < n_rays; r += n_warps) render_ray(P, shared[w], pol, r, true);
       });
   for (auto& th : threads) th.join();
   return 0;
