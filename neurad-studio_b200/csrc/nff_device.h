@@ -82,20 +82,25 @@ NFF_D Gauss sample_gaussian(const float o[3], const float d[3], float area, floa
   g.y = fadd(o[1], fmul(d[1], t));
   g.z = fadd(o[2], fmul(d[2], t));
   float cs = fmul(area, fmul(t, t));
-  g.std = powf(fmul(cs, md), 0.33333334f);
+  // reference: pow(x, 1/3) with the fp32 exponent 0.33333334f; cbrtf differs from it by < 3e-7 relative
+  // (|ln x| * 1e-8), far inside the 1e-4 budget, and costs ~12 instead of ~75 instructions
+  g.std = cbrtf(fmul(cs, md));
   return g;
 }
 // ScaledSceneContraction(order=inf) on a GaussiansStd (field_components/spatial_distortions.py:103-114,132-136)
 NFF_D Gauss contract(Gauss g, float scale) {
-  float x = fdiv(g.x, scale), y = fdiv(g.y, scale), z = fdiv(g.z, scale), sd = fdiv(g.std, scale);
+  // positions reaching this point already carry ~1e-6 relative noise from the resampled bin edges, so the
+  // reference's IEEE divisions are evaluated as multiplications by correctly-rounded reciprocals (<= 1.5 ulp)
+  const float inv = frcp(scale);
+  float x = fmul(g.x, inv), y = fmul(g.y, inv), z = fmul(g.z, inv), sd = fmul(g.std, inv);
   float mag = fmaxf(fmaxf(fabsf(x), fabsf(y)), fabsf(z));
   if (!(mag < 1.0f)) {
-    float cm = fmaxf(mag, 1.0f);
-    float a = fsub(2.0f, frcp(cm));
-    x = fmul(a, fdiv(x, cm));
-    y = fmul(a, fdiv(y, cm));
-    z = fmul(a, fdiv(z, cm));
-    float q = fdiv(powf(fsub(fmul(2.0f, cm), 1.0f), 0.33333334f), cm);
+    const float icm = frcp(mag);
+    const float a = fmul(fsub(2.0f, icm), icm);
+    x = fmul(a, x);
+    y = fmul(a, y);
+    z = fmul(a, z);
+    float q = fmul(cbrtf(fsub(fmul(2.0f, mag), 1.0f)), icm);
     sd = fmul(sd, fmul(q, q));
   }
   Gauss r;
@@ -154,31 +159,54 @@ NFF_D float trilerp(const float f[8], const Cell& c) {
   return blend(f0312, c.oz, f4756, iz);
 }
 
+// Fused-path variant: same blend tree with the second product folded into an FMA (one rounding fewer per blend,
+// 14 instead of 24 instructions); the stage operator b200nerf_hashgrid_fwd keeps the bit-exact form above.
+NFF_D float blend_f(float a, float wa, float b, float wb) { return fmaf(a, wa, b * wb); }
+NFF_D float trilerp_f(const float f[8], const Cell& c, float ix, float iy, float iz) {
+  float f03 = blend_f(f[0], c.ox, f[3], ix);
+  float f12 = blend_f(f[1], c.ox, f[2], ix);
+  float f56 = blend_f(f[5], c.ox, f[6], ix);
+  float f47 = blend_f(f[4], c.ox, f[7], ix);
+  float f0312 = blend_f(f03, c.oy, f12, iy);
+  float f4756 = blend_f(f47, c.oy, f56, iy);
+  return blend_f(f0312, c.oz, f4756, iz);
+}
+
 // One grid, all levels, F = 1, fused with the proposal field's Linear(L,1) decoder:
 //   sum_l dec[l] * interp_l * 1/max(1, 2*res_l*std)      (neurad_encoding.py:297-304, neurad_field.py:201,211)
 // The level loop stays rolled (one copy of the ~90-instruction body) so the kernel fits the instruction cache.
-NFF_D float encode_f1_dot(const float* NFF_RESTRICT table, const Grid& gr, int L, Gauss g,
-                          const float* NFF_RESTRICT dec) {
+template <int L, int G>
+NFF_D float encode_f1_dot(const float* NFF_RESTRICT table, const Grid& gr, Gauss g, const float* NFF_RESTRICT dec) {
+  // levels in groups of G: the 8*G gathers of a group are issued back to back before the first is consumed
+  // (the kernel is latency-bound on these loads: profiles/r01_ncu_render_v3.txt, stall_long_sb)
+  static_assert(L % G == 0, "group size must divide the level count");
   float acc = 0.0f;
-#pragma unroll 1
-  for (int l = 0; l < L; ++l) {
-    const float res = gr.res[l];
-    Cell c = grid_cell(g.x, g.y, g.z, res);
-    uint32_t r[8];
-    cell_rows(c, gr.mask, r);
-    const float* base = table + (size_t)l * gr.T;
-    float f[8];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) f[k] = ldg(base + r[k]);
-    float w = frcp(fmaxf(fmul(fmul(res, 2.0f), g.std), 1.0f));
-    acc = fmaf(fmul(trilerp(f, c), w), ldg(dec + l), acc);
+  for (int l0 = 0; l0 < L; l0 += G) {
+    Cell c[G];
+    float f[G][8];
+#pragma unroll
+    for (int j = 0; j < G; ++j) {
+      c[j] = grid_cell(g.x, g.y, g.z, gr.res[l0 + j]);
+      uint32_t r[8];
+      cell_rows(c[j], gr.mask, r);
+      const float* base = table + (size_t)(l0 + j) * gr.T;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) f[j][k] = ldg(base + r[k]);
+    }
+#pragma unroll
+    for (int j = 0; j < G; ++j) {
+      float w = frcp(fmaxf(fmul(fmul(gr.res[l0 + j], 2.0f), g.std), 1.0f));
+      float v = trilerp_f(f[j], c[j], 1.0f - c[j].ox, 1.0f - c[j].oy, 1.0f - c[j].oz);
+      acc = fmaf(fmul(v, w), ldg(dec + l0 + j), acc);
+    }
   }
   return acc;
 }
 // F = 4 (16-byte rows, one LDG.128 per corner); writes feature 4l+f of this lane's sample to panel[4l+f][lane].
 NFF_D void encode_f4_panel(const float* NFF_RESTRICT table, const Grid& gr, int L, Gauss g, float (*panel)[33]) {
   const int ln = lane();
-#pragma unroll 1
+#pragma unroll 2
   for (int l = 0; l < L; ++l) {
     const float res = gr.res[l];
     Cell c = grid_cell(g.x, g.y, g.z, res);
@@ -189,19 +217,20 @@ NFF_D void encode_f4_panel(const float* NFF_RESTRICT table, const Grid& gr, int 
 #pragma unroll
     for (int k = 0; k < 8; ++k) v[k] = ldg(base + r[k]);
     float w = frcp(fmaxf(fmul(fmul(res, 2.0f), g.std), 1.0f));
+    const float ix = 1.0f - c.ox, iy = 1.0f - c.oy, iz = 1.0f - c.oz;
     float f[8];
 #pragma unroll
     for (int k = 0; k < 8; ++k) f[k] = v[k].x;
-    panel[4 * l + 0][ln] = fmul(trilerp(f, c), w);
+    panel[4 * l + 0][ln] = fmul(trilerp_f(f, c, ix, iy, iz), w);
 #pragma unroll
     for (int k = 0; k < 8; ++k) f[k] = v[k].y;
-    panel[4 * l + 1][ln] = fmul(trilerp(f, c), w);
+    panel[4 * l + 1][ln] = fmul(trilerp_f(f, c, ix, iy, iz), w);
 #pragma unroll
     for (int k = 0; k < 8; ++k) f[k] = v[k].z;
-    panel[4 * l + 2][ln] = fmul(trilerp(f, c), w);
+    panel[4 * l + 2][ln] = fmul(trilerp_f(f, c, ix, iy, iz), w);
 #pragma unroll
     for (int k = 0; k < 8; ++k) f[k] = v[k].w;
-    panel[4 * l + 3][ln] = fmul(trilerp(f, c), w);
+    panel[4 * l + 3][ln] = fmul(trilerp_f(f, c, ix, iy, iz), w);
   }
 }
 
@@ -212,6 +241,7 @@ struct WarpSharedT {
   float cdf[kS0 + 4];
   float bins_a[kS0 + 4];
   float bins_b[kS1 + 4];
+  float bins_e[kS0 + 4];  // euclidean edges of the current level
   float w2b[kMaxCand][12];  // world->box [R^T | -R^T t], row major 3x4
   float bnd[kMaxCand][3];
   int32_t cand_id[kMaxCand];
@@ -350,11 +380,11 @@ NFF_D float proposal_density(const FieldGrids& fg, const WS& ws, const Gauss& g,
     Gauss ga = {pb[0], pb[1], pb[2], g.std};
     ga = contract(ga, fg.actor_scale);
     // actor features occupy the first 4 of the 6 decoder inputs; the zero padding contributes nothing
-    acc = encode_f1_dot(fg.actor_tables[ws.cand_id[c]], fg.act, 4, ga, fg.decoder);
+    acc = encode_f1_dot<4, 2>(fg.actor_tables[ws.cand_id[c]], fg.act, ga, fg.decoder);
     *actor_id = ws.cand_id[c];
   } else {
     Gauss gs = contract(g, fg.static_scale);
-    acc = encode_f1_dot(fg.stat.table, fg.stat, 6, gs, fg.decoder);
+    acc = encode_f1_dot<6, 3>(fg.stat.table, fg.stat, gs, fg.decoder);
     *actor_id = -1;
   }
   return expf(acc);
@@ -453,11 +483,14 @@ NFF_D float proposal_round(const RenderParams& P, const FieldGrids& fg, WS& ws, 
   const Sampling& sp = P.samp;
   const int S = io.S, S_new = io.S_new, ln = lane();
   float carry = 0.0f, depth_acc = 0.0f, part = 0.0f;
+  // spacing -> euclidean for the S+1 edges, once (each edge is shared by two samples)
+#pragma unroll 1
+  for (int i = ln; i <= S; i += 32) ws.bins_e[i] = to_euclid(io.bins_in[i], s_near, s_far, sp);
+  syncwarp();
 #pragma unroll 1
   for (int s0 = 0; s0 < S; s0 += 32) {
     const int s = s0 + ln;
-    float e0 = to_euclid(io.bins_in[s], s_near, s_far, sp);
-    float e1 = to_euclid(io.bins_in[s + 1], s_near, s_far, sp);
+    const float e0 = ws.bins_e[s], e1 = ws.bins_e[s + 1];
     Gauss g = sample_gaussian(o, d, area, e0, e1);
     int aid;
     float dens = proposal_density(fg, ws, g, &aid);
@@ -684,6 +717,9 @@ NFF_D void render_ray(const RenderParams& P, WS& ws, Mlp& mlp, int64_t ray, bool
   const float s_near = spacing_fn(near_, sp), s_far = spacing_fn(far_, sp);
 
   actor_candidates(P.actors, time, o, d, ws);
+#if defined(__CUDACC__)
+  if (ws.overflow && P.status && ln == 0) atomicExch(P.status, 3);  // > kMaxCand actors along one ray: fail loudly
+#endif
 
   // level-0 spacing bins: torch.linspace(0, 1, S0+1) (ray_samplers.py:102)
   for (int i = ln; i <= kS0; i += 32) ws.bins_a[i] = linspace01(i, kS0);

@@ -8,7 +8,7 @@
 namespace nff {
 
 constexpr int kMaxLevels = 16;     // per grid (HashEncoding default is 16 levels)
-constexpr int kMaxCand = 32;       // actor candidates per ray (ray line passes within the box's bounding sphere)
+constexpr int kMaxCand = 16;       // actor candidates per ray (ray line passes within the box's bounding sphere)
 constexpr int kS0 = 128;           // proposal samples, round 0   (SamplingSettings.num_proposal_samples[0])
 constexpr int kS1 = 64;            // proposal samples, round 1
 constexpr int kS2 = 32;            // nerf samples == warp width: one sample per lane in the shading phase
