@@ -80,7 +80,10 @@ int make_grid(const b200nerf_grid_desc* d, const float* table, Grid* g) {
 }  // namespace
 
 // =================================================================================================== kernels
-constexpr int kRenderWarps = 8;  // warps (= rays in flight) per CTA; 2 CTAs/SM -> 16 warps/SM at <=128 registers
+#ifndef NFF_WARPS
+#define NFF_WARPS 8
+#endif
+constexpr int kRenderWarps = NFF_WARPS;  // warps (= rays in flight) per CTA; 16 warps/SM at <=128 registers
 
 // CUDA-core MLP variant (exact fp32 FFMA): the reference/fallback numerics mode.
 template <int WARPS>

@@ -13,6 +13,13 @@
 #include "nff_params.h"
 #include "simt.h"
 
+#ifndef NFF_G_PROP
+#define NFF_G_PROP 1  // proposal-grid levels gathered per batch (8 loads each); 1 measured best (r01 variants)
+#endif
+#ifndef NFF_G_ACT
+#define NFF_G_ACT 2
+#endif
+
 namespace nff {
 using namespace simt;
 
@@ -238,16 +245,23 @@ NFF_D void encode_f4_panel(const float* NFF_RESTRICT table, const Grid& gr, int 
 // Per-warp shared state.  One warp == one ray.
 template <int ACT_ROWS>
 struct WarpSharedT {
-  float cdf[kS0 + 4];
+  // The sampling scratch (cdf, resampled bins, euclidean edges) is dead once the main-field phase starts and the
+  // activation panel is dead until then, so they share storage: every KB of shared memory given back is L1 cache
+  // for the hash-grid gathers (unified 228 KB L1/shared on sm_100).
+  union {
+    struct {
+      float cdf[kS0 + 4];
+      float bins_b[kS1 + 4];
+      float bins_e[kS0 + 4];  // euclidean edges of the current level
+    };
+    float act[ACT_ROWS][33];  // per-lane (column) grid features / MLP activations; also the composite transpose
+  };
   float bins_a[kS0 + 4];
-  float bins_b[kS1 + 4];
-  float bins_e[kS0 + 4];  // euclidean edges of the current level
   float w2b[kMaxCand][12];  // world->box [R^T | -R^T t], row major 3x4
   float bnd[kMaxCand][3];
   int32_t cand_id[kMaxCand];
   int32_t n_cand;
   int32_t overflow;
-  float act[ACT_ROWS][33];  // per-lane (column) grid features / MLP activations; also the composite transpose
 };
 using WarpShared = WarpSharedT<kNff + kSh>;  // CUDA-core MLP path (and the host emulation)
 
@@ -380,11 +394,11 @@ NFF_D float proposal_density(const FieldGrids& fg, const WS& ws, const Gauss& g,
     Gauss ga = {pb[0], pb[1], pb[2], g.std};
     ga = contract(ga, fg.actor_scale);
     // actor features occupy the first 4 of the 6 decoder inputs; the zero padding contributes nothing
-    acc = encode_f1_dot<4, 2>(fg.actor_tables[ws.cand_id[c]], fg.act, ga, fg.decoder);
+    acc = encode_f1_dot<4, NFF_G_ACT>(fg.actor_tables[ws.cand_id[c]], fg.act, ga, fg.decoder);
     *actor_id = ws.cand_id[c];
   } else {
     Gauss gs = contract(g, fg.static_scale);
-    acc = encode_f1_dot<6, 3>(fg.stat.table, fg.stat, gs, fg.decoder);
+    acc = encode_f1_dot<6, NFF_G_PROP>(fg.stat.table, fg.stat, gs, fg.decoder);
     *actor_id = -1;
   }
   return expf(acc);

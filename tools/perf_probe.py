@@ -3,6 +3,10 @@ import sys, os, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 import neurad_studio_b200 as nsb
+if os.environ.get('NFF_LIB'):
+    from neurad_studio_b200 import build as _b
+    _b.LIB_PATH = os.environ['NFF_LIB']
+    _b.needs_build = lambda: False
 from neurad_studio_b200 import scene
 from neurad_studio_b200.backend import B200Backend
 
