@@ -19,9 +19,18 @@
 #ifndef NFF_G_ACT
 #define NFF_G_ACT 2
 #endif
+#ifndef NFF_F4_UNROLL
+#define NFF_F4_UNROLL 2
+#endif
+#ifndef NFF_FAST_RCP
+#define NFF_FAST_RCP 0
+#endif
+#define NFF_STR2(x) #x
+#define NFF_STR(x) NFF_STR2(x)
 
 namespace nff {
 using namespace simt;
+constexpr int kF4Unroll = NFF_F4_UNROLL;
 
 // ------------------------------------------------------------------------------------------------ helpers
 NFF_D float nan_to_num(float v) {  // torch.nan_to_num defaults: nan->0, +-inf -> +-FLT_MAX
@@ -169,6 +178,15 @@ NFF_D float trilerp(const float f[8], const Cell& c) {
 // Fused-path variant: same blend tree with the second product folded into an FMA (one rounding fewer per blend,
 // 14 instead of 24 instructions); the stage operator b200nerf_hashgrid_fwd keeps the bit-exact form above.
 NFF_D float blend_f(float a, float wa, float b, float wb) { return fmaf(a, wa, b * wb); }
+// anti-aliasing weight 1/max(1, 2*res*std) (neurad_encoding.py:302)
+NFF_D float level_weight(float res, float std) {
+  const float t = fmaxf(fmul(fmul(res, 2.0f), std), 1.0f);
+#if NFF_FAST_RCP && defined(__CUDACC__)
+  return __fdividef(1.0f, t);  // MUFU.RCP, <= 1 ulp for t in [1, 2^126)
+#else
+  return frcp(t);
+#endif
+}
 NFF_D float trilerp_f(const float f[8], const Cell& c, float ix, float iy, float iz) {
   float f03 = blend_f(f[0], c.ox, f[3], ix);
   float f12 = blend_f(f[1], c.ox, f[2], ix);
@@ -203,7 +221,7 @@ NFF_D float encode_f1_dot(const float* NFF_RESTRICT table, const Grid& gr, Gauss
     }
 #pragma unroll
     for (int j = 0; j < G; ++j) {
-      float w = frcp(fmaxf(fmul(fmul(gr.res[l0 + j], 2.0f), g.std), 1.0f));
+      float w = level_weight(gr.res[l0 + j], g.std);
       float v = trilerp_f(f[j], c[j], 1.0f - c[j].ox, 1.0f - c[j].oy, 1.0f - c[j].oz);
       acc = fmaf(fmul(v, w), ldg(dec + l0 + j), acc);
     }
@@ -213,7 +231,7 @@ NFF_D float encode_f1_dot(const float* NFF_RESTRICT table, const Grid& gr, Gauss
 // F = 4 (16-byte rows, one LDG.128 per corner); writes feature 4l+f of this lane's sample to panel[4l+f][lane].
 NFF_D void encode_f4_panel(const float* NFF_RESTRICT table, const Grid& gr, int L, Gauss g, float (*panel)[33]) {
   const int ln = lane();
-#pragma unroll 2
+#pragma unroll kF4Unroll
   for (int l = 0; l < L; ++l) {
     const float res = gr.res[l];
     Cell c = grid_cell(g.x, g.y, g.z, res);
@@ -223,7 +241,7 @@ NFF_D void encode_f4_panel(const float* NFF_RESTRICT table, const Grid& gr, int 
     float4 v[8];
 #pragma unroll
     for (int k = 0; k < 8; ++k) v[k] = ldg(base + r[k]);
-    float w = frcp(fmaxf(fmul(fmul(res, 2.0f), g.std), 1.0f));
+    float w = level_weight(res, g.std);
     const float ix = 1.0f - c.ox, iy = 1.0f - c.oy, iz = 1.0f - c.oz;
     float f[8];
 #pragma unroll
