@@ -342,4 +342,7 @@ class B200Backend:
                 _ptr(t), _ptr(dist), self._stream,
             )
         )
-        return {"origins": o, "directions": d, "pixel_area": a, "times": t, "directions_norm": dist, "did_return": dist < 1e3}
+        res = {"origins": o, "directions": d, "pixel_area": a, "times": t, "directions_norm": dist}
+        if out is None:  # metadata["did_return"] (lidars.py:447); skipped on the pre-allocated hot path
+            res["did_return"] = dist < 1e3
+        return res

@@ -1,0 +1,275 @@
+"""Host-side mirror of the reference's plugin / operator API for the hot path, backed by libb200nerf.so.
+
+Same class names, constructor arguments, parameter names (state_dict keys) and call signatures as the reference
+modules, so that the parity tests read like the reference's own tests and a reference checkpoint loads unchanged:
+
+  reference (nerfstudio/...)                                   here
+  -----------------------------------------------------------  ---------------------------------------------
+  cameras/rays.py:252           RayBundle                      RayBundle
+  field_components/encodings.py:311  HashEncoding(implementation=) HashEncoding      (forward -> hashgrid_fwd kernel)
+  field_components/encodings.py:760  SHEncoding(levels=4)      SHEncoding        (forward -> sh4_fwd kernel)
+  field_components/mlp.py:60    MLP(implementation=)           MLP               (forward -> tcgen05 mlp_fwd kernel)
+  model_components/ray_samplers.py:255  PDFSampler             PDFSampler        (-> pdf_resample kernel)
+  model_components/renderers.py:59,322  Feature/AccumulationRenderer  same names (dense [N,S] inputs)
+  models/neurad.py:165          NeuRADModel.get_nff_outputs /  NeuRADModel       (-> fused nff_render_fwd kernel)
+                                get_outputs_for_camera_ray_bundle / decode_features (lidar half)
+
+Everything is inference-only (eval mode, no autograd): SURVEY.md section 8f ranks the backward pass as a later row.
+There is no CPU path: modules raise at call time if the parameters are not on a CUDA device.
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional, Tuple
+
+import torch
+from torch import Tensor, nn
+
+from .backend import B200Backend
+from .config import HashGridSettings, NeuRADConfig
+
+_BACKENDS: Dict[int, B200Backend] = {}
+
+
+def get_backend(device: torch.device) -> B200Backend:
+    """One B200Backend (= one b200nerf_ctx) per CUDA device and process."""
+    device = torch.device(device)
+    if device.type != "cuda":
+        raise RuntimeError("the b200 implementation runs on CUDA (sm_100a) devices only; there is no CPU fallback")
+    idx = device.index if device.index is not None else torch.cuda.current_device()
+    if idx not in _BACKENDS:
+        _BACKENDS[idx] = B200Backend(torch.device("cuda", idx))
+    return _BACKENDS[idx]
+
+
+@dataclass
+class RayBundle:
+    """cameras/rays.py:252-275 (the tensors the hot path reads; shapes [*batch, k])."""
+
+    origins: Tensor
+    directions: Tensor
+    pixel_area: Tensor
+    camera_indices: Optional[Tensor] = None
+    nears: Optional[Tensor] = None
+    fars: Optional[Tensor] = None
+    metadata: Dict[str, Tensor] = field(default_factory=dict)
+    times: Optional[Tensor] = None
+
+    @property
+    def shape(self) -> Tuple[int, ...]:
+        return tuple(self.origins.shape[:-1])
+
+    def __len__(self) -> int:
+        return self.origins.numel() // 3
+
+    def _map(self, fn) -> "RayBundle":
+        def m(t):
+            return None if t is None else fn(t)
+
+        return RayBundle(
+            origins=fn(self.origins), directions=fn(self.directions), pixel_area=fn(self.pixel_area),
+            camera_indices=m(self.camera_indices), nears=m(self.nears), fars=m(self.fars),
+            metadata={k: fn(v) for k, v in self.metadata.items()}, times=m(self.times),
+        )
+
+    def flatten(self) -> "RayBundle":
+        return self._map(lambda t: t.reshape(-1, t.shape[-1]))
+
+    def __getitem__(self, idx) -> "RayBundle":
+        return self._map(lambda t: t[idx])
+
+    def get_row_major_sliced_ray_bundle(self, start_idx: int, end_idx: int) -> "RayBundle":
+        return self.flatten()[start_idx:end_idx]  # rays.py:300-311
+
+    def as_backend_dict(self) -> Dict[str, Tensor]:
+        fb = self.flatten()
+        d = {"origins": fb.origins, "directions": fb.directions, "pixel_area": fb.pixel_area, "times": fb.times}
+        if fb.nears is not None:
+            d["nears"] = fb.nears
+        if fb.fars is not None:
+            d["fars"] = fb.fars
+        if "sensor_idxs" in fb.metadata:
+            d["sensor_idx"] = fb.metadata["sensor_idxs"]
+        if "is_lidar" in fb.metadata:
+            d["is_lidar"] = fb.metadata["is_lidar"]
+        return d
+
+
+class HashEncoding(nn.Module):
+    """field_components/encodings.py:311-471 with `implementation="b200"`.  Parameter `hash_table` [L*T, F] and
+    buffer `scalings` exactly as the torch implementation builds them (encodings.py:348-352, 380-384)."""
+
+    def __init__(self, num_levels: int = 16, min_res: int = 16, max_res: int = 1024, log2_hashmap_size: int = 19,
+                 features_per_level: int = 2, hash_init_scale: float = 0.001, implementation: str = "b200") -> None:
+        super().__init__()
+        if implementation != "b200":
+            raise ValueError("this module is the 'b200' implementation of HashEncoding")
+        self.num_levels, self.min_res, self.max_res = num_levels, min_res, max_res
+        self.features_per_level, self.log2_hashmap_size = features_per_level, log2_hashmap_size
+        self.hash_table_size = 2**log2_hashmap_size
+        self._g = HashGridSettings(features_per_level, num_levels, min_res, max_res, log2_hashmap_size)
+        self.register_buffer("scalings", self._g.scalings())
+        table = torch.rand(size=(self.hash_table_size * num_levels, features_per_level)) * 2 - 1
+        self.hash_table = nn.Parameter(table * hash_init_scale)
+
+    def get_out_dim(self) -> int:
+        return self.num_levels * self.features_per_level
+
+    @torch.no_grad()
+    def forward(self, in_tensor: Tensor) -> Tensor:
+        assert in_tensor.shape[-1] == 3  # encodings.py:428
+        be = get_backend(self.hash_table.device)
+        return be.hashgrid_fwd(self._g, self.hash_table, in_tensor, self.scalings)
+
+
+class SHEncoding(nn.Module):
+    """field_components/encodings.py:760-805 (levels = 4)."""
+
+    def __init__(self, levels: int = 4, implementation: str = "b200") -> None:
+        super().__init__()
+        if levels != 4:
+            raise ValueError("the b200 implementation provides SH levels = 4 (the only one NeuRAD uses)")
+        self.levels = levels
+
+    def get_out_dim(self) -> int:
+        return self.levels**2
+
+    @torch.no_grad()
+    def forward(self, in_tensor: Tensor) -> Tensor:
+        return get_backend(in_tensor.device).sh4_fwd(in_tensor)
+
+
+class MLP(nn.Module):
+    """field_components/mlp.py:60-183: `num_layers` Linear layers of width `layer_width`, ReLU in between, no
+    output activation.  Parameters are `layers.{i}.weight/bias` like the torch implementation (mlp.py:142-157)."""
+
+    def __init__(self, in_dim: int, num_layers: int, layer_width: int, out_dim: Optional[int] = None,
+                 implementation: str = "b200") -> None:
+        super().__init__()
+        assert in_dim > 0
+        self.in_dim, self.num_layers, self.layer_width = in_dim, num_layers, layer_width
+        self.out_dim = out_dim if out_dim is not None else layer_width
+        dims = [in_dim] + [layer_width] * (num_layers - 1) + [self.out_dim]
+        self.layers = nn.ModuleList([nn.Linear(dims[i], dims[i + 1]) for i in range(num_layers)])
+
+    @torch.no_grad()
+    def forward(self, in_tensor: Tensor) -> Tensor:
+        be = get_backend(in_tensor.device)
+        return be.mlp_fwd(in_tensor, [l.weight for l in self.layers], [l.bias for l in self.layers])
+
+
+class PDFSampler:
+    """model_components/ray_samplers.py:255-376 in eval mode with include_original=False: maps per-bin weights and
+    the existing spacing-domain bin edges to `num_samples`+1 new edges."""
+
+    def __init__(self, num_samples: Optional[int] = None, histogram_padding: float = 0.01) -> None:
+        self.num_samples, self.histogram_padding = num_samples, histogram_padding
+
+    @torch.no_grad()
+    def __call__(self, weights: Tensor, existing_bins: Tensor, num_samples: Optional[int] = None) -> Tensor:
+        n = num_samples or self.num_samples
+        assert n is not None
+        w = weights[..., 0] if weights.dim() == existing_bins.dim() + 1 else weights
+        be = get_backend(w.device)
+        return be.pdf_resample(w, existing_bins, n, self.histogram_padding)[0]
+
+
+class FeatureRenderer(nn.Module):
+    """model_components/renderers.py:59-90, unpacked branch: sum_s w_s * f_s."""
+
+    @classmethod
+    def forward(cls, features: Tensor, weights: Tensor) -> Tensor:
+        return torch.sum(features * weights, dim=-2)
+
+
+class AccumulationRenderer(nn.Module):
+    """model_components/renderers.py:322-350, unpacked branch."""
+
+    @classmethod
+    def forward(cls, weights: Tensor) -> Tensor:
+        return torch.sum(weights, dim=-2)
+
+
+class NeuRADModel(nn.Module):
+    """models/neurad.py:165 -- the forward (eval) half, with the reference's parameter names so that
+    `load_state_dict(reference_checkpoint["pipeline"], strict=False)` binds the tensors the path uses.
+
+    `get_nff_outputs` is ONE fused kernel launch (ray sampling, both proposal rounds, main field, compositing); the
+    reference's 32 768-ray chunk loop (neurad.py:650-659) is unnecessary because nothing per-sample goes to HBM."""
+
+    def __init__(self, config: NeuRADConfig, trajectories: Optional[List[dict]] = None) -> None:
+        super().__init__()
+        from . import scene  # synthetic init = the reference's random init shapes
+
+        self.config = config
+        p = scene.make_params(config, seed=0, table_scale=1e-3, trajectories=trajectories)
+        self._names = []
+        for k, v in p.items():
+            if k == "static_scale":
+                continue
+            name = k.replace(".", "__")
+            self._names.append((name, k))
+            if v.dtype.is_floating_point and not k.startswith("dynamic_actors.") and not k.endswith("scalings"):
+                self.register_parameter(name, nn.Parameter(v, requires_grad=False))
+            else:
+                self.register_buffer(name, v)
+        self.register_buffer("static_scale", torch.tensor(float(config.static_scale)))
+        self._bound_version = None
+
+    # -- state dict under the reference's dotted names ----------------------------------------------------------
+    def reference_state_dict(self) -> Dict[str, Tensor]:
+        return {k: getattr(self, n) for n, k in self._names}
+
+    def load_reference_state_dict(self, sd: Dict[str, Tensor]) -> None:
+        """Copy tensors from a reference `NeuRADModel.state_dict()` (keys like
+        `field.hashgrid.static_grid.hash_table`, `proposal_fields.1.density_decoder.weight`); unknown keys (rgb
+        decoder, camera optimizer, losses) are ignored, missing hot-path keys raise."""
+        for n, k in self._names:
+            if k not in sd:
+                raise KeyError(f"reference state dict lacks {k}")
+            getattr(self, n).data.copy_(sd[k].to(getattr(self, n).dtype))
+        self._bound_version = None
+
+    def _bind(self) -> B200Backend:
+        be = get_backend(self.static_scale.device)
+        ver = tuple(getattr(self, n)._version for n, _ in self._names) + (id(be), str(self.static_scale.device))
+        if ver != self._bound_version or be.cfg is not self.config:
+            params = self.reference_state_dict()
+            params["static_scale"] = self.static_scale
+            be.load_params(self.config, params)
+            self._bound_version = ver
+        return be
+
+    # -- forward API --------------------------------------------------------------------------------------------
+    @torch.no_grad()
+    def get_nff_outputs(self, ray_bundle: RayBundle, calc_lidar_losses: bool = False) -> Dict[str, Tensor]:
+        """neurad.py:368-421 (eval): features [N,48], depth, accumulation, prop_depth_0/1 [N,1]."""
+        be = self._bind()
+        return be.render(ray_bundle.as_backend_dict())
+
+    @torch.no_grad()
+    def decode_features(self, features: Tensor) -> Tuple[Tensor, Tensor]:
+        """neurad.py:337-357, lidar half: (intensity = sigmoid(o[...,0:1]), ray_drop_logits = o[...,1:2])."""
+        be = self._bind()
+        sd = self.reference_state_dict()
+        o = be.mlp_fwd(features, [sd[f"lidar_decoder.layers.{i}.weight"] for i in range(3)],
+                       [sd[f"lidar_decoder.layers.{i}.bias"] for i in range(3)])
+        return o[..., 0:1].sigmoid(), o[..., 1:2]
+
+    @torch.no_grad()
+    def get_outputs_for_camera_ray_bundle(self, camera_ray_bundle: RayBundle) -> Dict[str, Tensor]:
+        """neurad.py:623-675 without the rgb CNN: 2-D bundles are subsampled at
+        [step//2::step] like the reference (`compensate_upsampling_when_rendering`), 1-D bundles are lidar rays."""
+        if len(camera_ray_bundle.shape) == 1:
+            output_size = (camera_ray_bundle.shape[0],)
+        else:
+            assert len(camera_ray_bundle.shape) == 2, "Raybundle should be 2d (an image/patch)"
+            step = self.config.rgb_upsample_factor
+            camera_ray_bundle = camera_ray_bundle[step // 2 :: step, step // 2 :: step]
+            output_size = camera_ray_bundle.shape
+        be = self._bind()
+        out = be.render(camera_ray_bundle.as_backend_dict(), want_intensity=True)
+        res = {k: v.view(*output_size, -1) for k, v in out.items()}
+        res["ray_drop_prob"] = res["ray_drop_logits"].sigmoid()
+        return res

@@ -1,0 +1,31 @@
+"""CPU: the reference-API mirror constructs with the reference's parameter names and refuses to compute without a
+CUDA device (no CPU fallback)."""
+import pytest
+import torch
+
+import neurad_studio_b200 as nsb
+from tests.helpers import cfg_from_meta, load_golden
+
+
+def test_state_dict_names_and_no_cpu_path():
+    from neurad_studio_b200.nerfstudio_api import HashEncoding, NeuRADModel, RayBundle
+
+    meta, g = load_golden("nff_actors.npz")
+    cfg = cfg_from_meta(meta)
+    model = NeuRADModel(cfg)
+    model.load_reference_state_dict(g["param"])
+    sd = model.reference_state_dict()
+    for k in ("field.hashgrid.static_grid.hash_table", "field.mlp_geo.layers.1.weight", "proposal_fields.1.density_decoder.weight",
+              "appearance_embedding.weight", "lidar_decoder.layers.2.bias", "dynamic_actors.actor_rotations_6d",
+              "field.hashgrid.actor_grids.5.hash_table"):
+        assert k in sd and torch.equal(sd[k].float(), g["param"][k].float()), k
+    with pytest.raises(KeyError):
+        model.load_reference_state_dict({"field.hashgrid.static_grid.hash_table": sd["field.hashgrid.static_grid.hash_table"]})
+    r = g["ray"]
+    rb = RayBundle(origins=r["origins"], directions=r["directions"], pixel_area=r["pixel_area"], times=r["times"])
+    assert rb.shape == (r["origins"].shape[0],) and len(rb.get_row_major_sliced_ray_bundle(3, 10)) == 7
+    if not torch.cuda.is_available():
+        with pytest.raises(RuntimeError):
+            model.get_nff_outputs(rb)
+        with pytest.raises(RuntimeError):
+            HashEncoding(num_levels=2, log2_hashmap_size=8)(torch.rand(4, 3))
