@@ -19,6 +19,9 @@
 #ifndef NFF_G_ACT
 #define NFF_G_ACT 2
 #endif
+#ifndef NFF_ILP
+#define NFF_ILP 2  // independent samples per lane in the proposal rounds (64 % 32*NFF_ILP == 0)
+#endif
 #ifndef NFF_F4_UNROLL
 #define NFF_F4_UNROLL 2
 #endif
@@ -519,27 +522,40 @@ NFF_D float proposal_round(const RenderParams& P, const FieldGrids& fg, WS& ws, 
 #pragma unroll 1
   for (int i = ln; i <= S; i += 32) ws.bins_e[i] = to_euclid(io.bins_in[i], s_near, s_far, sp);
   syncwarp();
+  // NFF_ILP chunks (of 32 samples) are processed together: each lane carries NFF_ILP independent samples through
+  // gaussian -> contraction -> gathers -> interpolation, which is what fills the issue slots of a kernel that runs
+  // at 4 warps per scheduler (profiles/r01_ncu_render_v5_tc.txt: stall_wait + long_sb ~ 50 %)
+  constexpr int U = NFF_ILP;
 #pragma unroll 1
-  for (int s0 = 0; s0 < S; s0 += 32) {
-    const int s = s0 + ln;
-    const float e0 = ws.bins_e[s], e1 = ws.bins_e[s + 1];
-    Gauss g = sample_gaussian(o, d, area, e0, e1);
-    int aid;
-    float dens = proposal_density(fg, ws, g, &aid);
-    float dd = fmul(fsub(e1, e0), dens);
-    float incl = warp_scan_add(dd);
-    float prev = shfl_up(incl, 1);
-    float excl = carry + (ln == 0 ? 0.0f : prev);
-    carry += shfl(incl, 31);
-    float alpha = fsub(1.0f, expf(-dd));
-    float T = expf(-excl);
-    float wj = nan_to_num(fmul(alpha, T));
-    depth_acc = fadd(depth_acc, fmul(wj, fmul(fadd(e0, e1), 0.5f)));
-    if (io.tr_w) io.tr_w[ray * S + s] = wj;
-    if (io.tr_aid) io.tr_aid[ray * S + s] = aid;
-    wj = fadd(wj, sp.hist_pad);  // PDFSampler: histogram padding
-    ws.cdf[s + 1] = wj;
-    part += wj;
+  for (int s0 = 0; s0 < S; s0 += 32 * U) {
+    float e0[U], e1[U], dd[U];
+    int aid[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int s = s0 + 32 * u + ln;
+      e0[u] = ws.bins_e[s];
+      e1[u] = ws.bins_e[s + 1];
+      Gauss g = sample_gaussian(o, d, area, e0[u], e1[u]);
+      float dens = proposal_density(fg, ws, g, &aid[u]);
+      dd[u] = fmul(fsub(e1[u], e0[u]), dens);
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int s = s0 + 32 * u + ln;
+      float incl = warp_scan_add(dd[u]);
+      float prev = shfl_up(incl, 1);
+      float excl = carry + (ln == 0 ? 0.0f : prev);
+      carry += shfl(incl, 31);
+      float alpha = fsub(1.0f, expf(-dd[u]));
+      float T = expf(-excl);
+      float wj = nan_to_num(fmul(alpha, T));
+      depth_acc = fadd(depth_acc, fmul(wj, fmul(fadd(e0[u], e1[u]), 0.5f)));
+      if (io.tr_w) io.tr_w[ray * S + s] = wj;
+      if (io.tr_aid) io.tr_aid[ray * S + s] = aid[u];
+      wj = fadd(wj, sp.hist_pad);  // PDFSampler: histogram padding
+      ws.cdf[s + 1] = wj;
+      part += wj;
+    }
   }
   const float prop_depth = warp_sum(depth_acc);
   float tot = warp_sum(part);
