@@ -173,8 +173,10 @@ int b200nerf_mlp_fwd(b200nerf_ctx* ctx, const float* x, int64_t n_rows, int in_d
                      const float* const* weights_host, const float* const* biases_host, const int* out_dims_host,
                      float* y, void* stream);
 
-/* Numerics mode of the main-field MLPs inside b200nerf_nff_render_fwd: 1 (default) = tcgen05 tensor cores with
- * the 3xTF32 split (fp32-level accuracy, |err| ~1e-6 relative), 0 = CUDA-core fp32 FFMA. */
+/* Kernel variant used by b200nerf_nff_render_fwd:
+ *   2 (default) ray-per-lane mapping (a warp = 32 adjacent rays at one sample index: coherent gathers), MLPs on the
+ *     tcgen05 tensor cores with the 3xTF32 split (fp32-level accuracy, |err| ~1e-6 relative);
+ *   1 warp-per-ray mapping, tcgen05 MLPs;   0 warp-per-ray mapping, CUDA-core fp32 FFMA MLPs. */
 int b200nerf_set_mlp_mode(b200nerf_ctx* ctx, int mode);
 
 /* Synchronises with the device and reports (then clears) the device-side failure flag that kernels raise instead

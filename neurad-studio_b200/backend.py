@@ -264,8 +264,9 @@ class B200Backend:
         return y.reshape(*x.shape[:-1], out_dims[-1])
 
     def set_mlp_mode(self, mode: str):
-        """'tc' (default): main-field MLPs on the tcgen05 tensor cores (3xTF32); 'ffma': CUDA-core fp32."""
-        self._check(self.lib.b200nerf_set_mlp_mode(self._h, {"ffma": 0, "tc": 1}[mode]))
+        """Kernel variant of render(): 'lane' (default) ray-per-lane + tcgen05 MLPs; 'tc' warp-per-ray + tcgen05
+        MLPs (3xTF32); 'ffma' warp-per-ray + CUDA-core fp32 MLPs."""
+        self._check(self.lib.b200nerf_set_mlp_mode(self._h, {"ffma": 0, "tc": 1, "lane": 2}[mode]))
 
     def check_status(self):
         """Raise if a kernel set the device-side failure flag (synchronises)."""

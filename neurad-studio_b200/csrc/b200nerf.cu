@@ -9,6 +9,7 @@
 
 #include "../../include/b200nerf.h"
 #include "nff_device.h"
+#include "nff_lane.h"
 
 using namespace nff;
 
@@ -38,7 +39,9 @@ struct b200nerf_ctx {
   float* d_decoder[3] = {nullptr, nullptr, nullptr};
   float* d_main_mlp = nullptr;
   float* d_main_mlp_nn = nullptr;
-  int mlp_mode = 1;  // 1 = tcgen05 tensor cores (3xTF32), 0 = CUDA-core fp32 FFMA
+  int mlp_mode = 2;  // 2 = ray-per-lane + tcgen05, 1 = warp-per-ray + tcgen05 (3xTF32), 0 = warp-per-ray + CUDA-core fp32 FFMA
+  float* d_lane_scratch = nullptr;
+  int lane_ctas = 0;
   bool have_main_mlp = false;
   float beta = 0.f;
   float* d_lidar_mlp = nullptr;
@@ -134,6 +137,46 @@ __global__ void __launch_bounds__(WARPS * 32, 16 / WARPS) nff_render_tc_kernel(c
     const int64_t ray = base + warp;
     const bool active = ray < P.n_rays;
     render_ray(P, *ws, mlp, active ? ray : P.n_rays - 1, active);
+  }
+  tc::fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tc::tmem_dealloc(tcs->tmem_base, kCols);
+}
+
+
+// Ray-per-lane variant (nff_lane.h): a warp = 32 adjacent rays at the same sample index, CTA = 256 rays.
+__global__ void __launch_bounds__(kLaneThreads, 2) nff_render_lane_kernel(const __grid_constant__ RenderParams P,
+                                                                          float* __restrict__ scratch) {
+  extern __shared__ __align__(128) unsigned char smem_lane[];
+  TcShared* tcs = reinterpret_cast<TcShared*>(smem_lane);
+  constexpr int kTcBytes = (sizeof(TcShared) + 127) / 128 * 128;
+  float* geo_park = reinterpret_cast<float*>(smem_lane + kTcBytes);
+  const int tid = threadIdx.x, warp = tid >> 5, group = warp >> 2;
+  tc_stage_weights(*tcs, P.main_mlp_nn, tid, kLaneThreads);
+  tc::fence_async_smem();
+  constexpr uint32_t kCols = kTcTileCols * (kLaneThreads / 128);
+  if (warp == 0) tc::tmem_alloc(&tcs->tmem_base, kCols);
+  if (tid == 0)
+    for (int g = 0; g < kLaneThreads / 128; ++g) tc::mbar_init(&tcs->bar[g], 1);
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+  MlpLaneTc mlp;
+  mlp.core.t = tcs;
+  mlp.core.tile_base = tcs->tmem_base + (uint32_t)(group * kTcTileCols);
+  mlp.core.lane_base = mlp.core.tile_base + ((uint32_t)(32 * (warp & 3)) << 16);
+  mlp.core.bar = &tcs->bar[group];
+  mlp.core.parity = 0;
+  mlp.core.bar_id = 1 + group;
+  mlp.core.issuer = (tid & 127) == 0;
+  mlp.core.status = P.status;
+  mlp.geo_park = geo_park;
+  const LaneScratch sc = lane_scratch_of(scratch, blockIdx.x);
+  const int64_t stride = (int64_t)gridDim.x * kLaneThreads;
+  for (int64_t base = (int64_t)blockIdx.x * kLaneThreads; base < P.n_rays; base += stride) {
+    const int64_t ray = base + tid;
+    const bool active = ray < P.n_rays;
+    render_ray_lane(P, sc, mlp, tid, active ? ray : P.n_rays - 1, active);
   }
   tc::fence_before_sync();
   __syncthreads();
@@ -502,6 +545,10 @@ int b200nerf_create(int device_ordinal, b200nerf_ctx** out) {
                                 (int)((sizeof(TcShared) + 127) / 128 * 128 + kRenderWarps * sizeof(WarpSharedTc))));
   CUDA_TRY(cudaMalloc((void**)&c->d_status, sizeof(int)));
   CUDA_TRY(cudaMemset(c->d_status, 0, sizeof(int)));
+  CUDA_TRY(cudaFuncSetAttribute(nff_render_lane_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)((sizeof(TcShared) + 127) / 128 * 128 + sizeof(float) * kNff * kLaneThreads)));
+  c->lane_ctas = c->sm_count * 2;
+  CUDA_TRY(cudaMalloc((void**)&c->d_lane_scratch, sizeof(float) * lane_scratch_floats_per_cta() * c->lane_ctas));
   *out = c;
   return 0;
 }
@@ -515,6 +562,7 @@ int b200nerf_destroy(b200nerf_ctx* c) {
   }
   cudaFree(c->d_main_mlp);
   cudaFree(c->d_main_mlp_nn);
+  cudaFree(c->d_lane_scratch);
   cudaFree(c->d_lidar_mlp);
   cudaFree(c->d_act_times);
   cudaFree(c->d_act_kf);
@@ -746,7 +794,12 @@ int b200nerf_nff_render_fwd(b200nerf_ctx* c, const b200nerf_rays* rays, int64_t 
   int64_t max_blocks = (int64_t)c->sm_count * (16 / WARPS);  // persistent: resident CTAs only, grid-stride over rays
   int blocks = (int)(blocks_needed < max_blocks ? blocks_needed : max_blocks);
   cudaStream_t st = (cudaStream_t)stream;
-  if (c->mlp_mode == 1) {
+  if (c->mlp_mode == 2) {
+    const size_t smem = (sizeof(TcShared) + 127) / 128 * 128 + sizeof(float) * kNff * kLaneThreads;
+    int64_t need = (n_rays + kLaneThreads - 1) / kLaneThreads;
+    int lane_blocks = (int)(need < c->lane_ctas ? need : c->lane_ctas);
+    nff_render_lane_kernel<<<lane_blocks, kLaneThreads, smem, st>>>(P, c->d_lane_scratch);
+  } else if (c->mlp_mode == 1) {
     const size_t smem = (sizeof(TcShared) + 127) / 128 * 128 + WARPS * sizeof(WarpSharedTc);
     nff_render_tc_kernel<WARPS><<<blocks, WARPS * 32, smem, st>>>(P);
   } else {
@@ -807,7 +860,7 @@ int b200nerf_mlp_fwd(b200nerf_ctx* c, const float* x, int64_t n_rows, int in_dim
 
 int b200nerf_set_mlp_mode(b200nerf_ctx* c, int mode) {
   REQUIRE(c, "ctx is NULL");
-  REQUIRE(mode == 0 || mode == 1, "mlp mode: 0 = CUDA-core fp32 FFMA, 1 = tcgen05 3xTF32");
+  REQUIRE(mode >= 0 && mode <= 2, "render mode: 0 = warp-per-ray + CUDA-core fp32, 1 = warp-per-ray + tcgen05, 2 = ray-per-lane + tcgen05");
   c->mlp_mode = mode;
   return 0;
 }

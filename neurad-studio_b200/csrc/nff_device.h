@@ -108,18 +108,18 @@ NFF_D Gauss sample_gaussian(const float o[3], const float d[3], float area, floa
 }
 // ScaledSceneContraction(order=inf) on a GaussiansStd (field_components/spatial_distortions.py:103-114,132-136)
 NFF_D Gauss contract(Gauss g, float scale) {
-  // positions reaching this point already carry ~1e-6 relative noise from the resampled bin edges, so the
-  // reference's IEEE divisions are evaluated as multiplications by correctly-rounded reciprocals (<= 1.5 ulp)
-  const float inv = frcp(scale);
-  float x = fmul(g.x, inv), y = fmul(g.y, inv), z = fmul(g.z, inv), sd = fmul(g.std, inv);
+  // Positions keep the reference's exact op sequence (IEEE divisions): the finest grid level multiplies any rounding
+  // difference in x by its resolution (4096 / 8191 cells), so one ulp here is ~1e-4 in a feature.  The std only
+  // scales the smooth anti-aliasing weights, so it uses reciprocals and cbrt (<= 3e-7 relative).
+  float x = fdiv(g.x, scale), y = fdiv(g.y, scale), z = fdiv(g.z, scale);
+  float sd = fmul(g.std, frcp(scale));
   float mag = fmaxf(fmaxf(fabsf(x), fabsf(y)), fabsf(z));
   if (!(mag < 1.0f)) {
-    const float icm = frcp(mag);
-    const float a = fmul(fsub(2.0f, icm), icm);
-    x = fmul(a, x);
-    y = fmul(a, y);
-    z = fmul(a, z);
-    float q = fmul(cbrtf(fsub(fmul(2.0f, mag), 1.0f)), icm);
+    const float a = fsub(2.0f, frcp(mag));
+    x = fmul(a, fdiv(x, mag));
+    y = fmul(a, fdiv(y, mag));
+    z = fmul(a, fdiv(z, mag));
+    float q = fmul(cbrtf(fsub(fmul(2.0f, mag), 1.0f)), frcp(mag));
     sd = fmul(sd, fmul(q, q));
   }
   Gauss r;

@@ -8,6 +8,7 @@
 #include <vector>
 
 #include "../../neurad-studio_b200/csrc/nff_device.h"
+#include "../../neurad-studio_b200/csrc/nff_lane.h"
 
 using namespace nff;
 
@@ -20,7 +21,7 @@ static void pack_linear(const float* w, const float* b, int out_f, int in_f, int
 extern "C" {
 
 // ptrs / ints / floats layouts are documented in tests/host_emul/emul.py
-int emul_render(const void* const* ptrs, const int* ints, const float* floats, long long n_rays) {
+int emul_render(const void* const* ptrs, const int* ints, const float* floats, long long n_rays, int lane_mode) {
   RenderParams P{};
   std::vector<float> kf, bounds, radii;
   int pi = 0, ii = 0, fi = 0;
@@ -133,6 +134,14 @@ int emul_render(const void* const* ptrs, const int* ints, const float* floats, l
   P.trace.actor_id_main = (int32_t*)ptrs[pi++];
   P.n_rays = n_rays;
 
+  if (lane_mode) {
+    // ray-per-lane variant: no warp collectives, so plain sequential execution of every "thread" is exact
+    std::vector<float> scratch(lane_scratch_floats_per_cta());
+    LaneScratch sc = lane_scratch_of(scratch.data(), 0);
+    MlpLaneFfma pol{mlp.data()};
+    for (long long r = 0; r < n_rays; ++r) render_ray_lane(P, sc, pol, (int)(r % kLaneThreads), r, true);
+    return 0;
+  }
   // one emulated warp (32 threads) per hardware thread group; rays are distributed round-robin
   unsigned hw = std::thread::hardware_concurrency();
   int n_warps = hw >= 64 ? 2 : 1;

@@ -12,7 +12,7 @@ CSRC = os.path.join(os.path.dirname(os.path.dirname(HERE)), "neurad-studio_b200"
 
 
 def build(force=False):
-    deps = [SRC] + [os.path.join(CSRC, f) for f in ("nff_device.h", "nff_params.h", "simt.h")]
+    deps = [SRC] + [os.path.join(CSRC, f) for f in ("nff_device.h", "nff_lane.h", "nff_params.h", "simt.h")]
     if force or not os.path.exists(SO) or any(os.path.getmtime(d) > os.path.getmtime(SO) for d in deps):
         subprocess.check_call(
             ["g++", "-std=c++20", "-O2", "-ffp-contract=off", "-fPIC", "-shared", "-pthread", "-o", SO, SRC]
@@ -20,7 +20,7 @@ def build(force=False):
     return SO
 
 
-def render(cfg, params, rays, pdf_u, field_of_round=(2, 2)):
+def render(cfg, params, rays, pdf_u, field_of_round=(2, 2), lane_mode=False):
     """cfg: neurad_studio_b200.NeuRADConfig; params: reference-named tensors (CPU); rays: dict of CPU tensors."""
     lib = ctypes.CDLL(build())
     lib.emul_render.restype = ctypes.c_int
@@ -108,6 +108,6 @@ def render(cfg, params, rays, pdf_u, field_of_round=(2, 2)):
     c_ptrs = (ctypes.c_void_p * len(ptrs))(*ptrs)
     c_ints = (ctypes.c_int * len(ints))(*ints)
     c_floats = (ctypes.c_float * len(floats))(*floats)
-    rc = lib.emul_render(c_ptrs, c_ints, c_floats, ctypes.c_longlong(n))
+    rc = lib.emul_render(c_ptrs, c_ints, c_floats, ctypes.c_longlong(n), ctypes.c_int(1 if lane_mode else 0))
     assert rc == 0
     return out

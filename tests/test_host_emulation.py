@@ -13,12 +13,13 @@ def rel_to_max(a, b):
     return (a - b).abs().max().item() / (b.abs().max().item() + 1e-30)
 
 
+@pytest.mark.parametrize("lane_mode", [False, True], ids=["warp_per_ray", "ray_per_lane"])
 @pytest.mark.parametrize("name", ["nff_static.npz", "nff_actors.npz", "nff_sharp.npz"])
-def test_emulated_kernel_matches_reference_golden(name):
+def test_emulated_kernel_matches_reference_golden(name, lane_mode):
     meta, g = load_golden(name)
     cfg = cfg_from_meta(meta)
     p, r, ref = g["param"], g["ray"], g["ref"]
-    out = emul.render(cfg, p, r, O.pdf_u)
+    out = emul.render(cfg, p, r, O.pdf_u, lane_mode=lane_mode)
     for k in ("inds_1", "inds_2", "actor_id_0", "actor_id_1", "actor_id_main"):
         mism = (out[k].long() != ref[k].long()).float().mean().item()
         assert mism <= 1e-3, (k, mism)
