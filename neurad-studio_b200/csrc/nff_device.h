@@ -26,7 +26,7 @@
 #define NFF_F4_UNROLL 2
 #endif
 #ifndef NFF_FAST_RCP
-#define NFF_FAST_RCP 0
+#define NFF_FAST_RCP 1  // anti-aliasing weights via MUFU.RCP (smooth factor, <= 1 ulp)
 #endif
 #define NFF_STR2(x) #x
 #define NFF_STR(x) NFF_STR2(x)

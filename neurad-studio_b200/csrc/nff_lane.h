@@ -142,10 +142,9 @@ NFF_D float lane_proposal_density(const FieldGrids& fg, const LaneScratch& sc, i
   return expf(acc);
 }
 
-// F = 4 grid into registers (fully unrolled so that x[] stays in registers)
-template <int L>
-NFF_D void encode_f4_regs(const float* NFF_RESTRICT table, const Grid& gr, Gauss g, float* x) {
-#pragma unroll
+// F = 4 grid into the CTA's shared panel column [4l+f][tid] (rolled level loop: small code)
+NFF_D void encode_f4_col(const float* NFF_RESTRICT table, const Grid& gr, int L, Gauss g, float* x /* = panel + tid */) {
+#pragma unroll 2
   for (int l = 0; l < L; ++l) {
     const float res = gr.res[l];
     Cell c = grid_cell(g.x, g.y, g.z, res);
@@ -160,16 +159,16 @@ NFF_D void encode_f4_regs(const float* NFF_RESTRICT table, const Grid& gr, Gauss
     float f[8];
 #pragma unroll
     for (int k = 0; k < 8; ++k) f[k] = v[k].x;
-    x[4 * l + 0] = fmul(trilerp_f(f, c, ix, iy, iz), w);
+    x[(4 * l + 0) * kLaneThreads] = fmul(trilerp_f(f, c, ix, iy, iz), w);
 #pragma unroll
     for (int k = 0; k < 8; ++k) f[k] = v[k].y;
-    x[4 * l + 1] = fmul(trilerp_f(f, c, ix, iy, iz), w);
+    x[(4 * l + 1) * kLaneThreads] = fmul(trilerp_f(f, c, ix, iy, iz), w);
 #pragma unroll
     for (int k = 0; k < 8; ++k) f[k] = v[k].z;
-    x[4 * l + 2] = fmul(trilerp_f(f, c, ix, iy, iz), w);
+    x[(4 * l + 2) * kLaneThreads] = fmul(trilerp_f(f, c, ix, iy, iz), w);
 #pragma unroll
     for (int k = 0; k < 8; ++k) f[k] = v[k].w;
-    x[4 * l + 3] = fmul(trilerp_f(f, c, ix, iy, iz), w);
+    x[(4 * l + 3) * kLaneThreads] = fmul(trilerp_f(f, c, ix, iy, iz), w);
   }
 }
 
@@ -186,12 +185,13 @@ struct LaneRoundIO {
   float* tr_bins_e;
   int32_t* tr_inds;
 };
-template <class EdgeFn>
+// `bins_in` == nullptr: level-0 edges torch.linspace(0, 1, S+1); else the scratch column written by the previous round.
 NFF_D float lane_proposal_round(const RenderParams& P, const FieldGrids& fg, const LaneScratch& sc, int tid, int n_cand,
-                                const LaneRoundIO& io, EdgeFn edge, const float o[3], const float d[3], float area,
+                                const LaneRoundIO& io, const float* bins_in, const float o[3], const float d[3], float area,
                                 float s_near, float s_far, int64_t ray) {
   const Sampling& sp = P.samp;
   const int S = io.S, S_new = io.S_new;
+  auto edge = [bins_in, S](int i) { return bins_in ? bins_in[(size_t)i * kLaneThreads] : linspace01(i, S); };
   // running sums are kept in double: torch's CPU cumsum/cumprod (the oracle) accumulate in double
   // (acc_type<float, false>) and round per element; a sequential fp32 sum of 128 terms would be ~20x noisier
   double excl = 0.0, tot_d = 0.0;
@@ -253,6 +253,8 @@ NFF_D float lane_proposal_round(const RenderParams& P, const FieldGrids& fg, con
 // Input: the 32 grid features of this lane's sample in registers.  CUDA-core version (host emulation / fp32 mode):
 struct MlpLaneFfma {
   const float* w;  // packed transposed weights (nff_params.h)
+  float* panel_;   // [kNff][kLaneThreads]
+  NFF_D float* panel() const { return panel_; }
   NFF_D void run(const float* x, const float dir[3], float& sdf, float* feat, int /*tid*/) const {
     float h[kHidden], go[kNff + 1], in2[kNff + kSh], h2[kHidden];
     dense<kGeoIn, kHidden, kHidden, true>(w + kOffGeoW0, w + kOffGeoB0, x, h);
@@ -273,7 +275,8 @@ struct MlpLaneFfma {
 // Tensor-core version: tile = 128 rays x this sample index; geo_embedding is parked in shared memory for the residual.
 struct MlpLaneTc {
   MlpTc core;
-  float* geo_park;  // [kNff][kLaneThreads] shared memory
+  float* geo_park;  // [kNff][kLaneThreads] shared memory: grid-feature panel first, then the parked geo_embedding
+  NFF_D float* panel() const { return geo_park; }
   NFF_D void run(const float* x, const float dir[3], float& sdf, float* feat, int tid) {
     float h[kHidden], in2[kNff + kSh];
     core.layer<32>(0, x, h);
@@ -326,26 +329,23 @@ NFF_D void render_ray_lane(const RenderParams& P, const LaneScratch& sc, Mlp& ml
   if (overflow && P.status) atomicExch(P.status, 3);
 #endif
 
-  float prop_depth_0, prop_depth_1;
-  {
-    LaneRoundIO io{kS0, kS1, sp.u1, sc.bins1,
-                   active ? P.trace.prop_weights_0 : nullptr, active ? P.trace.actor_id_0 : nullptr,
-                   active ? P.trace.bins_s_1 : nullptr, active ? P.trace.bins_e_1 : nullptr,
-                   active ? P.trace.inds_1 : nullptr};
-    auto edge0 = [](int i) { return linspace01(i, kS0); };
-    prop_depth_0 = lane_proposal_round(P, P.fields[sp.field_of_round[0]], sc, tid, n_cand, io, edge0, o, d, area, s_near,
-                                       s_far, ray);
+  float prop_depth[2];
+#pragma unroll 1
+  for (int rd = 0; rd < 2; ++rd) {  // one copy of the round's code for both rounds (instruction-cache footprint)
+    LaneRoundIO io;
+    io.S = rd == 0 ? kS0 : kS1;
+    io.S_new = rd == 0 ? kS1 : kS2;
+    io.u_tab = rd == 0 ? sp.u1 : sp.u2;
+    io.bins_out = rd == 0 ? sc.bins1 : sc.bins2;
+    io.tr_w = !active ? nullptr : rd == 0 ? P.trace.prop_weights_0 : P.trace.prop_weights_1;
+    io.tr_aid = !active ? nullptr : rd == 0 ? P.trace.actor_id_0 : P.trace.actor_id_1;
+    io.tr_bins_s = !active ? nullptr : rd == 0 ? P.trace.bins_s_1 : P.trace.bins_s_2;
+    io.tr_bins_e = !active ? nullptr : rd == 0 ? P.trace.bins_e_1 : P.trace.bins_e_2;
+    io.tr_inds = !active ? nullptr : rd == 0 ? P.trace.inds_1 : P.trace.inds_2;
+    prop_depth[rd] = lane_proposal_round(P, P.fields[sp.field_of_round[rd]], sc, tid, n_cand, io,
+                                         rd == 0 ? nullptr : sc.bins1 + tid, o, d, area, s_near, s_far, ray);
   }
-  {
-    LaneRoundIO io{kS1, kS2, sp.u2, sc.bins2,
-                   active ? P.trace.prop_weights_1 : nullptr, active ? P.trace.actor_id_1 : nullptr,
-                   active ? P.trace.bins_s_2 : nullptr, active ? P.trace.bins_e_2 : nullptr,
-                   active ? P.trace.inds_2 : nullptr};
-    const float* b1 = sc.bins1 + tid;
-    auto edge1 = [b1](int i) { return b1[(size_t)i * kLaneThreads]; };
-    prop_depth_1 = lane_proposal_round(P, P.fields[sp.field_of_round[1]], sc, tid, n_cand, io, edge1, o, d, area, s_near,
-                                       s_far, ray);
-  }
+  const float prop_depth_0 = prop_depth[0], prop_depth_1 = prop_depth[1];
 
   // ---- main field: loop over the 32 samples of this ray (fields/neurad_field.py:128-152 + compositing) ----
   const FieldGrids& fm = P.fields[B200NERF_FIELD_MAIN];
@@ -362,7 +362,7 @@ NFF_D void render_ray_lane(const RenderParams& P, const LaneScratch& sc, Mlp& ml
     e_prev = e1;
     if (s == kS2 - 1) e1 = fadd(e1, fsub(sp.sky_distance, e1));  // sky sample (neurad.py:451-455)
     Gauss g = sample_gaussian(o, d, area, e0, e1);
-    float x[kGeoIn];
+    float* col = mlp.panel() + tid;  // this thread's column of the [32][kLaneThreads] shared panel
     float dir[3] = {d[0], d[1], d[2]};
     int aid = -1;
     {
@@ -372,8 +372,8 @@ NFF_D void render_ray_lane(const RenderParams& P, const LaneScratch& sc, Mlp& ml
         Gauss ga = {pb[0], pb[1], pb[2], g.std};
         ga = contract(ga, fm.actor_scale);
 #pragma unroll
-        for (int i = 16; i < 32; ++i) x[i] = 0.0f;  // F.pad(actor_features, (0, 32-16))
-        encode_f4_regs<4>(fm.actor_tables[aid], fm.act, ga, x);
+        for (int i = 16; i < 32; ++i) col[i * kLaneThreads] = 0.0f;  // F.pad(actor_features, (0, 32-16))
+        encode_f4_col(fm.actor_tables[aid], fm.act, 4, ga, col);
         float q0 = fadd(fadd(fmul(M[0], d[0]), fmul(M[1], d[1])), fmul(M[2], d[2]));
         float q1 = fadd(fadd(fmul(M[4], d[0]), fmul(M[5], d[1])), fmul(M[6], d[2]));
         float q2 = fadd(fadd(fmul(M[8], d[0]), fmul(M[9], d[1])), fmul(M[10], d[2]));
@@ -381,9 +381,12 @@ NFF_D void render_ray_lane(const RenderParams& P, const LaneScratch& sc, Mlp& ml
         dir[0] = fdiv(q0, n); dir[1] = fdiv(q1, n); dir[2] = fdiv(q2, n);
       } else {
         Gauss gs = contract(g, fm.static_scale);
-        encode_f4_regs<8>(fm.stat.table, fm.stat, gs, x);
+        encode_f4_col(fm.stat.table, fm.stat, 8, gs, col);
       }
     }
+    float x[kGeoIn];
+#pragma unroll
+    for (int i = 0; i < kGeoIn; ++i) x[i] = col[i * kLaneThreads];
     float sdf, feat[kNff];
     mlp.run(x, dir, sdf, feat, tid);
     const float alpha = frcp(fadd(1.0f, expf(fmul(sdf, P.beta))));

@@ -138,7 +138,8 @@ int emul_render(const void* const* ptrs, const int* ints, const float* floats, l
     // ray-per-lane variant: no warp collectives, so plain sequential execution of every "thread" is exact
     std::vector<float> scratch(lane_scratch_floats_per_cta());
     LaneScratch sc = lane_scratch_of(scratch.data(), 0);
-    MlpLaneFfma pol{mlp.data()};
+    std::vector<float> panel((size_t)kNff * kLaneThreads);
+    MlpLaneFfma pol{mlp.data(), panel.data()};
     for (long long r = 0; r < n_rays; ++r) render_ray_lane(P, sc, pol, (int)(r % kLaneThreads), r, true);
     return 0;
   }

@@ -31,7 +31,7 @@ def main():
     asm = subprocess.run(["nvdisasm", "-gi", "-c", os.path.join(d, cubin)], capture_output=True, text=True).stdout.split("\n")
     csrc = os.path.join(os.path.dirname(os.path.abspath(so)), "..", "csrc")
     ranges = {}
-    for f in ("nff_device.h", "tc_mlp.cuh"):
+    for f in ("nff_device.h", "nff_lane.h", "tc_mlp.cuh"):
         ranges[f] = function_ranges(os.path.join(csrc, f))
     def fn_of(file, line):
         for a, b, n in ranges.get(os.path.basename(file), []):
@@ -71,7 +71,7 @@ def main():
         # innermost meaningful function, skipping tiny wrappers
         skip = {"fmul", "fadd", "fsub", "fdiv", "frcp", "fsqrt", "ldg", "lane", "shfl", "shfl_up", "blend", "smem_u32", "tf32_hi"}
         inner = next((n for n in names if n not in skip), "kernel-body")
-        phase = "proposal" if "proposal_round" in names else ("mlp" if ("run" in names or "layer" in names) else "main/other")
+        phase = "proposal" if ("proposal_round" in names or "lane_proposal_round" in names) else ("mlp" if ("run" in names or "layer" in names) else "main/other")
         key = f"{phase:10s} {inner}"
         ie = int(r[idx["Instructions Executed"]] or 0); sm = int(r[idx["# Samples"]] or 0)
         agg_inst[key] += ie; agg_samp[key] += sm; tot_i += ie; tot_s += sm
