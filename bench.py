@@ -363,7 +363,7 @@ def main():
                 e2e={"value": e2e_value, "unit": "rays/s", "h2d_bytes_per_step": step.h2d_bytes, "d2h_bytes_per_step": step.d2h_bytes,
                      "ms_per_step": ms_e2e / args.steps},
                 roofline={"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                          "traffic": None, "kernel": "nff_render_tc_kernel<8>", "kernel_ms": kern_ms, "peak_source": peak_src,
+                          "traffic": None, "kernel": "nff_render_lane_kernel", "kernel_ms": kern_ms, "peak_source": peak_src,
                           "algorithmic_bytes_per_ray": ALGO_BYTES_PER_RAY})
     traffic_file = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(traffic_file):
