@@ -136,7 +136,7 @@ class Step:
         if time_kernel:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-        self.be.render(rays, out=out)
+        self.be.render(rays, out=out, image_width=640)
         self.launches += 1
         if time_kernel:
             e1.record()
@@ -164,25 +164,21 @@ class Step:
         for a, b in bounds:
             rays = {k: v[a:b] for k, v in self.rays.items()}
             rays["sensor_idx"], rays["is_lidar"] = self.sensor[a:b], self.is_lidar[a:b]
-            self.be.render(rays, out={k: v[a:b] for k, v in out.items()})
+            self.be.render(rays, out={k: v[a:b] for k, v in out.items()}, image_width=640 if b <= self.n_cam else 1800)
             self.launches += 1
-            if self.world == 1:
-                ev = torch.cuda.Event()
-                ev.record(main)
-                self._copy_stream.wait_event(ev)
-                with torch.cuda.stream(self._copy_stream):
-                    for k in self.host_out:
-                        self.host_out[k][a:b].copy_(out[k][a:b], non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(main)
+            self._copy_stream.wait_event(ev)
+            with torch.cuda.stream(self._copy_stream):
+                for k in self.host_out:
+                    self.host_out[k][a:b].copy_(out[k][a:b], non_blocking=True)
         if self.world > 1:
             import torch.distributed as dist
 
             for k, buf in self.gather.items():
                 dist.all_gather_into_tensor(buf.view(-1), buf[self.rank].reshape(-1))
-            for k in self.host_out:
-                self.host_out[k].copy_(out[k], non_blocking=True)
             main.synchronize()
-        else:
-            self._copy_stream.synchronize()
+        self._copy_stream.synchronize()
         return self.host_out
 
     @property
@@ -270,7 +266,7 @@ def main():
         "metric": "rays/sec (camera+lidar)", "unit": "rays/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": WORKLOAD, "rays_per_step_per_gpu": 6 * CAM_RAYS + 115200, "tables": "fp32, main 8x2^22x4 + proposal 6x2^20x1 (U(-1,1))",
-                   "l2": "inputs larger than L2 (560 MB of tables, 300 MB of outputs per step); no explicit flush", "parallelism": f"ray-shard dp{world}"},
+                   "l2": "inputs larger than L2 (560 MB of tables, 300 MB of outputs per step); no explicit flush", "kernel": "ray-per-lane, 2-D tile walk (image_width=640), tcgen05 3xTF32 MLPs", "parallelism": f"ray-shard dp{world}"},
     }
 
     if args.impl == "reference":

@@ -119,6 +119,10 @@ typedef struct {
   const float* fars;         /* [N] or NULL -> 1e6, clamped to sky_distance (neurad.py:445-448) */
   const int64_t* sensor_idx; /* [N] or NULL -> fallback sensor 0 (metadata["sensor_idxs"], neurad.py:424-427) */
   const uint8_t* is_lidar;   /* [N] or NULL -> all camera rays (metadata["is_lidar"]) */
+  int32_t image_width;       /* 0: no hint.  W > 0: the bundle is a row-major image (or stack of images) with W rays
+                                per row; the kernel then walks it in 32x8-pixel tiles (a warp = an 8x4 patch) so that
+                                the rays of a warp are neighbours in BOTH image directions.  Results are written at
+                                the rays' own indices, i.e. the output order is unchanged. */
 } b200nerf_rays;
 
 typedef struct {
@@ -218,6 +222,15 @@ int b200nerf_raygen_lidar_points(b200nerf_ctx* ctx, const float* l2w_host, const
                                  int64_t n_points, float scan_time, const float* velocity_host, float h_div,
                                  float v_div, float* origins, float* directions, float* pixel_area, float* times,
                                  float* distance, void* stream);
+
+/* Beam x azimuth lidar ray grid with a rolling-shutter sweep (viewer/render_state_machine.py:395-407 for the
+ * directions; cameras/lidars.py:421-423, 625-639 for the per-ray time offset `(azimuth/2pi - 0.5) * revolution_time`
+ * and the origin shift `velocity * dt`).  Elevations = linspace(elev_min, elev_max, beams), azimuths = i *
+ * azimuth_step.  Outputs [beams*n_azimuth, ...] in beam-major order.  BASELINE config 4's input shape (128 x 2048). */
+int b200nerf_raygen_lidar_grid(b200nerf_ctx* ctx, const float* l2w_host, float elev_min_rad, float elev_max_rad,
+                               int beams, int n_azimuth, double azimuth_step_rad, float scan_time,
+                               float revolution_time, const float* velocity_host, float h_div, float v_div,
+                               float* origins, float* directions, float* pixel_area, float* times, void* stream);
 
 #ifdef __cplusplus
 }

@@ -153,18 +153,21 @@ class B200Backend:
 
     # ------------------------------------------------------------------------------------------ fused path
     def render(self, rays: Dict[str, torch.Tensor], want_trace: bool = False, want_intensity: bool = False,
-               out: Optional[Dict[str, torch.Tensor]] = None) -> Dict[str, torch.Tensor]:
+               out: Optional[Dict[str, torch.Tensor]] = None, image_width: int = 0) -> Dict[str, torch.Tensor]:
         """NeuRADModel.get_nff_outputs (models/neurad.py:368-421) for a flat ray batch.
 
         rays: origins [N,3], directions [N,3], pixel_area [N,1]|[N], times [N,1]|[N] and optionally nears, fars,
         sensor_idx (int64), is_lidar (bool/uint8).  Returns features [N,48], depth/accumulation/prop_depth_i [N,1].
-        `out` may supply pre-allocated output tensors (e.g. a slice of an all-gather buffer)."""
+        `out` may supply pre-allocated output tensors (e.g. a slice of an all-gather buffer).  `image_width` > 0
+        declares the bundle a row-major image (stack) of that width so that the kernel can walk it in 2-D tiles
+        (better gather coherence); it does not change the output order."""
         cfg = self.cfg
         if cfg is None:
             raise RuntimeError("load_params() must be called before render()")
         o = self._dev(rays["origins"])
         n = o.shape[0]
         r = Rays()
+        r.image_width = int(image_width)
         hold = [o]
 
         def put(name, key, dtype=torch.float32, required=False):
@@ -347,3 +350,24 @@ class B200Backend:
         if out is None:  # metadata["did_return"] (lidars.py:447); skipped on the pre-allocated hot path
             res["did_return"] = dist < 1e3
         return res
+
+    def raygen_lidar_grid(self, l2w: torch.Tensor, elev_min_deg: float, elev_max_deg: float, beams: int, azim_res_deg: float,
+                          scan_time: float, revolution_time: float = 0.1, velocity: Optional[torch.Tensor] = None,
+                          out: Optional[Dict[str, torch.Tensor]] = None) -> Dict[str, torch.Tensor]:
+        """Beam x azimuth lidar grid with rolling shutter (BASELINE config 4 input: 128 beams x 2048 azimuths)."""
+        import math
+
+        import numpy as np
+
+        step = float(np.deg2rad(azim_res_deg))
+        n_az = int(math.ceil((2 * math.pi) / step))  # len(torch.arange(0, 2*pi, step))
+        n = beams * n_az
+        o, d, a, t = self._ray_buffers(n, out)
+        cl2w = (ctypes.c_float * 12)(*l2w.reshape(-1).tolist())
+        vel = (ctypes.c_float * 3)(*velocity.tolist()) if velocity is not None else None
+        e0, e1 = (float(v) for v in np.deg2rad((elev_min_deg, elev_max_deg)).astype(np.float32))
+        self._check(
+            self.lib.b200nerf_raygen_lidar_grid(self._h, cl2w, e0, e1, beams, n_az, step, scan_time, revolution_time, vel,
+                                                3.0e-3, 1.5e-3, _ptr(o), _ptr(d), _ptr(a), _ptr(t), self._stream)
+        )
+        return {"origins": o, "directions": d, "pixel_area": a, "times": t, "shape": (beams, n_az)}

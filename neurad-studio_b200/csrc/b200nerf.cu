@@ -172,11 +172,27 @@ __global__ void __launch_bounds__(kLaneThreads, 2) nff_render_lane_kernel(const 
   mlp.core.status = P.status;
   mlp.geo_park = geo_park;
   const LaneScratch sc = lane_scratch_of(scratch, blockIdx.x);
-  const int64_t stride = (int64_t)gridDim.x * kLaneThreads;
-  for (int64_t base = (int64_t)blockIdx.x * kLaneThreads; base < P.n_rays; base += stride) {
-    const int64_t ray = base + tid;
-    const bool active = ray < P.n_rays;
-    render_ray_lane(P, sc, mlp, tid, active ? ray : P.n_rays - 1, active);
+  const int W = P.rays.image_width;
+  if (W > 0) {
+    // 2-D walk: a CTA renders a 32x8-pixel tile, a warp an 8x4 patch of it
+    const int64_t H = (P.n_rays + W - 1) / W;
+    const int64_t tiles_x = (W + 31) / 32, tiles = tiles_x * ((H + 7) / 8);
+    const int lane_ = tid & 31;
+    const int dx = (warp & 3) * 8 + (lane_ & 7), dy = (warp >> 2) * 4 + (lane_ >> 3);
+    for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+      const int64_t px = (tile % tiles_x) * 32 + dx, py = (tile / tiles_x) * 8 + dy;
+      const int64_t ray = py * W + px;
+      const bool active = px < W && ray < P.n_rays;
+      const int64_t cl = (py < H ? py : H - 1) * W + (px < W ? px : W - 1);
+      render_ray_lane(P, sc, mlp, tid, active ? ray : (cl < P.n_rays ? cl : P.n_rays - 1), active);
+    }
+  } else {
+    const int64_t stride = (int64_t)gridDim.x * kLaneThreads;
+    for (int64_t base = (int64_t)blockIdx.x * kLaneThreads; base < P.n_rays; base += stride) {
+      const int64_t ray = base + tid;
+      const bool active = ray < P.n_rays;
+      render_ray_lane(P, sc, mlp, tid, active ? ray : P.n_rays - 1, active);
+    }
   }
   tc::fence_before_sync();
   __syncthreads();
@@ -518,6 +534,49 @@ __global__ void raygen_lidar_kernel(LidarArgs a, const float* __restrict__ pts, 
   if (distance) distance[i] = nrm;
 }
 
+
+// Beam x azimuth lidar ray grid (viewer/render_state_machine.py:395-407: d = (cos v cos h, cos v sin h, sin v) over
+// linspace elevations x arange azimuths) with a rolling-shutter sweep: per-ray time offset linear in azimuth over one
+// revolution and origin shifted by velocity * dt (cameras/lidars.py:421-423, 625-639).  BASELINE config 4's input shape.
+struct LidarGridArgs {
+  float l2w[12];
+  float elev0, elev1;   // radians
+  double az_step;       // radians (torch.arange evaluates start + i*step in double, then casts)
+  int beams, n_az;
+  float scan_time, rev_time, vel[3], h_div, v_div;
+  int has_vel;
+};
+__global__ void raygen_lidar_grid_kernel(LidarGridArgs a, float* __restrict__ origins, float* __restrict__ dirs,
+                                         float* __restrict__ area, float* __restrict__ times) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (int64_t)a.beams * a.n_az) return;
+  const int b = (int)(i / a.n_az), k = (int)(i % a.n_az);
+  // torch.linspace(e0, e1, beams): start + step*i for the first half, end - step*(n-1-i) for the second
+  const float step = a.beams > 1 ? fdiv(fsub(a.elev1, a.elev0), (float)(a.beams - 1)) : 0.f;
+  const float v = b < a.beams / 2 ? fadd(a.elev0, fmul(step, (float)b)) : fsub(a.elev1, fmul(step, (float)(a.beams - 1 - b)));
+  const float h = (float)((double)k * a.az_step);
+  const float cv = cosf(v), sv = sinf(v), ch = cosf(h), sh = sinf(h);
+  const float dl[3] = {fmul(cv, ch), fmul(cv, sh), sv};
+  float d[3], o[3];
+#pragma unroll
+  for (int r = 0; r < 3; ++r) {
+    d[r] = fadd(fadd(fmul(a.l2w[4 * r], dl[0]), fmul(a.l2w[4 * r + 1], dl[1])), fmul(a.l2w[4 * r + 2], dl[2]));
+    o[r] = a.l2w[4 * r + 3];
+  }
+  const float dt = fmul(fsub(fdiv(h, 6.283185307179586f), 0.5f), a.rev_time);
+  if (a.has_vel) {
+#pragma unroll
+    for (int r = 0; r < 3; ++r) o[r] = fadd(o[r], fmul(dt, a.vel[r]));
+  }
+#pragma unroll
+  for (int r = 0; r < 3; ++r) {
+    origins[3 * i + r] = o[r];
+    dirs[3 * i + r] = d[r];
+  }
+  area[i] = fmul(a.h_div, a.v_div);
+  times[i] = fadd(a.scan_time, dt);
+}
+
 // ===================================================================================================== C ABI
 extern "C" {
 
@@ -757,6 +816,7 @@ int b200nerf_nff_render_fwd(b200nerf_ctx* c, const b200nerf_rays* rays, int64_t 
                             const b200nerf_trace* trace, void* stream) {
   REQUIRE(c && rays && out, "NULL argument");
   REQUIRE(n_rays >= 0, "negative ray count");
+  REQUIRE(rays->image_width >= 0, "negative image_width");
   if (!(c->have_field[0] && c->have_main_mlp && c->have_samp && c->have_app))
     return fail(B200NERF_ERR_STATE, "set_field_grids(MAIN), set_main_mlps, set_sampling and set_appearance are required");
   for (int i = 0; i < 2; ++i) {
@@ -797,6 +857,10 @@ int b200nerf_nff_render_fwd(b200nerf_ctx* c, const b200nerf_rays* rays, int64_t 
   if (c->mlp_mode == 2) {
     const size_t smem = (sizeof(TcShared) + 127) / 128 * 128 + sizeof(float) * kNff * kLaneThreads;
     int64_t need = (n_rays + kLaneThreads - 1) / kLaneThreads;
+    if (rays->image_width > 0) {
+      const int64_t W = rays->image_width, H = (n_rays + W - 1) / W;
+      need = ((W + 31) / 32) * ((H + 7) / 8);
+    }
     int lane_blocks = (int)(need < c->lane_ctas ? need : c->lane_ctas);
     nff_render_lane_kernel<<<lane_blocks, kLaneThreads, smem, st>>>(P, c->d_lane_scratch);
   } else if (c->mlp_mode == 1) {
@@ -976,6 +1040,27 @@ int b200nerf_raygen_lidar_points(b200nerf_ctx* c, const float* l2w_host, const f
   if (velocity_host) memcpy(a.vel, velocity_host, sizeof(float) * 3);
   raygen_lidar_kernel<<<(unsigned)((n_points + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
       a, points, n_points, origins, directions, pixel_area, times, distance);
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+
+int b200nerf_raygen_lidar_grid(b200nerf_ctx* c, const float* l2w_host, float elev_min_rad, float elev_max_rad, int beams,
+                               int n_azimuth, double azimuth_step_rad, float scan_time, float revolution_time,
+                               const float* velocity_host, float h_div, float v_div, float* origins, float* directions,
+                               float* pixel_area, float* times, void* stream) {
+  REQUIRE(c && l2w_host && origins && directions && pixel_area && times, "NULL argument");
+  REQUIRE(beams >= 1 && n_azimuth >= 1, "bad lidar grid");
+  DeviceGuard g(c->device);
+  LidarGridArgs a{};
+  memcpy(a.l2w, l2w_host, sizeof(float) * 12);
+  a.elev0 = elev_min_rad; a.elev1 = elev_max_rad; a.az_step = azimuth_step_rad;
+  a.beams = beams; a.n_az = n_azimuth;
+  a.scan_time = scan_time; a.rev_time = revolution_time; a.h_div = h_div; a.v_div = v_div;
+  a.has_vel = velocity_host != nullptr;
+  if (velocity_host) memcpy(a.vel, velocity_host, sizeof(float) * 3);
+  int64_t n = (int64_t)beams * n_azimuth;
+  raygen_lidar_grid_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(a, origins, directions, pixel_area, times);
   CUDA_TRY(cudaGetLastError());
   return 0;
 }

@@ -4,7 +4,7 @@ from __future__ import annotations
 
 import ctypes
 import os
-from ctypes import POINTER, c_char_p, c_float, c_int, c_int32, c_int64, c_uint8, c_void_p
+from ctypes import POINTER, c_char_p, c_double, c_float, c_int, c_int32, c_int64, c_uint8, c_void_p
 
 from . import build as _build
 
@@ -23,7 +23,7 @@ class GridDesc(ctypes.Structure):
 
 class Rays(ctypes.Structure):
     _fields_ = [(n, c_void_p) for n in
-                ("origins", "directions", "pixel_area", "times", "nears", "fars", "sensor_idx", "is_lidar")]
+                ("origins", "directions", "pixel_area", "times", "nears", "fars", "sensor_idx", "is_lidar")] + [("image_width", c_int32)]
 
 
 class Outputs(ctypes.Structure):
@@ -70,6 +70,9 @@ SIGNATURES = {
     "b200nerf_raygen_pinhole": (c_int, [c_void_p, POINTER(c_float), c_float, c_float, c_float, c_float, c_int, c_int,
                                         c_int, c_int, c_int, c_int, c_int, c_int, c_float, POINTER(c_float), c_float,
                                         c_float, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "b200nerf_raygen_lidar_grid": (c_int, [c_void_p, POINTER(c_float), c_float, c_float, c_int, c_int, c_double, c_float,
+                                           c_float, POINTER(c_float), c_float, c_float, c_void_p, c_void_p, c_void_p,
+                                           c_void_p, c_void_p]),
     "b200nerf_raygen_lidar_points": (c_int, [c_void_p, POINTER(c_float), c_void_p, c_int, c_int64, c_float,
                                              POINTER(c_float), c_float, c_float, c_void_p, c_void_p, c_void_p,
                                              c_void_p, c_void_p, c_void_p]),

@@ -759,3 +759,22 @@ def generate_rays_lidar_grid(elev_min_deg: float, elev_max_deg: float, beams: in
         [torch.cos(v_angles) * torch.cos(h_angles), torch.cos(v_angles) * torch.sin(h_angles), torch.sin(v_angles)],
         dim=-1,
     )
+
+
+def generate_rays_lidar_grid_rs(l2w: Tensor, elev_min_deg: float, elev_max_deg: float, beams: int, azim_res_deg: float,
+                                scan_time: float, revolution_time: float = 0.1, velocity: Optional[Tensor] = None):
+    """BASELINE config 4 input: the viewer's beam x azimuth grid (above) swept with a rolling
+    shutter -- per-ray time offset linear in azimuth over one revolution and origin shifted by velocity * dt
+    (cameras/lidars.py:421-423, 625-639); pixel_area = the lidar beam divergence product (lidars.py:46-47)."""
+    v_angles = torch.linspace(*np.deg2rad((elev_min_deg, elev_max_deg)), beams)
+    h_angles = torch.arange(0, 2 * np.pi, np.deg2rad(azim_res_deg))
+    v, h = torch.meshgrid(v_angles, h_angles, indexing="ij")
+    v, h = v.flatten(), h.flatten()
+    d_l = torch.stack([torch.cos(v) * torch.cos(h), torch.cos(v) * torch.sin(h), torch.sin(v)], dim=-1)
+    directions = d_l @ l2w[:3, :3].T
+    dt = ((h / (2 * np.pi) - 0.5) * revolution_time)[:, None]
+    origins = l2w[:3, 3].expand(d_l.shape[0], 3)
+    if velocity is not None:
+        origins = origins + dt * velocity
+    return {"origins": origins, "directions": directions, "pixel_area": torch.full((d_l.shape[0], 1), 3.0e-3 * 1.5e-3),
+            "times": scan_time + dt}

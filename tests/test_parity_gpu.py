@@ -276,6 +276,14 @@ def test_full_size_properties(backend):
     backend.check_status()
     assert torch.equal(o3["features"], out["features"][1000:2003])
     assert torch.equal(o3["depth"], out["depth"][1000:2003])
+    # the 2-D tile walk (image_width hint) must not change any result: same rays, same per-ray arithmetic
+    o5 = backend.render(rays, image_width=640)
+    backend.check_status()
+    for k in ("features", "depth", "accumulation", "prop_depth_0", "prop_depth_1"):
+        assert torch.equal(o5[k], out[k]), k
+    o6 = backend.render(sub, image_width=77)  # ragged: 1003 rays = 13 rows of 77 + 2
+    for k in ("features", "depth"):
+        assert torch.equal(o6[k], o3[k]), k
     # the kernel variants agree to fp32 level on the whole image
     for mode in ("ffma", "tc"):
         backend.set_mlp_mode(mode)
@@ -389,3 +397,34 @@ def test_module_mirrors_hashencoding_mlp_sh():
     sh = SHEncoding(levels=4)
     d = torch.rand(10, 3, device="cuda")
     assert (sh(d).cpu() - O.sh_components_l4(d.cpu())).abs().max().item() < 2e-6
+
+
+def test_config4_lidar_grid_rolling_shutter(backend):
+    """BASELINE config 4: 128 beams x 2048 azimuths with a rolling-shutter sweep -> 262 144 rays through the
+    volumetric path; ray generation vs the oracle, render vs the oracle on a strided subsample, intensity in (0,1)."""
+    l2w = torch.zeros(3, 4)
+    l2w[:, :3] = torch.eye(3)
+    l2w[:, 3] = torch.tensor([3.0, -1.0, 2.0])
+    vel = torch.tensor([10.0, 0.5, 0.0])
+    rays = backend.raygen_lidar_grid(l2w, -25.0, 15.0, 128, 360.0 / 2048, scan_time=3.2, velocity=vel)
+    assert rays.pop("shape") == (128, 2048)
+    ref = O.generate_rays_lidar_grid_rs(l2w, -25.0, 15.0, 128, 360.0 / 2048, 3.2, velocity=vel)
+    for k in ("origins", "directions", "pixel_area", "times"):
+        assert (rays[k].cpu().reshape(ref[k].shape) - ref[k]).abs().max().item() < 2e-6, k
+    cfg = nsb.small_config(n_actors=0, log2_main=16, log2_prop=14)
+    params = scene.make_params(cfg, seed=51, beta=3.0, sdf_bias=0.6)
+    backend.load_params(cfg, params)
+    n = rays["origins"].shape[0]
+    rays["sensor_idx"] = torch.full((n, 1), 6, dtype=torch.long, device="cuda")
+    rays["is_lidar"] = torch.ones(n, 1, dtype=torch.uint8, device="cuda")
+    out = backend.render(rays, want_intensity=True, image_width=2048)
+    backend.check_status()
+    assert torch.isfinite(out["features"]).all() and ((out["intensity"] > 0) & (out["intensity"] < 1)).all()
+    sel = torch.arange(0, n, 257)
+    with torch.no_grad():
+        o = O.nff_outputs(params, to_oracle_cfg(cfg), ref["origins"][sel], ref["directions"][sel], ref["pixel_area"][sel],
+                          ref["times"][sel], torch.full((sel.numel(), 1), 6), torch.ones(sel.numel(), 1, dtype=torch.bool))
+        inten, _ = O.decode_lidar(params, o["features"])
+    for k in ("features", "depth", "accumulation"):
+        assert rel_to_max(out[k][sel.cuda()], o[k]) < 1e-4, (k, rel_to_max(out[k][sel.cuda()], o[k]))
+    assert rel_to_max(out["intensity"][sel.cuda()], inten) < 1e-4

@@ -36,13 +36,14 @@ rays_list.append(r)
 rays = {k: torch.cat([x[k] for x in rays_list]) for k in rays_list[0]}
 N = rays["origins"].shape[0]
 print("rays", N)
+IW = int(os.environ.get("IMAGE_WIDTH", "0"))
 for _ in range(2):
-    be.render(rays)
+    be.render(rays, image_width=IW)
 torch.cuda.synchronize()
 ts = []
 for _ in range(reps):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(); be.render(rays); e1.record(); torch.cuda.synchronize()
+    e0.record(); be.render(rays, image_width=IW); e1.record(); torch.cuda.synchronize()
     ts.append(e0.elapsed_time(e1))
 ms = sorted(ts)[len(ts) // 2]
 print(f"render: {ms:.3f} ms median of {ts}  -> {N / ms / 1e3:.2f} M rays/s; HBM-roofline frac (69.9 kB/ray, 6562.6 GB/s) = {N * 69900 / (ms * 1e-3) / 6562.6e9:.3f}")
