@@ -145,7 +145,7 @@ __global__ void __launch_bounds__(WARPS * 32, 16 / WARPS) nff_render_tc_kernel(c
 
 
 // Ray-per-lane variant (nff_lane.h): a warp = 32 adjacent rays at the same sample index, CTA = 256 rays.
-__global__ void __launch_bounds__(kLaneThreads, 2) nff_render_lane_kernel(const __grid_constant__ RenderParams P,
+__global__ void __launch_bounds__(kLaneThreads, kLaneCtasPerSm) nff_render_lane_kernel(const __grid_constant__ RenderParams P,
                                                                           float* __restrict__ scratch) {
   extern __shared__ __align__(128) unsigned char smem_lane[];
   TcShared* tcs = reinterpret_cast<TcShared*>(smem_lane);
@@ -170,17 +170,18 @@ __global__ void __launch_bounds__(kLaneThreads, 2) nff_render_lane_kernel(const 
   mlp.core.bar_id = 1 + group;
   mlp.core.issuer = (tid & 127) == 0;
   mlp.core.status = P.status;
-  mlp.geo_park = geo_park;
   const LaneScratch sc = lane_scratch_of(scratch, blockIdx.x);
+  mlp.geo_park = NFF_PANEL_GLOBAL ? sc.panel : geo_park;
   const int W = P.rays.image_width;
   if (W > 0) {
-    // 2-D walk: a CTA renders a 32x8-pixel tile, a warp an 8x4 patch of it
+    // 2-D walk: a CTA renders a 32 x (8|16)-pixel tile, a warp an 8x4 patch of it
+    constexpr int kTileH = kLaneThreads / 32;
     const int64_t H = (P.n_rays + W - 1) / W;
-    const int64_t tiles_x = (W + 31) / 32, tiles = tiles_x * ((H + 7) / 8);
+    const int64_t tiles_x = (W + 31) / 32, tiles = tiles_x * ((H + kTileH - 1) / kTileH);
     const int lane_ = tid & 31;
     const int dx = (warp & 3) * 8 + (lane_ & 7), dy = (warp >> 2) * 4 + (lane_ >> 3);
     for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
-      const int64_t px = (tile % tiles_x) * 32 + dx, py = (tile / tiles_x) * 8 + dy;
+      const int64_t px = (tile % tiles_x) * 32 + dx, py = (tile / tiles_x) * kTileH + dy;
       const int64_t ray = py * W + px;
       const bool active = px < W && ray < P.n_rays;
       const int64_t cl = (py < H ? py : H - 1) * W + (px < W ? px : W - 1);
@@ -605,8 +606,8 @@ int b200nerf_create(int device_ordinal, b200nerf_ctx** out) {
   CUDA_TRY(cudaMalloc((void**)&c->d_status, sizeof(int)));
   CUDA_TRY(cudaMemset(c->d_status, 0, sizeof(int)));
   CUDA_TRY(cudaFuncSetAttribute(nff_render_lane_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                (int)((sizeof(TcShared) + 127) / 128 * 128 + sizeof(float) * kNff * kLaneThreads)));
-  c->lane_ctas = c->sm_count * 2;
+                                (int)((sizeof(TcShared) + 127) / 128 * 128 + (NFF_PANEL_GLOBAL ? 0 : sizeof(float) * kNff * kLaneThreads))));
+  c->lane_ctas = c->sm_count * kLaneCtasPerSm;
   CUDA_TRY(cudaMalloc((void**)&c->d_lane_scratch, sizeof(float) * lane_scratch_floats_per_cta() * c->lane_ctas));
   *out = c;
   return 0;
@@ -855,11 +856,11 @@ int b200nerf_nff_render_fwd(b200nerf_ctx* c, const b200nerf_rays* rays, int64_t 
   int blocks = (int)(blocks_needed < max_blocks ? blocks_needed : max_blocks);
   cudaStream_t st = (cudaStream_t)stream;
   if (c->mlp_mode == 2) {
-    const size_t smem = (sizeof(TcShared) + 127) / 128 * 128 + sizeof(float) * kNff * kLaneThreads;
+    const size_t smem = (sizeof(TcShared) + 127) / 128 * 128 + (NFF_PANEL_GLOBAL ? 0 : sizeof(float) * kNff * kLaneThreads);
     int64_t need = (n_rays + kLaneThreads - 1) / kLaneThreads;
     if (rays->image_width > 0) {
       const int64_t W = rays->image_width, H = (n_rays + W - 1) / W;
-      need = ((W + 31) / 32) * ((H + 7) / 8);
+      need = ((W + 31) / 32) * ((H + kLaneThreads / 32 - 1) / (kLaneThreads / 32));
     }
     int lane_blocks = (int)(need < c->lane_ctas ? need : c->lane_ctas);
     nff_render_lane_kernel<<<lane_blocks, kLaneThreads, smem, st>>>(P, c->d_lane_scratch);

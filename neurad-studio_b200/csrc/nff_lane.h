@@ -19,7 +19,14 @@
 
 namespace nff {
 
-constexpr int kLaneThreads = 256;  // threads (= rays in flight) per CTA
+#ifndef NFF_LANE_THREADS
+#define NFF_LANE_THREADS 512
+#endif
+#ifndef NFF_PANEL_GLOBAL
+#define NFF_PANEL_GLOBAL 0  // 1: feature panel / geo park in the global scratch slab instead of shared memory
+#endif
+constexpr int kLaneThreads = NFF_LANE_THREADS;  // threads (= rays in flight) per CTA (256: 2 CTAs/SM, 512: 1 CTA/SM)
+constexpr int kLaneCtasPerSm = 512 / kLaneThreads;
 constexpr int kCandFloats = 16;    // per candidate: 12 (world->box 3x4) + 3 (bounds) + 1 (actor id bits)
 
 // per-CTA slab of the global scratch, all arrays [index][kLaneThreads]
@@ -28,9 +35,10 @@ struct LaneScratch {
   float* bins1;  // [kS1 + 1]   spacing edges after round 0
   float* bins2;  // [kS2 + 1]   spacing edges after round 1
   float* cand;   // [kMaxCand * kCandFloats]
+  float* panel;  // [kNff]      grid-feature panel / parked geo_embedding (when not kept in shared memory)
 };
 NFF_HD size_t lane_scratch_floats_per_cta() {
-  return (size_t)kLaneThreads * (kS0 + (kS1 + 1) + (kS2 + 1) + kMaxCand * kCandFloats);
+  return (size_t)kLaneThreads * (kS0 + (kS1 + 1) + (kS2 + 1) + kMaxCand * kCandFloats + kNff);
 }
 NFF_D LaneScratch lane_scratch_of(float* base, int cta) {
   float* p = base + (size_t)cta * lane_scratch_floats_per_cta();
@@ -39,6 +47,7 @@ NFF_D LaneScratch lane_scratch_of(float* base, int cta) {
   s.bins1 = s.w + (size_t)kS0 * kLaneThreads;
   s.bins2 = s.bins1 + (size_t)(kS1 + 1) * kLaneThreads;
   s.cand = s.bins2 + (size_t)(kS2 + 1) * kLaneThreads;
+  s.panel = s.cand + (size_t)kMaxCand * kCandFloats * kLaneThreads;
   return s;
 }
 
