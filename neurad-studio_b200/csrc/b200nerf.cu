@@ -172,28 +172,31 @@ __global__ void __launch_bounds__(kLaneThreads, kLaneCtasPerSm) nff_render_lane_
   mlp.core.status = P.status;
   const LaneScratch sc = lane_scratch_of(scratch, blockIdx.x);
   mlp.geo_park = NFF_PANEL_GLOBAL ? sc.panel : geo_park;
+  // Work units: with an image_width hint a CTA walks 32 x (threads/32)-pixel tiles and a warp renders an 8x4 patch
+  // (neighbours in both image directions); without it, kLaneThreads consecutive rays.  One call site for both so that
+  // the ~8k-instruction ray body exists once.
   const int W = P.rays.image_width;
-  if (W > 0) {
-    // 2-D walk: a CTA renders a 32 x (8|16)-pixel tile, a warp an 8x4 patch of it
-    constexpr int kTileH = kLaneThreads / 32;
-    const int64_t H = (P.n_rays + W - 1) / W;
-    const int64_t tiles_x = (W + 31) / 32, tiles = tiles_x * ((H + kTileH - 1) / kTileH);
-    const int lane_ = tid & 31;
-    const int dx = (warp & 3) * 8 + (lane_ & 7), dy = (warp >> 2) * 4 + (lane_ >> 3);
-    for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
-      const int64_t px = (tile % tiles_x) * 32 + dx, py = (tile / tiles_x) * kTileH + dy;
-      const int64_t ray = py * W + px;
-      const bool active = px < W && ray < P.n_rays;
-      const int64_t cl = (py < H ? py : H - 1) * W + (px < W ? px : W - 1);
-      render_ray_lane(P, sc, mlp, tid, active ? ray : (cl < P.n_rays ? cl : P.n_rays - 1), active);
+  constexpr int kTileH = kLaneThreads / 32;
+  const int64_t H = W > 0 ? (P.n_rays + W - 1) / W : 0;
+  const int64_t tiles_x = W > 0 ? (W + 31) / 32 : 1;
+  const int64_t units = W > 0 ? tiles_x * ((H + kTileH - 1) / kTileH) : (P.n_rays + kLaneThreads - 1) / kLaneThreads;
+  const int lane_ = tid & 31;
+  const int dx = (warp & 3) * 8 + (lane_ & 7), dy = (warp >> 2) * 4 + (lane_ >> 3);
+  for (int64_t unit = blockIdx.x; unit < units; unit += gridDim.x) {
+    int64_t ray, fallback;
+    bool active;
+    if (W > 0) {
+      const int64_t px = (unit % tiles_x) * 32 + dx, py = (unit / tiles_x) * kTileH + dy;
+      ray = py * W + px;
+      active = px < W && ray < P.n_rays;
+      fallback = (py < H ? py : H - 1) * W + (px < W ? px : W - 1);
+    } else {
+      ray = unit * kLaneThreads + tid;
+      active = ray < P.n_rays;
+      fallback = P.n_rays - 1;
     }
-  } else {
-    const int64_t stride = (int64_t)gridDim.x * kLaneThreads;
-    for (int64_t base = (int64_t)blockIdx.x * kLaneThreads; base < P.n_rays; base += stride) {
-      const int64_t ray = base + tid;
-      const bool active = ray < P.n_rays;
-      render_ray_lane(P, sc, mlp, tid, active ? ray : P.n_rays - 1, active);
-    }
+    if (fallback >= P.n_rays) fallback = P.n_rays - 1;
+    render_ray_lane(P, sc, mlp, tid, active ? ray : fallback, active);
   }
   tc::fence_before_sync();
   __syncthreads();
