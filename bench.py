@@ -97,15 +97,24 @@ def build_workload(cfg, frame: int):
 class Step:
     """The public-API call sequence of one step (what a user of the backend does to render one time step)."""
 
-    def __init__(self, be, cfg, cams, scan, world, rank):
+    def __init__(self, be, cfg, cams, scan, world, rank, gather="p2p"):
         self.be, self.cfg, self.cams, self.scan = be, cfg, cams, scan
         self.n_cam = len(cams) * CAM_RAYS
         self.n = self.n_cam + scan.points.shape[0]
         dev = be.device
         self.world, self.rank = world, rank
         fdim = cfg.feature_dim
-        # the all-gather buffers: every rank's slice is written directly by the render kernel
-        self.gather = {k: torch.empty(world, self.n, w, device=dev) for k, w in (("features", fdim), ("depth", 1), ("accumulation", 1))}
+        # the gather buffers [world, n, w]: every rank's slice is written directly by the render kernel; with
+        # gather="p2p" they live in symmetric memory and the kernel also stores each row into the peers' copies
+        self.p2p = world > 1 and gather == "p2p"
+        if self.p2p:
+            from neurad_studio_b200.dist import PeerGatherBuffers
+
+            self.pg = PeerGatherBuffers(self.n, fdim, dev)
+            self.pg.bind(be)
+            self.gather = self.pg.buf
+        else:
+            self.gather = {k: torch.empty(world, self.n, w, device=dev) for k, w in (("features", fdim), ("depth", 1), ("accumulation", 1))}
         self.local = {k: torch.empty(self.n, 1, device=dev) for k in ("prop_depth_0", "prop_depth_1")}
         self.sensor = torch.cat([torch.full((CAM_RAYS,), c.sensor_idx, dtype=torch.long) for c in cams] +
                                 [torch.full((scan.points.shape[0],), scan.sensor_idx, dtype=torch.long)]).to(dev)
@@ -141,12 +150,19 @@ class Step:
         if time_kernel:
             e1.record()
             self.kernel_events.append((e0, e1))
-        if self.world > 1:
+        self._finish_gather()
+        return out
+
+    def _finish_gather(self):
+        if self.world == 1:
+            return
+        if self.p2p:
+            self.pg.barrier()  # rows were stored into every peer by the render kernel; only a barrier is left
+        else:
             import torch.distributed as dist
 
             for k, buf in self.gather.items():
                 dist.all_gather_into_tensor(buf.view(-1), buf[self.rank].reshape(-1))
-        return out
 
     def run_e2e(self):
         """host buffers in, host buffers out: H2D of the step's inputs and D2H of its results inside the call.
@@ -175,12 +191,8 @@ class Step:
             with torch.cuda.stream(self._copy_stream):
                 for k in self.host_out:
                     self.host_out[k][a:b].copy_(out[k][a:b], non_blocking=True)
-        if self.world > 1:
-            import torch.distributed as dist
-
-            for k, buf in self.gather.items():
-                dist.all_gather_into_tensor(buf.view(-1), buf[self.rank].reshape(-1))
-            main.synchronize()
+        self._finish_gather()
+        main.synchronize()
         self._copy_stream.synchronize()
         return self.host_out
 
@@ -256,6 +268,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--cpu-sample", type=int, default=16384)
+    ap.add_argument("--gather", default="p2p", choices=["p2p", "nccl"],
+                    help="N>1: p2p = render epilogue stores rows into every peer's buffer over NVLink (default); "
+                         "nccl = all_gather_into_tensor after the render")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -269,7 +284,7 @@ def main():
         "metric": "rays/sec (camera+lidar)", "unit": "rays/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": WORKLOAD, "rays_per_step_per_gpu": 6 * CAM_RAYS + 115200, "tables": "fp32, main 8x2^22x4 + proposal 6x2^20x1 (U(-1,1))",
-                   "l2": "inputs larger than L2 (560 MB of tables, 300 MB of outputs per step); no explicit flush", "kernel": "ray-per-lane, 2-D tile walk (image_width=640), tcgen05 3xTF32 MLPs", "parallelism": f"ray-shard dp{world}"},
+                   "l2": "inputs larger than L2 (560 MB of tables, 300 MB of outputs per step); no explicit flush", "kernel": "ray-per-lane, 2-D tile walk (image_width=640), tcgen05 3xTF32 MLPs", "parallelism": f"ray-shard dp{world}" + ("" if world == 1 else f", gather={args.gather}")},
     }
 
     if args.impl == "reference":
@@ -308,7 +323,7 @@ def main():
     params = scene.make_params(cfg, seed=1, beta=3.0, sdf_bias=0.6, device=dev)
     be.load_params(cfg, params)
     cams, scan = build_workload(cfg, rank)
-    step = Step(be, cfg, cams, scan, world, rank)
+    step = Step(be, cfg, cams, scan, world, rank, args.gather)
 
     def barrier():
         if world > 1:

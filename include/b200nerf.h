@@ -135,6 +135,27 @@ typedef struct {
   float* ray_drop_logit; /* [N] or NULL */
 } b200nerf_outputs;
 
+/* Peer gather fused into the render epilogue (multi-GPU, one process per GPU): when set, every rendered ray's
+ * {features, depth, accumulation} row is ALSO stored, from inside the render kernel, at row `row_offset + ray` of each
+ * peer's buffer -- plain st.global on peer-mapped (NVLink / NVSwitch) addresses, e.g. the `buffer_ptrs` of a
+ * torch.distributed._symmetric_memory rendezvous.  This replaces the per-image all-gather: the transfer overlaps the
+ * rendering tile by tile and no NCCL kernel has to wait for the (persistent, all-SM) render kernel to drain.  The
+ * caller still needs a cross-rank barrier before reading.  `self_rank`'s entry is skipped when it equals the local
+ * `b200nerf_outputs` slice.  Reference counterpart: none (the reference renders on one device per process,
+ * pipelines/ad_pipeline.py:197-306). */
+#define B200NERF_MAX_PEERS 8
+typedef struct {
+  int32_t n_peers;   /* 0 disables */
+  int32_t self_rank; /* index into the arrays below that is this rank (skipped), or -1 */
+  int64_t row_offset;
+  float* features[B200NERF_MAX_PEERS];     /* [rows, nff_out_dim + appearance_dim] */
+  float* depth[B200NERF_MAX_PEERS];        /* [rows] */
+  float* accumulation[B200NERF_MAX_PEERS]; /* [rows] */
+} b200nerf_peer_outputs;
+
+/* Applies to subsequent b200nerf_nff_render_fwd calls of this context; NULL clears it. */
+int b200nerf_set_peer_outputs(b200nerf_ctx* ctx, const b200nerf_peer_outputs* peers);
+
 /* Optional per-stage dump used by the parity tests (any member may be NULL). */
 typedef struct {
   float* prop_weights_0; /* [N, n_prop0] */

@@ -11,7 +11,7 @@ import torch
 
 from . import lib as _lib
 from .config import HashGridSettings, NeuRADConfig
-from .lib import FIELD_MAIN, FIELD_PROP0, FIELD_PROP1, GridDesc, Outputs, Rays, Trace, TRACE_FIELDS
+from .lib import FIELD_MAIN, FIELD_PROP0, FIELD_PROP1, GridDesc, Outputs, PeerOutputs, Rays, Trace, TRACE_FIELDS
 
 
 def pdf_quantiles(num_samples: int) -> torch.Tensor:
@@ -270,6 +270,20 @@ class B200Backend:
         """Kernel variant of render(): 'lane' (default) ray-per-lane + tcgen05 MLPs; 'tc' warp-per-ray + tcgen05
         MLPs (3xTF32); 'ffma' warp-per-ray + CUDA-core fp32 MLPs."""
         self._check(self.lib.b200nerf_set_mlp_mode(self._h, {"ffma": 0, "tc": 1, "lane": 2}[mode]))
+
+    def set_peer_outputs(self, peer_ptrs: Optional[Dict[str, Sequence[int]]], self_rank: int = -1, row_offset: int = 0):
+        """Fuse the multi-GPU gather into the render epilogue: `peer_ptrs` maps "features" / "depth" / "accumulation"
+        to one device pointer per rank (peer-mapped, e.g. symmetric-memory `buffer_ptrs`); every rendered row is also
+        stored at `row_offset + ray` of each peer's buffer.  None clears it."""
+        if peer_ptrs is None:
+            self._check(self.lib.b200nerf_set_peer_outputs(self._h, None))
+            return
+        po = PeerOutputs()
+        n = len(peer_ptrs["features"])
+        po.n_peers, po.self_rank, po.row_offset = n, self_rank, row_offset
+        for i in range(n):
+            po.features[i], po.depth[i], po.accumulation[i] = peer_ptrs["features"][i], peer_ptrs["depth"][i], peer_ptrs["accumulation"][i]
+        self._check(self.lib.b200nerf_set_peer_outputs(self._h, ctypes.byref(po)))
 
     def check_status(self):
         """Raise if a kernel set the device-side failure flag (synchronises)."""

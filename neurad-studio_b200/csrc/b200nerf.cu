@@ -42,6 +42,7 @@ struct b200nerf_ctx {
   int mlp_mode = 2;  // 2 = ray-per-lane + tcgen05, 1 = warp-per-ray + tcgen05 (3xTF32), 0 = warp-per-ray + CUDA-core fp32 FFMA
   float* d_lane_scratch = nullptr;
   int lane_ctas = 0;
+  b200nerf_peer_outputs peers{};
   bool have_main_mlp = false;
   float beta = 0.f;
   float* d_lidar_mlp = nullptr;
@@ -852,6 +853,11 @@ int b200nerf_nff_render_fwd(b200nerf_ctx* c, const b200nerf_rays* rays, int64_t 
   P.rays = *rays;
   P.out = *out;
   if (trace) P.trace = *trace;
+  P.peers = c->peers;
+  if (c->peers.n_peers > 0 && c->mlp_mode != 2)
+    return fail(B200NERF_ERR_UNSUPPORTED, "peer outputs are implemented by the ray-per-lane kernel (mode 2) only");
+  if (c->peers.n_peers > 0 && ((kNff + c->app.dim) & 3) != 0)
+    return fail(B200NERF_ERR_UNSUPPORTED, "peer outputs need a feature width that is a multiple of 4");
   P.n_rays = n_rays;
   constexpr int WARPS = kRenderWarps;
   int64_t blocks_needed = (n_rays + WARPS - 1) / WARPS;
@@ -923,6 +929,23 @@ int b200nerf_mlp_fwd(b200nerf_ctx* c, const float* x, int64_t n_rows, int in_dim
   int grid = (int)(tiles < (int64_t)c->sm_count * 2 ? tiles : (int64_t)c->sm_count * 2);
   mlp_tc_kernel<<<grid, 128, smem, (cudaStream_t)stream>>>(a, x, y, n_rows, c->d_status);
   CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+int b200nerf_set_peer_outputs(b200nerf_ctx* c, const b200nerf_peer_outputs* peers) {
+  REQUIRE(c, "ctx is NULL");
+  if (!peers || peers->n_peers == 0) {
+    c->peers = b200nerf_peer_outputs{};
+    return 0;
+  }
+  REQUIRE(peers->n_peers > 0 && peers->n_peers <= B200NERF_MAX_PEERS, "n_peers must be in [1, 8]");
+  REQUIRE(peers->self_rank >= -1 && peers->self_rank < peers->n_peers, "self_rank out of range");
+  REQUIRE(peers->row_offset >= 0, "negative row_offset");
+  for (int p = 0; p < peers->n_peers; ++p) {
+    if (p == peers->self_rank) continue;
+    REQUIRE(peers->features[p] && peers->depth[p] && peers->accumulation[p], "NULL peer buffer");
+  }
+  c->peers = *peers;
   return 0;
 }
 

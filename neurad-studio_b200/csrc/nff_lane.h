@@ -439,6 +439,23 @@ NFF_D void render_ray_lane(const RenderParams& P, const LaneScratch& sc, Mlp& ml
   P.out.accumulation[ray] = acc;
   P.out.prop_depth_0[ray] = prop_depth_0;
   P.out.prop_depth_1[ray] = prop_depth_1;
+#if defined(__CUDACC__)
+  // Peer gather fused into the epilogue: store the finished row straight into every peer's buffer over NVLink
+  // (st.global on peer-mapped addresses).  The row was just written locally, so it is re-read from L1/L2 as float4.
+  if (P.peers.n_peers > 0) {
+    const int64_t row = P.peers.row_offset + ray;
+    const float4* src = reinterpret_cast<const float4*>(fo);
+    const int n4 = fdim >> 2;  // fdim is a multiple of 4 (32 + 16)
+#pragma unroll 1
+    for (int p = 0; p < P.peers.n_peers; ++p) {
+      if (p == P.peers.self_rank) continue;
+      float4* dst = reinterpret_cast<float4*>(P.peers.features[p] + row * fdim);
+      for (int i = 0; i < n4; ++i) dst[i] = src[i];
+      P.peers.depth[p][row] = depth;
+      P.peers.accumulation[p][row] = acc;
+    }
+  }
+#endif
 }
 
 }  // namespace nff

@@ -108,6 +108,7 @@ struct RenderParams {
   b200nerf_rays rays;
   b200nerf_outputs out;
   b200nerf_trace trace;
+  b200nerf_peer_outputs peers;
   int64_t n_rays;
 };
 

@@ -53,3 +53,38 @@ class ShardedOutputs:
                 dist.all_gather_into_tensor(b.view(-1), b[self.rank].reshape(-1).clone() if b.device.type == "cpu" else b[self.rank].reshape(-1), group=self.group)
             out[k] = torch.cat([b[r, : self.sizes[r]] for r in range(self.world)], dim=0)
         return out
+
+
+class PeerGatherBuffers:
+    """Gather buffers in symmetric (peer-mapped) memory for the fused render+gather path.
+
+    Every rank allocates `[world, rows_per_rank, width]` per output through torch.distributed._symmetric_memory and
+    exchanges the mappings once (`rendezvous`).  `bind(backend)` then tells the render kernel to store each finished
+    row into ALL ranks' buffers (its own slice locally, the others over NVLink), so that after `barrier()` every rank
+    holds the complete gather -- no NCCL collective on the data path."""
+
+    WIDTHS = ("features", "depth", "accumulation")
+
+    def __init__(self, rows_per_rank: int, feature_dim: int, device, group=None):
+        import torch.distributed._symmetric_memory as symm_mem
+
+        self.group = group if group is not None else dist.group.WORLD
+        self.world, self.rank = dist.get_world_size(self.group), dist.get_rank(self.group)
+        self.rows = rows_per_rank
+        widths = {"features": feature_dim, "depth": 1, "accumulation": 1}
+        self.buf, self.hdl = {}, {}
+        for k, w in widths.items():
+            t = symm_mem.empty(self.world * rows_per_rank * w, dtype=torch.float32, device=device)
+            self.hdl[k] = symm_mem.rendezvous(t, self.group)
+            self.buf[k] = t.view(self.world, rows_per_rank, w)
+
+    def local(self) -> Dict[str, torch.Tensor]:
+        return {k: b[self.rank] for k, b in self.buf.items()}
+
+    def bind(self, backend) -> None:
+        ptrs = {k: [int(p) for p in self.hdl[k].buffer_ptrs] for k in self.buf}
+        backend.set_peer_outputs(ptrs, self_rank=self.rank, row_offset=self.rank * self.rows)
+
+    def barrier(self) -> None:
+        """Device-side cross-rank barrier on the current stream (all ranks' rows have landed once it completes)."""
+        self.hdl["features"].barrier()

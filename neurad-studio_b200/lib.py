@@ -31,6 +31,14 @@ class Outputs(ctypes.Structure):
                 ("features", "depth", "accumulation", "prop_depth_0", "prop_depth_1", "intensity", "ray_drop_logit")]
 
 
+MAX_PEERS = 8
+
+
+class PeerOutputs(ctypes.Structure):
+    _fields_ = [("n_peers", c_int32), ("self_rank", c_int32), ("row_offset", c_int64),
+                ("features", c_void_p * MAX_PEERS), ("depth", c_void_p * MAX_PEERS), ("accumulation", c_void_p * MAX_PEERS)]
+
+
 TRACE_FIELDS = ("prop_weights_0", "prop_weights_1", "bins_s_1", "bins_e_1", "bins_s_2", "bins_e_2", "inds_1", "inds_2",
                 "sdf", "alpha", "field_feature", "weights", "actor_id_0", "actor_id_1", "actor_id_main")
 
@@ -63,6 +71,7 @@ SIGNATURES = {
                                  POINTER(c_int), c_void_p, c_void_p]),
     "b200nerf_check_status": (c_int, [c_void_p]),
     "b200nerf_set_mlp_mode": (c_int, [c_void_p, c_int]),
+    "b200nerf_set_peer_outputs": (c_int, [c_void_p, POINTER(PeerOutputs)]),
     "b200nerf_pdf_resample": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_void_p,
                                       c_void_p, c_void_p, c_void_p]),
     "b200nerf_density_to_weights": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p]),
