@@ -315,8 +315,7 @@ def main():
     if world > 1:
         import torch.distributed as dist
 
-        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"  # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # NCCL's banner / logs off stdout: rank 0 prints ONE JSON line
         dist.init_process_group("nccl", device_id=dev)
     from neurad_studio_b200 import scene
     from neurad_studio_b200.backend import B200Backend
