@@ -208,20 +208,26 @@ NFF_D float lane_proposal_round(const RenderParams& P, const FieldGrids& fg, con
   float e_prev = to_euclid(edge(0), s_near, s_far, sp);
 #pragma unroll 1
   for (int s = 0; s < S; ++s) {
-    const float e0 = e_prev;
-    const float e1 = to_euclid(edge(s + 1), s_near, s_far, sp);
-    e_prev = e1;
-    Gauss g = sample_gaussian(o, d, area, e0, e1);
-    int aid;
-    float dens = lane_proposal_density(fg, sc, tid, n_cand, g, &aid);
-    float dd = fmul(fsub(e1, e0), dens);
-    float alpha = fsub(1.0f, expf(-dd));
-    float T = expf(-(float)excl);
-    excl += (double)dd;  // torch.cumsum order
-    float w = nan_to_num(fmul(alpha, T));
-    depth_acc = fadd(depth_acc, fmul(w, fmul(fadd(e0, e1), 0.5f)));
+    const float T = expf(-(float)excl);
+    // Exact early termination: once exp(-sum) has underflowed to 0 it stays 0 (the sum only grows), so every later
+    // weight of this round is exactly 0 whatever the density is (nan_to_num(x * 0) == 0) -- the gathers are skipped
+    // when that holds for all 32 rays of the warp.  Not taken when per-sample actor ids are being traced.
+    float w = 0.0f;
+    if (!(vote_all_converged(T == 0.0f) && io.tr_aid == nullptr)) {
+      const float e0 = e_prev;
+      const float e1 = to_euclid(edge(s + 1), s_near, s_far, sp);
+      e_prev = e1;
+      Gauss g = sample_gaussian(o, d, area, e0, e1);
+      int aid;
+      float dens = lane_proposal_density(fg, sc, tid, n_cand, g, &aid);
+      float dd = fmul(fsub(e1, e0), dens);
+      float alpha = fsub(1.0f, expf(-dd));
+      excl += (double)dd;  // torch.cumsum order
+      w = nan_to_num(fmul(alpha, T));
+      depth_acc = fadd(depth_acc, fmul(w, fmul(fadd(e0, e1), 0.5f)));
+      if (io.tr_aid) io.tr_aid[ray * S + s] = aid;
+    }
     if (io.tr_w) io.tr_w[ray * S + s] = w;
-    if (io.tr_aid) io.tr_aid[ray * S + s] = aid;
     w = fadd(w, sp.hist_pad);
     sc.w[(size_t)s * kLaneThreads + tid] = w;
     tot_d += (double)w;
@@ -234,6 +240,7 @@ NFF_D float lane_proposal_round(const RenderParams& P, const FieldGrids& fg, con
   int k = 1;
   double run = (double)fdiv(fadd(sc.w[tid], pad_each), tot);  // unclamped cumsum up to index k
   float c_km1 = 0.0f, c_k = fminf(1.0f, (float)run);
+  float w_next = sc.w[(size_t)kLaneThreads + tid];  // weight k, loaded one step ahead of the dependent compare
 #pragma unroll 1
   for (int i = 0; i <= S_new; ++i) {
     const float u = ldg(io.u_tab + i);
@@ -241,7 +248,9 @@ NFF_D float lane_proposal_round(const RenderParams& P, const FieldGrids& fg, con
       ++k;
       c_km1 = c_k;
       if (k <= S) {
-        run += (double)fdiv(fadd(sc.w[(size_t)(k - 1) * kLaneThreads + tid], pad_each), tot);
+        const float wk = w_next;
+        w_next = sc.w[(size_t)(k < S ? k : S - 1) * kLaneThreads + tid];
+        run += (double)fdiv(fadd(wk, pad_each), tot);
         c_k = fminf(1.0f, (float)run);
       }
     }

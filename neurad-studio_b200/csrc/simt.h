@@ -25,6 +25,8 @@ NFF_D float shfl_up(float v, int d) { return __shfl_up_sync(0xffffffffu, v, d); 
 NFF_D float shfl_down(float v, int d) { return __shfl_down_sync(0xffffffffu, v, d); }
 NFF_D float shfl_xor(float v, int m) { return __shfl_xor_sync(0xffffffffu, v, m); }
 NFF_D unsigned vote_ballot(bool p) { return __ballot_sync(0xffffffffu, p); }
+// true iff p holds on every lane of the (converged) warp
+NFF_D bool vote_all_converged(bool p) { return __all_sync(0xffffffffu, p); }
 NFF_D void syncwarp() { __syncwarp(); }
 NFF_D void syncblock() { __syncthreads(); }
 NFF_D int popc(unsigned x) { return __popc(x); }
@@ -85,6 +87,8 @@ inline unsigned vote_ballot(bool p) {
   t_warp->bar.arrive_and_wait();
   return r;
 }
+// the host emulation of the ray-per-lane kernel runs lanes one after the other: a per-lane decision is exact there
+inline bool vote_all_converged(bool p) { return p; }
 inline void syncwarp() { t_warp->bar.arrive_and_wait(); }
 inline void syncblock() { t_warp->bar.arrive_and_wait(); }  // host emulation runs one warp per block
 inline int popc(unsigned x) { return __builtin_popcount(x); }
