@@ -426,11 +426,11 @@ NFF_D void render_ray_lane(const RenderParams& P, const LaneScratch& sc, Mlp& ml
       }
     }
   }
-  if (!active) return;
+  // ---- outputs ----
   const int fdim = P.nff_dim + P.app.dim;
-  float* fo = P.out.features + ray * fdim;
+  float app[kApp];
 #pragma unroll
-  for (int i = 0; i < kNff; ++i) fo[i] = fsum[i];
+  for (int i = 0; i < kApp; ++i) app[i] = 0.0f;
   if (P.app.dim > 0) {  // _get_appearance_embedding, temporal branch (neurad.py:423-441)
     float sens = P.rays.sensor_idx ? (float)P.rays.sensor_idx[ray] : 0.0f;
     float eps_ = (float)P.app.eps;
@@ -439,30 +439,76 @@ NFF_D void render_ray_lane(const RenderParams& P, const LaneScratch& sc, Mlp& ml
     float after = fminf(fmaxf(fadd(before, 1.0f), 0.0f), eps_ - 1.0f);
     float ratio = fsub(tidx, before);
     int ib = (int)fadd(before, fmul(sens, eps_)), ia = (int)fadd(after, fmul(sens, eps_));
-    for (int i = 0; i < P.app.dim; ++i) {
-      float eb = ldg(P.app.emb + (size_t)ib * P.app.dim + i), ea = ldg(P.app.emb + (size_t)ia * P.app.dim + i);
-      fo[P.nff_dim + i] = fadd(fmul(eb, fsub(1.0f, ratio)), fmul(ea, ratio));
+#pragma unroll
+    for (int i = 0; i < kApp; ++i) {
+      if (i < P.app.dim) {
+        float eb = ldg(P.app.emb + (size_t)ib * P.app.dim + i), ea = ldg(P.app.emb + (size_t)ia * P.app.dim + i);
+        app[i] = fadd(fmul(eb, fsub(1.0f, ratio)), fmul(ea, ratio));
+      }
     }
   }
+#if defined(__CUDACC__)
+  if (fdim == kNff + kApp) {
+    // Coalesced feature rows.  The 8 lanes 8g..8g+7 of a warp own 8 CONSECUTIVE rays (an image-row segment of the
+    // 8x4 patch, or 8 flat neighbours), i.e. 8*48 floats = 1536 contiguous bytes of the output.  Each segment is
+    // staged through the warp's slice of the shared panel and written with three fully coalesced 512-byte STG.128
+    // instructions -- to the local buffer and, for the fused multi-GPU gather, to every peer's buffer over NVLink
+    // (st.global on peer-mapped addresses; small scattered remote writes are what made the naive version slow).
+    const int ln = tid & 31;
+    float* slice = mlp.panel() + (tid & ~31);  // rows 0..31 (stride kLaneThreads) x 32 columns of this warp
+    const unsigned act_mask = __ballot_sync(0xffffffffu, active);
+#pragma unroll 1
+    for (int g = 0; g < 4; ++g) {
+      __syncwarp();
+      if ((ln >> 3) == g) {
+        const int r = ln & 7;
+#pragma unroll
+        for (int j = 0; j < kNff; ++j) {
+          const int slot = r * (kNff + kApp) + j;
+          slice[(slot >> 5) * kLaneThreads + (slot & 31)] = fsum[j];
+        }
+#pragma unroll
+        for (int j = 0; j < kApp; ++j) {
+          const int slot = r * (kNff + kApp) + kNff + j;
+          slice[(slot >> 5) * kLaneThreads + (slot & 31)] = app[j];
+        }
+      }
+      __syncwarp();
+      const int k = __popc((act_mask >> (8 * g)) & 0xffu);  // active rays of the segment form a prefix
+      const int64_t ray0 = __shfl_sync(0xffffffffu, ray, 8 * g);
+      if (k == 0) continue;
+#pragma unroll
+      for (int t = 0; t < 3; ++t) {
+        const int f = t * 32 + ln;  // float4 index inside the segment's 96 float4
+        if (f / 12 < k) {
+          const float4 v = *reinterpret_cast<const float4*>(&slice[(f >> 3) * kLaneThreads + ((f & 7) << 2)]);
+          reinterpret_cast<float4*>(P.out.features + ray0 * fdim)[f] = v;
+          for (int p = 0; p < P.peers.n_peers; ++p) {
+            if (p == P.peers.self_rank) continue;
+            reinterpret_cast<float4*>(P.peers.features[p] + (P.peers.row_offset + ray0) * fdim)[f] = v;
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else
+#endif
+  if (active) {
+    float* fo = P.out.features + ray * fdim;
+#pragma unroll
+    for (int i = 0; i < kNff; ++i) fo[i] = fsum[i];
+    for (int i = 0; i < P.app.dim; ++i) fo[P.nff_dim + i] = app[i];
+  }
+  if (!active) return;
   P.out.depth[ray] = depth;
   P.out.accumulation[ray] = acc;
   P.out.prop_depth_0[ray] = prop_depth_0;
   P.out.prop_depth_1[ray] = prop_depth_1;
 #if defined(__CUDACC__)
-  // Peer gather fused into the epilogue: store the finished row straight into every peer's buffer over NVLink
-  // (st.global on peer-mapped addresses).  The row was just written locally, so it is re-read from L1/L2 as float4.
-  if (P.peers.n_peers > 0) {
-    const int64_t row = P.peers.row_offset + ray;
-    const float4* src = reinterpret_cast<const float4*>(fo);
-    const int n4 = fdim >> 2;  // fdim is a multiple of 4 (32 + 16)
-#pragma unroll 1
-    for (int p = 0; p < P.peers.n_peers; ++p) {
-      if (p == P.peers.self_rank) continue;
-      float4* dst = reinterpret_cast<float4*>(P.peers.features[p] + row * fdim);
-      for (int i = 0; i < n4; ++i) dst[i] = src[i];
-      P.peers.depth[p][row] = depth;
-      P.peers.accumulation[p][row] = acc;
-    }
+  for (int p = 0; p < P.peers.n_peers; ++p) {
+    if (p == P.peers.self_rank) continue;
+    P.peers.depth[p][P.peers.row_offset + ray] = depth;
+    P.peers.accumulation[p][P.peers.row_offset + ray] = acc;
   }
 #endif
 }
