@@ -261,6 +261,16 @@ def oracle_rays_per_sec(cfg, n_sample: int, repeats: int = 1, _threads_fixed: bo
     return n / best, n, best
 
 
+_SAVED_STDOUT = None
+
+
+def _emit(line: dict):
+    sys.stdout.flush()
+    if _SAVED_STDOUT is not None:
+        os.dup2(_SAVED_STDOUT, 1)
+    print(json.dumps(line), flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -315,7 +325,12 @@ def main():
     if world > 1:
         import torch.distributed as dist
 
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # NCCL's banner / logs off stdout: rank 0 prints ONE JSON line
+        # NCCL / c10d print a version banner on stdout at first use; rank 0 must print ONE JSON line, so stdout is
+        # pointed at stderr until the result line is written (restored in _emit)
+        sys.stdout.flush()
+        global _SAVED_STDOUT
+        _SAVED_STDOUT = os.dup(1)
+        os.dup2(2, 1)
         dist.init_process_group("nccl", device_id=dev)
     from neurad_studio_b200 import scene
     from neurad_studio_b200.backend import B200Backend
@@ -387,7 +402,7 @@ def main():
         v, n, dt = oracle_rays_per_sec(cfg, args.cpu_sample)
         line["cpu_baseline"] = {"value": v, "unit": "rays/s", "cores": torch.get_num_threads(), "kind": "port",
                                 "sample": f"{n} rays (12:1 camera:lidar) of the same workload in {dt:.1f} s, oracle port of the reference torch path, best of thread counts probed, host has {os.cpu_count()} cpus"}
-    print(json.dumps(line))
+    _emit(line)
     if world > 1:
         import torch.distributed as dist
 
