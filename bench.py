@@ -125,6 +125,22 @@ class Step:
         self.host_out = {k: torch.empty(self.n, w).pin_memory() for k, w in (("features", fdim), ("depth", 1), ("accumulation", 1))}
         self.kernel_events = []
         self.launches = 0
+        # peer lists: device peers (fused multi-GPU gather) and, for the e2e arm, the pinned host buffers as one more
+        # "peer" (pinned host memory is device-mapped under UVA)
+        keys = ("features", "depth", "accumulation")
+        widths = {"features": fdim, "depth": 1, "accumulation": 1}
+        host_ptrs = {k: self.host_out[k].data_ptr() for k in keys}
+        if self.p2p:
+            self._dev_peers = {k: [int(p) for p in self.pg.hdl[k].buffer_ptrs] for k in keys}
+            # GPU peers hold [world, n, w] (this rank's rows at row_offset = rank * n); the host buffer is [n, w], so
+            # its base pointer is shifted back by that offset
+            self._e2e_row_offset = self.rank * self.n
+            self._e2e_peers = {k: self._dev_peers[k] + [host_ptrs[k] - self._e2e_row_offset * widths[k] * 4] for k in keys}
+            self._e2e_self = self.rank
+        else:
+            self._dev_peers = None
+            self._e2e_row_offset = 0
+            self._e2e_peers, self._e2e_self = {k: [host_ptrs[k]] for k in keys}, -1
 
     def _raygen(self, points):
         be = self.be
@@ -165,35 +181,25 @@ class Step:
                 dist.all_gather_into_tensor(buf.view(-1), buf[self.rank].reshape(-1))
 
     def run_e2e(self):
-        """host buffers in, host buffers out: H2D of the step's inputs and D2H of its results inside the call.
-        The step is rendered in four chunks so that the device->host copy of chunk i (side stream, pinned memory)
-        overlaps the render of chunk i+1."""
+        """host buffers in, host buffers out, inside the call: H2D of the step's inputs (camera descriptors + the lidar
+        sweep from pinned memory) and the step's results landing in pinned host memory.  The results are not copied
+        after the fact: the pinned output buffers are handed to the library as one more "peer" (set_peer_outputs), so the
+        render epilogue streams every finished row to the host over PCIe while the kernel is still rendering."""
         dev = self.be.device
-        main = torch.cuda.current_stream(dev)
-        if not hasattr(self, "_copy_stream"):
-            self._copy_stream = torch.cuda.Stream(dev)
         pts = self.points_pinned.to(dev, non_blocking=True)
         self._raygen(pts)
+        rays = dict(self.rays, sensor_idx=self.sensor, is_lidar=self.is_lidar)
         out = {k: self.gather[k][self.rank] for k in self.gather}
         out.update(self.local)
-        # four row-chunks of the stacked 640-wide image, shrinking (40/30/20/10 %) so that the un-overlapped
-        # device->host copy of the last chunk is short; boundaries on multiples of 8 rows (the kernel's tile height)
-        rows = self.n // 640
-        cuts = [0] + [int(rows * f) // 8 * 8 * 640 for f in (0.4, 0.7, 0.9)] + [self.n]
-        for a, b in zip(cuts[:-1], cuts[1:]):
-            rays = {k: v[a:b] for k, v in self.rays.items()}
-            rays["sensor_idx"], rays["is_lidar"] = self.sensor[a:b], self.is_lidar[a:b]
-            self.be.render(rays, out={k: v[a:b] for k, v in out.items()}, image_width=640)
-            self.launches += 1
-            ev = torch.cuda.Event()
-            ev.record(main)
-            self._copy_stream.wait_event(ev)
-            with torch.cuda.stream(self._copy_stream):
-                for k in self.host_out:
-                    self.host_out[k][a:b].copy_(out[k][a:b], non_blocking=True)
+        self.be.set_peer_outputs(self._e2e_peers, self_rank=self._e2e_self, row_offset=self._e2e_row_offset)
+        self.be.render(rays, out=out, image_width=640)
+        self.launches += 1
         self._finish_gather()
-        main.synchronize()
-        self._copy_stream.synchronize()
+        torch.cuda.current_stream(dev).synchronize()
+        if self.p2p:
+            self.be.set_peer_outputs(self._dev_peers, self_rank=self.rank, row_offset=self.rank * self.n)
+        else:
+            self.be.set_peer_outputs(None)
         return self.host_out
 
     @property

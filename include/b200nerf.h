@@ -141,9 +141,10 @@ typedef struct {
  * torch.distributed._symmetric_memory rendezvous.  This replaces the per-image all-gather: the transfer overlaps the
  * rendering tile by tile and no NCCL kernel has to wait for the (persistent, all-SM) render kernel to drain.  The
  * caller still needs a cross-rank barrier before reading.  `self_rank`'s entry is skipped when it equals the local
- * `b200nerf_outputs` slice.  Reference counterpart: none (the reference renders on one device per process,
+ * `b200nerf_outputs` slice.  A "peer" may also be pinned, device-mapped HOST memory: the results then stream to the
+ * host over PCIe while the kernel is still rendering (no separate device->host copy).  Reference counterpart: none (the reference renders on one device per process,
  * pipelines/ad_pipeline.py:197-306). */
-#define B200NERF_MAX_PEERS 8
+#define B200NERF_MAX_PEERS 16
 typedef struct {
   int32_t n_peers;   /* 0 disables */
   int32_t self_rank; /* index into the arrays below that is this rank (skipped), or -1 */

@@ -938,7 +938,7 @@ int b200nerf_set_peer_outputs(b200nerf_ctx* c, const b200nerf_peer_outputs* peer
     c->peers = b200nerf_peer_outputs{};
     return 0;
   }
-  REQUIRE(peers->n_peers > 0 && peers->n_peers <= B200NERF_MAX_PEERS, "n_peers must be in [1, 8]");
+  REQUIRE(peers->n_peers > 0 && peers->n_peers <= B200NERF_MAX_PEERS, "n_peers must be in [1, 16]");
   REQUIRE(peers->self_rank >= -1 && peers->self_rank < peers->n_peers, "self_rank out of range");
   REQUIRE(peers->row_offset >= 0, "negative row_offset");
   for (int p = 0; p < peers->n_peers; ++p) {

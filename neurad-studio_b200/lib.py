@@ -31,7 +31,7 @@ class Outputs(ctypes.Structure):
                 ("features", "depth", "accumulation", "prop_depth_0", "prop_depth_1", "intensity", "ray_drop_logit")]
 
 
-MAX_PEERS = 8
+MAX_PEERS = 16
 
 
 class PeerOutputs(ctypes.Structure):
