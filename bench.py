@@ -383,6 +383,8 @@ def main():
     kern_ms = sorted(a.elapsed_time(b) for a, b in step.kernel_events)
     kern_ms = sum(kern_ms) / len(kern_ms)
     ms_e2e = timed(step.run_e2e, args.steps)
+    # the host buffers the e2e arm filled must hold exactly what the device buffers hold
+    e2e_ok = all(torch.equal(step.host_out[k], step.gather[k][rank].cpu()) for k in step.host_out)
     clocks = sampler.stop() if rank == 0 else None
     rays_total = step.n * world * args.steps
     value = rays_total / (ms * 1e-3)
@@ -397,7 +399,8 @@ def main():
     achieved = step.n * ALGO_BYTES_PER_RAY / (kern_ms * 1e-3) / 1e9
     line = dict(base, value=value, ms_per_step=ms / args.steps, clocks=clocks, gpu_launches=launches,
                 e2e={"value": e2e_value, "unit": "rays/s", "h2d_bytes_per_step": step.h2d_bytes, "d2h_bytes_per_step": step.d2h_bytes,
-                     "ms_per_step": ms_e2e / args.steps},
+                     "ms_per_step": ms_e2e / args.steps, "host_buffers_verified": bool(e2e_ok),
+                     "how": "host descriptors -> ray generation -> fused render; the render epilogue stores every finished row into pinned host memory (device-mapped) while rendering"},
                 roofline={"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                           "traffic": None, "kernel": "nff_render_lane_kernel", "kernel_ms": kern_ms, "peak_source": peak_src,
                           "algorithmic_bytes_per_ray": ALGO_BYTES_PER_RAY})

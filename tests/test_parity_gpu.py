@@ -428,3 +428,26 @@ def test_config4_lidar_grid_rolling_shutter(backend):
     for k in ("features", "depth", "accumulation"):
         assert rel_to_max(out[k][sel.cuda()], o[k]) < 1e-4, (k, rel_to_max(out[k][sel.cuda()], o[k]))
     assert rel_to_max(out["intensity"][sel.cuda()], inten) < 1e-4
+
+
+def test_peer_outputs_stream_to_pinned_host_memory(backend):
+    """set_peer_outputs with a pinned (device-mapped) host buffer as the only "peer": the render epilogue writes every
+    finished row to the host while rendering; the host copy must equal the device output bit for bit, for a ray count
+    that is not a multiple of the 8-ray output segments or of the 512-ray CTA, with and without the 2-D tile walk."""
+    cfg = nsb.small_config(n_actors=0, log2_main=14, log2_prop=13)
+    params = scene.make_params(cfg, seed=61, beta=3.0, sdf_bias=0.6)
+    backend.load_params(cfg, params)
+    n = 3001
+    rays = scene.random_rays(n, cfg, seed=62)
+    for width in (0, 77):
+        host = {"features": torch.zeros(n, cfg.feature_dim).pin_memory(), "depth": torch.zeros(n, 1).pin_memory(),
+                "accumulation": torch.zeros(n, 1).pin_memory()}
+        backend.set_peer_outputs({k: [v.data_ptr()] for k, v in host.items()}, self_rank=-1, row_offset=0)
+        try:
+            out = backend.render(rays, image_width=width)
+            torch.cuda.synchronize()
+            backend.check_status()
+        finally:
+            backend.set_peer_outputs(None)
+        for k, v in host.items():
+            assert torch.equal(v, out[k].cpu()), (k, width)
