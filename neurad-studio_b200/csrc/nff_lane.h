@@ -28,17 +28,18 @@ namespace nff {
 constexpr int kLaneThreads = NFF_LANE_THREADS;  // threads (= rays in flight) per CTA (256: 2 CTAs/SM, 512: 1 CTA/SM)
 constexpr int kLaneCtasPerSm = 512 / kLaneThreads;
 constexpr int kCandFloats = 16;    // per candidate: 12 (world->box 3x4) + 3 (bounds) + 1 (actor id bits)
+constexpr int kLaneMaxCand = 32;   // actor candidates per ray (they live in the global scratch slab, so this is cheap)
 
 // per-CTA slab of the global scratch, all arrays [index][kLaneThreads]
 struct LaneScratch {
   float* w;      // [kS0]       padded proposal weights of the current round
   float* bins1;  // [kS1 + 1]   spacing edges after round 0
   float* bins2;  // [kS2 + 1]   spacing edges after round 1
-  float* cand;   // [kMaxCand * kCandFloats]
+  float* cand;   // [kLaneMaxCand * kCandFloats]
   float* panel;  // [kNff]      grid-feature panel / parked geo_embedding (when not kept in shared memory)
 };
 NFF_HD size_t lane_scratch_floats_per_cta() {
-  return (size_t)kLaneThreads * (kS0 + (kS1 + 1) + (kS2 + 1) + kMaxCand * kCandFloats + kNff);
+  return (size_t)kLaneThreads * (kS0 + (kS1 + 1) + (kS2 + 1) + kLaneMaxCand * kCandFloats + kNff);
 }
 NFF_D LaneScratch lane_scratch_of(float* base, int cta) {
   float* p = base + (size_t)cta * lane_scratch_floats_per_cta();
@@ -47,7 +48,7 @@ NFF_D LaneScratch lane_scratch_of(float* base, int cta) {
   s.bins1 = s.w + (size_t)kS0 * kLaneThreads;
   s.bins2 = s.bins1 + (size_t)(kS1 + 1) * kLaneThreads;
   s.cand = s.bins2 + (size_t)(kS2 + 1) * kLaneThreads;
-  s.panel = s.cand + (size_t)kMaxCand * kCandFloats * kLaneThreads;
+  s.panel = s.cand + (size_t)kLaneMaxCand * kCandFloats * kLaneThreads;
   return s;
 }
 
@@ -86,7 +87,7 @@ NFF_D int lane_actor_candidates(const Actors& A, float time, const float o[3], c
     float cz = fsub(fmul(v[0], d[1]), fmul(v[1], d[0]));
     float dist = fsqrt(fadd(fadd(fmul(cx, cx), fmul(cy, cy)), fmul(cz, cz)));
     if (!(valid && dist < ldg(A.radii + a) * 1.001f)) continue;
-    if (n >= kMaxCand) {
+    if (n >= kLaneMaxCand) {
       *overflow = 1;
       continue;
     }
