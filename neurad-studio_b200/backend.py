@@ -37,6 +37,9 @@ def grid_desc(g: HashGridSettings, scalings: Optional[torch.Tensor] = None) -> G
     return d
 
 
+DEFAULT_MODE = "split"
+
+
 class B200Backend:
     """One context per CUDA device.  `load_params` takes tensors under the reference's state_dict names."""
 
@@ -267,9 +270,10 @@ class B200Backend:
         return y.reshape(*x.shape[:-1], out_dims[-1])
 
     def set_mlp_mode(self, mode: str):
-        """Kernel variant of render(): 'lane' (default) ray-per-lane + tcgen05 MLPs; 'tc' warp-per-ray + tcgen05
-        MLPs (3xTF32); 'ffma' warp-per-ray + CUDA-core fp32 MLPs."""
-        self._check(self.lib.b200nerf_set_mlp_mode(self._h, {"ffma": 0, "tc": 1, "lane": 2}[mode]))
+        """Kernel variant of render(): 'split' (default) ray-per-lane in two kernels -- sampling at 32 warps/SM, then
+        shading with tcgen05 MLPs; 'lane' the same code as one fused kernel; 'tc' warp-per-ray + tcgen05 MLPs
+        (3xTF32); 'ffma' warp-per-ray + CUDA-core fp32 MLPs."""
+        self._check(self.lib.b200nerf_set_mlp_mode(self._h, {"ffma": 0, "tc": 1, "lane": 2, "split": 3}[mode]))
 
     def set_peer_outputs(self, peer_ptrs: Optional[Dict[str, Sequence[int]]], self_rank: int = -1, row_offset: int = 0):
         """Fuse the multi-GPU gather into the render epilogue: `peer_ptrs` maps "features" / "depth" / "accumulation"

@@ -39,9 +39,11 @@ struct b200nerf_ctx {
   float* d_decoder[3] = {nullptr, nullptr, nullptr};
   float* d_main_mlp = nullptr;
   float* d_main_mlp_nn = nullptr;
-  int mlp_mode = 2;  // 2 = ray-per-lane + tcgen05, 1 = warp-per-ray + tcgen05 (3xTF32), 0 = warp-per-ray + CUDA-core fp32 FFMA
+  int mlp_mode = 3;  // 3 = ray-per-lane in two kernels (sampling | shading + tcgen05), 2 = the same as one fused kernel, 1 = warp-per-ray + tcgen05 (3xTF32), 0 = warp-per-ray + CUDA-core fp32 FFMA
   float* d_lane_scratch = nullptr;
   int lane_ctas = 0;
+  float* d_handoff = nullptr;        // [kS2+1][rays] spacing edges between the sampling and the shading kernel
+  int64_t handoff_rays = 0;
   b200nerf_peer_outputs peers{};
   bool have_main_mlp = false;
   float beta = 0.f;
@@ -145,7 +147,102 @@ __global__ void __launch_bounds__(WARPS * 32, 16 / WARPS) nff_render_tc_kernel(c
 }
 
 
-// Ray-per-lane variant (nff_lane.h): a warp = 32 adjacent rays at the same sample index, CTA = 256 rays.
+
+// Work units of the ray-per-lane kernels: with an image_width hint a CTA walks 32 x (threads/32)-pixel tiles and a warp
+// renders an 8x4 patch (neighbours in both image directions); without it, kLaneThreads consecutive rays.  Inactive
+// lanes (outside the image / beyond the last ray) get a valid fallback ray: they compute but never store.
+__device__ __forceinline__ int64_t lane_units(const RenderParams& P) {
+  const int W = P.rays.image_width;
+  if (W <= 0) return (P.n_rays + kLaneThreads - 1) / kLaneThreads;
+  constexpr int kTileH = kLaneThreads / 32;
+  const int64_t H = (P.n_rays + W - 1) / W;
+  return (int64_t)((W + 31) / 32) * ((H + kTileH - 1) / kTileH);
+}
+__device__ __forceinline__ bool lane_unit_ray(const RenderParams& P, int64_t unit, int tid, int64_t* ray_out) {
+  const int W = P.rays.image_width;
+  int64_t ray, fallback;
+  bool active;
+  if (W > 0) {
+    constexpr int kTileH = kLaneThreads / 32;
+    const int64_t H = (P.n_rays + W - 1) / W, tiles_x = (W + 31) / 32;
+    const int warp = tid >> 5, lane_ = tid & 31;
+    const int64_t px = (unit % tiles_x) * 32 + (warp & 3) * 8 + (lane_ & 7);
+    const int64_t py = (unit / tiles_x) * kTileH + (warp >> 2) * 4 + (lane_ >> 3);
+    ray = py * W + px;
+    active = px < W && ray < P.n_rays;
+    fallback = (py < H ? py : H - 1) * W + (px < W ? px : W - 1);
+  } else {
+    ray = unit * kLaneThreads + tid;
+    active = ray < P.n_rays;
+    fallback = P.n_rays - 1;
+  }
+  if (fallback >= P.n_rays) fallback = P.n_rays - 1;
+  *ray_out = active ? ray : fallback;
+  return active;
+}
+
+// Two-stage variant of the ray-per-lane path.  Stage 1 (sampling: both proposal rounds) needs neither TMEM nor shared
+// memory and fits 64 registers, so it runs at 32 warps/SM with the whole 228 KB as L1; stage 2 (main field + MLPs +
+// compositing) is the tensor-core kernel at 16 warps/SM.  The hand-over is 33 spacing edges per ray ([edge][ray],
+// 132 B/ray) -- still nothing per-sample in HBM.
+#ifndef NFF_SAMPLE_CTAS
+#define NFF_SAMPLE_CTAS 2
+#endif
+__global__ void __launch_bounds__(kLaneThreads, NFF_SAMPLE_CTAS) nff_sample_lane_kernel(const __grid_constant__ RenderParams P,
+                                                                                        float* __restrict__ scratch,
+                                                                                        float* __restrict__ handoff) {
+  const int tid = threadIdx.x;
+  const LaneScratch sc = lane_scratch_of(scratch, blockIdx.x);
+  for (int64_t unit = blockIdx.x; unit < lane_units(P); unit += gridDim.x) {
+    int64_t ray;
+    const bool active = lane_unit_ray(P, unit, tid, &ray);
+    const LaneRay R = lane_ray_setup(P, sc, tid, ray);
+    // inactive lanes write their (discarded) edges into the slab column instead of another ray's hand-over column
+    float* col = active ? handoff + ray : sc.bins2 + tid;
+    sample_ray_lane(P, sc, R, tid, ray, active, col, active ? P.n_rays : (int64_t)kLaneThreads);
+  }
+}
+
+__global__ void __launch_bounds__(kLaneThreads, kLaneCtasPerSm) nff_shade_lane_kernel(const __grid_constant__ RenderParams P,
+                                                                                      float* __restrict__ scratch,
+                                                                                      const float* __restrict__ handoff) {
+  extern __shared__ __align__(128) unsigned char smem_shade[];
+  TcShared* tcs = reinterpret_cast<TcShared*>(smem_shade);
+  constexpr int kTcBytes = (sizeof(TcShared) + 127) / 128 * 128;
+  float* geo_park = reinterpret_cast<float*>(smem_shade + kTcBytes);
+  const int tid = threadIdx.x, warp = tid >> 5, group = warp >> 2;
+  tc_stage_weights(*tcs, P.main_mlp_nn, tid, kLaneThreads);
+  tc::fence_async_smem();
+  constexpr uint32_t kCols = kTcTileCols * (kLaneThreads / 128);
+  if (warp == 0) tc::tmem_alloc(&tcs->tmem_base, kCols);
+  if (tid == 0)
+    for (int g = 0; g < kLaneThreads / 128; ++g) tc::mbar_init(&tcs->bar[g], 1);
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+  MlpLaneTc mlp;
+  mlp.core.t = tcs;
+  mlp.core.tile_base = tcs->tmem_base + (uint32_t)(group * kTcTileCols);
+  mlp.core.lane_base = mlp.core.tile_base + ((uint32_t)(32 * (warp & 3)) << 16);
+  mlp.core.bar = &tcs->bar[group];
+  mlp.core.parity = 0;
+  mlp.core.bar_id = 1 + group;
+  mlp.core.issuer = (tid & 127) == 0;
+  mlp.core.status = P.status;
+  const LaneScratch sc = lane_scratch_of(scratch, blockIdx.x);
+  mlp.geo_park = NFF_PANEL_GLOBAL ? sc.panel : geo_park;
+  for (int64_t unit = blockIdx.x; unit < lane_units(P); unit += gridDim.x) {
+    int64_t ray;
+    const bool active = lane_unit_ray(P, unit, tid, &ray);
+    const LaneRay R = lane_ray_setup(P, sc, tid, ray);
+    shade_ray_lane(P, sc, R, mlp, tid, ray, active, handoff + ray, P.n_rays);
+  }
+  tc::fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tc::tmem_dealloc(tcs->tmem_base, kCols);
+}
+
+// Ray-per-lane variant (nff_lane.h), single fused kernel: a warp = 32 adjacent rays at the same sample index.
 __global__ void __launch_bounds__(kLaneThreads, kLaneCtasPerSm) nff_render_lane_kernel(const __grid_constant__ RenderParams P,
                                                                           float* __restrict__ scratch) {
   extern __shared__ __align__(128) unsigned char smem_lane[];
@@ -173,31 +270,10 @@ __global__ void __launch_bounds__(kLaneThreads, kLaneCtasPerSm) nff_render_lane_
   mlp.core.status = P.status;
   const LaneScratch sc = lane_scratch_of(scratch, blockIdx.x);
   mlp.geo_park = NFF_PANEL_GLOBAL ? sc.panel : geo_park;
-  // Work units: with an image_width hint a CTA walks 32 x (threads/32)-pixel tiles and a warp renders an 8x4 patch
-  // (neighbours in both image directions); without it, kLaneThreads consecutive rays.  One call site for both so that
-  // the ~8k-instruction ray body exists once.
-  const int W = P.rays.image_width;
-  constexpr int kTileH = kLaneThreads / 32;
-  const int64_t H = W > 0 ? (P.n_rays + W - 1) / W : 0;
-  const int64_t tiles_x = W > 0 ? (W + 31) / 32 : 1;
-  const int64_t units = W > 0 ? tiles_x * ((H + kTileH - 1) / kTileH) : (P.n_rays + kLaneThreads - 1) / kLaneThreads;
-  const int lane_ = tid & 31;
-  const int dx = (warp & 3) * 8 + (lane_ & 7), dy = (warp >> 2) * 4 + (lane_ >> 3);
-  for (int64_t unit = blockIdx.x; unit < units; unit += gridDim.x) {
-    int64_t ray, fallback;
-    bool active;
-    if (W > 0) {
-      const int64_t px = (unit % tiles_x) * 32 + dx, py = (unit / tiles_x) * kTileH + dy;
-      ray = py * W + px;
-      active = px < W && ray < P.n_rays;
-      fallback = (py < H ? py : H - 1) * W + (px < W ? px : W - 1);
-    } else {
-      ray = unit * kLaneThreads + tid;
-      active = ray < P.n_rays;
-      fallback = P.n_rays - 1;
-    }
-    if (fallback >= P.n_rays) fallback = P.n_rays - 1;
-    render_ray_lane(P, sc, mlp, tid, active ? ray : fallback, active);
+  for (int64_t unit = blockIdx.x; unit < lane_units(P); unit += gridDim.x) {
+    int64_t ray;
+    const bool active = lane_unit_ray(P, unit, tid, &ray);
+    render_ray_lane(P, sc, mlp, tid, ray, active);
   }
   tc::fence_before_sync();
   __syncthreads();
@@ -583,6 +659,30 @@ __global__ void raygen_lidar_grid_kernel(LidarGridArgs a, float* __restrict__ or
 }
 
 // ===================================================================================================== C ABI
+// Rebase every per-ray pointer of a parameter block to ray `start` (slicing a bundle into several launches).
+template <class T>
+static inline void adv(T*& p, int64_t n) {
+  if (p) p += n;
+}
+static void offset_rays(RenderParams& Q, int64_t start, int fdim) {
+  if (start == 0) return;
+  adv(Q.rays.origins, 3 * start); adv(Q.rays.directions, 3 * start); adv(Q.rays.pixel_area, start);
+  adv(Q.rays.times, start); adv(Q.rays.nears, start); adv(Q.rays.fars, start);
+  adv(Q.rays.sensor_idx, start); adv(Q.rays.is_lidar, start);
+  adv(Q.out.features, (int64_t)fdim * start); adv(Q.out.depth, start); adv(Q.out.accumulation, start);
+  adv(Q.out.prop_depth_0, start); adv(Q.out.prop_depth_1, start);
+  b200nerf_trace& t = Q.trace;
+  adv(t.prop_weights_0, kS0 * start); adv(t.prop_weights_1, kS1 * start);
+  adv(t.bins_s_1, (kS1 + 1) * start); adv(t.bins_e_1, (kS1 + 1) * start);
+  adv(t.bins_s_2, (kS2 + 1) * start); adv(t.bins_e_2, (kS2 + 1) * start);
+  adv(t.inds_1, (kS1 + 1) * start); adv(t.inds_2, (kS2 + 1) * start);
+  adv(t.sdf, kS2 * start); adv(t.alpha, kS2 * start); adv(t.field_feature, (int64_t)kS2 * kNff * start);
+  adv(t.weights, kS2 * start);
+  adv(t.actor_id_0, kS0 * start); adv(t.actor_id_1, kS1 * start); adv(t.actor_id_main, kS2 * start);
+  Q.peers.row_offset += start;
+}
+
+
 extern "C" {
 
 const char* b200nerf_last_error(void) { return g_err.c_str(); }
@@ -611,8 +711,13 @@ int b200nerf_create(int device_ordinal, b200nerf_ctx** out) {
   CUDA_TRY(cudaMemset(c->d_status, 0, sizeof(int)));
   CUDA_TRY(cudaFuncSetAttribute(nff_render_lane_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 (int)((sizeof(TcShared) + 127) / 128 * 128 + (NFF_PANEL_GLOBAL ? 0 : sizeof(float) * kNff * kLaneThreads))));
-  c->lane_ctas = c->sm_count * kLaneCtasPerSm;
+  c->lane_ctas = c->sm_count * (kLaneCtasPerSm > NFF_SAMPLE_CTAS ? kLaneCtasPerSm : NFF_SAMPLE_CTAS);
   CUDA_TRY(cudaMalloc((void**)&c->d_lane_scratch, sizeof(float) * lane_scratch_floats_per_cta() * c->lane_ctas));
+  CUDA_TRY(cudaFuncSetAttribute(nff_shade_lane_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)((sizeof(TcShared) + 127) / 128 * 128 + (NFF_PANEL_GLOBAL ? 0 : sizeof(float) * kNff * kLaneThreads))));
+  CUDA_TRY(cudaFuncSetAttribute(nff_sample_lane_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 0));  // all L1
+  c->handoff_rays = (int64_t)1 << 21;
+  CUDA_TRY(cudaMalloc((void**)&c->d_handoff, sizeof(float) * (kS2 + 1) * c->handoff_rays));
   *out = c;
   return 0;
 }
@@ -627,6 +732,7 @@ int b200nerf_destroy(b200nerf_ctx* c) {
   cudaFree(c->d_main_mlp);
   cudaFree(c->d_main_mlp_nn);
   cudaFree(c->d_lane_scratch);
+  cudaFree(c->d_handoff);
   cudaFree(c->d_lidar_mlp);
   cudaFree(c->d_act_times);
   cudaFree(c->d_act_kf);
@@ -854,8 +960,8 @@ int b200nerf_nff_render_fwd(b200nerf_ctx* c, const b200nerf_rays* rays, int64_t 
   P.out = *out;
   if (trace) P.trace = *trace;
   P.peers = c->peers;
-  if (c->peers.n_peers > 0 && c->mlp_mode != 2)
-    return fail(B200NERF_ERR_UNSUPPORTED, "peer outputs are implemented by the ray-per-lane kernel (mode 2) only");
+  if (c->peers.n_peers > 0 && c->mlp_mode < 2)
+    return fail(B200NERF_ERR_UNSUPPORTED, "peer outputs are implemented by the ray-per-lane kernels (modes 2, 3) only");
   if (c->peers.n_peers > 0 && ((kNff + c->app.dim) & 3) != 0)
     return fail(B200NERF_ERR_UNSUPPORTED, "peer outputs need a feature width that is a multiple of 4");
   P.n_rays = n_rays;
@@ -864,7 +970,32 @@ int b200nerf_nff_render_fwd(b200nerf_ctx* c, const b200nerf_rays* rays, int64_t 
   int64_t max_blocks = (int64_t)c->sm_count * (16 / WARPS);  // persistent: resident CTAs only, grid-stride over rays
   int blocks = (int)(blocks_needed < max_blocks ? blocks_needed : max_blocks);
   cudaStream_t st = (cudaStream_t)stream;
-  if (c->mlp_mode == 2) {
+  if (c->mlp_mode == 3) {
+    // sampling kernel -> [33][rays] spacing edges -> shading kernel; bundles larger than the hand-over buffer are
+    // rendered in slices (whole 16-row tile bands when an image_width hint is given)
+    const size_t smem = (sizeof(TcShared) + 127) / 128 * 128 + (NFF_PANEL_GLOBAL ? 0 : sizeof(float) * kNff * kLaneThreads);
+    int64_t slice = c->handoff_rays;
+    if (rays->image_width > 0) {
+      const int64_t band = (int64_t)rays->image_width * (kLaneThreads / 32);
+      REQUIRE(band <= slice, "image_width too large for the two-stage renderer");
+      slice = slice / band * band;
+    }
+    const int fdim = kNff + c->app.dim;
+    for (int64_t start = 0; start < n_rays; start += slice) {
+      const int64_t cnt = n_rays - start < slice ? n_rays - start : slice;
+      RenderParams Q = P;
+      Q.n_rays = cnt;
+      offset_rays(Q, start, fdim);
+      int64_t need = (cnt + kLaneThreads - 1) / kLaneThreads;
+      if (rays->image_width > 0) {
+        const int64_t W = rays->image_width, H = (cnt + W - 1) / W;
+        need = ((W + 31) / 32) * ((H + kLaneThreads / 32 - 1) / (kLaneThreads / 32));
+      }
+      const int64_t max_a = (int64_t)c->sm_count * NFF_SAMPLE_CTAS, max_b = (int64_t)c->sm_count * kLaneCtasPerSm;
+      nff_sample_lane_kernel<<<(int)(need < max_a ? need : max_a), kLaneThreads, 0, st>>>(Q, c->d_lane_scratch, c->d_handoff);
+      nff_shade_lane_kernel<<<(int)(need < max_b ? need : max_b), kLaneThreads, smem, st>>>(Q, c->d_lane_scratch, c->d_handoff);
+    }
+  } else if (c->mlp_mode == 2) {
     const size_t smem = (sizeof(TcShared) + 127) / 128 * 128 + (NFF_PANEL_GLOBAL ? 0 : sizeof(float) * kNff * kLaneThreads);
     int64_t need = (n_rays + kLaneThreads - 1) / kLaneThreads;
     if (rays->image_width > 0) {
@@ -951,7 +1082,7 @@ int b200nerf_set_peer_outputs(b200nerf_ctx* c, const b200nerf_peer_outputs* peer
 
 int b200nerf_set_mlp_mode(b200nerf_ctx* c, int mode) {
   REQUIRE(c, "ctx is NULL");
-  REQUIRE(mode >= 0 && mode <= 2, "render mode: 0 = warp-per-ray + CUDA-core fp32, 1 = warp-per-ray + tcgen05, 2 = ray-per-lane + tcgen05");
+  REQUIRE(mode >= 0 && mode <= 3, "render mode: 0 = warp-per-ray + CUDA-core fp32, 1 = warp-per-ray + tcgen05, 2 = ray-per-lane + tcgen05, 3 = ray-per-lane in two kernels (sampling, shading)");
   c->mlp_mode = mode;
   return 0;
 }

@@ -188,7 +188,8 @@ NFF_D void encode_f4_col(const float* NFF_RESTRICT table, const Grid& gr, int L,
 struct LaneRoundIO {
   int S, S_new;
   const float* u_tab;
-  float* bins_out;  // [S_new+1][kLaneThreads] scratch
+  float* bins_out;  // this lane's column of the new edges: element i at bins_out[i * bins_stride]
+  int64_t bins_stride;
   float* tr_w;
   int32_t* tr_aid;
   float* tr_bins_s;
@@ -260,7 +261,7 @@ NFF_D float lane_proposal_round(const RenderParams& P, const FieldGrids& fg, con
     float t = nan_to_num(fdiv(fsub(u, c_km1), fsub(k > S ? c_km1 : c_k, c_km1)));
     t = fminf(fmaxf(t, 0.0f), 1.0f);
     const float nb = fadd(b0, fmul(t, fsub(b1, b0)));
-    io.bins_out[(size_t)i * kLaneThreads + tid] = nb;
+    io.bins_out[(size_t)i * io.bins_stride] = nb;
     if (io.tr_inds) io.tr_inds[ray * (S_new + 1) + i] = k;
     if (io.tr_bins_s) io.tr_bins_s[ray * (S_new + 1) + i] = nb;
     if (io.tr_bins_e) io.tr_bins_e[ray * (S_new + 1) + i] = to_euclid(nb, s_near, s_far, sp);
@@ -325,29 +326,41 @@ struct MlpLaneTc {
 
 // --------------------------------------------------------------------------------------------- the whole ray
 // NeuRADModel.get_nff_outputs (models/neurad.py:368-421), eval mode, for the ray owned by this lane.
-template <class Mlp>
-NFF_D void render_ray_lane(const RenderParams& P, const LaneScratch& sc, Mlp& mlp, int tid, int64_t ray, bool active) {
-  const Sampling& sp = P.samp;
+// Per-ray constants shared by the sampling and the shading stage.
+struct LaneRay {
   float o[3], d[3];
+  float area, time, s_near, s_far;
+  int n_cand;
+};
+NFF_D LaneRay lane_ray_setup(const RenderParams& P, const LaneScratch& sc, int tid, int64_t ray) {
+  const Sampling& sp = P.samp;
+  LaneRay R;
 #pragma unroll
   for (int i = 0; i < 3; ++i) {
-    o[i] = ldg(P.rays.origins + 3 * ray + i);
-    d[i] = ldg(P.rays.directions + 3 * ray + i);
+    R.o[i] = ldg(P.rays.origins + 3 * ray + i);
+    R.d[i] = ldg(P.rays.directions + 3 * ray + i);
   }
   const bool lidar = P.rays.is_lidar ? P.rays.is_lidar[ray] != 0 : false;
-  const float area = fmul(ldg(P.rays.pixel_area + ray), lidar ? 1.0f : sp.cam_area_scale);
-  const float time = ldg(P.rays.times + ray);
-  float far_ = P.rays.fars ? ldg(P.rays.fars + ray) : 1.0e6f;
+  R.area = fmul(ldg(P.rays.pixel_area + ray), lidar ? 1.0f : sp.cam_area_scale);  // _scale_pixel_area (neurad.py:702-709)
+  R.time = ldg(P.rays.times + ray);
+  float far_ = P.rays.fars ? ldg(P.rays.fars + ray) : 1.0e6f;  // _get_ray_samples (neurad.py:443-449)
   far_ = fminf(far_, sp.sky_distance);
   const float near_ = P.rays.nears ? ldg(P.rays.nears + ray) : 0.0f;
-  const float s_near = spacing_fn(near_, sp), s_far = spacing_fn(far_, sp);
-
+  R.s_near = spacing_fn(near_, sp);
+  R.s_far = spacing_fn(far_, sp);
   int overflow = 0;
-  const int n_cand = lane_actor_candidates(P.actors, time, o, d, sc, tid, &overflow);
+  R.n_cand = lane_actor_candidates(P.actors, R.time, R.o, R.d, sc, tid, &overflow);
 #if defined(__CUDACC__)
   if (overflow && P.status) atomicExch(P.status, 3);
 #endif
+  return R;
+}
 
+// Sampling stage: both proposal rounds (ProposalNetworkSampler.generate_ray_samples, ray_samplers.py:623-666).  The
+// final spacing edges go to this lane's column `bins2` (element i at bins2[i * bins2_stride]); prop depths to P.out.
+NFF_D void sample_ray_lane(const RenderParams& P, const LaneScratch& sc, const LaneRay& R, int tid, int64_t ray, bool active,
+                           float* bins2, int64_t bins2_stride) {
+  const Sampling& sp = P.samp;
   float prop_depth[2];
 #pragma unroll 1
   for (int rd = 0; rd < 2; ++rd) {  // one copy of the round's code for both rounds (instruction-cache footprint)
@@ -355,16 +368,31 @@ NFF_D void render_ray_lane(const RenderParams& P, const LaneScratch& sc, Mlp& ml
     io.S = rd == 0 ? kS0 : kS1;
     io.S_new = rd == 0 ? kS1 : kS2;
     io.u_tab = rd == 0 ? sp.u1 : sp.u2;
-    io.bins_out = rd == 0 ? sc.bins1 : sc.bins2;
+    io.bins_out = rd == 0 ? sc.bins1 + tid : bins2;
+    io.bins_stride = rd == 0 ? (int64_t)kLaneThreads : bins2_stride;
     io.tr_w = !active ? nullptr : rd == 0 ? P.trace.prop_weights_0 : P.trace.prop_weights_1;
     io.tr_aid = !active ? nullptr : rd == 0 ? P.trace.actor_id_0 : P.trace.actor_id_1;
     io.tr_bins_s = !active ? nullptr : rd == 0 ? P.trace.bins_s_1 : P.trace.bins_s_2;
     io.tr_bins_e = !active ? nullptr : rd == 0 ? P.trace.bins_e_1 : P.trace.bins_e_2;
     io.tr_inds = !active ? nullptr : rd == 0 ? P.trace.inds_1 : P.trace.inds_2;
-    prop_depth[rd] = lane_proposal_round(P, P.fields[sp.field_of_round[rd]], sc, tid, n_cand, io,
-                                         rd == 0 ? nullptr : sc.bins1 + tid, o, d, area, s_near, s_far, ray);
+    prop_depth[rd] = lane_proposal_round(P, P.fields[sp.field_of_round[rd]], sc, tid, R.n_cand, io,
+                                         rd == 0 ? nullptr : sc.bins1 + tid, R.o, R.d, R.area, R.s_near, R.s_far, ray);
   }
-  const float prop_depth_0 = prop_depth[0], prop_depth_1 = prop_depth[1];
+  if (active) {
+    P.out.prop_depth_0[ray] = prop_depth[0];
+    P.out.prop_depth_1[ray] = prop_depth[1];
+  }
+}
+
+// Shading stage: main field on the 32 resampled intervals + compositing + outputs (neurad.py:368-401).
+template <class Mlp>
+NFF_D void shade_ray_lane(const RenderParams& P, const LaneScratch& sc, const LaneRay& R, Mlp& mlp, int tid, int64_t ray,
+                          bool active, const float* bins2, int64_t bins2_stride) {
+  const Sampling& sp = P.samp;
+  const float* o = R.o;
+  const float* d = R.d;
+  const float area = R.area, time = R.time, s_near = R.s_near, s_far = R.s_far;
+  const int n_cand = R.n_cand;
 
   // ---- main field: loop over the 32 samples of this ray (fields/neurad_field.py:128-152 + compositing) ----
   const FieldGrids& fm = P.fields[B200NERF_FIELD_MAIN];
@@ -373,11 +401,11 @@ NFF_D void render_ray_lane(const RenderParams& P, const LaneScratch& sc, Mlp& ml
   for (int i = 0; i < kNff; ++i) fsum[i] = 0.0f;
   double T_d = 1.0;
   float acc = 0.0f, depth = 0.0f;
-  float e_prev = to_euclid(sc.bins2[tid], s_near, s_far, sp);
+  float e_prev = to_euclid(bins2[0], s_near, s_far, sp);
 #pragma unroll 1
   for (int s = 0; s < kS2; ++s) {
     const float e0 = e_prev;
-    float e1 = to_euclid(sc.bins2[(size_t)(s + 1) * kLaneThreads + tid], s_near, s_far, sp);
+    float e1 = to_euclid(bins2[(size_t)(s + 1) * bins2_stride], s_near, s_far, sp);
     e_prev = e1;
     if (s == kS2 - 1) e1 = fadd(e1, fsub(sp.sky_distance, e1));  // sky sample (neurad.py:451-455)
     Gauss g = sample_gaussian(o, d, area, e0, e1);
@@ -503,8 +531,6 @@ NFF_D void render_ray_lane(const RenderParams& P, const LaneScratch& sc, Mlp& ml
   if (!active) return;
   P.out.depth[ray] = depth;
   P.out.accumulation[ray] = acc;
-  P.out.prop_depth_0[ray] = prop_depth_0;
-  P.out.prop_depth_1[ray] = prop_depth_1;
 #if defined(__CUDACC__)
   for (int p = 0; p < P.peers.n_peers; ++p) {
     if (p == P.peers.self_rank) continue;
@@ -512,6 +538,15 @@ NFF_D void render_ray_lane(const RenderParams& P, const LaneScratch& sc, Mlp& ml
     P.peers.accumulation[p][P.peers.row_offset + ray] = acc;
   }
 #endif
+}
+
+// NeuRADModel.get_nff_outputs (models/neurad.py:368-421), eval mode, for the ray owned by this lane: both stages back to
+// back with the resampled edges handed over through the CTA's scratch slab.
+template <class Mlp>
+NFF_D void render_ray_lane(const RenderParams& P, const LaneScratch& sc, Mlp& mlp, int tid, int64_t ray, bool active) {
+  const LaneRay R = lane_ray_setup(P, sc, tid, ray);
+  sample_ray_lane(P, sc, R, tid, ray, active, sc.bins2 + tid, kLaneThreads);
+  shade_ray_lane(P, sc, R, mlp, tid, ray, active, sc.bins2 + tid, kLaneThreads);
 }
 
 }  // namespace nff

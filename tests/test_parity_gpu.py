@@ -14,6 +14,7 @@ import torch
 
 import neurad_studio_b200 as nsb
 from neurad_studio_b200 import scene
+from neurad_studio_b200.backend import DEFAULT_MODE
 from oracle import neurad_oracle as O
 from oracle.convert import to_oracle_cfg
 from tests.helpers import cfg_from_meta, load_golden
@@ -46,7 +47,7 @@ def _check_against(out, ref, beta, index_rate=1e-3):
         assert rel_to_max(out[k], ref[k]) < 2e-3, (k, rel_to_max(out[k], ref[k]))
 
 
-@pytest.mark.parametrize("mode", ["lane", "tc", "ffma"])
+@pytest.mark.parametrize("mode", ["lane", "split", "tc", "ffma"])
 @pytest.mark.parametrize("name", ["nff_static.npz", "nff_actors.npz", "nff_sharp.npz"])
 def test_fused_render_matches_reference_golden(backend, name, mode):
     """All kernel variants: ray-per-lane + tcgen05 (default), warp-per-ray + tcgen05, warp-per-ray + CUDA-core fp32."""
@@ -59,7 +60,7 @@ def test_fused_render_matches_reference_golden(backend, name, mode):
         out = backend.render(r, want_trace=True, want_intensity=True)
         backend.check_status()
     finally:
-        backend.set_mlp_mode("lane")
+        backend.set_mlp_mode(DEFAULT_MODE)
     _check_against(out, ref, meta["beta"])
     assert rel_to_max(out["intensity"], ref["intensity"]) < 1e-4
     assert rel_to_max(out["ray_drop_logits"], ref["ray_drop_logits"]) < 1e-4
@@ -284,11 +285,36 @@ def test_full_size_properties(backend):
     o6 = backend.render(sub, image_width=77)  # ragged: 1003 rays = 13 rows of 77 + 2
     for k in ("features", "depth"):
         assert torch.equal(o6[k], o3[k]), k
+    # two-kernel variant (sampling | shading) runs the same arithmetic: identical results, also when the bundle is
+    # sliced because it exceeds the 2^21-ray hand-over buffer (with and without the tile walk)
+    backend.set_mlp_mode("split")
+    try:
+        o7 = backend.render(rays, image_width=640)
+        big = {k: torch.cat([v] * 10) for k, v in rays.items() if isinstance(v, torch.Tensor)}
+        o8 = backend.render(big)
+        o9 = backend.render(big, image_width=640)
+        backend.check_status()
+    finally:
+        backend.set_mlp_mode(DEFAULT_MODE)
+    n0 = out["depth"].shape[0]
+    assert big["origins"].shape[0] > (1 << 21)
+    for k in ("features", "depth", "accumulation", "prop_depth_0", "prop_depth_1"):
+        assert torch.equal(o7[k], out[k]), k
+        for o in (o8, o9):
+            for rep in (0, 8, 9):  # first slice, the copy straddling the slice boundary, last slice
+                assert torch.equal(o[k][rep * n0 : (rep + 1) * n0], out[k]), (k, rep)
+    backend.set_mlp_mode("lane")  # the single-kernel variant of the same code
+    try:
+        o10 = backend.render(rays, image_width=640)
+    finally:
+        backend.set_mlp_mode(DEFAULT_MODE)
+    for k in ("features", "depth", "accumulation", "prop_depth_0", "prop_depth_1"):
+        assert torch.equal(o10[k], out[k]), k
     # the kernel variants agree to fp32 level on the whole image
     for mode in ("ffma", "tc"):
         backend.set_mlp_mode(mode)
         o4 = backend.render(rays)
-        backend.set_mlp_mode("lane")
+        backend.set_mlp_mode(DEFAULT_MODE)
         assert rel_to_max(o4["features"], out["features"]) < 1e-4, mode
         assert rel_to_max(o4["depth"], out["depth"]) < 1e-4, mode
 

@@ -17,7 +17,7 @@ cfg = nsb.NeuRADConfig(n_actors=n_actors)
 trajs = scene.make_trajectories(n_actors, cfg.duration) if n_actors else None
 params = scene.make_params(cfg, seed=1, beta=3.0, sdf_bias=0.6, device="cuda", trajectories=trajs)
 be.load_params(cfg, params)
-be.set_mlp_mode(os.environ.get('MLP_MODE', 'lane'))
+be.set_mlp_mode(os.environ.get('MLP_MODE', 'split'))
 rays_list = []
 for cam in scene.pandaset_rig():
     r = be.raygen_pinhole(cam, 1, 3, 1, 3)
