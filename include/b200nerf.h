@@ -194,7 +194,8 @@ int b200nerf_sh4_fwd(b200nerf_ctx* ctx, const float* dirs, float* out, int64_t n
  * MLPs on the tcgen05 tensor cores with the 3xTF32 split (fp32-level accuracy): x [n_rows, in_dim] -> y [n_rows,
  * out_dims[n_layers-1]]; ReLU between layers, none at the output.  `weights_host` / `biases_host` are HOST arrays
  * of `n_layers` device pointers in nn.Linear layout ([out,in] / [out]; biases_host or its entries may be NULL).
- * Limits: 1..3 layers, every width <= 48. */
+ * Limits: 1..3 layers, every width <= 64 (<= 48: 48-column TMEM tile; wider, e.g. BASELINE config 1's 32 -> 64 -> 4:
+ * 64-column tile). */
 int b200nerf_mlp_fwd(b200nerf_ctx* ctx, const float* x, int64_t n_rows, int in_dim, int n_layers,
                      const float* const* weights_host, const float* const* biases_host, const int* out_dims_host,
                      float* y, void* stream);
@@ -223,6 +224,44 @@ int b200nerf_density_to_weights(b200nerf_ctx* ctx, const float* deltas, const fl
 /* nerfacc.render_weight_from_alpha on dense [N,S] (call site neurad.py:717). */
 int b200nerf_alpha_to_weights(b200nerf_ctx* ctx, const float* alphas, int n_rays, int s, float* weights,
                               void* stream);
+
+/* ---- generic sampler / renderer operators (BASELINE config 1 and the reference's per-module API) -------- */
+
+/* SpacedSampler.generate_ray_samples in eval mode (model_components/ray_samplers.py:80-132) for the reference's
+ * spacing functions: UniformSampler (:135-156), LinearDisparitySampler (:159-180), PowerSampler (:838-852, needs
+ * power_lambda / power_scaling), SqrtSampler (:183-204), LogSampler (:207-228).
+ * nears [N] (NULL -> 0), fars [N] -> euclidean bin edges bins_e [N, S+1]; the spacing-domain edges
+ * linspace(0,1,S+1) are the same for every ray and written to bins_s [S+1] when non-NULL. */
+enum { B200NERF_SPACING_UNIFORM = 0, B200NERF_SPACING_LINDISP = 1, B200NERF_SPACING_POWER = 2,
+       B200NERF_SPACING_SQRT = 3, B200NERF_SPACING_LOG = 4 };
+int b200nerf_spaced_sample(b200nerf_ctx* ctx, int kind, float power_lambda, float power_scaling, const float* nears,
+                           const float* fars, int64_t n_rays, int n_samples, float* bins_s, float* bins_e,
+                           void* stream);
+
+/* Frustums.get_positions (cameras/rays.py:50-59): origins + directions * (start + end) / 2 -> [N, S, 3]; with
+ * `aabb_host` (6 floats, [2,3]) additionally SceneBox.get_normalized_positions (data/scene_box.py:63-79). */
+int b200nerf_frustum_positions(b200nerf_ctx* ctx, const float* origins, const float* directions, const float* bins_e,
+                               int64_t n_rays, int n_samples, const float* aabb_host, float* positions, void* stream);
+
+/* Head activations of a density + colour field: raw [P, 1+C] -> density [P] = trunc_exp(raw[:,0])
+ * (field_components/activations.py:28-35), rgb [P, C] = sigmoid(raw[:,1:]). */
+int b200nerf_density_rgb_heads(b200nerf_ctx* ctx, const float* raw, int64_t n_points, int n_channels, float* density,
+                               float* rgb, void* stream);
+
+/* Renderers on dense [N,S] samples (model_components/renderers.py):
+ *   out_values [N,C]     = sum_s w*v                     FeatureRenderer (:83-85); with value_nan_to_num = 1 and
+ *                          + background*(1 - sum_s w)    `background_host` (C floats) RGBRenderer in eval mode
+ *                                                        (:103-148, 233-268; NULL = "random"/no blending)
+ *   out_accumulation [N] = sum_s w                       AccumulationRenderer (:322-350)
+ *   out_depth [N]        DEPTH_EXPECTED: sum w*mid / (sum w + 1e-10), clipped to the GLOBAL [min, max] of mid over
+ *                        the whole batch as DepthRenderer("expected") does (:396-416); DEPTH_MEDIAN (:383-394);
+ *                        DEPTH_SIMPLE: NeuRAD's un-normalised render_depth_simple (models/neurad.py:727-734)
+ * with mid = (starts + ends) / 2, starts / ends [N,S].  Any output (and its inputs) may be NULL. */
+enum { B200NERF_DEPTH_NONE = 0, B200NERF_DEPTH_EXPECTED = 1, B200NERF_DEPTH_MEDIAN = 2, B200NERF_DEPTH_SIMPLE = 3 };
+int b200nerf_composite(b200nerf_ctx* ctx, const float* weights, const float* values, int n_channels,
+                       int value_nan_to_num, const float* background_host, const float* starts, const float* ends,
+                       int depth_method, int64_t n_rays, int n_samples, float* out_values, float* out_accumulation,
+                       float* out_depth, void* stream);
 
 /* ---- ray generation ------------------------------------------------------------------------------------- */
 

@@ -5,7 +5,7 @@ is in libb200nerf.so.  There is no CPU path: constructing a `B200Backend` withou
 from __future__ import annotations
 
 import ctypes
-from typing import Dict, Optional, Sequence
+from typing import Dict, Optional, Sequence, Tuple
 
 import torch
 
@@ -317,6 +317,73 @@ class B200Backend:
         a = self._dev(alphas)
         out = torch.empty_like(a)
         self._check(self.lib.b200nerf_alpha_to_weights(self._h, _ptr(a), a.shape[0], a.shape[1], _ptr(out), self._stream))
+        return out
+
+    # ------------------------------------------------------------------- generic sampler / renderer operators
+    SPACINGS = {"uniform": 0, "lindisp": 1, "power": 2, "sqrt": 3, "log": 4}
+    DEPTH_METHODS = {None: 0, "expected": 1, "median": 2, "simple": 3}
+
+    def spaced_sample(self, nears: Optional[torch.Tensor], fars: torch.Tensor, num_samples: int, spacing: str = "uniform",
+                      power_lambda: float = -1.0, power_scaling: float = 0.1) -> Tuple[torch.Tensor, torch.Tensor]:
+        """SpacedSampler.generate_ray_samples, eval mode (model_components/ray_samplers.py:80-132):
+        nears/fars [N] or [N,1] -> (spacing bins [S+1], euclidean bin edges [N,S+1])."""
+        f = self._dev(fars).reshape(-1)
+        nr = None if nears is None else self._dev(nears).reshape(-1)
+        n = f.shape[0]
+        bins_s = torch.empty(num_samples + 1, device=self.device)
+        bins_e = torch.empty(n, num_samples + 1, device=self.device)
+        self._check(self.lib.b200nerf_spaced_sample(self._h, self.SPACINGS[spacing], power_lambda, power_scaling, _ptr(nr), _ptr(f), n,
+                                                    num_samples, _ptr(bins_s), _ptr(bins_e), self._stream))
+        if n == 0:
+            bins_s = torch.linspace(0.0, 1.0, num_samples + 1, device=self.device)
+        return bins_s, bins_e
+
+    def frustum_positions(self, origins: torch.Tensor, directions: torch.Tensor, bins_e: torch.Tensor,
+                          aabb: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """Frustums.get_positions (cameras/rays.py:50-59) for contiguous bins [N,S+1] -> [N,S,3]; with `aabb` [2,3]
+        also SceneBox.get_normalized_positions (data/scene_box.py:63-79)."""
+        o, d, b = self._dev(origins).reshape(-1, 3), self._dev(directions).reshape(-1, 3), self._dev(bins_e)
+        n, s = b.shape[0], b.shape[1] - 1
+        out = torch.empty(n, s, 3, device=self.device)
+        ab = None if aabb is None else (ctypes.c_float * 6)(*[float(v) for v in aabb.detach().float().cpu().reshape(-1)])
+        self._check(self.lib.b200nerf_frustum_positions(self._h, _ptr(o), _ptr(d), _ptr(b), n, s, ab, _ptr(out), self._stream))
+        return out
+
+    def density_rgb_heads(self, raw: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+        """raw [*, 1+C] -> (density [*,1] = trunc_exp(raw[...,0]), rgb [*,C] = sigmoid(raw[...,1:]))."""
+        r = self._dev(raw)
+        c = r.shape[-1] - 1
+        flat = r.reshape(-1, c + 1)
+        density = torch.empty(flat.shape[0], device=self.device)
+        rgb = torch.empty(flat.shape[0], c, device=self.device)
+        self._check(self.lib.b200nerf_density_rgb_heads(self._h, _ptr(flat), flat.shape[0], c, _ptr(density), _ptr(rgb), self._stream))
+        return density.reshape(*r.shape[:-1], 1), rgb.reshape(*r.shape[:-1], c)
+
+    def composite(self, weights: torch.Tensor, values: Optional[torch.Tensor] = None, starts: Optional[torch.Tensor] = None,
+                  ends: Optional[torch.Tensor] = None, depth_method: Optional[str] = None, background: Optional[Sequence[float]] = None,
+                  value_nan_to_num: bool = False, want_accumulation: bool = True) -> Dict[str, torch.Tensor]:
+        """Feature/RGB/Accumulation/Depth renderers on dense samples (model_components/renderers.py): weights [N,S]
+        (or [N,S,1]), values [N,S,C], starts/ends [N,S] -> {"values" [N,C], "accumulation" [N,1], "depth" [N,1]}."""
+        w = self._dev(weights)
+        n, s = w.shape[0], w.shape[1]
+        w = w.reshape(n, s)
+        out: Dict[str, torch.Tensor] = {}
+        v = ov = None
+        c = 0
+        if values is not None:
+            c = values.shape[-1]
+            v = self._dev(values).reshape(n, s, c)
+            ov = out["values"] = torch.empty(n, c, device=self.device)
+        oa = None
+        if want_accumulation:
+            oa = out["accumulation"] = torch.empty(n, 1, device=self.device)
+        st = en = od = None
+        if depth_method is not None:
+            st, en = self._dev(starts).reshape(n, s), self._dev(ends).reshape(n, s)
+            od = out["depth"] = torch.empty(n, 1, device=self.device)
+        bg = None if background is None else (ctypes.c_float * c)(*[float(b) for b in background])
+        self._check(self.lib.b200nerf_composite(self._h, _ptr(w), _ptr(v), c, int(value_nan_to_num), bg, _ptr(st), _ptr(en),
+                                                self.DEPTH_METHODS[depth_method], n, s, _ptr(ov), _ptr(oa), _ptr(od), self._stream))
         return out
 
     # ------------------------------------------------------------------------------------------- ray generation

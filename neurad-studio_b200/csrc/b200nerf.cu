@@ -42,6 +42,7 @@ struct b200nerf_ctx {
   int mlp_mode = 3;  // 3 = ray-per-lane in two kernels (sampling | shading + tcgen05), 2 = the same as one fused kernel, 1 = warp-per-ray + tcgen05 (3xTF32), 0 = warp-per-ray + CUDA-core fp32 FFMA
   float* d_lane_scratch = nullptr;
   int lane_ctas = 0;
+  unsigned* d_minmax = nullptr;      // [2] ordered-bit min / max of the depth steps (DepthRenderer "expected" clip)
   float* d_handoff = nullptr;        // [kS2+1][rays] spacing edges between the sampling and the shading kernel
   int64_t handoff_rays = 0;
   b200nerf_peer_outputs peers{};
@@ -409,6 +410,176 @@ __global__ void weights_kernel(const float* __restrict__ a, const float* __restr
   }
 }
 
+// ---------------------------------------------------------------------------------------- generic stage operators
+// SpacedSampler.generate_ray_samples, eval mode (model_components/ray_samplers.py:80-132) for the reference's spacing
+// functions: Uniform (:135-156), LinearDisparity (:159-180), Sqrt (:183-204), Log (:207-228), Power (:838-852).
+struct SpacingArgs {
+  int kind;
+  Sampling power;  // kind == B200NERF_SPACING_POWER
+};
+__device__ __forceinline__ float spacing_apply(const SpacingArgs& a, float x) {
+  switch (a.kind) {
+    case 0: return x;
+    case 1: return fdiv(1.0f, x);
+    case 2: return spacing_fn(x, a.power);
+    case 3: return fsqrt(x);
+    default: return logf(x);
+  }
+}
+__device__ __forceinline__ float spacing_invert(const SpacingArgs& a, float y) {
+  switch (a.kind) {
+    case 0: return y;
+    case 1: return fdiv(1.0f, y);
+    case 2: return spacing_fn_inv(y, a.power);
+    case 3: return fmul(y, y);
+    default: return expf(y);
+  }
+}
+__global__ void spaced_sample_kernel(const SpacingArgs a, const float* __restrict__ nears, const float* __restrict__ fars,
+                                     int64_t n_rays, int S, float* __restrict__ bins_s, float* __restrict__ bins_e) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_rays * (S + 1)) return;
+  const int64_t ray = i / (S + 1);
+  const int e = (int)(i % (S + 1));
+  const float u = linspace01(e, S);
+  if (bins_s && ray == 0) bins_s[e] = u;
+  const float s_near = spacing_apply(a, nears ? nears[ray] : 0.0f), s_far = spacing_apply(a, fars[ray]);
+  bins_e[i] = spacing_invert(a, fadd(fmul(u, s_far), fmul(fsub(1.0f, u), s_near)));
+}
+// Frustums.get_positions (cameras/rays.py:50-59) + SceneBox.get_normalized_positions (data/scene_box.py:63-79)
+struct AabbArgs {
+  int normalize;
+  float lo[3], len[3];
+};
+__global__ void frustum_positions_kernel(const AabbArgs a, const float* __restrict__ origins, const float* __restrict__ dirs,
+                                         const float* __restrict__ bins_e, int64_t n_rays, int S, float* __restrict__ out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_rays * S) return;
+  const int64_t ray = i / S;
+  const int s = (int)(i % S);
+  const float t = fadd(bins_e[ray * (S + 1) + s], bins_e[ray * (S + 1) + s + 1]);
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    float p = fadd(origins[3 * ray + k], fdiv(fmul(dirs[3 * ray + k], t), 2.0f));
+    if (a.normalize) p = fdiv(fsub(p, a.lo[k]), a.len[k]);
+    out[3 * i + k] = p;
+  }
+}
+// Field head activations of the reference's density + colour fields: density = trunc_exp(raw[...,0])
+// (field_components/activations.py:28-35), rgb = Sigmoid(raw[...,1:1+C]).
+__global__ void density_rgb_heads_kernel(const float* __restrict__ raw, int64_t n, int C, float* __restrict__ density,
+                                         float* __restrict__ rgb) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n * (C + 1)) return;
+  const int64_t p = i / (C + 1);
+  const int k = (int)(i % (C + 1));
+  const float v = raw[i];
+  if (k == 0) density[p] = expf(v);
+  else rgb[p * C + (k - 1)] = fdiv(1.0f, fadd(1.0f, expf(-v)));
+}
+
+// Renderers on dense [N,S] samples, one warp per ray (lane = sample):
+//   values:        FeatureRenderer / RGBRenderer.combine_rgb (renderers.py:83-85, 103-148): sum_s w*v (+ bg*(1-acc))
+//   accumulation:  AccumulationRenderer (renderers.py:322-350)
+//   depth:         DepthRenderer "expected" (:396-416, the global clip is applied by depth_clip_kernel), "median"
+//                  (:383-394), or NeuRAD's un-normalised render_depth_simple (models/neurad.py:727-734)
+__device__ __forceinline__ unsigned order_bits(float f) {
+  unsigned u = __float_as_uint(f);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float unorder_bits(unsigned u) {
+  return __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u);
+}
+struct CompositeArgs {
+  int C, value_nan_to_num, has_background, depth_method;
+  float background[64];
+};
+__global__ void composite_kernel(const CompositeArgs a, const float* __restrict__ weights, const float* __restrict__ values,
+                                 const float* __restrict__ starts, const float* __restrict__ ends, int64_t n_rays, int S,
+                                 float* __restrict__ out_values, float* __restrict__ out_acc, float* __restrict__ out_depth,
+                                 unsigned* __restrict__ minmax) {
+  const int ln = threadIdx.x & 31;
+  const int64_t ray = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (ray >= n_rays) return;
+  float acc = 0.f, dsum = 0.f, smin = 3.4e38f, smax = -3.4e38f, median = 0.f;
+  double carry = 0.0;
+  int below = 0;
+  const bool want_depth = a.depth_method != 0 && out_depth;
+  for (int s0 = 0; s0 < S; s0 += 32) {
+    const int s = s0 + ln;
+    const float w = s < S ? weights[ray * S + s] : 0.f;
+    acc += w;
+    if (want_depth) {
+      const float mid = s < S ? fdiv(fadd(starts[ray * S + s], ends[ray * S + s]), 2.0f) : 0.f;
+      dsum += fmul(w, mid);
+      if (s < S) { smin = fminf(smin, mid); smax = fmaxf(smax, mid); }
+      if (a.depth_method == 2) {  // torch.cumsum accumulates fp32 inputs in double on the CPU path; mirror that
+        double c = (double)w;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+          double n = __shfl_up_sync(0xffffffffu, c, d);
+          if (ln >= d) c += n;
+        }
+        c += carry;
+        carry = __shfl_sync(0xffffffffu, c, 31);
+        below += __popc(__ballot_sync(0xffffffffu, s < S && (float)c < 0.5f));
+      }
+    }
+  }
+  acc = warp_sum(acc);
+  if (out_acc && ln == 0) out_acc[ray] = acc;
+  if (want_depth) {
+    dsum = warp_sum(dsum);
+    if (a.depth_method == 2) {
+      const int idx = below < S - 1 ? below : S - 1;
+      median = fdiv(fadd(starts[ray * S + idx], ends[ray * S + idx]), 2.0f);
+    }
+    if (a.depth_method == 1) {
+#pragma unroll
+      for (int m = 16; m >= 1; m >>= 1) {
+        smin = fminf(smin, __shfl_xor_sync(0xffffffffu, smin, m));
+        smax = fmaxf(smax, __shfl_xor_sync(0xffffffffu, smax, m));
+      }
+      if (ln == 0) {
+        atomicMin(&minmax[0], order_bits(smin));
+        atomicMax(&minmax[1], order_bits(smax));
+      }
+    }
+    if (ln == 0)
+      out_depth[ray] = a.depth_method == 1 ? fdiv(dsum, fadd(acc, 1e-10f)) : a.depth_method == 2 ? median : dsum;
+  }
+  if (values && out_values) {
+    const int C = a.C;
+    for (int c0 = 0; c0 < C; c0 += 8) {  // 8 channels per pass keeps the per-lane partial sums in registers
+      float part[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) part[k] = 0.f;
+      for (int s = ln; s < S; s += 32) {
+        const float w = weights[ray * S + s];
+        const float* v = values + (ray * S + s) * C + c0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+          if (c0 + k < C) {
+            float x = v[k];
+            if (a.value_nan_to_num) x = nan_to_num(x);
+            part[k] += fmul(w, x);
+          }
+      }
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const float t = warp_sum(part[k]);
+        if (ln == 0 && c0 + k < C) out_values[ray * C + c0 + k] = a.has_background ? fadd(t, fmul(a.background[c0 + k], fsub(1.0f, acc))) : t;
+      }
+    }
+  }
+}
+__global__ void depth_clip_kernel(float* __restrict__ depth, int64_t n, const unsigned* __restrict__ minmax) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float lo = unorder_bits(minmax[0]), hi = unorder_bits(minmax[1]);
+  depth[i] = fminf(fmaxf(depth[i], lo), hi);  // torch.clip
+}
+
 // Per-keyframe Gram-Schmidt of the 6-D rotations (utils/poses.py:107-114) + actor_bounds / radii
 // (dynamic_actors.py:107-108, neurad_encoding.py:227).
 __global__ void actors_prep_kernel(int n_times, int n_actors, const float* __restrict__ rot6, const float* __restrict__ pos,
@@ -460,7 +631,7 @@ struct MlpArgs {
   int smem_off[3];  // float offsets of each layer's (hi) tile; lo follows at +n_pad*k_pad
   int bias_off;
 };
-constexpr int kTcKMax = 48, kTcNMax = 48;
+template <int kTcKMax, int kTcNMax>
 __global__ void __launch_bounds__(128) mlp_tc_kernel(const MlpArgs a, const float* __restrict__ x, float* __restrict__ y,
                                                      int64_t n_rows, int* __restrict__ status) {
   extern __shared__ __align__(128) float sm_mlp[];
@@ -505,6 +676,9 @@ __global__ void __launch_bounds__(128) mlp_tc_kernel(const MlpArgs a, const floa
       tc::tmem_ld16(lane_base + Cols::d, d);
       if (a.n_pad[l] > 16) tc::tmem_ld16(lane_base + Cols::d + 16, d + 16);
       if (a.n_pad[l] > 32) tc::tmem_ld16(lane_base + Cols::d + 32, d + 32);
+      if constexpr (kTcNMax > 48) {
+        if (a.n_pad[l] > 48) tc::tmem_ld16(lane_base + Cols::d + 48, d + 48);
+      }
       tc::wait_ld();
       const float* bias = sm_mlp + a.bias_off + l * kTcNMax;
       const bool last = l == a.n_layers - 1;
@@ -716,6 +890,7 @@ int b200nerf_create(int device_ordinal, b200nerf_ctx** out) {
   CUDA_TRY(cudaFuncSetAttribute(nff_shade_lane_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 (int)((sizeof(TcShared) + 127) / 128 * 128 + (NFF_PANEL_GLOBAL ? 0 : sizeof(float) * kNff * kLaneThreads))));
   CUDA_TRY(cudaFuncSetAttribute(nff_sample_lane_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 0));  // all L1
+  CUDA_TRY(cudaMalloc((void**)&c->d_minmax, 2 * sizeof(unsigned)));
   c->handoff_rays = (int64_t)1 << 21;
   CUDA_TRY(cudaMalloc((void**)&c->d_handoff, sizeof(float) * (kS2 + 1) * c->handoff_rays));
   *out = c;
@@ -733,6 +908,7 @@ int b200nerf_destroy(b200nerf_ctx* c) {
   cudaFree(c->d_main_mlp_nn);
   cudaFree(c->d_lane_scratch);
   cudaFree(c->d_handoff);
+  cudaFree(c->d_minmax);
   cudaFree(c->d_lidar_mlp);
   cudaFree(c->d_act_times);
   cudaFree(c->d_act_kf);
@@ -1027,17 +1203,19 @@ int b200nerf_mlp_fwd(b200nerf_ctx* c, const float* x, int64_t n_rows, int in_dim
                      float* y, void* stream) {
   REQUIRE(c && weights_host && out_dims_host, "NULL argument");
   REQUIRE(n_layers >= 1 && n_layers <= 3, "MLP depth must be 1..3 Linear layers");
-  REQUIRE(in_dim >= 1 && in_dim <= kTcKMax, "in_dim must be <= 48");
+  constexpr int kWide = 64;
+  REQUIRE(in_dim >= 1 && in_dim <= kWide, "in_dim must be <= 64");
   if (n_rows == 0) return 0;
   REQUIRE(x && y, "NULL argument");
   DeviceGuard g(c->device);
   MlpArgs a{};
   a.n_layers = n_layers;
   a.in_dim = in_dim;
-  int k = in_dim, off = 0;
+  int k = in_dim, off = 0, wmax = in_dim;
   for (int l = 0; l < n_layers; ++l) {
     int n = out_dims_host[l];
-    REQUIRE(n >= 1 && n <= kTcNMax, "layer widths must be <= 48");
+    REQUIRE(n >= 1 && n <= kWide, "layer widths must be <= 64");
+    wmax = n > wmax ? n : wmax;
     REQUIRE(weights_host[l] != nullptr, "NULL weight");
     a.w[l] = weights_host[l];
     a.b[l] = biases_host ? biases_host[l] : nullptr;
@@ -1050,16 +1228,117 @@ int b200nerf_mlp_fwd(b200nerf_ctx* c, const float* x, int64_t n_rows, int in_dim
     k = n;
   }
   a.bias_off = off;
-  size_t smem = sizeof(float) * (off + 3 * kTcNMax);
+  // NeuRAD's own MLPs (<= 48 wide) use the 48-column tile; wider ones (config 1's 32 -> 64 -> 4) the 64-column tile
+  const int tile_w = wmax <= 48 ? 48 : kWide;
+  size_t smem = sizeof(float) * (off + 3 * tile_w);
   static bool attr_set = false;
   if (!attr_set) {
-    CUDA_TRY(cudaFuncSetAttribute(mlp_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+    CUDA_TRY(cudaFuncSetAttribute(mlp_tc_kernel<48, 48>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+    CUDA_TRY(cudaFuncSetAttribute(mlp_tc_kernel<64, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
     attr_set = true;
   }
   int64_t tiles = (n_rows + 127) / 128;
   int grid = (int)(tiles < (int64_t)c->sm_count * 2 ? tiles : (int64_t)c->sm_count * 2);
-  mlp_tc_kernel<<<grid, 128, smem, (cudaStream_t)stream>>>(a, x, y, n_rows, c->d_status);
+  if (tile_w == 48)
+    mlp_tc_kernel<48, 48><<<grid, 128, smem, (cudaStream_t)stream>>>(a, x, y, n_rows, c->d_status);
+  else
+    mlp_tc_kernel<64, 64><<<grid, 128, smem, (cudaStream_t)stream>>>(a, x, y, n_rows, c->d_status);
   CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+int b200nerf_spaced_sample(b200nerf_ctx* c, int kind, float power_lambda, float power_scaling, const float* nears,
+                           const float* fars, int64_t n_rays, int n_samples, float* bins_s, float* bins_e, void* stream) {
+  REQUIRE(c, "ctx is NULL");
+  REQUIRE(kind >= B200NERF_SPACING_UNIFORM && kind <= B200NERF_SPACING_LOG, "unknown spacing kind");
+  REQUIRE(n_rays >= 0 && n_samples >= 1, "bad sample grid");
+  if (n_rays == 0) return 0;
+  REQUIRE(fars && bins_e, "NULL argument");
+  SpacingArgs a{};
+  a.kind = kind;
+  if (kind == B200NERF_SPACING_POWER) {
+    REQUIRE(power_lambda != 0.f && power_lambda != 1.f, "power_lambda 0 / 1 (log / identity spacing) is not supported");
+    REQUIRE(power_scaling > 0.f, "power_scaling must be positive");
+    a.power.lam = power_lambda;
+    a.power.scaling = power_scaling;
+    double lam1 = power_lambda - 1.0 < 0 ? -(power_lambda - 1.0) : (power_lambda - 1.0);
+    a.power.lam_1 = (float)lam1;
+    a.power.ratio = (float)(lam1 / (double)power_lambda);
+  }
+  DeviceGuard g(c->device);
+  const int64_t n = n_rays * (n_samples + 1);
+  spaced_sample_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(a, nears, fars, n_rays, n_samples, bins_s, bins_e);
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+int b200nerf_frustum_positions(b200nerf_ctx* c, const float* origins, const float* directions, const float* bins_e,
+                               int64_t n_rays, int n_samples, const float* aabb_host, float* positions, void* stream) {
+  REQUIRE(c, "ctx is NULL");
+  REQUIRE(n_rays >= 0 && n_samples >= 1, "bad sample grid");
+  if (n_rays == 0) return 0;
+  REQUIRE(origins && directions && bins_e && positions, "NULL argument");
+  AabbArgs a{};
+  if (aabb_host) {
+    a.normalize = 1;
+    for (int k = 0; k < 3; ++k) {
+      a.lo[k] = aabb_host[k];
+      a.len[k] = aabb_host[3 + k] - aabb_host[k];  // fp32 subtraction, as aabb[1] - aabb[0] in the reference
+      REQUIRE(a.len[k] > 0.f, "empty aabb");
+    }
+  }
+  DeviceGuard g(c->device);
+  const int64_t n = n_rays * n_samples;
+  frustum_positions_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(a, origins, directions, bins_e, n_rays,
+                                                                                          n_samples, positions);
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+int b200nerf_density_rgb_heads(b200nerf_ctx* c, const float* raw, int64_t n_points, int n_channels, float* density,
+                               float* rgb, void* stream) {
+  REQUIRE(c, "ctx is NULL");
+  REQUIRE(n_points >= 0 && n_channels >= 1, "bad shape");
+  if (n_points == 0) return 0;
+  REQUIRE(raw && density && rgb, "NULL argument");
+  DeviceGuard g(c->device);
+  const int64_t n = n_points * (n_channels + 1);
+  density_rgb_heads_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(raw, n_points, n_channels, density, rgb);
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+int b200nerf_composite(b200nerf_ctx* c, const float* weights, const float* values, int n_channels, int value_nan_to_num,
+                       const float* background_host, const float* starts, const float* ends, int depth_method,
+                       int64_t n_rays, int n_samples, float* out_values, float* out_accumulation, float* out_depth,
+                       void* stream) {
+  REQUIRE(c, "ctx is NULL");
+  REQUIRE(n_rays >= 0 && n_samples >= 1, "bad sample grid");
+  REQUIRE(depth_method >= B200NERF_DEPTH_NONE && depth_method <= B200NERF_DEPTH_SIMPLE, "unknown depth method");
+  REQUIRE(n_channels >= 0 && n_channels <= 64, "at most 64 value channels");
+  if (n_rays == 0) return 0;
+  REQUIRE(weights, "NULL weights");
+  REQUIRE(!(values || out_values) || (values && out_values && n_channels > 0), "values / out_values must come together");
+  REQUIRE(depth_method == B200NERF_DEPTH_NONE || (starts && ends && out_depth), "depth needs starts, ends and out_depth");
+  CompositeArgs a{};
+  a.C = n_channels;
+  a.value_nan_to_num = value_nan_to_num;
+  a.has_background = background_host != nullptr;
+  a.depth_method = depth_method;
+  if (background_host) memcpy(a.background, background_host, sizeof(float) * n_channels);
+  DeviceGuard g(c->device);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (depth_method == B200NERF_DEPTH_EXPECTED) {
+    CUDA_TRY(cudaMemsetAsync(c->d_minmax, 0xff, sizeof(unsigned), st));
+    CUDA_TRY(cudaMemsetAsync(c->d_minmax + 1, 0x00, sizeof(unsigned), st));
+  }
+  composite_kernel<<<(unsigned)((n_rays + 3) / 4), 128, 0, st>>>(a, weights, values, starts, ends, n_rays, n_samples, out_values,
+                                                                 out_accumulation, out_depth, c->d_minmax);
+  CUDA_TRY(cudaGetLastError());
+  if (depth_method == B200NERF_DEPTH_EXPECTED) {
+    depth_clip_kernel<<<(unsigned)((n_rays + 255) / 256), 256, 0, st>>>(out_depth, n_rays, c->d_minmax);
+    CUDA_TRY(cudaGetLastError());
+  }
   return 0;
 }
 

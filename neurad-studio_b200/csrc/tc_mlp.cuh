@@ -124,7 +124,7 @@ struct TileCols {
 template <int K_MAX>
 __device__ __forceinline__ void store_a(uint32_t lane_base, int k0, const float* x, int n) {
 #pragma unroll
-  for (int c = 0; c < 48; c += 8) {
+  for (int c = 0; c < K_MAX; c += 8) {
     if (c < n) {
       uint32_t h[8], l[8];
 #pragma unroll

@@ -76,6 +76,13 @@ SIGNATURES = {
                                       c_void_p, c_void_p, c_void_p]),
     "b200nerf_density_to_weights": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p]),
     "b200nerf_alpha_to_weights": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p]),
+    "b200nerf_spaced_sample": (c_int, [c_void_p, c_int, c_float, c_float, c_void_p, c_void_p, c_int64, c_int, c_void_p,
+                                       c_void_p, c_void_p]),
+    "b200nerf_frustum_positions": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, POINTER(c_float),
+                                           c_void_p, c_void_p]),
+    "b200nerf_density_rgb_heads": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p, c_void_p]),
+    "b200nerf_composite": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, POINTER(c_float), c_void_p, c_void_p,
+                                   c_int, c_int64, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     "b200nerf_raygen_pinhole": (c_int, [c_void_p, POINTER(c_float), c_float, c_float, c_float, c_float, c_int, c_int,
                                         c_int, c_int, c_int, c_int, c_int, c_int, c_float, POINTER(c_float), c_float,
                                         c_float, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),

@@ -10,7 +10,9 @@ modules, so that the parity tests read like the reference's own tests and a refe
   field_components/encodings.py:760  SHEncoding(levels=4)      SHEncoding        (forward -> sh4_fwd kernel)
   field_components/mlp.py:60    MLP(implementation=)           MLP               (forward -> tcgen05 mlp_fwd kernel)
   model_components/ray_samplers.py:255  PDFSampler             PDFSampler        (-> pdf_resample kernel)
-  model_components/renderers.py:59,322  Feature/AccumulationRenderer  same names (dense [N,S] inputs)
+  model_components/ray_samplers.py:56,135,838  Spaced/Uniform/.../PowerSampler  same names (-> spaced_sample kernel)
+  cameras/rays.py:33,127        Frustums, RaySamples           same names (get_positions / get_weights kernels)
+  model_components/renderers.py:59,93,322,353  Feature/RGB/Accumulation/DepthRenderer  same names (-> composite kernel)
   models/neurad.py:165          NeuRADModel.get_nff_outputs /  NeuRADModel       (-> fused nff_render_fwd kernel)
                                 get_outputs_for_camera_ray_bundle / decode_features (lidar half)
 
@@ -175,20 +177,173 @@ class PDFSampler:
         return be.pdf_resample(w, existing_bins, n, self.histogram_padding)[0]
 
 
+@dataclass
+class Frustums:
+    """cameras/rays.py:33-60 for contiguous samples: per-ray origins/directions [N,3] and the euclidean bin edges
+    [N,S+1] (starts = edges[:, :-1], ends = edges[:, 1:]) -- never expanded to [N,S,3] views."""
+
+    origins: Tensor
+    directions: Tensor
+    bin_edges: Tensor
+
+    @property
+    def starts(self) -> Tensor:
+        return self.bin_edges[:, :-1, None]
+
+    @property
+    def ends(self) -> Tensor:
+        return self.bin_edges[:, 1:, None]
+
+    @torch.no_grad()
+    def get_positions(self, normalize_aabb: Optional[Tensor] = None) -> Tensor:
+        """Frustums.get_positions (rays.py:50-59); with `normalize_aabb` [2,3] followed by
+        SceneBox.get_normalized_positions (data/scene_box.py:63-79)."""
+        be = get_backend(self.bin_edges.device)
+        return be.frustum_positions(self.origins, self.directions, self.bin_edges, normalize_aabb)
+
+
+@dataclass
+class RaySamples:
+    """cameras/rays.py:127-249 (the members the hot path reads)."""
+
+    frustums: Frustums
+    spacing_bins: Tensor  # [S+1], shared by all rays
+
+    @property
+    def spacing_starts(self) -> Tensor:
+        return self.spacing_bins[None, :-1, None]
+
+    @property
+    def spacing_ends(self) -> Tensor:
+        return self.spacing_bins[None, 1:, None]
+
+    @property
+    def deltas(self) -> Tensor:
+        return self.frustums.ends - self.frustums.starts
+
+    @torch.no_grad()
+    def get_weights(self, densities: Tensor) -> Tensor:
+        """RaySamples.get_weights (rays.py:188-210): densities [N,S,1] -> weights [N,S,1]."""
+        be = get_backend(densities.device)
+        return be.density_to_weights(self.deltas[..., 0], densities[..., 0])[..., None]
+
+
+class SpacedSampler:
+    """model_components/ray_samplers.py:56-132 in eval mode (no stratified jitter)."""
+
+    spacing = "uniform"
+
+    def __init__(self, num_samples: Optional[int] = None, train_stratified: bool = True, single_jitter: bool = False) -> None:
+        self.num_samples = num_samples
+
+    def _power(self) -> Tuple[float, float]:
+        return -1.0, 0.1
+
+    @torch.no_grad()
+    def __call__(self, ray_bundle: RayBundle, num_samples: Optional[int] = None) -> RaySamples:
+        assert ray_bundle.nears is not None and ray_bundle.fars is not None
+        n = num_samples or self.num_samples
+        assert n is not None
+        be = get_backend(ray_bundle.origins.device)
+        lam, scaling = self._power()
+        bins_s, bins_e = be.spaced_sample(ray_bundle.nears, ray_bundle.fars, n, self.spacing, lam, scaling)
+        return RaySamples(Frustums(ray_bundle.origins.reshape(-1, 3), ray_bundle.directions.reshape(-1, 3), bins_e), bins_s)
+
+    generate_ray_samples = __call__
+
+
+class UniformSampler(SpacedSampler):
+    """ray_samplers.py:135-156."""
+
+
+class LinearDisparitySampler(SpacedSampler):
+    """ray_samplers.py:159-180."""
+
+    spacing = "lindisp"
+
+
+class SqrtSampler(SpacedSampler):
+    """ray_samplers.py:183-204."""
+
+    spacing = "sqrt"
+
+
+class LogSampler(SpacedSampler):
+    """ray_samplers.py:207-228."""
+
+    spacing = "log"
+
+
+class PowerSampler(SpacedSampler):
+    """ray_samplers.py:838-852 (NeuRAD's initial sampler: power_lambda=-1, power_scaling=0.1, neurad.py:232-235)."""
+
+    spacing = "power"
+
+    def __init__(self, num_samples: Optional[int] = None, power_lambda: float = -1.0, power_scaling: float = 0.1, **kw) -> None:
+        super().__init__(num_samples, **kw)
+        self.power_lambda, self.power_scaling = power_lambda, power_scaling
+
+    def _power(self) -> Tuple[float, float]:
+        return self.power_lambda, self.power_scaling
+
+
 class FeatureRenderer(nn.Module):
     """model_components/renderers.py:59-90, unpacked branch: sum_s w_s * f_s."""
 
     @classmethod
+    @torch.no_grad()
     def forward(cls, features: Tensor, weights: Tensor) -> Tensor:
-        return torch.sum(features * weights, dim=-2)
+        return get_backend(weights.device).composite(weights, features, want_accumulation=False)["values"]
+
+
+class RGBRenderer(nn.Module):
+    """model_components/renderers.py:93-268 in eval mode: nan_to_num(rgb), composite, blend a constant background
+    ("random" / None = no blending, like black; "last_sample" is not provided)."""
+
+    COLORS = {"white": (1.0, 1.0, 1.0), "black": (0.0, 0.0, 0.0), "red": (1.0, 0.0, 0.0), "green": (0.0, 1.0, 0.0),
+              "blue": (0.0, 0.0, 1.0)}  # utils/colors.py:21-31
+
+    def __init__(self, background_color="random") -> None:
+        super().__init__()
+        if isinstance(background_color, str) and background_color not in ("random",) + tuple(self.COLORS):
+            raise NotImplementedError(f"background_color={background_color!r}")
+        self.background_color = background_color
+
+    @torch.no_grad()
+    def forward(self, rgb: Tensor, weights: Tensor) -> Tensor:
+        bg = self.background_color
+        if isinstance(bg, str):
+            bg = None if bg == "random" else self.COLORS[bg]
+        elif isinstance(bg, Tensor):
+            bg = [float(v) for v in bg.reshape(-1)]
+        be = get_backend(weights.device)
+        return be.composite(weights, rgb, background=bg, value_nan_to_num=True, want_accumulation=False)["values"]
 
 
 class AccumulationRenderer(nn.Module):
     """model_components/renderers.py:322-350, unpacked branch."""
 
     @classmethod
+    @torch.no_grad()
     def forward(cls, weights: Tensor) -> Tensor:
-        return torch.sum(weights, dim=-2)
+        return get_backend(weights.device).composite(weights)["accumulation"]
+
+
+class DepthRenderer(nn.Module):
+    """model_components/renderers.py:353-418: "median" or "expected" (with its batch-global clip)."""
+
+    def __init__(self, method: str = "median") -> None:
+        super().__init__()
+        if method not in ("median", "expected"):
+            raise NotImplementedError(f"Method {method} not implemented")
+        self.method = method
+
+    @torch.no_grad()
+    def forward(self, weights: Tensor, ray_samples: RaySamples) -> Tensor:
+        fr = ray_samples.frustums
+        be = get_backend(weights.device)
+        return be.composite(weights, starts=fr.starts.contiguous(), ends=fr.ends.contiguous(), depth_method=self.method,
+                            want_accumulation=False)["depth"]
 
 
 class NeuRADModel(nn.Module):

@@ -71,3 +71,38 @@ def test_raygen_matches_reference_golden():
     o = O.generate_rays_lidar_points(li["l2w"], li["points"], float(li["time"]), li["velocity"])
     for k in ("origins", "directions", "pixel_area", "times"):
         assert torch.equal(o[k], li[k]), k
+
+
+def test_config1_oracle_matches_reference_golden():
+    """BASELINE config 1 (64x64 pinhole, UniformSampler(32), 16x2 hash grid, MLP 32->64->4, RGB / expected-depth /
+    accumulation renderers): the restatement reproduces the reference's outputs bit for bit."""
+    from oracle import simple_oracle as S
+    from tests.helpers import load_config1
+
+    meta, p, r, ref = load_config1()
+    with torch.no_grad():
+        out = S.config1_render(p, r["origins"], r["directions"], r["nears"], r["fars"], 32, want_trace=True)
+    for k in ("rgb", "depth", "depth_median", "accumulation", "bins_e"):
+        assert torch.equal(out[k].reshape(ref[k].shape), ref[k]), k
+    for k in ("positions", "encoding", "raw", "density", "rgb_samples", "weights"):
+        assert torch.equal(out[k][::8].reshape(ref[k + "_sub"].shape), ref[k + "_sub"]), k
+    assert 0.5 < float(ref["accumulation"].mean()) < 1.0  # the case exercises compositing, not a saturated ray
+
+
+def test_spacing_functions_match_reference_samplers():
+    """SpacedSampler family (ray_samplers.py:135-228, 838-852), pinned by closed forms on a tiny case."""
+    from oracle import simple_oracle as S
+
+    nears, fars = torch.tensor([[1.0], [2.0]]), torch.tensor([[4.0], [10.0]])
+    _, e = S.spaced_sample(nears, fars, 3, S.SPACING_UNIFORM)
+    assert torch.allclose(e, torch.tensor([[1.0, 2.0, 3.0, 4.0], [2.0, 14 / 3, 22 / 3, 10.0]]))
+    _, e = S.spaced_sample(nears, fars, 2, S.SPACING_LINDISP)
+    assert torch.allclose(e[:, 1], 1 / (0.5 * (1 / nears[:, 0] + 1 / fars[:, 0])))
+    _, e = S.spaced_sample(nears, fars, 2, S.SPACING_SQRT)
+    assert torch.allclose(e[:, 1], (0.5 * (nears[:, 0].sqrt() + fars[:, 0].sqrt())) ** 2)
+    _, e = S.spaced_sample(nears, fars, 2, S.SPACING_LOG)
+    assert torch.allclose(e[:, 1], (nears[:, 0] * fars[:, 0]).sqrt())
+    for kind in range(5):
+        _, e = S.spaced_sample(nears, fars, 8, kind)
+        assert torch.allclose(e[:, 0], nears[:, 0], rtol=1e-5) and torch.allclose(e[:, -1], fars[:, 0], rtol=1e-5)
+        assert (e[:, 1:] > e[:, :-1]).all()

@@ -340,11 +340,12 @@ def test_errors_are_loud(backend):
 
 
 # ---------------------------------------------------------------------------------------- tensor-core MLP (tcgen05)
-@pytest.mark.parametrize("dims", [(32, 32, 33), (48, 32, 32, 32), (48, 32, 32, 2), (32, 32), (40, 24, 17)])
+@pytest.mark.parametrize("dims", [(32, 32, 33), (48, 32, 32, 32), (48, 32, 32, 2), (32, 32), (40, 24, 17), (32, 64, 4), (64, 64, 64, 64), (50, 57, 3)])
 @pytest.mark.parametrize("n_rows", [1000, 128 * 300 + 5])
 def test_mlp_fwd_tensor_core_vs_fp32(backend, dims, n_rows):
     """MLP.forward on tcgen05 with the 3xTF32 split vs a plain fp32 (float64-accumulated) reference of the same op:
-    NeuRAD's three MLP shapes (mlp_geo 32-32-33, mlp_feature 48-32-32-32, lidar_decoder 48-32-32-2)."""
+    NeuRAD's three MLP shapes (mlp_geo 32-32-33, mlp_feature 48-32-32-32, lidar_decoder 48-32-32-2) on the 48-column
+    tile; BASELINE config 1's 32-64-4 and other <= 64-wide shapes on the 64-column tile."""
     gen = torch.Generator().manual_seed(sum(dims) + n_rows)
     x = torch.randn(n_rows, dims[0], generator=gen)
     ws, bs = [], []
@@ -477,3 +478,103 @@ def test_peer_outputs_stream_to_pinned_host_memory(backend):
             backend.set_peer_outputs(None)
         for k, v in host.items():
             assert torch.equal(v, out[k].cpu()), (k, width)
+
+
+# ------------------------------------------------------------------- BASELINE config 1 + generic sampler / renderers
+def test_config1_matches_reference_golden(backend):
+    """BASELINE config 1 through the reference-API mirror, stage by stage and end to end, against the outputs of
+    the real reference (tests/golden/config1.npz): Cameras -> UniformSampler(32) -> normalised positions ->
+    HashEncoding(16x2, 2^19) -> MLP 32->64->4 -> trunc_exp / sigmoid -> get_weights -> RGB / depth / accumulation."""
+    from neurad_studio_b200.nerfstudio_api import (MLP, AccumulationRenderer, DepthRenderer, HashEncoding, RayBundle, RGBRenderer,
+                                                   UniformSampler)
+    from tests.helpers import load_config1
+
+    meta, p, r, ref = load_config1()
+    cam = scene.PinholeCamera(c2w=torch.eye(4)[:3], fx=64.0, fy=64.0, cx=32.0, cy=32.0, width=64, height=64, time=0.0,
+                              velocity=None, rolling_shutter_time=0.0, time_to_center_pixel=0.0)
+    rays = backend.raygen_pinhole(cam)
+    assert (rays["origins"].cpu() - r["origins"]).abs().max().item() == 0.0
+    assert (rays["directions"].cpu() - r["directions"]).abs().max().item() < 2e-7
+    rb = RayBundle(origins=rays["origins"], directions=rays["directions"], pixel_area=rays["pixel_area"],
+                   nears=r["nears"].cuda(), fars=r["fars"].cuda())
+    enc = HashEncoding(num_levels=16, min_res=16, max_res=1024, log2_hashmap_size=meta["log2_hashmap_size"], features_per_level=2)
+    assert torch.equal(enc.scalings, p["scalings"])
+    enc.hash_table.data = p["hash_table"]
+    mlp = MLP(in_dim=32, num_layers=2, layer_width=64, out_dim=4)
+    mlp.load_state_dict({"layers.0.weight": p["w0"], "layers.0.bias": p["b0"], "layers.1.weight": p["w1"], "layers.1.bias": p["b1"]})
+    enc, mlp = enc.cuda(), mlp.cuda()
+    rs = UniformSampler(num_samples=32)(rb)
+    assert (rs.frustums.bin_edges.cpu() - ref["bins_e"]).abs().max().item() < 1e-6
+    assert torch.equal(rs.spacing_bins.cpu(), torch.linspace(0.0, 1.0, 33))
+    pos = rs.frustums.get_positions(normalize_aabb=p["aabb"])
+    assert (pos[::8].cpu() - ref["positions_sub"]).abs().max().item() < 1e-6
+    feat = enc(pos.view(-1, 3))
+    assert rel_to_max(feat.view(4096, 32, 32)[::8], ref["encoding_sub"]) < 1e-4
+    raw = mlp(feat).view(4096, 32, 4)
+    backend.check_status()
+    assert rel_to_max(raw[::8], ref["raw_sub"]) < 1e-4
+    density, rgb_s = backend.density_rgb_heads(raw)
+    assert rel_to_max(density[::8], ref["density_sub"]) < 1e-4 and rel_to_max(rgb_s[::8], ref["rgb_samples_sub"]) < 1e-4
+    w = rs.get_weights(density)
+    assert rel_to_max(w[::8], ref["weights_sub"]) < 1e-4
+    out = {"rgb": RGBRenderer("black")(rgb_s, w), "depth": DepthRenderer("expected")(w, rs),
+           "depth_median": DepthRenderer("median")(w, rs), "accumulation": AccumulationRenderer()(w)}
+    for k, v in out.items():
+        assert v.shape == ref[k].shape, k
+        assert rel_to_max(v, ref[k]) < 1e-4, (k, rel_to_max(v, ref[k]))
+    # the median picks a sample index: it has to be the reference's index for every ray
+    assert torch.equal(out["depth_median"].cpu(), ref["depth_median"]) or rel_to_max(out["depth_median"], ref["depth_median"]) < 1e-6
+
+
+@pytest.mark.parametrize("spacing,kind", [("uniform", 0), ("lindisp", 1), ("power", 2), ("sqrt", 3), ("log", 4)])
+def test_spaced_samplers_match_oracle(backend, spacing, kind):
+    from oracle import simple_oracle as S
+
+    gen = torch.Generator().manual_seed(kind)
+    n = 1000
+    nears = torch.rand(n, 1, generator=gen) * 2 + 0.05
+    fars = nears + torch.rand(n, 1, generator=gen) * 100 + 1.0
+    for s in (1, 32, 48, 128):
+        bs_ref, be_ref = S.spaced_sample(nears, fars, s, kind, -1.0, 0.1)
+        bs, be = backend.spaced_sample(nears, fars, s, spacing, -1.0, 0.1)
+        assert torch.equal(bs.cpu(), bs_ref[0])
+        assert rel_to_max(be, be_ref) < (1e-6 if kind < 4 else 1e-5), (spacing, s)
+        if kind in (0, 1, 3):  # only IEEE +,-,*,/,sqrt: bit-exact
+            assert torch.equal(be.cpu(), be_ref)
+    lam_ref = S.spaced_sample(nears, fars, 16, S.SPACING_POWER, -1.7, 0.25)[1]
+    assert rel_to_max(backend.spaced_sample(nears, fars, 16, "power", -1.7, 0.25)[1], lam_ref) < 1e-5
+    assert backend.spaced_sample(None, fars, 4)[1][:, 0].abs().max().item() == 0.0  # nears default to 0
+    assert backend.spaced_sample(nears[:0], fars[:0], 4)[1].shape == (0, 5)
+
+
+@pytest.mark.parametrize("n_samples,n_channels", [(32, 3), (40, 48), (7, 1), (100, 9)])
+def test_composite_matches_oracle(backend, n_samples, n_channels):
+    from oracle import simple_oracle as S
+
+    gen = torch.Generator().manual_seed(n_samples * 100 + n_channels)
+    n = 777
+    dens = torch.rand(n, n_samples, generator=gen) * 3
+    edges = torch.cumsum(torch.rand(n, n_samples + 1, generator=gen) * 0.3 + 0.01, -1)
+    starts, ends = edges[:, :-1, None], edges[:, 1:, None]
+    w = O.weights_from_density((ends - starts)[..., 0], dens)[..., None]
+    vals = torch.randn(n, n_samples, n_channels, generator=gen)
+    vals[3, 2, 0] = float("nan")
+    vals[5, 1, -1] = float("inf")
+    bg = [0.25 * (i % 4) for i in range(n_channels)]
+    ref_rgb = S.rgb_render(vals, w, torch.tensor(bg))
+    out = backend.composite(w, vals, starts, ends, "expected", background=bg, value_nan_to_num=True)
+    assert rel_to_max(out["values"], ref_rgb) < 1e-5
+    assert rel_to_max(out["accumulation"], w.sum(-2)) < 1e-6
+    assert rel_to_max(out["depth"], S.depth_expected(w, starts, ends)) < 1e-5
+    good = torch.nan_to_num(vals)
+    feat = backend.composite(w, good, want_accumulation=False)
+    assert set(feat) == {"values"} and rel_to_max(feat["values"], (w * good).sum(-2)) < 1e-5
+    med = backend.composite(w, None, starts, ends, "median", want_accumulation=False)["depth"]
+    ref_med = S.depth_median(w, starts, ends)
+    assert (med.cpu() != ref_med).float().mean().item() < 0.005  # same sample index (ties at the 0.5 crossing aside)
+    simple = backend.composite(w, None, starts, ends, "simple")["depth"]
+    assert rel_to_max(simple, (w * (starts + ends) / 2).sum(-2)) < 1e-5
+    # the "expected" clip is global over the batch: one heavy ray in a second call must not leak into the first
+    lo = backend.composite(w[:5], None, starts[:5] * 0 + 1.0, ends[:5] * 0 + 1.0, "expected")["depth"]
+    assert (lo - 1.0).abs().max().item() < 1e-6
+    assert backend.composite(w[:0], vals[:0])["values"].shape == (0, n_channels)
