@@ -402,7 +402,7 @@ def main():
                      "ms_per_step": ms_e2e / args.steps, "host_buffers_verified": bool(e2e_ok),
                      "how": "host descriptors -> ray generation -> fused render; the render epilogue stores every finished row into pinned host memory (device-mapped) while rendering"},
                 roofline={"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                          "traffic": None, "kernel": "nff_render_lane_kernel", "kernel_ms": kern_ms, "peak_source": peak_src,
+                          "traffic": None, "kernel": "nff_sample_lane_kernel + nff_shade_lane_kernel (one render)", "kernel_ms": kern_ms, "peak_source": peak_src,
                           "algorithmic_bytes_per_ray": ALGO_BYTES_PER_RAY})
     traffic_file = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(traffic_file):
