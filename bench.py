@@ -162,7 +162,7 @@ class Step:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
         self.be.render(rays, out=out, image_width=640)
-        self.launches += 1
+        self.launches += 2  # nff_sample_lane_kernel + nff_shade_lane_kernel
         if time_kernel:
             e1.record()
             self.kernel_events.append((e0, e1))
@@ -193,7 +193,7 @@ class Step:
         out.update(self.local)
         self.be.set_peer_outputs(self._e2e_peers, self_rank=self._e2e_self, row_offset=self._e2e_row_offset)
         self.be.render(rays, out=out, image_width=640)
-        self.launches += 1
+        self.launches += 2  # nff_sample_lane_kernel + nff_shade_lane_kernel
         self._finish_gather()
         torch.cuda.current_stream(dev).synchronize()
         if self.p2p:

@@ -263,6 +263,52 @@ int b200nerf_composite(b200nerf_ctx* ctx, const float* weights, const float* val
                        int depth_method, int64_t n_rays, int n_samples, float* out_values, float* out_accumulation,
                        float* out_depth, void* stream);
 
+/* ---- camera rgb decoder ------------------------------------------------------------ */
+
+/* NeuRADModel.rgb_decoder (models/neurad.py:201-216; BasicBlock model_components/cnns.py:19-46), eval mode:
+ *   rgb_decoder.0  Conv2d(in_dim -> 32, 1x1) + ReLU        in_conv   weight [32,in_dim,1,1], bias [32]
+ *   rgb_decoder.2, .3, .5, .6  BasicBlock(32, 7x7, BN)      block[b][k]: main_branch.{0|3} Conv2d [32,32,7,7] + bias
+ *                                                           and main_branch.{1|4} BatchNorm2d weight/bias/running_*
+ *   rgb_decoder.4  ConvTranspose2d(32 -> 32, k = s = 3)     up_conv   weight [32,32,3,3], bias [32]
+ *   rgb_decoder.7  Conv2d(32 -> 3, 1x1) (+ Sigmoid)         out_conv  weight [3,32,1,1], bias [3]
+ * All pointers are DEVICE fp32 tensors in the reference's state_dict layout.  The library folds the BatchNorms into
+ * the convolutions and keeps its own re-laid-out copy: call again after the parameters change. */
+typedef struct {
+  const float* weight;
+  const float* bias;
+} b200nerf_conv_params;
+typedef struct {
+  const float* conv_weight;
+  const float* conv_bias;
+  const float* bn_weight;
+  const float* bn_bias;
+  const float* bn_running_mean;
+  const float* bn_running_var;
+} b200nerf_conv_bn_params;
+typedef struct {
+  int32_t in_dim;     /* nff_out_dim + appearance_dim (48), <= 64 */
+  int32_t hidden_dim; /* rgb_hidden_dim, must be 32 */
+  int32_t upsample;   /* rgb_upsample_factor, must be 3 */
+  float bn_eps;       /* BatchNorm2d.eps (1e-5) */
+  b200nerf_conv_params in_conv;
+  b200nerf_conv_bn_params block[4][2];
+  b200nerf_conv_params up_conv;
+  b200nerf_conv_params out_conv;
+} b200nerf_rgb_decoder_params;
+int b200nerf_set_rgb_decoder(b200nerf_ctx* ctx, const b200nerf_rgb_decoder_params* params);
+
+/* Scratch the decoder needs for `batch` feature images of height x width (intermediate activations: 3 buffers at
+ * feature resolution + 3 at image resolution, 128 B per pixel).  The caller allocates it (16-byte aligned). */
+int64_t b200nerf_rgb_decode_workspace_bytes(int batch, int height, int width);
+
+/* The camera half of NeuRADModel.decode_features (models/neurad.py:359-366): features [batch, height, width, in_dim]
+ * (= the row-major ray order of b200nerf_nff_render_fwd's `features` output, so no permute is needed) ->
+ * rgb [batch, 3*height, 3*width, 3].  impl 0: the 7x7 convolutions run as implicit GEMMs on the tcgen05 tensor cores
+ * (bf16 hi/lo split, fp32 accumulate, fp32-level accuracy); impl 1: the same pipeline on the CUDA cores in fp32
+ * (slow cross-check of the same op). */
+int b200nerf_rgb_decode_fwd(b200nerf_ctx* ctx, const float* features, int batch, int height, int width, float* rgb,
+                            void* workspace, int64_t workspace_bytes, int impl, void* stream);
+
 /* ---- ray generation ------------------------------------------------------------------------------------- */
 
 /* Cameras.generate_rays for one PERSPECTIVE camera without distortion, top-to-bottom rolling shutter

@@ -11,7 +11,7 @@ import torch
 
 from . import lib as _lib
 from .config import HashGridSettings, NeuRADConfig
-from .lib import FIELD_MAIN, FIELD_PROP0, FIELD_PROP1, GridDesc, Outputs, PeerOutputs, Rays, Trace, TRACE_FIELDS
+from .lib import ConvBnParams, ConvParams, RgbDecoderParams, FIELD_MAIN, FIELD_PROP0, FIELD_PROP1, GridDesc, Outputs, PeerOutputs, Rays, Trace, TRACE_FIELDS
 
 
 def pdf_quantiles(num_samples: int) -> torch.Tensor:
@@ -385,6 +385,51 @@ class B200Backend:
         self._check(self.lib.b200nerf_composite(self._h, _ptr(w), _ptr(v), c, int(value_nan_to_num), bg, _ptr(st), _ptr(en),
                                                 self.DEPTH_METHODS[depth_method], n, s, _ptr(ov), _ptr(oa), _ptr(od), self._stream))
         return out
+
+    # ------------------------------------------------------------------------------------- camera rgb decoder
+    def set_rgb_decoder(self, sd: Dict[str, torch.Tensor], prefix: str = "rgb_decoder", bn_eps: float = 1e-5) -> None:
+        """Bind NeuRADModel.rgb_decoder (models/neurad.py:201-216) from a reference state dict: keys
+        `{prefix}.0.weight`, `{prefix}.2.main_branch.0.weight`, `{prefix}.2.main_branch.1.running_mean`, ...
+        BatchNorms are folded into the 7x7 convolutions inside the library (eval-mode semantics)."""
+        keep = []
+        pre = prefix + "." if prefix else ""
+
+        def t(key):
+            v = self._dev(sd[pre + key])
+            keep.append(v)
+            return v.data_ptr()
+
+        p = RgbDecoderParams()
+        w0 = sd[pre + "0.weight"]
+        p.in_dim, p.hidden_dim, p.upsample, p.bn_eps = w0.shape[1], w0.shape[0], sd[pre + "4.weight"].shape[-1], bn_eps
+        p.in_conv = ConvParams(t("0.weight"), t("0.bias"))
+        for b, blk in enumerate((2, 3, 5, 6)):
+            for k, (cv, bn) in enumerate(((0, 1), (3, 4))):
+                m = f"{blk}.main_branch"
+                p.block[b][k] = ConvBnParams(t(f"{m}.{cv}.weight"), t(f"{m}.{cv}.bias"), t(f"{m}.{bn}.weight"), t(f"{m}.{bn}.bias"),
+                                             t(f"{m}.{bn}.running_mean"), t(f"{m}.{bn}.running_var"))
+        p.up_conv = ConvParams(t("4.weight"), t("4.bias"))
+        p.out_conv = ConvParams(t("7.weight"), t("7.bias"))
+        self._check(self.lib.b200nerf_set_rgb_decoder(self._h, ctypes.byref(p)))  # synchronous: `keep` may go now
+        self._dec_in_dim = int(w0.shape[1])
+
+    def rgb_decode(self, features: torch.Tensor, impl: str = "tc") -> torch.Tensor:
+        """Camera half of NeuRADModel.decode_features (neurad.py:359-366): features [B,H,W,C] (or [H,W,C]) ->
+        rgb [B,3H,3W,3].  impl "tc": tcgen05 implicit-GEMM convolutions; "ref": CUDA-core fp32 cross-check."""
+        f = self._dev(features)
+        if f.dim() == 3:
+            f = f[None]
+        b, h, w, c = f.shape
+        if c != getattr(self, "_dec_in_dim", None):
+            raise _lib.B200NerfError(f"feature width {c} does not match the bound rgb decoder")
+        need = int(self.lib.b200nerf_rgb_decode_workspace_bytes(b, h, w))
+        ws = getattr(self, "_dec_ws", None)
+        if ws is None or ws.numel() < need:
+            ws = self._dec_ws = torch.empty(max(need, 16), dtype=torch.uint8, device=self.device)
+        rgb = torch.empty(b, 3 * h, 3 * w, 3, device=self.device)
+        self._check(self.lib.b200nerf_rgb_decode_fwd(self._h, _ptr(f), b, h, w, _ptr(rgb), _ptr(ws), ws.numel(),
+                                                     {"tc": 0, "ref": 1}[impl], self._stream))
+        return rgb
 
     # ------------------------------------------------------------------------------------------- ray generation
     def _ray_buffers(self, n: int, out: Optional[Dict[str, torch.Tensor]]):

@@ -96,6 +96,7 @@ class NeuRADConfig:
     appearance_dim: int = 16
     temporal_appearance_freq: float = 1.0
     rgb_upsample_factor: int = 3
+    rgb_hidden_dim: int = 32
     actor_bbox_padding: Tuple[float, float, float] = (0.25, 0.25, 0.1)
     # scene-level constants (dataset metadata in the reference)
     static_scale: float = 100.0

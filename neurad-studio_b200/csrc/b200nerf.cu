@@ -10,6 +10,7 @@
 #include "../../include/b200nerf.h"
 #include "nff_device.h"
 #include "nff_lane.h"
+#include "rgb_decoder.cuh"
 
 using namespace nff;
 
@@ -60,6 +61,13 @@ struct b200nerf_ctx {
   float *d_u1 = nullptr, *d_u2 = nullptr;
   int* d_status = nullptr;
   int n_prop0 = 0, n_prop1 = 0, n_nerf = 0;
+  // NeuRADModel.rgb_decoder (rgb_decoder.cuh): folded / re-laid-out parameters owned by the context
+  bool have_rgb_decoder = false;
+  int dec_in_dim = 0;
+  unsigned char* d_dec_wimg[8] = {};  // [49][hi|lo] bf16 UMMA B tiles per 7x7 conv
+  float* d_dec_wf32[8] = {};          // [49][ci][co] fp32 (CUDA-core reference kernel)
+  float* d_dec_bias = nullptr;        // [8][32] folded conv + BN biases
+  float* d_dec_small = nullptr;       // in conv w [32*in] b [32] | convT w [32*32*9] b [32] | out conv w [3*32] b [3]
 };
 
 namespace {
@@ -918,6 +926,12 @@ int b200nerf_destroy(b200nerf_ctx* c) {
   cudaFree(c->d_u1);
   cudaFree(c->d_u2);
   cudaFree(c->d_status);
+  for (int i = 0; i < 8; ++i) {
+    cudaFree(c->d_dec_wimg[i]);
+    cudaFree(c->d_dec_wf32[i]);
+  }
+  cudaFree(c->d_dec_bias);
+  cudaFree(c->d_dec_small);
   delete c;
   return 0;
 }
@@ -1339,6 +1353,138 @@ int b200nerf_composite(b200nerf_ctx* c, const float* weights, const float* value
     depth_clip_kernel<<<(unsigned)((n_rays + 255) / 256), 256, 0, st>>>(out_depth, n_rays, c->d_minmax);
     CUDA_TRY(cudaGetLastError());
   }
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------- rgb decoder (f1)
+namespace {
+constexpr int kDecMaxIn = 64;
+inline int64_t dec_small_floats() { return dec::kC * kDecMaxIn + dec::kC + dec::kC * dec::kC * 9 + dec::kC + 3 * dec::kC + 4; }
+struct DecSmall {
+  float *in_w, *in_b, *up_w, *up_b, *out_w, *out_b;
+};
+inline DecSmall dec_small(float* base) {
+  DecSmall d;
+  d.in_w = base;
+  d.in_b = d.in_w + dec::kC * kDecMaxIn;
+  d.up_w = d.in_b + dec::kC;
+  d.up_b = d.up_w + dec::kC * dec::kC * 9;
+  d.out_w = d.up_b + dec::kC;
+  d.out_b = d.out_w + 3 * dec::kC;
+  return d;
+}
+inline int64_t act_bytes(int64_t pixels) { return pixels * 128; }
+}  // namespace
+
+int b200nerf_set_rgb_decoder(b200nerf_ctx* c, const b200nerf_rgb_decoder_params* p) {
+  REQUIRE(c && p, "NULL argument");
+  REQUIRE(p->hidden_dim == dec::kC, "rgb_hidden_dim must be 32");
+  REQUIRE(p->upsample == dec::kUp, "rgb_upsample_factor must be 3");
+  REQUIRE(p->in_dim >= 1 && p->in_dim <= kDecMaxIn, "decoder in_dim must be in [1, 64]");
+  REQUIRE(p->bn_eps > 0.f, "bn_eps must be positive");
+  REQUIRE(p->in_conv.weight && p->in_conv.bias && p->up_conv.weight && p->up_conv.bias && p->out_conv.weight && p->out_conv.bias,
+          "NULL decoder tensor");
+  DeviceGuard g(c->device);
+  if (!c->d_dec_bias) {
+    for (int i = 0; i < 8; ++i) {
+      CUDA_TRY(cudaMalloc((void**)&c->d_dec_wimg[i], (size_t)dec::kK7 * dec::kWRowBytes));
+      CUDA_TRY(cudaMalloc((void**)&c->d_dec_wf32[i], sizeof(float) * dec::kTaps * dec::kC * dec::kC));
+    }
+    CUDA_TRY(cudaMalloc((void**)&c->d_dec_bias, sizeof(float) * 8 * dec::kC));
+    CUDA_TRY(cudaMalloc((void**)&c->d_dec_small, sizeof(float) * dec_small_floats()));
+    CUDA_TRY(cudaFuncSetAttribute(dec::dec_conv7_tc_kernel<dec::EPI_RELU>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(dec::ConvSmem)));
+    CUDA_TRY(cudaFuncSetAttribute(dec::dec_conv7_tc_kernel<dec::EPI_RES_RELU>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(dec::ConvSmem)));
+    CUDA_TRY(cudaFuncSetAttribute(dec::dec_conv7_tc_kernel<dec::EPI_RES_RELU_RGB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(dec::ConvSmem)));
+  }
+  for (int b = 0; b < 4; ++b)
+    for (int k = 0; k < 2; ++k) {
+      const b200nerf_conv_bn_params& q = p->block[b][k];
+      REQUIRE(q.conv_weight && q.conv_bias && q.bn_weight && q.bn_bias && q.bn_running_mean && q.bn_running_var, "NULL BasicBlock tensor");
+      const int i = 2 * b + k, n = dec::kTaps * dec::kC * dec::kC;
+      dec::dec_fold_conv_kernel<<<(n + 255) / 256, 256>>>(q.conv_weight, q.conv_bias, q.bn_weight, q.bn_bias, q.bn_running_mean,
+                                                          q.bn_running_var, p->bn_eps, c->d_dec_wimg[i], c->d_dec_wf32[i],
+                                                          c->d_dec_bias + i * dec::kC);
+      CUDA_TRY(cudaGetLastError());
+    }
+  const DecSmall d = dec_small(c->d_dec_small);
+  CUDA_TRY(cudaMemcpy(d.in_w, p->in_conv.weight, sizeof(float) * dec::kC * p->in_dim, cudaMemcpyDeviceToDevice));
+  CUDA_TRY(cudaMemcpy(d.in_b, p->in_conv.bias, sizeof(float) * dec::kC, cudaMemcpyDeviceToDevice));
+  CUDA_TRY(cudaMemcpy(d.up_w, p->up_conv.weight, sizeof(float) * dec::kC * dec::kC * 9, cudaMemcpyDeviceToDevice));
+  CUDA_TRY(cudaMemcpy(d.up_b, p->up_conv.bias, sizeof(float) * dec::kC, cudaMemcpyDeviceToDevice));
+  CUDA_TRY(cudaMemcpy(d.out_w, p->out_conv.weight, sizeof(float) * 3 * dec::kC, cudaMemcpyDeviceToDevice));
+  CUDA_TRY(cudaMemcpy(d.out_b, p->out_conv.bias, sizeof(float) * 3, cudaMemcpyDeviceToDevice));
+  CUDA_TRY(cudaDeviceSynchronize());
+  c->dec_in_dim = p->in_dim;
+  c->have_rgb_decoder = true;
+  return 0;
+}
+
+int64_t b200nerf_rgb_decode_workspace_bytes(int batch, int height, int width) {
+  if (batch <= 0 || height <= 0 || width <= 0) return 0;
+  const int64_t lo = (int64_t)batch * height * width;
+  return 3 * act_bytes(lo) + 3 * act_bytes(lo * dec::kUp * dec::kUp);
+}
+
+int b200nerf_rgb_decode_fwd(b200nerf_ctx* c, const float* features, int batch, int height, int width, float* rgb,
+                            void* workspace, int64_t workspace_bytes, int impl, void* stream) {
+  REQUIRE(c, "ctx is NULL");
+  REQUIRE(batch >= 0 && height >= 0 && width >= 0, "negative image shape");
+  REQUIRE(impl == 0 || impl == 1, "impl: 0 = tcgen05 (bf16x3), 1 = CUDA-core fp32 cross-check");
+  if (!c->have_rgb_decoder) return fail(B200NERF_ERR_STATE, "set_rgb_decoder was not called");
+  if (batch == 0 || height == 0 || width == 0) return 0;
+  REQUIRE(features && rgb && workspace, "NULL argument");
+  REQUIRE(workspace_bytes >= b200nerf_rgb_decode_workspace_bytes(batch, height, width), "workspace too small (see b200nerf_rgb_decode_workspace_bytes)");
+  REQUIRE(((uintptr_t)workspace & 15) == 0, "workspace must be 16-byte aligned");
+  DeviceGuard g(c->device);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t lo_px = (int64_t)batch * height * width, hi_px = lo_px * dec::kUp * dec::kUp;
+  unsigned char* ws = (unsigned char*)workspace;
+  uint4* lo[3];
+  uint4* hi[3];
+  for (int i = 0; i < 3; ++i) lo[i] = (uint4*)(ws + i * act_bytes(lo_px));
+  for (int i = 0; i < 3; ++i) hi[i] = (uint4*)(ws + 3 * act_bytes(lo_px) + i * act_bytes(hi_px));
+  const DecSmall d = dec_small(c->d_dec_small);
+  dec::dec_input_kernel<<<(unsigned)((lo_px + 127) / 128), 128, sizeof(float) * (c->dec_in_dim * dec::kC + dec::kC), st>>>(
+      features, lo_px, c->dec_in_dim, d.in_w, d.in_b, lo[0]);
+  CUDA_TRY(cudaGetLastError());
+  auto conv = [&](int layer, int epi, const uint4* in, const uint4* res, uint4* out, float* out_rgb, int H, int W) -> int {
+    dec::ConvArgs a{};
+    a.in = in; a.residual = res; a.out_act = out; a.out_rgb = out_rgb;
+    a.w_img = c->d_dec_wimg[layer]; a.w_f32 = c->d_dec_wf32[layer]; a.bias = c->d_dec_bias + layer * dec::kC;
+    a.out_w = d.out_w; a.out_b = d.out_b;
+    a.batch = batch; a.H = H; a.W = W; a.status = c->d_status;
+    if (impl == 0) {
+      const int64_t tiles = (int64_t)batch * ((H + dec::kTH - 1) / dec::kTH) * ((W + dec::kStrip - 1) / dec::kStrip);
+      const int grid = (int)(tiles < c->sm_count ? tiles : c->sm_count);
+      const size_t smem = sizeof(dec::ConvSmem);
+      if (epi == dec::EPI_RELU) dec::dec_conv7_tc_kernel<dec::EPI_RELU><<<grid, dec::kConvThreads, smem, st>>>(a);
+      else if (epi == dec::EPI_RES_RELU) dec::dec_conv7_tc_kernel<dec::EPI_RES_RELU><<<grid, dec::kConvThreads, smem, st>>>(a);
+      else dec::dec_conv7_tc_kernel<dec::EPI_RES_RELU_RGB><<<grid, dec::kConvThreads, smem, st>>>(a);
+    } else {
+      const unsigned grid = (unsigned)((int64_t)batch * H * ((W + 127) / 128));
+      if (epi == dec::EPI_RELU) dec::dec_conv7_ref_kernel<dec::EPI_RELU><<<grid, 128, 0, st>>>(a);
+      else if (epi == dec::EPI_RES_RELU) dec::dec_conv7_ref_kernel<dec::EPI_RES_RELU><<<grid, 128, 0, st>>>(a);
+      else dec::dec_conv7_ref_kernel<dec::EPI_RES_RELU_RGB><<<grid, 128, 0, st>>>(a);
+    }
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(B200NERF_ERR_CUDA, cudaGetErrorString(e));
+    return 0;
+  };
+  const int H = height, W = width, HO = height * dec::kUp, WO = width * dec::kUp;
+  // rgb_decoder.2, .3: BasicBlocks at feature resolution
+  if (int e = conv(0, dec::EPI_RELU, lo[0], nullptr, lo[1], nullptr, H, W)) return e;
+  if (int e = conv(1, dec::EPI_RES_RELU, lo[1], lo[0], lo[2], nullptr, H, W)) return e;
+  if (int e = conv(2, dec::EPI_RELU, lo[2], nullptr, lo[1], nullptr, H, W)) return e;
+  if (int e = conv(3, dec::EPI_RES_RELU, lo[1], lo[2], lo[0], nullptr, H, W)) return e;
+  // rgb_decoder.4: 3x transposed conv
+  dec::dec_upsample_kernel<<<(unsigned)((hi_px + 127) / 128), 128, sizeof(float) * (9 * dec::kC * dec::kC + dec::kC), st>>>(
+      lo[0], batch, H, W, d.up_w, d.up_b, hi[0]);
+  CUDA_TRY(cudaGetLastError());
+  // rgb_decoder.5, .6 at image resolution; .7/.8 (1x1 conv + sigmoid) in the last epilogue
+  if (int e = conv(4, dec::EPI_RELU, hi[0], nullptr, hi[1], nullptr, HO, WO)) return e;
+  if (int e = conv(5, dec::EPI_RES_RELU, hi[1], hi[0], hi[2], nullptr, HO, WO)) return e;
+  if (int e = conv(6, dec::EPI_RELU, hi[2], nullptr, hi[1], nullptr, HO, WO)) return e;
+  if (int e = conv(7, dec::EPI_RES_RELU_RGB, hi[1], hi[2], nullptr, rgb, HO, WO)) return e;
   return 0;
 }
 

@@ -1,0 +1,386 @@
+// rgb_decoder.cuh -- NeuRADModel.rgb_decoder (models/neurad.py:201-216, model_components/cnns.py:19-46) in eval mode:
+//   Conv2d(in->32, 1x1) + ReLU -> 2 x BasicBlock(32, 7x7, BN) -> ConvTranspose2d(32->32, k = s = 3) -> 2 x BasicBlock
+//   -> Conv2d(32->3, 1x1) -> Sigmoid,            feature image [B,H,W,in] (row-major rays) -> rgb [B,3H,3W,3].
+//
+// 97 % of the work is the eight 7x7 convolutions (50 176 MAC per pixel each).  They run as implicit GEMMs on the
+// tcgen05 tensor cores: M = 128 consecutive pixels of one image row, N = 32 output channels, K = 49 taps x 32 input
+// channels, fp32 accumulators in TMEM.  BatchNorm is folded into the conv weights/bias when the parameters are set.
+//
+// fp32-level accuracy from bf16 tensor-core inputs: every activation and weight is split into two bf16 numbers
+// (hi = bf16(v), lo = bf16(v - hi)) and each k-step issues three MMAs  a_hi*w_hi + a_lo*w_hi + a_hi*w_lo  into the
+// same accumulator; the dropped a_lo*w_lo term is ~2^-18 relative.  This costs 1.5x the tensor time of a single TF32
+// pass (bf16 runs at twice the TF32 rate) and needs exactly the bytes of fp32 storage.
+//
+// Activations between layers therefore live in HBM already split ("ACT" layout): per pixel 128 B = 8 chunks of 8 bf16,
+// chunk c < 4: hi of channels 8c..8c+7, chunk 4+c: lo.  A conv CTA copies a (3+6) x (128+6) pixel window of it into
+// shared memory as 8 planes [chunk][row][pixel][16 B]; in that layout the A operand of tap (dy,dx) for output row r is
+// the SAME planes read from a shifted start address ((r+dy)*PW + dx)*16 B -- the canonical K-major no-swizzle UMMA
+// layout with SBO = 128 B (8-pixel groups are contiguous) and LBO = the plane stride -- so the im2col matrix is never
+// materialised.  The folded weights of one tap row (7 taps x {hi,lo} x 32x32 bf16 = 28 KB, pre-arranged in the UMMA B
+// layout by dec_fold_conv_kernel) are double-buffered in shared memory and streamed from L2 while the tensor core works
+// on the previous tap row.
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "tc_mlp.cuh"
+
+namespace dec {
+
+constexpr int kC = 32;           // hidden channels (rgb_hidden_dim)
+constexpr int kUp = 3;           // rgb_upsample_factor
+constexpr int kK7 = 7, kPad = 3; // BasicBlock kernel_size / padding
+constexpr int kTaps = kK7 * kK7;
+constexpr int kStrip = 128;      // pixels per MMA (M)
+constexpr int kPW = kStrip + 2 * kPad;
+constexpr int kTH = 3;           // output rows per tile
+constexpr int kIR = kTH + 2 * kPad;
+constexpr int kPlaneBytes = kIR * kPW * 16 + 16;  // +16: consecutive planes start 4 banks apart (conflict-free fills)
+constexpr int kActBytes = 8 * kPlaneBytes;
+constexpr int kWTileBytes = kC * kC * 2;                 // one 32x32 bf16 B tile
+constexpr int kWRowBytes = kK7 * 2 * kWTileBytes;        // one tap row: 7 taps x {hi, lo}
+constexpr int kConvThreads = 256;
+constexpr int kTmemCols = 128;                           // kTH accumulators x 32 columns, power of two
+static_assert(kTH * kC <= kTmemCols, "accumulators do not fit the TMEM allocation");
+
+struct ConvSmem {
+  alignas(128) unsigned char act[kActBytes];
+  alignas(128) unsigned char w[2][kWRowBytes];
+  float bias[kC];
+  float out_w[3 * kC];
+  float out_b[4];
+  alignas(8) uint64_t bar[2];
+  uint32_t tmem_base;
+};
+
+// ------------------------------------------------------------------------------------------------ bf16 split
+__device__ __forceinline__ void split_bf16(float v, __nv_bfloat16& hi, __nv_bfloat16& lo) {
+  hi = __float2bfloat16_rn(v);
+  lo = __float2bfloat16_rn(v - __bfloat162float(hi));
+}
+// 32 channels of one pixel -> ACT (8 x uint4)
+__device__ __forceinline__ void store_act(uint4* dst, const float* v) {
+  __align__(16) __nv_bfloat16 hi[kC], lo[kC];
+#pragma unroll
+  for (int k = 0; k < kC; ++k) split_bf16(v[k], hi[k], lo[k]);
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    dst[c] = *reinterpret_cast<const uint4*>(&hi[8 * c]);
+    dst[4 + c] = *reinterpret_cast<const uint4*>(&lo[8 * c]);
+  }
+}
+__device__ __forceinline__ void load_act(const uint4* src, float* v) {
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    const uint4 h = src[c], l = src[4 + c];
+    const __nv_bfloat16* hb = reinterpret_cast<const __nv_bfloat16*>(&h);
+    const __nv_bfloat16* lb = reinterpret_cast<const __nv_bfloat16*>(&l);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v[8 * c + k] = __bfloat162float(hb[k]) + __bfloat162float(lb[k]);
+  }
+}
+
+// ---------------------------------------------------------------------------------------- parameter preparation
+// Conv2d [co][ci][7][7] + BatchNorm2d (eval) -> folded  w' = w * s[co],  b' = (b - mean) * s + beta,  s = gamma /
+// sqrt(var + eps)  (BasicBlock.main_branch, cnns.py:37-43), written as
+//   w_img : [dy][dx][hi|lo] 32x32 bf16 tiles in the UMMA K-major no-swizzle B layout (n = co, k = ci):
+//           byte offset of (n,k) = (n/8)*512 + (k/8)*128 + (n%8)*16 + (k%8)*2
+//   w_f32 : [dy][dx][ci][co] fp32 (CUDA-core reference kernel)
+//   bias  : [co]
+__global__ void dec_fold_conv_kernel(const float* __restrict__ w, const float* __restrict__ b, const float* __restrict__ gamma,
+                                     const float* __restrict__ beta, const float* __restrict__ mean, const float* __restrict__ var,
+                                     float eps, unsigned char* __restrict__ w_img, float* __restrict__ w_f32, float* __restrict__ bias) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < kC) {
+    const float s = gamma[i] / sqrtf(var[i] + eps);
+    bias[i] = (b[i] - mean[i]) * s + beta[i];
+  }
+  if (i >= kTaps * kC * kC) return;
+  const int co = i / (kC * kTaps), ci = (i / kTaps) % kC, tap = i % kTaps;  // i = flat index of w[co][ci][dy][dx]
+  const float s = gamma[co] / sqrtf(var[co] + eps);
+  const float v = w[i] * s;
+  w_f32[(tap * kC + ci) * kC + co] = v;
+  __nv_bfloat16 hi, lo;
+  split_bf16(v, hi, lo);
+  const int off = (co >> 3) * 512 + (ci >> 3) * 128 + (co & 7) * 16 + (ci & 7) * 2;
+  unsigned char* tile = w_img + (size_t)tap * 2 * kWTileBytes;
+  *reinterpret_cast<__nv_bfloat16*>(tile + off) = hi;
+  *reinterpret_cast<__nv_bfloat16*>(tile + kWTileBytes + off) = lo;
+}
+
+// ------------------------------------------------------------------------------------- 1x1 input conv + ReLU
+// rgb_decoder.0/.1: features fp32 [P, in_dim] -> ACT [P]; w [32][in_dim], b [32] (Conv2d 1x1 layout)
+__global__ void dec_input_kernel(const float* __restrict__ x, int64_t n_pix, int in_dim, const float* __restrict__ w,
+                                 const float* __restrict__ b, uint4* __restrict__ out) {
+  extern __shared__ float sw[];  // [in_dim][32] transposed + bias
+  for (int i = threadIdx.x; i < in_dim * kC; i += blockDim.x) sw[(i % in_dim) * kC + i / in_dim] = w[i];
+  for (int i = threadIdx.x; i < kC; i += blockDim.x) sw[in_dim * kC + i] = b[i];
+  __syncthreads();
+  const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n_pix) return;
+  float acc[kC];
+#pragma unroll
+  for (int k = 0; k < kC; ++k) acc[k] = sw[in_dim * kC + k];
+  for (int c = 0; c < in_dim; ++c) {
+    const float v = x[p * in_dim + c];
+#pragma unroll
+    for (int k = 0; k < kC; ++k) acc[k] = fmaf(v, sw[c * kC + k], acc[k]);
+  }
+#pragma unroll
+  for (int k = 0; k < kC; ++k) acc[k] = fmaxf(acc[k], 0.f);
+  store_act(out + p * 8, acc);
+}
+
+// --------------------------------------------------------------------------- ConvTranspose2d, kernel = stride = 3
+// rgb_decoder.4: out[3y+i][3x+j][co] = b[co] + sum_ci in[y][x][ci] * w[ci][co][i][j]   (one thread per OUTPUT pixel)
+__global__ void dec_upsample_kernel(const uint4* __restrict__ in, int batch, int H, int W, const float* __restrict__ w,
+                                    const float* __restrict__ b, uint4* __restrict__ out) {
+  extern __shared__ float sw[];  // [i*3+j][ci][co] + bias
+  for (int i = threadIdx.x; i < kC * kC * kUp * kUp; i += blockDim.x) {
+    const int ci = i / (kC * 9), co = (i / 9) % kC, ij = i % 9;
+    sw[(ij * kC + ci) * kC + co] = w[i];
+  }
+  for (int i = threadIdx.x; i < kC; i += blockDim.x) sw[9 * kC * kC + i] = b[i];
+  __syncthreads();
+  const int64_t HO = (int64_t)H * kUp, WO = (int64_t)W * kUp;
+  const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= batch * HO * WO) return;
+  const int64_t img = p / (HO * WO), Y = (p / WO) % HO, X = p % WO;
+  const int ij = (int)(Y % kUp) * kUp + (int)(X % kUp);
+  float v[kC], acc[kC];
+  load_act(in + ((img * H + Y / kUp) * W + X / kUp) * 8, v);
+#pragma unroll
+  for (int k = 0; k < kC; ++k) acc[k] = sw[9 * kC * kC + k];
+  const float* wt = sw + ij * kC * kC;
+#pragma unroll 4
+  for (int c = 0; c < kC; ++c) {
+#pragma unroll
+    for (int k = 0; k < kC; ++k) acc[k] = fmaf(v[c], wt[c * kC + k], acc[k]);
+  }
+  store_act(out + p * 8, acc);
+}
+
+// ------------------------------------------------------------------------------------------------ epilogues
+enum { EPI_RELU = 0, EPI_RES_RELU = 1, EPI_RES_RELU_RGB = 2 };
+// acc = conv + folded bias for one pixel.  EPI_RELU: first conv of a BasicBlock.  EPI_RES_RELU: second conv:
+// relu(x + main_branch(x)) (cnns.py:31-32).  EPI_RES_RELU_RGB: the last block, followed by rgb_decoder.7/.8
+// (Conv2d 32->3 1x1 + Sigmoid) while the pixel is still in registers -> fp32 rgb.
+template <int EPI>
+__device__ __forceinline__ void conv_epilogue(float* acc, const uint4* __restrict__ residual, int64_t pix, uint4* __restrict__ out_act,
+                                              float* __restrict__ out_rgb, const float* out_w, const float* out_b) {
+  if (EPI != EPI_RELU) {
+    float x[kC];
+    load_act(residual + pix * 8, x);
+#pragma unroll
+    for (int k = 0; k < kC; ++k) acc[k] += x[k];
+  }
+#pragma unroll
+  for (int k = 0; k < kC; ++k) acc[k] = fmaxf(acc[k], 0.f);
+  if (EPI == EPI_RES_RELU_RGB) {
+#pragma unroll
+    for (int o = 0; o < 3; ++o) {
+      float s = out_b[o];
+#pragma unroll
+      for (int k = 0; k < kC; ++k) s = fmaf(acc[k], out_w[o * kC + k], s);
+      out_rgb[pix * 3 + o] = 1.0f / (1.0f + expf(-s));
+    }
+  } else {
+    store_act(out_act + pix * 8, acc);
+  }
+}
+
+// ------------------------------------------------------------------------------- 7x7 conv on the tensor cores
+__device__ __forceinline__ uint64_t smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  // cute::UMMA::SmemDescriptor: start>>4 [0,14), LBO>>4 [16,30), SBO>>4 [32,46), version 1 [46,48), SWIZZLE_NONE
+  return (uint64_t)((saddr & 0x3ffffu) >> 4) | ((uint64_t)(lbo_bytes >> 4) << 16) | ((uint64_t)(sbo_bytes >> 4) << 32) | (1ull << 46);
+}
+// cute::UMMA::InstrDescriptor for kind::f16: D = F32 (1<<4), A = B = BF16 (1<<7, 1<<10), both K-major, N>>3, M>>4
+__host__ __device__ constexpr uint32_t idesc_bf16(int m, int n) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+__device__ __forceinline__ void mma_bf16_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+struct ConvArgs {
+  const uint4* in;        // ACT [B][H][W]
+  const uint4* residual;  // ACT (EPI_RES_*) or nullptr
+  uint4* out_act;         // ACT or nullptr
+  float* out_rgb;         // [B][H][W][3] (EPI_RES_RELU_RGB)
+  const unsigned char* w_img;  // [7][kWRowBytes]
+  const float* w_f32;     // [49][ci][co]
+  const float* bias;      // [32] folded
+  const float* out_w;     // [3][32] (EPI_RES_RELU_RGB)
+  const float* out_b;     // [3]
+  int batch, H, W;
+  int* status;
+};
+
+template <int EPI>
+__global__ void __launch_bounds__(kConvThreads, 1) dec_conv7_tc_kernel(const ConvArgs a) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  ConvSmem& S = *reinterpret_cast<ConvSmem*>(smem_raw);
+  const int tid = threadIdx.x, warp = tid >> 5, ln = tid & 31;
+  if (tid < kC) S.bias[tid] = a.bias[tid];
+  if (EPI == EPI_RES_RELU_RGB) {
+    if (tid < 3 * kC) S.out_w[tid] = a.out_w[tid];
+    if (tid < 3) S.out_b[tid] = a.out_b[tid];
+  }
+  if (warp == 0) tc::tmem_alloc(&S.tmem_base, kTmemCols);
+  if (tid == 0) {
+    tc::mbar_init(&S.bar[0], 1);
+    tc::mbar_init(&S.bar[1], 1);
+  }
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+  const uint32_t tmem = S.tmem_base;
+  const uint32_t act_s = tc::smem_u32(S.act);
+  const uint32_t w_s[2] = {tc::smem_u32(S.w[0]), tc::smem_u32(S.w[1])};
+  constexpr uint32_t kIdesc = idesc_bf16(kStrip, kC);
+  uint32_t parity[2] = {0u, 0u};
+  bool ok = true;
+
+  const int tiles_x = (a.W + kStrip - 1) / kStrip, tiles_y = (a.H + kTH - 1) / kTH;
+  const int64_t n_tiles = (int64_t)a.batch * tiles_y * tiles_x;
+  for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const int tx = (int)(tile % tiles_x), ty = (int)((tile / tiles_x) % tiles_y);
+    const int64_t img = tile / ((int64_t)tiles_x * tiles_y);
+    const int x0 = tx * kStrip, y0 = ty * kTH;
+    const uint4* in_img = a.in + img * (int64_t)a.H * a.W * 8;
+    // ---- input window -> 8 chunk planes; pixels outside the image are the conv's zero padding
+    for (int i = tid; i < kIR * kPW * 8; i += kConvThreads) {
+      const int c = i & 7, ip = (i >> 3) % kPW, ir = (i >> 3) / kPW;
+      const int y = y0 - kPad + ir, x = x0 - kPad + ip;
+      uint4 v = make_uint4(0u, 0u, 0u, 0u);
+      if (y >= 0 && y < a.H && x >= 0 && x < a.W) v = in_img[((int64_t)y * a.W + x) * 8 + c];
+      *reinterpret_cast<uint4*>(S.act + c * kPlaneBytes + (ir * kPW + ip) * 16) = v;
+    }
+    {  // tap row 0 of the weights
+      const uint4* src = reinterpret_cast<const uint4*>(a.w_img);
+      uint4* dst = reinterpret_cast<uint4*>(S.w[0]);
+      for (int i = tid; i < kWRowBytes / 16; i += kConvThreads) dst[i] = src[i];
+    }
+    tc::fence_async_smem();  // generic-proxy writes -> visible to the tensor core (async proxy)
+    tc::fence_before_sync();
+    __syncthreads();
+    for (int dy = 0; dy < kK7; ++dy) {
+      const int buf = dy & 1;
+      if (tid == 0) {
+        tc::fence_after_sync();
+        for (int r = 0; r < kTH; ++r) {
+          const uint32_t d = tmem + (uint32_t)(r * kC);
+          for (int dx = 0; dx < kK7; ++dx) {
+            const uint32_t a_off = (uint32_t)(((r + dy) * kPW + dx) * 16);
+            const uint32_t wh = w_s[buf] + (uint32_t)(dx * 2 * kWTileBytes), wl = wh + kWTileBytes;
+#pragma unroll
+            for (int ks = 0; ks < 2; ++ks) {  // 16 input channels (two 8-channel chunks) per MMA
+              const uint64_t a_hi = smem_desc(act_s + (uint32_t)(2 * ks) * kPlaneBytes + a_off, kPlaneBytes, 128);
+              const uint64_t a_lo = smem_desc(act_s + (uint32_t)(4 + 2 * ks) * kPlaneBytes + a_off, kPlaneBytes, 128);
+              const uint64_t b_hi = smem_desc(wh + (uint32_t)(ks * 256), 128, 512);
+              const uint64_t b_lo = smem_desc(wl + (uint32_t)(ks * 256), 128, 512);
+              mma_bf16_ss(d, a_hi, b_hi, kIdesc, (dy | dx | ks) != 0);
+              mma_bf16_ss(d, a_lo, b_hi, kIdesc, 1);
+              mma_bf16_ss(d, a_hi, b_lo, kIdesc, 1);
+            }
+          }
+        }
+        tc::mma_commit(&S.bar[buf]);
+      }
+      if (dy + 1 < kK7) {
+        const int nb = buf ^ 1;
+        if (dy >= 1) {  // the MMAs of tap row dy-1 read w[nb]: wait for them before overwriting it
+          ok &= tc::mbar_wait(&S.bar[nb], parity[nb]);
+          parity[nb] ^= 1u;
+        }
+        const uint4* src = reinterpret_cast<const uint4*>(a.w_img + (size_t)(dy + 1) * kWRowBytes);
+        uint4* dst = reinterpret_cast<uint4*>(S.w[nb]);
+        for (int i = tid; i < kWRowBytes / 16; i += kConvThreads) dst[i] = src[i];
+        tc::fence_async_smem();
+        tc::fence_before_sync();
+        __syncthreads();
+      }
+    }
+    // tap rows 5 (bar[1]) and 6 (bar[0]) are still outstanding; the commit of row 6 covers every earlier MMA
+    ok &= tc::mbar_wait(&S.bar[1], parity[1]);
+    parity[1] ^= 1u;
+    ok &= tc::mbar_wait(&S.bar[0], parity[0]);
+    parity[0] ^= 1u;
+    tc::fence_after_sync();
+    // ---- epilogue: warps 0-3 take output rows 0 and 2, warps 4-7 row 1; a thread owns one pixel (= TMEM lane)
+    const uint32_t lane_base = tmem + ((uint32_t)(32 * (warp & 3)) << 16);
+    const int m = 32 * (warp & 3) + ln;
+    for (int r = warp >> 2; r < kTH; r += 2) {
+      uint32_t dreg[kC];
+      tc::tmem_ld16(lane_base + (uint32_t)(r * kC), dreg);
+      tc::tmem_ld16(lane_base + (uint32_t)(r * kC + 16), dreg + 16);
+      tc::wait_ld();
+      const int y = y0 + r, x = x0 + m;
+      if (y < a.H && x < a.W) {
+        float acc[kC];
+#pragma unroll
+        for (int k = 0; k < kC; ++k) acc[k] = __uint_as_float(dreg[k]) + S.bias[k];
+        const int64_t pix = (img * a.H + y) * a.W + x;
+        conv_epilogue<EPI>(acc, a.residual, pix, a.out_act, a.out_rgb, S.out_w, S.out_b);
+      }
+    }
+    tc::fence_before_sync();
+    __syncthreads();  // accumulators and the input window are free again
+    tc::fence_after_sync();
+  }
+  if (!ok && a.status) atomicExch(a.status, 2);
+  tc::fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tc::tmem_dealloc(tmem, kTmemCols);
+}
+
+// ------------------------------------------------------------------ 7x7 conv on the CUDA cores (fp32 reference)
+// Same inputs, outputs and epilogues as dec_conv7_tc_kernel; one thread per output pixel, the weights of one tap row
+// (7 x 32 x 32 fp32 = 28 KB) staged in shared memory.  ~20x slower; kept as the in-library cross-check of the
+// tensor-core path (b200nerf_rgb_decode_fwd impl = 1) and for the numerics tests.
+template <int EPI>
+__global__ void __launch_bounds__(128) dec_conv7_ref_kernel(const ConvArgs a) {
+  __shared__ float sw[kK7 * kC * kC];
+  __shared__ float s_out[3 * kC + 4];
+  const int tid = threadIdx.x;
+  if (EPI == EPI_RES_RELU_RGB) {
+    if (tid < 3 * kC) s_out[tid] = a.out_w[tid];
+    if (tid < 3) s_out[3 * kC + tid] = a.out_b[tid];
+  }
+  const int tiles_x = (a.W + 127) / 128;
+  const int64_t row_id = blockIdx.x / tiles_x;  // (img, y)
+  const int x = (blockIdx.x % tiles_x) * 128 + tid;
+  const int64_t img = row_id / a.H;
+  const int y = (int)(row_id % a.H);
+  float acc[kC];
+#pragma unroll
+  for (int k = 0; k < kC; ++k) acc[k] = a.bias[k];
+  for (int dy = 0; dy < kK7; ++dy) {
+    __syncthreads();
+    for (int i = tid; i < kK7 * kC * kC; i += 128) sw[i] = a.w_f32[(size_t)dy * kK7 * kC * kC + i];
+    __syncthreads();
+    const int yy = y + dy - kPad;
+    if (yy < 0 || yy >= a.H || x >= a.W) continue;
+    for (int dx = 0; dx < kK7; ++dx) {
+      const int xx = x + dx - kPad;
+      if (xx < 0 || xx >= a.W) continue;
+      float v[kC];
+      load_act(a.in + ((img * a.H + yy) * (int64_t)a.W + xx) * 8, v);
+      const float* wt = sw + dx * kC * kC;
+#pragma unroll 4
+      for (int c = 0; c < kC; ++c) {
+#pragma unroll
+        for (int k = 0; k < kC; ++k) acc[k] = fmaf(v[c], wt[c * kC + k], acc[k]);
+      }
+    }
+  }
+  if (x < a.W) conv_epilogue<EPI>(acc, a.residual, (img * a.H + y) * (int64_t)a.W + x, a.out_act, a.out_rgb, s_out, s_out + 3 * kC);
+}
+
+}  // namespace dec

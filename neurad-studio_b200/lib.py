@@ -48,6 +48,20 @@ class Trace(ctypes.Structure):
 
 
 # name -> (restype, argtypes); every symbol include/b200nerf.h declares
+class ConvParams(ctypes.Structure):
+    _fields_ = [("weight", c_void_p), ("bias", c_void_p)]
+
+
+class ConvBnParams(ctypes.Structure):
+    _fields_ = [("conv_weight", c_void_p), ("conv_bias", c_void_p), ("bn_weight", c_void_p), ("bn_bias", c_void_p),
+                ("bn_running_mean", c_void_p), ("bn_running_var", c_void_p)]
+
+
+class RgbDecoderParams(ctypes.Structure):
+    _fields_ = [("in_dim", ctypes.c_int32), ("hidden_dim", ctypes.c_int32), ("upsample", ctypes.c_int32), ("bn_eps", c_float),
+                ("in_conv", ConvParams), ("block", (ConvBnParams * 2) * 4), ("up_conv", ConvParams), ("out_conv", ConvParams)]
+
+
 SIGNATURES = {
     "b200nerf_last_error": (c_char_p, []),
     "b200nerf_version": (c_int, []),
@@ -83,6 +97,10 @@ SIGNATURES = {
     "b200nerf_density_rgb_heads": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p, c_void_p]),
     "b200nerf_composite": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, POINTER(c_float), c_void_p, c_void_p,
                                    c_int, c_int64, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "b200nerf_set_rgb_decoder": (c_int, [c_void_p, POINTER(RgbDecoderParams)]),
+    "b200nerf_rgb_decode_workspace_bytes": (c_int64, [c_int, c_int, c_int]),
+    "b200nerf_rgb_decode_fwd": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_int64, c_int,
+                                        c_void_p]),
     "b200nerf_raygen_pinhole": (c_int, [c_void_p, POINTER(c_float), c_float, c_float, c_float, c_float, c_int, c_int,
                                         c_int, c_int, c_int, c_int, c_int, c_int, c_float, POINTER(c_float), c_float,
                                         c_float, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),

@@ -346,6 +346,55 @@ class DepthRenderer(nn.Module):
                             want_accumulation=False)["depth"]
 
 
+class BasicBlock(nn.Module):
+    """model_components/cnns.py:35-46 as a parameter container (same sub-module names, hence the same state_dict keys:
+    `main_branch.0` Conv2d, `.1` BatchNorm2d, `.3` Conv2d, `.4` BatchNorm2d).  The arithmetic runs inside
+    RGBDecoder.forward; calling a block on its own is not provided."""
+
+    def __init__(self, in_dim: int, dim: int, kernel_size: int, padding: int, use_bn: bool = False) -> None:
+        super().__init__()
+        if in_dim != dim or kernel_size != 7 or padding != 3 or not use_bn:
+            raise NotImplementedError("the b200 decoder implements NeuRAD's BasicBlock(32, 32, 7, 3, use_bn=True)")
+        self.res_branch = nn.Identity()
+        self.main_branch = nn.Sequential(
+            nn.Conv2d(in_dim, dim, kernel_size=kernel_size, padding=padding), nn.BatchNorm2d(dim), nn.ReLU(inplace=True),
+            nn.Conv2d(dim, dim, kernel_size=kernel_size, padding=padding), nn.BatchNorm2d(dim))
+        self.final_activation = nn.ReLU(inplace=True)
+
+    def forward(self, x: Tensor) -> Tensor:
+        raise RuntimeError("BasicBlock is evaluated by RGBDecoder.forward (fused tcgen05 convolutions)")
+
+
+class RGBDecoder(nn.Sequential):
+    """NeuRADModel.rgb_decoder (models/neurad.py:201-216): same module indices 0..8 and parameter names as the
+    reference's nn.Sequential, so `load_state_dict` takes the reference's `rgb_decoder.*` tensors unchanged.
+    forward takes the feature image channels-LAST, [B,H,W,C] (the ray order of get_nff_outputs; the reference permutes
+    to NCHW and back, neurad.py:362-365) and returns rgb [B,3H,3W,3] in eval mode (BatchNorm running statistics)."""
+
+    def __init__(self, in_dim: int = 48, hidden_dim: int = 32, upsample: int = 3) -> None:
+        super().__init__(
+            nn.Conv2d(in_dim, hidden_dim, kernel_size=1, padding=0), nn.ReLU(inplace=True),
+            BasicBlock(hidden_dim, hidden_dim, kernel_size=7, padding=3, use_bn=True),
+            BasicBlock(hidden_dim, hidden_dim, kernel_size=7, padding=3, use_bn=True),
+            nn.ConvTranspose2d(hidden_dim, hidden_dim, kernel_size=upsample, stride=upsample),
+            BasicBlock(hidden_dim, hidden_dim, kernel_size=7, padding=3, use_bn=True),
+            BasicBlock(hidden_dim, hidden_dim, kernel_size=7, padding=3, use_bn=True),
+            nn.Conv2d(hidden_dim, 3, kernel_size=1, padding=0), nn.Sigmoid())
+        self._bound = None
+
+    @torch.no_grad()
+    def forward(self, features: Tensor, impl: str = "tc") -> Tensor:
+        if self.training:
+            raise RuntimeError("the b200 rgb decoder is inference-only (BatchNorm in eval mode); call .eval()")
+        be = get_backend(features.device)
+        sd = self.state_dict()
+        ver = tuple(v._version for v in sd.values()) + (id(be),)
+        if ver != self._bound:
+            be.set_rgb_decoder(sd, prefix="", bn_eps=self[2].main_branch[1].eps)
+            self._bound = ver
+        return be.rgb_decode(features, impl)
+
+
 class NeuRADModel(nn.Module):
     """models/neurad.py:165 -- the forward (eval) half, with the reference's parameter names so that
     `load_state_dict(reference_checkpoint["pipeline"], strict=False)` binds the tensors the path uses.
@@ -370,6 +419,7 @@ class NeuRADModel(nn.Module):
             else:
                 self.register_buffer(name, v)
         self.register_buffer("static_scale", torch.tensor(float(config.static_scale)))
+        self.rgb_decoder = RGBDecoder(config.nff_out_dim + config.appearance_dim, config.rgb_hidden_dim, config.rgb_upsample_factor)
         self._bound_version = None
 
     # -- state dict under the reference's dotted names ----------------------------------------------------------
@@ -384,6 +434,9 @@ class NeuRADModel(nn.Module):
             if k not in sd:
                 raise KeyError(f"reference state dict lacks {k}")
             getattr(self, n).data.copy_(sd[k].to(getattr(self, n).dtype))
+        dec = {k[len("rgb_decoder."):]: v for k, v in sd.items() if k.startswith("rgb_decoder.")}
+        if dec:  # the camera decoder is optional in a hot-path-only state dict
+            self.rgb_decoder.load_state_dict(dec, strict=False)
         self._bound_version = None
 
     def _bind(self) -> B200Backend:
@@ -414,7 +467,7 @@ class NeuRADModel(nn.Module):
 
     @torch.no_grad()
     def get_outputs_for_camera_ray_bundle(self, camera_ray_bundle: RayBundle) -> Dict[str, Tensor]:
-        """neurad.py:623-675 without the rgb CNN: 2-D bundles are subsampled at
+        """neurad.py:623-675: 2-D bundles are subsampled at
         [step//2::step] like the reference (`compensate_upsampling_when_rendering`), 1-D bundles are lidar rays."""
         if len(camera_ray_bundle.shape) == 1:
             output_size = (camera_ray_bundle.shape[0],)
@@ -427,4 +480,6 @@ class NeuRADModel(nn.Module):
         out = be.render(camera_ray_bundle.as_backend_dict(), want_intensity=True)
         res = {k: v.view(*output_size, -1) for k, v in out.items()}
         res["ray_drop_prob"] = res["ray_drop_logits"].sigmoid()
+        if len(output_size) == 2:  # camera: decode the feature image to rgb at `step` x the ray resolution
+            res["rgb"] = self.rgb_decoder(res["features"][None])[0]
         return res

@@ -582,3 +582,96 @@ def test_composite_matches_oracle(backend, n_samples, n_channels):
     lo = backend.composite(w[:5], None, starts[:5] * 0 + 1.0, ends[:5] * 0 + 1.0, "expected")["depth"]
     assert (lo - 1.0).abs().max().item() < 1e-6
     assert backend.composite(w[:0], vals[:0])["values"].shape == (0, n_channels)
+
+
+# ------------------------------------------------------------------------------- camera rgb decoder
+def _decoder_golden():
+    meta, g = load_golden("rgb_decoder.npz")
+    return g["param"], g["in"]["features"], g["ref"]["rgb"]
+
+
+@pytest.mark.parametrize("impl", ["ref", "tc"])
+def test_rgb_decoder_matches_reference_golden(backend, impl):
+    """NeuRADModel.rgb_decoder (1x1 conv, 4 BasicBlocks with BatchNorm, 3x transposed conv, 1x1 conv + sigmoid) on the
+    reference's own output for a 2 x 19 x 45 feature image: CUDA-core fp32 pipeline and tcgen05 (bf16 hi/lo split)
+    pipeline, both within the 1e-4 parity bar."""
+    p, feats, ref = _decoder_golden()
+    backend.set_rgb_decoder(p)
+    rgb = backend.rgb_decode(feats, impl)
+    backend.check_status()
+    assert rgb.shape == ref.shape == (2, 57, 135, 3)
+    err = (rgb.cpu() - ref).abs().max().item()
+    assert err < 1e-4, (impl, err)  # rgb is in (0,1): absolute == relative to the output range
+    assert rel_to_max(rgb, ref) < 1e-4
+
+
+def test_rgb_decoder_tensor_core_multi_tile(backend):
+    """Several strips / row tiles / images, ragged edges (width 300 -> 900 = 7 x 128 + 4, heights not multiples of 3):
+    tcgen05 path vs the CPU oracle and vs the in-library CUDA-core path."""
+    from oracle import decoder_oracle as D
+
+    p = D.random_decoder_params(seed=21)
+    gen = torch.Generator().manual_seed(22)
+    feats = torch.randn(2, 13, 300, 48, generator=gen) * 0.7
+    backend.set_rgb_decoder(p)
+    tc = backend.rgb_decode(feats, "tc")
+    backend.check_status()
+    ref_k = backend.rgb_decode(feats, "ref")
+    with torch.no_grad():
+        ref = D.rgb_decoder(p, feats)
+    assert tc.shape == ref.shape == (2, 39, 900, 3)
+    assert (ref_k.cpu() - ref).abs().max().item() < 1e-4
+    assert (tc.cpu() - ref).abs().max().item() < 1e-4
+    assert torch.equal(tc, backend.rgb_decode(feats, "tc"))  # deterministic
+    # a single image given as [H,W,C] and batch-composition independence
+    one = backend.rgb_decode(feats[1], "tc")
+    assert torch.equal(one[0], tc[1])
+
+
+def test_rgb_decoder_api_and_errors(backend):
+    from neurad_studio_b200.backend import B200Backend
+    from neurad_studio_b200.lib import B200NerfError
+    from neurad_studio_b200.nerfstudio_api import RGBDecoder
+
+    p, feats, ref = _decoder_golden()
+    dec = RGBDecoder(48, 32, 3)
+    dec.load_state_dict({k[len("rgb_decoder."):]: v for k, v in p.items()}, strict=False)
+    dec = dec.cuda()
+    with pytest.raises(RuntimeError):
+        dec(feats.cuda())  # training mode: BatchNorm batch statistics are not provided
+    dec.eval()
+    rgb = dec(feats.cuda())
+    assert (rgb.cpu() - ref).abs().max().item() < 1e-4
+    fresh = B200Backend(torch.device("cuda", 0))
+    with pytest.raises(B200NerfError):
+        fresh.rgb_decode(feats)  # set_rgb_decoder missing (feature width unknown)
+    fresh.set_rgb_decoder(p)
+    with pytest.raises(B200NerfError):
+        fresh.rgb_decode(feats[..., :40])
+    assert fresh.rgb_decode(feats[:, :0]).shape == (2, 0, 135, 3)
+
+
+def test_camera_outputs_include_rgb():
+    """get_outputs_for_camera_ray_bundle on a 2-D bundle: rays at [1::3, 1::3], NFF, then the rgb decoder -> an image at
+    the full bundle resolution (neurad.py:623-675)."""
+    from neurad_studio_b200.nerfstudio_api import NeuRADModel, RayBundle
+    from oracle import decoder_oracle as D
+
+    meta, g = load_golden("nff_static.npz")
+    cfg = cfg_from_meta(meta)
+    sd = dict(g["param"])
+    sd.update(D.random_decoder_params(seed=31))
+    model = NeuRADModel(cfg)
+    model.load_reference_state_dict(sd)
+    model = model.cuda().eval()
+    cam = scene.pandaset_rig(time=1.0, width=48, height=27)[0]
+    be = model._bind()
+    r = be.raygen_pinhole(cam)
+    shp = r.pop("shape")
+    rb = RayBundle(origins=r["origins"].view(*shp, 3), directions=r["directions"].view(*shp, 3),
+                   pixel_area=r["pixel_area"].view(*shp, 1), times=r["times"].view(*shp, 1))
+    out = model.get_outputs_for_camera_ray_bundle(rb)
+    assert out["features"].shape == (9, 16, 48) and out["rgb"].shape == (27, 48, 3)
+    with torch.no_grad():
+        ref = D.rgb_decoder(sd, out["features"].cpu()[None])[0]
+    assert (out["rgb"].cpu() - ref).abs().max().item() < 1e-4
