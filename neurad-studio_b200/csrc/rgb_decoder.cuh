@@ -52,6 +52,7 @@ struct ConvSmem {
   float out_b[4];
   alignas(8) uint64_t bar[2];
   uint32_t tmem_base;
+  volatile int abort;  // a completion barrier timed out: every thread leaves at the next block-wide sync
 };
 
 // ------------------------------------------------------------------------------------------------ bf16 split
@@ -208,6 +209,23 @@ __device__ __forceinline__ void mma_bf16_ss(uint32_t d_tmem, uint64_t a_desc, ui
       : "memory");
 }
 
+// Bounded completion wait (a wrong descriptor must surface as a failed status, not as a wedged GPU).
+__device__ __forceinline__ bool bar_wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = tc::smem_u32(bar);
+  for (int it = 0; it < (1 << 17); ++it) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.b32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(addr), "r"(parity)
+        : "memory");
+    if (ok) return true;
+  }
+  return false;
+}
+
 struct ConvArgs {
   const uint4* in;        // ACT [B][H][W]
   const uint4* residual;  // ACT (EPI_RES_*) or nullptr
@@ -236,6 +254,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) dec_conv7_tc_kernel(const Con
   if (tid == 0) {
     tc::mbar_init(&S.bar[0], 1);
     tc::mbar_init(&S.bar[1], 1);
+    S.abort = 0;
   }
   tc::fence_before_sync();
   __syncthreads();
@@ -245,7 +264,6 @@ __global__ void __launch_bounds__(kConvThreads, 1) dec_conv7_tc_kernel(const Con
   const uint32_t w_s[2] = {tc::smem_u32(S.w[0]), tc::smem_u32(S.w[1])};
   constexpr uint32_t kIdesc = idesc_bf16(kStrip, kC);
   uint32_t parity[2] = {0u, 0u};
-  bool ok = true;
 
   const int tiles_x = (a.W + kStrip - 1) / kStrip, tiles_y = (a.H + kTH - 1) / kTH;
   const int64_t n_tiles = (int64_t)a.batch * tiles_y * tiles_x;
@@ -296,7 +314,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) dec_conv7_tc_kernel(const Con
       if (dy + 1 < kK7) {
         const int nb = buf ^ 1;
         if (dy >= 1) {  // the MMAs of tap row dy-1 read w[nb]: wait for them before overwriting it
-          ok &= tc::mbar_wait(&S.bar[nb], parity[nb]);
+          if (!bar_wait(&S.bar[nb], parity[nb])) S.abort = 1;
           parity[nb] ^= 1u;
         }
         const uint4* src = reinterpret_cast<const uint4*>(a.w_img + (size_t)(dy + 1) * kWRowBytes);
@@ -305,12 +323,14 @@ __global__ void __launch_bounds__(kConvThreads, 1) dec_conv7_tc_kernel(const Con
         tc::fence_async_smem();
         tc::fence_before_sync();
         __syncthreads();
+        if (S.abort) break;
       }
     }
+    if (S.abort) break;
     // tap rows 5 (bar[1]) and 6 (bar[0]) are still outstanding; the commit of row 6 covers every earlier MMA
-    ok &= tc::mbar_wait(&S.bar[1], parity[1]);
+    if (!bar_wait(&S.bar[1], parity[1])) S.abort = 1;
     parity[1] ^= 1u;
-    ok &= tc::mbar_wait(&S.bar[0], parity[0]);
+    if (!bar_wait(&S.bar[0], parity[0])) S.abort = 1;
     parity[0] ^= 1u;
     tc::fence_after_sync();
     // ---- epilogue: warps 0-3 take output rows 0 and 2, warps 4-7 row 1; a thread owns one pixel (= TMEM lane)
@@ -333,8 +353,9 @@ __global__ void __launch_bounds__(kConvThreads, 1) dec_conv7_tc_kernel(const Con
     tc::fence_before_sync();
     __syncthreads();  // accumulators and the input window are free again
     tc::fence_after_sync();
+    if (S.abort) break;
   }
-  if (!ok && a.status) atomicExch(a.status, 2);
+  if (S.abort && tid == 0 && a.status) atomicExch(a.status, 2);
   tc::fence_before_sync();
   __syncthreads();
   if (warp == 0) tc::tmem_dealloc(tmem, kTmemCols);
