@@ -124,7 +124,7 @@ __global__ void __launch_bounds__(WARPS * 32, 16 / WARPS) nff_render_tc_kernel(c
   unsigned char* smem_raw = smem_tc;
   TcShared* tcs = reinterpret_cast<TcShared*>(smem_raw);
   constexpr int kTcBytes = (sizeof(TcShared) + 127) / 128 * 128;
-  const int warp = threadIdx.x >> 5, group = warp >> 2;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), group = warp >> 2;
   WarpSharedTc* ws = reinterpret_cast<WarpSharedTc*>(smem_raw + kTcBytes) + warp;
   tc_stage_weights(*tcs, P.main_mlp_nn, threadIdx.x, WARPS * 32);
   tc::fence_async_smem();
@@ -137,12 +137,12 @@ __global__ void __launch_bounds__(WARPS * 32, 16 / WARPS) nff_render_tc_kernel(c
   tc::fence_after_sync();
   MlpTc mlp;
   mlp.t = tcs;
-  mlp.tile_base = tcs->tmem_base + (uint32_t)(group * kTcTileCols);
+  mlp.tile_base = __shfl_sync(0xffffffffu, tcs->tmem_base, 0) + (uint32_t)(group * kTcTileCols);
   mlp.lane_base = mlp.tile_base + ((uint32_t)(32 * (warp & 3)) << 16);
   mlp.bar = &tcs->bar[group];
   mlp.parity = 0;
   mlp.bar_id = 1 + group;
-  mlp.issuer = (threadIdx.x & 127) == 0;
+  mlp.issuer = (warp & 3) == 0;
   mlp.status = P.status;
   const int64_t stride = (int64_t)gridDim.x * WARPS;
   for (int64_t base = (int64_t)blockIdx.x * WARPS; base < P.n_rays; base += stride) {
@@ -219,7 +219,7 @@ __global__ void __launch_bounds__(kLaneThreads, kLaneCtasPerSm) nff_shade_lane_k
   TcShared* tcs = reinterpret_cast<TcShared*>(smem_shade);
   constexpr int kTcBytes = (sizeof(TcShared) + 127) / 128 * 128;
   float* geo_park = reinterpret_cast<float*>(smem_shade + kTcBytes);
-  const int tid = threadIdx.x, warp = tid >> 5, group = warp >> 2;
+  const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), group = warp >> 2;
   tc_stage_weights(*tcs, P.main_mlp_nn, tid, kLaneThreads);
   tc::fence_async_smem();
   constexpr uint32_t kCols = kTcTileCols * (kLaneThreads / 128);
@@ -231,12 +231,12 @@ __global__ void __launch_bounds__(kLaneThreads, kLaneCtasPerSm) nff_shade_lane_k
   tc::fence_after_sync();
   MlpLaneTc mlp;
   mlp.core.t = tcs;
-  mlp.core.tile_base = tcs->tmem_base + (uint32_t)(group * kTcTileCols);
+  mlp.core.tile_base = __shfl_sync(0xffffffffu, tcs->tmem_base, 0) + (uint32_t)(group * kTcTileCols);
   mlp.core.lane_base = mlp.core.tile_base + ((uint32_t)(32 * (warp & 3)) << 16);
   mlp.core.bar = &tcs->bar[group];
   mlp.core.parity = 0;
   mlp.core.bar_id = 1 + group;
-  mlp.core.issuer = (tid & 127) == 0;
+  mlp.core.issuer = (warp & 3) == 0;
   mlp.core.status = P.status;
   const LaneScratch sc = lane_scratch_of(scratch, blockIdx.x);
   mlp.geo_park = NFF_PANEL_GLOBAL ? sc.panel : geo_park;
@@ -258,7 +258,7 @@ __global__ void __launch_bounds__(kLaneThreads, kLaneCtasPerSm) nff_render_lane_
   TcShared* tcs = reinterpret_cast<TcShared*>(smem_lane);
   constexpr int kTcBytes = (sizeof(TcShared) + 127) / 128 * 128;
   float* geo_park = reinterpret_cast<float*>(smem_lane + kTcBytes);
-  const int tid = threadIdx.x, warp = tid >> 5, group = warp >> 2;
+  const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), group = warp >> 2;
   tc_stage_weights(*tcs, P.main_mlp_nn, tid, kLaneThreads);
   tc::fence_async_smem();
   constexpr uint32_t kCols = kTcTileCols * (kLaneThreads / 128);
@@ -270,12 +270,12 @@ __global__ void __launch_bounds__(kLaneThreads, kLaneCtasPerSm) nff_render_lane_
   tc::fence_after_sync();
   MlpLaneTc mlp;
   mlp.core.t = tcs;
-  mlp.core.tile_base = tcs->tmem_base + (uint32_t)(group * kTcTileCols);
+  mlp.core.tile_base = __shfl_sync(0xffffffffu, tcs->tmem_base, 0) + (uint32_t)(group * kTcTileCols);
   mlp.core.lane_base = mlp.core.tile_base + ((uint32_t)(32 * (warp & 3)) << 16);
   mlp.core.bar = &tcs->bar[group];
   mlp.core.parity = 0;
   mlp.core.bar_id = 1 + group;
-  mlp.core.issuer = (tid & 127) == 0;
+  mlp.core.issuer = (warp & 3) == 0;
   mlp.core.status = P.status;
   const LaneScratch sc = lane_scratch_of(scratch, blockIdx.x);
   mlp.geo_park = NFF_PANEL_GLOBAL ? sc.panel : geo_park;
@@ -646,7 +646,7 @@ __global__ void __launch_bounds__(128) mlp_tc_kernel(const MlpArgs a, const floa
   __shared__ uint32_t tmem_base_s;
   __shared__ __align__(8) uint64_t bar;
   using Cols = tc::TileCols<kTcKMax, kTcNMax>;
-  const int tid = threadIdx.x, warp = tid >> 5;
+  const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
   for (int l = 0; l < a.n_layers; ++l) {
     float* hi = sm_mlp + a.smem_off[l];
     tc::stage_b_tile(hi, hi + a.n_pad[l] * a.k_pad[l], a.w[l], a.n_real[l], a.k_real[l], a.n_pad[l], a.k_pad[l], tid, 128);
@@ -658,7 +658,7 @@ __global__ void __launch_bounds__(128) mlp_tc_kernel(const MlpArgs a, const floa
   tc::fence_before_sync();
   __syncthreads();
   tc::fence_after_sync();
-  const uint32_t tmem_base = tmem_base_s;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, tmem_base_s, 0);
   const uint32_t lane_base = tmem_base + ((uint32_t)(32 * (warp & 3)) << 16);
   uint32_t parity = 0;
   const int out_dim = a.n_real[a.n_layers - 1];
@@ -672,7 +672,7 @@ __global__ void __launch_bounds__(128) mlp_tc_kernel(const MlpArgs a, const floa
       tc::wait_st();
       tc::fence_before_sync();
       __syncthreads();
-      if (tid == 0) {
+      if (warp == 0) {  // converged warp, one elected lane issues (see tc::issue_layer)
         tc::fence_after_sync();
         const float* hi = sm_mlp + a.smem_off[l];
         tc::issue_layer<kTcKMax>(tmem_base, Cols::d, hi, hi + a.n_pad[l] * a.k_pad[l], a.k_pad[l], a.n_pad[l], &bar);

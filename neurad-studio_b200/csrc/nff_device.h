@@ -685,7 +685,7 @@ struct MlpTc {
   uint64_t* bar;
   uint32_t parity;
   int bar_id;
-  bool issuer;
+  bool issuer;  // warp-uniform: this warp is the first of its 4-warp tile and issues the tile's MMAs
   int* status;
 
   // store K activations of this thread's row, run layer l on the tensor cores, fetch the 32 outputs

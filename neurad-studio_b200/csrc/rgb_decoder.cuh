@@ -226,6 +226,17 @@ __device__ __forceinline__ bool bar_wait(uint64_t* bar, uint32_t parity) {
   return false;
 }
 
+__device__ __forceinline__ uint32_t elect_one() {  // one lane of the converged warp (the same one every time)
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred P;\n\t"
+      "elect.sync _|P, 0xffffffff;\n\t"
+      "selp.b32 %0, 1, 0, P;\n\t}"
+      : "=r"(pred));
+  return pred;
+}
+__device__ __forceinline__ uint64_t make_desc(uint32_t lo, uint32_t hi) { return ((uint64_t)hi << 32) | lo; }
+
 struct ConvArgs {
   const uint4* in;        // ACT [B][H][W]
   const uint4* residual;  // ACT (EPI_RES_*) or nullptr
@@ -244,7 +255,8 @@ template <int EPI>
 __global__ void __launch_bounds__(kConvThreads, 1) dec_conv7_tc_kernel(const ConvArgs a) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   ConvSmem& S = *reinterpret_cast<ConvSmem*>(smem_raw);
-  const int tid = threadIdx.x, warp = tid >> 5, ln = tid & 31;
+  const int tid = threadIdx.x, ln = tid & 31;
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);  // provably warp-uniform
   if (tid < kC) S.bias[tid] = a.bias[tid];
   if (EPI == EPI_RES_RELU_RGB) {
     if (tid < 3 * kC) S.out_w[tid] = a.out_w[tid];
@@ -259,9 +271,13 @@ __global__ void __launch_bounds__(kConvThreads, 1) dec_conv7_tc_kernel(const Con
   tc::fence_before_sync();
   __syncthreads();
   tc::fence_after_sync();
-  const uint32_t tmem = S.tmem_base;
-  const uint32_t act_s = tc::smem_u32(S.act);
-  const uint32_t w_s[2] = {tc::smem_u32(S.w[0]), tc::smem_u32(S.w[1])};
+  const uint32_t tmem = __shfl_sync(0xffffffffu, S.tmem_base, 0);
+  // low 32 bits of the shared-memory descriptors: start address >> 4 in [0,14), LBO >> 4 in [16,30); the high words
+  // (SBO >> 4, version 1, no swizzle) are constants.  Advancing an operand = adding 16-byte units to the low word.
+  const uint32_t a_lo32 = ((tc::smem_u32(S.act) & 0x3ffffu) >> 4) | ((uint32_t)(kPlaneBytes >> 4) << 16);
+  const uint32_t b_lo32[2] = {((tc::smem_u32(S.w[0]) & 0x3ffffu) >> 4) | ((128u >> 4) << 16),
+                              ((tc::smem_u32(S.w[1]) & 0x3ffffu) >> 4) | ((128u >> 4) << 16)};
+  constexpr uint32_t kDescHiA = (128u >> 4) | (1u << 14), kDescHiB = (512u >> 4) | (1u << 14);  // bits [32,64)
   constexpr uint32_t kIdesc = idesc_bf16(kStrip, kC);
   uint32_t parity[2] = {0u, 0u};
 
@@ -290,26 +306,34 @@ __global__ void __launch_bounds__(kConvThreads, 1) dec_conv7_tc_kernel(const Con
     __syncthreads();
     for (int dy = 0; dy < kK7; ++dy) {
       const int buf = dy & 1;
-      if (tid == 0) {
+      if (warp == 0) {
+        // The whole (converged) warp walks the tap loop so that every descriptor is a warp-uniform value the compiler
+        // keeps in uniform registers -- tcgen05.mma takes its operands from there; built inside a single-thread branch
+        // each MMA pays a register->uniform broadcast loop -- and one elected lane issues.
         tc::fence_after_sync();
+        const uint32_t leader = elect_one();
+#pragma unroll 1
         for (int r = 0; r < kTH; ++r) {
           const uint32_t d = tmem + (uint32_t)(r * kC);
+          const uint32_t a_row = a_lo32 + (uint32_t)((r + dy) * kPW);  // descriptor low words advance in 16-byte units
+#pragma unroll
           for (int dx = 0; dx < kK7; ++dx) {
-            const uint32_t a_off = (uint32_t)(((r + dy) * kPW + dx) * 16);
-            const uint32_t wh = w_s[buf] + (uint32_t)(dx * 2 * kWTileBytes), wl = wh + kWTileBytes;
 #pragma unroll
             for (int ks = 0; ks < 2; ++ks) {  // 16 input channels (two 8-channel chunks) per MMA
-              const uint64_t a_hi = smem_desc(act_s + (uint32_t)(2 * ks) * kPlaneBytes + a_off, kPlaneBytes, 128);
-              const uint64_t a_lo = smem_desc(act_s + (uint32_t)(4 + 2 * ks) * kPlaneBytes + a_off, kPlaneBytes, 128);
-              const uint64_t b_hi = smem_desc(wh + (uint32_t)(ks * 256), 128, 512);
-              const uint64_t b_lo = smem_desc(wl + (uint32_t)(ks * 256), 128, 512);
-              mma_bf16_ss(d, a_hi, b_hi, kIdesc, (dy | dx | ks) != 0);
-              mma_bf16_ss(d, a_lo, b_hi, kIdesc, 1);
-              mma_bf16_ss(d, a_hi, b_lo, kIdesc, 1);
+              const uint32_t ah = a_row + (uint32_t)(dx + 2 * ks * (kPlaneBytes / 16));
+              const uint32_t al = ah + (uint32_t)(4 * (kPlaneBytes / 16));
+              const uint32_t bh = b_lo32[buf] + (uint32_t)((dx * 2 * kWTileBytes + ks * 256) / 16);
+              const uint32_t bl = bh + (uint32_t)(kWTileBytes / 16);
+              if (leader) {
+                mma_bf16_ss(d, make_desc(ah, kDescHiA), make_desc(bh, kDescHiB), kIdesc, (dy | dx | ks) != 0);
+                mma_bf16_ss(d, make_desc(al, kDescHiA), make_desc(bh, kDescHiB), kIdesc, 1);
+                mma_bf16_ss(d, make_desc(ah, kDescHiA), make_desc(bl, kDescHiB), kIdesc, 1);
+              }
             }
           }
         }
-        tc::mma_commit(&S.bar[buf]);
+        if (leader) tc::mma_commit(&S.bar[buf]);
+        __syncwarp();
       }
       if (dy + 1 < kK7) {
         const int nb = buf ^ 1;

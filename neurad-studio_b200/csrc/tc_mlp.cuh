@@ -140,23 +140,41 @@ __device__ __forceinline__ void store_a(uint32_t lane_base, int k0, const float*
   }
 }
 
-// Issue one layer: D[128 x N] = A[128 x K] * W^T with the 3xTF32 split.  Called by ONE thread.
+__device__ __forceinline__ uint32_t elect_one() {  // one lane of the converged warp (the same one every time)
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred P;\n\t"
+      "elect.sync _|P, 0xffffffff;\n\t"
+      "selp.b32 %0, 1, 0, P;\n\t}"
+      : "=r"(pred));
+  return pred;
+}
+// Issue one layer: D[128 x N] = A[128 x K] * W^T with the 3xTF32 split.  Called by ONE CONVERGED WARP with
+// warp-uniform arguments: the descriptors are then warp-uniform values the compiler keeps in uniform registers (where
+// tcgen05.mma takes its operands from) and one elected lane issues.  Built inside a single-thread branch instead, every
+// MMA pays a ~10-instruction register->uniform-register broadcast loop.
 template <int K_MAX>
 __device__ __forceinline__ void issue_layer(uint32_t tmem_base, int d_col, const float* b_hi, const float* b_lo, int k_pad, int n_pad,
                                             uint64_t* bar) {
+  const uint32_t leader = elect_one();
   const uint32_t idesc = idesc_tf32(128, n_pad);
-  const uint64_t dh = b_desc(b_hi, k_pad), dl = b_desc(b_lo, k_pad);
+  // low words: start >> 4 | LBO (128 B) >> 4 << 16; high words: SBO >> 4 | version 1
+  const uint32_t h32 = ((smem_u32(b_hi) & 0x3ffffu) >> 4) | ((128u >> 4) << 16);
+  const uint32_t l32 = ((smem_u32(b_lo) & 0x3ffffu) >> 4) | ((128u >> 4) << 16);
+  const uint32_t hi32 = (uint32_t)(((k_pad >> 2) * 128) >> 4) | (1u << 14);
   const uint32_t d = tmem_base + (uint32_t)d_col;
-  uint32_t acc = 0;
   for (int ks = 0; ks < k_pad / 8; ++ks) {
-    const uint64_t adv = (uint64_t)(ks * 2 * 128) >> 4;  // two 16-byte K-chunks (= 2 core matrices) per k-step
+    const uint32_t adv = (uint32_t)(ks * 2 * 128) >> 4;  // two 16-byte K-chunks (= 2 core matrices) per k-step
     const uint32_t a_hi = tmem_base + (uint32_t)(ks * 8), a_lo = tmem_base + (uint32_t)(K_MAX + ks * 8);
-    mma_tf32_ts(d, a_hi, dh + adv, idesc, acc);
-    acc = 1;
-    mma_tf32_ts(d, a_lo, dh + adv, idesc, 1);
-    mma_tf32_ts(d, a_hi, dl + adv, idesc, 1);
+    const uint64_t dh = ((uint64_t)hi32 << 32) | (h32 + adv), dl = ((uint64_t)hi32 << 32) | (l32 + adv);
+    if (leader) {
+      mma_tf32_ts(d, a_hi, dh, idesc, ks != 0);
+      mma_tf32_ts(d, a_lo, dh, idesc, 1);
+      mma_tf32_ts(d, a_hi, dl, idesc, 1);
+    }
   }
-  mma_commit(bar);
+  if (leader) mma_commit(bar);
+  __syncwarp();
 }
 
 }  // namespace tc
