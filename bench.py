@@ -284,6 +284,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--cpu-sample", type=int, default=16384)
+    ap.add_argument("--no-decoder", action="store_true", help="skip the extra 'with_rgb_decoder' measurement (N = 1)")
     ap.add_argument("--gather", default="p2p", choices=["p2p", "nccl"],
                     help="N>1: p2p = render epilogue stores rows into every peer's buffer over NVLink (default); "
                          "nccl = all_gather_into_tensor after the render")
@@ -385,6 +386,42 @@ def main():
     ms_e2e = timed(step.run_e2e, args.steps)
     # the host buffers the e2e arm filled must hold exactly what the device buffers hold
     e2e_ok = all(torch.equal(step.host_out[k], step.gather[k][rank].cpu()) for k in step.host_out)
+    # (ii) of SURVEY 8(d): the same step followed by the camera rgb decoder (NeuRADModel.rgb_decoder, tcgen05 implicit-GEMM
+    # convolutions) on the six rendered feature images -> 6 x 1080 x 1920 rgb.  Reported beside the headline, N = 1 only
+    # (the decoder needs whole images; the multi-GPU arm shards rays, not images).
+    dec_line = None
+    if world == 1 and not args.no_decoder:
+        be.set_rgb_decoder(scene.make_rgb_decoder_params(seed=2, device=dev))
+        n_cams = len(cams)
+        rgb = torch.empty(n_cams, 1080, 1920, 3, device=dev)
+        dec_events = []
+
+        def run_with_decoder():
+            out = step.run_device(False)
+            feats = out["features"][: step.n_cam].view(n_cams, 360, 640, -1)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            be.rgb_decode(feats, out=rgb)
+            e1.record()
+            dec_events.append((e0, e1))
+
+        for _ in range(2):
+            run_with_decoder()
+        dec_events.clear()
+        ms_dec = timed(run_with_decoder, args.steps)
+        be.check_status()
+        d_ms = sorted(a.elapsed_time(b) for a, b in dec_events)
+        d_ms = sum(d_ms) / len(d_ms)
+        mac_per_ray = 48 * 32 + 4 * 50176 + 32 * 288 + 9 * (4 * 50176 + 3 * 32)
+        tf = 2.0 * mac_per_ray * step.n_cam / (d_ms * 1e-3) / 1e12
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
+        tpeak = float(peaks.get("bf16_tflops_sustained", 1443.2))
+        dec_line = {"value": step.n * args.steps / (ms_dec * 1e-3), "unit": "rays/s", "ms_per_step": ms_dec / args.steps,
+                    "decoder_ms": d_ms, "decoder_camera_rays_per_s": step.n_cam / (d_ms * 1e-3), "gpu_launches_decoder": 10,
+                    "roofline": {"bound": "tensor", "achieved": tf, "executed": 3 * tf, "peak": tpeak, "unit": "TFLOP/s",
+                                 "frac": tf / tpeak, "frac_executed": 3 * tf / tpeak,
+                                 "note": "achieved = algorithmic 4.04 MFLOP/camera ray; executed = 3x (bf16 hi/lo split: three MMAs per product for fp32-level accuracy); peak = measured sustained dense bf16"},
+                    "what": "render step + NeuRADModel.rgb_decoder on the 6 feature images (6x360x640x48 -> 6x1080x1920x3 rgb)"}
     clocks = sampler.stop() if rank == 0 else None
     rays_total = step.n * world * args.steps
     value = rays_total / (ms * 1e-3)
@@ -407,6 +444,8 @@ def main():
     traffic_file = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(traffic_file):
         line["roofline"]["traffic"] = json.load(open(traffic_file)).get("dram_bytes_per_launch")
+    if dec_line is not None:
+        line["with_rgb_decoder"] = dec_line
     if world == 1 and args.cpu_sample > 0:
         v, n, dt = oracle_rays_per_sec(cfg, args.cpu_sample)
         line["cpu_baseline"] = {"value": v, "unit": "rays/s", "cores": torch.get_num_threads(), "kind": "port",

@@ -413,7 +413,7 @@ class B200Backend:
         self._check(self.lib.b200nerf_set_rgb_decoder(self._h, ctypes.byref(p)))  # synchronous: `keep` may go now
         self._dec_in_dim = int(w0.shape[1])
 
-    def rgb_decode(self, features: torch.Tensor, impl: str = "tc") -> torch.Tensor:
+    def rgb_decode(self, features: torch.Tensor, impl: str = "tc", out: Optional[torch.Tensor] = None) -> torch.Tensor:
         """Camera half of NeuRADModel.decode_features (neurad.py:359-366): features [B,H,W,C] (or [H,W,C]) ->
         rgb [B,3H,3W,3].  impl "tc": tcgen05 implicit-GEMM convolutions; "ref": CUDA-core fp32 cross-check."""
         f = self._dev(features)
@@ -426,7 +426,9 @@ class B200Backend:
         ws = getattr(self, "_dec_ws", None)
         if ws is None or ws.numel() < need:
             ws = self._dec_ws = torch.empty(max(need, 16), dtype=torch.uint8, device=self.device)
-        rgb = torch.empty(b, 3 * h, 3 * w, 3, device=self.device)
+        rgb = out if out is not None else torch.empty(b, 3 * h, 3 * w, 3, device=self.device)
+        if rgb.shape != (b, 3 * h, 3 * w, 3) or not rgb.is_contiguous() or rgb.dtype != torch.float32 or rgb.device != f.device:
+            raise _lib.B200NerfError("rgb_decode: `out` must be a contiguous fp32 [B,3H,3W,3] tensor on the backend's device")
         self._check(self.lib.b200nerf_rgb_decode_fwd(self._h, _ptr(f), b, h, w, _ptr(rgb), _ptr(ws), ws.numel(),
                                                      {"tc": 0, "ref": 1}[impl], self._stream))
         return rgb

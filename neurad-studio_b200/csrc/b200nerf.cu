@@ -1477,7 +1477,8 @@ int b200nerf_rgb_decode_fwd(b200nerf_ctx* c, const float* features, int batch, i
   if (int e = conv(2, dec::EPI_RELU, lo[2], nullptr, lo[1], nullptr, H, W)) return e;
   if (int e = conv(3, dec::EPI_RES_RELU, lo[1], lo[2], lo[0], nullptr, H, W)) return e;
   // rgb_decoder.4: 3x transposed conv
-  dec::dec_upsample_kernel<<<(unsigned)((hi_px + 127) / 128), 128, sizeof(float) * (9 * dec::kC * dec::kC + dec::kC), st>>>(
+  dec::dec_upsample_kernel<<<(unsigned)((lo_px + 2 * dec::kUpThreads - 1) / (2 * dec::kUpThreads)), dec::kUpThreads,
+                             sizeof(float) * (9 * dec::kC * dec::kC + dec::kC), st>>>(
       lo[0], batch, H, W, d.up_w, d.up_b, hi[0]);
   CUDA_TRY(cudaGetLastError());
   // rgb_decoder.5, .6 at image resolution; .7/.8 (1x1 conv + sigmoid) in the last epilogue

@@ -60,25 +60,38 @@ __device__ __forceinline__ void split_bf16(float v, __nv_bfloat16& hi, __nv_bflo
   hi = __float2bfloat16_rn(v);
   lo = __float2bfloat16_rn(v - __bfloat162float(hi));
 }
-// 32 channels of one pixel -> ACT (8 x uint4)
+// two fp32 -> packed bf16x2 hi word and lo word (element 0 in the low half = lower address)
+__device__ __forceinline__ void split_pack2(float a, float b, uint32_t& hi, uint32_t& lo) {
+  const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  hi = *reinterpret_cast<const uint32_t*>(&h);
+  const __nv_bfloat162 l = __floats2bfloat162_rn(a - __uint_as_float(hi << 16), b - __uint_as_float(hi & 0xffff0000u));
+  lo = *reinterpret_cast<const uint32_t*>(&l);
+}
+// 32 channels of one pixel -> ACT (8 x uint4), registers only
 __device__ __forceinline__ void store_act(uint4* dst, const float* v) {
-  __align__(16) __nv_bfloat16 hi[kC], lo[kC];
-#pragma unroll
-  for (int k = 0; k < kC; ++k) split_bf16(v[k], hi[k], lo[k]);
 #pragma unroll
   for (int c = 0; c < 4; ++c) {
-    dst[c] = *reinterpret_cast<const uint4*>(&hi[8 * c]);
-    dst[4 + c] = *reinterpret_cast<const uint4*>(&lo[8 * c]);
+    uint4 h, l;
+    split_pack2(v[8 * c + 0], v[8 * c + 1], h.x, l.x);
+    split_pack2(v[8 * c + 2], v[8 * c + 3], h.y, l.y);
+    split_pack2(v[8 * c + 4], v[8 * c + 5], h.z, l.z);
+    split_pack2(v[8 * c + 6], v[8 * c + 7], h.w, l.w);
+    dst[c] = h;
+    dst[4 + c] = l;
   }
+}
+__device__ __forceinline__ void unpack2(uint32_t h, uint32_t l, float& a, float& b) {
+  a = __uint_as_float(h << 16) + __uint_as_float(l << 16);
+  b = __uint_as_float(h & 0xffff0000u) + __uint_as_float(l & 0xffff0000u);
 }
 __device__ __forceinline__ void load_act(const uint4* src, float* v) {
 #pragma unroll
   for (int c = 0; c < 4; ++c) {
     const uint4 h = src[c], l = src[4 + c];
-    const __nv_bfloat16* hb = reinterpret_cast<const __nv_bfloat16*>(&h);
-    const __nv_bfloat16* lb = reinterpret_cast<const __nv_bfloat16*>(&l);
-#pragma unroll
-    for (int k = 0; k < 8; ++k) v[8 * c + k] = __bfloat162float(hb[k]) + __bfloat162float(lb[k]);
+    unpack2(h.x, l.x, v[8 * c + 0], v[8 * c + 1]);
+    unpack2(h.y, l.y, v[8 * c + 2], v[8 * c + 3]);
+    unpack2(h.z, l.z, v[8 * c + 4], v[8 * c + 5]);
+    unpack2(h.w, l.w, v[8 * c + 6], v[8 * c + 7]);
   }
 }
 
@@ -134,32 +147,55 @@ __global__ void dec_input_kernel(const float* __restrict__ x, int64_t n_pix, int
 }
 
 // --------------------------------------------------------------------------- ConvTranspose2d, kernel = stride = 3
-// rgb_decoder.4: out[3y+i][3x+j][co] = b[co] + sum_ci in[y][x][ci] * w[ci][co][i][j]   (one thread per OUTPUT pixel)
-__global__ void dec_upsample_kernel(const uint4* __restrict__ in, int batch, int H, int W, const float* __restrict__ w,
-                                    const float* __restrict__ b, uint4* __restrict__ out) {
-  extern __shared__ float sw[];  // [i*3+j][ci][co] + bias
+// rgb_decoder.4: out[3y+i][3x+j][co] = b[co] + sum_ci in[y][x][ci] * w[ci][co][i][j].  One thread owns TWO input pixels
+// and produces their 2 x 9 output pixels; the weights [ij][ci][co] sit in shared memory and every read is a warp-wide
+// broadcast feeding 8 FMAs (2 pixels x 4 channels).
+constexpr int kUpThreads = 128;
+__global__ void __launch_bounds__(kUpThreads) dec_upsample_kernel(const uint4* __restrict__ in, int batch, int H, int W,
+                                                                   const float* __restrict__ w, const float* __restrict__ b,
+                                                                   uint4* __restrict__ out) {
+  extern __shared__ __align__(16) float sw[];  // [i*3+j][ci][co] + bias
   for (int i = threadIdx.x; i < kC * kC * kUp * kUp; i += blockDim.x) {
     const int ci = i / (kC * 9), co = (i / 9) % kC, ij = i % 9;
     sw[(ij * kC + ci) * kC + co] = w[i];
   }
   for (int i = threadIdx.x; i < kC; i += blockDim.x) sw[9 * kC * kC + i] = b[i];
   __syncthreads();
-  const int64_t HO = (int64_t)H * kUp, WO = (int64_t)W * kUp;
-  const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (p >= batch * HO * WO) return;
-  const int64_t img = p / (HO * WO), Y = (p / WO) % HO, X = p % WO;
-  const int ij = (int)(Y % kUp) * kUp + (int)(X % kUp);
-  float v[kC], acc[kC];
-  load_act(in + ((img * H + Y / kUp) * W + X / kUp) * 8, v);
+  const int64_t n_in = (int64_t)batch * H * W;
+  const int64_t p0 = ((int64_t)blockIdx.x * kUpThreads + threadIdx.x) * 2;
+  if (p0 >= n_in) return;
+  const bool two = p0 + 1 < n_in;
+  float v0[kC], v1[kC];
+  load_act(in + p0 * 8, v0);
+  load_act(in + (two ? p0 + 1 : p0) * 8, v1);
+  const int64_t WO = (int64_t)W * kUp;
+  int64_t base[2];
 #pragma unroll
-  for (int k = 0; k < kC; ++k) acc[k] = sw[9 * kC * kC + k];
-  const float* wt = sw + ij * kC * kC;
-#pragma unroll 4
-  for (int c = 0; c < kC; ++c) {
-#pragma unroll
-    for (int k = 0; k < kC; ++k) acc[k] = fmaf(v[c], wt[c * kC + k], acc[k]);
+  for (int q = 0; q < 2; ++q) {
+    const int64_t p = p0 + q, img = p / ((int64_t)H * W), y = (p / W) % H, x = p % W;
+    base[q] = (img * H * kUp + y * kUp) * WO + x * kUp;
   }
-  store_act(out + p * 8, acc);
+#pragma unroll 1
+  for (int ij = 0; ij < 9; ++ij) {
+    float a0[kC], a1[kC];
+#pragma unroll
+    for (int k = 0; k < kC; ++k) a0[k] = a1[k] = sw[9 * kC * kC + k];
+    const float4* wt = reinterpret_cast<const float4*>(sw + ij * kC * kC);
+#pragma unroll
+    for (int c = 0; c < kC; ++c) {
+#pragma unroll
+      for (int k4 = 0; k4 < kC / 4; ++k4) {
+        const float4 ww = wt[c * (kC / 4) + k4];
+        a0[4 * k4 + 0] = fmaf(v0[c], ww.x, a0[4 * k4 + 0]); a1[4 * k4 + 0] = fmaf(v1[c], ww.x, a1[4 * k4 + 0]);
+        a0[4 * k4 + 1] = fmaf(v0[c], ww.y, a0[4 * k4 + 1]); a1[4 * k4 + 1] = fmaf(v1[c], ww.y, a1[4 * k4 + 1]);
+        a0[4 * k4 + 2] = fmaf(v0[c], ww.z, a0[4 * k4 + 2]); a1[4 * k4 + 2] = fmaf(v1[c], ww.z, a1[4 * k4 + 2]);
+        a0[4 * k4 + 3] = fmaf(v0[c], ww.w, a0[4 * k4 + 3]); a1[4 * k4 + 3] = fmaf(v1[c], ww.w, a1[4 * k4 + 3]);
+      }
+    }
+    const int64_t off = (int64_t)(ij / 3) * WO + ij % 3;
+    store_act(out + (base[0] + off) * 8, a0);
+    if (two) store_act(out + (base[1] + off) * 8, a1);
+  }
 }
 
 // ------------------------------------------------------------------------------------------------ epilogues
@@ -237,6 +273,13 @@ __device__ __forceinline__ uint32_t elect_one() {  // one lane of the converged 
 }
 __device__ __forceinline__ uint64_t make_desc(uint32_t lo, uint32_t hi) { return ((uint64_t)hi << 32) | lo; }
 
+// 16-byte asynchronous global -> shared copy (LDGSTS); src_bytes = 0 writes zeros (the conv's padding) without
+// reading.  Many of these are in flight per thread, which is what hides the L2 latency of the window / weight loads.
+__device__ __forceinline__ void cp_async16(uint32_t dst_smem, const void* src, uint32_t src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst_smem), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
 struct ConvArgs {
   const uint4* in;        // ACT [B][H][W]
   const uint4* residual;  // ACT (EPI_RES_*) or nullptr
@@ -277,30 +320,37 @@ __global__ void __launch_bounds__(kConvThreads, 1) dec_conv7_tc_kernel(const Con
   const uint32_t a_lo32 = ((tc::smem_u32(S.act) & 0x3ffffu) >> 4) | ((uint32_t)(kPlaneBytes >> 4) << 16);
   const uint32_t b_lo32[2] = {((tc::smem_u32(S.w[0]) & 0x3ffffu) >> 4) | ((128u >> 4) << 16),
                               ((tc::smem_u32(S.w[1]) & 0x3ffffu) >> 4) | ((128u >> 4) << 16)};
+  const uint32_t act_u32 = tc::smem_u32(S.act);
+  const uint32_t w_u32[2] = {tc::smem_u32(S.w[0]), tc::smem_u32(S.w[1])};
   constexpr uint32_t kDescHiA = (128u >> 4) | (1u << 14), kDescHiB = (512u >> 4) | (1u << 14);  // bits [32,64)
   constexpr uint32_t kIdesc = idesc_bf16(kStrip, kC);
   uint32_t parity[2] = {0u, 0u};
 
   const int tiles_x = (a.W + kStrip - 1) / kStrip, tiles_y = (a.H + kTH - 1) / kTH;
   const int64_t n_tiles = (int64_t)a.batch * tiles_y * tiles_x;
-  for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+  // asynchronous fill of the input window (8 chunk planes; pixels outside the image are the conv's zero padding) and of
+  // tap row 0 of the weights for one tile
+  auto issue_tile_loads = [&](int64_t tile) {
     const int tx = (int)(tile % tiles_x), ty = (int)((tile / tiles_x) % tiles_y);
     const int64_t img = tile / ((int64_t)tiles_x * tiles_y);
     const int x0 = tx * kStrip, y0 = ty * kTH;
     const uint4* in_img = a.in + img * (int64_t)a.H * a.W * 8;
-    // ---- input window -> 8 chunk planes; pixels outside the image are the conv's zero padding
     for (int i = tid; i < kIR * kPW * 8; i += kConvThreads) {
       const int c = i & 7, ip = (i >> 3) % kPW, ir = (i >> 3) / kPW;
       const int y = y0 - kPad + ir, x = x0 - kPad + ip;
-      uint4 v = make_uint4(0u, 0u, 0u, 0u);
-      if (y >= 0 && y < a.H && x >= 0 && x < a.W) v = in_img[((int64_t)y * a.W + x) * 8 + c];
-      *reinterpret_cast<uint4*>(S.act + c * kPlaneBytes + (ir * kPW + ip) * 16) = v;
+      const bool inside = y >= 0 && y < a.H && x >= 0 && x < a.W;
+      const uint4* src = inside ? in_img + ((int64_t)y * a.W + x) * 8 + c : in_img;
+      cp_async16(act_u32 + (uint32_t)(c * kPlaneBytes + (ir * kPW + ip) * 16), src, inside ? 16u : 0u);
     }
-    {  // tap row 0 of the weights
-      const uint4* src = reinterpret_cast<const uint4*>(a.w_img);
-      uint4* dst = reinterpret_cast<uint4*>(S.w[0]);
-      for (int i = tid; i < kWRowBytes / 16; i += kConvThreads) dst[i] = src[i];
-    }
+    const uint4* src = reinterpret_cast<const uint4*>(a.w_img);
+    for (int i = tid; i < kWRowBytes / 16; i += kConvThreads) cp_async16(w_u32[0] + (uint32_t)(i * 16), src + i, 16u);
+  };
+  if ((int64_t)blockIdx.x < n_tiles) issue_tile_loads(blockIdx.x);
+  for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const int tx = (int)(tile % tiles_x), ty = (int)((tile / tiles_x) % tiles_y);
+    const int64_t img = tile / ((int64_t)tiles_x * tiles_y);
+    const int x0 = tx * kStrip, y0 = ty * kTH;
+    cp_async_wait_all();
     tc::fence_async_smem();  // generic-proxy writes -> visible to the tensor core (async proxy)
     tc::fence_before_sync();
     __syncthreads();
@@ -342,8 +392,8 @@ __global__ void __launch_bounds__(kConvThreads, 1) dec_conv7_tc_kernel(const Con
           parity[nb] ^= 1u;
         }
         const uint4* src = reinterpret_cast<const uint4*>(a.w_img + (size_t)(dy + 1) * kWRowBytes);
-        uint4* dst = reinterpret_cast<uint4*>(S.w[nb]);
-        for (int i = tid; i < kWRowBytes / 16; i += kConvThreads) dst[i] = src[i];
+        for (int i = tid; i < kWRowBytes / 16; i += kConvThreads) cp_async16(w_u32[nb] + (uint32_t)(i * 16), src + i, 16u);
+        cp_async_wait_all();
         tc::fence_async_smem();
         tc::fence_before_sync();
         __syncthreads();
@@ -357,6 +407,9 @@ __global__ void __launch_bounds__(kConvThreads, 1) dec_conv7_tc_kernel(const Con
     if (!bar_wait(&S.bar[0], parity[0])) S.abort = 1;
     parity[0] ^= 1u;
     tc::fence_after_sync();
+    // every MMA of this tile has completed: the window and both weight buffers are free, so the next tile's loads fly
+    // while this tile's accumulators are drained
+    if (tile + gridDim.x < n_tiles) issue_tile_loads(tile + gridDim.x);
     // ---- epilogue: warps 0-3 take output rows 0 and 2, warps 4-7 row 1; a thread owns one pixel (= TMEM lane)
     const uint32_t lane_base = tmem + ((uint32_t)(32 * (warp & 3)) << 16);
     const int m = 32 * (warp & 3) + ln;
@@ -379,6 +432,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) dec_conv7_tc_kernel(const Con
     tc::fence_after_sync();
     if (S.abort) break;
   }
+  cp_async_wait_all();
   if (S.abort && tid == 0 && a.status) atomicExch(a.status, 2);
   tc::fence_before_sync();
   __syncthreads();

@@ -260,3 +260,30 @@ def random_rays(
         "sensor_idx": sensor[:, None].long(),
         "is_lidar": is_lidar[:, None],
     }
+
+
+def make_rgb_decoder_params(seed: int = 0, in_dim: int = 48, hidden: int = 32, upsample: int = 3, device="cpu",
+                            prefix: str = "rgb_decoder") -> Dict[str, torch.Tensor]:
+    """Random-init NeuRADModel.rgb_decoder parameters under the reference's state_dict keys (models/neurad.py:201-216,
+    model_components/cnns.py:35-46): torch's default Conv2d init bounds, BatchNorm affine / running statistics
+    randomised so that the eval-mode folding is exercised.  Synthetic data for the bench and the tests."""
+    g = torch.Generator().manual_seed(seed)
+
+    def conv(co, ci, k, gain=1.0):
+        bound = 1.0 / (ci * k * k) ** 0.5
+        return (torch.rand(co, ci, k, k, generator=g) * 2 - 1) * bound * gain, (torch.rand(co, generator=g) * 2 - 1) * bound
+
+    p: Dict[str, torch.Tensor] = {}
+    p[f"{prefix}.0.weight"], p[f"{prefix}.0.bias"] = conv(hidden, in_dim, 1)
+    for blk in (2, 3, 5, 6):
+        for c, b in ((0, 1), (3, 4)):
+            p[f"{prefix}.{blk}.main_branch.{c}.weight"], p[f"{prefix}.{blk}.main_branch.{c}.bias"] = conv(hidden, hidden, 7, 1.7)
+            p[f"{prefix}.{blk}.main_branch.{b}.weight"] = torch.rand(hidden, generator=g) * 0.8 + 0.6
+            p[f"{prefix}.{blk}.main_branch.{b}.bias"] = torch.randn(hidden, generator=g) * 0.1
+            p[f"{prefix}.{blk}.main_branch.{b}.running_mean"] = torch.randn(hidden, generator=g) * 0.1
+            p[f"{prefix}.{blk}.main_branch.{b}.running_var"] = torch.rand(hidden, generator=g) * 0.5 + 0.25
+    bound = 1.0 / (hidden * upsample * upsample) ** 0.5
+    p[f"{prefix}.4.weight"] = (torch.rand(hidden, hidden, upsample, upsample, generator=g) * 2 - 1) * bound * 3
+    p[f"{prefix}.4.bias"] = (torch.rand(hidden, generator=g) * 2 - 1) * bound
+    p[f"{prefix}.7.weight"], p[f"{prefix}.7.bias"] = conv(3, hidden, 1)
+    return {k: v.to(device) for k, v in p.items()}
