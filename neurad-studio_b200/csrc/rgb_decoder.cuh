@@ -16,9 +16,16 @@
 // shared memory as 8 planes [chunk][row][pixel][16 B]; in that layout the A operand of tap (dy,dx) for output row r is
 // the SAME planes read from a shifted start address ((r+dy)*PW + dx)*16 B -- the canonical K-major no-swizzle UMMA
 // layout with SBO = 128 B (8-pixel groups are contiguous) and LBO = the plane stride -- so the im2col matrix is never
-// materialised.  The folded weights of one tap row (7 taps x {hi,lo} x 32x32 bf16 = 28 KB, pre-arranged in the UMMA B
-// layout by dec_fold_conv_kernel) are double-buffered in shared memory and streamed from L2 while the tensor core works
-// on the previous tap row.
+// materialised.  The folded weights of one tap COLUMN dx ({hi,lo} x 7 taps x 32x32 bf16 = 28 KB, pre-arranged in the
+// UMMA B layout by dec_fold_conv_kernel) are double-buffered in shared memory and streamed from L2 while the tensor
+// core works on the previous column.
+//
+// Shared-memory bandwidth, not the tensor pipe, bounds an SS-mode MMA this narrow (128 x 32 x 16: 4 KB of A per 65 k
+// MAC), so the loop is arranged to read each A block once for ALL the output rows it feeds: input row i at shift dx
+// contributes to output row r through tap dy = i - r, for up to three r at once.  With the three accumulators side by
+// side in TMEM ([D0|D1|D2], 32 columns each) and the tap tiles stored in descending dy, that is ONE MMA with N = 96
+// (N = 32/64 at the window's top and bottom rows): 378 MMAs per tile instead of 882, ~2.5 MB instead of 4.5 MB of
+// operand reads.  The accumulators start from the folded bias (written with tcgen05.st), every MMA accumulates.
 #pragma once
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
@@ -39,7 +46,7 @@ constexpr int kIR = kTH + 2 * kPad;
 constexpr int kPlaneBytes = kIR * kPW * 16 + 16;  // +16: consecutive planes start 4 banks apart (conflict-free fills)
 constexpr int kActBytes = 8 * kPlaneBytes;
 constexpr int kWTileBytes = kC * kC * 2;                 // one 32x32 bf16 B tile
-constexpr int kWRowBytes = kK7 * 2 * kWTileBytes;        // one tap row: 7 taps x {hi, lo}
+constexpr int kWRowBytes = kK7 * 2 * kWTileBytes;        // one tap column: {hi, lo} x 7 taps (dy descending)
 constexpr int kConvThreads = 256;
 constexpr int kTmemCols = 128;                           // kTH accumulators x 32 columns, power of two
 static_assert(kTH * kC <= kTmemCols, "accumulators do not fit the TMEM allocation");
@@ -98,8 +105,9 @@ __device__ __forceinline__ void load_act(const uint4* src, float* v) {
 // ---------------------------------------------------------------------------------------- parameter preparation
 // Conv2d [co][ci][7][7] + BatchNorm2d (eval) -> folded  w' = w * s[co],  b' = (b - mean) * s + beta,  s = gamma /
 // sqrt(var + eps)  (BasicBlock.main_branch, cnns.py:37-43), written as
-//   w_img : [dy][dx][hi|lo] 32x32 bf16 tiles in the UMMA K-major no-swizzle B layout (n = co, k = ci):
-//           byte offset of (n,k) = (n/8)*512 + (k/8)*128 + (n%8)*16 + (k%8)*2
+//   w_img : [dx][hi|lo][6 - dy] 32x32 bf16 tiles in the UMMA K-major no-swizzle B layout (n = co, k = ci):
+//           byte offset of (n,k) = (n/8)*512 + (k/8)*128 + (n%8)*16 + (k%8)*2.  Tiles of one tap COLUMN are contiguous
+//           in DESCENDING dy, so that [W(dy), W(dy-1), W(dy-2)] is one N = 96 B operand (see dec_conv7_tc_kernel)
 //   w_f32 : [dy][dx][ci][co] fp32 (CUDA-core reference kernel)
 //   bias  : [co]
 __global__ void dec_fold_conv_kernel(const float* __restrict__ w, const float* __restrict__ b, const float* __restrict__ gamma,
@@ -118,9 +126,10 @@ __global__ void dec_fold_conv_kernel(const float* __restrict__ w, const float* _
   __nv_bfloat16 hi, lo;
   split_bf16(v, hi, lo);
   const int off = (co >> 3) * 512 + (ci >> 3) * 128 + (co & 7) * 16 + (ci & 7) * 2;
-  unsigned char* tile = w_img + (size_t)tap * 2 * kWTileBytes;
+  const int dy = tap / kK7, dx = tap % kK7;
+  unsigned char* tile = w_img + (size_t)dx * kWRowBytes + (size_t)(kK7 - 1 - dy) * kWTileBytes;
   *reinterpret_cast<__nv_bfloat16*>(tile + off) = hi;
-  *reinterpret_cast<__nv_bfloat16*>(tile + kWTileBytes + off) = lo;
+  *reinterpret_cast<__nv_bfloat16*>(tile + kK7 * kWTileBytes + off) = lo;
 }
 
 // ------------------------------------------------------------------------------------- 1x1 input conv + ReLU
@@ -280,12 +289,23 @@ __device__ __forceinline__ void cp_async16(uint32_t dst_smem, const void* src, u
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
+// this thread's TMEM lane, 32 accumulator columns <- the folded bias
+__device__ __forceinline__ void arm_accumulator(uint32_t taddr, const float* bias) {
+#pragma unroll
+  for (int c = 0; c < kC; c += 8) {
+    uint32_t v[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v[k] = __float_as_uint(bias[c + k]);
+    tc::tmem_st8(taddr + (uint32_t)c, v);
+  }
+}
+
 struct ConvArgs {
   const uint4* in;        // ACT [B][H][W]
   const uint4* residual;  // ACT (EPI_RES_*) or nullptr
   uint4* out_act;         // ACT or nullptr
   float* out_rgb;         // [B][H][W][3] (EPI_RES_RELU_RGB)
-  const unsigned char* w_img;  // [7][kWRowBytes]
+  const unsigned char* w_img;  // [7 dx][kWRowBytes]
   const float* w_f32;     // [49][ci][co]
   const float* bias;      // [32] folded
   const float* out_w;     // [3][32] (EPI_RES_RELU_RGB)
@@ -323,7 +343,6 @@ __global__ void __launch_bounds__(kConvThreads, 1) dec_conv7_tc_kernel(const Con
   const uint32_t act_u32 = tc::smem_u32(S.act);
   const uint32_t w_u32[2] = {tc::smem_u32(S.w[0]), tc::smem_u32(S.w[1])};
   constexpr uint32_t kDescHiA = (128u >> 4) | (1u << 14), kDescHiB = (512u >> 4) | (1u << 14);  // bits [32,64)
-  constexpr uint32_t kIdesc = idesc_bf16(kStrip, kC);
   uint32_t parity[2] = {0u, 0u};
 
   const int tiles_x = (a.W + kStrip - 1) / kStrip, tiles_y = (a.H + kTH - 1) / kTH;
@@ -346,6 +365,8 @@ __global__ void __launch_bounds__(kConvThreads, 1) dec_conv7_tc_kernel(const Con
     for (int i = tid; i < kWRowBytes / 16; i += kConvThreads) cp_async16(w_u32[0] + (uint32_t)(i * 16), src + i, 16u);
   };
   if ((int64_t)blockIdx.x < n_tiles) issue_tile_loads(blockIdx.x);
+  for (int r = warp >> 2; r < kTH; r += 2) arm_accumulator(tmem + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)(r * kC), S.bias);
+  tc::wait_st();
   for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     const int tx = (int)(tile % tiles_x), ty = (int)((tile / tiles_x) % tiles_y);
     const int64_t img = tile / ((int64_t)tiles_x * tiles_y);
@@ -354,54 +375,56 @@ __global__ void __launch_bounds__(kConvThreads, 1) dec_conv7_tc_kernel(const Con
     tc::fence_async_smem();  // generic-proxy writes -> visible to the tensor core (async proxy)
     tc::fence_before_sync();
     __syncthreads();
-    for (int dy = 0; dy < kK7; ++dy) {
-      const int buf = dy & 1;
+    for (int dx = 0; dx < kK7; ++dx) {
+      const int buf = dx & 1, nb = buf ^ 1;
       if (warp == 0) {
-        // The whole (converged) warp walks the tap loop so that every descriptor is a warp-uniform value the compiler
-        // keeps in uniform registers -- tcgen05.mma takes its operands from there; built inside a single-thread branch
-        // each MMA pays a register->uniform broadcast loop -- and one elected lane issues.
+        // The whole (converged) warp walks the loop so that every descriptor is a warp-uniform value the compiler keeps
+        // in uniform registers -- tcgen05.mma takes its operands from there; built inside a single-thread branch each
+        // MMA pays a register->uniform broadcast loop -- and one elected lane issues.
         tc::fence_after_sync();
         const uint32_t leader = elect_one();
-#pragma unroll 1
-        for (int r = 0; r < kTH; ++r) {
-          const uint32_t d = tmem + (uint32_t)(r * kC);
-          const uint32_t a_row = a_lo32 + (uint32_t)((r + dy) * kPW);  // descriptor low words advance in 16-byte units
 #pragma unroll
-          for (int dx = 0; dx < kK7; ++dx) {
+        for (int i = 0; i < kIR; ++i) {  // input row i feeds output rows r_min..r_max through taps dy = i - r
+          constexpr int kLast = kK7 - 1;
+          const int r_min = i > kLast ? i - kLast : 0, r_max = i < kTH - 1 ? i : kTH - 1, nr = r_max - r_min + 1;
+          const uint32_t d = tmem + (uint32_t)(r_min * kC);
+          const uint32_t idesc = idesc_bf16(kStrip, kC * nr);
+          const uint32_t slot = (uint32_t)(kLast - (i - r_min));  // first (largest-dy) tile of the N-concatenated B
 #pragma unroll
-            for (int ks = 0; ks < 2; ++ks) {  // 16 input channels (two 8-channel chunks) per MMA
-              const uint32_t ah = a_row + (uint32_t)(dx + 2 * ks * (kPlaneBytes / 16));
-              const uint32_t al = ah + (uint32_t)(4 * (kPlaneBytes / 16));
-              const uint32_t bh = b_lo32[buf] + (uint32_t)((dx * 2 * kWTileBytes + ks * 256) / 16);
-              const uint32_t bl = bh + (uint32_t)(kWTileBytes / 16);
-              if (leader) {
-                mma_bf16_ss(d, make_desc(ah, kDescHiA), make_desc(bh, kDescHiB), kIdesc, (dy | dx | ks) != 0);
-                mma_bf16_ss(d, make_desc(al, kDescHiA), make_desc(bh, kDescHiB), kIdesc, 1);
-                mma_bf16_ss(d, make_desc(ah, kDescHiA), make_desc(bl, kDescHiB), kIdesc, 1);
-              }
+          for (int ks = 0; ks < 2; ++ks) {  // 16 input channels (two 8-channel chunks) per MMA
+            const uint32_t ah = a_lo32 + (uint32_t)(i * kPW + 2 * ks * (kPlaneBytes / 16)) + (uint32_t)dx;
+            const uint32_t al = ah + (uint32_t)(4 * (kPlaneBytes / 16));
+            const uint32_t bh = b_lo32[buf] + (slot * kWTileBytes + (uint32_t)(ks * 256)) / 16;
+            const uint32_t bl = bh + (uint32_t)(kK7 * kWTileBytes / 16);
+            if (leader) {
+              mma_bf16_ss(d, make_desc(ah, kDescHiA), make_desc(bh, kDescHiB), idesc, 1);
+              mma_bf16_ss(d, make_desc(al, kDescHiA), make_desc(bh, kDescHiB), idesc, 1);
+              mma_bf16_ss(d, make_desc(ah, kDescHiA), make_desc(bl, kDescHiB), idesc, 1);
             }
           }
         }
         if (leader) tc::mma_commit(&S.bar[buf]);
         __syncwarp();
-      }
-      if (dy + 1 < kK7) {
-        const int nb = buf ^ 1;
-        if (dy >= 1) {  // the MMAs of tap row dy-1 read w[nb]: wait for them before overwriting it
+        if (dx >= 1 && dx + 1 < kK7) parity[nb] ^= 1u;  // keep the phase bookkeeping of the loading warps
+      } else if (dx + 1 < kK7) {
+        // warps 1..7 stream the next tap column while warp 0 is busy issuing
+        if (dx >= 1) {  // the MMAs of column dx-1 read w[nb]: wait for them before overwriting it
           if (!bar_wait(&S.bar[nb], parity[nb])) S.abort = 1;
           parity[nb] ^= 1u;
         }
-        const uint4* src = reinterpret_cast<const uint4*>(a.w_img + (size_t)(dy + 1) * kWRowBytes);
-        for (int i = tid; i < kWRowBytes / 16; i += kConvThreads) cp_async16(w_u32[nb] + (uint32_t)(i * 16), src + i, 16u);
+        const uint4* src = reinterpret_cast<const uint4*>(a.w_img + (size_t)(dx + 1) * kWRowBytes);
+        for (int i = tid - 32; i < kWRowBytes / 16; i += kConvThreads - 32) cp_async16(w_u32[nb] + (uint32_t)(i * 16), src + i, 16u);
         cp_async_wait_all();
         tc::fence_async_smem();
+      }
+      if (dx + 1 < kK7) {
         tc::fence_before_sync();
         __syncthreads();
         if (S.abort) break;
       }
     }
     if (S.abort) break;
-    // tap rows 5 (bar[1]) and 6 (bar[0]) are still outstanding; the commit of row 6 covers every earlier MMA
+    // tap columns 5 (bar[1]) and 6 (bar[0]) are still outstanding; the commit of column 6 covers every earlier MMA
     if (!bar_wait(&S.bar[1], parity[1])) S.abort = 1;
     parity[1] ^= 1u;
     if (!bar_wait(&S.bar[0], parity[0])) S.abort = 1;
@@ -418,15 +441,17 @@ __global__ void __launch_bounds__(kConvThreads, 1) dec_conv7_tc_kernel(const Con
       tc::tmem_ld16(lane_base + (uint32_t)(r * kC), dreg);
       tc::tmem_ld16(lane_base + (uint32_t)(r * kC + 16), dreg + 16);
       tc::wait_ld();
+      arm_accumulator(lane_base + (uint32_t)(r * kC), S.bias);  // folded bias: the next tile's MMAs all accumulate
       const int y = y0 + r, x = x0 + m;
       if (y < a.H && x < a.W) {
         float acc[kC];
 #pragma unroll
-        for (int k = 0; k < kC; ++k) acc[k] = __uint_as_float(dreg[k]) + S.bias[k];
+        for (int k = 0; k < kC; ++k) acc[k] = __uint_as_float(dreg[k]);
         const int64_t pix = (img * a.H + y) * a.W + x;
         conv_epilogue<EPI>(acc, a.residual, pix, a.out_act, a.out_rgb, S.out_w, S.out_b);
       }
     }
+    tc::wait_st();
     tc::fence_before_sync();
     __syncthreads();  // accumulators and the input window are free again
     tc::fence_after_sync();

@@ -2,8 +2,8 @@
 (neurad-studio_b200/csrc/rgb_decoder.cuh).  tcgen05 cannot run here, but the address arithmetic can: the model reads
 the A / B operands through the canonical K-major no-swizzle descriptor rule
     element (row, k) of a bf16 operand = start + (row/8)*SBO + (k/8)*LBO + (row%8)*16 + (k%8)*2   [bytes]
-exactly as the kernel programs them (plane-shifted activation windows, folded weight tiles), accumulates the same MMA
-sequence, and must reproduce torch's conv2d.  Integer-valued data keeps every product exact."""
+exactly as the kernel programs them (plane-shifted activation windows, tap-column weight images with the tiles of one
+column in descending dy so that up to three taps form one N = 96 operand), accumulates the same MMA sequence, and must reproduce torch's conv2d.  Integer-valued data keeps every product exact."""
 import numpy as np
 import torch
 import torch.nn.functional as F
@@ -24,7 +24,8 @@ def fold_image(w):
         for ci in range(C):
             for tap in range(K7 * K7):
                 off = (co >> 3) * 512 + (ci >> 3) * 128 + (co & 7) * 16 + (ci & 7) * 2
-                view[(tap * 2 * WTILE + off) // 2] = wb[co, ci, tap // K7, tap % K7]
+                dy, dx = tap // K7, tap % K7
+                view[(dx * WROW + (K7 - 1 - dy) * WTILE + off) // 2] = wb[co, ci, dy, dx]
     return img
 
 
@@ -59,17 +60,17 @@ def test_conv7_descriptor_walk_reproduces_conv2d():
                     for c in range(4):  # hi chunks; lo planes (4..7) stay zero
                         base = (c * PLANE + (ir * PW + ip) * 16) // 2
                         av[base:base + 8] = xb[y, xx, 8 * c:8 * c + 8]
+        d = np.zeros((STRIP, TH * C), dtype=np.float64)  # [D0 | D1 | D2] side by side, as in TMEM
+        for dx in range(K7):
+            wcol = w_img[dx * WROW:(dx + 1) * WROW]
+            for i in range(IR):  # input row i feeds output rows r_min..r_max through taps dy = i - r
+                r_min, r_max = max(0, i - (K7 - 1)), min(TH - 1, i)
+                nr = r_max - r_min + 1
+                slot = (K7 - 1) - (i - r_min)
+                for ks in range(2):
+                    a = operand(act, 2 * ks * PLANE + (i * PW + dx) * 16, PLANE, 128, STRIP)
+                    b = operand(wcol, slot * WTILE + ks * 256, 128, 512, C * nr)  # N = 32 * nr: concatenated tap tiles
+                    d[:, r_min * C:(r_max + 1) * C] += a.astype(np.float64) @ b.astype(np.float64).T
         for r in range(TH):
-            if y0 + r >= H:
-                continue
-            d = np.zeros((STRIP, C), dtype=np.float64)
-            for dy in range(K7):
-                wrow = w_img[dy * WROW:(dy + 1) * WROW]
-                for dx in range(K7):
-                    a_off = ((r + dy) * PW + dx) * 16
-                    wh = dx * 2 * WTILE
-                    for ks in range(2):
-                        a = operand(act, 2 * ks * PLANE + a_off, PLANE, 128, STRIP)
-                        b = operand(wrow, wh + ks * 256, 128, 512, C)
-                        d += a.astype(np.float64) @ b.astype(np.float64).T
-            assert np.array_equal(d[:W], ref[y0 + r].astype(np.float64)), (y0, r)
+            if y0 + r < H:
+                assert np.array_equal(d[:W, r * C:(r + 1) * C], ref[y0 + r].astype(np.float64)), (y0, r)
