@@ -304,8 +304,9 @@ int64_t b200nerf_rgb_decode_workspace_bytes(int batch, int height, int width);
 /* The camera half of NeuRADModel.decode_features (models/neurad.py:359-366): features [batch, height, width, in_dim]
  * (= the row-major ray order of b200nerf_nff_render_fwd's `features` output, so no permute is needed) ->
  * rgb [batch, 3*height, 3*width, 3].  impl 0: the 7x7 convolutions run as implicit GEMMs on the tcgen05 tensor cores
- * (bf16 hi/lo split, fp32 accumulate, fp32-level accuracy); impl 1: the same pipeline on the CUDA cores in fp32
- * (slow cross-check of the same op). */
+ * (bf16 hi/lo split, fp32 accumulate, fp32-level accuracy), operands moved by the TMA engine; impl 2: the same with
+ * per-thread 16-byte asynchronous copies instead of TMA; impl 1: the same pipeline on the CUDA cores in fp32 (slow
+ * cross-check of the same op). */
 int b200nerf_rgb_decode_fwd(b200nerf_ctx* ctx, const float* features, int batch, int height, int width, float* rgb,
                             void* workspace, int64_t workspace_bytes, int impl, void* stream);
 

@@ -415,7 +415,8 @@ class B200Backend:
 
     def rgb_decode(self, features: torch.Tensor, impl: str = "tc", out: Optional[torch.Tensor] = None) -> torch.Tensor:
         """Camera half of NeuRADModel.decode_features (neurad.py:359-366): features [B,H,W,C] (or [H,W,C]) ->
-        rgb [B,3H,3W,3].  impl "tc": tcgen05 implicit-GEMM convolutions; "ref": CUDA-core fp32 cross-check."""
+        rgb [B,3H,3W,3].  impl "tc": tcgen05 implicit-GEMM convolutions with TMA operand loads; "tc_ldgsts": the same
+        with per-thread cp.async loads; "ref": CUDA-core fp32 cross-check."""
         f = self._dev(features)
         if f.dim() == 3:
             f = f[None]
@@ -430,7 +431,7 @@ class B200Backend:
         if rgb.shape != (b, 3 * h, 3 * w, 3) or not rgb.is_contiguous() or rgb.dtype != torch.float32 or rgb.device != f.device:
             raise _lib.B200NerfError("rgb_decode: `out` must be a contiguous fp32 [B,3H,3W,3] tensor on the backend's device")
         self._check(self.lib.b200nerf_rgb_decode_fwd(self._h, _ptr(f), b, h, w, _ptr(rgb), _ptr(ws), ws.numel(),
-                                                     {"tc": 0, "ref": 1}[impl], self._stream))
+                                                     {"tc": 0, "ref": 1, "tc_ldgsts": 2}[impl], self._stream))
         return rgb
 
     # ------------------------------------------------------------------------------------------- ray generation

@@ -1374,6 +1374,32 @@ inline DecSmall dec_small(float* base) {
   return d;
 }
 inline int64_t act_bytes(int64_t pixels) { return pixels * 128; }
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time dependency on libcuda)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+inline EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+  }
+  return fn;
+}
+// ACT buffer [batch][H][W][8 chunks][8 bf16] as a 5-D tensor; one copy = one chunk plane of a (kIR x kPW)-pixel window
+inline bool act_window_map(CUtensorMap* map, const void* act, int batch, int H, int W) {
+  EncodeTiledFn enc = encode_tiled_fn();
+  if (!enc) return false;
+  const cuuint64_t dims[5] = {8, 8, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)batch};
+  const cuuint64_t strides[4] = {16, 128, (cuuint64_t)W * 128, (cuuint64_t)H * W * 128};
+  const cuuint32_t box[5] = {8, 1, (cuuint32_t)dec::kPW, (cuuint32_t)dec::kIR, 1};
+  const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  return enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(act), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+             CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
 }  // namespace
 
 int b200nerf_set_rgb_decoder(b200nerf_ctx* c, const b200nerf_rgb_decoder_params* p) {
@@ -1395,6 +1421,9 @@ int b200nerf_set_rgb_decoder(b200nerf_ctx* c, const b200nerf_rgb_decoder_params*
     CUDA_TRY(cudaFuncSetAttribute(dec::dec_conv7_tc_kernel<dec::EPI_RELU>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(dec::ConvSmem)));
     CUDA_TRY(cudaFuncSetAttribute(dec::dec_conv7_tc_kernel<dec::EPI_RES_RELU>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(dec::ConvSmem)));
     CUDA_TRY(cudaFuncSetAttribute(dec::dec_conv7_tc_kernel<dec::EPI_RES_RELU_RGB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(dec::ConvSmem)));
+    CUDA_TRY(cudaFuncSetAttribute(dec::dec_conv7_tma_kernel<dec::EPI_RELU>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(dec::ConvSmem)));
+    CUDA_TRY(cudaFuncSetAttribute(dec::dec_conv7_tma_kernel<dec::EPI_RES_RELU>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(dec::ConvSmem)));
+    CUDA_TRY(cudaFuncSetAttribute(dec::dec_conv7_tma_kernel<dec::EPI_RES_RELU_RGB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(dec::ConvSmem)));
   }
   for (int b = 0; b < 4; ++b)
     for (int k = 0; k < 2; ++k) {
@@ -1429,7 +1458,7 @@ int b200nerf_rgb_decode_fwd(b200nerf_ctx* c, const float* features, int batch, i
                             void* workspace, int64_t workspace_bytes, int impl, void* stream) {
   REQUIRE(c, "ctx is NULL");
   REQUIRE(batch >= 0 && height >= 0 && width >= 0, "negative image shape");
-  REQUIRE(impl == 0 || impl == 1, "impl: 0 = tcgen05 (bf16x3), 1 = CUDA-core fp32 cross-check");
+  REQUIRE(impl >= 0 && impl <= 2, "impl: 0 = tcgen05 + TMA loads, 1 = CUDA-core fp32 cross-check, 2 = tcgen05 + LDGSTS loads");
   if (!c->have_rgb_decoder) return fail(B200NERF_ERR_STATE, "set_rgb_decoder was not called");
   if (batch == 0 || height == 0 || width == 0) return 0;
   REQUIRE(features && rgb && workspace, "NULL argument");
@@ -1454,6 +1483,16 @@ int b200nerf_rgb_decode_fwd(b200nerf_ctx* c, const float* features, int batch, i
     a.out_w = d.out_w; a.out_b = d.out_b;
     a.batch = batch; a.H = H; a.W = W; a.status = c->d_status;
     if (impl == 0) {
+      dec::ConvArgsTma t{};
+      t.a = a;
+      if (!act_window_map(&t.in_map, in, batch, H, W)) return fail(B200NERF_ERR_CUDA, "cuTensorMapEncodeTiled failed for the decoder's input window");
+      const int64_t tiles = (int64_t)batch * ((H + dec::kTH - 1) / dec::kTH) * ((W + dec::kStrip - 1) / dec::kStrip);
+      const int grid = (int)(tiles < c->sm_count ? tiles : c->sm_count);
+      const size_t smem = sizeof(dec::ConvSmem);
+      if (epi == dec::EPI_RELU) dec::dec_conv7_tma_kernel<dec::EPI_RELU><<<grid, dec::kConvThreads, smem, st>>>(t);
+      else if (epi == dec::EPI_RES_RELU) dec::dec_conv7_tma_kernel<dec::EPI_RES_RELU><<<grid, dec::kConvThreads, smem, st>>>(t);
+      else dec::dec_conv7_tma_kernel<dec::EPI_RES_RELU_RGB><<<grid, dec::kConvThreads, smem, st>>>(t);
+    } else if (impl == 2) {
       const int64_t tiles = (int64_t)batch * ((H + dec::kTH - 1) / dec::kTH) * ((W + dec::kStrip - 1) / dec::kStrip);
       const int grid = (int)(tiles < c->sm_count ? tiles : c->sm_count);
       const size_t smem = sizeof(dec::ConvSmem);

@@ -27,6 +27,7 @@
 // (N = 32/64 at the window's top and bottom rows): 378 MMAs per tile instead of 882, ~2.5 MB instead of 4.5 MB of
 // operand reads.  The accumulators start from the folded bias (written with tcgen05.st), every MMA accumulates.
 #pragma once
+#include <cuda.h>
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -43,7 +44,7 @@ constexpr int kStrip = 128;      // pixels per MMA (M)
 constexpr int kPW = kStrip + 2 * kPad;
 constexpr int kTH = 3;           // output rows per tile
 constexpr int kIR = kTH + 2 * kPad;
-constexpr int kPlaneBytes = kIR * kPW * 16 + 16;  // +16: consecutive planes start 4 banks apart (conflict-free fills)
+constexpr int kPlaneBytes = (kIR * kPW * 16 + 127) / 128 * 128;  // TMA destinations are 128-byte aligned
 constexpr int kActBytes = 8 * kPlaneBytes;
 constexpr int kWTileBytes = kC * kC * 2;                 // one 32x32 bf16 B tile
 constexpr int kWRowBytes = kK7 * 2 * kWTileBytes;        // one tap column: {hi, lo} x 7 taps (dy descending)
@@ -57,7 +58,10 @@ struct ConvSmem {
   float bias[kC];
   float out_w[3 * kC];
   float out_b[4];
-  alignas(8) uint64_t bar[2];
+  alignas(8) uint64_t bar[2];      // MMA completion per weight buffer
+  alignas(8) uint64_t bar_w[2];    // TMA kernel: weight column landed in w[b]
+  alignas(8) uint64_t bar_win;     // TMA kernel: input window landed
+  alignas(8) uint64_t bar_done;    // TMA kernel: every MMA of the tile has completed (one commit per tile)
   uint32_t tmem_base;
   volatile int abort;  // a completion barrier timed out: every thread leaves at the next block-wide sync
 };
@@ -458,6 +462,192 @@ __global__ void __launch_bounds__(kConvThreads, 1) dec_conv7_tc_kernel(const Con
     if (S.abort) break;
   }
   cp_async_wait_all();
+  if (S.abort && tid == 0 && a.status) atomicExch(a.status, 2);
+  tc::fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tc::tmem_dealloc(tmem, kTmemCols);
+}
+
+// ---------------------------------------------------------------- 7x7 conv on the tensor cores, TMA operand loads
+// Same tile loop and MMA schedule as dec_conv7_tc_kernel, but the operands are moved by the TMA engine instead of
+// 16-byte LDGSTS issued by every thread (9 648 per tile: the LSU issue alone cost ~11 k cycles per tile):
+//   * the input window is 8 tensor copies (one per chunk plane) from a 5-D tensor map over the ACT buffer
+//     [image][y][x][chunk][8 bf16] with box (8, 1, 134, 9, 1); coordinates may be negative / beyond the image, the TMA
+//     zero-fills, which IS the convolution's padding;
+//   * a weight column is one 28 KB bulk copy.
+// One elected lane of warp 1 is the producer, warp 0 issues the MMAs; they hand buffers to each other through mbarriers
+// (transaction-count barriers for the loads, tcgen05.commit barriers for the MMAs), so the tap-column loop has no
+// block-wide barrier at all.  All 8 warps run the epilogue.
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(tc::smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2, int c3, int c4, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5, %6}], [%7];"
+      ::"r"(dst), "l"((uint64_t)map), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4), "r"(tc::smem_u32(bar))
+      : "memory");
+}
+__device__ __forceinline__ void bulk_load(uint32_t dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes),
+               "r"(tc::smem_u32(bar))
+               : "memory");
+}
+
+struct ConvArgsTma {
+  alignas(64) CUtensorMap in_map;  // ACT input as [B][H][W][8][8 x bf16], box (8,1,kPW,kIR,1)
+  ConvArgs a;
+};
+
+template <int EPI>
+__global__ void __launch_bounds__(kConvThreads, 1) dec_conv7_tma_kernel(const __grid_constant__ ConvArgsTma P) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  ConvSmem& S = *reinterpret_cast<ConvSmem*>(smem_raw);
+  const ConvArgs& a = P.a;
+  const int tid = threadIdx.x, ln = tid & 31;
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);  // provably warp-uniform
+  if (tid < kC) S.bias[tid] = a.bias[tid];
+  if (EPI == EPI_RES_RELU_RGB) {
+    if (tid < 3 * kC) S.out_w[tid] = a.out_w[tid];
+    if (tid < 3) S.out_b[tid] = a.out_b[tid];
+  }
+  if (warp == 0) tc::tmem_alloc(&S.tmem_base, kTmemCols);
+  if (tid == 0) {
+    tc::mbar_init(&S.bar[0], 1);
+    tc::mbar_init(&S.bar[1], 1);
+    tc::mbar_init(&S.bar_w[0], 1);
+    tc::mbar_init(&S.bar_w[1], 1);
+    tc::mbar_init(&S.bar_win, 1);
+    tc::mbar_init(&S.bar_done, 1);
+    S.abort = 0;
+  }
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+  const uint32_t tmem = __shfl_sync(0xffffffffu, S.tmem_base, 0);
+  const uint32_t a_lo32 = ((tc::smem_u32(S.act) & 0x3ffffu) >> 4) | ((uint32_t)(kPlaneBytes >> 4) << 16);
+  const uint32_t b_lo32[2] = {((tc::smem_u32(S.w[0]) & 0x3ffffu) >> 4) | ((128u >> 4) << 16),
+                              ((tc::smem_u32(S.w[1]) & 0x3ffffu) >> 4) | ((128u >> 4) << 16)};
+  const uint32_t act_u32 = tc::smem_u32(S.act);
+  const uint32_t w_u32[2] = {tc::smem_u32(S.w[0]), tc::smem_u32(S.w[1])};
+  constexpr uint32_t kDescHiA = (128u >> 4) | (1u << 14), kDescHiB = (512u >> 4) | (1u << 14);  // bits [32,64)
+  constexpr uint32_t kWinBytes = 8u * kIR * kPW * 16u;
+
+  const int tiles_x = (a.W + kStrip - 1) / kStrip, tiles_y = (a.H + kTH - 1) / kTH;
+  const int64_t n_tiles = (int64_t)a.batch * tiles_y * tiles_x;
+  // per-barrier completion counters (identical in every thread): phase parity of completion #k is k & 1
+  uint32_t n_mma[2] = {0u, 0u}, n_w[2] = {0u, 0u}, n_win = 0u;
+  const bool producer_warp = warp == 1;
+
+  // producer: window of `tile` -> act planes, tap column 0 -> w[0]
+  auto issue_tile_loads = [&](int64_t tile) {
+    const int tx = (int)(tile % tiles_x), ty = (int)((tile / tiles_x) % tiles_y);
+    const int img = (int)(tile / ((int64_t)tiles_x * tiles_y));
+    mbar_expect_tx(&S.bar_win, kWinBytes);
+#pragma unroll
+    for (int c = 0; c < 8; ++c)
+      tma_load_5d(act_u32 + (uint32_t)(c * kPlaneBytes), &P.in_map, 0, c, tx * kStrip - kPad, ty * kTH - kPad, img, &S.bar_win);
+    mbar_expect_tx(&S.bar_w[0], kWRowBytes);
+    bulk_load(w_u32[0], a.w_img, kWRowBytes, &S.bar_w[0]);
+  };
+  if (producer_warp && (int64_t)blockIdx.x < n_tiles) {
+    if (elect_one()) issue_tile_loads(blockIdx.x);
+    __syncwarp();
+  }
+  for (int r = warp >> 2; r < kTH; r += 2) arm_accumulator(tmem + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)(r * kC), S.bias);
+  tc::wait_st();
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+
+  for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const int tx = (int)(tile % tiles_x), ty = (int)((tile / tiles_x) % tiles_y);
+    const int64_t img = tile / ((int64_t)tiles_x * tiles_y);
+    const int x0 = tx * kStrip, y0 = ty * kTH;
+    if (warp == 0) {
+      // ---- MMA warp: window landed, then per tap column: column landed -> 54 MMAs -> commit
+      if (!bar_wait(&S.bar_win, n_win & 1u)) S.abort = 1;
+      tc::fence_after_sync();
+      const uint32_t leader = elect_one();
+#pragma unroll 1
+      for (int dx = 0; dx < kK7; ++dx) {
+        const int buf = dx & 1;
+        if (!bar_wait(&S.bar_w[buf], (n_w[buf] + (uint32_t)(dx >> 1)) & 1u)) S.abort = 1;
+        tc::fence_after_sync();
+#pragma unroll
+        for (int i = 0; i < kIR; ++i) {  // input row i feeds output rows r_min..r_max through taps dy = i - r
+          constexpr int kLast = kK7 - 1;
+          const int r_min = i > kLast ? i - kLast : 0, r_max = i < kTH - 1 ? i : kTH - 1, nr = r_max - r_min + 1;
+          const uint32_t d = tmem + (uint32_t)(r_min * kC);
+          const uint32_t idesc = idesc_bf16(kStrip, kC * nr);
+          const uint32_t slot = (uint32_t)(kLast - (i - r_min));
+#pragma unroll
+          for (int ks = 0; ks < 2; ++ks) {
+            const uint32_t ah = a_lo32 + (uint32_t)(i * kPW + 2 * ks * (kPlaneBytes / 16)) + (uint32_t)dx;
+            const uint32_t al = ah + (uint32_t)(4 * (kPlaneBytes / 16));
+            const uint32_t bh = b_lo32[buf] + (slot * kWTileBytes + (uint32_t)(ks * 256)) / 16;
+            const uint32_t bl = bh + (uint32_t)(kK7 * kWTileBytes / 16);
+            if (leader) {
+              mma_bf16_ss(d, make_desc(ah, kDescHiA), make_desc(bh, kDescHiB), idesc, 1);
+              mma_bf16_ss(d, make_desc(al, kDescHiA), make_desc(bh, kDescHiB), idesc, 1);
+              mma_bf16_ss(d, make_desc(ah, kDescHiA), make_desc(bl, kDescHiB), idesc, 1);
+            }
+          }
+        }
+        if (leader) tc::mma_commit(&S.bar[buf]);
+        __syncwarp();
+      }
+      if (leader) tc::mma_commit(&S.bar_done);
+      __syncwarp();
+    } else if (producer_warp) {
+      // ---- producer: column dx+1 into the buffer the MMAs of column dx-1 have finished reading
+      const uint32_t leader = elect_one();
+#pragma unroll 1
+      for (int dx = 0; dx + 1 < kK7; ++dx) {
+        const int nb = (dx & 1) ^ 1;
+        if (dx >= 1 && !bar_wait(&S.bar[nb], (n_mma[nb] + (uint32_t)((dx - 1) >> 1)) & 1u)) S.abort = 1;
+        if (leader) {
+          mbar_expect_tx(&S.bar_w[nb], kWRowBytes);
+          bulk_load(w_u32[nb], a.w_img + (size_t)(dx + 1) * kWRowBytes, kWRowBytes, &S.bar_w[nb]);
+        }
+        __syncwarp();
+      }
+    }
+    // Every warp waits for the tile's ONE bar_done completion.  (A parity wait is only sound for a waiter that is at
+    // most one completion behind or ahead of the barrier, so the epilogue warps, which skip the per-column
+    // completions, get their own once-per-tile barrier; the producer and the MMA warp follow theirs one by one.)
+    if (!bar_wait(&S.bar_done, n_win & 1u)) S.abort = 1;
+    // completions of this tile: MMA barriers 4 (columns 0,2,4,6) + 3 (1,3,5); weight barriers 4 + 3; window / done 1
+    n_mma[0] += 4u; n_mma[1] += 3u; n_w[0] += 4u; n_w[1] += 3u; n_win += 1u;
+    tc::fence_after_sync();
+    // the window and both weight buffers are free: the next tile's loads fly while the accumulators are drained
+    if (producer_warp && tile + gridDim.x < n_tiles) {
+      if (elect_one()) issue_tile_loads(tile + gridDim.x);
+      __syncwarp();
+    }
+    // ---- epilogue: warps 0-3 take output rows 0 and 2, warps 4-7 row 1; a thread owns one pixel (= TMEM lane)
+    const uint32_t lane_base = tmem + ((uint32_t)(32 * (warp & 3)) << 16);
+    const int m = 32 * (warp & 3) + ln;
+    for (int r = warp >> 2; r < kTH; r += 2) {
+      uint32_t dreg[kC];
+      tc::tmem_ld16(lane_base + (uint32_t)(r * kC), dreg);
+      tc::tmem_ld16(lane_base + (uint32_t)(r * kC + 16), dreg + 16);
+      tc::wait_ld();
+      arm_accumulator(lane_base + (uint32_t)(r * kC), S.bias);  // folded bias: the next tile's MMAs all accumulate
+      const int y = y0 + r, x = x0 + m;
+      if (y < a.H && x < a.W) {
+        float acc[kC];
+#pragma unroll
+        for (int k = 0; k < kC; ++k) acc[k] = __uint_as_float(dreg[k]);
+        const int64_t pix = (img * a.H + y) * a.W + x;
+        conv_epilogue<EPI>(acc, a.residual, pix, a.out_act, a.out_rgb, S.out_w, S.out_b);
+      }
+    }
+    tc::wait_st();
+    tc::fence_before_sync();
+    __syncthreads();  // accumulators re-armed and drained by everyone before the next tile's MMAs
+    tc::fence_after_sync();
+    if (S.abort) break;
+  }
   if (S.abort && tid == 0 && a.status) atomicExch(a.status, 2);
   tc::fence_before_sync();
   __syncthreads();

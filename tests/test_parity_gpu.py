@@ -590,7 +590,7 @@ def _decoder_golden():
     return g["param"], g["in"]["features"], g["ref"]["rgb"]
 
 
-@pytest.mark.parametrize("impl", ["ref", "tc"])
+@pytest.mark.parametrize("impl", ["ref", "tc", "tc_ldgsts"])
 def test_rgb_decoder_matches_reference_golden(backend, impl):
     """NeuRADModel.rgb_decoder (1x1 conv, 4 BasicBlocks with BatchNorm, 3x transposed conv, 1x1 conv + sigmoid) on the
     reference's own output for a 2 x 19 x 45 feature image: CUDA-core fp32 pipeline and tcgen05 (bf16 hi/lo split)
@@ -623,6 +623,9 @@ def test_rgb_decoder_tensor_core_multi_tile(backend):
     assert (ref_k.cpu() - ref).abs().max().item() < 1e-4
     assert (tc.cpu() - ref).abs().max().item() < 1e-4
     assert torch.equal(tc, backend.rgb_decode(feats, "tc"))  # deterministic
+    backend.check_status()
+    assert torch.equal(tc, backend.rgb_decode(feats, "tc_ldgsts"))  # TMA and per-thread async copies feed the same MMAs
+    backend.check_status()
     # a single image given as [H,W,C] and batch-composition independence
     one = backend.rgb_decode(feats[1], "tc")
     assert torch.equal(one[0], tc[1])

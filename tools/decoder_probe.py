@@ -11,12 +11,12 @@ reps = int(sys.argv[4]) if len(sys.argv) > 4 else 3
 be = B200Backend(torch.device("cuda", 0))
 be.set_rgb_decoder(D.random_decoder_params(seed=1))
 feats = torch.randn(B, H, W, 48, device="cuda") * 0.7
-for impl in (["tc", "ref"] if os.environ.get("DEC_REF", "1") == "1" else ["tc"]):
+for impl in os.environ.get("DEC_IMPLS", "tc,tc_ldgsts,ref").split(","):
     out = be.rgb_decode(feats, impl)
     torch.cuda.synchronize()
     be.check_status()
     ts = []
-    for _ in range(reps if impl == "tc" else 1):
+    for _ in range(reps if impl != "ref" else 1):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(); out = be.rgb_decode(feats, impl); e1.record(); torch.cuda.synchronize()
         ts.append(e0.elapsed_time(e1))
