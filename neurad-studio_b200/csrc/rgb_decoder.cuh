@@ -12,7 +12,7 @@
 // pass (bf16 runs at twice the TF32 rate) and needs exactly the bytes of fp32 storage.
 //
 // Activations between layers therefore live in HBM already split ("ACT" layout): per pixel 128 B = 8 chunks of 8 bf16,
-// chunk c < 4: hi of channels 8c..8c+7, chunk 4+c: lo.  A conv CTA copies a (3+6) x (128+6) pixel window of it into
+// chunk c < 4: hi of channels 8c..8c+7, chunk 4+c: lo.  A conv CTA copies a (4+6) x (128+6) pixel window of it into
 // shared memory as 8 planes [chunk][row][pixel][16 B]; in that layout the A operand of tap (dy,dx) for output row r is
 // the SAME planes read from a shifted start address ((r+dy)*PW + dx)*16 B -- the canonical K-major no-swizzle UMMA
 // layout with SBO = 128 B (8-pixel groups are contiguous) and LBO = the plane stride -- so the im2col matrix is never
@@ -22,10 +22,10 @@
 //
 // Shared-memory bandwidth, not the tensor pipe, bounds an SS-mode MMA this narrow (128 x 32 x 16: 4 KB of A per 65 k
 // MAC), so the loop is arranged to read each A block once for ALL the output rows it feeds: input row i at shift dx
-// contributes to output row r through tap dy = i - r, for up to three r at once.  With the three accumulators side by
-// side in TMEM ([D0|D1|D2], 32 columns each) and the tap tiles stored in descending dy, that is ONE MMA with N = 96
-// (N = 32/64 at the window's top and bottom rows): 378 MMAs per tile instead of 882, ~2.5 MB instead of 4.5 MB of
-// operand reads.  The accumulators start from the folded bias (written with tcgen05.st), every MMA accumulates.
+// contributes to output row r through tap dy = i - r, for up to four r at once.  With the four accumulators side by
+// side in TMEM ([D0|D1|D2|D3], 32 columns each) and the tap tiles stored in descending dy, that is ONE MMA with N = 128
+// (N = 32..96 at the window's top and bottom rows): 420 MMAs per 4-row tile instead of 1176.  Measured, the operand
+// fetch sustains ~64 B/clk, which makes shared-memory bytes per MAC the bound of this kernel (profiles/).  The accumulators start from the folded bias (written with tcgen05.st), every MMA accumulates.
 #pragma once
 #include <cuda.h>
 #include <cuda_bf16.h>
@@ -42,7 +42,7 @@ constexpr int kK7 = 7, kPad = 3; // BasicBlock kernel_size / padding
 constexpr int kTaps = kK7 * kK7;
 constexpr int kStrip = 128;      // pixels per MMA (M)
 constexpr int kPW = kStrip + 2 * kPad;
-constexpr int kTH = 3;           // output rows per tile
+constexpr int kTH = 4;           // output rows per tile
 constexpr int kIR = kTH + 2 * kPad;
 constexpr int kPlaneBytes = (kIR * kPW * 16 + 127) / 128 * 128;  // TMA destinations are 128-byte aligned
 constexpr int kActBytes = 8 * kPlaneBytes;
@@ -65,6 +65,8 @@ struct ConvSmem {
   uint32_t tmem_base;
   volatile int abort;  // a completion barrier timed out: every thread leaves at the next block-wide sync
 };
+
+static_assert(sizeof(ConvSmem) <= 227 * 1024, "ConvSmem exceeds the 227 KB a CTA may opt in to");
 
 // ------------------------------------------------------------------------------------------------ bf16 split
 __device__ __forceinline__ void split_bf16(float v, __nv_bfloat16& hi, __nv_bfloat16& lo) {
@@ -437,7 +439,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) dec_conv7_tc_kernel(const Con
     // every MMA of this tile has completed: the window and both weight buffers are free, so the next tile's loads fly
     // while this tile's accumulators are drained
     if (tile + gridDim.x < n_tiles) issue_tile_loads(tile + gridDim.x);
-    // ---- epilogue: warps 0-3 take output rows 0 and 2, warps 4-7 row 1; a thread owns one pixel (= TMEM lane)
+    // ---- epilogue: warps 0-3 take output rows 0 and 2, warps 4-7 rows 1 and 3; a thread owns one pixel (= TMEM lane)
     const uint32_t lane_base = tmem + ((uint32_t)(32 * (warp & 3)) << 16);
     const int m = 32 * (warp & 3) + ln;
     for (int r = warp >> 2; r < kTH; r += 2) {
@@ -624,7 +626,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) dec_conv7_tma_kernel(const __
       if (elect_one()) issue_tile_loads(tile + gridDim.x);
       __syncwarp();
     }
-    // ---- epilogue: warps 0-3 take output rows 0 and 2, warps 4-7 row 1; a thread owns one pixel (= TMEM lane)
+    // ---- epilogue: warps 0-3 take output rows 0 and 2, warps 4-7 rows 1 and 3; a thread owns one pixel (= TMEM lane)
     const uint32_t lane_base = tmem + ((uint32_t)(32 * (warp & 3)) << 16);
     const int m = 32 * (warp & 3) + ln;
     for (int r = warp >> 2; r < kTH; r += 2) {

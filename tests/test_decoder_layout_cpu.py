@@ -8,9 +8,9 @@ import numpy as np
 import torch
 import torch.nn.functional as F
 
-C, K7, PAD, STRIP, TH = 32, 7, 3, 128, 3
+C, K7, PAD, STRIP, TH = 32, 7, 3, 128, 4
 PW, IR = STRIP + 2 * PAD, TH + 2 * PAD
-PLANE = IR * PW * 16 + 16
+PLANE = (IR * PW * 16 + 127) // 128 * 128
 WTILE = C * C * 2
 WROW = K7 * 2 * WTILE
 
@@ -44,7 +44,7 @@ def operand(buf, start, lbo, sbo, rows):
 
 def test_conv7_descriptor_walk_reproduces_conv2d():
     g = torch.Generator().manual_seed(0)
-    H, W = 5, 20
+    H, W = 6, 20
     x = torch.randint(-3, 4, (1, C, H, W), generator=g).float()
     w = torch.randint(-2, 3, (C, C, K7, K7), generator=g).float()
     ref = F.conv2d(x, w, padding=PAD)[0].permute(1, 2, 0).numpy()  # [H,W,C]
