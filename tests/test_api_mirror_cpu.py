@@ -29,3 +29,23 @@ def test_state_dict_names_and_no_cpu_path():
             model.get_nff_outputs(rb)
         with pytest.raises(RuntimeError):
             HashEncoding(num_levels=2, log2_hashmap_size=8)(torch.rand(4, 3))
+
+
+def test_rgb_decoder_mirror_has_the_reference_state_dict_keys():
+    """RGBDecoder / BasicBlock are parameter containers with the reference's module indices and names
+    (models/neurad.py:201-216, model_components/cnns.py:35-46): the keys of the reference-generated golden load
+    unchanged, and nothing computes without a CUDA device."""
+    from neurad_studio_b200 import scene
+    from neurad_studio_b200.nerfstudio_api import RGBDecoder
+
+    _, g = load_golden("rgb_decoder.npz")
+    dec = RGBDecoder(48, 32, 3)
+    sd = {k[len("rgb_decoder."):]: v for k, v in g["param"].items()}
+    missing, unexpected = dec.load_state_dict(sd, strict=False)
+    assert not unexpected and all(k.endswith("num_batches_tracked") for k in missing)
+    synth = scene.make_rgb_decoder_params(seed=1)
+    assert set(synth) == set(g["param"]) and all(synth[k].shape == g["param"][k].shape for k in synth)
+    dec.eval()
+    if not torch.cuda.is_available():
+        with pytest.raises(RuntimeError):
+            dec(g["in"]["features"])
