@@ -200,6 +200,46 @@ int b200nerf_mlp_fwd(b200nerf_ctx* ctx, const float* x, int64_t n_rows, int in_d
                      const float* const* weights_host, const float* const* biases_host, const int* out_dims_host,
                      float* y, void* stream);
 
+/* ---- module-level seams: the reference's Field / Sampler / Encoding nn.Modules as stand-alone operators ----
+ * (SURVEY.md 8b).  The fused b200nerf_nff_render_fwd never materialises a per-sample tensor; these do, because the
+ * reference's modules hand [N,S,...] tensors to each other.  They use the parameters bound with b200nerf_set_*. */
+
+/* Frustums.get_fast_isotropic_gaussian(num_multisamples=1) (cameras/rays.py:109-124): per-ray origins/directions
+ * [N,3], pixel_area [N] (already scaled), euclidean bin edges [N,S+1] -> mean [N,S,3], std [N,S]. */
+int b200nerf_isotropic_gaussian_fwd(b200nerf_ctx* ctx, const float* origins, const float* directions,
+                                    const float* pixel_area, const float* bins_e, int64_t n_rays, int n_samples,
+                                    float* mean, float* std, void* stream);
+
+/* NeuRADHashEncoding.forward(positions: GaussiansStd, times, directions) (field_components/neurad_encoding.py:150-187)
+ * of field `field`: scene contraction, static grid, dynamic-actor assignment at each ray's time, per-actor grids
+ * (zero padded to the static width), anti-aliasing rescale.  mean [N,S,3], std [N,S], times [N] (the reference
+ * reads times[:,0]; may be NULL without actors), directions [N,3] (directions_per_ray != 0) or [N,S,3] or NULL.
+ * Outputs (each optional): features [N*S, L*F]; density [N,S] = trunc_exp(density_decoder(features))
+ * (NeuRADProposalField.get_density, fields/neurad_field.py:208-213); directions_out [N,S,3] (box frame and
+ * renormalised for samples inside an actor, :203-209); actor_id [N,S] (actor index or -1). */
+int b200nerf_neurad_encoding_fwd(b200nerf_ctx* ctx, int field, const float* mean, const float* std, const float* times,
+                                 const float* directions, int directions_per_ray, int64_t n_rays, int n_samples,
+                                 float* features, float* density, float* directions_out, int32_t* actor_id,
+                                 void* stream);
+
+/* NeuRADField.forward between and after its two MLPs (fields/neurad_field.py:139-149):
+ *   mid : geo_out [P, G+1] = (sdf | geo_embedding), directions [P,3] -> mlp_feature_in [P, G+16] =
+ *         [geo_embedding | SHEncoding(4)(get_normalized_directions(d))]
+ *   tail: feature [P,G] = geo_embedding + mlp_feature_out; sdf [P] = geo_out[:,0]; alpha [P] = sigmoid(-sdf * beta)
+ *         with beta = |sdf_to_density.beta| + 1e-4 (model_components/utils.py:29-41).  sdf / alpha may be NULL.
+ * The MLPs themselves run through b200nerf_mlp_fwd (tcgen05). */
+int b200nerf_field_mid_fwd(b200nerf_ctx* ctx, const float* geo_out, const float* directions, int64_t n_points,
+                           int geo_feat_dim, float* mlp_feature_in, void* stream);
+int b200nerf_field_tail_fwd(b200nerf_ctx* ctx, const float* geo_out, const float* mlp_feature_out, int64_t n_points,
+                            int geo_feat_dim, float beta, float* feature, float* sdf, float* alpha, void* stream);
+
+/* spacing_to_euclidean_fn of a SpacedSampler (ray_samplers.py:119-120) on per-ray spacing-domain edges
+ * bins_s [N, n_edges] -> bins_e [N, n_edges]; PDFSampler's resampled bins go through it (ray_samplers.py:363-366).
+ * `kind` / power_* as in b200nerf_spaced_sample. */
+int b200nerf_spacing_to_euclidean(b200nerf_ctx* ctx, int kind, float power_lambda, float power_scaling,
+                                  const float* nears, const float* fars, const float* bins_s, int64_t n_rays,
+                                  int n_edges, float* bins_e, void* stream);
+
 /* Kernel variant used by b200nerf_nff_render_fwd:
  *   2 (default) ray-per-lane mapping (a warp = 32 adjacent rays at one sample index: coherent gathers), MLPs on the
  *     tcgen05 tensor cores with the 3xTF32 split (fp32-level accuracy, |err| ~1e-6 relative);

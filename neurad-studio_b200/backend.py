@@ -117,6 +117,9 @@ class B200Backend:
             ts += [self._dev(p[nme + ".weight"]), self._dev(p[nme + ".bias"])]
         beta = float(p["field.sdf_to_density.beta"].abs().item() + 0.0001)  # model_components/utils.py:38-41
         self._check(self.lib.b200nerf_set_main_mlps(self._h, *[_ptr(t) for t in ts], beta))
+        # the module-level NeuRADField.forward runs the same MLPs through b200nerf_mlp_fwd
+        self._field_mlps = {"geo": (ts[0:4:2], ts[1:4:2]), "feature": (ts[4::2], ts[5::2])}
+        self._beta = beta
         if "lidar_decoder.layers.0.weight" in p:
             ts = []
             for i in range(3):
@@ -317,6 +320,93 @@ class B200Backend:
         a = self._dev(alphas)
         out = torch.empty_like(a)
         self._check(self.lib.b200nerf_alpha_to_weights(self._h, _ptr(a), a.shape[0], a.shape[1], _ptr(out), self._stream))
+        return out
+
+    # ------------------------------------------------------------ module-level seams (Field / Sampler / Encoding)
+    def isotropic_gaussian(self, origins: torch.Tensor, directions: torch.Tensor, pixel_area: torch.Tensor,
+                           bins_e: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+        """Frustums.get_fast_isotropic_gaussian(1) (cameras/rays.py:109-124): per-ray origins / directions [N,3],
+        pixel_area [N], euclidean edges [N,S+1] -> (mean [N,S,3], std [N,S])."""
+        o, d = self._dev(origins).reshape(-1, 3), self._dev(directions).reshape(-1, 3)
+        a, b = self._dev(pixel_area).reshape(-1), self._dev(bins_e)
+        n, s = b.shape[0], b.shape[1] - 1
+        mean = torch.empty(n, s, 3, device=self.device)
+        std = torch.empty(n, s, device=self.device)
+        self._check(self.lib.b200nerf_isotropic_gaussian_fwd(self._h, _ptr(o), _ptr(d), _ptr(a), _ptr(b), n, s, _ptr(mean), _ptr(std), self._stream))
+        return mean, std
+
+    def neurad_encoding(self, field: int, mean: torch.Tensor, std: torch.Tensor, times: Optional[torch.Tensor],
+                        directions: Optional[torch.Tensor] = None, want_features: bool = True, want_density: bool = False,
+                        want_actor_id: bool = False) -> Dict[str, torch.Tensor]:
+        """NeuRADHashEncoding.forward (field_components/neurad_encoding.py:150-187) of the bound field `field`:
+        mean [N,S,3], std [N,S] (or [N,S,1]), times [N] (or [N,1] / [N,S,1]: the reference reads times[:,0]),
+        directions [N,3] or [N,S,3] -> {"features" [N*S,D], "directions" [N,S,3], "density" [N,S], "actor_id" [N,S]}."""
+        m = self._dev(mean)
+        n, s = m.shape[0], m.shape[1]
+        m = m.reshape(n, s, 3)
+        sd = self._dev(std).reshape(n, s)
+        t = None
+        if times is not None:
+            t = times.reshape(n, -1)[:, 0] if times.numel() != n else times.reshape(n)
+            t = self._dev(t)
+        d = per_ray = None
+        if directions is not None:
+            per_ray = directions.numel() == 3 * n and s != 1
+            d = self._dev(directions).reshape(n, 3) if per_ray else self._dev(directions).reshape(n, s, 3)
+        g = {FIELD_MAIN: self.cfg.grid, FIELD_PROP0: self.cfg.proposal_grid_1, FIELD_PROP1: self.cfg.proposal_grid_2}[field].static
+        out: Dict[str, torch.Tensor] = {}
+        f = de = do = ai = None
+        if want_features:
+            f = out["features"] = torch.empty(n * s, g.num_levels * g.hashgrid_dim, device=self.device)
+        if want_density:
+            de = out["density"] = torch.empty(n, s, device=self.device)
+        if d is not None:
+            do = out["directions"] = torch.empty(n, s, 3, device=self.device)
+        if want_actor_id:
+            ai = out["actor_id"] = torch.empty(n, s, device=self.device, dtype=torch.int32)
+        self._check(self.lib.b200nerf_neurad_encoding_fwd(self._h, field, _ptr(m), _ptr(sd), _ptr(t), _ptr(d), int(bool(per_ray)), n, s,
+                                                          _ptr(f), _ptr(de), _ptr(do), _ptr(ai), self._stream))
+        return out
+
+    def field_forward(self, mean: torch.Tensor, std: torch.Tensor, times: torch.Tensor, directions: torch.Tensor) -> Dict[str, torch.Tensor]:
+        """NeuRADField.forward (fields/neurad_field.py:128-152) on gaussians: encoding -> mlp_geo (tcgen05) ->
+        [geo_embedding | SH] -> mlp_feature (tcgen05) -> residual, sdf, alpha.  Five launches, all ours:
+        {"feature" [N,S,G], "sdf" [N,S,1], "alpha" [N,S,1]}."""
+        n, s = mean.shape[0], mean.shape[1]
+        enc = self.neurad_encoding(FIELD_MAIN, mean, std, times, directions)
+        gw, gb = self._field_mlps["geo"]
+        fw, fb = self._field_mlps["feature"]
+        geo = self.mlp_fwd(enc["features"], gw, gb)
+        h = self.mlp_fwd(self._field_mid(geo, enc["directions"]), fw, fb)
+        feature, sdf, alpha = self._field_tail(geo, h)
+        gdim = feature.shape[1]
+        return {"feature": feature.view(n, s, gdim), "sdf": sdf.view(n, s, 1), "alpha": alpha.view(n, s, 1)}
+
+    def _field_mid(self, geo: torch.Tensor, directions: torch.Tensor) -> torch.Tensor:
+        """geo_out [P,G+1], directions [P,3] -> mlp_feature's input [P,G+16] (neurad_field.py:139-141)."""
+        p, gdim = geo.shape[0], geo.shape[1] - 1
+        x2 = torch.empty(p, gdim + 16, device=self.device)
+        self._check(self.lib.b200nerf_field_mid_fwd(self._h, _ptr(geo), _ptr(self._dev(directions).reshape(p, 3)), p, gdim, _ptr(x2), self._stream))
+        return x2
+
+    def _field_tail(self, geo: torch.Tensor, h: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+        """(feature [P,G] = geo_embedding + mlp_feature_out, sdf [P], alpha [P]) (neurad_field.py:141-149)."""
+        p, gdim = geo.shape[0], geo.shape[1] - 1
+        feature = torch.empty(p, gdim, device=self.device)
+        sdf = torch.empty(p, device=self.device)
+        alpha = torch.empty(p, device=self.device)
+        self._check(self.lib.b200nerf_field_tail_fwd(self._h, _ptr(geo), _ptr(h), p, gdim, self._beta, _ptr(feature), _ptr(sdf), _ptr(alpha), self._stream))
+        return feature, sdf, alpha
+
+    def spacing_to_euclidean(self, bins_s: torch.Tensor, nears: Optional[torch.Tensor], fars: torch.Tensor, spacing: str = "power",
+                             power_lambda: float = -1.0, power_scaling: float = 0.1) -> torch.Tensor:
+        """spacing_to_euclidean_fn (ray_samplers.py:119-120) on per-ray spacing edges [N,E] -> euclidean edges [N,E]."""
+        b = self._dev(bins_s)
+        f = self._dev(fars).reshape(-1)
+        nr = None if nears is None else self._dev(nears).reshape(-1)
+        out = torch.empty_like(b)
+        self._check(self.lib.b200nerf_spacing_to_euclidean(self._h, self.SPACINGS[spacing], power_lambda, power_scaling, _ptr(nr), _ptr(f),
+                                                           _ptr(b), b.shape[0], b.shape[1], _ptr(out), self._stream))
         return out
 
     # ------------------------------------------------------------------- generic sampler / renderer operators

@@ -93,6 +93,7 @@ class NeuRADConfig:
     geo_hidden_dim: int = 32
     nff_hidden_dim: int = 32
     nff_out_dim: int = 32
+    num_multisamples: int = 1  # NeuRADFieldConfig.num_multisamples, neurad_field.py:67
     appearance_dim: int = 16
     temporal_appearance_freq: float = 1.0
     rgb_upsample_factor: int = 3

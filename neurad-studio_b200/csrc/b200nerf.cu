@@ -11,6 +11,7 @@
 #include "nff_device.h"
 #include "nff_lane.h"
 #include "rgb_decoder.cuh"
+#include "modules.cuh"
 
 using namespace nff;
 
@@ -451,6 +452,17 @@ __global__ void spaced_sample_kernel(const SpacingArgs a, const float* __restric
   const int e = (int)(i % (S + 1));
   const float u = linspace01(e, S);
   if (bins_s && ray == 0) bins_s[e] = u;
+  const float s_near = spacing_apply(a, nears ? nears[ray] : 0.0f), s_far = spacing_apply(a, fars[ray]);
+  bins_e[i] = spacing_invert(a, fadd(fmul(u, s_far), fmul(fsub(1.0f, u), s_near)));
+}
+// spacing_to_euclidean_fn (ray_samplers.py:119-120) applied to per-ray spacing-domain edges, e.g. PDFSampler's output
+// bins (ray_samplers.py:363-366): euclid = g^-1(x * g(far) + (1 - x) * g(near)).
+__global__ void spacing_to_euclidean_kernel(const SpacingArgs a, const float* __restrict__ nears, const float* __restrict__ fars,
+                                            const float* __restrict__ bins_s, int64_t n_rays, int S1, float* __restrict__ bins_e) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_rays * S1) return;
+  const int64_t ray = i / S1;
+  const float u = bins_s[i];
   const float s_near = spacing_apply(a, nears ? nears[ray] : 0.0f), s_far = spacing_apply(a, fars[ray]);
   bins_e[i] = spacing_invert(a, fadd(fmul(u, s_far), fmul(fsub(1.0f, u), s_near)));
 }
@@ -1261,27 +1273,117 @@ int b200nerf_mlp_fwd(b200nerf_ctx* c, const float* x, int64_t n_rows, int in_dim
   return 0;
 }
 
+static int make_spacing(int kind, float power_lambda, float power_scaling, SpacingArgs* a) {
+  REQUIRE(kind >= B200NERF_SPACING_UNIFORM && kind <= B200NERF_SPACING_LOG, "unknown spacing kind");
+  a->kind = kind;
+  if (kind == B200NERF_SPACING_POWER) {
+    REQUIRE(power_lambda != 0.f && power_lambda != 1.f, "power_lambda 0 / 1 (log / identity spacing) is not supported");
+    REQUIRE(power_scaling > 0.f, "power_scaling must be positive");
+    a->power.lam = power_lambda;
+    a->power.scaling = power_scaling;
+    double lam1 = power_lambda - 1.0 < 0 ? -(power_lambda - 1.0) : (power_lambda - 1.0);
+    a->power.lam_1 = (float)lam1;
+    a->power.ratio = (float)(lam1 / (double)power_lambda);
+  }
+  return 0;
+}
+
 int b200nerf_spaced_sample(b200nerf_ctx* c, int kind, float power_lambda, float power_scaling, const float* nears,
                            const float* fars, int64_t n_rays, int n_samples, float* bins_s, float* bins_e, void* stream) {
   REQUIRE(c, "ctx is NULL");
-  REQUIRE(kind >= B200NERF_SPACING_UNIFORM && kind <= B200NERF_SPACING_LOG, "unknown spacing kind");
   REQUIRE(n_rays >= 0 && n_samples >= 1, "bad sample grid");
   if (n_rays == 0) return 0;
   REQUIRE(fars && bins_e, "NULL argument");
   SpacingArgs a{};
-  a.kind = kind;
-  if (kind == B200NERF_SPACING_POWER) {
-    REQUIRE(power_lambda != 0.f && power_lambda != 1.f, "power_lambda 0 / 1 (log / identity spacing) is not supported");
-    REQUIRE(power_scaling > 0.f, "power_scaling must be positive");
-    a.power.lam = power_lambda;
-    a.power.scaling = power_scaling;
-    double lam1 = power_lambda - 1.0 < 0 ? -(power_lambda - 1.0) : (power_lambda - 1.0);
-    a.power.lam_1 = (float)lam1;
-    a.power.ratio = (float)(lam1 / (double)power_lambda);
-  }
+  if (int rc = make_spacing(kind, power_lambda, power_scaling, &a)) return rc;
   DeviceGuard g(c->device);
   const int64_t n = n_rays * (n_samples + 1);
   spaced_sample_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(a, nears, fars, n_rays, n_samples, bins_s, bins_e);
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+// ------------------------------------------------------------------------- module-level seams
+int b200nerf_isotropic_gaussian_fwd(b200nerf_ctx* c, const float* origins, const float* directions,
+                                    const float* pixel_area, const float* bins_e, int64_t n_rays, int n_samples,
+                                    float* mean, float* std, void* stream) {
+  REQUIRE(c, "ctx is NULL");
+  REQUIRE(n_rays >= 0 && n_samples >= 1, "bad sample grid");
+  if (n_rays == 0) return 0;
+  REQUIRE(origins && directions && pixel_area && bins_e && mean && std, "NULL argument");
+  DeviceGuard g(c->device);
+  const int64_t n = n_rays * n_samples;
+  isotropic_gaussian_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(origins, directions, pixel_area, bins_e,
+                                                                                           n_rays, n_samples, mean, std);
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+int b200nerf_neurad_encoding_fwd(b200nerf_ctx* c, int field, const float* mean, const float* std, const float* times,
+                                 const float* directions, int directions_per_ray, int64_t n_rays, int n_samples,
+                                 float* features, float* density, float* directions_out, int32_t* actor_id,
+                                 void* stream) {
+  REQUIRE(c, "ctx is NULL");
+  REQUIRE(field >= 0 && field < 3, "field must be B200NERF_FIELD_MAIN / PROP0 / PROP1");
+  if (!c->have_field[field]) return fail(B200NERF_ERR_STATE, "b200nerf_set_field_grids was not called for this field");
+  REQUIRE(n_rays >= 0 && n_samples >= 1, "bad sample grid");
+  const FieldGrids& fg = c->fields[field];
+  REQUIRE(fg.stat.L * fg.stat.F <= kModMaxDim, "encoding rows wider than 64 features are not supported");
+  REQUIRE(c->actors.n_actors == 0 || fg.act.L * fg.act.F <= fg.stat.L * fg.stat.F,
+          "actor features must fit the static feature width (they are zero padded to it)");
+  if (c->actors.n_actors > kModMaxActors) return fail(B200NERF_ERR_UNSUPPORTED, "more than 64 actors");
+  if (density && !fg.decoder) return fail(B200NERF_ERR_STATE, "b200nerf_set_proposal_decoder was not called for this field");
+  REQUIRE(!directions_out || directions, "directions_out needs directions");
+  if (n_rays == 0) return 0;
+  REQUIRE(mean && std, "NULL argument");
+  REQUIRE(c->actors.n_actors == 0 || times, "times are required when the scene has actors");
+  DeviceGuard g(c->device);
+  EncodingArgs a{mean, std, times, directions, features, density, directions_out, actor_id, n_rays, n_samples,
+                 directions_per_ray ? 1 : 0};
+  const unsigned grid = (unsigned)((n_rays + kModWarps - 1) / kModWarps);
+  neurad_encoding_fwd_kernel<<<grid, kModWarps * 32, 0, (cudaStream_t)stream>>>(fg, c->actors, a);
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+int b200nerf_field_mid_fwd(b200nerf_ctx* c, const float* geo_out, const float* directions, int64_t n_points,
+                           int geo_feat_dim, float* mlp_feature_in, void* stream) {
+  REQUIRE(c, "ctx is NULL");
+  REQUIRE(n_points >= 0 && geo_feat_dim >= 1, "bad shape");
+  if (n_points == 0) return 0;
+  REQUIRE(geo_out && directions && mlp_feature_in, "NULL argument");
+  DeviceGuard g(c->device);
+  field_mid_kernel<<<(unsigned)((n_points + 127) / 128), 128, 0, (cudaStream_t)stream>>>(geo_out, directions, n_points, geo_feat_dim,
+                                                                                          mlp_feature_in);
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+int b200nerf_field_tail_fwd(b200nerf_ctx* c, const float* geo_out, const float* mlp_feature_out, int64_t n_points,
+                            int geo_feat_dim, float beta, float* feature, float* sdf, float* alpha, void* stream) {
+  REQUIRE(c, "ctx is NULL");
+  REQUIRE(n_points >= 0 && geo_feat_dim >= 1, "bad shape");
+  if (n_points == 0) return 0;
+  REQUIRE(geo_out && mlp_feature_out && feature, "NULL argument");
+  DeviceGuard g(c->device);
+  field_tail_kernel<<<(unsigned)((n_points + 127) / 128), 128, 0, (cudaStream_t)stream>>>(geo_out, mlp_feature_out, n_points,
+                                                                                           geo_feat_dim, beta, feature, sdf, alpha);
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+int b200nerf_spacing_to_euclidean(b200nerf_ctx* c, int kind, float power_lambda, float power_scaling, const float* nears,
+                                  const float* fars, const float* bins_s, int64_t n_rays, int n_edges, float* bins_e,
+                                  void* stream) {
+  REQUIRE(c, "ctx is NULL");
+  REQUIRE(n_rays >= 0 && n_edges >= 1, "bad bin grid");
+  SpacingArgs a{};
+  if (int rc = make_spacing(kind, power_lambda, power_scaling, &a)) return rc;
+  if (n_rays == 0) return 0;
+  REQUIRE(fars && bins_s && bins_e, "NULL argument");
+  DeviceGuard g(c->device);
+  const int64_t n = n_rays * n_edges;
+  spacing_to_euclidean_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(a, nears, fars, bins_s, n_rays, n_edges, bins_e);
   CUDA_TRY(cudaGetLastError());
   return 0;
 }

@@ -1,0 +1,148 @@
+// nff_modules.h -- device code of the MODULE-LEVEL seams of the reference API (Field, Sampler,
+// NeuRADHashEncoding as stand-alone operators) and of their backward operators.
+//
+// The fused renderer (nff_lane.h / nff_device.h) never materialises a per-sample tensor; these operators do, because
+// the reference's per-module API hands [N,S,...] tensors from one nn.Module to the next.  Everything here is written
+// per thread (no warp collectives), so the test-only host emulation (tests/host_emul) can run it as plain loops.
+#pragma once
+
+#include "nff_device.h"
+
+namespace nff {
+
+constexpr int kModMaxActors = 64;  // actors per scene the module-level operators accept (frames live in shared memory)
+constexpr int kModMaxDim = 64;     // max L*F of a NeuRADHashEncoding output row
+
+// world -> box frame of one actor at one ray's time: [R^T | -R^T t] row major 3x4, padded half extents, validity
+struct ActorFrame {
+  float w2b[12];
+  float bnd[3];
+  int32_t valid;
+};
+
+// torch.searchsorted(pose_times, t) (left) + the lerp fraction of interpolate_trajectories_6d (utils/poses.py:117-134)
+NFF_D void keyframe_bracket(const Actors& A, float time, int& left, int& right, float& frac) {
+  int lo = 0, hi = A.n_times;
+  while (lo < hi) {
+    int mid = (lo + hi) >> 1;
+    if (ldg(A.times + mid) < time) lo = mid + 1; else hi = mid;
+  }
+  right = lo;
+  left = right - 1 < 0 ? 0 : right - 1;
+  if (right > A.n_times - 1) right = A.n_times - 1;
+  float tl = ldg(A.times + left), tr = ldg(A.times + right);
+  frac = fdiv(fsub(time, tl), fadd(fsub(tr, tl), 1e-6f));
+  frac = fminf(fmaxf(frac, 0.0f), 1.0f);
+}
+
+// DynamicActors.get_boxes2world (model_components/dynamic_actors.py:251-268) for ONE actor: keyframe lerp of the
+// Gram-Schmidt'ed 6-D rotation + position (utils/poses.py:90-150), rotation_6d_to_matrix
+// (cameras/camera_utils.py:422-443), pose inverse (utils/poses.py:42-55).  Same op sequence as actor_candidates()
+// of the fused kernel, without the ray-line cull (a conservative optimisation there; the in-box test decides).
+NFF_D void actor_frame(const Actors& A, int a, int left, int right, float frac, ActorFrame& f) {
+  const float* kl = A.keyframes + ((size_t)left * A.n_actors + a) * 9;
+  const float* kr = A.keyframes + ((size_t)right * A.n_actors + a) * 9;
+  float p[9];
+  for (int i = 0; i < 9; ++i) {
+    float l_ = ldg(kl + i), r_ = ldg(kr + i);
+    p[i] = fadd(l_, fmul(fsub(r_, l_), frac));
+  }
+  f.valid = (A.present[(size_t)left * A.n_actors + a] | A.present[(size_t)right * A.n_actors + a]) != 0;
+  float b1[3] = {p[0], p[1], p[2]};
+  normalize3(b1);
+  float dt = fadd(fadd(fmul(b1[0], p[3]), fmul(b1[1], p[4])), fmul(b1[2], p[5]));
+  float b2[3] = {fsub(p[3], fmul(dt, b1[0])), fsub(p[4], fmul(dt, b1[1])), fsub(p[5], fmul(dt, b1[2]))};
+  normalize3(b2);
+  float b3[3] = {fsub(fmul(b1[1], b2[2]), fmul(b1[2], b2[1])), fsub(fmul(b1[2], b2[0]), fmul(b1[0], b2[2])),
+                 fsub(fmul(b1[0], b2[1]), fmul(b1[1], b2[0]))};
+  float R[9] = {b1[0], b2[0], b3[0], b1[1], b2[1], b3[1], b1[2], b2[2], b3[2]};
+  for (int i = 0; i < 3; ++i) {
+    f.w2b[4 * i + 0] = R[3 * i + 0];
+    f.w2b[4 * i + 1] = R[3 * i + 1];
+    f.w2b[4 * i + 2] = R[3 * i + 2];
+    f.w2b[4 * i + 3] = -fadd(fadd(fmul(R[3 * i + 0], p[6]), fmul(R[3 * i + 1], p[7])), fmul(R[3 * i + 2], p[8]));
+    f.bnd[i] = ldg(A.bounds + 3 * a + i);
+  }
+}
+
+// _get_actor_indices, per-sample part (field_components/neurad_encoding.py:241-254): the actor whose padded box
+// contains the sample mean (highest index wins = the reference's sequential index_put on CPU), or -1.
+NFF_D int actor_containing(const ActorFrame* frames, int n_actors, float x, float y, float z, float pb[3]) {
+  int hit = -1;
+  for (int a = 0; a < n_actors; ++a) {
+    const ActorFrame& f = frames[a];
+    if (!f.valid) continue;
+    const float* M = f.w2b;
+    float q0 = fadd(fadd(fadd(fmul(M[0], x), fmul(M[1], y)), fmul(M[2], z)), M[3]);
+    float q1 = fadd(fadd(fadd(fmul(M[4], x), fmul(M[5], y)), fmul(M[6], z)), M[7]);
+    float q2 = fadd(fadd(fadd(fmul(M[8], x), fmul(M[9], y)), fmul(M[10], z)), M[11]);
+    if (fabsf(q0) < f.bnd[0] && fabsf(q1) < f.bnd[1] && fabsf(q2) < f.bnd[2]) {
+      hit = a;
+      pb[0] = q0; pb[1] = q1; pb[2] = q2;
+    }
+  }
+  return hit;
+}
+
+// HashEncoding.pytorch_fwd + _rescale_grid_features for one contracted gaussian, generic L / F:
+// out[l*F + f] = trilerp_l,f * 1/max(1, 2*res_l*std)   (encodings.py:425-466, neurad_encoding.py:297-304).
+// `cells` (optional, [L]) keeps each level's cell for the backward operator.
+NFF_D void encode_levels(const float* NFF_RESTRICT table, const Grid& gr, const Gauss& g, float* out) {
+  for (int l = 0; l < gr.L; ++l) {
+    Cell c = grid_cell(g.x, g.y, g.z, gr.res[l]);
+    uint32_t r[8];
+    cell_rows(c, gr.mask, r);
+    const float* base = table + (size_t)l * gr.T * gr.F;
+    const float w = level_weight(gr.res[l], g.std);
+    for (int f = 0; f < gr.F; ++f) {
+      float v[8];
+      for (int k = 0; k < 8; ++k) v[k] = ldg(base + (size_t)r[k] * gr.F + f);
+      out[l * gr.F + f] = fmul(trilerp(v, c), w);
+    }
+  }
+}
+
+// NeuRADHashEncoding.forward for one sample (field_components/neurad_encoding.py:150-187): static features, or the
+// containing actor's features zero-padded to the static width; the direction goes to the box frame, renormalised
+// with +EPS (:203-209).  Returns the actor index or -1.  `feat` must hold fg.stat.L * fg.stat.F floats.
+NFF_D int neurad_encode_point(const FieldGrids& fg, const ActorFrame* frames, int n_actors, const Gauss& g,
+                              float* feat, float dir[3]) {
+  float pb[3];
+  const int a = n_actors > 0 ? actor_containing(frames, n_actors, g.x, g.y, g.z, pb) : -1;
+  const int D = fg.stat.L * fg.stat.F;
+  if (a >= 0) {
+    Gauss ga = {pb[0], pb[1], pb[2], g.std};
+    ga = contract(ga, fg.actor_scale);
+    encode_levels(fg.actor_tables[a], fg.act, ga, feat);
+    for (int i = fg.act.L * fg.act.F; i < D; ++i) feat[i] = 0.0f;  // F.pad(actor_features, (0, D - Da))
+    if (dir) {
+      const float* M = frames[a].w2b;
+      float q0 = fadd(fadd(fmul(M[0], dir[0]), fmul(M[1], dir[1])), fmul(M[2], dir[2]));
+      float q1 = fadd(fadd(fmul(M[4], dir[0]), fmul(M[5], dir[1])), fmul(M[6], dir[2]));
+      float q2 = fadd(fadd(fmul(M[8], dir[0]), fmul(M[9], dir[1])), fmul(M[10], dir[2]));
+      float n = fadd(fsqrt(fadd(fadd(fmul(q0, q0), fmul(q1, q1)), fmul(q2, q2))), 1.0e-7f);
+      dir[0] = fdiv(q0, n); dir[1] = fdiv(q1, n); dir[2] = fdiv(q2, n);
+    }
+  } else {
+    Gauss gs = contract(g, fg.static_scale);
+    encode_levels(fg.stat.table, fg.stat, gs, feat);
+  }
+  return a;
+}
+
+// --------------------------------------------------------------------------------------------- backward pieces
+// d(out[l*F+f]) / d(table rows): the trilinear corner weights of `trilerp` times the anti-aliasing weight.  Corner
+// order as cell_rows(): ccc, cfc, ffc, fcc, ccf, cff, fff, fcf.
+NFF_D void corner_weights(const Cell& c, float w[8]) {
+  const float ox = c.ox, oy = c.oy, oz = c.oz, ix = 1.0f - c.ox, iy = 1.0f - c.oy, iz = 1.0f - c.oz;
+  w[0] = ox * oy * oz;
+  w[1] = ox * iy * oz;
+  w[2] = ix * iy * oz;
+  w[3] = ix * oy * oz;
+  w[4] = ox * oy * iz;
+  w[5] = ox * iy * iz;
+  w[6] = ix * iy * iz;
+  w[7] = ix * oy * iz;
+}
+
+}  // namespace nff

@@ -92,6 +92,15 @@ SIGNATURES = {
     "b200nerf_alpha_to_weights": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p]),
     "b200nerf_spaced_sample": (c_int, [c_void_p, c_int, c_float, c_float, c_void_p, c_void_p, c_int64, c_int, c_void_p,
                                        c_void_p, c_void_p]),
+    "b200nerf_isotropic_gaussian_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p,
+                                                c_void_p, c_void_p]),
+    "b200nerf_neurad_encoding_fwd": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int64, c_int,
+                                             c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "b200nerf_field_mid_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p]),
+    "b200nerf_field_tail_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_float, c_void_p, c_void_p, c_void_p,
+                                        c_void_p]),
+    "b200nerf_spacing_to_euclidean": (c_int, [c_void_p, c_int, c_float, c_float, c_void_p, c_void_p, c_void_p, c_int64, c_int,
+                                              c_void_p, c_void_p]),
     "b200nerf_frustum_positions": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, POINTER(c_float),
                                            c_void_p, c_void_p]),
     "b200nerf_density_rgb_heads": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p, c_void_p]),

@@ -15,6 +15,11 @@ modules, so that the parity tests read like the reference's own tests and a refe
   model_components/renderers.py:59,93,322,353  Feature/RGB/Accumulation/DepthRenderer  same names (-> composite kernel)
   models/neurad.py:165          NeuRADModel.get_nff_outputs /  NeuRADModel       (-> fused nff_render_fwd kernel)
                                 get_outputs_for_camera_ray_bundle / decode_features (lidar half)
+  field_components/neurad_encoding.py:85  NeuRADHashEncoding   NeuRADHashEncoding (-> neurad_encoding_fwd kernel)
+  fields/neurad_field.py:76,186  NeuRADField, NeuRADProposalField  same names (encoding + tcgen05 MLPs + head kernels)
+  model_components/ray_samplers.py:569  ProposalNetworkSampler  ProposalNetworkSampler (stage kernels, density_fns)
+                                NeuRADModel.field / .proposal_fields / .sampler / .density_fns as in neurad.py:180-248;
+                                get_nff_outputs(fused=False) walks these modules like the reference does
 
 Everything is inference-only (eval mode, no autograd): SURVEY.md section 8f ranks the backward pass as a later row.
 There is no CPU path: modules raise at call time if the parameters are not on a CUDA device.
@@ -23,6 +28,7 @@ from __future__ import annotations
 
 import math
 from dataclasses import dataclass, field
+from enum import Enum
 from typing import Dict, List, Optional, Tuple
 
 import torch
@@ -162,29 +168,63 @@ class MLP(nn.Module):
 
 
 class PDFSampler:
-    """model_components/ray_samplers.py:255-376 in eval mode with include_original=False: maps per-bin weights and
-    the existing spacing-domain bin edges to `num_samples`+1 new edges."""
+    """model_components/ray_samplers.py:255-376 in eval mode with include_original=False.
 
-    def __init__(self, num_samples: Optional[int] = None, histogram_padding: float = 0.01) -> None:
+    Reference signature `pdf_sampler(ray_bundle, ray_samples, weights, num_samples=)` -> RaySamples (the resampled
+    spacing bins mapped through the existing samples' spacing_to_euclidean_fn, :363-375); the short form
+    `pdf_sampler(weights, existing_bins, num_samples)` returns just the new spacing-domain edges."""
+
+    def __init__(self, num_samples: Optional[int] = None, train_stratified: bool = True, single_jitter: bool = False,
+                 include_original: bool = False, histogram_padding: float = 0.01) -> None:
+        if include_original:
+            raise NotImplementedError("include_original=True is not on NeuRAD's path (ray_samplers.py:606)")
         self.num_samples, self.histogram_padding = num_samples, histogram_padding
 
     @torch.no_grad()
-    def __call__(self, weights: Tensor, existing_bins: Tensor, num_samples: Optional[int] = None) -> Tensor:
-        n = num_samples or self.num_samples
+    def __call__(self, *args, num_samples: Optional[int] = None, **kw):
+        if args and isinstance(args[0], RayBundle) or "ray_bundle" in kw:
+            return self.generate_ray_samples(*args, num_samples=num_samples, **kw)
+        weights, existing_bins = args[0], args[1]
+        n = num_samples or (args[2] if len(args) > 2 else None) or self.num_samples
         assert n is not None
         w = weights[..., 0] if weights.dim() == existing_bins.dim() + 1 else weights
         be = get_backend(w.device)
         return be.pdf_resample(w, existing_bins, n, self.histogram_padding)[0]
 
+    @torch.no_grad()
+    def generate_ray_samples(self, ray_bundle: Optional["RayBundle"] = None, ray_samples: Optional["RaySamples"] = None,
+                             weights: Optional[Tensor] = None, num_samples: Optional[int] = None) -> "RaySamples":
+        if ray_samples is None or ray_bundle is None:
+            raise ValueError("ray_samples and ray_bundle must be provided")  # ray_samplers.py:300-301
+        assert weights is not None, "weights must be provided"
+        n = num_samples or self.num_samples
+        assert n is not None
+        be = get_backend(weights.device)
+        existing = ray_samples.per_ray_spacing_bins()
+        w = weights[..., 0] if weights.dim() == 3 else weights
+        bins = be.pdf_resample(w, existing, n, self.histogram_padding)[0]
+        fr = ray_samples.frustums
+        return RaySamples(Frustums(fr.origins, fr.directions, ray_samples.spacing_to_euclidean_fn(bins), fr.pixel_area), bins,
+                          times=ray_samples.times, metadata=ray_samples.metadata, spacing=ray_samples.spacing)
+
+
+@dataclass
+class GaussiansStd:
+    """utils/math.py GaussiansStd: isotropic gaussians, mean [N,S,3] and std [N,S] (one multisample)."""
+
+    mean: Tensor
+    std: Tensor
+
 
 @dataclass
 class Frustums:
-    """cameras/rays.py:33-60 for contiguous samples: per-ray origins/directions [N,3] and the euclidean bin edges
-    [N,S+1] (starts = edges[:, :-1], ends = edges[:, 1:]) -- never expanded to [N,S,3] views."""
+    """cameras/rays.py:33-60 for contiguous samples: per-ray origins/directions [N,3], pixel_area [N,1] and the
+    euclidean bin edges [N,S+1] (starts = edges[:, :-1], ends = edges[:, 1:]) -- never expanded to [N,S,3] views."""
 
     origins: Tensor
     directions: Tensor
     bin_edges: Tensor
+    pixel_area: Optional[Tensor] = None
 
     @property
     def starts(self) -> Tensor:
@@ -201,25 +241,55 @@ class Frustums:
         be = get_backend(self.bin_edges.device)
         return be.frustum_positions(self.origins, self.directions, self.bin_edges, normalize_aabb)
 
+    @torch.no_grad()
+    def get_fast_isotropic_gaussian(self, num_multisamples: int = 1) -> GaussiansStd:
+        """rays.py:109-124 (NeuRAD uses one multisample, neurad_field.py:67)."""
+        if num_multisamples != 1:
+            raise NotImplementedError("num_multisamples != 1")
+        assert self.pixel_area is not None, "frustums built without pixel_area"
+        be = get_backend(self.bin_edges.device)
+        return GaussiansStd(*be.isotropic_gaussian(self.origins, self.directions, self.pixel_area, self.bin_edges))
+
 
 @dataclass
 class RaySamples:
-    """cameras/rays.py:127-249 (the members the hot path reads)."""
+    """cameras/rays.py:127-249 (the members the hot path reads).  `spacing_bins` is [S+1] when every ray shares the
+    initial sampler's edges and [N,S+1] after PDF resampling; `spacing` = (kind, power_lambda, power_scaling, nears,
+    fars) defines spacing_to_euclidean_fn (ray_samplers.py:119-120)."""
 
     frustums: Frustums
-    spacing_bins: Tensor  # [S+1], shared by all rays
+    spacing_bins: Tensor
+    times: Optional[Tensor] = None  # [N,1]
+    metadata: Dict[str, Tensor] = field(default_factory=dict)
+    spacing: Optional[tuple] = None
+
+    @property
+    def shape(self) -> Tuple[int, int]:
+        return (self.frustums.bin_edges.shape[0], self.frustums.bin_edges.shape[1] - 1)
+
+    def per_ray_spacing_bins(self) -> Tensor:
+        b = self.spacing_bins
+        return b if b.dim() == 2 else b[None, :].expand(self.shape[0], -1).contiguous()
 
     @property
     def spacing_starts(self) -> Tensor:
-        return self.spacing_bins[None, :-1, None]
+        b = self.spacing_bins
+        return b[:, :-1, None] if b.dim() == 2 else b[None, :-1, None]
 
     @property
     def spacing_ends(self) -> Tensor:
-        return self.spacing_bins[None, 1:, None]
+        b = self.spacing_bins
+        return b[:, 1:, None] if b.dim() == 2 else b[None, 1:, None]
 
     @property
     def deltas(self) -> Tensor:
         return self.frustums.ends - self.frustums.starts
+
+    @torch.no_grad()
+    def spacing_to_euclidean_fn(self, bins: Tensor) -> Tensor:
+        assert self.spacing is not None, "ray samples built without a spacing function"
+        kind, lam, scaling, nears, fars = self.spacing
+        return get_backend(bins.device).spacing_to_euclidean(bins, nears, fars, kind, lam, scaling)
 
     @torch.no_grad()
     def get_weights(self, densities: Tensor) -> Tensor:
@@ -247,7 +317,11 @@ class SpacedSampler:
         be = get_backend(ray_bundle.origins.device)
         lam, scaling = self._power()
         bins_s, bins_e = be.spaced_sample(ray_bundle.nears, ray_bundle.fars, n, self.spacing, lam, scaling)
-        return RaySamples(Frustums(ray_bundle.origins.reshape(-1, 3), ray_bundle.directions.reshape(-1, 3), bins_e), bins_s)
+        area = None if ray_bundle.pixel_area is None else ray_bundle.pixel_area.reshape(-1, 1)
+        times = None if ray_bundle.times is None else ray_bundle.times.reshape(-1, 1)
+        return RaySamples(Frustums(ray_bundle.origins.reshape(-1, 3), ray_bundle.directions.reshape(-1, 3), bins_e, area), bins_s,
+                          times=times, metadata=ray_bundle.metadata,
+                          spacing=(self.spacing, lam, scaling, ray_bundle.nears, ray_bundle.fars))
 
     generate_ray_samples = __call__
 
@@ -346,6 +420,132 @@ class DepthRenderer(nn.Module):
                             want_accumulation=False)["depth"]
 
 
+class ProposalNetworkSampler:
+    """model_components/ray_samplers.py:569-666, eval mode: initial sampler, then per proposal level density_fns[i] ->
+    RaySamples.get_weights -> PDFSampler.  Every step is one of the library's stage kernels; the fused
+    `b200nerf_nff_render_fwd` does the same work without materialising any of these tensors."""
+
+    def __init__(self, num_proposal_samples_per_ray: Tuple[int, ...] = (64,), num_nerf_samples_per_ray: int = 32,
+                 num_proposal_network_iterations: int = 2, single_jitter: bool = False, update_sched=lambda x: 1,
+                 initial_sampler: Optional[SpacedSampler] = None, pdf_sampler: Optional[PDFSampler] = None) -> None:
+        if num_proposal_network_iterations < 1:
+            raise ValueError("num_proposal_network_iterations must be >= 1")  # ray_samplers.py:597-598
+        if initial_sampler is None:
+            raise NotImplementedError("UniformLinDispPiecewiseSampler (the nerfstudio default) is not on NeuRAD's path; "
+                                      "pass initial_sampler=PowerSampler(...) as neurad.py:232-235 does")
+        self.num_proposal_samples_per_ray = num_proposal_samples_per_ray
+        self.num_nerf_samples_per_ray = num_nerf_samples_per_ray
+        self.num_proposal_network_iterations = num_proposal_network_iterations
+        self.update_sched = update_sched
+        self.initial_sampler = initial_sampler
+        self.pdf_sampler = pdf_sampler if pdf_sampler is not None else PDFSampler(include_original=False, single_jitter=single_jitter)
+        self._anneal, self._steps_since_update, self._step = 1.0, 0, 0
+
+    def set_anneal(self, anneal: float) -> None:
+        self._anneal = anneal
+
+    def step_cb(self, step) -> None:
+        self._step = step
+        self._steps_since_update += 1
+
+    @torch.no_grad()
+    def generate_ray_samples(self, ray_bundle: Optional[RayBundle] = None, density_fns: Optional[list] = None,
+                             pass_ray_samples: bool = False) -> Tuple[RaySamples, List[Tensor], List[RaySamples]]:
+        assert ray_bundle is not None
+        assert density_fns is not None
+        if not pass_ray_samples:
+            density_fns = [lambda rs, f=f: f(rs.frustums.get_positions()) for f in density_fns]
+        ray_bundle = ray_bundle.flatten()
+        weights_list, ray_samples_list = [], []
+        n = self.num_proposal_network_iterations
+        weights = ray_samples = None
+        for i_level in range(n + 1):
+            is_prop = i_level < n
+            num_samples = self.num_proposal_samples_per_ray[i_level] if is_prop else self.num_nerf_samples_per_ray
+            if i_level == 0:
+                ray_samples = self.initial_sampler(ray_bundle, num_samples=num_samples)
+            else:
+                annealed = weights if self._anneal == 1.0 else torch.pow(weights, self._anneal)
+                ray_samples = self.pdf_sampler(ray_bundle, ray_samples, annealed, num_samples=num_samples)
+            if is_prop:
+                density = density_fns[i_level](ray_samples)
+                weights = ray_samples.get_weights(density)
+                weights_list.append(weights)
+                ray_samples_list.append(ray_samples)
+        self._steps_since_update = 0
+        return ray_samples, weights_list, ray_samples_list
+
+    __call__ = generate_ray_samples
+
+
+class FieldHeadNames(Enum):
+    """field_components/field_heads.py:28-44 (the heads NeuRAD's fields return)."""
+
+    DENSITY = "density"
+    SDF = "sdf"
+    ALPHA = "alpha"
+    FEATURE = "feature"
+
+
+class NeuRADHashEncoding:
+    """field_components/neurad_encoding.py:85-187 of one field of a NeuRADModel mirror (the parameters live in the model
+    under the reference's names and are bound to the device context by it)."""
+
+    def __init__(self, model: "NeuRADModel", field_index: int) -> None:
+        self._model, self._field = model, field_index
+        g = [model.config.grid, model.config.proposal_grid_1, model.config.proposal_grid_2][field_index].static
+        self.scene_repr_dim = g.num_levels * g.hashgrid_dim
+
+    def get_out_dim(self) -> int:
+        return self.scene_repr_dim
+
+    @torch.no_grad()
+    def forward(self, positions: GaussiansStd, times: Tensor, directions: Optional[Tensor] = None) -> Tuple[Tensor, Optional[Tensor]]:
+        """(features [N*S, D], directions [N,S,3] in the actor frame where a sample is inside an actor | None)."""
+        out = self._model._bind().neurad_encoding(self._field, positions.mean, positions.std, times, directions)
+        return out["features"], out.get("directions")
+
+    __call__ = forward
+
+
+class NeuRADProposalField:
+    """fields/neurad_field.py:186-216."""
+
+    def __init__(self, model: "NeuRADModel", field_index: int) -> None:
+        self._model, self._field = model, field_index
+        self.hashgrid = NeuRADHashEncoding(model, field_index)
+
+    @torch.no_grad()
+    def get_density(self, ray_samples: RaySamples) -> Tuple[Tensor, None]:
+        """density [N,S,1] = trunc_exp(density_decoder(hashgrid(gaussians))) (neurad_field.py:208-213)."""
+        pos = ray_samples.frustums.get_fast_isotropic_gaussian(num_multisamples=1)
+        out = self._model._bind().neurad_encoding(self._field, pos.mean, pos.std, ray_samples.times, None,
+                                                  want_features=False, want_density=True)
+        return out["density"][..., None], None
+
+    def get_outputs(self, ray_samples: RaySamples, density_embedding: Optional[Tensor] = None) -> dict:
+        return {}
+
+
+class NeuRADField:
+    """fields/neurad_field.py:76-152 (use_sdf=True)."""
+
+    def __init__(self, model: "NeuRADModel") -> None:
+        self._model = model
+        self.hashgrid = NeuRADHashEncoding(model, 0)
+
+    @torch.no_grad()
+    def forward(self, ray_samples: RaySamples, compute_normals: bool = False) -> Dict[FieldHeadNames, Tensor]:
+        """{FEATURE [N,S,32], SDF [N,S,1], ALPHA [N,S,1]}."""
+        if compute_normals:
+            raise NotImplementedError("NeuRADField never computes normals (neurad_field.py:128)")
+        g = ray_samples.frustums.get_fast_isotropic_gaussian(self._model.config.num_multisamples)
+        out = self._model._bind().field_forward(g.mean, g.std, ray_samples.times, ray_samples.frustums.directions)
+        return {FieldHeadNames.FEATURE: out["feature"], FieldHeadNames.SDF: out["sdf"], FieldHeadNames.ALPHA: out["alpha"]}
+
+    __call__ = forward
+
+
 class BasicBlock(nn.Module):
     """model_components/cnns.py:35-46 as a parameter container (same sub-module names, hence the same state_dict keys:
     `main_branch.0` Conv2d, `.1` BatchNorm2d, `.3` Conv2d, `.4` BatchNorm2d).  The arithmetic runs inside
@@ -421,6 +621,22 @@ class NeuRADModel(nn.Module):
         self.register_buffer("static_scale", torch.tensor(float(config.static_scale)))
         self.rgb_decoder = RGBDecoder(config.nff_out_dim + config.appearance_dim, config.rgb_hidden_dim, config.rgb_upsample_factor)
         self._bound_version = None
+        # the reference's sub-modules (neurad.py:180-254), as views onto this model's parameters
+        self.field = NeuRADField(self)
+        self.proposal_fields = [NeuRADProposalField(self, 1), NeuRADProposalField(self, 2)]
+        sp = config.sampling
+        self.sampler = ProposalNetworkSampler(
+            num_nerf_samples_per_ray=sp.num_nerf_samples, num_proposal_samples_per_ray=tuple(sp.num_proposal_samples),
+            num_proposal_network_iterations=len(sp.num_proposal_samples),
+            initial_sampler=PowerSampler(power_lambda=sp.power_lambda, power_scaling=sp.power_scaling),
+            pdf_sampler=PDFSampler(include_original=False, histogram_padding=sp.histogram_padding),
+        )
+        # neurad.py:248 builds `[lambda x: prop_field.get_density(x)[0] for prop_field in self.proposal_fields]`: the
+        # closures bind late, so EVERY entry evaluates the LAST proposal field.  Same here.
+        last = self.proposal_fields[-1]
+        self.density_fns = [lambda ray_samples: last.get_density(ray_samples)[0] for _ in self.proposal_fields]
+        self.renderer_feat = FeatureRenderer()
+        self.renderer_accumulation = AccumulationRenderer()
 
     # -- state dict under the reference's dotted names ----------------------------------------------------------
     def reference_state_dict(self) -> Dict[str, Tensor]:
@@ -451,10 +667,84 @@ class NeuRADModel(nn.Module):
 
     # -- forward API --------------------------------------------------------------------------------------------
     @torch.no_grad()
-    def get_nff_outputs(self, ray_bundle: RayBundle, calc_lidar_losses: bool = False) -> Dict[str, Tensor]:
-        """neurad.py:368-421 (eval): features [N,48], depth, accumulation, prop_depth_0/1 [N,1]."""
+    def get_nff_outputs(self, ray_bundle: RayBundle, calc_lidar_losses: bool = False, fused: bool = True) -> Dict[str, Tensor]:
+        """neurad.py:368-421 (eval): features [N,48], depth, accumulation, prop_depth_0/1 [N,1].
+
+        fused=True (default): ONE kernel pair for the whole function.  fused=False: the reference's own module walk
+        (sampler with density_fns -> field -> _render_weights -> renderers -> appearance), every step a stage kernel of
+        the library -- the per-module API of SURVEY 8b; additionally returns the reference's training-side extras
+        `weights_list` / `ray_samples_list` (neurad.py:404-405)."""
         be = self._bind()
-        return be.render(ray_bundle.as_backend_dict())
+        if fused:
+            return be.render(ray_bundle.as_backend_dict())
+        rb = self._scale_pixel_area(ray_bundle.flatten())
+        ray_samples, prop_ray_samples, prop_weights = self._get_ray_samples(rb)
+        out = self.field(ray_samples)
+        weights = self._render_weights(out, ray_samples)
+        accumulation = self.renderer_accumulation(weights)
+        weights = weights.clone()
+        weights[:, -1:] += 1.0 - accumulation[:, None]  # sky sample takes the remaining transmittance (neurad.py:379-381)
+        features = self.renderer_feat(out[FieldHeadNames.FEATURE], weights)
+        features = torch.cat([features, self._get_appearance_embedding(rb, features)], dim=-1)
+        res = {"features": features, "accumulation": accumulation,
+               "depth": self.renderer_depth(weights[:, :-1], ray_samples, drop_last=True)}
+        for i, (w, rs) in enumerate(zip(prop_weights, prop_ray_samples)):
+            res[f"prop_depth_{i}"] = self.renderer_depth(w, rs)
+        res["weights_list"] = prop_weights + [weights]
+        res["ray_samples_list"] = prop_ray_samples + [ray_samples]
+        return res
+
+    def _scale_pixel_area(self, ray_bundle: RayBundle) -> RayBundle:
+        """neurad.py:702-709: camera rays cover upsample^2 pixels."""
+        area = ray_bundle.pixel_area
+        is_lidar = ray_bundle.metadata.get("is_lidar")
+        scale = float(self.config.rgb_upsample_factor**2)
+        scaled = area * scale if is_lidar is None else torch.where(is_lidar.reshape(area.shape).bool(), area, area * scale)
+        out = ray_bundle._map(lambda t: t)
+        out.pixel_area = scaled
+        return out
+
+    def _get_ray_samples(self, ray_bundle: RayBundle):
+        """neurad.py:443-459: far clamp, proposal sampling, the last sample stretched to the sky."""
+        sky = self.config.sampling.sky_distance
+        n = len(ray_bundle)
+        dev = ray_bundle.origins.device
+        ray_bundle.fars = torch.full((n, 1), sky, device=dev) if ray_bundle.fars is None else ray_bundle.fars.clamp_max(sky)
+        ray_bundle.nears = torch.zeros((n, 1), device=dev) if ray_bundle.nears is None else ray_bundle.nears
+        ray_samples, prop_weights, prop_ray_samples = self.sampler(ray_bundle, self.density_fns, pass_ray_samples=True)
+        edges = ray_samples.frustums.bin_edges
+        edges[:, -1] += sky - edges[:, -1]  # `ends[-1] += sky - ends[-1]`, the reference's exact expression
+        return ray_samples, prop_ray_samples, prop_weights
+
+    def _render_weights(self, outputs, ray_samples: RaySamples) -> Tensor:
+        """neurad.py:711-724, use_sdf branch: nerfacc.render_weight_from_alpha on [N,S]."""
+        return self._bind().alpha_to_weights(outputs[FieldHeadNames.ALPHA][..., 0])[..., None]
+
+    def renderer_depth(self, weights: Tensor, ray_samples: RaySamples, drop_last: bool = False) -> Tensor:
+        """render_depth_simple (neurad.py:727-734): sum_i w_i (start_i + end_i) / 2, un-normalised; `drop_last` is the
+        `[..., :-1, :]` slice that leaves the sky sample out (neurad.py:389-390)."""
+        fr = ray_samples.frustums
+        st, en = fr.starts, fr.ends
+        if drop_last:
+            st, en = st[:, :-1], en[:, :-1]
+        return self._bind().composite(weights, starts=st.contiguous(), ends=en.contiguous(), depth_method="simple",
+                                      want_accumulation=False)["depth"]
+
+    def _get_appearance_embedding(self, ray_bundle: RayBundle, features: Tensor) -> Tensor:
+        """neurad.py:423-441: per-sensor embedding, linearly interpolated in time (temporal_appearance_freq)."""
+        sd = self.reference_state_dict()
+        emb = sd["appearance_embedding.weight"]
+        n = len(ray_bundle)
+        sensor = ray_bundle.metadata.get("sensor_idxs")
+        sensor = torch.zeros(n, dtype=torch.long, device=emb.device) if sensor is None else sensor.reshape(-1).long()
+        eps = self.config.embeds_per_sensor
+        t = ray_bundle.times.reshape(-1) / self.config.duration * eps
+        before = t.floor().clamp(0, eps - 1)
+        after = (before + 1).clamp(0, eps - 1)
+        frac = (t - before)[:, None]
+        e0 = emb[(before + sensor * eps).long()]
+        e1 = emb[(after + sensor * eps).long()]
+        return e0 * (1 - frac) + e1 * frac
 
     @torch.no_grad()
     def decode_features(self, features: Tensor) -> Tuple[Tensor, Tensor]:

@@ -1,0 +1,111 @@
+"""TEST SCAFFOLDING ONLY -- a CPU stand-in for B200Backend's LEAF operators, so that the Python glue of the reference-API
+mirror (RaySamples / PDFSampler / ProposalNetworkSampler / NeuRADField / the per-module walk of get_nff_outputs, and
+B200Backend.field_forward's composition) can be executed in the GPU-less container.
+
+Leaves map onto the oracle (already GPU-validated operators) or onto the host emulation of the new device code
+(tests/host_emul: the module-level encoding).  Nothing here is importable from the product package; the product has
+no CPU path (tests/test_cabi.py::test_no_cpu_fallback)."""
+from typing import Dict, Optional
+
+import torch
+
+from neurad_studio_b200.backend import B200Backend
+from neurad_studio_b200.lib import FIELD_MAIN
+from oracle import neurad_oracle as O
+from oracle import simple_oracle as S
+from oracle.convert import to_oracle_cfg
+from tests.host_emul import emul
+
+
+class FakeBackend(B200Backend):
+    def __init__(self):  # no library, no context
+        self.device = torch.device("cpu")
+        self.cfg = None
+        self.params: Dict[str, torch.Tensor] = {}
+
+    def close(self):
+        pass
+
+    def check_status(self):
+        pass
+
+    def load_params(self, cfg, params, density_field_of_round=(2, 2)):
+        self.cfg, self.params = cfg, {k: v.detach().cpu() for k, v in params.items()}
+        p = self.params
+        names = ["field.mlp_geo.layers.0", "field.mlp_geo.layers.1", "field.mlp_feature.layers.0",
+                 "field.mlp_feature.layers.1", "field.mlp_feature.layers.2"]
+        ts = []
+        for nme in names:
+            ts += [p[nme + ".weight"], p[nme + ".bias"]]
+        self._field_mlps = {"geo": (ts[0:4:2], ts[1:4:2]), "feature": (ts[4::2], ts[5::2])}
+        self._beta = float(p["field.sdf_to_density.beta"].abs().item() + 0.0001)
+
+    # ---- leaves backed by the host emulation of the NEW device code
+    def isotropic_gaussian(self, origins, directions, pixel_area, bins_e):
+        return emul.gaussian(origins, directions, pixel_area, bins_e)
+
+    def neurad_encoding(self, field, mean, std, times, directions=None, want_features=True, want_density=False,
+                        want_actor_id=False):
+        return emul.encoding(self.cfg, self.params, O.pdf_u, field, mean, std, times, directions, want_features,
+                             want_density, want_actor_id)
+
+    def _field_mid(self, geo, directions):
+        return torch.cat([geo[:, 1:], O.sh_components_l4((directions.reshape(-1, 3) + 1.0) / 2.0)], dim=-1)
+
+    def _field_tail(self, geo, h):
+        sdf = geo[:, 0]
+        return geo[:, 1:] + h, sdf, torch.sigmoid(-sdf * self._beta)
+
+    # ---- leaves that exist (and are GPU-validated) since earlier commits: the oracle's restatements
+    def mlp_fwd(self, x, weights, biases=None):
+        y = x.reshape(-1, x.shape[-1])
+        for i, w in enumerate(weights):
+            y = torch.nn.functional.linear(y, w, None if biases is None else biases[i])
+            if i < len(weights) - 1:
+                y = torch.relu(y)
+        return y.reshape(*x.shape[:-1], y.shape[-1])
+
+    def spaced_sample(self, nears, fars, num_samples, spacing="uniform", power_lambda=-1.0, power_scaling=0.1):
+        f = fars.reshape(-1, 1)
+        nr = torch.zeros_like(f) if nears is None else nears.reshape(-1, 1)
+        bins, euclid = S.spaced_sample(nr, f, num_samples, self.SPACINGS[spacing], power_lambda, power_scaling)
+        return bins[0], euclid
+
+    def spacing_to_euclidean(self, bins_s, nears, fars, spacing="power", power_lambda=-1.0, power_scaling=0.1):
+        fn, inv = S.spacing_fns(self.SPACINGS[spacing], power_lambda, power_scaling)
+        f = fars.reshape(-1, 1)
+        nr = torch.zeros_like(f) if nears is None else nears.reshape(-1, 1)
+        return inv(bins_s * fn(f) + (1 - bins_s) * fn(nr))
+
+    def pdf_resample(self, weights, bins, num_samples, histogram_padding=0.01):
+        r = O.pdf_resample(weights, bins, num_samples, histogram_padding)
+        return r["bins"], r["cdf"], r["inds"].int()
+
+    def density_to_weights(self, deltas, densities):
+        return O.weights_from_density(deltas, densities)
+
+    def alpha_to_weights(self, alphas):
+        return O.render_weight_from_alpha(alphas)
+
+    def composite(self, weights, values=None, starts=None, ends=None, depth_method=None, background=None,
+                  value_nan_to_num=False, want_accumulation=True):
+        n, s = weights.shape[0], weights.shape[1]
+        w = weights.reshape(n, s, 1)
+        out = {}
+        if values is not None:
+            out["values"] = (w * values.reshape(n, s, -1)).sum(dim=-2)
+        if want_accumulation:
+            out["accumulation"] = w.sum(dim=-2)
+        if depth_method is not None:
+            assert depth_method == "simple"
+            out["depth"] = (w * (starts.reshape(n, s, 1) + ends.reshape(n, s, 1)) / 2).sum(dim=-2)
+        return out
+
+    def render(self, rays, want_trace=False, want_intensity=False, out=None, image_width=0):
+        n = rays["origins"].shape[0]
+        col = lambda t: t.reshape(n, 1)  # noqa: E731
+        with torch.no_grad():
+            return O.nff_outputs(self.params, to_oracle_cfg(self.cfg), rays["origins"], rays["directions"],
+                                 col(rays["pixel_area"]), col(rays["times"]),
+                                 col(rays.get("sensor_idx", torch.zeros(n, dtype=torch.long))),
+                                 col(rays["is_lidar"]).bool() if "is_lidar" in rays else None)

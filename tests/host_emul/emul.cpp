@@ -9,6 +9,7 @@
 
 #include "../../neurad-studio_b200/csrc/nff_device.h"
 #include "../../neurad-studio_b200/csrc/nff_lane.h"
+#include "../../neurad-studio_b200/csrc/nff_modules.h"
 
 using namespace nff;
 
@@ -18,13 +19,17 @@ static void pack_linear(const float* w, const float* b, int out_f, int in_f, int
   for (int o = 0; o < outp; ++o) db[o] = (o < out_f && b) ? b[o] : 0.f;
 }
 
-extern "C" {
-
 // ptrs / ints / floats layouts are documented in tests/host_emul/emul.py
-int emul_render(const void* const* ptrs, const int* ints, const float* floats, long long n_rays, int lane_mode) {
+// everything up to (not including) the rays: grids, MLPs, actors, sampling, appearance
+struct Parsed {
   RenderParams P{};
-  std::vector<float> kf, bounds, radii;
+  std::vector<float> kf, bounds, radii, mlp;
   int pi = 0, ii = 0, fi = 0;
+};
+static void parse_params(const void* const* ptrs, const int* ints, const float* floats, Parsed& Q) {
+  RenderParams& P = Q.P;
+  std::vector<float>&kf = Q.kf, &bounds = Q.bounds, &radii = Q.radii;
+  int &pi = Q.pi, &ii = Q.ii, &fi = Q.fi;
   const int n_actors = ints[ii++];
   const int n_times = ints[ii++];
   for (int f = 0; f < 3; ++f) {
@@ -45,7 +50,8 @@ int emul_render(const void* const* ptrs, const int* ints, const float* floats, l
     fg.static_scale = floats[fi++];
     fg.actor_scale = floats[fi++];
   }
-  std::vector<float> mlp(kMainMlpFloats);
+  std::vector<float>& mlp = Q.mlp;
+  mlp.resize(kMainMlpFloats);
   const float* t[10];
   for (int k = 0; k < 10; ++k) t[k] = (const float*)ptrs[pi++];
   pack_linear(t[0], t[1], kHidden, kGeoIn, kHidden, &mlp[kOffGeoW0], &mlp[kOffGeoB0]);
@@ -101,6 +107,16 @@ int emul_render(const void* const* ptrs, const int* ints, const float* floats, l
   P.app.dim = ints[ii++];
   P.app.eps = ints[ii++];
   P.app.duration = floats[fi++];
+}
+
+extern "C" {
+
+int emul_render(const void* const* ptrs, const int* ints, const float* floats, long long n_rays, int lane_mode) {
+  Parsed Q;
+  parse_params(ptrs, ints, floats, Q);
+  RenderParams& P = Q.P;
+  std::vector<float>& mlp = Q.mlp;
+  int &pi = Q.pi;
   // rays
   P.rays.origins = (const float*)ptrs[pi++];
   P.rays.directions = (const float*)ptrs[pi++];
@@ -160,6 +176,71 @@ int emul_render(const void* const* ptrs, const int* ints, const float* floats, l
         for (long long r = w; r < n_rays; r += n_warps) render_ray(P, shared[w], pol, r, true);
       });
   for (auto& th : threads) th.join();
+  return 0;
+}
+
+// Frustums.get_fast_isotropic_gaussian as the kernels compute it (nff_device.h: sample_gaussian).
+int emul_gaussian(const float* origins, const float* dirs, const float* area, const float* bins_e, long long n_rays, int S,
+                  float* mean, float* std) {
+  for (long long r = 0; r < n_rays; ++r)
+    for (int s = 0; s < S; ++s) {
+      const long long i = r * S + s;
+      Gauss g = sample_gaussian(origins + 3 * r, dirs + 3 * r, area[r], bins_e[r * (S + 1) + s], bins_e[r * (S + 1) + s + 1]);
+      mean[3 * i] = g.x; mean[3 * i + 1] = g.y; mean[3 * i + 2] = g.z;
+      std[i] = g.std;
+    }
+  return 0;
+}
+
+// NeuRADHashEncoding.forward as the module-level operator computes it (nff_modules.h: neurad_encode_point; same loop
+// structure as neurad_encoding_fwd_kernel in modules.cuh).  extra = {mean [N,S,3], std [N,S], times [N] or NULL,
+// dirs ([N,3] if dirs_per_ray else [N,S,3]) or NULL, features [N*S,D] or NULL, density [N,S] or NULL, dirs_out [N,S,3]
+// or NULL, actor_id [N,S] (int32) or NULL}
+int emul_encoding(const void* const* ptrs, const int* ints, const float* floats, const void* const* extra, long long n_rays,
+                  int S, int field, int dirs_per_ray) {
+  Parsed Q;
+  parse_params(ptrs, ints, floats, Q);
+  const FieldGrids& fg = Q.P.fields[field];
+  const Actors& A = Q.P.actors;
+  const float* mean = (const float*)extra[0];
+  const float* std_ = (const float*)extra[1];
+  const float* times = (const float*)extra[2];
+  const float* dirs = (const float*)extra[3];
+  float* features = (float*)extra[4];
+  float* density = (float*)extra[5];
+  float* dirs_out = (float*)extra[6];
+  int32_t* actor_id = (int32_t*)extra[7];
+  const int D = fg.stat.L * fg.stat.F;
+  std::vector<ActorFrame> frames(A.n_actors > 0 ? A.n_actors : 1);
+  for (long long r = 0; r < n_rays; ++r) {
+    if (A.n_actors > 0) {
+      int left, right;
+      float frac;
+      keyframe_bracket(A, times[r], left, right, frac);
+      for (int a = 0; a < A.n_actors; ++a) actor_frame(A, a, left, right, frac, frames[a]);
+    }
+    for (int s = 0; s < S; ++s) {
+      const long long i = r * S + s;
+      Gauss g = {mean[3 * i], mean[3 * i + 1], mean[3 * i + 2], std_[i]};
+      float dir[3] = {0.f, 0.f, 0.f};
+      if (dirs) {
+        const float* dp = dirs + 3 * (dirs_per_ray ? r : i);
+        dir[0] = dp[0]; dir[1] = dp[1]; dir[2] = dp[2];
+      }
+      float feat[kModMaxDim];
+      const int aid = neurad_encode_point(fg, frames.data(), A.n_actors, g, feat, dirs ? dir : nullptr);
+      if (features)
+        for (int k = 0; k < D; ++k) features[i * D + k] = feat[k];
+      if (density) {
+        float acc = 0.f;
+        for (int k = 0; k < D; ++k) acc = std::fmaf(feat[k], fg.decoder[k], acc);
+        density[i] = std::exp(acc);
+      }
+      if (dirs_out)
+        for (int k = 0; k < 3; ++k) dirs_out[3 * i + k] = dir[k];
+      if (actor_id) actor_id[i] = aid;
+    }
+  }
   return 0;
 }
 }

@@ -12,7 +12,7 @@ CSRC = os.path.join(os.path.dirname(os.path.dirname(HERE)), "neurad-studio_b200"
 
 
 def build(force=False):
-    deps = [SRC] + [os.path.join(CSRC, f) for f in ("nff_device.h", "nff_lane.h", "nff_params.h", "simt.h")]
+    deps = [SRC] + [os.path.join(CSRC, f) for f in ("nff_device.h", "nff_lane.h", "nff_modules.h", "nff_params.h", "simt.h")]
     if force or not os.path.exists(SO) or any(os.path.getmtime(d) > os.path.getmtime(SO) for d in deps):
         subprocess.check_call(
             ["g++", "-std=c++20", "-O2", "-ffp-contract=off", "-fPIC", "-shared", "-pthread", "-o", SO, SRC]
@@ -20,20 +20,29 @@ def build(force=False):
     return SO
 
 
-def render(cfg, params, rays, pdf_u, field_of_round=(2, 2), lane_mode=False):
-    """cfg: neurad_studio_b200.NeuRADConfig; params: reference-named tensors (CPU); rays: dict of CPU tensors."""
-    lib = ctypes.CDLL(build())
-    lib.emul_render.restype = ctypes.c_int
-    keep, ptrs, ints, floats = [], [], [], []
+class _Pack:
+    """ptrs / ints / floats argument arrays of the emulation entry points."""
 
-    def P(t):
+    def __init__(self):
+        self.keep, self.ptrs, self.ints, self.floats = [], [], [], []
+
+    def P(self, t):
         if t is None:
-            ptrs.append(None)
-            return
+            self.ptrs.append(None)
+            return None
         t = t.contiguous()
-        keep.append(t)
-        ptrs.append(ctypes.c_void_p(t.data_ptr()))
+        self.keep.append(t)
+        self.ptrs.append(ctypes.c_void_p(t.data_ptr()))
+        return t
 
+    def c_arrays(self):
+        return ((ctypes.c_void_p * len(self.ptrs))(*self.ptrs), (ctypes.c_int * len(self.ints))(*self.ints),
+                (ctypes.c_float * len(self.floats))(*self.floats))
+
+
+def _pack_params(pk, cfg, params, pdf_u, field_of_round):
+    """Everything emul.cpp's parse_params() reads: grids, MLPs, actors, sampling, appearance."""
+    keep, ptrs, ints, floats, P = pk.keep, pk.ptrs, pk.ints, pk.floats, pk.P
     n_actors = cfg.n_actors
     n_times = int(params["dynamic_actors.unique_timestamps"].shape[0]) if n_actors else 0
     ints += [n_actors, n_times]
@@ -79,6 +88,16 @@ def render(cfg, params, rays, pdf_u, field_of_round=(2, 2), lane_mode=False):
     P(params["appearance_embedding.weight"])
     ints += [int(params["appearance_embedding.weight"].shape[0]), cfg.appearance_dim, cfg.embeds_per_sensor]
     floats.append(cfg.duration)
+
+
+def render(cfg, params, rays, pdf_u, field_of_round=(2, 2), lane_mode=False):
+    """cfg: neurad_studio_b200.NeuRADConfig; params: reference-named tensors (CPU); rays: dict of CPU tensors."""
+    lib = ctypes.CDLL(build())
+    lib.emul_render.restype = ctypes.c_int
+    pk = _Pack()
+    _pack_params(pk, cfg, params, pdf_u, field_of_round)
+    keep, P = pk.keep, pk.P
+    sp = cfg.sampling
     n = rays["origins"].shape[0]
     P(rays["origins"].float())
     P(rays["directions"].float())
@@ -105,9 +124,52 @@ def render(cfg, params, rays, pdf_u, field_of_round=(2, 2), lane_mode=False):
     for k in out:
         P(out[k])
         out[k] = keep[-1]
-    c_ptrs = (ctypes.c_void_p * len(ptrs))(*ptrs)
-    c_ints = (ctypes.c_int * len(ints))(*ints)
-    c_floats = (ctypes.c_float * len(floats))(*floats)
+    c_ptrs, c_ints, c_floats = pk.c_arrays()
     rc = lib.emul_render(c_ptrs, c_ints, c_floats, ctypes.c_longlong(n), ctypes.c_int(1 if lane_mode else 0))
+    assert rc == 0
+    return out
+
+
+def gaussian(origins, directions, pixel_area, bins_e):
+    """sample_gaussian() of csrc/nff_device.h on frustums: (mean [N,S,3], std [N,S])."""
+    lib = ctypes.CDLL(build())
+    n, s = bins_e.shape[0], bins_e.shape[1] - 1
+    ts = [t.float().contiguous() for t in (origins.reshape(-1, 3), directions.reshape(-1, 3), pixel_area.reshape(-1), bins_e)]
+    mean, std = torch.zeros(n, s, 3), torch.zeros(n, s)
+    rc = lib.emul_gaussian(*[ctypes.c_void_p(t.data_ptr()) for t in ts], ctypes.c_longlong(n), ctypes.c_int(s),
+                           ctypes.c_void_p(mean.data_ptr()), ctypes.c_void_p(std.data_ptr()))
+    assert rc == 0
+    return mean, std
+
+
+def encoding(cfg, params, pdf_u, field, mean, std, times, directions=None, want_features=True, want_density=False,
+             want_actor_id=True):
+    """The module-level NeuRADHashEncoding.forward device code (csrc/nff_modules.h) of field `field` (0 main, 1 / 2
+    proposal): mean [N,S,3], std [N,S], times [N], directions [N,3] / [N,S,3] / None -> {"features" [N*S,D],
+    "directions" [N,S,3], "actor_id" [N,S], "density" [N,S]} (same contract as B200Backend.neurad_encoding)."""
+    lib = ctypes.CDLL(build())
+    lib.emul_encoding.restype = ctypes.c_int
+    pk = _Pack()
+    _pack_params(pk, cfg, params, pdf_u, (2, 2))
+    g = [cfg.grid, cfg.proposal_grid_1, cfg.proposal_grid_2][field].static
+    n, s = mean.shape[0], mean.shape[1]
+    ex = _Pack()
+    ex.P(mean.float().reshape(n, s, 3))
+    ex.P(std.float().reshape(n, s))
+    ex.P(None if times is None else times.float().reshape(n, -1)[:, 0])
+    per_ray = directions is not None and directions.numel() == 3 * n and s != 1
+    ex.P(None if directions is None else directions.float().reshape(n, 3) if per_ray else directions.float().reshape(n, s, 3))
+    out = {}
+    feats = ex.P(torch.zeros(n * s, g.num_levels * g.hashgrid_dim) if want_features else None)
+    dens = ex.P(torch.zeros(n, s) if want_density else None)
+    dout = ex.P(torch.zeros(n, s, 3) if directions is not None else None)
+    aid = ex.P(torch.zeros(n, s, dtype=torch.int32) if want_actor_id else None)
+    for k, v in (("features", feats), ("density", dens), ("directions", dout), ("actor_id", aid)):
+        if v is not None:
+            out[k] = v
+    c_ptrs, c_ints, c_floats = pk.c_arrays()
+    c_extra = (ctypes.c_void_p * len(ex.ptrs))(*ex.ptrs)
+    rc = lib.emul_encoding(c_ptrs, c_ints, c_floats, c_extra, ctypes.c_longlong(n), ctypes.c_int(s), ctypes.c_int(field),
+                           ctypes.c_int(1 if per_ray else 0))
     assert rc == 0
     return out

@@ -1,0 +1,132 @@
+"""Bodies of the module-level seam tests (Field, Sampler, NeuRADHashEncoding as stand-alone operators),
+shared by tests/test_zz_module_seams_gpu.py (dev = "cuda": the real library through the C ABI) and
+tests/test_module_glue_cpu.py (dev = "cpu": the same Python glue over tests/fake_backend.py)."""
+import pytest
+import torch
+
+from oracle import neurad_oracle as O
+from oracle.convert import to_oracle_cfg
+from tests.helpers import cfg_from_meta, load_golden
+
+
+def rel_to_max(a, b):
+    a, b = a.detach().cpu().float(), b.detach().cpu().float()
+    return (a.reshape(b.shape) - b).abs().max().item() / (b.abs().max().item() + 1e-30)
+
+
+def _model_and_bundle(name, dev):
+    from neurad_studio_b200.nerfstudio_api import NeuRADModel, RayBundle
+
+    meta, g = load_golden(name)
+    cfg = cfg_from_meta(meta)
+    p, r, ref = g["param"], g["ray"], g["ref"]
+    model = NeuRADModel(cfg)
+    model.load_reference_state_dict(p)
+    model = model.to(dev).eval()
+    rb = RayBundle(origins=r["origins"].to(dev), directions=r["directions"].to(dev), pixel_area=r["pixel_area"].to(dev),
+                   times=r["times"].to(dev), metadata={"is_lidar": r["is_lidar"].to(dev), "sensor_idxs": r["sensor_idx"].to(dev)})
+    return meta, cfg, model, rb, g
+
+
+def _samples_from_edges(model, rb, edges, dev, spacing_bins=None):
+    from neurad_studio_b200.nerfstudio_api import Frustums, RaySamples
+
+    sb = model._scale_pixel_area(rb.flatten())
+    fr = Frustums(sb.origins, sb.directions, edges.to(dev).contiguous(), sb.pixel_area.reshape(-1, 1))
+    return RaySamples(fr, spacing_bins if spacing_bins is not None else torch.linspace(0, 1, edges.shape[1]).to(dev),
+                      times=sb.times.reshape(-1, 1), metadata=sb.metadata)
+
+
+def field_forward_matches_reference_golden(name, dev):
+    """NeuRADField.forward(ray_samples) on the reference's own final samples -> FEATURE / SDF / ALPHA."""
+    from neurad_studio_b200.nerfstudio_api import FieldHeadNames
+
+    meta, cfg, model, rb, g = _model_and_bundle(name, dev)
+    ref = g["ref"]
+    n = len(rb)
+    starts, ends = ref["starts"].reshape(n, -1), ref["ends"].reshape(n, -1)
+    rs = _samples_from_edges(model, rb, torch.cat([starts, ends[:, -1:]], 1), dev)
+    out = model.field(rs)
+    assert out[FieldHeadNames.FEATURE].shape == (n, starts.shape[1], cfg.nff_out_dim)
+    assert rel_to_max(out[FieldHeadNames.SDF], ref["sdf"]) < 1e-4
+    assert rel_to_max(out[FieldHeadNames.ALPHA], ref["alpha"]) < 1e-4
+    assert rel_to_max(out[FieldHeadNames.FEATURE], ref["field_feature"]) < 1e-4
+    model._bind().check_status()
+
+
+def proposal_density_and_encoding_match_reference_golden(name, dev):
+    """NeuRADProposalField.get_density on the reference's proposal samples (both rounds use proposal_fields[1]: the
+    late-binding quirk), actor ids bit-exact; NeuRADHashEncoding.forward vs the oracle's restatement."""
+    meta, cfg, model, rb, g = _model_and_bundle(name, dev)
+    ref = g["ref"]
+    n = len(rb)
+    for rd in (0, 1):
+        rs = _samples_from_edges(model, rb, ref[f"bins_e_{rd}"].reshape(n, -1), dev)
+        dens, _ = model.density_fns[rd](rs), None
+        assert dens.shape == (n, rs.shape[1], 1)
+        assert rel_to_max(dens, ref[f"density_{rd}"]) < 1e-4
+        w = rs.get_weights(dens)
+        assert rel_to_max(w, ref[f"prop_weights_{rd}"]) < 1e-4
+        be = model._bind()
+        gs = rs.frustums.get_fast_isotropic_gaussian()
+        enc = be.neurad_encoding(2, gs.mean, gs.std, rs.times, None, want_actor_id=True)
+        assert torch.equal(enc["actor_id"].cpu().long(), ref[f"actor_id_{rd}"].reshape(n, -1).long())
+    # the encoding module of the main field against the oracle
+    starts, ends = ref["starts"].reshape(n, -1), ref["ends"].reshape(n, -1)
+    rs = _samples_from_edges(model, rb, torch.cat([starts, ends[:, -1:]], 1), dev)
+    gs = rs.frustums.get_fast_isotropic_gaussian()
+    feats, dirs = model.field.hashgrid(gs, rs.times, rs.frustums.directions)
+    sb = model._scale_pixel_area(rb.flatten())
+    trace = {}
+    with torch.no_grad():
+        O.main_field(g["param"], to_oracle_cfg(cfg), sb.origins.cpu(), sb.directions.cpu(), sb.pixel_area.reshape(-1).cpu(),
+                     sb.times.reshape(-1).cpu(), starts, ends, trace)
+    assert feats.shape == (n * starts.shape[1], model.field.hashgrid.get_out_dim())
+    assert rel_to_max(feats, trace["grid_features"].reshape(feats.shape)) < 1e-4
+    assert dirs.shape == (n, starts.shape[1], 3)
+
+
+def proposal_sampler_and_module_walk_match_reference_golden(name, dev):
+    """ProposalNetworkSampler.forward(ray_bundle, density_fns) and the whole per-module walk of get_nff_outputs
+    (fused=False) against the reference's goldens and against the fused kernels."""
+    meta, cfg, model, rb, g = _model_and_bundle(name, dev)
+    ref = g["ref"]
+    n = len(rb)
+    mod = model.get_nff_outputs(rb, fused=False)
+    fused = model.get_nff_outputs(rb)
+    tol_depth = 5e-4 if meta["beta"] >= 20 else 1e-4
+    for k in ("features", "accumulation", "prop_depth_0", "prop_depth_1"):
+        assert rel_to_max(mod[k], ref[k]) < 1e-4, k
+        assert rel_to_max(mod[k], fused[k]) < 1e-4, k
+    assert rel_to_max(mod["depth"], ref["depth"]) < tol_depth
+    rs_list, w_list = mod["ray_samples_list"], mod["weights_list"]
+    assert [r.shape[1] for r in rs_list] == [128, 64, 32] and len(w_list) == 3
+    for rd in (0, 1):
+        assert rel_to_max(w_list[rd], ref[f"prop_weights_{rd}"]) < 1e-4
+    for lvl in (1, 2):
+        assert (rs_list[lvl].spacing_bins.cpu() - ref[f"bins_s_{lvl}"].reshape(n, -1)).abs().max().item() < 1e-5
+    e2 = rs_list[2].frustums.bin_edges.cpu()
+    assert rel_to_max(e2[:, :-1], ref["bins_e_2"].reshape(n, -1)[:, :-1]) < 1e-4
+    assert torch.all(e2[:, -1] == cfg.sampling.sky_distance)  # the sky sample (neurad.py:451-455)
+    model._bind().check_status()
+
+
+def module_operator_errors_and_empty_inputs(dev):
+    from neurad_studio_b200.backend import B200Backend
+    from neurad_studio_b200.lib import B200NerfError
+
+    meta, cfg, model, rb, g = _model_and_bundle("nff_actors.npz", dev)
+    be = model._bind()
+    fresh = B200Backend(torch.device(dev, 0))
+    fresh.cfg = cfg
+    z3, z1 = torch.zeros(2, 4, 3, device=dev), torch.zeros(2, 4, device=dev)
+    with pytest.raises(B200NerfError):
+        fresh.neurad_encoding(0, z3, z1, torch.zeros(2, device=dev))  # set_field_grids missing
+    with pytest.raises(B200NerfError):
+        be.neurad_encoding(0, z3 + 0.5, z1 + 0.1, torch.zeros(2, device=dev), want_density=True)  # main field has no density head
+    out = be.neurad_encoding(2, z3[:0], z1[:0], torch.zeros(0, device=dev), want_density=True)
+    assert out["features"].shape[0] == 0 and out["density"].shape == (0, 4)
+    e = be.spacing_to_euclidean(torch.rand(0, 5, device=dev), None, torch.zeros(0, device=dev))
+    assert e.shape == (0, 5)
+    with pytest.raises(B200NerfError):
+        be.spacing_to_euclidean(torch.rand(3, 5, device=dev), None, torch.ones(3, device=dev), "power", 1.0, 0.1)

@@ -1,0 +1,32 @@
+"""CPU: the Python glue of the module-level seams (RaySamples / PDFSampler / ProposalNetworkSampler / NeuRADField /
+NeuRADProposalField mirrors, the per-module walk of NeuRADModel.get_nff_outputs(fused=False), B200Backend.field_forward's
+composition) run over tests/fake_backend.py -- the new device code through the host emulation, the older operators through
+the oracle -- against the reference's golden values.  The same bodies run on the GPU in test_zz_module_seams_gpu.py."""
+import pytest
+
+from tests import module_seam_cases as C
+from tests.fake_backend import FakeBackend
+
+
+@pytest.fixture(autouse=True)
+def fake_backend(monkeypatch):
+    from neurad_studio_b200 import nerfstudio_api
+
+    be = FakeBackend()
+    monkeypatch.setattr(nerfstudio_api, "get_backend", lambda device: be)
+    return be
+
+
+@pytest.mark.parametrize("name", ["nff_static.npz", "nff_actors.npz", "nff_sharp.npz"])
+def test_field_forward_glue(name):
+    C.field_forward_matches_reference_golden(name, "cpu")
+
+
+@pytest.mark.parametrize("name", ["nff_static.npz", "nff_actors.npz"])
+def test_proposal_density_and_encoding_glue(name):
+    C.proposal_density_and_encoding_match_reference_golden(name, "cpu")
+
+
+@pytest.mark.parametrize("name", ["nff_static.npz", "nff_actors.npz", "nff_sharp.npz"])
+def test_proposal_sampler_and_module_walk_glue(name):
+    C.proposal_sampler_and_module_walk_match_reference_golden(name, "cpu")
