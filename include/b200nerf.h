@@ -213,12 +213,13 @@ int b200nerf_isotropic_gaussian_fwd(b200nerf_ctx* ctx, const float* origins, con
 /* NeuRADHashEncoding.forward(positions: GaussiansStd, times, directions) (field_components/neurad_encoding.py:150-187)
  * of field `field`: scene contraction, static grid, dynamic-actor assignment at each ray's time, per-actor grids
  * (zero padded to the static width), anti-aliasing rescale.  mean [N,S,3], std [N,S], times [N] (the reference
- * reads times[:,0]; may be NULL without actors), directions [N,3] (directions_per_ray != 0) or [N,S,3] or NULL.
+ * reads times[:,0]; may be NULL without actors), flip [N] (+1 / -1) or NULL = the training-mode random actor flip
+ * drawn by the caller (:212-219), directions [N,3] (directions_per_ray != 0) or [N,S,3] or NULL.
  * Outputs (each optional): features [N*S, L*F]; density [N,S] = trunc_exp(density_decoder(features))
  * (NeuRADProposalField.get_density, fields/neurad_field.py:208-213); directions_out [N,S,3] (box frame and
  * renormalised for samples inside an actor, :203-209); actor_id [N,S] (actor index or -1). */
 int b200nerf_neurad_encoding_fwd(b200nerf_ctx* ctx, int field, const float* mean, const float* std, const float* times,
-                                 const float* directions, int directions_per_ray, int64_t n_rays, int n_samples,
+                                 const float* flip, const float* directions, int directions_per_ray, int64_t n_rays, int n_samples,
                                  float* features, float* density, float* directions_out, int32_t* actor_id,
                                  void* stream);
 
@@ -239,6 +240,54 @@ int b200nerf_field_tail_fwd(b200nerf_ctx* ctx, const float* geo_out, const float
 int b200nerf_spacing_to_euclidean(b200nerf_ctx* ctx, int kind, float power_lambda, float power_scaling,
                                   const float* nears, const float* fars, const float* bins_s, int64_t n_rays,
                                   int n_edges, float* bins_e, void* stream);
+
+/* ---- backward operators: gradients of the module-level operators with respect to the trained
+ * parameters.  The reference gets these from torch autograd (torch mode) or tiny-cuda-nn's backward kernels; here each
+ * forward operator has a hand-written counterpart.  Sample positions carry no gradient (PDFSampler detaches its bins,
+ * ray_samplers.py:363-364; camera / actor-pose optimisation is not part of this row).  All grad_* outputs are
+ * ACCUMULATED into (+=): zero them first (they are the .grad tensors of the parameters). */
+
+/* Backward of b200nerf_neurad_encoding_fwd for field `field`: scatter-add into the hash-table gradients.
+ *   features mode: dfeatures [N*S, L*F] = dL/d features.
+ *   density mode : density [N,S] (the forward output) and ddensity [N,S] = dL/d density; folds in the proposal head
+ *                  (trunc_exp, Linear(L*F,1,bias=False)); grad_decoder [L*F] receives dL/d density_decoder.weight.
+ * grad_static_table [L*T, F] (or NULL); grad_actor_tables_host = HOST array of n_actors device pointers
+ * [La*Ta, F] (entries or the array may be NULL). */
+int b200nerf_neurad_encoding_bwd(b200nerf_ctx* ctx, int field, const float* mean, const float* std, const float* times,
+                                 const float* flip, int64_t n_rays, int n_samples, const float* dfeatures,
+                                 const float* density, const float* ddensity, float* grad_static_table,
+                                 float* const* grad_actor_tables_host, float* grad_decoder, void* stream);
+
+/* nerfacc.render_weight_from_alpha backward (call site models/neurad.py:717): alphas, dweights [N,S] -> dalphas. */
+int b200nerf_alpha_to_weights_bwd(b200nerf_ctx* ctx, const float* alphas, const float* dweights, int64_t n_rays, int s,
+                                  float* dalphas, void* stream);
+/* RaySamples.get_weights backward (cameras/rays.py:188-210): deltas, densities, dweights [N,S] -> ddensities. */
+int b200nerf_density_to_weights_bwd(b200nerf_ctx* ctx, const float* deltas, const float* densities,
+                                    const float* dweights, int64_t n_rays, int s, float* ddensities, void* stream);
+
+/* FeatureRenderer / AccumulationRenderer / render_depth_simple backward (renderers.py:83-85,349; neurad.py:727-734):
+ * given dL/d values_out [N,C], dL/d accumulation [N], dL/d depth [N] (each optional) -> dweights [N,S] and
+ * dvalues [N,S,C] (each optional). */
+int b200nerf_composite_bwd(b200nerf_ctx* ctx, const float* weights, const float* values, int n_channels,
+                           const float* starts, const float* ends, const float* dvalues_out,
+                           const float* daccumulation, const float* ddepth, int64_t n_rays, int n_samples,
+                           float* dweights, float* dvalues, void* stream);
+
+/* NeuRADField heads backward (fields/neurad_field.py:139-149): dfeature [P,G], dsdf [P], dalpha [P],
+ * dmlp_feature_in [P,G+16] (each optional) -> dgeo_out [P,G+1]; dbeta [1] (optional) accumulates
+ * dL/d(|beta| + 1e-4).  dL/d mlp_feature_out is dfeature itself. */
+int b200nerf_field_heads_bwd(b200nerf_ctx* ctx, const float* geo_out, const float* dfeature, const float* dsdf,
+                             const float* dalpha, const float* dmlp_feature_in, int64_t n_points, int geo_feat_dim,
+                             float beta, float* dgeo_out, float* dbeta, void* stream);
+
+/* MLP backward pieces (field_components/mlp.py:142-178).  For layer l with input X (a hidden pre-activation Z when
+ * relu_x != 0, so act = ReLU) and output gradient dY:
+ *   b200nerf_linear_wgrad : dweight [out,in] += dY^T act(X), dbias [out] += sum dY            (widths <= 64)
+ *   dX = dY W runs through b200nerf_mlp_fwd with the transposed weight (tcgen05), then
+ *   b200nerf_relu_bwd     : dZ *= (Z > 0) in place. */
+int b200nerf_linear_wgrad(b200nerf_ctx* ctx, const float* x, const float* dy, int64_t n_rows, int in_dim, int out_dim,
+                          int relu_x, float* dweight, float* dbias, void* stream);
+int b200nerf_relu_bwd(b200nerf_ctx* ctx, const float* z, float* dz, int64_t n, void* stream);
 
 /* Kernel variant used by b200nerf_nff_render_fwd:
  *   2 (default) ray-per-lane mapping (a warp = 32 adjacent rays at one sample index: coherent gathers), MLPs on the

@@ -1,0 +1,186 @@
+"""torch.autograd bindings of the module-level operators: every forward operator of the library
+that sits on the training path gets its hand-written backward operator, so `loss.backward()` through the reference-API
+mirror (NeuRADField / NeuRADProposalField / RaySamples.get_weights / renderers, `get_nff_outputs(fused=False)`) reaches
+the hash tables, density decoders, MLPs and beta without any torch reference math in between.
+
+The reference gets these gradients from torch autograd (implementation="torch") or tiny-cuda-nn's backward kernels
+(field_components/encodings.py:386-404, mlp.py:116-140).  Sample positions carry no gradient: PDFSampler detaches its
+bins (ray_samplers.py:363-364), NeuRADHashEncoding computes the actor split under no_grad (neurad_encoding.py:166-168),
+and pose / camera optimisation is outside this row."""
+from __future__ import annotations
+
+from typing import List, Optional
+
+import torch
+from torch import Tensor
+from torch.autograd import Function
+
+
+class EncodingFn(Function):
+    """NeuRADHashEncoding.forward: (features [N*S,D], directions [N,S,3]); gradients go to the hash tables."""
+
+    @staticmethod
+    def forward(ctx, be, field: int, mean, std, times, directions, flip, static_table, *actor_tables):
+        out = be.neurad_encoding(field, mean, std, times, directions, flip=flip)
+        ctx.be, ctx.field = be, field
+        ctx.table_shapes = [static_table.shape] + [t.shape for t in actor_tables]
+        ctx.save_for_backward(mean, std, times, flip)
+        dirs = out.get("directions")
+        if dirs is None:
+            dirs = mean.new_zeros(0)
+        ctx.mark_non_differentiable(dirs)
+        return out["features"], dirs
+
+    @staticmethod
+    def backward(ctx, dfeatures, _ddirs):
+        mean, std, times, flip = ctx.saved_tensors
+        needs = ctx.needs_input_grad[7:]
+        shapes, dev = ctx.table_shapes, dfeatures.device
+        g_static = torch.zeros(shapes[0], device=dev) if needs[0] else None
+        g_actors: List[Optional[Tensor]] = [torch.zeros(shapes[1 + a], device=dev) if nd else None for a, nd in enumerate(needs[1:])]
+        ctx.be.neurad_encoding_bwd(ctx.field, mean, std, times, {"static": g_static, "actors": g_actors},
+                                   dfeatures=dfeatures.contiguous(), flip=flip)
+        return (None,) * 7 + (g_static, *g_actors)
+
+
+class DensityFn(Function):
+    """NeuRADProposalField.get_density: density [N,S]; gradients go to the hash tables and the density decoder."""
+
+    @staticmethod
+    def forward(ctx, be, field: int, mean, std, times, flip, static_table, decoder_weight, *actor_tables):
+        out = be.neurad_encoding(field, mean, std, times, None, want_features=False, want_density=True, flip=flip)
+        ctx.be, ctx.field = be, field
+        ctx.save_for_backward(mean, std, times, flip, out["density"])
+        ctx.decoder_shape = decoder_weight.shape
+        ctx.table_shapes = [static_table.shape] + [t.shape for t in actor_tables]
+        return out["density"]
+
+    @staticmethod
+    def backward(ctx, ddensity):
+        mean, std, times, flip, density = ctx.saved_tensors
+        needs = ctx.needs_input_grad[6:]
+        shapes, dev = ctx.table_shapes, ddensity.device
+        g_static = torch.zeros(shapes[0], device=dev) if needs[0] else None
+        g_dec = torch.zeros(ctx.decoder_shape, device=dev) if needs[1] else None
+        g_actors = [torch.zeros(shapes[1 + a], device=dev) if nd else None for a, nd in enumerate(needs[2:])]
+        ctx.be.neurad_encoding_bwd(ctx.field, mean, std, times, {"static": g_static, "actors": g_actors, "decoder": g_dec},
+                                   density=density, ddensity=ddensity.contiguous(), flip=flip)
+        return (None,) * 6 + (g_static, g_dec, *g_actors)
+
+
+class MlpFn(Function):
+    """MLP.forward (ReLU hidden layers, linear output) on the tcgen05 operator; args: x, then weight_0, bias_0, ..."""
+
+    @staticmethod
+    def forward(ctx, be, x, *wb):
+        ws, bs = list(wb[0::2]), list(wb[1::2])
+        ctx.be = be
+        ctx.save_for_backward(x, *wb)
+        return be.mlp_fwd(x, ws, bs)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, *wb = ctx.saved_tensors
+        ws, bs = list(wb[0::2]), list(wb[1::2])
+        needs = ctx.needs_input_grad
+        dws = [torch.zeros_like(w) if needs[2 + 2 * l] or needs[3 + 2 * l] else None for l, w in enumerate(ws)]
+        dbs = [torch.zeros_like(b) if dws[l] is not None else None for l, b in enumerate(bs)]
+        dx = ctx.be.mlp_bwd(x, ws, bs, dy.contiguous(), dws, dbs, need_dx=needs[1])
+        grads = []
+        for l in range(len(ws)):
+            grads += [dws[l] if needs[2 + 2 * l] else None, dbs[l] if needs[3 + 2 * l] else None]
+        return (None, dx, *grads)
+
+
+class FieldMidFn(Function):
+    """[geo_embedding | SH4((d+1)/2)] (fields/neurad_field.py:139-141); gradient to geo_out only."""
+
+    @staticmethod
+    def forward(ctx, be, geo_out, directions):
+        ctx.be = be
+        ctx.save_for_backward(geo_out)
+        return be._field_mid(geo_out, directions)
+
+    @staticmethod
+    def backward(ctx, dx2):
+        (geo,) = ctx.saved_tensors
+        dgeo, _ = ctx.be.field_heads_bwd(geo, None, None, None, dx2.contiguous())
+        return None, dgeo, None
+
+
+class FieldTailFn(Function):
+    """feature = geo_embedding + mlp_feature_out, sdf, alpha = sigmoid(-sdf (|beta| + 1e-4)) (neurad_field.py:141-149)."""
+
+    @staticmethod
+    def forward(ctx, be, geo_out, mlp_out, beta_param):
+        ctx.be = be
+        ctx.save_for_backward(geo_out, beta_param)
+        return be._field_tail(geo_out, mlp_out)
+
+    @staticmethod
+    def backward(ctx, dfeature, dsdf, dalpha):
+        geo, beta_param = ctx.saved_tensors
+        dgeo, dbeta = ctx.be.field_heads_bwd(geo, dfeature.contiguous(), dsdf, dalpha, None)
+        # d(|beta| + 1e-4) / d beta = sign(beta)  (model_components/utils.py:38-41)
+        g_beta = (dbeta.reshape(beta_param.shape) * torch.sign(beta_param)) if ctx.needs_input_grad[3] else None
+        return None, dgeo, dfeature, g_beta
+
+
+class AlphaToWeightsFn(Function):
+    """nerfacc.render_weight_from_alpha on dense [N,S] (models/neurad.py:717)."""
+
+    @staticmethod
+    def forward(ctx, be, alphas):
+        ctx.be = be
+        ctx.save_for_backward(alphas)
+        return be.alpha_to_weights(alphas)
+
+    @staticmethod
+    def backward(ctx, dw):
+        (alphas,) = ctx.saved_tensors
+        return None, ctx.be.alpha_to_weights_bwd(alphas, dw.contiguous())
+
+
+class DensityToWeightsFn(Function):
+    """RaySamples.get_weights (cameras/rays.py:188-210); gradient to the densities (bin widths are detached)."""
+
+    @staticmethod
+    def forward(ctx, be, deltas, densities):
+        ctx.be = be
+        ctx.save_for_backward(deltas, densities)
+        return be.density_to_weights(deltas, densities)
+
+    @staticmethod
+    def backward(ctx, dw):
+        deltas, densities = ctx.saved_tensors
+        return None, None, ctx.be.density_to_weights_bwd(deltas, densities, dw.contiguous())
+
+
+class CompositeFn(Function):
+    """FeatureRenderer / AccumulationRenderer / render_depth_simple in one pass: returns (values [N,C], accumulation
+    [N,1], depth [N,1]); tensors that were not asked for come back empty."""
+
+    @staticmethod
+    def forward(ctx, be, weights, values, starts, ends, want_acc: bool, want_depth: bool):
+        out = be.composite(weights, values, starts, ends, "simple" if want_depth else None, want_accumulation=want_acc)
+        ctx.be = be
+        ctx.save_for_backward(weights, values if values is not None else weights.new_zeros(0),
+                              starts if starts is not None else weights.new_zeros(0),
+                              ends if ends is not None else weights.new_zeros(0))
+        ctx.has = (values is not None, want_acc, want_depth)
+        e = weights.new_zeros(0)
+        return out.get("values", e), out.get("accumulation", e), out.get("depth", e)
+
+    @staticmethod
+    def backward(ctx, dvalues_out, dacc, ddepth):
+        weights, values, starts, ends = ctx.saved_tensors
+        has_v, has_a, has_d = ctx.has
+        dw, dv = ctx.be.composite_bwd(weights, values if has_v else None, starts if has_d else None, ends if has_d else None,
+                                      dvalues_out.contiguous() if has_v else None, dacc.contiguous() if has_a else None,
+                                      ddepth.contiguous() if has_d else None,
+                                      need_dweights=ctx.needs_input_grad[1], need_dvalues=has_v and ctx.needs_input_grad[2])
+        if dw is not None:
+            dw = dw.reshape(weights.shape)
+        if dv is not None:
+            dv = dv.reshape(values.shape)
+        return None, dw, dv, None, None, None, None

@@ -337,10 +337,11 @@ class B200Backend:
 
     def neurad_encoding(self, field: int, mean: torch.Tensor, std: torch.Tensor, times: Optional[torch.Tensor],
                         directions: Optional[torch.Tensor] = None, want_features: bool = True, want_density: bool = False,
-                        want_actor_id: bool = False) -> Dict[str, torch.Tensor]:
+                        want_actor_id: bool = False, flip: Optional[torch.Tensor] = None) -> Dict[str, torch.Tensor]:
         """NeuRADHashEncoding.forward (field_components/neurad_encoding.py:150-187) of the bound field `field`:
         mean [N,S,3], std [N,S] (or [N,S,1]), times [N] (or [N,1] / [N,S,1]: the reference reads times[:,0]),
-        directions [N,3] or [N,S,3] -> {"features" [N*S,D], "directions" [N,S,3], "density" [N,S], "actor_id" [N,S]}."""
+        directions [N,3] or [N,S,3] -> {"features" [N*S,D], "directions" [N,S,3], "density" [N,S], "actor_id" [N,S]}.
+        `flip` [N] (+1 / -1): the training-mode random actor flip drawn by the caller (:212-219)."""
         m = self._dev(mean)
         n, s = m.shape[0], m.shape[1]
         m = m.reshape(n, s, 3)
@@ -364,16 +365,18 @@ class B200Backend:
             do = out["directions"] = torch.empty(n, s, 3, device=self.device)
         if want_actor_id:
             ai = out["actor_id"] = torch.empty(n, s, device=self.device, dtype=torch.int32)
-        self._check(self.lib.b200nerf_neurad_encoding_fwd(self._h, field, _ptr(m), _ptr(sd), _ptr(t), _ptr(d), int(bool(per_ray)), n, s,
-                                                          _ptr(f), _ptr(de), _ptr(do), _ptr(ai), self._stream))
+        fl = None if flip is None else self._dev(flip).reshape(n)
+        self._check(self.lib.b200nerf_neurad_encoding_fwd(self._h, field, _ptr(m), _ptr(sd), _ptr(t), _ptr(fl), _ptr(d), int(bool(per_ray)),
+                                                          n, s, _ptr(f), _ptr(de), _ptr(do), _ptr(ai), self._stream))
         return out
 
-    def field_forward(self, mean: torch.Tensor, std: torch.Tensor, times: torch.Tensor, directions: torch.Tensor) -> Dict[str, torch.Tensor]:
+    def field_forward(self, mean: torch.Tensor, std: torch.Tensor, times: torch.Tensor, directions: torch.Tensor,
+                      flip: Optional[torch.Tensor] = None) -> Dict[str, torch.Tensor]:
         """NeuRADField.forward (fields/neurad_field.py:128-152) on gaussians: encoding -> mlp_geo (tcgen05) ->
         [geo_embedding | SH] -> mlp_feature (tcgen05) -> residual, sdf, alpha.  Five launches, all ours:
         {"feature" [N,S,G], "sdf" [N,S,1], "alpha" [N,S,1]}."""
         n, s = mean.shape[0], mean.shape[1]
-        enc = self.neurad_encoding(FIELD_MAIN, mean, std, times, directions)
+        enc = self.neurad_encoding(FIELD_MAIN, mean, std, times, directions, flip=flip)
         gw, gb = self._field_mlps["geo"]
         fw, fb = self._field_mlps["feature"]
         geo = self.mlp_fwd(enc["features"], gw, gb)
@@ -408,6 +411,107 @@ class B200Backend:
         self._check(self.lib.b200nerf_spacing_to_euclidean(self._h, self.SPACINGS[spacing], power_lambda, power_scaling, _ptr(nr), _ptr(f),
                                                            _ptr(b), b.shape[0], b.shape[1], _ptr(out), self._stream))
         return out
+
+    # ------------------------------------------------------------------------- backward operators
+    def neurad_encoding_bwd(self, field: int, mean: torch.Tensor, std: torch.Tensor, times: Optional[torch.Tensor],
+                            grads: Dict[str, object], dfeatures: Optional[torch.Tensor] = None, density: Optional[torch.Tensor] = None,
+                            ddensity: Optional[torch.Tensor] = None, flip: Optional[torch.Tensor] = None) -> None:
+        """Backward of neurad_encoding: scatter-adds into grads["static"] [L*T,F], grads["actors"] (list of per-actor
+        [La*Ta,F] tensors or None) and, in density mode (density + ddensity given), grads["decoder"] [L*F]."""
+        m = self._dev(mean)
+        n, s = m.shape[0], m.shape[1]
+        m = m.reshape(n, s, 3)
+        sd = self._dev(std).reshape(n, s)
+        t = None
+        if times is not None:
+            t = self._dev(times.reshape(n, -1)[:, 0] if times.numel() != n else times.reshape(n))
+        fl = None if flip is None else self._dev(flip).reshape(n)
+        df = None if dfeatures is None else self._dev(dfeatures).reshape(n * s, -1)
+        de = None if density is None else self._dev(density).reshape(n, s)
+        dd = None if ddensity is None else self._dev(ddensity).reshape(n, s)
+        for g in [grads.get("static"), grads.get("decoder")] + list(grads.get("actors") or []):
+            assert g is None or (g.is_contiguous() and g.dtype == torch.float32 and g.device == self.device)
+        acts = grads.get("actors")
+        arr = None
+        if acts:
+            arr = (ctypes.c_void_p * len(acts))(*[None if g is None else g.data_ptr() for g in acts])
+        self._check(self.lib.b200nerf_neurad_encoding_bwd(self._h, field, _ptr(m), _ptr(sd), _ptr(t), _ptr(fl), n, s, _ptr(df), _ptr(de), _ptr(dd),
+                                                          _ptr(grads.get("static")), arr, _ptr(grads.get("decoder")), self._stream))
+
+    def alpha_to_weights_bwd(self, alphas: torch.Tensor, dweights: torch.Tensor) -> torch.Tensor:
+        a, dw = self._dev(alphas), self._dev(dweights)
+        out = torch.empty_like(a)
+        self._check(self.lib.b200nerf_alpha_to_weights_bwd(self._h, _ptr(a), _ptr(dw), a.shape[0], a.shape[1], _ptr(out), self._stream))
+        return out
+
+    def density_to_weights_bwd(self, deltas: torch.Tensor, densities: torch.Tensor, dweights: torch.Tensor) -> torch.Tensor:
+        d, r, dw = self._dev(deltas), self._dev(densities), self._dev(dweights)
+        out = torch.empty_like(d)
+        self._check(self.lib.b200nerf_density_to_weights_bwd(self._h, _ptr(d), _ptr(r), _ptr(dw), d.shape[0], d.shape[1], _ptr(out), self._stream))
+        return out
+
+    def composite_bwd(self, weights: torch.Tensor, values: Optional[torch.Tensor], starts: Optional[torch.Tensor], ends: Optional[torch.Tensor],
+                      dvalues_out: Optional[torch.Tensor], dacc: Optional[torch.Tensor], ddepth: Optional[torch.Tensor],
+                      need_dweights: bool = True, need_dvalues: bool = True) -> Tuple[Optional[torch.Tensor], Optional[torch.Tensor]]:
+        """Backward of composite(values / accumulation / "simple" depth): returns (dweights [N,S], dvalues [N,S,C])."""
+        w = self._dev(weights)
+        n, s = w.shape[0], w.shape[1]
+        w = w.reshape(n, s)
+        c = 0 if values is None else values.shape[-1]
+        v = None if values is None else self._dev(values).reshape(n, s, c)
+        st = None if starts is None else self._dev(starts).reshape(n, s)
+        en = None if ends is None else self._dev(ends).reshape(n, s)
+        go = None if dvalues_out is None else self._dev(dvalues_out).reshape(n, c)
+        ga = None if dacc is None else self._dev(dacc).reshape(n)
+        gd = None if ddepth is None else self._dev(ddepth).reshape(n)
+        dw = torch.empty(n, s, device=self.device) if need_dweights else None
+        dv = torch.empty(n, s, c, device=self.device) if (need_dvalues and go is not None) else None
+        self._check(self.lib.b200nerf_composite_bwd(self._h, _ptr(w), _ptr(v), c, _ptr(st), _ptr(en), _ptr(go), _ptr(ga), _ptr(gd), n, s,
+                                                    _ptr(dw), _ptr(dv), self._stream))
+        return dw, dv
+
+    def field_heads_bwd(self, geo: torch.Tensor, dfeature: Optional[torch.Tensor], dsdf: Optional[torch.Tensor],
+                        dalpha: Optional[torch.Tensor], dx2: Optional[torch.Tensor]) -> Tuple[torch.Tensor, torch.Tensor]:
+        """NeuRADField heads backward: returns (dgeo_out [P,G+1], dbeta [1] = dL/d(|beta|+1e-4))."""
+        p, gdim = geo.shape[0], geo.shape[1] - 1
+        f = lambda t, *shape: None if t is None else self._dev(t).reshape(*shape)  # noqa: E731
+        dgeo = torch.empty(p, gdim + 1, device=self.device)
+        dbeta = torch.zeros(1, device=self.device)
+        self._check(self.lib.b200nerf_field_heads_bwd(self._h, _ptr(geo), _ptr(f(dfeature, p, gdim)), _ptr(f(dsdf, p)), _ptr(f(dalpha, p)),
+                                                      _ptr(f(dx2, p, gdim + 16)), p, gdim, self._beta, _ptr(dgeo), _ptr(dbeta), self._stream))
+        return dgeo, dbeta
+
+    def linear_wgrad(self, x: torch.Tensor, dy: torch.Tensor, relu_x: bool, dweight: torch.Tensor, dbias: Optional[torch.Tensor]) -> None:
+        """dweight [out,in] += dY^T act(X); dbias [out] += sum dY (act = ReLU when X is a hidden pre-activation)."""
+        xs, ds = self._dev(x), self._dev(dy)
+        self._check(self.lib.b200nerf_linear_wgrad(self._h, _ptr(xs), _ptr(ds), xs.shape[0], xs.shape[1], ds.shape[1], int(relu_x),
+                                                   _ptr(dweight), _ptr(dbias), self._stream))
+
+    def relu_bwd(self, z: torch.Tensor, dz: torch.Tensor) -> torch.Tensor:
+        """dz *= (z > 0), in place."""
+        self._check(self.lib.b200nerf_relu_bwd(self._h, _ptr(z), _ptr(dz), dz.numel(), self._stream))
+        return dz
+
+    def mlp_bwd(self, x: torch.Tensor, weights: Sequence[torch.Tensor], biases: Optional[Sequence[Optional[torch.Tensor]]], dy: torch.Tensor,
+                dweights: Sequence[Optional[torch.Tensor]], dbiases: Sequence[Optional[torch.Tensor]], need_dx: bool = True) -> Optional[torch.Tensor]:
+        """MLP.forward backward (field_components/mlp.py:142-178): accumulates into dweights[l] / dbiases[l] (entries may
+        be None) and returns dL/dx.  Hidden pre-activations are recomputed with prefix forward passes (tcgen05); dX = dY W
+        runs through the same tensor-core operator with the transposed weight; dW through linear_wgrad."""
+        x2 = self._dev(x).reshape(-1, x.shape[-1])
+        nl = len(weights)
+        bs = list(biases) if biases is not None else [None] * nl
+        zs = [self.mlp_fwd(x2, weights[: l + 1], bs[: l + 1]) for l in range(nl - 1)]  # pre-activation of hidden layer l
+        g = self._dev(dy).reshape(x2.shape[0], -1)
+        for l in range(nl - 1, -1, -1):
+            inp = x2 if l == 0 else zs[l - 1]
+            if dweights[l] is not None:
+                self.linear_wgrad(inp, g, l > 0, dweights[l], dbiases[l])
+            if l == 0 and not need_dx:
+                return None
+            g = self.mlp_fwd(g, [weights[l].t().contiguous()], None)
+            if l > 0:
+                g = self.relu_bwd(zs[l - 1], g)
+        return g.reshape(*x.shape)
 
     # ------------------------------------------------------------------- generic sampler / renderer operators
     SPACINGS = {"uniform": 0, "lindisp": 1, "power": 2, "sqrt": 3, "log": 4}

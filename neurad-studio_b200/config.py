@@ -99,6 +99,7 @@ class NeuRADConfig:
     rgb_upsample_factor: int = 3
     rgb_hidden_dim: int = 32
     actor_bbox_padding: Tuple[float, float, float] = (0.25, 0.25, 0.1)
+    actor_flip_prob: float = 0.5  # ActorSettings.flip_prob (neurad_encoding.py:50), training mode only
     # scene-level constants (dataset metadata in the reference)
     static_scale: float = 100.0
     duration: float = 8.0

@@ -69,6 +69,7 @@ struct b200nerf_ctx {
   float* d_dec_wf32[8] = {};          // [49][ci][co] fp32 (CUDA-core reference kernel)
   float* d_dec_bias = nullptr;        // [8][32] folded conv + BN biases
   float* d_dec_small = nullptr;       // in conv w [32*in] b [32] | convT w [32*32*9] b [32] | out conv w [3*32] b [3]
+  float** d_grad_actor_ptrs = nullptr;  // [kModMaxActors] per-actor gradient accumulators of the current encoding_bwd call
 };
 
 namespace {
@@ -913,6 +914,7 @@ int b200nerf_create(int device_ordinal, b200nerf_ctx** out) {
   CUDA_TRY(cudaMalloc((void**)&c->d_minmax, 2 * sizeof(unsigned)));
   c->handoff_rays = (int64_t)1 << 21;
   CUDA_TRY(cudaMalloc((void**)&c->d_handoff, sizeof(float) * (kS2 + 1) * c->handoff_rays));
+  CUDA_TRY(cudaMalloc((void**)&c->d_grad_actor_ptrs, sizeof(float*) * kModMaxActors));
   *out = c;
   return 0;
 }
@@ -927,6 +929,7 @@ int b200nerf_destroy(b200nerf_ctx* c) {
   cudaFree(c->d_main_mlp);
   cudaFree(c->d_main_mlp_nn);
   cudaFree(c->d_lane_scratch);
+  cudaFree(c->d_grad_actor_ptrs);
   cudaFree(c->d_handoff);
   cudaFree(c->d_minmax);
   cudaFree(c->d_lidar_mlp);
@@ -1320,7 +1323,7 @@ int b200nerf_isotropic_gaussian_fwd(b200nerf_ctx* c, const float* origins, const
 }
 
 int b200nerf_neurad_encoding_fwd(b200nerf_ctx* c, int field, const float* mean, const float* std, const float* times,
-                                 const float* directions, int directions_per_ray, int64_t n_rays, int n_samples,
+                                 const float* flip, const float* directions, int directions_per_ray, int64_t n_rays, int n_samples,
                                  float* features, float* density, float* directions_out, int32_t* actor_id,
                                  void* stream) {
   REQUIRE(c, "ctx is NULL");
@@ -1338,7 +1341,7 @@ int b200nerf_neurad_encoding_fwd(b200nerf_ctx* c, int field, const float* mean, 
   REQUIRE(mean && std, "NULL argument");
   REQUIRE(c->actors.n_actors == 0 || times, "times are required when the scene has actors");
   DeviceGuard g(c->device);
-  EncodingArgs a{mean, std, times, directions, features, density, directions_out, actor_id, n_rays, n_samples,
+  EncodingArgs a{mean, std, times, directions, flip, features, density, directions_out, actor_id, n_rays, n_samples,
                  directions_per_ray ? 1 : 0};
   const unsigned grid = (unsigned)((n_rays + kModWarps - 1) / kModWarps);
   neurad_encoding_fwd_kernel<<<grid, kModWarps * 32, 0, (cudaStream_t)stream>>>(fg, c->actors, a);
@@ -1384,6 +1387,122 @@ int b200nerf_spacing_to_euclidean(b200nerf_ctx* c, int kind, float power_lambda,
   DeviceGuard g(c->device);
   const int64_t n = n_rays * n_edges;
   spacing_to_euclidean_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(a, nears, fars, bins_s, n_rays, n_edges, bins_e);
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+// --------------------------------------------------------------------------- backward operators
+int b200nerf_neurad_encoding_bwd(b200nerf_ctx* c, int field, const float* mean, const float* std, const float* times,
+                                 const float* flip, int64_t n_rays, int n_samples, const float* dfeatures,
+                                 const float* density, const float* ddensity, float* grad_static_table,
+                                 float* const* grad_actor_tables_host, float* grad_decoder, void* stream) {
+  REQUIRE(c, "ctx is NULL");
+  REQUIRE(field >= 0 && field < 3, "field must be B200NERF_FIELD_MAIN / PROP0 / PROP1");
+  if (!c->have_field[field]) return fail(B200NERF_ERR_STATE, "b200nerf_set_field_grids was not called for this field");
+  REQUIRE(n_rays >= 0 && n_samples >= 1, "bad sample grid");
+  REQUIRE((dfeatures != nullptr) != (ddensity != nullptr), "pass either dfeatures or (density, ddensity)");
+  REQUIRE(!ddensity || density, "density mode needs the forward density");
+  const FieldGrids& fg = c->fields[field];
+  if (ddensity && !fg.decoder) return fail(B200NERF_ERR_STATE, "b200nerf_set_proposal_decoder was not called for this field");
+  REQUIRE(!grad_decoder || ddensity, "grad_decoder belongs to the density mode");
+  if (c->actors.n_actors > kModMaxActors) return fail(B200NERF_ERR_UNSUPPORTED, "more than 64 actors");
+  if (n_rays == 0) return 0;
+  REQUIRE(mean && std, "NULL argument");
+  REQUIRE(c->actors.n_actors == 0 || times, "times are required when the scene has actors");
+  DeviceGuard g(c->device);
+  float* const* d_ptrs = nullptr;
+  if (grad_actor_tables_host && c->actors.n_actors > 0) {
+    CUDA_TRY(cudaMemcpyAsync(c->d_grad_actor_ptrs, grad_actor_tables_host, sizeof(float*) * c->actors.n_actors,
+                             cudaMemcpyHostToDevice, (cudaStream_t)stream));
+    d_ptrs = c->d_grad_actor_ptrs;
+  }
+  EncodingBwdArgs a{mean, std, times, flip, dfeatures, density, ddensity, grad_static_table, d_ptrs, grad_decoder, n_rays,
+                    n_samples};
+  const unsigned grid = (unsigned)((n_rays + kModWarps - 1) / kModWarps);
+  neurad_encoding_bwd_kernel<<<grid, kModWarps * 32, 0, (cudaStream_t)stream>>>(fg, c->actors, a);
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+int b200nerf_alpha_to_weights_bwd(b200nerf_ctx* c, const float* alphas, const float* dweights, int64_t n_rays, int s,
+                                  float* dalphas, void* stream) {
+  REQUIRE(c, "ctx is NULL");
+  REQUIRE(n_rays >= 0 && s >= 1, "bad shape");
+  if (n_rays == 0) return 0;
+  REQUIRE(alphas && dweights && dalphas, "NULL argument");
+  DeviceGuard g(c->device);
+  weights_bwd_kernel<true><<<(unsigned)((n_rays + 127) / 128), 128, 0, (cudaStream_t)stream>>>(alphas, nullptr, dweights, n_rays, s, dalphas);
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+int b200nerf_density_to_weights_bwd(b200nerf_ctx* c, const float* deltas, const float* densities, const float* dweights,
+                                    int64_t n_rays, int s, float* ddensities, void* stream) {
+  REQUIRE(c, "ctx is NULL");
+  REQUIRE(n_rays >= 0 && s >= 1, "bad shape");
+  if (n_rays == 0) return 0;
+  REQUIRE(deltas && densities && dweights && ddensities, "NULL argument");
+  DeviceGuard g(c->device);
+  weights_bwd_kernel<false><<<(unsigned)((n_rays + 127) / 128), 128, 0, (cudaStream_t)stream>>>(deltas, densities, dweights, n_rays, s,
+                                                                                                 ddensities);
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+int b200nerf_composite_bwd(b200nerf_ctx* c, const float* weights, const float* values, int n_channels, const float* starts,
+                           const float* ends, const float* dvalues_out, const float* daccumulation, const float* ddepth,
+                           int64_t n_rays, int n_samples, float* dweights, float* dvalues, void* stream) {
+  REQUIRE(c, "ctx is NULL");
+  REQUIRE(n_rays >= 0 && n_samples >= 1 && n_channels >= 0, "bad shape");
+  if (n_rays == 0) return 0;
+  REQUIRE(dweights || dvalues, "nothing to compute");
+  REQUIRE(!dvalues_out || (weights && values && n_channels > 0), "dvalues_out needs weights and values");
+  REQUIRE(!dvalues || dvalues_out, "dvalues needs dvalues_out");
+  REQUIRE(!ddepth || (starts && ends), "ddepth needs starts and ends");
+  DeviceGuard g(c->device);
+  const int64_t n = n_rays * n_samples;
+  composite_bwd_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(weights, values, n_channels, starts, ends, dvalues_out,
+                                                                                      daccumulation, ddepth, n_rays, n_samples, dweights, dvalues);
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+int b200nerf_field_heads_bwd(b200nerf_ctx* c, const float* geo_out, const float* dfeature, const float* dsdf,
+                             const float* dalpha, const float* dmlp_feature_in, int64_t n_points, int geo_feat_dim,
+                             float beta, float* dgeo_out, float* dbeta, void* stream) {
+  REQUIRE(c, "ctx is NULL");
+  REQUIRE(n_points >= 0 && geo_feat_dim >= 1, "bad shape");
+  if (n_points == 0) return 0;
+  REQUIRE(geo_out && dgeo_out, "NULL argument");
+  DeviceGuard g(c->device);
+  field_heads_bwd_kernel<<<(unsigned)((n_points + 127) / 128), 128, 0, (cudaStream_t)stream>>>(geo_out, dfeature, dsdf, dalpha, dmlp_feature_in,
+                                                                                                n_points, geo_feat_dim, beta, dgeo_out, dbeta);
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+int b200nerf_relu_bwd(b200nerf_ctx* c, const float* z, float* dz, int64_t n, void* stream) {
+  REQUIRE(c, "ctx is NULL");
+  REQUIRE(n >= 0, "bad shape");
+  if (n == 0) return 0;
+  REQUIRE(z && dz, "NULL argument");
+  DeviceGuard g(c->device);
+  relu_bwd_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(z, dz, n);
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+int b200nerf_linear_wgrad(b200nerf_ctx* c, const float* x, const float* dy, int64_t n_rows, int in_dim, int out_dim,
+                          int relu_x, float* dweight, float* dbias, void* stream) {
+  REQUIRE(c, "ctx is NULL");
+  REQUIRE(n_rows >= 0, "bad shape");
+  REQUIRE(in_dim >= 1 && in_dim <= 64 && out_dim >= 1 && out_dim <= 64, "layer widths must be <= 64");
+  if (n_rows == 0) return 0;
+  REQUIRE(x && dy && dweight, "NULL argument");
+  DeviceGuard g(c->device);
+  const int64_t tiles = (n_rows + kWgradRows - 1) / kWgradRows;
+  const int grid = (int)(tiles < (int64_t)c->sm_count * 4 ? tiles : (int64_t)c->sm_count * 4);
+  linear_wgrad_kernel<<<grid, kWgradThreads, 0, (cudaStream_t)stream>>>(x, dy, n_rows, in_dim, out_dim, relu_x, dweight, dbias);
   CUDA_TRY(cudaGetLastError());
   return 0;
 }

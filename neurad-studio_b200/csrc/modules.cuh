@@ -31,6 +31,7 @@ struct EncodingArgs {
   const float* std;     // [N,S]
   const float* times;   // [N] (the reference reads times[:, 0], neurad_encoding.py:194)
   const float* dirs;    // [N,3] (dirs_per_ray) or [N,S,3] or NULL
+  const float* flip;    // [N] +1 / -1 or NULL: training-mode actor flip (neurad_encoding.py:212-219)
   float* features;      // [N*S, D] or NULL
   float* density;       // [N,S] or NULL: trunc_exp(Linear(D,1,bias=False)(features)) (neurad_field.py:208-213)
   float* dirs_out;      // [N,S,3] or NULL
@@ -56,6 +57,7 @@ __global__ void __launch_bounds__(kModWarps * 32) neurad_encoding_fwd_kernel(con
   }
   __syncwarp();
   const int D = fg.stat.L * fg.stat.F;
+  const float flip = a.flip ? a.flip[ray] : 1.0f;
   for (int s = ln; s < a.S; s += 32) {
     const int64_t i = ray * a.S + s;
     Gauss g = {a.mean[3 * i], a.mean[3 * i + 1], a.mean[3 * i + 2], a.std[i]};
@@ -65,7 +67,7 @@ __global__ void __launch_bounds__(kModWarps * 32) neurad_encoding_fwd_kernel(con
       dir[0] = dp[0]; dir[1] = dp[1]; dir[2] = dp[2];
     }
     float feat[kModMaxDim];
-    const int aid = neurad_encode_point(fg, frames[warp], A.n_actors, g, feat, a.dirs ? dir : nullptr);
+    const int aid = neurad_encode_point(fg, frames[warp], A.n_actors, g, feat, a.dirs ? dir : nullptr, flip);
     if (a.features)
       for (int k = 0; k < D; ++k) a.features[i * D + k] = feat[k];
     if (a.density) {
@@ -109,6 +111,185 @@ __global__ void field_tail_kernel(const float* __restrict__ geo_out, const float
   const float sd = geo_out[i * (G + 1)];
   if (sdf) sdf[i] = sd;
   if (alpha) alpha[i] = frcp(fadd(1.0f, expf(fmul(sd, beta))));
+}
+
+// =============================================================================================== backward operators
+// the gradients of the module-level operators with respect to the trained parameters.
+
+struct EncodingBwdArgs {
+  const float* mean;       // [N,S,3]
+  const float* std;        // [N,S]
+  const float* times;      // [N]
+  const float* flip;       // [N] or NULL
+  const float* dfeatures;  // [N*S, D]            (features mode)
+  const float* density;    // [N,S]  forward output (density mode: NeuRADProposalField.get_density)
+  const float* ddensity;   // [N,S]  dL/d density  (density mode)
+  float* grad_static;      // [L*T, F] accumulated (+=), or NULL
+  float* const* grad_actor_tables;  // device array [n_actors] of [La*Ta, F] accumulators (entries may be NULL), or NULL
+  float* grad_decoder;     // [D] accumulated, density mode, or NULL
+  int64_t n_rays;
+  int32_t S;
+};
+
+// Backward of neurad_encoding_fwd_kernel: scatter-add into the hash tables (RED.ADD.F32).  Density mode folds the
+// proposal head in: g = dL/d density * density (trunc_exp' = exp), dfeat_k = g * decoder_k, d decoder_k += g * feat_k.
+__global__ void __launch_bounds__(kModWarps * 32) neurad_encoding_bwd_kernel(const FieldGrids fg, const Actors A,
+                                                                              const EncodingBwdArgs a) {
+  __shared__ ActorFrame frames[kModWarps][kModMaxActors];
+  __shared__ float dec_part[kModWarps][kModMaxDim];
+  const int warp = threadIdx.x >> 5, ln = threadIdx.x & 31;
+  const int64_t ray = (int64_t)blockIdx.x * kModWarps + warp;
+  const int D = fg.stat.L * fg.stat.F;
+  const bool density_mode = a.ddensity != nullptr;
+  float dec_acc[kModMaxDim];
+  if (density_mode && a.grad_decoder)
+    for (int k = 0; k < D; ++k) dec_acc[k] = 0.f;
+  if (ray < a.n_rays) {
+    if (A.n_actors > 0) {
+      int left, right;
+      float frac;
+      keyframe_bracket(A, a.times[ray], left, right, frac);
+      for (int k = ln; k < A.n_actors; k += 32) actor_frame(A, k, left, right, frac, frames[warp][k]);
+    }
+    __syncwarp();
+    const float flip = a.flip ? a.flip[ray] : 1.0f;
+    for (int s = ln; s < a.S; s += 32) {
+      const int64_t i = ray * a.S + s;
+      Gauss g = {a.mean[3 * i], a.mean[3 * i + 1], a.mean[3 * i + 2], a.std[i]};
+      float dfeat[kModMaxDim];
+      if (density_mode) {
+        const float gd = a.ddensity[i] * a.density[i];
+        if (a.grad_decoder) {
+          float feat[kModMaxDim];
+          neurad_encode_point(fg, frames[warp], A.n_actors, g, feat, nullptr, flip);
+          for (int k = 0; k < D; ++k) dec_acc[k] = fmaf(gd, feat[k], dec_acc[k]);
+        }
+        for (int k = 0; k < D; ++k) dfeat[k] = gd * __ldg(fg.decoder + k);
+      } else {
+        for (int k = 0; k < D; ++k) dfeat[k] = a.dfeatures[i * D + k];
+      }
+      neurad_encode_point_bwd(fg, a.grad_static, a.grad_actor_tables, frames[warp], A.n_actors, g, flip, dfeat);
+    }
+  }
+  if (density_mode && a.grad_decoder) {  // warp, then block reduction; one atomic per CTA and decoder weight
+    for (int k = 0; k < D; ++k) {
+      const float t = warp_sum(ray < a.n_rays ? dec_acc[k] : 0.f);
+      if (ln == 0) dec_part[warp][k] = t;
+    }
+    __syncthreads();
+    if (threadIdx.x < D) {
+      float t = 0.f;
+      for (int w = 0; w < kModWarps; ++w) t += dec_part[w][threadIdx.x];
+      atomicAdd(a.grad_decoder + threadIdx.x, t);
+    }
+  }
+}
+
+// nerfacc.render_weight_from_alpha / RaySamples.get_weights backward: one thread per ray, sequential scans (S is at
+// most a few hundred; the [N,S] rows are read with a stride, so this is a latency-tolerant but simple first version).
+template <bool FROM_ALPHA>
+__global__ void weights_bwd_kernel(const float* __restrict__ a, const float* __restrict__ b, const float* __restrict__ dw,
+                                   int64_t n_rays, int S, float* __restrict__ out) {
+  const int64_t ray = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (ray >= n_rays) return;
+  if (FROM_ALPHA)
+    alpha_weights_bwd_ray(a + ray * S, dw + ray * S, S, out + ray * S);
+  else
+    density_weights_bwd_ray(a + ray * S, b + ray * S, dw + ray * S, S, out + ray * S);
+}
+
+// Renderers backward (FeatureRenderer / AccumulationRenderer / render_depth_simple): out_c = sum_s w_s v_sc,
+// acc = sum_s w_s, depth = sum_s w_s (start_s + end_s)/2  =>  dv_sc = w_s dout_c;
+// dw_s = sum_c dout_c v_sc + dacc + ddepth (start_s + end_s)/2.   One thread per (ray, sample).
+__global__ void composite_bwd_kernel(const float* __restrict__ weights, const float* __restrict__ values, int C,
+                                     const float* __restrict__ starts, const float* __restrict__ ends,
+                                     const float* __restrict__ dvalues_out, const float* __restrict__ dacc,
+                                     const float* __restrict__ ddepth, int64_t n_rays, int S, float* __restrict__ dweights,
+                                     float* __restrict__ dvalues) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_rays * S) return;
+  const int64_t ray = i / S;
+  float dw = dacc ? dacc[ray] : 0.f;
+  if (ddepth) dw = fmaf(ddepth[ray], (starts[i] + ends[i]) * 0.5f, dw);
+  if (dvalues_out) {
+    const float w = weights[i];
+    for (int c = 0; c < C; ++c) {
+      const float go = dvalues_out[ray * C + c];
+      if (dweights) dw = fmaf(go, values[i * C + c], dw);
+      if (dvalues) dvalues[i * C + c] = w * go;
+    }
+  }
+  if (dweights) dweights[i] = dw;
+}
+
+// NeuRADField heads backward (neurad_field.py:139-149): given dL/dfeature [P,G], dL/dsdf [P] (or NULL), dL/dalpha [P]
+// (or NULL) and dL/d(mlp_feature input) [P,G+16] (or NULL; its SH part has no trained parameter behind it):
+//   d geo_out[:,0]  = dsdf + dalpha * (-beta * alpha * (1 - alpha))
+//   d geo_out[:,1:] = dfeature + dx2[:, :G]              d mlp_feature_out = dfeature (the caller reuses the tensor)
+//   d beta         += sum dalpha * (-sdf * alpha * (1 - alpha))
+__global__ void field_heads_bwd_kernel(const float* __restrict__ geo_out, const float* __restrict__ dfeature,
+                                       const float* __restrict__ dsdf, const float* __restrict__ dalpha,
+                                       const float* __restrict__ dx2, int64_t n, int G, float beta, float* __restrict__ dgeo,
+                                       float* __restrict__ dbeta) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  float db = 0.f;
+  if (i < n) {
+    const float sd = geo_out[i * (G + 1)];
+    float g0 = dsdf ? dsdf[i] : 0.f;
+    if (dalpha) {
+      const float al = frcp(fadd(1.0f, expf(fmul(sd, beta))));
+      const float t = dalpha[i] * al * (1.0f - al);
+      g0 -= beta * t;
+      db = -sd * t;
+    }
+    dgeo[i * (G + 1)] = g0;
+    for (int k = 0; k < G; ++k)
+      dgeo[i * (G + 1) + 1 + k] = (dfeature ? dfeature[i * G + k] : 0.f) + (dx2 ? dx2[i * (G + kSh) + k] : 0.f);
+  }
+  if (dbeta) {
+    db = warp_sum(db);
+    if ((threadIdx.x & 31) == 0 && db != 0.f) atomicAdd(dbeta, db);
+  }
+}
+
+// dZ *= (Z > 0): ReLU backward on a hidden pre-activation.
+__global__ void relu_bwd_kernel(const float* __restrict__ z, float* __restrict__ dz, int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n && !(z[i] > 0.f)) dz[i] = 0.f;
+}
+
+// Weight / bias gradient of one Linear layer of the tiny MLPs: dW[o][i] += sum_p dY[p][o] * act(X[p][i]),
+// db[o] += sum_p dY[p][o]; K, N <= 64.  A CTA walks row tiles of 32, stages X / dY in shared memory and keeps its
+// share of the N*K outputs in registers (first version on the CUDA cores: K = rows is the long GEMM dimension here and
+// the output is at most 64 x 64; a split-K tcgen05 version is the next step for this operator).
+constexpr int kWgradThreads = 256, kWgradRows = 32, kWgradMaxOut = 64 * 64 / kWgradThreads;
+__global__ void __launch_bounds__(kWgradThreads) linear_wgrad_kernel(const float* __restrict__ x, const float* __restrict__ dy,
+                                                                     int64_t n_rows, int K, int N, int relu_x,
+                                                                     float* __restrict__ dW, float* __restrict__ db) {
+  __shared__ float xs[kWgradRows * 64];
+  __shared__ float dys[kWgradRows * 64];
+  float acc[kWgradMaxOut];
+#pragma unroll
+  for (int j = 0; j < kWgradMaxOut; ++j) acc[j] = 0.f;
+  float bacc = 0.f;  // thread o < N accumulates db[o]
+  const int64_t n_tiles = (n_rows + kWgradRows - 1) / kWgradRows;
+  for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+    const int64_t r0 = t * kWgradRows;
+    const int rows = (int)(n_rows - r0 < kWgradRows ? n_rows - r0 : kWgradRows);
+    for (int e = threadIdx.x; e < rows * K; e += kWgradThreads) xs[e] = x[r0 * K + e];
+    for (int e = threadIdx.x; e < rows * N; e += kWgradThreads) dys[e] = dy[r0 * N + e];
+    __syncthreads();
+    wgrad_tile(threadIdx.x, kWgradThreads, xs, dys, rows, K, N, relu_x != 0, acc);
+    if (db && threadIdx.x < N)
+      for (int r = 0; r < rows; ++r) bacc += dys[r * N + threadIdx.x];
+    __syncthreads();
+  }
+#pragma unroll
+  for (int j = 0; j < kWgradMaxOut; ++j) {
+    const int e = threadIdx.x + j * kWgradThreads;
+    if (e < N * K) atomicAdd(dW + e, acc[j]);
+  }
+  if (db && threadIdx.x < N) atomicAdd(db + threadIdx.x, bacc);
 }
 
 }  // namespace nff

@@ -86,7 +86,6 @@ NFF_D int actor_containing(const ActorFrame* frames, int n_actors, float x, floa
 
 // HashEncoding.pytorch_fwd + _rescale_grid_features for one contracted gaussian, generic L / F:
 // out[l*F + f] = trilerp_l,f * 1/max(1, 2*res_l*std)   (encodings.py:425-466, neurad_encoding.py:297-304).
-// `cells` (optional, [L]) keeps each level's cell for the backward operator.
 NFF_D void encode_levels(const float* NFF_RESTRICT table, const Grid& gr, const Gauss& g, float* out) {
   for (int l = 0; l < gr.L; ++l) {
     Cell c = grid_cell(g.x, g.y, g.z, gr.res[l]);
@@ -104,14 +103,16 @@ NFF_D void encode_levels(const float* NFF_RESTRICT table, const Grid& gr, const 
 
 // NeuRADHashEncoding.forward for one sample (field_components/neurad_encoding.py:150-187): static features, or the
 // containing actor's features zero-padded to the static width; the direction goes to the box frame, renormalised
-// with +EPS (:203-209).  Returns the actor index or -1.  `feat` must hold fg.stat.L * fg.stat.F floats.
+// with +EPS (:203-209).  Returns the actor index or -1.  `feat` must hold fg.stat.L * fg.stat.F floats.  `flip` (+1 / -1 per
+// ray) is the training-mode random actor flip, drawn by the caller.
 NFF_D int neurad_encode_point(const FieldGrids& fg, const ActorFrame* frames, int n_actors, const Gauss& g,
-                              float* feat, float dir[3]) {
+                              float* feat, float dir[3], float flip = 1.0f) {
   float pb[3];
   const int a = n_actors > 0 ? actor_containing(frames, n_actors, g.x, g.y, g.z, pb) : -1;
   const int D = fg.stat.L * fg.stat.F;
   if (a >= 0) {
-    Gauss ga = {pb[0], pb[1], pb[2], g.std};
+    // training-mode actor flip (neurad_encoding.py:212-219): x -> -x in the box frame for the whole ray
+    Gauss ga = {flip < 0.0f ? -pb[0] : pb[0], pb[1], pb[2], g.std};
     ga = contract(ga, fg.actor_scale);
     encode_levels(fg.actor_tables[a], fg.act, ga, feat);
     for (int i = fg.act.L * fg.act.F; i < D; ++i) feat[i] = 0.0f;  // F.pad(actor_features, (0, D - Da))
@@ -122,6 +123,7 @@ NFF_D int neurad_encode_point(const FieldGrids& fg, const ActorFrame* frames, in
       float q2 = fadd(fadd(fmul(M[8], dir[0]), fmul(M[9], dir[1])), fmul(M[10], dir[2]));
       float n = fadd(fsqrt(fadd(fadd(fmul(q0, q0), fmul(q1, q1)), fmul(q2, q2))), 1.0e-7f);
       dir[0] = fdiv(q0, n); dir[1] = fdiv(q1, n); dir[2] = fdiv(q2, n);
+      if (flip < 0.0f) dir[0] = -dir[0];
     }
   } else {
     Gauss gs = contract(g, fg.static_scale);
@@ -131,6 +133,10 @@ NFF_D int neurad_encode_point(const FieldGrids& fg, const ActorFrame* frames, in
 }
 
 // --------------------------------------------------------------------------------------------- backward pieces
+// SURVEY 8f row f2.  Gradients flow to the parameters the reference trains through this path (hash tables, proposal
+// density decoders, MLPs, beta); sample positions carry no gradient (PDFSampler detaches its bins,
+// ray_samplers.py:363-364; pose / camera optimisation is out of scope for this row).
+//
 // d(out[l*F+f]) / d(table rows): the trilinear corner weights of `trilerp` times the anti-aliasing weight.  Corner
 // order as cell_rows(): ccc, cfc, ffc, fcc, ccf, cff, fff, fcf.
 NFF_D void corner_weights(const Cell& c, float w[8]) {
@@ -143,6 +149,106 @@ NFF_D void corner_weights(const Cell& c, float w[8]) {
   w[5] = ox * iy * iz;
   w[6] = ix * iy * iz;
   w[7] = ix * oy * iz;
+}
+
+// Backward of encode_levels(): grad_table[row*F + f] += dfeat[l*F + f] * level_weight_l * corner_weight_k.  When a
+// coordinate is an exact integer ceil == floor and two corners name the same row; both contributions are added,
+// like the forward reads the row twice (encodings.py:436-466).
+NFF_D void encode_levels_bwd(float* grad_table, const Grid& gr, const Gauss& g, const float* dfeat) {
+  for (int l = 0; l < gr.L; ++l) {
+    Cell c = grid_cell(g.x, g.y, g.z, gr.res[l]);
+    uint32_t r[8];
+    cell_rows(c, gr.mask, r);
+    float cw[8];
+    corner_weights(c, cw);
+    float* base = grad_table + (size_t)l * gr.T * gr.F;
+    const float w = level_weight(gr.res[l], g.std);
+    for (int f = 0; f < gr.F; ++f) {
+      const float gs = dfeat[l * gr.F + f] * w;
+      if (gs == 0.0f) continue;
+      for (int k = 0; k < 8; ++k) atomic_add(base + (size_t)r[k] * gr.F + f, gs * cw[k]);
+    }
+  }
+}
+
+// Backward of neurad_encode_point(): routes dfeat to the static table or to the containing actor's table (the zero
+// padded tail of an actor sample's feature row has no parameter behind it).  `flip` is the per-ray actor flip of
+// training mode (+1 / -1, neurad_encoding.py:212-219).
+NFF_D int neurad_encode_point_bwd(const FieldGrids& fg, float* grad_static, float* const* grad_actor_tables,
+                                  const ActorFrame* frames, int n_actors, const Gauss& g, float flip, const float* dfeat) {
+  float pb[3];
+  const int a = n_actors > 0 ? actor_containing(frames, n_actors, g.x, g.y, g.z, pb) : -1;
+  if (a >= 0) {
+    Gauss ga = {flip < 0.0f ? -pb[0] : pb[0], pb[1], pb[2], g.std};
+    ga = contract(ga, fg.actor_scale);
+    if (grad_actor_tables && grad_actor_tables[a]) encode_levels_bwd(grad_actor_tables[a], fg.act, ga, dfeat);
+  } else if (grad_static) {
+    Gauss gs = contract(g, fg.static_scale);
+    encode_levels_bwd(grad_static, fg.stat, gs, dfeat);
+  }
+  return a;
+}
+
+// nerfacc.render_weight_from_alpha backward for one ray (sequential; S <= a few hundred): w_i = a_i * T_i,
+// T_i = prod_{j<i} (1 - a_j)  =>  dL/da_i = dw_i * T_i - (sum_{k>i} dw_k * w_k) / (1 - a_i).
+// The quotient is guarded like nerfacc's backward (1 - a clamped from below) so a saturated sample gives a finite
+// gradient.
+NFF_D void alpha_weights_bwd_ray(const float* alpha, const float* dw, int S, float* dalpha) {
+  float T = 1.0f;
+  // forward pass for the transmittances, stored in dalpha[] temporarily
+  for (int i = 0; i < S; ++i) {
+    dalpha[i] = T;
+    T *= 1.0f - alpha[i];
+  }
+  float suffix = 0.0f;  // sum_{k>i} dw_k * w_k
+  for (int i = S - 1; i >= 0; --i) {
+    const float Ti = dalpha[i];
+    const float one_m = fmaxf(1.0f - alpha[i], 1e-10f);
+    dalpha[i] = dw[i] * Ti - suffix / one_m;
+    suffix += dw[i] * alpha[i] * Ti;
+  }
+}
+
+// RaySamples.get_weights backward for one ray: w_i = (1 - e^{-a_i}) * e^{-A_i}, a = delta * density,
+// A_i = sum_{j<i} a_j  =>  dL/da_i = dw_i * e^{-a_i} * e^{-A_i} - sum_{k>i} dw_k * w_k;  d density_i = delta_i * dL/da_i.
+NFF_D void density_weights_bwd_ray(const float* delta, const float* density, const float* dw, int S, float* ddensity) {
+  float A = 0.0f;
+  for (int i = 0; i < S; ++i) {
+    ddensity[i] = A;  // stash A_i
+    A += delta[i] * density[i];
+  }
+  float suffix = 0.0f;
+  for (int i = S - 1; i >= 0; --i) {
+    const float a = delta[i] * density[i];
+    const float eA = expf(-ddensity[i]), ea = expf(-a);
+    const float w = (1.0f - ea) * eA;
+    ddensity[i] = delta[i] * (dw[i] * ea * eA - suffix);
+    suffix += dw[i] * w;
+  }
+}
+
+// One tile of the weight gradient of a Linear layer, dW[o][i] += sum_r dY[r][o] * act(X[r][i]) (act = ReLU when the
+// layer's input is a hidden activation stored as its pre-activation).  Thread `tid` of `nthreads` owns the outputs
+// e = tid + j * nthreads (e = o*K + i), j < MAXOUT, and keeps them in acc[] (registers: the j loop is unrolled).
+// xs [rows][K], dys [rows][N] are the staged tiles.
+template <int MAXOUT>
+NFF_D void wgrad_tile(int tid, int nthreads, const float* xs, const float* dys, int rows, int K, int N, bool relu_x,
+                      float (&acc)[MAXOUT]) {
+#if defined(__CUDACC__)
+#pragma unroll
+#endif
+  for (int j = 0; j < MAXOUT; ++j) {
+    const int e = tid + j * nthreads;
+    if (e >= N * K) continue;
+    const int o = e / K, i = e - o * K;
+    float a = acc[j];
+    for (int r = 0; r < rows; ++r) {
+      float x = xs[r * K + i];
+      if (relu_x) x = fmaxf(x, 0.0f);
+      a = fmaf(dys[r * N + o], x, a);
+    }
+    acc[j] = a;
+  }
 }
 
 }  // namespace nff

@@ -40,6 +40,8 @@ NFF_D float frcp(float a) { return __frcp_rn(a); }
 NFF_D float fsqrt(float a) { return __fsqrt_rn(a); }
 template <typename T>
 NFF_D T ldg(const T* p) { return __ldg(p); }
+// scatter-accumulate of the backward operators (hash-grid gradients): RED.ADD.F32 to global memory
+NFF_D void atomic_add(float* p, float v) { atomicAdd(p, v); }
 }  // namespace simt
 
 #else
@@ -101,6 +103,7 @@ inline float frcp(float a) { return 1.0f / a; }
 inline float fsqrt(float a) { return std::sqrt(a); }
 template <typename T>
 inline T ldg(const T* p) { return *p; }
+inline void atomic_add(float* p, float v) { *p += v; }  // the backward emulation runs its "threads" one after the other
 }  // namespace simt
 
 inline float fminf_(float a, float b) { return std::fmin(a, b); }

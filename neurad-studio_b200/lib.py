@@ -94,8 +94,18 @@ SIGNATURES = {
                                        c_void_p, c_void_p]),
     "b200nerf_isotropic_gaussian_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p,
                                                 c_void_p, c_void_p]),
-    "b200nerf_neurad_encoding_fwd": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int64, c_int,
-                                             c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "b200nerf_neurad_encoding_fwd": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int64,
+                                             c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "b200nerf_neurad_encoding_bwd": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p,
+                                             c_void_p, c_void_p, c_void_p, POINTER(c_void_p), c_void_p, c_void_p]),
+    "b200nerf_alpha_to_weights_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p]),
+    "b200nerf_density_to_weights_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p]),
+    "b200nerf_composite_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                       c_int64, c_int, c_void_p, c_void_p, c_void_p]),
+    "b200nerf_field_heads_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_float,
+                                         c_void_p, c_void_p, c_void_p]),
+    "b200nerf_linear_wgrad": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    "b200nerf_relu_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
     "b200nerf_field_mid_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p]),
     "b200nerf_field_tail_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_float, c_void_p, c_void_p, c_void_p,
                                         c_void_p]),

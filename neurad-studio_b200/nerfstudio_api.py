@@ -34,6 +34,7 @@ from typing import Dict, List, Optional, Tuple
 import torch
 from torch import Tensor, nn
 
+from . import autograd as AG
 from .backend import B200Backend
 from .config import HashGridSettings, NeuRADConfig
 
@@ -291,11 +292,15 @@ class RaySamples:
         kind, lam, scaling, nears, fars = self.spacing
         return get_backend(bins.device).spacing_to_euclidean(bins, nears, fars, kind, lam, scaling)
 
-    @torch.no_grad()
     def get_weights(self, densities: Tensor) -> Tensor:
-        """RaySamples.get_weights (rays.py:188-210): densities [N,S,1] -> weights [N,S,1]."""
+        """RaySamples.get_weights (rays.py:188-210): densities [N,S,1] -> weights [N,S,1]; differentiable with respect
+        to the densities (hand-written backward operator) when they require grad."""
         be = get_backend(densities.device)
-        return be.density_to_weights(self.deltas[..., 0], densities[..., 0])[..., None]
+        deltas = self.deltas[..., 0].detach().contiguous()
+        if torch.is_grad_enabled() and densities.requires_grad:
+            return AG.DensityToWeightsFn.apply(be, deltas, densities[..., 0].contiguous())[..., None]
+        with torch.no_grad():
+            return be.density_to_weights(deltas, densities[..., 0])[..., None]
 
 
 class SpacedSampler:
@@ -448,7 +453,6 @@ class ProposalNetworkSampler:
         self._step = step
         self._steps_since_update += 1
 
-    @torch.no_grad()
     def generate_ray_samples(self, ray_bundle: Optional[RayBundle] = None, density_fns: Optional[list] = None,
                              pass_ray_samples: bool = False) -> Tuple[RaySamples, List[Tensor], List[RaySamples]]:
         assert ray_bundle is not None
@@ -459,20 +463,28 @@ class ProposalNetworkSampler:
         weights_list, ray_samples_list = [], []
         n = self.num_proposal_network_iterations
         weights = ray_samples = None
+        # the proposal networks only receive gradients every update_sched(step) steps (ray_samplers.py:639, 656-661)
+        updated = self._steps_since_update > self.update_sched(self._step) or self._step < 10
         for i_level in range(n + 1):
             is_prop = i_level < n
             num_samples = self.num_proposal_samples_per_ray[i_level] if is_prop else self.num_nerf_samples_per_ray
-            if i_level == 0:
-                ray_samples = self.initial_sampler(ray_bundle, num_samples=num_samples)
-            else:
-                annealed = weights if self._anneal == 1.0 else torch.pow(weights, self._anneal)
-                ray_samples = self.pdf_sampler(ray_bundle, ray_samples, annealed, num_samples=num_samples)
+            with torch.no_grad():  # sample placement is not differentiated (bins.detach(), ray_samplers.py:363-364)
+                if i_level == 0:
+                    ray_samples = self.initial_sampler(ray_bundle, num_samples=num_samples)
+                else:
+                    annealed = weights if self._anneal == 1.0 else torch.pow(weights, self._anneal)
+                    ray_samples = self.pdf_sampler(ray_bundle, ray_samples, annealed.detach(), num_samples=num_samples)
             if is_prop:
-                density = density_fns[i_level](ray_samples)
+                if updated:
+                    density = density_fns[i_level](ray_samples)
+                else:
+                    with torch.no_grad():
+                        density = density_fns[i_level](ray_samples)
                 weights = ray_samples.get_weights(density)
                 weights_list.append(weights)
                 ray_samples_list.append(ray_samples)
-        self._steps_since_update = 0
+        if updated:
+            self._steps_since_update = 0
         return ray_samples, weights_list, ray_samples_list
 
     __call__ = generate_ray_samples
@@ -515,12 +527,22 @@ class NeuRADProposalField:
         self._model, self._field = model, field_index
         self.hashgrid = NeuRADHashEncoding(model, field_index)
 
-    @torch.no_grad()
     def get_density(self, ray_samples: RaySamples) -> Tuple[Tensor, None]:
-        """density [N,S,1] = trunc_exp(density_decoder(hashgrid(gaussians))) (neurad_field.py:208-213)."""
+        """density [N,S,1] = trunc_exp(density_decoder(hashgrid(gaussians))) (neurad_field.py:208-213); with grad mode
+        on and trainable parameters the backward operator delivers d/d(hash tables, density_decoder.weight)."""
+        m = self._model
         pos = ray_samples.frustums.get_fast_isotropic_gaussian(num_multisamples=1)
-        out = self._model._bind().neurad_encoding(self._field, pos.mean, pos.std, ray_samples.times, None,
-                                                  want_features=False, want_density=True)
+        be = m._bind()
+        flip = m._draw_actor_flip(ray_samples.shape[0])
+        pre = f"proposal_fields.{self._field - 1}"
+        tables = m._grid_params(pre)
+        dec = m._param(f"{pre}.density_decoder.weight")
+        if torch.is_grad_enabled() and any(t.requires_grad for t in tables + [dec]):
+            dens = AG.DensityFn.apply(be, self._field, pos.mean, pos.std, ray_samples.times, flip, tables[0], dec, *tables[1:])
+            return dens[..., None], None
+        with torch.no_grad():
+            out = be.neurad_encoding(self._field, pos.mean, pos.std, ray_samples.times, None, want_features=False,
+                                     want_density=True, flip=flip)
         return out["density"][..., None], None
 
     def get_outputs(self, ray_samples: RaySamples, density_embedding: Optional[Tensor] = None) -> dict:
@@ -534,13 +556,31 @@ class NeuRADField:
         self._model = model
         self.hashgrid = NeuRADHashEncoding(model, 0)
 
-    @torch.no_grad()
     def forward(self, ray_samples: RaySamples, compute_normals: bool = False) -> Dict[FieldHeadNames, Tensor]:
-        """{FEATURE [N,S,32], SDF [N,S,1], ALPHA [N,S,1]}."""
+        """{FEATURE [N,S,32], SDF [N,S,1], ALPHA [N,S,1]}.  With grad mode on and trainable parameters every stage is an
+        autograd node with a hand-written backward operator (hash tables, both MLPs, beta)."""
         if compute_normals:
             raise NotImplementedError("NeuRADField never computes normals (neurad_field.py:128)")
-        g = ray_samples.frustums.get_fast_isotropic_gaussian(self._model.config.num_multisamples)
-        out = self._model._bind().field_forward(g.mean, g.std, ray_samples.times, ray_samples.frustums.directions)
+        m = self._model
+        g = ray_samples.frustums.get_fast_isotropic_gaussian(m.config.num_multisamples)
+        be = m._bind()
+        flip = m._draw_actor_flip(ray_samples.shape[0])
+        n, s = ray_samples.shape
+        tables = m._grid_params("field")
+        geo_wb = m._mlp_params("field.mlp_geo", 2)
+        feat_wb = m._mlp_params("field.mlp_feature", 3)
+        beta = m._param("field.sdf_to_density.beta")
+        if torch.is_grad_enabled() and any(t.requires_grad for t in tables + geo_wb + feat_wb + [beta]):
+            feats, dirs = AG.EncodingFn.apply(be, 0, g.mean, g.std, ray_samples.times, ray_samples.frustums.directions, flip,
+                                              tables[0], *tables[1:])
+            geo = AG.MlpFn.apply(be, feats, *geo_wb)
+            h = AG.MlpFn.apply(be, AG.FieldMidFn.apply(be, geo, dirs), *feat_wb)
+            feature, sdf, alpha = AG.FieldTailFn.apply(be, geo, h, beta)
+            gdim = feature.shape[1]
+            out = {"feature": feature.view(n, s, gdim), "sdf": sdf.view(n, s, 1), "alpha": alpha.view(n, s, 1)}
+        else:
+            with torch.no_grad():
+                out = be.field_forward(g.mean, g.std, ray_samples.times, ray_samples.frustums.directions, flip=flip)
         return {FieldHeadNames.FEATURE: out["feature"], FieldHeadNames.SDF: out["sdf"], FieldHeadNames.ALPHA: out["alpha"]}
 
     __call__ = forward
@@ -666,8 +706,7 @@ class NeuRADModel(nn.Module):
         return be
 
     # -- forward API --------------------------------------------------------------------------------------------
-    @torch.no_grad()
-    def get_nff_outputs(self, ray_bundle: RayBundle, calc_lidar_losses: bool = False, fused: bool = True) -> Dict[str, Tensor]:
+    def get_nff_outputs(self, ray_bundle: RayBundle, calc_lidar_losses: bool = False, fused: Optional[bool] = None) -> Dict[str, Tensor]:
         """neurad.py:368-421 (eval): features [N,48], depth, accumulation, prop_depth_0/1 [N,1].
 
         fused=True (default): ONE kernel pair for the whole function.  fused=False: the reference's own module walk
@@ -675,19 +714,25 @@ class NeuRADModel(nn.Module):
         the library -- the per-module API of SURVEY 8b; additionally returns the reference's training-side extras
         `weights_list` / `ray_samples_list` (neurad.py:404-405)."""
         be = self._bind()
+        wants_grad = torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())
+        if fused is None:
+            fused = not wants_grad  # the fused kernels are forward-only; training walks the modules (autograd operators)
         if fused:
-            return be.render(ray_bundle.as_backend_dict())
+            if wants_grad:
+                raise RuntimeError("the fused renderer has no backward pass: call get_nff_outputs(fused=False) (or None) to train")
+            with torch.no_grad():
+                return be.render(ray_bundle.as_backend_dict())
         rb = self._scale_pixel_area(ray_bundle.flatten())
         ray_samples, prop_ray_samples, prop_weights = self._get_ray_samples(rb)
         out = self.field(ray_samples)
         weights = self._render_weights(out, ray_samples)
-        accumulation = self.renderer_accumulation(weights)
-        weights = weights.clone()
-        weights[:, -1:] += 1.0 - accumulation[:, None]  # sky sample takes the remaining transmittance (neurad.py:379-381)
-        features = self.renderer_feat(out[FieldHeadNames.FEATURE], weights)
+        accumulation = self._composite(weights, want_acc=True)[1]
+        # the sky sample takes the remaining transmittance (neurad.py:379-381)
+        weights = torch.cat((weights[:, :-1], weights[:, -1:] + 1.0 - accumulation[:, None]), dim=1)
+        features = self._composite(weights, values=out[FieldHeadNames.FEATURE])[0]
         features = torch.cat([features, self._get_appearance_embedding(rb, features)], dim=-1)
         res = {"features": features, "accumulation": accumulation,
-               "depth": self.renderer_depth(weights[:, :-1], ray_samples, drop_last=True)}
+               "depth": self.renderer_depth(weights[:, :-1], ray_samples, drop_last=True)}  # sky sample left out (neurad.py:386-390)
         for i, (w, rs) in enumerate(zip(prop_weights, prop_ray_samples)):
             res[f"prop_depth_{i}"] = self.renderer_depth(w, rs)
         res["weights_list"] = prop_weights + [weights]
@@ -718,7 +763,28 @@ class NeuRADModel(nn.Module):
 
     def _render_weights(self, outputs, ray_samples: RaySamples) -> Tensor:
         """neurad.py:711-724, use_sdf branch: nerfacc.render_weight_from_alpha on [N,S]."""
-        return self._bind().alpha_to_weights(outputs[FieldHeadNames.ALPHA][..., 0])[..., None]
+        alphas = outputs[FieldHeadNames.ALPHA][..., 0]
+        be = self._bind()
+        if torch.is_grad_enabled() and alphas.requires_grad:
+            return AG.AlphaToWeightsFn.apply(be, alphas.contiguous())[..., None]
+        with torch.no_grad():
+            return be.alpha_to_weights(alphas)[..., None]
+
+    def _composite(self, weights: Tensor, values: Optional[Tensor] = None, starts: Optional[Tensor] = None,
+                   ends: Optional[Tensor] = None, want_acc: bool = False):
+        """(values [N,C], accumulation [N,1], depth [N,1]) through the composite operator; an autograd node when an input
+        requires grad."""
+        be = self._bind()
+        want_depth = starts is not None
+        w = weights.reshape(weights.shape[0], weights.shape[1]).contiguous()
+        st = None if starts is None else starts.reshape(w.shape).detach().contiguous()
+        en = None if ends is None else ends.reshape(w.shape).detach().contiguous()
+        v = None if values is None else values.contiguous()
+        if torch.is_grad_enabled() and (w.requires_grad or (v is not None and v.requires_grad)):
+            return AG.CompositeFn.apply(be, w, v, st, en, want_acc, want_depth)
+        with torch.no_grad():
+            out = be.composite(w, v, st, en, "simple" if want_depth else None, want_accumulation=want_acc)
+        return out.get("values"), out.get("accumulation"), out.get("depth")
 
     def renderer_depth(self, weights: Tensor, ray_samples: RaySamples, drop_last: bool = False) -> Tensor:
         """render_depth_simple (neurad.py:727-734): sum_i w_i (start_i + end_i) / 2, un-normalised; `drop_last` is the
@@ -727,8 +793,30 @@ class NeuRADModel(nn.Module):
         st, en = fr.starts, fr.ends
         if drop_last:
             st, en = st[:, :-1], en[:, :-1]
-        return self._bind().composite(weights, starts=st.contiguous(), ends=en.contiguous(), depth_method="simple",
-                                      want_accumulation=False)["depth"]
+        return self._composite(weights, starts=st, ends=en)[2]
+
+    # -- parameter access under the reference's names (leaf tensors, so autograd delivers .grad to them) ----------
+    def _param(self, key: str) -> Tensor:
+        return getattr(self, key.replace(".", "__"))
+
+    def _grid_params(self, prefix: str) -> List[Tensor]:
+        """[static table, actor table 0, actor table 1, ...] of `prefix`.hashgrid."""
+        tabs = [self._param(f"{prefix}.hashgrid.static_grid.hash_table")]
+        return tabs + [self._param(f"{prefix}.hashgrid.actor_grids.{a}.hash_table") for a in range(self.config.n_actors)]
+
+    def _mlp_params(self, prefix: str, n_layers: int) -> List[Tensor]:
+        out: List[Tensor] = []
+        for i in range(n_layers):
+            out += [self._param(f"{prefix}.layers.{i}.weight"), self._param(f"{prefix}.layers.{i}.bias")]
+        return out
+
+    def _draw_actor_flip(self, n_rays: int) -> Optional[Tensor]:
+        """Training-mode random actor flip, one draw per ray and per encoding call (neurad_encoding.py:212-219):
+        -1 with probability flip_prob, else +1.  None in eval mode / without actors."""
+        p = self.config.actor_flip_prob
+        if not self.training or self.config.n_actors == 0 or p <= 1e-7:
+            return None
+        return torch.bernoulli(torch.full((n_rays,), p, device=self.static_scale.device)) * -2 + 1
 
     def _get_appearance_embedding(self, ray_bundle: RayBundle, features: Tensor) -> Tensor:
         """neurad.py:423-441: per-sensor embedding, linearly interpolated in time (temporal_appearance_freq)."""

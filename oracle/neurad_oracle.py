@@ -597,7 +597,7 @@ def nff_outputs(
     for i_level, S in enumerate(levels):
         if i_level > 0:
             r = pdf_resample(weights, bins_s, S, cfg.histogram_padding)  # anneal == 1.0 -> pow is the identity
-            bins_s = r["bins"]
+            bins_s = r["bins"].detach()  # "Stop gradients" (ray_samplers.py:363-364); values unchanged
             bins_e = sp.to_euclidean(bins_s)
             if want_trace:
                 trace[f"cdf_{i_level}"] = r["cdf"]

@@ -45,18 +45,71 @@ class FakeBackend(B200Backend):
         return emul.gaussian(origins, directions, pixel_area, bins_e)
 
     def neurad_encoding(self, field, mean, std, times, directions=None, want_features=True, want_density=False,
-                        want_actor_id=False):
-        return emul.encoding(self.cfg, self.params, O.pdf_u, field, mean, std, times, directions, want_features,
-                             want_density, want_actor_id)
+                        want_actor_id=False, flip=None):
+        return emul.encoding(self.cfg, self.params, O.pdf_u, field, mean.detach(), std.detach(), times, directions,
+                             want_features, want_density, want_actor_id, flip)
 
+    def neurad_encoding_bwd(self, field, mean, std, times, grads, dfeatures=None, density=None, ddensity=None, flip=None):
+        emul.encoding_bwd(self.cfg, self.params, O.pdf_u, field, mean, std, times, grads, dfeatures, density, ddensity, flip)
+
+    def alpha_to_weights_bwd(self, alphas, dweights):
+        return emul.weights_bwd(True, alphas, None, dweights)
+
+    def density_to_weights_bwd(self, deltas, densities, dweights):
+        return emul.weights_bwd(False, deltas, densities, dweights)
+
+    def linear_wgrad(self, x, dy, relu_x, dweight, dbias):
+        emul.linear_wgrad(x.detach(), dy.detach(), relu_x, dweight, dbias)
+
+    # backward leaves whose kernels are a few lines each (modules.cuh): the same formulas in torch
+    def relu_bwd(self, z, dz):
+        dz[~(z > 0)] = 0
+        return dz
+
+    def field_heads_bwd(self, geo, dfeature, dsdf, dalpha, dx2):
+        p, gdim = geo.shape[0], geo.shape[1] - 1
+        dgeo = torch.zeros(p, gdim + 1)
+        dbeta = torch.zeros(1)
+        sd = geo[:, 0]
+        if dsdf is not None:
+            dgeo[:, 0] += dsdf.reshape(p)
+        if dalpha is not None:
+            al = torch.sigmoid(-sd * self._beta)
+            t = dalpha.reshape(p) * al * (1 - al)
+            dgeo[:, 0] -= self._beta * t
+            dbeta += (-sd * t).sum()
+        if dfeature is not None:
+            dgeo[:, 1:] += dfeature.reshape(p, gdim)
+        if dx2 is not None:
+            dgeo[:, 1:] += dx2.reshape(p, gdim + 16)[:, :gdim]
+        return dgeo, dbeta
+
+    def composite_bwd(self, weights, values, starts, ends, dvalues_out, dacc, ddepth, need_dweights=True, need_dvalues=True):
+        n, s = weights.shape[0], weights.shape[1]
+        w = weights.reshape(n, s)
+        dw = torch.zeros(n, s)
+        dv = None
+        if dacc is not None:
+            dw += dacc.reshape(n, 1)
+        if ddepth is not None:
+            dw += ddepth.reshape(n, 1) * (starts.reshape(n, s) + ends.reshape(n, s)) * 0.5
+        if dvalues_out is not None:
+            c = values.shape[-1]
+            dw += (values.reshape(n, s, c) * dvalues_out.reshape(n, 1, c)).sum(-1)
+            dv = w[..., None] * dvalues_out.reshape(n, 1, c)
+        return (dw if need_dweights else None), (dv if need_dvalues else None)
+
+    @torch.no_grad()
     def _field_mid(self, geo, directions):
         return torch.cat([geo[:, 1:], O.sh_components_l4((directions.reshape(-1, 3) + 1.0) / 2.0)], dim=-1)
 
+    @torch.no_grad()
     def _field_tail(self, geo, h):
         sdf = geo[:, 0]
         return geo[:, 1:] + h, sdf, torch.sigmoid(-sdf * self._beta)
 
     # ---- leaves that exist (and are GPU-validated) since earlier commits: the oracle's restatements
+    @torch.no_grad()
     def mlp_fwd(self, x, weights, biases=None):
         y = x.reshape(-1, x.shape[-1])
         for i, w in enumerate(weights):
@@ -81,12 +134,15 @@ class FakeBackend(B200Backend):
         r = O.pdf_resample(weights, bins, num_samples, histogram_padding)
         return r["bins"], r["cdf"], r["inds"].int()
 
+    @torch.no_grad()
     def density_to_weights(self, deltas, densities):
         return O.weights_from_density(deltas, densities)
 
+    @torch.no_grad()
     def alpha_to_weights(self, alphas):
         return O.render_weight_from_alpha(alphas)
 
+    @torch.no_grad()
     def composite(self, weights, values=None, starts=None, ends=None, depth_method=None, background=None,
                   value_nan_to_num=False, want_accumulation=True):
         n, s = weights.shape[0], weights.shape[1]

@@ -195,7 +195,7 @@ int emul_gaussian(const float* origins, const float* dirs, const float* area, co
 // NeuRADHashEncoding.forward as the module-level operator computes it (nff_modules.h: neurad_encode_point; same loop
 // structure as neurad_encoding_fwd_kernel in modules.cuh).  extra = {mean [N,S,3], std [N,S], times [N] or NULL,
 // dirs ([N,3] if dirs_per_ray else [N,S,3]) or NULL, features [N*S,D] or NULL, density [N,S] or NULL, dirs_out [N,S,3]
-// or NULL, actor_id [N,S] (int32) or NULL}
+// or NULL, actor_id [N,S] (int32) or NULL, flip [N] or NULL}
 int emul_encoding(const void* const* ptrs, const int* ints, const float* floats, const void* const* extra, long long n_rays,
                   int S, int field, int dirs_per_ray) {
   Parsed Q;
@@ -210,6 +210,7 @@ int emul_encoding(const void* const* ptrs, const int* ints, const float* floats,
   float* density = (float*)extra[5];
   float* dirs_out = (float*)extra[6];
   int32_t* actor_id = (int32_t*)extra[7];
+  const float* flips = (const float*)extra[8];
   const int D = fg.stat.L * fg.stat.F;
   std::vector<ActorFrame> frames(A.n_actors > 0 ? A.n_actors : 1);
   for (long long r = 0; r < n_rays; ++r) {
@@ -219,6 +220,7 @@ int emul_encoding(const void* const* ptrs, const int* ints, const float* floats,
       keyframe_bracket(A, times[r], left, right, frac);
       for (int a = 0; a < A.n_actors; ++a) actor_frame(A, a, left, right, frac, frames[a]);
     }
+    const float flip = flips ? flips[r] : 1.0f;
     for (int s = 0; s < S; ++s) {
       const long long i = r * S + s;
       Gauss g = {mean[3 * i], mean[3 * i + 1], mean[3 * i + 2], std_[i]};
@@ -228,7 +230,7 @@ int emul_encoding(const void* const* ptrs, const int* ints, const float* floats,
         dir[0] = dp[0]; dir[1] = dp[1]; dir[2] = dp[2];
       }
       float feat[kModMaxDim];
-      const int aid = neurad_encode_point(fg, frames.data(), A.n_actors, g, feat, dirs ? dir : nullptr);
+      const int aid = neurad_encode_point(fg, frames.data(), A.n_actors, g, feat, dirs ? dir : nullptr, flip);
       if (features)
         for (int k = 0; k < D; ++k) features[i * D + k] = feat[k];
       if (density) {
@@ -241,6 +243,92 @@ int emul_encoding(const void* const* ptrs, const int* ints, const float* floats,
       if (actor_id) actor_id[i] = aid;
     }
   }
+  return 0;
+}
+
+// Backward of the module-level encoding (nff_modules.h: neurad_encode_point_bwd; loop structure of
+// neurad_encoding_bwd_kernel).  extra = {mean, std, times|NULL, flip|NULL, dfeatures|NULL, density|NULL, ddensity|NULL,
+// grad_static|NULL, grad_actor_ptrs (array of n_actors float*)|NULL, grad_decoder|NULL}
+int emul_encoding_bwd(const void* const* ptrs, const int* ints, const float* floats, const void* const* extra, long long n_rays,
+                      int S, int field) {
+  Parsed Q;
+  parse_params(ptrs, ints, floats, Q);
+  const FieldGrids& fg = Q.P.fields[field];
+  const Actors& A = Q.P.actors;
+  const float* mean = (const float*)extra[0];
+  const float* std_ = (const float*)extra[1];
+  const float* times = (const float*)extra[2];
+  const float* flips = (const float*)extra[3];
+  const float* dfeatures = (const float*)extra[4];
+  const float* density = (const float*)extra[5];
+  const float* ddensity = (const float*)extra[6];
+  float* grad_static = (float*)extra[7];
+  float* const* grad_actors = (float* const*)extra[8];
+  float* grad_decoder = (float*)extra[9];
+  const int D = fg.stat.L * fg.stat.F;
+  std::vector<ActorFrame> frames(A.n_actors > 0 ? A.n_actors : 1);
+  for (long long r = 0; r < n_rays; ++r) {
+    if (A.n_actors > 0) {
+      int left, right;
+      float frac;
+      keyframe_bracket(A, times[r], left, right, frac);
+      for (int a = 0; a < A.n_actors; ++a) actor_frame(A, a, left, right, frac, frames[a]);
+    }
+    const float flip = flips ? flips[r] : 1.0f;
+    for (int s = 0; s < S; ++s) {
+      const long long i = r * S + s;
+      Gauss g = {mean[3 * i], mean[3 * i + 1], mean[3 * i + 2], std_[i]};
+      float dfeat[kModMaxDim];
+      if (ddensity) {
+        const float gd = ddensity[i] * density[i];
+        if (grad_decoder) {
+          float feat[kModMaxDim];
+          neurad_encode_point(fg, frames.data(), A.n_actors, g, feat, nullptr, flip);
+          for (int k = 0; k < D; ++k) grad_decoder[k] = std::fmaf(gd, feat[k], grad_decoder[k]);
+        }
+        for (int k = 0; k < D; ++k) dfeat[k] = gd * fg.decoder[k];
+      } else {
+        for (int k = 0; k < D; ++k) dfeat[k] = dfeatures[i * D + k];
+      }
+      neurad_encode_point_bwd(fg, grad_static, grad_actors, frames.data(), A.n_actors, g, flip, dfeat);
+    }
+  }
+  return 0;
+}
+
+// weights backward rows (alpha_weights_bwd_ray / density_weights_bwd_ray)
+int emul_weights_bwd(int from_alpha, const float* a, const float* b, const float* dw, long long n_rays, int S, float* out) {
+  for (long long r = 0; r < n_rays; ++r) {
+    if (from_alpha)
+      alpha_weights_bwd_ray(a + r * S, dw + r * S, S, out + r * S);
+    else
+      density_weights_bwd_ray(a + r * S, b + r * S, dw + r * S, S, out + r * S);
+  }
+  return 0;
+}
+
+// linear_wgrad_kernel's tiling (modules.cuh) with `n_ctas` CTAs of 256 "threads" run one after the other.
+int emul_linear_wgrad(const float* x, const float* dy, long long n_rows, int K, int N, int relu_x, int n_ctas, float* dW,
+                      float* db) {
+  constexpr int kThreads = 256, kRows = 32, kMaxOut = 64 * 64 / kThreads;
+  const long long n_tiles = (n_rows + kRows - 1) / kRows;
+  for (int cta = 0; cta < n_ctas; ++cta)
+    for (int tid = 0; tid < kThreads; ++tid) {
+      float acc[kMaxOut] = {};
+      float bacc = 0.f;
+      for (long long t = cta; t < n_tiles; t += n_ctas) {
+        const long long r0 = t * kRows;
+        const int rows = (int)(n_rows - r0 < kRows ? n_rows - r0 : kRows);
+        wgrad_tile(tid, kThreads, x + r0 * K, dy + r0 * N, rows, K, N, relu_x != 0, acc);
+        if (db && tid < N)
+          for (int r = 0; r < rows; ++r) bacc += dy[(r0 + r) * N + tid];
+      }
+      for (int j = 0; j < kMaxOut; ++j) {
+        const int e = tid + j * kThreads;
+        if (e < N * K) dW[e] += acc[j];
+      }
+      if (db && tid < N) db[tid] += bacc;
+    }
   return 0;
 }
 }

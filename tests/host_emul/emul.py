@@ -143,7 +143,7 @@ def gaussian(origins, directions, pixel_area, bins_e):
 
 
 def encoding(cfg, params, pdf_u, field, mean, std, times, directions=None, want_features=True, want_density=False,
-             want_actor_id=True):
+             want_actor_id=True, flip=None):
     """The module-level NeuRADHashEncoding.forward device code (csrc/nff_modules.h) of field `field` (0 main, 1 / 2
     proposal): mean [N,S,3], std [N,S], times [N], directions [N,3] / [N,S,3] / None -> {"features" [N*S,D],
     "directions" [N,S,3], "actor_id" [N,S], "density" [N,S]} (same contract as B200Backend.neurad_encoding)."""
@@ -164,6 +164,7 @@ def encoding(cfg, params, pdf_u, field, mean, std, times, directions=None, want_
     dens = ex.P(torch.zeros(n, s) if want_density else None)
     dout = ex.P(torch.zeros(n, s, 3) if directions is not None else None)
     aid = ex.P(torch.zeros(n, s, dtype=torch.int32) if want_actor_id else None)
+    ex.P(None if flip is None else flip.float().reshape(n))
     for k, v in (("features", feats), ("density", dens), ("directions", dout), ("actor_id", aid)):
         if v is not None:
             out[k] = v
@@ -173,3 +174,61 @@ def encoding(cfg, params, pdf_u, field, mean, std, times, directions=None, want_
                            ctypes.c_int(1 if per_ray else 0))
     assert rc == 0
     return out
+
+
+def encoding_bwd(cfg, params, pdf_u, field, mean, std, times, grads, dfeatures=None, density=None, ddensity=None, flip=None):
+    """Backward of `encoding` (csrc/nff_modules.h: neurad_encode_point_bwd).  `grads` = {"static": tensor | None,
+    "actors": [tensor | None] * n_actors | None, "decoder": tensor | None}, accumulated in place (same contract as
+    B200Backend.neurad_encoding_bwd)."""
+    lib = ctypes.CDLL(build())
+    lib.emul_encoding_bwd.restype = ctypes.c_int
+    pk = _Pack()
+    _pack_params(pk, cfg, params, pdf_u, (2, 2))
+    n, s = mean.shape[0], mean.shape[1]
+    ex = _Pack()
+    ex.P(mean.float().reshape(n, s, 3))
+    ex.P(std.float().reshape(n, s))
+    ex.P(None if times is None else times.float().reshape(n, -1)[:, 0])
+    ex.P(None if flip is None else flip.float().reshape(n))
+    ex.P(None if dfeatures is None else dfeatures.float().reshape(n * s, -1))
+    ex.P(None if density is None else density.float().reshape(n, s))
+    ex.P(None if ddensity is None else ddensity.float().reshape(n, s))
+    for t in (grads.get("static"),):
+        assert t is None or (t.is_contiguous() and t.dtype == torch.float32)
+        ex.ptrs.append(None if t is None else ctypes.c_void_p(t.data_ptr()))
+    acts = grads.get("actors")
+    if acts:
+        arr = (ctypes.c_void_p * len(acts))(*[None if t is None else t.data_ptr() for t in acts])
+        ex.keep.append(arr)
+        ex.ptrs.append(ctypes.cast(arr, ctypes.c_void_p))
+    else:
+        ex.ptrs.append(None)
+    t = grads.get("decoder")
+    ex.ptrs.append(None if t is None else ctypes.c_void_p(t.data_ptr()))
+    c_ptrs, c_ints, c_floats = pk.c_arrays()
+    c_extra = (ctypes.c_void_p * len(ex.ptrs))(*ex.ptrs)
+    rc = lib.emul_encoding_bwd(c_ptrs, c_ints, c_floats, c_extra, ctypes.c_longlong(n), ctypes.c_int(s), ctypes.c_int(field))
+    assert rc == 0
+
+
+def weights_bwd(from_alpha, a, b, dw):
+    """alpha_weights_bwd_ray / density_weights_bwd_ray on [N,S] rows."""
+    lib = ctypes.CDLL(build())
+    a = a.float().contiguous()
+    b = None if b is None else b.float().contiguous()
+    dw = dw.float().contiguous()
+    out = torch.zeros_like(a)
+    p = lambda t: None if t is None else ctypes.c_void_p(t.data_ptr())  # noqa: E731
+    rc = lib.emul_weights_bwd(ctypes.c_int(int(from_alpha)), p(a), p(b), p(dw), ctypes.c_longlong(a.shape[0]), ctypes.c_int(a.shape[1]), p(out))
+    assert rc == 0
+    return out
+
+
+def linear_wgrad(x, dy, relu_x, dW, db, n_ctas=3):
+    """linear_wgrad_kernel's tiling: accumulates dY^T act(X) into dW [N,K] and sum dY into db [N]."""
+    lib = ctypes.CDLL(build())
+    x, dy = x.float().contiguous(), dy.float().contiguous()
+    p = lambda t: None if t is None else ctypes.c_void_p(t.data_ptr())  # noqa: E731
+    rc = lib.emul_linear_wgrad(p(x), p(dy), ctypes.c_longlong(x.shape[0]), ctypes.c_int(x.shape[1]), ctypes.c_int(dy.shape[1]),
+                               ctypes.c_int(int(relu_x)), ctypes.c_int(n_ctas), p(dW), p(db))
+    assert rc == 0

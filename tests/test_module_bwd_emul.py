@@ -1,0 +1,111 @@
+"""CPU: the device code of the BACKWARD operators (csrc/nff_modules.h) run by the host emulation, against
+torch autograd through the oracle (whose forward is pinned bit-for-bit to the reference, so its autograd is the
+reference's autograd in torch mode)."""
+import pytest
+import torch
+
+from oracle import neurad_oracle as O
+from oracle.convert import to_oracle_cfg
+from tests.helpers import cfg_from_meta, load_golden
+from tests.host_emul import emul
+
+
+def rel_to_max(a, b):
+    return (a - b).abs().max().item() / (b.abs().max().item() + 1e-30)
+
+
+def test_weights_backward_rows():
+    gen = torch.Generator().manual_seed(3)
+    n, s = 37, 45
+    alphas = (torch.rand(n, s, generator=gen) * 0.9).requires_grad_(True)
+    g = torch.randn(n, s, generator=gen)
+    (O.render_weight_from_alpha(alphas) * g).sum().backward()
+    assert rel_to_max(emul.weights_bwd(True, alphas.detach(), None, g), alphas.grad) < 1e-5
+    deltas = torch.rand(n, s, generator=gen) + 0.05
+    dens = (torch.rand(n, s, generator=gen) * 2).requires_grad_(True)
+    (O.weights_from_density(deltas, dens) * g).sum().backward()
+    assert rel_to_max(emul.weights_bwd(False, deltas, dens.detach(), g), dens.grad) < 1e-5
+    # a saturated sample (alpha == 1) gives finite gradients (the guarded quotient)
+    a1 = alphas.detach().clone()
+    a1[:, 7] = 1.0
+    assert torch.isfinite(emul.weights_bwd(True, a1, None, g)).all()
+
+
+@pytest.mark.parametrize("k,n,relu", [(32, 33, False), (48, 32, True), (64, 64, True), (6, 1, False), (50, 57, True)])
+def test_linear_wgrad_tiling(k, n, relu):
+    gen = torch.Generator().manual_seed(k * 100 + n)
+    rows = 32 * 7 + 5
+    x, dy = torch.randn(rows, k, generator=gen), torch.randn(rows, n, generator=gen)
+    dW, db = torch.zeros(n, k), torch.zeros(n)
+    emul.linear_wgrad(x, dy, relu, dW, db, n_ctas=3)
+    xa = torch.relu(x) if relu else x
+    assert rel_to_max(dW, dy.t() @ xa) < 1e-5 and rel_to_max(db, dy.sum(0)) < 1e-5
+    emul.linear_wgrad(x, dy, relu, dW, db, n_ctas=1)  # accumulates
+    assert rel_to_max(dW, 2 * (dy.t() @ xa)) < 1e-5
+
+
+def _grad_params(p, prefix, n_actors):
+    """Leaf copies (requires_grad) of one field's tables (+ decoder) inside a copy of the parameter dict."""
+    q = dict(p)
+    keys = [f"{prefix}.hashgrid.static_grid.hash_table"] + [f"{prefix}.hashgrid.actor_grids.{a}.hash_table" for a in range(n_actors)]
+    if f"{prefix}.density_decoder.weight" in p:
+        keys.append(f"{prefix}.density_decoder.weight")
+    for k in keys:
+        q[k] = p[k].clone().requires_grad_(True)
+    return q, keys
+
+
+@pytest.mark.parametrize("name", ["nff_static.npz", "nff_actors.npz"])
+def test_encoding_backward_features_mode(name):
+    meta, g = load_golden(name)
+    cfg = cfg_from_meta(meta)
+    ocfg = to_oracle_cfg(cfg)
+    p, r, ref = g["param"], g["ray"], g["ref"]
+    n = r["origins"].shape[0]
+    starts, ends = ref["starts"].reshape(n, -1), ref["ends"].reshape(n, -1)
+    s = starts.shape[1]
+    lidar = r["is_lidar"].reshape(-1).bool()
+    area = r["pixel_area"].reshape(-1) * torch.where(lidar, 1.0, float(cfg.rgb_upsample_factor**2))
+    q, keys = _grad_params(p, "field", meta["n_actors"])
+    mean, std = O.fast_isotropic_gaussian(r["origins"][:, None, :], r["directions"][:, None, :], area[:, None, None],
+                                          starts[..., None], ends[..., None])
+    t = r["times"].reshape(n, 1, 1).expand(n, s, 1)
+    feats, _ = O.hashgrid_forward(q, "field", ocfg.main, ocfg, mean, std, t, None)
+    G = torch.randn(feats.shape, generator=torch.Generator().manual_seed(1))
+    (feats * G).sum().backward()
+    em_mean, em_std = emul.gaussian(r["origins"], r["directions"], area, torch.cat([starts, ends[:, -1:]], 1))
+    grads = {"static": torch.zeros_like(p[keys[0]]), "actors": [torch.zeros_like(p[k]) for k in keys[1:]]}
+    emul.encoding_bwd(cfg, p, O.pdf_u, 0, em_mean, em_std, r["times"], grads, dfeatures=G)
+    assert rel_to_max(grads["static"], q[keys[0]].grad) < 1e-4
+    hit = 0
+    for a, k in enumerate(keys[1:]):
+        want = q[k].grad if q[k].grad is not None else torch.zeros_like(p[k])
+        assert (grads["actors"][a] - want).abs().max().item() <= 1e-4 * max(want.abs().max().item(), 1e-6)
+        hit += int(want.abs().max().item() > 0)
+    assert hit > 0 or meta["n_actors"] == 0
+
+
+@pytest.mark.parametrize("name", ["nff_static.npz", "nff_actors.npz"])
+def test_encoding_backward_density_mode(name):
+    meta, g = load_golden(name)
+    cfg = cfg_from_meta(meta)
+    ocfg = to_oracle_cfg(cfg)
+    p, r, ref = g["param"], g["ray"], g["ref"]
+    n = r["origins"].shape[0]
+    edges = ref["bins_e_1"].reshape(n, -1)
+    lidar = r["is_lidar"].reshape(-1).bool()
+    area = r["pixel_area"].reshape(-1) * torch.where(lidar, 1.0, float(cfg.rgb_upsample_factor**2))
+    q, keys = _grad_params(p, "proposal_fields.1", meta["n_actors"])
+    dens = O.proposal_density(q, 1, ocfg, r["origins"], r["directions"], area, r["times"].reshape(-1), edges[:, :-1], edges[:, 1:])
+    G = torch.randn(dens.shape, generator=torch.Generator().manual_seed(2))
+    (dens * G).sum().backward()
+    em_mean, em_std = emul.gaussian(r["origins"], r["directions"], area, edges)
+    n_act = meta["n_actors"]
+    grads = {"static": torch.zeros_like(p[keys[0]]), "actors": [torch.zeros_like(p[k]) for k in keys[1:1 + n_act]],
+             "decoder": torch.zeros(p[keys[-1]].numel())}
+    emul.encoding_bwd(cfg, p, O.pdf_u, 2, em_mean, em_std, r["times"], grads, density=dens.detach(), ddensity=G)
+    assert rel_to_max(grads["static"], q[keys[0]].grad) < 1e-4
+    assert rel_to_max(grads["decoder"], q[keys[-1]].grad.reshape(-1)) < 1e-4
+    for a, k in enumerate(keys[1:1 + n_act]):
+        want = q[k].grad if q[k].grad is not None else torch.zeros_like(p[k])
+        assert (grads["actors"][a] - want).abs().max().item() <= 1e-4 * max(want.abs().max().item(), 1e-6)

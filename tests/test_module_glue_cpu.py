@@ -30,3 +30,12 @@ def test_proposal_density_and_encoding_glue(name):
 @pytest.mark.parametrize("name", ["nff_static.npz", "nff_actors.npz", "nff_sharp.npz"])
 def test_proposal_sampler_and_module_walk_glue(name):
     C.proposal_sampler_and_module_walk_match_reference_golden(name, "cpu")
+
+
+@pytest.mark.parametrize("name", ["nff_static.npz", "nff_actors.npz"])
+def test_training_gradients_glue(name):
+    C.training_gradients_match_reference_golden(name, "cpu")
+
+
+def test_backward_stage_operators_glue():
+    C.backward_stage_operators_match_torch_autograd("cpu")

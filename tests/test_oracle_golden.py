@@ -106,3 +106,26 @@ def test_spacing_functions_match_reference_samplers():
         _, e = S.spaced_sample(nears, fars, 8, kind)
         assert torch.allclose(e[:, 0], nears[:, 0], rtol=1e-5) and torch.allclose(e[:, -1], fars[:, 0], rtol=1e-5)
         assert (e[:, 1:] > e[:, :-1]).all()
+
+
+@pytest.mark.parametrize("name", ["nff_static.npz", "nff_actors.npz"])
+def test_oracle_autograd_matches_reference_gradients(name):
+    """torch autograd through the oracle reproduces the gradients the unmodified reference computed
+    (tests/golden/grads_*.npz, oracle/make_golden_grads.py) for every parameter the path trains."""
+    from tests.module_seam_cases import OUT_KEYS, check_grads, load_golden_grads, loss_weights
+
+    gmeta, want = load_golden_grads(name)
+    meta, g = load_golden(name)
+    cfg = cfg_from_meta(meta)
+    n = gmeta["n_rays"]
+    p = {k: v.clone() for k, v in g["param"].items()}
+    keys = [k for k, v in p.items() if v.dtype.is_floating_point and not k.startswith("dynamic_actors.")
+            and not k.endswith("scalings") and k != "static_scale"]
+    for k in keys:
+        p[k].requires_grad_(True)
+    r = g["ray"]
+    out = O.nff_outputs(p, to_oracle_cfg(cfg), r["origins"][:n], r["directions"][:n], r["pixel_area"][:n], r["times"][:n],
+                        r["sensor_idx"][:n], r["is_lidar"][:n])
+    G = loss_weights({k: out[k].shape for k in OUT_KEYS}, gmeta["loss_seed"])
+    sum((out[k] * G[k]).sum() for k in OUT_KEYS).backward()
+    check_grads({k: p[k].grad for k in keys}, want, min_checked=15)

@@ -28,3 +28,12 @@ def test_proposal_sampler_and_module_walk_match_reference_golden(name):
 
 def test_module_operator_errors_and_empty_inputs():
     C.module_operator_errors_and_empty_inputs("cuda")
+
+
+@pytest.mark.parametrize("name", ["nff_static.npz", "nff_actors.npz"])
+def test_training_gradients_match_reference_golden(name):
+    C.training_gradients_match_reference_golden(name, "cuda")
+
+
+def test_backward_stage_operators_match_torch_autograd():
+    C.backward_stage_operators_match_torch_autograd("cuda")
