@@ -241,6 +241,19 @@ int b200nerf_spacing_to_euclidean(b200nerf_ctx* ctx, int kind, float power_lambd
                                   const float* nears, const float* fars, const float* bins_s, int64_t n_rays,
                                   int n_edges, float* bins_e, void* stream);
 
+/* Training-mode sampling.  The random numbers are drawn by the caller (torch.rand, as the
+ * reference does) so that the operators stay deterministic functions of their inputs:
+ *   SpacedSampler with train_stratified (ray_samplers.py:107-115): t_rand [N,1] (single_jitter) or [N,S+1];
+ *     outputs per-ray spacing bins [N,S+1] and euclidean edges [N,S+1].
+ *   PDFSampler with train_stratified (ray_samplers.py:321-329): u = u_base + rand / (S_new+1), u_base =
+ *     linspace(0, 1 - 1/nb, nb) [S_new+1] (device), rand [N,1] or [N,S_new+1]; other arguments as b200nerf_pdf_resample. */
+int b200nerf_spaced_sample_stratified(b200nerf_ctx* ctx, int kind, float power_lambda, float power_scaling,
+                                      const float* nears, const float* fars, const float* t_rand, int rand_cols,
+                                      int64_t n_rays, int n_samples, float* bins_s, float* bins_e, void* stream);
+int b200nerf_pdf_resample_stratified(b200nerf_ctx* ctx, const float* weights, const float* bins, const float* u_base,
+                                     const float* rand, int rand_cols, int n_rays, int s_old, int s_new,
+                                     float histogram_padding, float* new_bins, float* cdf, int32_t* inds, void* stream);
+
 /* ---- backward operators: gradients of the module-level operators with respect to the trained
  * parameters.  The reference gets these from torch autograd (torch mode) or tiny-cuda-nn's backward kernels; here each
  * forward operator has a hand-written counterpart.  Sample positions carry no gradient (PDFSampler detaches its bins,

@@ -308,6 +308,35 @@ class B200Backend:
         self._check(self.lib.b200nerf_pdf_resample(self._h, _ptr(w), _ptr(b), _ptr(u), n, s, num_samples, histogram_padding, _ptr(nb), _ptr(cdf), _ptr(inds), self._stream))
         return nb, cdf, inds
 
+    def pdf_resample_stratified(self, weights: torch.Tensor, bins: torch.Tensor, num_samples: int, rand: torch.Tensor,
+                                histogram_padding: float = 0.01):
+        """PDFSampler in training mode (train_stratified, ray_samplers.py:321-329): `rand` [N,1] (single_jitter) or
+        [N,S_new+1] uniform numbers drawn by the caller; returns like pdf_resample."""
+        w, b, r = self._dev(weights), self._dev(bins), self._dev(rand)
+        n, s = w.shape
+        nb = num_samples + 1
+        u = torch.linspace(0.0, 1.0 - (1.0 / nb), steps=nb).to(self.device)
+        out = torch.empty(n, nb, device=self.device)
+        cdf = torch.empty(n, s + 1, device=self.device)
+        inds = torch.empty(n, nb, device=self.device, dtype=torch.int32)
+        self._check(self.lib.b200nerf_pdf_resample_stratified(self._h, _ptr(w), _ptr(b), _ptr(u), _ptr(r), r.shape[1], n, s, num_samples,
+                                                              histogram_padding, _ptr(out), _ptr(cdf), _ptr(inds), self._stream))
+        return out, cdf, inds
+
+    def spaced_sample_stratified(self, nears: Optional[torch.Tensor], fars: torch.Tensor, num_samples: int, t_rand: torch.Tensor,
+                                 spacing: str = "uniform", power_lambda: float = -1.0, power_scaling: float = 0.1):
+        """SpacedSampler in training mode (train_stratified, ray_samplers.py:107-115): `t_rand` [N,1] (single_jitter)
+        or [N,S+1]; returns (per-ray spacing bins [N,S+1], euclidean edges [N,S+1])."""
+        f = self._dev(fars).reshape(-1)
+        nr = None if nears is None else self._dev(nears).reshape(-1)
+        r = self._dev(t_rand).reshape(f.shape[0], -1)
+        n = f.shape[0]
+        bins_s = torch.empty(n, num_samples + 1, device=self.device)
+        bins_e = torch.empty(n, num_samples + 1, device=self.device)
+        self._check(self.lib.b200nerf_spaced_sample_stratified(self._h, self.SPACINGS[spacing], power_lambda, power_scaling, _ptr(nr), _ptr(f),
+                                                               _ptr(r), r.shape[1], n, num_samples, _ptr(bins_s), _ptr(bins_e), self._stream))
+        return bins_s, bins_e
+
     def density_to_weights(self, deltas: torch.Tensor, densities: torch.Tensor) -> torch.Tensor:
         """RaySamples.get_weights (cameras/rays.py:188-210) on [N,S]."""
         d, s = self._dev(deltas), self._dev(densities)

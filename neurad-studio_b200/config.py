@@ -80,6 +80,7 @@ class SamplingSettings:
     power_scaling: float = 0.1
     sky_distance: float = 20000.0
     histogram_padding: float = 0.01  # PDFSampler default, ray_samplers.py:272
+    single_jitter: bool = True  # SamplingSettings.single_jitter (neurad.py:101), training mode only
 
 
 @dataclass

@@ -346,10 +346,12 @@ __global__ void sh4_fwd_kernel(const float* __restrict__ dirs, float* __restrict
 }
 
 // PDFSampler (ray_samplers.py:309-361), generic S: one warp per ray, cdf in shared memory.
+// Training mode (train_stratified, ray_samplers.py:321-329): u = linspace(0, 1 - 1/nb, nb) + rand / nb with `rand`
+// [N, rand_cols] (rand_cols = 1: single_jitter, else nb); `u` then holds the linspace part.
 __global__ void pdf_resample_kernel(const float* __restrict__ weights, const float* __restrict__ bins,
                                     const float* __restrict__ u, int n_rays, int S, int S_new, float hist_pad,
                                     float* __restrict__ new_bins, float* __restrict__ cdf_out,
-                                    int32_t* __restrict__ inds) {
+                                    int32_t* __restrict__ inds, const float* __restrict__ rand = nullptr, int rand_cols = 0) {
   extern __shared__ float sm[];
   const int warp = threadIdx.x >> 5, ln = threadIdx.x & 31;
   float* cdf = sm + warp * (S + 1);
@@ -377,6 +379,7 @@ __global__ void pdf_resample_kernel(const float* __restrict__ weights, const flo
     for (int s = ln; s <= S; s += 32) cdf_out[(size_t)ray * (S + 1) + s] = cdf[s];
   for (int i = ln; i <= S_new; i += 32) {
     float uu = u[i];
+    if (rand) uu = __fadd_rn(uu, __fdiv_rn(rand[(size_t)ray * rand_cols + (rand_cols == 1 ? 0 : i)], (float)(S_new + 1)));
     int lo = 0, hi = S + 1;
     while (lo < hi) {
       int mid = (lo + hi) >> 1;
@@ -453,6 +456,25 @@ __global__ void spaced_sample_kernel(const SpacingArgs a, const float* __restric
   const int e = (int)(i % (S + 1));
   const float u = linspace01(e, S);
   if (bins_s && ray == 0) bins_s[e] = u;
+  const float s_near = spacing_apply(a, nears ? nears[ray] : 0.0f), s_far = spacing_apply(a, fars[ray]);
+  bins_e[i] = spacing_invert(a, fadd(fmul(u, s_far), fmul(fsub(1.0f, u), s_near)));
+}
+// Training mode of SpacedSampler.generate_ray_samples (train_stratified, ray_samplers.py:107-115): every edge moves
+// inside [lower, upper] = the midpoints towards its neighbours, bins = lower + (upper - lower) * t_rand with t_rand
+// [N, rand_cols] (rand_cols = 1: single_jitter, else S+1) drawn by the caller; per-ray spacing bins are an output.
+__global__ void spaced_sample_jitter_kernel(const SpacingArgs a, const float* __restrict__ nears, const float* __restrict__ fars,
+                                            const float* __restrict__ t_rand, int rand_cols, int64_t n_rays, int S,
+                                            float* __restrict__ bins_s, float* __restrict__ bins_e) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_rays * (S + 1)) return;
+  const int64_t ray = i / (S + 1);
+  const int e = (int)(i % (S + 1));
+  const float b = linspace01(e, S);
+  const float lower = e == 0 ? b : fdiv(fadd(b, linspace01(e - 1, S)), 2.0f);
+  const float upper = e == S ? b : fdiv(fadd(linspace01(e + 1, S), b), 2.0f);
+  const float t = t_rand[ray * rand_cols + (rand_cols == 1 ? 0 : e)];
+  const float u = fadd(lower, fmul(fsub(upper, lower), t));
+  bins_s[i] = u;
   const float s_near = spacing_apply(a, nears ? nears[ray] : 0.0f), s_far = spacing_apply(a, fars[ray]);
   bins_e[i] = spacing_invert(a, fadd(fmul(u, s_far), fmul(fsub(1.0f, u), s_near)));
 }
@@ -1375,6 +1397,24 @@ int b200nerf_field_tail_fwd(b200nerf_ctx* c, const float* geo_out, const float* 
   return 0;
 }
 
+int b200nerf_spaced_sample_stratified(b200nerf_ctx* c, int kind, float power_lambda, float power_scaling, const float* nears,
+                                      const float* fars, const float* t_rand, int rand_cols, int64_t n_rays, int n_samples,
+                                      float* bins_s, float* bins_e, void* stream) {
+  REQUIRE(c, "ctx is NULL");
+  REQUIRE(n_rays >= 0 && n_samples >= 1, "bad sample grid");
+  REQUIRE(rand_cols == 1 || rand_cols == n_samples + 1, "t_rand must be [N,1] (single_jitter) or [N,S+1]");
+  SpacingArgs a{};
+  if (int rc = make_spacing(kind, power_lambda, power_scaling, &a)) return rc;
+  if (n_rays == 0) return 0;
+  REQUIRE(fars && t_rand && bins_s && bins_e, "NULL argument");
+  DeviceGuard g(c->device);
+  const int64_t n = n_rays * (n_samples + 1);
+  spaced_sample_jitter_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(a, nears, fars, t_rand, rand_cols, n_rays,
+                                                                                             n_samples, bins_s, bins_e);
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
 int b200nerf_spacing_to_euclidean(b200nerf_ctx* c, int kind, float power_lambda, float power_scaling, const float* nears,
                                   const float* fars, const float* bins_s, int64_t n_rays, int n_edges, float* bins_e,
                                   void* stream) {
@@ -1822,6 +1862,22 @@ int b200nerf_pdf_resample(b200nerf_ctx* c, const float* weights, const float* bi
   size_t smem = sizeof(float) * warps * (s_old + 1);
   pdf_resample_kernel<<<(n_rays + warps - 1) / warps, warps * 32, smem, (cudaStream_t)stream>>>(
       weights, bins, u, n_rays, s_old, s_new, hist_pad, new_bins, cdf, inds);
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+int b200nerf_pdf_resample_stratified(b200nerf_ctx* c, const float* weights, const float* bins, const float* u_base,
+                                     const float* rand, int rand_cols, int n_rays, int s_old, int s_new, float hist_pad,
+                                     float* new_bins, float* cdf, int32_t* inds, void* stream) {
+  REQUIRE(c && weights && bins && u_base && rand && new_bins, "NULL argument");
+  REQUIRE(s_old >= 1 && s_old <= 2048 && s_new >= 1, "sample counts out of range");
+  REQUIRE(rand_cols == 1 || rand_cols == s_new + 1, "rand must be [N,1] (single_jitter) or [N,S_new+1]");
+  if (n_rays == 0) return 0;
+  DeviceGuard g(c->device);
+  const int warps = 4;
+  size_t smem = sizeof(float) * warps * (s_old + 1);
+  pdf_resample_kernel<<<(n_rays + warps - 1) / warps, warps * 32, smem, (cudaStream_t)stream>>>(
+      weights, bins, u_base, n_rays, s_old, s_new, hist_pad, new_bins, cdf, inds, rand, rand_cols);
   CUDA_TRY(cudaGetLastError());
   return 0;
 }

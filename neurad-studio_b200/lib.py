@@ -111,6 +111,10 @@ SIGNATURES = {
                                         c_void_p]),
     "b200nerf_spacing_to_euclidean": (c_int, [c_void_p, c_int, c_float, c_float, c_void_p, c_void_p, c_void_p, c_int64, c_int,
                                               c_void_p, c_void_p]),
+    "b200nerf_spaced_sample_stratified": (c_int, [c_void_p, c_int, c_float, c_float, c_void_p, c_void_p, c_void_p, c_int, c_int64,
+                                                  c_int, c_void_p, c_void_p, c_void_p]),
+    "b200nerf_pdf_resample_stratified": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
+                                                 c_float, c_void_p, c_void_p, c_void_p, c_void_p]),
     "b200nerf_frustum_positions": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, POINTER(c_float),
                                            c_void_p, c_void_p]),
     "b200nerf_density_rgb_heads": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p, c_void_p]),

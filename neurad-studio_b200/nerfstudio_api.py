@@ -180,6 +180,8 @@ class PDFSampler:
         if include_original:
             raise NotImplementedError("include_original=True is not on NeuRAD's path (ray_samplers.py:606)")
         self.num_samples, self.histogram_padding = num_samples, histogram_padding
+        self.train_stratified, self.single_jitter = train_stratified, single_jitter
+        self.training = False  # the reference's samplers are nn.Modules; NeuRADModel.train() propagates the flag
 
     @torch.no_grad()
     def __call__(self, *args, num_samples: Optional[int] = None, **kw):
@@ -203,7 +205,11 @@ class PDFSampler:
         be = get_backend(weights.device)
         existing = ray_samples.per_ray_spacing_bins()
         w = weights[..., 0] if weights.dim() == 3 else weights
-        bins = be.pdf_resample(w, existing, n, self.histogram_padding)[0]
+        if self.train_stratified and self.training:  # ray_samplers.py:321-329: the jitter is drawn here, like the reference
+            rand = torch.rand((w.shape[0], 1 if self.single_jitter else n + 1), device=w.device)
+            bins = be.pdf_resample_stratified(w, existing, n, rand, self.histogram_padding)[0]
+        else:
+            bins = be.pdf_resample(w, existing, n, self.histogram_padding)[0]
         fr = ray_samples.frustums
         return RaySamples(Frustums(fr.origins, fr.directions, ray_samples.spacing_to_euclidean_fn(bins), fr.pixel_area), bins,
                           times=ray_samples.times, metadata=ray_samples.metadata, spacing=ray_samples.spacing)
@@ -304,12 +310,14 @@ class RaySamples:
 
 
 class SpacedSampler:
-    """model_components/ray_samplers.py:56-132 in eval mode (no stratified jitter)."""
+    """model_components/ray_samplers.py:56-132; `.training` + train_stratified select the stratified jitter (:107-115)."""
 
     spacing = "uniform"
 
     def __init__(self, num_samples: Optional[int] = None, train_stratified: bool = True, single_jitter: bool = False) -> None:
         self.num_samples = num_samples
+        self.train_stratified, self.single_jitter = train_stratified, single_jitter
+        self.training = False
 
     def _power(self) -> Tuple[float, float]:
         return -1.0, 0.1
@@ -321,7 +329,12 @@ class SpacedSampler:
         assert n is not None
         be = get_backend(ray_bundle.origins.device)
         lam, scaling = self._power()
-        bins_s, bins_e = be.spaced_sample(ray_bundle.nears, ray_bundle.fars, n, self.spacing, lam, scaling)
+        if self.train_stratified and self.training:  # ray_samplers.py:107-115
+            num_rays = ray_bundle.origins.reshape(-1, 3).shape[0]
+            t_rand = torch.rand((num_rays, 1 if self.single_jitter else n + 1), device=ray_bundle.origins.device)
+            bins_s, bins_e = be.spaced_sample_stratified(ray_bundle.nears, ray_bundle.fars, n, t_rand, self.spacing, lam, scaling)
+        else:
+            bins_s, bins_e = be.spaced_sample(ray_bundle.nears, ray_bundle.fars, n, self.spacing, lam, scaling)
         area = None if ray_bundle.pixel_area is None else ray_bundle.pixel_area.reshape(-1, 1)
         times = None if ray_bundle.times is None else ray_bundle.times.reshape(-1, 1)
         return RaySamples(Frustums(ray_bundle.origins.reshape(-1, 3), ray_bundle.directions.reshape(-1, 3), bins_e, area), bins_s,
@@ -358,9 +371,14 @@ class PowerSampler(SpacedSampler):
 
     spacing = "power"
 
-    def __init__(self, num_samples: Optional[int] = None, power_lambda: float = -1.0, power_scaling: float = 0.1, **kw) -> None:
+    def __init__(self, num_samples: Optional[int] = None, lambda_: float = -1.5, scaling: float = 2.0, **kw) -> None:
+        # the reference's argument names and defaults (ray_samplers.py:845); NeuRAD passes lambda_=-1, scaling=0.1
+        if "power_lambda" in kw:
+            lambda_ = kw.pop("power_lambda")
+        if "power_scaling" in kw:
+            scaling = kw.pop("power_scaling")
         super().__init__(num_samples, **kw)
-        self.power_lambda, self.power_scaling = power_lambda, power_scaling
+        self.power_lambda, self.power_scaling = lambda_, scaling
 
     def _power(self) -> Tuple[float, float]:
         return self.power_lambda, self.power_scaling
@@ -445,6 +463,11 @@ class ProposalNetworkSampler:
         self.initial_sampler = initial_sampler
         self.pdf_sampler = pdf_sampler if pdf_sampler is not None else PDFSampler(include_original=False, single_jitter=single_jitter)
         self._anneal, self._steps_since_update, self._step = 1.0, 0, 0
+        self.training = False
+
+    def train(self, mode: bool = True) -> "ProposalNetworkSampler":
+        self.training = self.initial_sampler.training = self.pdf_sampler.training = mode
+        return self
 
     def set_anneal(self, anneal: float) -> None:
         self._anneal = anneal
@@ -668,8 +691,10 @@ class NeuRADModel(nn.Module):
         self.sampler = ProposalNetworkSampler(
             num_nerf_samples_per_ray=sp.num_nerf_samples, num_proposal_samples_per_ray=tuple(sp.num_proposal_samples),
             num_proposal_network_iterations=len(sp.num_proposal_samples),
-            initial_sampler=PowerSampler(power_lambda=sp.power_lambda, power_scaling=sp.power_scaling),
-            pdf_sampler=PDFSampler(include_original=False, histogram_padding=sp.histogram_padding),
+            single_jitter=sp.single_jitter,
+            initial_sampler=PowerSampler(lambda_=sp.power_lambda, scaling=sp.power_scaling),
+            pdf_sampler=PDFSampler(include_original=False, single_jitter=sp.single_jitter, histogram_padding=sp.histogram_padding),
+            update_sched=lambda x: 0,
         )
         # neurad.py:248 builds `[lambda x: prop_field.get_density(x)[0] for prop_field in self.proposal_fields]`: the
         # closures bind late, so EVERY entry evaluates the LAST proposal field.  Same here.
@@ -677,6 +702,14 @@ class NeuRADModel(nn.Module):
         self.density_fns = [lambda ray_samples: last.get_density(ray_samples)[0] for _ in self.proposal_fields]
         self.renderer_feat = FeatureRenderer()
         self.renderer_accumulation = AccumulationRenderer()
+
+    def train(self, mode: bool = True) -> "NeuRADModel":
+        """nn.Module.train, also reaching the samplers (nn.Modules in the reference): stratified jitter and the random
+        actor flip are training-mode behaviour (ray_samplers.py:107-115, 321-329; neurad_encoding.py:212-219)."""
+        super().train(mode)
+        if hasattr(self, "sampler"):
+            self.sampler.train(mode)
+        return self
 
     # -- state dict under the reference's dotted names ----------------------------------------------------------
     def reference_state_dict(self) -> Dict[str, Tensor]:

@@ -155,12 +155,14 @@ def pdf_u(num_samples: int) -> Tensor:
 
 
 def pdf_resample(
-    weights: Tensor, existing_bins: Tensor, num_samples: int, histogram_padding: float = 0.01, eps: float = 1e-5
+    weights: Tensor, existing_bins: Tensor, num_samples: int, histogram_padding: float = 0.01, eps: float = 1e-5,
+    rand: Optional[Tensor] = None,
 ) -> Dict[str, Tensor]:
     """PDFSampler.generate_ray_samples, eval mode, include_original=False (ray_samplers.py:280-361).
 
     weights [N,S]; existing_bins [N,S+1] (spacing domain).  Returns new spacing bins [N,num_samples+1] plus the
-    intermediate cdf and searchsorted indices (the bit-exact targets)."""
+    intermediate cdf and searchsorted indices (the bit-exact targets).  `rand` switches to the training-mode
+    stratified quantiles."""
     num_bins = num_samples + 1
     weights = weights + histogram_padding
     weights_sum = torch.sum(weights, dim=-1, keepdim=True)
@@ -170,7 +172,12 @@ def pdf_resample(
     pdf = weights / weights_sum
     cdf = torch.min(torch.ones_like(pdf), torch.cumsum(pdf, dim=-1))
     cdf = torch.cat([torch.zeros_like(cdf[..., :1]), cdf], dim=-1)
-    u = pdf_u(num_samples).expand(size=(*cdf.shape[:-1], num_bins)).clone().contiguous()
+    if rand is None:
+        u = pdf_u(num_samples).expand(size=(*cdf.shape[:-1], num_bins)).clone().contiguous()
+    else:  # training mode, train_stratified (ray_samplers.py:321-329); rand [N,1] (single_jitter) or [N,num_bins] in [0,1)
+        u = torch.linspace(0.0, 1.0 - (1.0 / num_bins), steps=num_bins)
+        u = u.expand(size=(*cdf.shape[:-1], num_bins)).clone()
+        u = (u + rand / num_bins).contiguous()
     inds = torch.searchsorted(cdf, u, side="right")
     below = torch.clamp(inds - 1, 0, existing_bins.shape[-1] - 1)
     above = torch.clamp(inds, 0, existing_bins.shape[-1] - 1)

@@ -51,11 +51,16 @@ def spacing_fns(kind: int, lam: float = -1.0, scaling: float = 0.1):
 
 
 def spaced_sample(nears: Tensor, fars: Tensor, num_samples: int, kind: int = SPACING_UNIFORM, lam: float = -1.0,
-                  scaling: float = 0.1):
+                  scaling: float = 0.1, t_rand: Optional[Tensor] = None):
     """SpacedSampler.generate_ray_samples, eval mode (ray_samplers.py:80-132): returns (spacing bins [1,S+1],
     euclidean bins [N,S+1])."""
     fn, inv = spacing_fns(kind, lam, scaling)
     bins = torch.linspace(0.0, 1.0, num_samples + 1)[None, ...]
+    if t_rand is not None:  # training mode, train_stratified (ray_samplers.py:107-115); t_rand [N,1] or [N,S+1]
+        bin_centers = (bins[..., 1:] + bins[..., :-1]) / 2.0
+        bin_upper = torch.cat([bin_centers, bins[..., -1:]], -1)
+        bin_lower = torch.cat([bins[..., :1], bin_centers], -1)
+        bins = bin_lower + (bin_upper - bin_lower) * t_rand
     s_near, s_far = fn(nears), fn(fars)
     euclid = inv(bins * s_far + (1 - bins) * s_near)
     return bins, euclid

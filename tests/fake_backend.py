@@ -130,6 +130,16 @@ class FakeBackend(B200Backend):
         nr = torch.zeros_like(f) if nears is None else nears.reshape(-1, 1)
         return inv(bins_s * fn(f) + (1 - bins_s) * fn(nr))
 
+    def spaced_sample_stratified(self, nears, fars, num_samples, t_rand, spacing="uniform", power_lambda=-1.0, power_scaling=0.1):
+        f = fars.reshape(-1, 1)
+        nr = torch.zeros_like(f) if nears is None else nears.reshape(-1, 1)
+        bins, euclid = S.spaced_sample(nr, f, num_samples, self.SPACINGS[spacing], power_lambda, power_scaling, t_rand=t_rand)
+        return bins.expand_as(euclid).contiguous(), euclid
+
+    def pdf_resample_stratified(self, weights, bins, num_samples, rand, histogram_padding=0.01):
+        r = O.pdf_resample(weights, bins, num_samples, histogram_padding, rand=rand)
+        return r["bins"], r["cdf"], r["inds"].int()
+
     def pdf_resample(self, weights, bins, num_samples, histogram_padding=0.01):
         r = O.pdf_resample(weights, bins, num_samples, histogram_padding)
         return r["bins"], r["cdf"], r["inds"].int()

@@ -239,3 +239,55 @@ def backward_stage_operators_match_torch_autograd(dev):
         assert rel_to_max(dx, x.grad) < 2e-5, dims
         for i in range(len(ws)):
             assert rel_to_max(dws[i], ws[i].grad) < 2e-5 and rel_to_max(dbs[i], bs[i].grad) < 2e-5, (dims, i)
+
+
+def stratified_sampling_matches_reference_golden(dev):
+    """Training-mode sampling operators (train_stratified: SpacedSampler jitter, PDFSampler jitter; both single_jitter
+    settings) fed the jitter the reference drew, against the reference modules' outputs (tests/golden/stratified.npz,
+    oracle/make_golden_stratified.py)."""
+    from neurad_studio_b200 import nerfstudio_api
+
+    be = nerfstudio_api.get_backend(torch.device(dev, 0) if dev == "cuda" else torch.device(dev))
+    meta, g = load_golden("stratified.npz")
+    nears, fars = g["in"]["nears"].to(dev), g["in"]["fars"].to(dev)
+    for tag in ("single", "full"):
+        t = g[tag]
+        bins_s, bins_e = be.spaced_sample_stratified(nears, fars, meta["s0"], t["t_rand"].to(dev), "power", meta["power_lambda"],
+                                                     meta["power_scaling"])
+        assert (bins_s.cpu() - t["bins_s"]).abs().max().item() < 1e-6
+        assert rel_to_max(bins_e, t["bins_e"]) < 1e-5
+        new_s, _, inds = be.pdf_resample_stratified(t["weights"].to(dev), t["bins_s"].to(dev), meta["s1"], t["rand"].to(dev),
+                                                    meta["histogram_padding"])
+        assert (new_s.cpu() - t["new_bins_s"]).abs().max().item() < 1e-5
+        assert (inds.cpu().long() != t["inds"].long()).float().mean().item() < 5e-3
+        new_e = be.spacing_to_euclidean(new_s, nears, fars, "power", meta["power_lambda"], meta["power_scaling"])
+        assert rel_to_max(new_e, t["new_bins_e"]) < 1e-4
+        assert torch.all(new_s[:, 1:] >= new_s[:, :-1])
+
+
+def training_mode_walk_runs(name, dev):
+    """model.train(): stratified jitter in both samplers, one random actor flip per ray and encoding call, gradients
+    delivered; two calls differ (fresh jitter) while eval mode stays deterministic."""
+    meta, cfg, model, rb, g = _model_and_bundle(name, dev)
+    rb = rb[:64]
+    model.requires_grad_(True)
+    model.train()
+    assert model.sampler.initial_sampler.training and model.sampler.pdf_sampler.training
+    torch.manual_seed(0)
+    a = model.get_nff_outputs(rb)
+    b = model.get_nff_outputs(rb)
+    for k in ("features", "depth", "accumulation"):
+        assert torch.isfinite(a[k]).all() and a[k].shape == b[k].shape
+    assert not torch.equal(a["depth"], b["depth"])
+    e2 = a["ray_samples_list"][2].frustums.bin_edges
+    assert torch.all(e2[:, 1:] >= e2[:, :-1]) and torch.all(e2[:, -1] == cfg.sampling.sky_distance)
+    a["features"].sum().backward()
+    assert model._param("field.mlp_geo.layers.0.weight").grad.abs().max().item() > 0
+    if meta["n_actors"]:
+        flips = torch.stack([model._draw_actor_flip(4096) for _ in range(2)])
+        assert set(flips.unique().tolist()) == {-1.0, 1.0} and abs(flips.mean().item()) < 0.1
+    model.eval()
+    assert model._draw_actor_flip(8) is None and not model.sampler.pdf_sampler.training
+    with torch.no_grad():
+        c, d = model.get_nff_outputs(rb, fused=False), model.get_nff_outputs(rb, fused=False)
+    assert torch.equal(c["depth"], d["depth"])

@@ -39,3 +39,12 @@ def test_training_gradients_glue(name):
 
 def test_backward_stage_operators_glue():
     C.backward_stage_operators_match_torch_autograd("cpu")
+
+
+def test_stratified_sampling_glue():
+    C.stratified_sampling_matches_reference_golden("cpu")
+
+
+@pytest.mark.parametrize("name", ["nff_static.npz", "nff_actors.npz"])
+def test_training_mode_walk_glue(name):
+    C.training_mode_walk_runs(name, "cpu")

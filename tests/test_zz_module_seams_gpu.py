@@ -37,3 +37,12 @@ def test_training_gradients_match_reference_golden(name):
 
 def test_backward_stage_operators_match_torch_autograd():
     C.backward_stage_operators_match_torch_autograd("cuda")
+
+
+def test_stratified_sampling_matches_reference_golden():
+    C.stratified_sampling_matches_reference_golden("cuda")
+
+
+@pytest.mark.parametrize("name", ["nff_static.npz", "nff_actors.npz"])
+def test_training_mode_walk_runs(name):
+    C.training_mode_walk_runs(name, "cuda")
