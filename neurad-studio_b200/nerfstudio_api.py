@@ -21,8 +21,9 @@ modules, so that the parity tests read like the reference's own tests and a refe
                                 NeuRADModel.field / .proposal_fields / .sampler / .density_fns as in neurad.py:180-248;
                                 get_nff_outputs(fused=False) walks these modules like the reference does
 
-Everything is inference-only (eval mode, no autograd): SURVEY.md section 8f ranks the backward pass as a later row.
-There is no CPU path: modules raise at call time if the parameters are not on a CUDA device.
+Inference runs the fused kernels; with grad mode on and trainable parameters the per-module walk runs instead, every
+stage an autograd node backed by a hand-written backward operator (autograd.py).  The rgb
+decoder is inference-only.  There is no CPU path: modules raise at call time if the parameters are not on a CUDA device.
 """
 from __future__ import annotations
 
