@@ -302,6 +302,28 @@ int b200nerf_linear_wgrad(b200nerf_ctx* ctx, const float* x, const float* dy, in
                           int relu_x, float* dweight, float* dbias, void* stream);
 int b200nerf_relu_bwd(b200nerf_ctx* ctx, const float* z, float* dz, int64_t n, void* stream);
 
+/* NeuRAD's per-ray training regularisers (models/neurad.py:262,524,541-545) on the `weights_list` / `ray_samples_list`
+ * of get_nff_outputs; spacing-domain edges ("sdist", losses.py:119-125) and weights as [N,S+1] / [N,S].  Per-ray losses
+ * out (the reference takes the mean over rays); the optional gradient outputs are d loss_ray / d weights.
+ *   distortion loss   (lossfun_distortion, losses.py:160-177): gradient to the final level's weights.
+ *   zipnerf interlevel (losses.py:645-705) for ONE proposal level with blur half-width `pulse_width` (0.03 / 0.003 for
+ *     levels 0 / 1): the final level (sdist, weights) is detached by the reference, the gradient goes to prop_weights.
+ * n_samples <= 64. */
+int b200nerf_distortion_loss(b200nerf_ctx* ctx, const float* sdist, const float* weights, int64_t n_rays, int n_samples,
+                             float* loss_per_ray, float* dweights, void* stream);
+int b200nerf_zipnerf_interlevel_loss(b200nerf_ctx* ctx, const float* sdist, const float* weights, int n_samples,
+                                     const float* prop_sdist, const float* prop_weights, int n_prop_samples,
+                                     float pulse_width, int64_t n_rays, float* loss_per_ray, float* dprop_weights,
+                                     void* stream);
+
+/* NeuRADModel._compute_is_close_to_lidar (models/neurad.py:677-700), training mode: mask [N,S] (uint8) = for lidar rays,
+ * (did_return & |directions_norm - sample midpoint| < carving_epsilon) | (~did_return & midpoint < non_return_distance);
+ * without did_return (NULL) just the first term; 0 for camera rays.  bins_e [N,S+1] euclidean edges, is_lidar /
+ * did_return [N] uint8, directions_norm [N] (the measured lidar distance). */
+int b200nerf_lidar_carving_mask(b200nerf_ctx* ctx, const float* bins_e, const uint8_t* is_lidar,
+                                const float* directions_norm, const uint8_t* did_return, float carving_epsilon,
+                                float non_return_distance, int64_t n_rays, int n_samples, uint8_t* mask, void* stream);
+
 /* Kernel variant used by b200nerf_nff_render_fwd:
  *   2 (default) ray-per-lane mapping (a warp = 32 adjacent rays at one sample index: coherent gathers), MLPs on the
  *     tcgen05 tensor cores with the 3xTF32 split (fp32-level accuracy, |err| ~1e-6 relative);

@@ -184,3 +184,33 @@ class CompositeFn(Function):
         if dv is not None:
             dv = dv.reshape(values.shape)
         return None, dw, dv, None, None, None, None
+
+
+class DistortionLossFn(Function):
+    """lossfun_distortion per ray (losses.py:160-172): gradient to the weights; the spacing edges are detached."""
+
+    @staticmethod
+    def forward(ctx, be, sdist, weights):
+        loss, dw = be.distortion_loss(sdist, weights, want_grad=True)
+        ctx.save_for_backward(dw)
+        return loss
+
+    @staticmethod
+    def backward(ctx, dloss):
+        (dw,) = ctx.saved_tensors
+        return None, None, dw * dloss[:, None]
+
+
+class InterlevelLossFn(Function):
+    """zipnerf_interlevel_loss for one proposal level, per ray (losses.py:645-705): gradient to the proposal weights."""
+
+    @staticmethod
+    def forward(ctx, be, sdist, weights, prop_sdist, prop_weights, pulse_width: float):
+        loss, dwp = be.zipnerf_interlevel_loss(sdist, weights, prop_sdist, prop_weights, pulse_width, want_grad=True)
+        ctx.save_for_backward(dwp)
+        return loss
+
+    @staticmethod
+    def backward(ctx, dloss):
+        (dwp,) = ctx.saved_tensors
+        return None, None, None, None, dwp * dloss[:, None], None

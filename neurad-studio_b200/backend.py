@@ -542,6 +542,42 @@ class B200Backend:
                 g = self.relu_bwd(zs[l - 1], g)
         return g.reshape(*x.shape)
 
+    def lidar_carving_mask(self, bins_e: torch.Tensor, is_lidar: torch.Tensor, directions_norm: torch.Tensor,
+                           did_return: Optional[torch.Tensor], carving_epsilon: float, non_return_distance: float) -> torch.Tensor:
+        """NeuRADModel._compute_is_close_to_lidar (models/neurad.py:677-700): bool mask [N,S] of the samples close to the
+        measured lidar return (or, for rays without a return, inside the lidar range); False for camera rays."""
+        b = self._dev(bins_e)
+        n, s = b.shape[0], b.shape[1] - 1
+        il = self._dev(is_lidar.reshape(n), torch.uint8)
+        dn = self._dev(directions_norm).reshape(n)
+        dr = None if did_return is None else self._dev(did_return.reshape(n), torch.uint8)
+        mask = torch.empty(n, s, device=self.device, dtype=torch.uint8)
+        self._check(self.lib.b200nerf_lidar_carving_mask(self._h, _ptr(b), _ptr(il), _ptr(dn), _ptr(dr), float(carving_epsilon),
+                                                         float(non_return_distance), n, s, _ptr(mask), self._stream))
+        return mask.bool()
+
+    def distortion_loss(self, sdist: torch.Tensor, weights: torch.Tensor, want_grad: bool = False):
+        """lossfun_distortion per ray (model_components/losses.py:160-172): sdist [N,S+1], weights [N,S] ->
+        (loss [N], d loss / d weights [N,S] or None)."""
+        c, w = self._dev(sdist), self._dev(weights)
+        n, s = w.shape
+        loss = torch.empty(n, device=self.device)
+        dw = torch.empty(n, s, device=self.device) if want_grad else None
+        self._check(self.lib.b200nerf_distortion_loss(self._h, _ptr(c), _ptr(w), n, s, _ptr(loss), _ptr(dw), self._stream))
+        return loss, dw
+
+    def zipnerf_interlevel_loss(self, sdist: torch.Tensor, weights: torch.Tensor, prop_sdist: torch.Tensor, prop_weights: torch.Tensor,
+                                pulse_width: float, want_grad: bool = False):
+        """zipnerf_interlevel_loss for one proposal level, per ray (losses.py:645-705): final level sdist [N,S+1] /
+        weights [N,S] (detached), proposal level [N,Sp+1] / [N,Sp] -> (loss [N], d loss / d prop_weights [N,Sp] or None)."""
+        c, w, cp, wp = self._dev(sdist), self._dev(weights), self._dev(prop_sdist), self._dev(prop_weights)
+        n, s, sp = w.shape[0], w.shape[1], wp.shape[1]
+        loss = torch.empty(n, device=self.device)
+        dwp = torch.empty(n, sp, device=self.device) if want_grad else None
+        self._check(self.lib.b200nerf_zipnerf_interlevel_loss(self._h, _ptr(c), _ptr(w), s, _ptr(cp), _ptr(wp), sp, float(pulse_width), n,
+                                                              _ptr(loss), _ptr(dwp), self._stream))
+        return loss, dwp
+
     # ------------------------------------------------------------------- generic sampler / renderer operators
     SPACINGS = {"uniform": 0, "lindisp": 1, "power": 2, "sqrt": 3, "log": 4}
     DEPTH_METHODS = {None: 0, "expected": 1, "median": 2, "simple": 3}

@@ -100,6 +100,8 @@ class NeuRADConfig:
     rgb_upsample_factor: int = 3
     rgb_hidden_dim: int = 32
     actor_bbox_padding: Tuple[float, float, float] = (0.25, 0.25, 0.1)
+    carving_epsilon: float = 0.1  # LossSettings (neurad.py:79,87): lidar carving masks of the training outputs
+    non_return_lidar_distance: float = 150.0
     actor_flip_prob: float = 0.5  # ActorSettings.flip_prob (neurad_encoding.py:50), training mode only
     # scene-level constants (dataset metadata in the reference)
     static_scale: float = 100.0

@@ -1547,6 +1547,52 @@ int b200nerf_linear_wgrad(b200nerf_ctx* c, const float* x, const float* dy, int6
   return 0;
 }
 
+int b200nerf_distortion_loss(b200nerf_ctx* c, const float* sdist, const float* weights, int64_t n_rays, int n_samples,
+                             float* loss_per_ray, float* dweights, void* stream) {
+  REQUIRE(c, "ctx is NULL");
+  REQUIRE(n_rays >= 0, "bad shape");
+  REQUIRE(n_samples >= 1 && n_samples <= kLossMaxS, "the loss operators take at most 64 samples per ray");
+  if (n_rays == 0) return 0;
+  REQUIRE(sdist && weights && loss_per_ray, "NULL argument");
+  DeviceGuard g(c->device);
+  distortion_loss_kernel<<<(unsigned)((n_rays + 127) / 128), 128, 0, (cudaStream_t)stream>>>(sdist, weights, n_rays, n_samples, loss_per_ray,
+                                                                                             dweights);
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+int b200nerf_zipnerf_interlevel_loss(b200nerf_ctx* c, const float* sdist, const float* weights, int n_samples,
+                                     const float* prop_sdist, const float* prop_weights, int n_prop_samples, float pulse_width,
+                                     int64_t n_rays, float* loss_per_ray, float* dprop_weights, void* stream) {
+  REQUIRE(c, "ctx is NULL");
+  REQUIRE(n_rays >= 0 && n_prop_samples >= 1, "bad shape");
+  REQUIRE(n_samples >= 1 && n_samples <= kLossMaxS, "the loss operators take at most 64 samples of the final level per ray");
+  REQUIRE(pulse_width > 0.f, "pulse_width must be positive");
+  if (n_rays == 0) return 0;
+  REQUIRE(sdist && weights && prop_sdist && prop_weights && loss_per_ray, "NULL argument");
+  DeviceGuard g(c->device);
+  zipnerf_interlevel_kernel<<<(unsigned)((n_rays + 63) / 64), 64, 0, (cudaStream_t)stream>>>(sdist, weights, n_samples, prop_sdist, prop_weights,
+                                                                                             n_prop_samples, pulse_width, n_rays, loss_per_ray,
+                                                                                             dprop_weights);
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+int b200nerf_lidar_carving_mask(b200nerf_ctx* c, const float* bins_e, const uint8_t* is_lidar, const float* directions_norm,
+                                const uint8_t* did_return, float carving_epsilon, float non_return_distance, int64_t n_rays,
+                                int n_samples, uint8_t* mask, void* stream) {
+  REQUIRE(c, "ctx is NULL");
+  REQUIRE(n_rays >= 0 && n_samples >= 1, "bad sample grid");
+  if (n_rays == 0) return 0;
+  REQUIRE(bins_e && is_lidar && directions_norm && mask, "NULL argument");
+  DeviceGuard g(c->device);
+  const int64_t n = n_rays * n_samples;
+  lidar_carving_mask_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(bins_e, is_lidar, directions_norm, did_return,
+                                                                                           carving_epsilon, non_return_distance, n_rays, n_samples, mask);
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
 int b200nerf_frustum_positions(b200nerf_ctx* c, const float* origins, const float* directions, const float* bins_e,
                                int64_t n_rays, int n_samples, const float* aabb_host, float* positions, void* stream) {
   REQUIRE(c, "ctx is NULL");

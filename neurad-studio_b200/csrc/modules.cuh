@@ -292,4 +292,53 @@ __global__ void __launch_bounds__(kWgradThreads) linear_wgrad_kernel(const float
   if (db && threadIdx.x < N) atomicAdd(db + threadIdx.x, bacc);
 }
 
+// Training regularisers of NeuRAD (models/neurad.py:524,541-545), one thread per ray; per-ray losses out (the caller
+// takes the mean like losses.py:176,704) and, optionally, the gradient with respect to the weights that carry one.
+__global__ void distortion_loss_kernel(const float* __restrict__ c, const float* __restrict__ w, int64_t n_rays, int S,
+                                       float* __restrict__ loss, float* __restrict__ dw) {
+  const int64_t ray = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (ray >= n_rays) return;
+  float cl[kLossMaxS + 1], wl[kLossMaxS], dl[kLossMaxS];
+  for (int i = 0; i <= S; ++i) cl[i] = c[ray * (S + 1) + i];
+  for (int i = 0; i < S; ++i) wl[i] = w[ray * S + i];
+  loss[ray] = distortion_loss_ray(cl, wl, S, dw ? dl : nullptr);
+  if (dw)
+    for (int i = 0; i < S; ++i) dw[ray * S + i] = dl[i];
+}
+
+__global__ void zipnerf_interlevel_kernel(const float* __restrict__ c, const float* __restrict__ w, int S,
+                                          const float* __restrict__ cp, const float* __restrict__ wp, int Sp, float pulse_width,
+                                          int64_t n_rays, float* __restrict__ loss, float* __restrict__ dwp) {
+  const int64_t ray = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (ray >= n_rays) return;
+  float cl[kLossMaxS + 1], wl[kLossMaxS];
+  for (int i = 0; i <= S; ++i) cl[i] = c[ray * (S + 1) + i];
+  for (int i = 0; i < S; ++i) wl[i] = w[ray * S + i];
+  // the proposal level is read and its gradient written in place in global memory (row-strided, once each)
+  loss[ray] = zipnerf_interlevel_ray(cl, wl, S, cp + ray * (Sp + 1), wp + ray * Sp, Sp, pulse_width, dwp ? dwp + ray * Sp : nullptr);
+}
+
+// NeuRADModel._compute_is_close_to_lidar (models/neurad.py:677-700), training mode: which samples of a LIDAR ray lie
+// within carving_epsilon of the measured return (directions_norm = the measured distance), or, for rays without a return,
+// closer than non_return_lidar_distance.  Camera rays get 0.  One thread per (ray, sample); bins_e [N,S+1].
+__global__ void lidar_carving_mask_kernel(const float* __restrict__ bins_e, const uint8_t* __restrict__ is_lidar,
+                                          const float* __restrict__ directions_norm, const uint8_t* __restrict__ did_return,
+                                          float carving_epsilon, float non_return_distance, int64_t n_rays, int S,
+                                          uint8_t* __restrict__ mask) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_rays * S) return;
+  const int64_t ray = i / S;
+  const int s = (int)(i % S);
+  uint8_t m = 0;
+  if (is_lidar[ray]) {
+    const float mid = fmul(fadd(bins_e[ray * (S + 1) + s], bins_e[ray * (S + 1) + s + 1]), 0.5f);
+    const bool close_to_hit = fabsf(fsub(directions_norm[ray], mid)) < carving_epsilon;
+    if (did_return)
+      m = did_return[ray] ? close_to_hit : (mid < non_return_distance);
+    else
+      m = close_to_hit;
+  }
+  mask[i] = m;
+}
+
 }  // namespace nff

@@ -227,6 +227,109 @@ NFF_D void density_weights_bwd_ray(const float* delta, const float* density, con
   }
 }
 
+// ------------------------------------------------------------------------------------------------ training losses
+// The two per-ray regularisers NeuRAD trains with (models/neurad.py:262,524,541-545), one thread per ray; both are
+// functions of the `weights_list` / `ray_samples_list` the module walk returns.
+constexpr int kLossMaxS = 64;  // samples of the final level the loss kernels accept
+
+// lossfun_distortion (model_components/losses.py:160-172) for one ray: c [S+1] spacing-domain edges, w [S]:
+//   sum_i w_i sum_j w_j |u_i - u_j| + sum_i w_i^2 (c_{i+1} - c_i) / 3,  u = bin midpoints.
+// dw (optional) receives d loss / d w_i = 2 sum_j w_j |u_i - u_j| + 2 w_i (c_{i+1} - c_i) / 3.
+NFF_D float distortion_loss_ray(const float* c, const float* w, int S, float* dw) {
+  float inter = 0.0f, intra = 0.0f;
+  for (int i = 0; i < S; ++i) {
+    const float ui = (c[i + 1] + c[i]) / 2.0f;
+    float inner = 0.0f;
+    for (int j = 0; j < S; ++j) inner += w[j] * fabsf(ui - (c[j + 1] + c[j]) / 2.0f);
+    inter += w[i] * inner;
+    const float d = c[i + 1] - c[i];
+    intra += w[i] * w[i] * d;
+    if (dw) dw[i] = 2.0f * inner + 2.0f * w[i] * d / 3.0f;
+  }
+  return inter + intra / 3.0f;
+}
+
+// zipnerf_interlevel_loss (losses.py:645-705) for one ray and one proposal level: the final level's histogram (c [S+1],
+// w [S], both detached in the reference) is normalised, blurred with a box of half width r (_blur_stepfun), integrated
+// to a piecewise-quadratic cdf and resampled at the proposal edges cp [Sp+1] (_sorted_interp_quad); the loss is
+// sum_s relu(w_s - wp_s)^2 / (wp_s + 1e-5).  Only wp carries a gradient: dwp (optional) receives it.
+NFF_D float zipnerf_interlevel_ray(const float* c, const float* w, int S, const float* cp, const float* wp, int Sp, float r,
+                                   float* dwp) {
+  constexpr int kM = 2 * (kLossMaxS + 1);  // blurred knots
+  float xs[kM + 2], ys[kM + 2], cdf[kM + 2];  // padded by one knot at either end (losses.py:691-693)
+  const int M = 2 * (S + 1);
+  // w = cat(w[:-1], w[-1] + (1 - sum w)); w_norm = w / diff(c)
+  float acc = 0.0f;
+  for (int i = 0; i < S; ++i) acc += w[i];
+  // y1_k = (y_k - y_{k-1}) / (2r) with y_{-1} = y_S = 0: the derivative of the box-blurred step function at c_k -/+ r
+  // merge the two sorted knot sequences c_k - r (slope +y1_k) and c_k + r (slope -y1_k)
+  int ia = 0, ib = 0;
+  // cumulative sums in double, like torch.cumsum on the CPU (the oracle's accumulate type): in fp32 the blurred pdf
+  // picks up ~1e-5 relative noise that the division by (wp + 1e-5) below amplifies to 1e-2 in the gradient
+  double slope = 0.0, raw = 0.0;
+  float xprev = 0.0f;
+  float* x_ = xs + 1;
+  float* y_ = ys + 1;
+  auto wn = [&](int k) -> float {  // normalised weight of bin k (0 outside)
+    if (k < 0 || k >= S) return 0.0f;
+    const float wk = k == S - 1 ? w[k] + (1.0f - acc) : w[k];
+    return wk / (c[k + 1] - c[k]);
+  };
+  for (int m = 0; m < M; ++m) {
+    const bool take_a = ib >= S + 1 || (ia < S + 1 && c[ia] - r <= c[ib] + r);
+    const int k = take_a ? ia : ib;
+    const float x = take_a ? c[k] - r : c[k] + r;
+    const float y1 = (wn(k) - wn(k - 1)) / (2.0f * r);
+    // yr = cumsum(diff(xr) * cumsum(y2)).clamp_min(0), prefixed with 0: the clamp applies to the finished cumsum, it
+    // does not feed back into it; each cumsum result is rounded to fp32 before it is used, as torch stores it
+    if (m > 0) raw += (double)((x - xprev) * (float)slope);
+    x_[m] = x;
+    y_[m] = m == 0 ? 0.0f : fmaxf((float)raw, 0.0f);
+    slope += (double)(take_a ? y1 : -y1);
+    xprev = x;
+    if (take_a) ++ia; else ++ib;
+  }
+  // piecewise linear pdf -> piecewise quadratic cdf; pad with (0, 0, 0) in front and (1, 0, 1) behind
+  xs[0] = 0.0f; ys[0] = 0.0f; cdf[0] = 0.0f;
+  double run = 0.0;
+  cdf[1] = 0.0f;
+  for (int m = 1; m < M; ++m) {
+    run += (double)(0.5f * (y_[m] + y_[m - 1]) * (x_[m] - x_[m - 1]));
+    cdf[1 + m] = (float)run;
+  }
+  xs[M + 1] = 1.0f; ys[M + 1] = 0.0f; cdf[M + 1] = 1.0f;
+  const int L = M + 2;
+  // _sorted_interp_quad at the proposal edges, then the difference of neighbours
+  float prev = 0.0f, loss = 0.0f;
+  for (int e = 0; e <= Sp; ++e) {
+    const float x = cp[e];
+    int lo = 0, hi = L;  // torch.searchsorted(xp, x) (left): first index with xp[idx] >= x
+    while (lo < hi) {
+      const int mid = (lo + hi) >> 1;
+      if (xs[mid] < x) lo = mid + 1; else hi = mid;
+    }
+    const int left = lo - 1 < 0 ? 0 : lo - 1;
+    const int right = lo > L - 1 ? L - 1 : lo;
+    const float xp0 = xs[left], xp1 = xs[right];
+    float off = nan_to_num((x - xp0) / (xp1 - xp0));
+    off = fminf(fmaxf(off, 0.0f), 1.0f);
+    const float v = cdf[left] + (x - xp0) * (ys[left] + ys[right] * off + ys[left] * (1.0f - off)) * 0.5f;
+    if (e > 0) {
+      const float ws = v - prev;
+      const float d = ws - wp[e - 1];
+      const float den = wp[e - 1] + 1e-5f;
+      if (d > 0.0f) {
+        loss += d * d / den;
+        if (dwp) dwp[e - 1] = -2.0f * d / den - d * d / (den * den);
+      } else if (dwp) {
+        dwp[e - 1] = 0.0f;
+      }
+    }
+    prev = v;
+  }
+  return loss;
+}
+
 // One tile of the weight gradient of a Linear layer, dW[o][i] += sum_r dY[r][o] * act(X[r][i]) (act = ReLU when the
 // layer's input is a hidden activation stored as its pre-activation).  Thread `tid` of `nthreads` owns the outputs
 // e = tid + j * nthreads (e = o*K + i), j < MAXOUT, and keeps them in acc[] (registers: the j loop is unrolled).

@@ -115,6 +115,11 @@ SIGNATURES = {
                                                   c_int, c_void_p, c_void_p, c_void_p]),
     "b200nerf_pdf_resample_stratified": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
                                                  c_float, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "b200nerf_distortion_loss": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p, c_void_p]),
+    "b200nerf_zipnerf_interlevel_loss": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_float, c_int64,
+                                                 c_void_p, c_void_p, c_void_p]),
+    "b200nerf_lidar_carving_mask": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_float, c_int64, c_int,
+                                            c_void_p, c_void_p]),
     "b200nerf_frustum_positions": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, POINTER(c_float),
                                            c_void_p, c_void_p]),
     "b200nerf_density_rgb_heads": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p, c_void_p]),

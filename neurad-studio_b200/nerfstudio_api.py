@@ -275,6 +275,13 @@ class RaySamples:
     def shape(self) -> Tuple[int, int]:
         return (self.frustums.bin_edges.shape[0], self.frustums.bin_edges.shape[1] - 1)
 
+    def without_last_sample(self) -> "RaySamples":
+        """`ray_samples[..., :-1]` (neurad.py:385-386: the sky sample is dropped before depth and the training lists)."""
+        fr = self.frustums
+        sb = self.spacing_bins
+        return RaySamples(Frustums(fr.origins, fr.directions, fr.bin_edges[:, :-1], fr.pixel_area), sb[..., :-1],
+                          times=self.times, metadata=self.metadata, spacing=self.spacing)
+
     def per_ray_spacing_bins(self) -> Tensor:
         b = self.spacing_bins
         return b if b.dim() == 2 else b[None, :].expand(self.shape[0], -1).contiguous()
@@ -767,10 +774,22 @@ class NeuRADModel(nn.Module):
         features = torch.cat([features, self._get_appearance_embedding(rb, features)], dim=-1)
         res = {"features": features, "accumulation": accumulation,
                "depth": self.renderer_depth(weights[:, :-1], ray_samples, drop_last=True)}  # sky sample left out (neurad.py:386-390)
+        lidar_losses = self.training and calc_lidar_losses
         for i, (w, rs) in enumerate(zip(prop_weights, prop_ray_samples)):
             res[f"prop_depth_{i}"] = self.renderer_depth(w, rs)
-        res["weights_list"] = prop_weights + [weights]
-        res["ray_samples_list"] = prop_ray_samples + [ray_samples]
+            if lidar_losses:  # neurad.py:402-404
+                weights_mask = (~rs.metadata["is_close_to_lidar"]) & rs.metadata["is_lidar"].reshape(-1, 1, 1).bool()
+                res[f"prop_weights_loss_{i}"] = ((w * weights_mask) ** 2).sum()
+        if lidar_losses:  # neurad.py:410-419 (the sky sample is already dropped there)
+            md = ray_samples.metadata
+            weights_mask = ((~md["is_close_to_lidar"][:, :-1]) & md["is_lidar"].reshape(-1, 1, 1).bool()).squeeze(-1)
+            weights_idx = weights_mask.nonzero(as_tuple=True)
+            res["non_nearby_weights"] = weights[:, :-1][weights_idx]
+            lidar_start_ray = md["is_lidar"].reshape(-1).int().argmax()  # argmax gives the first True
+            res["non_nearby_lidar_ray_indices"] = weights_idx[0] - lidar_start_ray
+        # neurad.py:385-386, 404-405: the sky sample is dropped from the final level before the lists are built
+        res["weights_list"] = prop_weights + [weights[:, :-1]]
+        res["ray_samples_list"] = prop_ray_samples + [ray_samples.without_last_sample()]
         return res
 
     def _scale_pixel_area(self, ray_bundle: RayBundle) -> RayBundle:
@@ -793,7 +812,23 @@ class NeuRADModel(nn.Module):
         ray_samples, prop_weights, prop_ray_samples = self.sampler(ray_bundle, self.density_fns, pass_ray_samples=True)
         edges = ray_samples.frustums.bin_edges
         edges[:, -1] += sky - edges[:, -1]  # `ends[-1] += sky - ends[-1]`, the reference's exact expression
+        ray_samples.spacing_bins[:, -1] = 1 - 1e-7  # "Hacky, but sky is ish at infinity" (neurad.py:455)
+        # the reference computes the masks whenever is_lidar is present (and needs directions_norm for it); bundles without
+        # the measured distances simply get no masks here, and calc_lidar_losses then fails loudly on the missing key
+        if self.training and "is_lidar" in ray_bundle.metadata and "directions_norm" in ray_bundle.metadata:
+            self._compute_is_close_to_lidar(ray_samples, *prop_ray_samples)
         return ray_samples, prop_ray_samples, prop_weights
+
+    def _compute_is_close_to_lidar(self, *all_ray_samples: RaySamples) -> None:
+        """neurad.py:677-700: metadata["is_close_to_lidar"] [N,S,1] for every level (lidar carving supervision)."""
+        be = self._bind()
+        for rs in all_ray_samples:
+            if rs is None:
+                continue
+            md = rs.metadata = dict(rs.metadata)  # one dict per level (the reference's metadata is per RaySamples too)
+            md["is_close_to_lidar"] = be.lidar_carving_mask(rs.frustums.bin_edges, md["is_lidar"], md["directions_norm"],
+                                                            md.get("did_return"), self.config.carving_epsilon,
+                                                            self.config.non_return_lidar_distance)[..., None]
 
     def _render_weights(self, outputs, ray_samples: RaySamples) -> Tensor:
         """neurad.py:711-724, use_sdf branch: nerfacc.render_weight_from_alpha on [N,S]."""

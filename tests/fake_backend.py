@@ -140,6 +140,19 @@ class FakeBackend(B200Backend):
         r = O.pdf_resample(weights, bins, num_samples, histogram_padding, rand=rand)
         return r["bins"], r["cdf"], r["inds"].int()
 
+    def lidar_carving_mask(self, bins_e, is_lidar, directions_norm, did_return, carving_epsilon, non_return_distance):
+        from oracle import losses_oracle as LO
+
+        n = bins_e.shape[0]
+        return LO.is_close_to_lidar(bins_e, is_lidar.reshape(n).bool(), directions_norm.reshape(n),
+                                    None if did_return is None else did_return.reshape(n).bool(), carving_epsilon, non_return_distance)
+
+    def distortion_loss(self, sdist, weights, want_grad=False):
+        return emul.distortion_loss(sdist, weights.detach(), want_grad)
+
+    def zipnerf_interlevel_loss(self, sdist, weights, prop_sdist, prop_weights, pulse_width, want_grad=False):
+        return emul.zipnerf_interlevel(sdist, weights, prop_sdist, prop_weights.detach(), pulse_width, want_grad)
+
     def pdf_resample(self, weights, bins, num_samples, histogram_padding=0.01):
         r = O.pdf_resample(weights, bins, num_samples, histogram_padding)
         return r["bins"], r["cdf"], r["inds"].int()

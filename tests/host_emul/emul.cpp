@@ -331,4 +331,17 @@ int emul_linear_wgrad(const float* x, const float* dy, long long n_rows, int K, 
     }
   return 0;
 }
+
+// training regularisers (nff_modules.h: distortion_loss_ray / zipnerf_interlevel_ray), one "thread" per ray
+int emul_distortion_loss(const float* c, const float* w, long long n_rays, int S, float* loss, float* dw) {
+  for (long long r = 0; r < n_rays; ++r) loss[r] = distortion_loss_ray(c + r * (S + 1), w + r * S, S, dw ? dw + r * S : nullptr);
+  return 0;
+}
+int emul_zipnerf_interlevel(const float* c, const float* w, int S, const float* cp, const float* wp, int Sp, float pulse_width,
+                            long long n_rays, float* loss, float* dwp) {
+  for (long long r = 0; r < n_rays; ++r)
+    loss[r] = zipnerf_interlevel_ray(c + r * (S + 1), w + r * S, S, cp + r * (Sp + 1), wp + r * Sp, Sp, pulse_width,
+                                     dwp ? dwp + r * Sp : nullptr);
+  return 0;
+}
 }

@@ -232,3 +232,29 @@ def linear_wgrad(x, dy, relu_x, dW, db, n_ctas=3):
     rc = lib.emul_linear_wgrad(p(x), p(dy), ctypes.c_longlong(x.shape[0]), ctypes.c_int(x.shape[1]), ctypes.c_int(dy.shape[1]),
                                ctypes.c_int(int(relu_x)), ctypes.c_int(n_ctas), p(dW), p(db))
     assert rc == 0
+
+
+def distortion_loss(sdist, weights, want_grad=True):
+    """distortion_loss_ray per ray: (loss [N], dweights [N,S])."""
+    lib = ctypes.CDLL(build())
+    c, w = sdist.float().contiguous(), weights.float().contiguous()
+    loss = torch.zeros(c.shape[0])
+    dw = torch.zeros_like(w) if want_grad else None
+    p = lambda t: None if t is None else ctypes.c_void_p(t.data_ptr())  # noqa: E731
+    rc = lib.emul_distortion_loss(p(c), p(w), ctypes.c_longlong(c.shape[0]), ctypes.c_int(w.shape[1]), p(loss), p(dw))
+    assert rc == 0
+    return loss, dw
+
+
+def zipnerf_interlevel(sdist, weights, prop_sdist, prop_weights, pulse_width, want_grad=True):
+    """zipnerf_interlevel_ray per ray for one proposal level: (loss [N], dprop_weights [N,Sp])."""
+    lib = ctypes.CDLL(build())
+    c, w = sdist.float().contiguous(), weights.float().contiguous()
+    cp, wp = prop_sdist.float().contiguous(), prop_weights.float().contiguous()
+    loss = torch.zeros(c.shape[0])
+    dwp = torch.zeros_like(wp) if want_grad else None
+    p = lambda t: None if t is None else ctypes.c_void_p(t.data_ptr())  # noqa: E731
+    rc = lib.emul_zipnerf_interlevel(p(c), p(w), ctypes.c_int(w.shape[1]), p(cp), p(wp), ctypes.c_int(wp.shape[1]),
+                                     ctypes.c_float(pulse_width), ctypes.c_longlong(c.shape[0]), p(loss), p(dwp))
+    assert rc == 0
+    return loss, dwp

@@ -100,14 +100,13 @@ def proposal_sampler_and_module_walk_match_reference_golden(name, dev):
         assert rel_to_max(mod[k], fused[k]) < 1e-4, k
     assert rel_to_max(mod["depth"], ref["depth"]) < tol_depth
     rs_list, w_list = mod["ray_samples_list"], mod["weights_list"]
-    assert [r.shape[1] for r in rs_list] == [128, 64, 32] and len(w_list) == 3
+    # proposal levels, then the final level WITHOUT the sky sample (neurad.py:385-386, 404-405)
+    assert [r.shape[1] for r in rs_list] == [128, 64, 31] and [w.shape[1] for w in w_list] == [128, 64, 31]
     for rd in (0, 1):
         assert rel_to_max(w_list[rd], ref[f"prop_weights_{rd}"]) < 1e-4
-    for lvl in (1, 2):
-        assert (rs_list[lvl].spacing_bins.cpu() - ref[f"bins_s_{lvl}"].reshape(n, -1)).abs().max().item() < 1e-5
-    e2 = rs_list[2].frustums.bin_edges.cpu()
-    assert rel_to_max(e2[:, :-1], ref["bins_e_2"].reshape(n, -1)[:, :-1]) < 1e-4
-    assert torch.all(e2[:, -1] == cfg.sampling.sky_distance)  # the sky sample (neurad.py:451-455)
+    assert (rs_list[1].spacing_bins.cpu() - ref["bins_s_1"].reshape(n, -1)).abs().max().item() < 1e-5
+    assert (rs_list[2].spacing_bins.cpu() - ref["bins_s_2"].reshape(n, -1)[:, :-1]).abs().max().item() < 1e-5
+    assert rel_to_max(rs_list[2].frustums.bin_edges, ref["bins_e_2"].reshape(n, -1)[:, :-1]) < 1e-4
     model._bind().check_status()
 
 
@@ -280,7 +279,7 @@ def training_mode_walk_runs(name, dev):
         assert torch.isfinite(a[k]).all() and a[k].shape == b[k].shape
     assert not torch.equal(a["depth"], b["depth"])
     e2 = a["ray_samples_list"][2].frustums.bin_edges
-    assert torch.all(e2[:, 1:] >= e2[:, :-1]) and torch.all(e2[:, -1] == cfg.sampling.sky_distance)
+    assert torch.all(e2[:, 1:] >= e2[:, :-1]) and e2.shape[1] == cfg.sampling.num_nerf_samples
     a["features"].sum().backward()
     assert model._param("field.mlp_geo.layers.0.weight").grad.abs().max().item() > 0
     if meta["n_actors"]:
@@ -291,3 +290,70 @@ def training_mode_walk_runs(name, dev):
     with torch.no_grad():
         c, d = model.get_nff_outputs(rb, fused=False), model.get_nff_outputs(rb, fused=False)
     assert torch.equal(c["depth"], d["depth"])
+
+
+def training_losses_match_reference_golden(dev):
+    """distortion_loss / zipnerf_interlevel_loss (reference signatures: weights_list, ray_samples_list) through the loss
+    kernels and their autograd bindings, against the reference's own values and autograd gradients
+    (tests/golden/losses.npz: loss = 3 * interlevel + 5 * distortion on a real render's lists)."""
+    from neurad_studio_b200 import losses as L
+    from neurad_studio_b200.nerfstudio_api import Frustums, RaySamples
+
+    meta, g = load_golden("losses.npz")
+    sd = [g["in"][f"sdist_{i}"].to(dev) for i in range(3)]
+    ws = [g["in"][f"weights_{i}"].to(dev).requires_grad_(True) for i in range(3)]
+    n = sd[0].shape[0]
+    z3 = torch.zeros(n, 3, device=dev)
+    rs_list = [RaySamples(Frustums(z3, z3, s.clone()), s) for s in sd]
+    w_list = [w[..., None] for w in ws]
+    li = L.zipnerf_interlevel_loss(w_list, rs_list)
+    ld = L.distortion_loss(w_list, rs_list)
+    assert abs(li.item() - g["ref"]["interlevel"].item()) < 5e-4 * abs(g["ref"]["interlevel"].item())
+    assert abs(ld.item() - g["ref"]["distortion"].item()) < 1e-5 * abs(g["ref"]["distortion"].item())
+    (li * 3 + ld * 5).backward()
+    assert rel_to_max(ws[2].grad, g["ref"]["grad_2"]) < 1e-4
+    for i in range(2):  # ill-conditioned by 1 / (wp + 1e-5): the reference's own fp32 result is 1-2e-4 from float64
+        assert rel_to_max(ws[i].grad, g["ref"][f"grad_{i}"]) < 5e-4, i
+    with torch.no_grad():
+        assert abs(L.distortion_loss(w_list, rs_list).item() - ld.item()) < 1e-7
+    assert torch.equal(L.ray_samples_to_sdist(rs_list[1]), sd[1])
+
+
+def lidar_carving_masks_and_training_outputs(dev):
+    """_compute_is_close_to_lidar against the reference's own masks (tests/golden/losses.npz), and the training-only
+    outputs of get_nff_outputs(calc_lidar_losses=True) (neurad.py:402-419)."""
+    from neurad_studio_b200 import nerfstudio_api
+
+    be = nerfstudio_api.get_backend(torch.device(dev, 0) if dev == "cuda" else torch.device(dev))
+    meta, g = load_golden("losses.npz")
+    i = g["in"]
+    for tag, dr in (("with_return", i["carv_did_return"]), ("no_return_key", None)):
+        m = be.lidar_carving_mask(i["carv_edges"].to(dev), i["carv_is_lidar"].to(dev), i["carv_directions_norm"].to(dev),
+                                  None if dr is None else dr.to(dev), 0.1, 150.0)
+        assert m.dtype == torch.bool and torch.equal(m.cpu(), g["ref"][f"carving_{tag}"])
+    meta, cfg, model, rb, gg = _model_and_bundle("nff_actors.npz", dev)
+    rb = rb[:64]
+    n = len(rb)
+    gen = torch.Generator().manual_seed(5)
+    rb.metadata["directions_norm"] = (5 + 60 * torch.rand(n, 1, generator=gen)).to(dev)
+    rb.metadata["did_return"] = (torch.rand(n, 1, generator=gen) < 0.8).to(dev)
+    model.requires_grad_(True)
+    model.train()
+    out = model.get_nff_outputs(rb, calc_lidar_losses=True)
+    is_lidar = rb.metadata["is_lidar"].reshape(-1).bool()
+    assert is_lidar.any() and (~is_lidar).any()
+    for k in ("prop_weights_loss_0", "prop_weights_loss_1"):
+        assert out[k].dim() == 0 and torch.isfinite(out[k]) and out[k].item() >= 0
+    rs = out["ray_samples_list"]
+    close = rs[0].metadata["is_close_to_lidar"]
+    assert close.shape == (n, 128, 1) and not close[~is_lidar].any()
+    w_main = out["weights_list"][-1]
+    assert out["non_nearby_weights"].shape[1] == 1 and out["non_nearby_weights"].shape[0] == out["non_nearby_lidar_ray_indices"].shape[0]
+    assert out["non_nearby_weights"].shape[0] <= int(is_lidar.sum()) * w_main.shape[1]
+    first_lidar = int(is_lidar.int().argmax())
+    assert (out["non_nearby_lidar_ray_indices"] + first_lidar).max().item() < n
+    (out["prop_weights_loss_0"] + out["non_nearby_weights"].pow(2).sum()).backward()
+    assert model._param("proposal_fields.1.density_decoder.weight").grad is not None
+    model.eval()
+    with torch.no_grad():
+        assert "prop_weights_loss_0" not in model.get_nff_outputs(rb, calc_lidar_losses=True, fused=False)

@@ -109,3 +109,23 @@ def test_encoding_backward_density_mode(name):
     for a, k in enumerate(keys[1:1 + n_act]):
         want = q[k].grad if q[k].grad is not None else torch.zeros_like(p[k])
         assert (grads["actors"][a] - want).abs().max().item() <= 1e-4 * max(want.abs().max().item(), 1e-6)
+
+
+def test_training_losses_match_reference_golden():
+    """distortion_loss_ray / zipnerf_interlevel_ray (csrc/nff_modules.h) against the reference's own loss values and
+    autograd gradients (tests/golden/losses.npz, oracle/make_golden_losses.py: loss = 3 * interlevel + 5 * distortion)."""
+    meta, g = load_golden("losses.npz")
+    sd = [g["in"][f"sdist_{i}"] for i in range(3)]
+    w = [g["in"][f"weights_{i}"] for i in range(3)]
+    n = sd[0].shape[0]
+    dl, ddw = emul.distortion_loss(sd[2], w[2])
+    assert abs(dl.mean().item() - g["ref"]["distortion"].item()) < 1e-5 * abs(g["ref"]["distortion"].item())
+    assert rel_to_max(ddw * 5 / n, g["ref"]["grad_2"]) < 1e-4  # only the distortion loss reaches the final level's weights
+    total = 0.0
+    for i in range(2):
+        li, dwp = emul.zipnerf_interlevel(sd[2], w[2], sd[i], w[i], meta["pulse_widths"][i])
+        total += li.mean().item()
+        # relu(w_s - wp)^2 / (wp + 1e-5) amplifies rounding in the blurred cdf: the reference's own fp32 result is 1-2e-4
+        # away from a float64 evaluation, and so is this one (cumulative sums in double, like torch's CPU cumsum)
+        assert rel_to_max(dwp * 3 / n, g["ref"][f"grad_{i}"]) < 5e-4, i
+    assert abs(total - g["ref"]["interlevel"].item()) < 5e-4 * abs(g["ref"]["interlevel"].item())

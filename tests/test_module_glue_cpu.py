@@ -48,3 +48,11 @@ def test_stratified_sampling_glue():
 @pytest.mark.parametrize("name", ["nff_static.npz", "nff_actors.npz"])
 def test_training_mode_walk_glue(name):
     C.training_mode_walk_runs(name, "cpu")
+
+
+def test_training_losses_glue():
+    C.training_losses_match_reference_golden("cpu")
+
+
+def test_lidar_carving_masks_glue():
+    C.lidar_carving_masks_and_training_outputs("cpu")

@@ -48,3 +48,11 @@ def test_stratified_sampling_matches_reference_golden():
 @pytest.mark.parametrize("name", ["nff_static.npz", "nff_actors.npz"])
 def test_training_mode_walk_runs(name):
     C.training_mode_walk_runs(name, "cuda")
+
+
+def test_training_losses_match_reference_golden():
+    C.training_losses_match_reference_golden("cuda")
+
+
+def test_lidar_carving_masks_and_training_outputs():
+    C.lidar_carving_masks_and_training_outputs("cuda")
