@@ -903,14 +903,61 @@ class NeuRADModel(nn.Module):
         e1 = emb[(after + sensor * eps).long()]
         return e0 * (1 - frac) + e1 * frac
 
-    @torch.no_grad()
-    def decode_features(self, features: Tensor) -> Tuple[Tensor, Tensor]:
-        """neurad.py:337-357, lidar half: (intensity = sigmoid(o[...,0:1]), ray_drop_logits = o[...,1:2])."""
+    def decode_features(self, features: Tensor, patch_size: Optional[Tuple[int, int]] = None, is_lidar: Optional[Tensor] = None,
+                        intensity_for_cam: bool = False):
+        """neurad.py:337-366.  With `patch_size` (the reference's signature) returns (rgb, intensity, ray_drop_logits):
+        lidar rays (`is_lidar` [N,1]) go through `lidar_decoder` (MLP 48->32->32->2 on the tcgen05 operator, intensity =
+        sigmoid), camera rays are reshaped to patches [B,ph,pw,C] and decoded by `rgb_decoder` to [B,3ph,3pw,3]
+        (channels-last in and out: the reference's two permutes cancel).  Without `patch_size`: the lidar half only,
+        (intensity, ray_drop_logits) for all rows."""
         be = self._bind()
-        sd = self.reference_state_dict()
-        o = be.mlp_fwd(features, [sd[f"lidar_decoder.layers.{i}.weight"] for i in range(3)],
-                       [sd[f"lidar_decoder.layers.{i}.bias"] for i in range(3)])
-        return o[..., 0:1].sigmoid(), o[..., 1:2]
+        wb = self._mlp_params("lidar_decoder", 3)
+
+        def lidar_head(x):
+            if x.shape[0] == 0:
+                return x.new_zeros(0, 2)
+            if torch.is_grad_enabled() and (x.requires_grad or any(t.requires_grad for t in wb)):
+                return AG.MlpFn.apply(be, x.contiguous(), *wb)
+            with torch.no_grad():
+                return be.mlp_fwd(x, wb[0::2], wb[1::2])
+
+        if patch_size is None:
+            o = lidar_head(features)
+            return o[..., 0:1].sigmoid(), o[..., 1:2]
+        if is_lidar is None:
+            lidar_features, cam_features = features[:0], features
+        else:
+            m = is_lidar.reshape(-1).bool()
+            lidar_features, cam_features = features[m], features[~m]
+        if intensity_for_cam:
+            o = lidar_head(features)
+        elif lidar_features.numel() > 0:
+            o = lidar_head(lidar_features)
+        else:
+            o = None
+        intensity, ray_drop_logit = (None, None) if o is None else (o[..., 0:1].sigmoid(), o[..., 1:2])
+        rgb = None
+        if cam_features.numel() > 0:
+            patches = cam_features.reshape(-1, *patch_size, cam_features.shape[-1])
+            rgb = self.rgb_decoder(patches)  # eval mode only: raises in training mode (BatchNorm batch statistics)
+        return rgb, intensity, ray_drop_logit
+
+    def get_outputs(self, ray_bundle: RayBundle, patch_size: Tuple[int, int], intensity_for_cam: bool = False,
+                    calc_lidar_losses: bool = True) -> Dict[str, Tensor]:
+        """neurad.py:311-335: get_nff_outputs + decode_features; `features` is dropped from the result.  (The camera
+        optimizer's `apply_to_raybundle` of training mode is pose optimisation: not part of this path.)"""
+        out = self.get_nff_outputs(ray_bundle, calc_lidar_losses)
+        rgb, intensity, ray_drop_logits = self.decode_features(out["features"], patch_size, ray_bundle.flatten().metadata.get("is_lidar"),
+                                                               intensity_for_cam)
+        out.pop("features", None)
+        for k, v in (("rgb", rgb), ("intensity", intensity), ("ray_drop_logits", ray_drop_logits)):
+            if v is not None:
+                out[k] = v
+        return out
+
+    def forward(self, ray_bundle: RayBundle, patch_size: Tuple[int, int] = (1, 1), intensity_for_cam: bool = False,
+                calc_lidar_losses: bool = True) -> Dict[str, Tensor]:
+        return self.get_outputs(ray_bundle, patch_size, intensity_for_cam, calc_lidar_losses)
 
     @torch.no_grad()
     def get_outputs_for_camera_ray_bundle(self, camera_ray_bundle: RayBundle) -> Dict[str, Tensor]:

@@ -147,6 +147,17 @@ class FakeBackend(B200Backend):
         return LO.is_close_to_lidar(bins_e, is_lidar.reshape(n).bool(), directions_norm.reshape(n),
                                     None if did_return is None else did_return.reshape(n).bool(), carving_epsilon, non_return_distance)
 
+    def set_rgb_decoder(self, sd, prefix="rgb_decoder", bn_eps=1e-5):
+        pre = prefix + "." if prefix else ""
+        self._dec = {"rgb_decoder." + k[len(pre):]: v.detach().cpu() for k, v in sd.items() if k.startswith(pre)}
+
+    @torch.no_grad()
+    def rgb_decode(self, features, impl="tc", out=None):
+        from oracle import decoder_oracle as D
+
+        f = features if features.dim() == 4 else features[None]
+        return D.rgb_decoder(self._dec, f)
+
     def distortion_loss(self, sdist, weights, want_grad=False):
         return emul.distortion_loss(sdist, weights.detach(), want_grad)
 

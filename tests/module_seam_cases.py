@@ -357,3 +357,51 @@ def lidar_carving_masks_and_training_outputs(dev):
     model.eval()
     with torch.no_grad():
         assert "prop_weights_loss_0" not in model.get_nff_outputs(rb, calc_lidar_losses=True, fused=False)
+
+
+def get_outputs_and_decode_features(dev):
+    """NeuRADModel.get_outputs / forward / decode_features with the reference's signatures (neurad.py:302-366) on a mixed
+    camera + lidar bundle: lidar rows through the lidar decoder, camera rows as patches through the rgb decoder."""
+    from oracle import decoder_oracle as D
+
+    meta, cfg, model, rb, g = _model_and_bundle("nff_actors.npz", dev)
+    ref = g["ref"]
+    dec = D.random_decoder_params(seed=41)
+    model.rgb_decoder.load_state_dict({k[len("rgb_decoder."):]: v for k, v in dec.items()}, strict=False)
+    model = model.to(dev).eval()
+    il_all = rb.metadata["is_lidar"].reshape(-1).bool()
+    # 64 camera rays (one 4 x 16 patch, the image geometry the decoder is GPU-validated on) + every lidar ray
+    keep = torch.cat([(~il_all).nonzero()[:64, 0], il_all.nonzero()[:, 0]])
+    rb, ref_i, ref_d = rb[keep], ref["intensity"][keep.cpu()], ref["ray_drop_logits"][keep.cpu()]
+    is_lidar = rb.metadata["is_lidar"].reshape(-1).bool()
+    n_cam = int((~is_lidar).sum())
+    assert n_cam == 64 and is_lidar.any()
+    with torch.no_grad():
+        nff = model.get_nff_outputs(rb)
+        out = model(rb, patch_size=(4, 16))
+        assert "features" not in out and set(("rgb", "intensity", "ray_drop_logits", "depth", "accumulation")) <= set(out)
+        assert out["rgb"].shape == (1, 12, 48, 3) and out["intensity"].shape == (int(is_lidar.sum()), 1)
+        assert rel_to_max(out["intensity"], ref_i[is_lidar.cpu()]) < 1e-4
+        assert rel_to_max(out["ray_drop_logits"], ref_d[is_lidar.cpu()]) < 1e-4
+        want = D.rgb_decoder(dec, nff["features"].cpu()[~is_lidar.cpu()].reshape(1, 4, 16, -1))
+        assert (out["rgb"].cpu() - want).abs().max().item() < 1e-4
+        # two 2 x 16 patches, intensity for every (camera) ray
+        cam_feats = nff["features"][~is_lidar]
+        rgb, inten, drop = model.decode_features(cam_feats, (2, 16), None, intensity_for_cam=True)
+        assert rgb.shape == (2, 6, 48, 3) and inten.shape == (64, 1) and drop.shape == (64, 1)
+        assert (rgb.cpu() - D.rgb_decoder(dec, cam_feats.cpu().reshape(2, 2, 16, -1))).abs().max().item() < 1e-4
+        # legacy short form: the lidar half on every row
+        i2, d2 = model.decode_features(nff["features"])
+        assert rel_to_max(i2, ref_i) < 1e-4 and rel_to_max(d2, ref_d) < 1e-4
+    # the lidar decoder trains through the MLP backward operator
+    model.requires_grad_(True)
+    feats = nff["features"][is_lidar].detach().clone().requires_grad_(True)
+    _, inten, drop = model.decode_features(feats, (1, 1), torch.ones(feats.shape[0], 1, dtype=torch.bool, device=dev))
+    (inten.sum() + drop.pow(2).sum()).backward()
+    w0 = model._param("lidar_decoder.layers.0.weight")
+    assert w0.grad is not None and w0.grad.abs().max().item() > 0 and feats.grad.abs().max().item() > 0
+    p = {k: g["param"][k].clone().requires_grad_(True) for k in g["param"] if k.startswith("lidar_decoder.")}
+    f2 = feats.detach().cpu().clone().requires_grad_(True)
+    i_ref, d_ref = O.decode_lidar(p, f2)
+    (i_ref.sum() + d_ref.pow(2).sum()).backward()
+    assert rel_to_max(w0.grad, p["lidar_decoder.layers.0.weight"].grad) < 2e-4 and rel_to_max(feats.grad, f2.grad) < 2e-4

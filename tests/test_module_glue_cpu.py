@@ -56,3 +56,7 @@ def test_training_losses_glue():
 
 def test_lidar_carving_masks_glue():
     C.lidar_carving_masks_and_training_outputs("cpu")
+
+
+def test_get_outputs_and_decode_features_glue():
+    C.get_outputs_and_decode_features("cpu")

@@ -56,3 +56,7 @@ def test_training_losses_match_reference_golden():
 
 def test_lidar_carving_masks_and_training_outputs():
     C.lidar_carving_masks_and_training_outputs("cuda")
+
+
+def test_get_outputs_and_decode_features():
+    C.get_outputs_and_decode_features("cuda")
