@@ -66,10 +66,13 @@ class NeuRADHashEncodingConfig:
     static: HashGridSettings = field(default_factory=_main_static)
     actor: HashGridSettings = field(default_factory=_main_actor)
     actor_scale: float = 10.0
+    # ActorSettings.flip_prob, training mode only: 0.25 for the main field's grid (fields/neurad_field.py:51), the
+    # ActorSettings default 0.5 for the proposal fields' grids (field_components/neurad_encoding.py:50)
+    flip_prob: float = 0.25
 
 
 def _prop_grid() -> NeuRADHashEncodingConfig:
-    return NeuRADHashEncodingConfig(static=_prop_static(), actor=_prop_actor())
+    return NeuRADHashEncodingConfig(static=_prop_static(), actor=_prop_actor(), flip_prob=0.5)
 
 
 @dataclass
@@ -102,7 +105,6 @@ class NeuRADConfig:
     actor_bbox_padding: Tuple[float, float, float] = (0.25, 0.25, 0.1)
     carving_epsilon: float = 0.1  # LossSettings (neurad.py:79,87): lidar carving masks of the training outputs
     non_return_lidar_distance: float = 150.0
-    actor_flip_prob: float = 0.5  # ActorSettings.flip_prob (neurad_encoding.py:50), training mode only
     # scene-level constants (dataset metadata in the reference)
     static_scale: float = 100.0
     duration: float = 8.0

@@ -564,7 +564,7 @@ class NeuRADProposalField:
         m = self._model
         pos = ray_samples.frustums.get_fast_isotropic_gaussian(num_multisamples=1)
         be = m._bind()
-        flip = m._draw_actor_flip(ray_samples.shape[0])
+        flip = m._draw_actor_flip(ray_samples.shape[0], self._field)
         pre = f"proposal_fields.{self._field - 1}"
         tables = m._grid_params(pre)
         dec = m._param(f"{pre}.density_decoder.weight")
@@ -879,10 +879,11 @@ class NeuRADModel(nn.Module):
             out += [self._param(f"{prefix}.layers.{i}.weight"), self._param(f"{prefix}.layers.{i}.bias")]
         return out
 
-    def _draw_actor_flip(self, n_rays: int) -> Optional[Tensor]:
+    def _draw_actor_flip(self, n_rays: int, field_index: int = 0) -> Optional[Tensor]:
         """Training-mode random actor flip, one draw per ray and per encoding call (neurad_encoding.py:212-219):
-        -1 with probability flip_prob, else +1.  None in eval mode / without actors."""
-        p = self.config.actor_flip_prob
+        -1 with probability flip_prob of that field's grid (0.25 main, 0.5 proposal), else +1.  None in eval mode /
+        without actors."""
+        p = [self.config.grid, self.config.proposal_grid_1, self.config.proposal_grid_2][field_index].flip_prob
         if not self.training or self.config.n_actors == 0 or p <= 1e-7:
             return None
         return torch.bernoulli(torch.full((n_rays,), p, device=self.static_scale.device)) * -2 + 1

@@ -406,9 +406,11 @@ def hashgrid_forward(
     times: Tensor,
     directions: Optional[Tensor],
     trace: Optional[dict] = None,
+    flip: Optional[Tensor] = None,
 ) -> Tuple[Tensor, Optional[Tensor]]:
-    """neurad_encoding.py:150-223, 265-304 (eval mode: no flip).  mean [N,S,M,3], std [N,S,M,1], times [N,S,1],
-    directions [N,S,3] or None.  Returns (features [N*S, L*F], directions [N,S,3] | None)."""
+    """neurad_encoding.py:150-223, 265-304.  mean [N,S,M,3], std [N,S,M,1], times [N,S,1], directions [N,S,3] or None.
+    `flip` [N] (+1 / -1 per ray) is the training-mode random actor flip (:212-219, drawn with torch.bernoulli there);
+    None = eval mode.  Returns (features [N*S, L*F], directions [N,S,3] | None)."""
     sg, ag = fcfg.static, fcfg.actor
     s_scal = params[f"{prefix}.hashgrid.static_grid.scalings"]
     c_mean, c_std = scaled_contraction(mean, std, params["static_scale"])
@@ -435,6 +437,12 @@ def hashgrid_forward(
         dirs = transform_points_pairwise(directions[ray_idx, sample_idx], w2b, with_translation=False).squeeze(1)
         dirs = dirs / (torch.linalg.norm(dirs, dim=-1, keepdim=True) + EPS)
         directions[ray_idx, sample_idx] = dirs
+    if flip is not None:  # neurad_encoding.py:212-219
+        fl = torch.ones_like(pos[..., 0:1, :])
+        fl[..., 0] = flip[ray_idx].unsqueeze(-1)
+        pos = pos * fl
+        if directions is not None:
+            directions[ray_idx, sample_idx, 0] = directions[ray_idx, sample_idx, 0] * fl[..., 0].squeeze(-1)
     if actor_idx.shape[0] == 0:
         return features.view(-1, out_dim), directions
     a_mean, a_std = scaled_contraction(pos, std[ray_idx, sample_idx], fcfg.actor_scale)

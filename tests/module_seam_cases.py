@@ -282,9 +282,10 @@ def training_mode_walk_runs(name, dev):
     assert torch.all(e2[:, 1:] >= e2[:, :-1]) and e2.shape[1] == cfg.sampling.num_nerf_samples
     a["features"].sum().backward()
     assert model._param("field.mlp_geo.layers.0.weight").grad.abs().max().item() > 0
-    if meta["n_actors"]:
-        flips = torch.stack([model._draw_actor_flip(4096) for _ in range(2)])
-        assert set(flips.unique().tolist()) == {-1.0, 1.0} and abs(flips.mean().item()) < 0.1
+    if meta["n_actors"]:  # P(flip) = 0.25 for the main field's grid, 0.5 for the proposal fields' (neurad_field.py:51)
+        for fidx, p_flip in ((0, 0.25), (2, 0.5)):
+            flips = torch.cat([model._draw_actor_flip(4096, fidx) for _ in range(2)])
+            assert set(flips.unique().tolist()) == {-1.0, 1.0} and abs((flips < 0).float().mean().item() - p_flip) < 0.05
     model.eval()
     assert model._draw_actor_flip(8) is None and not model.sampler.pdf_sampler.training
     with torch.no_grad():
@@ -405,3 +406,23 @@ def get_outputs_and_decode_features(dev):
     i_ref, d_ref = O.decode_lidar(p, f2)
     (i_ref.sum() + d_ref.pow(2).sum()).backward()
     assert rel_to_max(w0.grad, p["lidar_decoder.layers.0.weight"].grad) < 2e-4 and rel_to_max(feats.grad, f2.grad) < 2e-4
+
+
+def train_mode_encoding_matches_reference_golden(dev):
+    """NeuRADHashEncoding.forward in training mode: the per-ray actor flip (x -> -x in the box frame for positions and
+    directions) fed the flips the reference drew, against the reference module's outputs
+    (tests/golden/train_encoding.npz, oracle/make_golden_train_encoding.py)."""
+    gmeta, tg = load_golden("train_encoding.npz")
+    meta, cfg, model, rb, g = _model_and_bundle("nff_actors.npz", dev)
+    ref = g["ref"]
+    n = len(rb)
+    starts, ends = ref["starts"].reshape(n, -1), ref["ends"].reshape(n, -1)
+    rs = _samples_from_edges(model, rb, torch.cat([starts, ends[:, -1:]], 1), dev)
+    gs = rs.frustums.get_fast_isotropic_gaussian()
+    be = model._bind()
+    flip = tg["in"]["flip"].to(dev)
+    out = be.neurad_encoding(0, gs.mean, gs.std, rs.times, rs.frustums.directions, flip=flip)
+    assert rel_to_max(out["features"], tg["ref"]["features"]) < 1e-4
+    assert (out["directions"].cpu() - tg["ref"]["directions"]).abs().max().item() < 1e-5
+    ev = be.neurad_encoding(0, gs.mean, gs.std, rs.times, rs.frustums.directions)
+    assert not torch.equal(ev["directions"], out["directions"]) and not torch.equal(ev["features"], out["features"])

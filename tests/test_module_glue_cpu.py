@@ -60,3 +60,7 @@ def test_lidar_carving_masks_glue():
 
 def test_get_outputs_and_decode_features_glue():
     C.get_outputs_and_decode_features("cpu")
+
+
+def test_train_mode_encoding_glue():
+    C.train_mode_encoding_matches_reference_golden("cpu")

@@ -58,3 +58,36 @@ def test_main_encoding_matches_oracle(name):
         d = out["directions"]
         assert torch.equal(d[~inside], r["directions"][:, None, :].expand(n, s, 3)[~inside])
         assert (d[inside].norm(dim=-1) - 1).abs().max() < 1e-5
+
+
+def test_overlapping_actor_boxes_highest_index_wins():
+    """Two actors share a trajectory, so their padded boxes coincide: the reference's `features[ray_idx, sample_idx] = ...`
+    (neurad_encoding.py:185) is a sequential index_put on CPU and the LAST triple (highest actor index) wins; the operator
+    picks the same actor."""
+    meta, g = load_golden("nff_actors.npz")
+    cfg = cfg_from_meta(meta)
+    ocfg = to_oracle_cfg(cfg)
+    p, r, ref = dict(g["param"]), g["ray"], g["ref"]
+    n = r["origins"].shape[0]
+    base = ref["actor_id_main"].reshape(n, -1)
+    a_lo = int(base[base >= 0].min())  # an actor that is hit in this case
+    a_hi = a_lo + 1 if a_lo + 1 < meta["n_actors"] else a_lo - 1
+    for k in ("actor_positions", "actor_rotations_6d", "actor_present_at_time"):
+        t = p[f"dynamic_actors.{k}"].clone()
+        t[:, a_hi] = t[:, a_lo]
+        p[f"dynamic_actors.{k}"] = t
+    sz = p["dynamic_actors.actor_sizes"].clone()
+    sz[a_hi] = sz[a_lo]
+    p["dynamic_actors.actor_sizes"] = sz
+    starts, ends = ref["starts"].reshape(n, -1), ref["ends"].reshape(n, -1)
+    area = scaled_area(cfg, r)
+    trace = {}
+    with torch.no_grad():
+        O.main_field(p, ocfg, r["origins"], r["directions"], area, r["times"].reshape(-1), starts, ends, trace)
+    mean, std = emul.gaussian(r["origins"], r["directions"], area, torch.cat([starts, ends[:, -1:]], 1))
+    out = emul.encoding(cfg, p, O.pdf_u, 0, mean, std, r["times"], r["directions"])
+    want = trace["actor_id"].reshape(n, -1)
+    winner = max(a_lo, a_hi)
+    assert (want == winner).any() and not (want == min(a_lo, a_hi)).any()
+    assert torch.equal(out["actor_id"].long(), want)
+    assert rel_to_max(out["features"].view(n, starts.shape[1], -1), trace["grid_features"]) < 1e-4

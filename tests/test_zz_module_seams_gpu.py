@@ -60,3 +60,7 @@ def test_lidar_carving_masks_and_training_outputs():
 
 def test_get_outputs_and_decode_features():
     C.get_outputs_and_decode_features("cuda")
+
+
+def test_train_mode_encoding_matches_reference_golden():
+    C.train_mode_encoding_matches_reference_golden("cuda")
