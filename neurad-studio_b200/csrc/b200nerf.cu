@@ -69,6 +69,7 @@ struct b200nerf_ctx {
   float* d_dec_wf32[8] = {};          // [49][ci][co] fp32 (CUDA-core reference kernel)
   float* d_dec_bias = nullptr;        // [8][32] folded conv + BN biases
   float* d_dec_small = nullptr;       // in conv w [32*in] b [32] | convT w [32*32*9] b [32] | out conv w [3*32] b [3]
+  bool mlp_attr_set = false;            // mlp_tc_kernel's dynamic shared memory opt-in done on this device
   float** d_grad_actor_ptrs = nullptr;  // [kModMaxActors] per-actor gradient accumulators of the current encoding_bwd call
 };
 
@@ -1282,7 +1283,8 @@ int b200nerf_mlp_fwd(b200nerf_ctx* c, const float* x, int64_t n_rows, int in_dim
   // NeuRAD's own MLPs (<= 48 wide) use the 48-column tile; wider ones (config 1's 32 -> 64 -> 4) the 64-column tile
   const int tile_w = wmax <= 48 ? 48 : kWide;
   size_t smem = sizeof(float) * (off + 3 * tile_w);
-  static bool attr_set = false;
+  // function attributes are per device: one flag per context (several contexts, one per GPU, may share the process)
+  bool& attr_set = c->mlp_attr_set;
   if (!attr_set) {
     CUDA_TRY(cudaFuncSetAttribute(mlp_tc_kernel<48, 48>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
     CUDA_TRY(cudaFuncSetAttribute(mlp_tc_kernel<64, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
