@@ -163,6 +163,12 @@ NFF_D void encode_levels_bwd(float* grad_table, const Grid& gr, const Gauss& g, 
     corner_weights(c, cw);
     float* base = grad_table + (size_t)l * gr.T * gr.F;
     const float w = level_weight(gr.res[l], g.std);
+    if (gr.F == 4) {  // NeuRAD's main grids: a row is 16 bytes -> one vector reduction per corner instead of four
+      const float g0 = dfeat[4 * l] * w, g1 = dfeat[4 * l + 1] * w, g2 = dfeat[4 * l + 2] * w, g3 = dfeat[4 * l + 3] * w;
+      if (g0 == 0.0f && g1 == 0.0f && g2 == 0.0f && g3 == 0.0f) continue;
+      for (int k = 0; k < 8; ++k) atomic_add4(base + (size_t)r[k] * 4, g0 * cw[k], g1 * cw[k], g2 * cw[k], g3 * cw[k]);
+      continue;
+    }
     for (int f = 0; f < gr.F; ++f) {
       const float gs = dfeat[l * gr.F + f] * w;
       if (gs == 0.0f) continue;

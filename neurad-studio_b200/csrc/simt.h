@@ -42,6 +42,10 @@ template <typename T>
 NFF_D T ldg(const T* p) { return __ldg(p); }
 // scatter-accumulate of the backward operators (hash-grid gradients): RED.ADD.F32 to global memory
 NFF_D void atomic_add(float* p, float v) { atomicAdd(p, v); }
+// one 16-byte vector reduction (REDG.E.ADD.F32x4, sm_90+) for a whole F = 4 hash-table row; p must be 16-byte aligned
+NFF_D void atomic_add4(float* p, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
 }  // namespace simt
 
 #else
@@ -104,6 +108,7 @@ inline float fsqrt(float a) { return std::sqrt(a); }
 template <typename T>
 inline T ldg(const T* p) { return *p; }
 inline void atomic_add(float* p, float v) { *p += v; }  // the backward emulation runs its "threads" one after the other
+inline void atomic_add4(float* p, float a, float b, float c, float d) { p[0] += a; p[1] += b; p[2] += c; p[3] += d; }
 }  // namespace simt
 
 inline float fminf_(float a, float b) { return std::fmin(a, b); }
