@@ -155,31 +155,63 @@ class MLP(nn.Module):
     output activation.  Parameters are `layers.{i}.weight/bias` like the torch implementation (mlp.py:142-157)."""
 
     def __init__(self, in_dim: int, num_layers: int, layer_width: int, out_dim: Optional[int] = None,
+                 activation: Optional[nn.Module] = None, out_activation: Optional[nn.Module] = None,
                  implementation: str = "b200") -> None:
         super().__init__()
         assert in_dim > 0
+        if activation is not None and not isinstance(activation, nn.ReLU):
+            raise NotImplementedError("the tensor-core MLP operator has ReLU hidden activations (all NeuRAD uses)")
         self.in_dim, self.num_layers, self.layer_width = in_dim, num_layers, layer_width
         self.out_dim = out_dim if out_dim is not None else layer_width
-        dims = [in_dim] + [layer_width] * (num_layers - 1) + [self.out_dim]
-        self.layers = nn.ModuleList([nn.Linear(dims[i], dims[i + 1]) for i in range(num_layers)])
+        self.out_activation = out_activation  # applied on the operator's output (none on NeuRAD's path)
+        self.build_nn_modules()
+
+    def build_nn_modules(self) -> None:
+        """mlp.py:142-157 (the reference builds its layers here too; calling it again re-initialises them)."""
+        dims = [self.in_dim] + [self.layer_width] * (self.num_layers - 1) + [self.out_dim]
+        self.layers = nn.ModuleList([nn.Linear(dims[i], dims[i + 1]) for i in range(self.num_layers)])
+
+    def get_out_dim(self) -> int:
+        return self.out_dim
 
     @torch.no_grad()
     def forward(self, in_tensor: Tensor) -> Tensor:
         be = get_backend(in_tensor.device)
-        return be.mlp_fwd(in_tensor, [l.weight for l in self.layers], [l.bias for l in self.layers])
+        y = be.mlp_fwd(in_tensor, [l.weight for l in self.layers], [l.bias for l in self.layers])
+        return y if self.out_activation is None else self.out_activation(y)
+
+
+class NearFarCollider:
+    """model_components/scene_colliders.py:169-191: fixed nears / fars on a ray bundle."""
+
+    def __init__(self, near_plane: float, far_plane: float, reset_near_plane: bool = True) -> None:
+        self.near_plane, self.far_plane, self.reset_near_plane = near_plane, far_plane, reset_near_plane
+        self.training = True  # a freshly constructed nn.Module is in training mode
+
+    def set_nears_and_fars(self, ray_bundle: RayBundle) -> RayBundle:
+        ones = torch.ones_like(ray_bundle.origins[..., 0:1])
+        near_plane = self.near_plane if (self.training or not self.reset_near_plane) else 0
+        ray_bundle.nears = ones * near_plane
+        ray_bundle.fars = ones * self.far_plane
+        return ray_bundle
+
+    def __call__(self, ray_bundle: RayBundle) -> RayBundle:
+        if ray_bundle.nears is not None and ray_bundle.fars is not None:
+            return ray_bundle  # scene_colliders.py:35-39
+        return self.set_nears_and_fars(ray_bundle)
 
 
 class PDFSampler:
-    """model_components/ray_samplers.py:255-376 in eval mode with include_original=False.
+    """model_components/ray_samplers.py:255-376 (include_original=True, the reference's default, merges the old edges
+    into the new ones with a sort; NeuRAD's sampler passes False).
 
     Reference signature `pdf_sampler(ray_bundle, ray_samples, weights, num_samples=)` -> RaySamples (the resampled
     spacing bins mapped through the existing samples' spacing_to_euclidean_fn, :363-375); the short form
     `pdf_sampler(weights, existing_bins, num_samples)` returns just the new spacing-domain edges."""
 
     def __init__(self, num_samples: Optional[int] = None, train_stratified: bool = True, single_jitter: bool = False,
-                 include_original: bool = False, histogram_padding: float = 0.01) -> None:
-        if include_original:
-            raise NotImplementedError("include_original=True is not on NeuRAD's path (ray_samplers.py:606)")
+                 include_original: bool = True, histogram_padding: float = 0.01) -> None:
+        self.include_original = include_original  # NeuRAD's sampler passes False (ray_samplers.py:606)
         self.num_samples, self.histogram_padding = num_samples, histogram_padding
         self.train_stratified, self.single_jitter = train_stratified, single_jitter
         self.training = False  # the reference's samplers are nn.Modules; NeuRADModel.train() propagates the flag
@@ -187,6 +219,8 @@ class PDFSampler:
     @torch.no_grad()
     def __call__(self, *args, num_samples: Optional[int] = None, **kw):
         if args and isinstance(args[0], RayBundle) or "ray_bundle" in kw:
+            if len(args) > 3:  # (ray_bundle, ray_samples, weights, num_samples) as in tests/model_components/test_ray_sampler.py
+                num_samples, args = args[3], args[:3]
             return self.generate_ray_samples(*args, num_samples=num_samples, **kw)
         weights, existing_bins = args[0], args[1]
         n = num_samples or (args[2] if len(args) > 2 else None) or self.num_samples
@@ -211,6 +245,8 @@ class PDFSampler:
             bins = be.pdf_resample_stratified(w, existing, n, rand, self.histogram_padding)[0]
         else:
             bins = be.pdf_resample(w, existing, n, self.histogram_padding)[0]
+        if self.include_original:  # ray_samplers.py:360-361
+            bins, _ = torch.sort(torch.cat([existing, bins], -1), -1)
         fr = ray_samples.frustums
         return RaySamples(Frustums(fr.origins, fr.directions, ray_samples.spacing_to_euclidean_fn(bins), fr.pixel_area), bins,
                           times=ray_samples.times, metadata=ray_samples.metadata, spacing=ray_samples.spacing)
@@ -224,15 +260,30 @@ class GaussiansStd:
     std: Tensor
 
 
-@dataclass
 class Frustums:
     """cameras/rays.py:33-60 for contiguous samples: per-ray origins/directions [N,3], pixel_area [N,1] and the
-    euclidean bin edges [N,S+1] (starts = edges[:, :-1], ends = edges[:, 1:]) -- never expanded to [N,S,3] views."""
+    euclidean bin edges [N,S+1] (starts = edges[:, :-1], ends = edges[:, 1:]) -- never expanded to [N,S,3] views.
+    The reference's keyword form `Frustums(origins=, directions=, starts=, ends=, pixel_area=)` is accepted when the bins
+    are contiguous (ends[i] == starts[i+1], which every sampler of the path produces)."""
 
-    origins: Tensor
-    directions: Tensor
-    bin_edges: Tensor
-    pixel_area: Optional[Tensor] = None
+    def __init__(self, origins: Tensor, directions: Tensor, bin_edges: Optional[Tensor] = None, pixel_area: Optional[Tensor] = None,
+                 starts: Optional[Tensor] = None, ends: Optional[Tensor] = None) -> None:
+        if bin_edges is None:
+            if starts is None or ends is None:
+                raise ValueError("Frustums needs bin_edges or starts + ends")
+            st = starts.reshape(origins.reshape(-1, 3).shape[0], -1)
+            en = ends.reshape(st.shape)
+            if st.shape[1] > 1 and not torch.equal(st[:, 1:], en[:, :-1]):
+                raise NotImplementedError("non-contiguous sample bins (ends[i] != starts[i+1])")
+            bin_edges = torch.cat([st, en[:, -1:]], dim=1)
+        self.origins, self.directions, self.bin_edges, self.pixel_area = origins, directions, bin_edges, pixel_area
+
+    @classmethod
+    def get_mock_frustum(cls, device="cpu") -> "Frustums":
+        """rays.py:126-139: a size-1 placeholder frustum."""
+        one = torch.ones((1, 1), device=device)
+        return cls(origins=torch.ones((1, 3), device=device), directions=torch.ones((1, 3), device=device), starts=one, ends=one,
+                   pixel_area=one)
 
     @property
     def starts(self) -> Tensor:

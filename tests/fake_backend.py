@@ -118,6 +118,22 @@ class FakeBackend(B200Backend):
                 y = torch.relu(y)
         return y.reshape(*x.shape[:-1], y.shape[-1])
 
+    @torch.no_grad()
+    def frustum_positions(self, origins, directions, bins_e, aabb=None):
+        assert aabb is None
+        n = bins_e.shape[0]
+        return S.frustum_positions(origins.reshape(n, 3), directions.reshape(n, 3), bins_e[:, :-1, None], bins_e[:, 1:, None])
+
+    @torch.no_grad()
+    def hashgrid_fwd(self, g, table, x, scalings=None, want_indices=False):
+        sc = g.scalings() if scalings is None else scalings
+        y = O.hash_encode(x.reshape(-1, 3), table, sc, 2 ** g.log2_hashmap_size)
+        return y.reshape(*x.shape[:-1], y.shape[-1])
+
+    @torch.no_grad()
+    def sh4_fwd(self, dirs):
+        return O.sh_components_l4(dirs)
+
     def spaced_sample(self, nears, fars, num_samples, spacing="uniform", power_lambda=-1.0, power_scaling=0.1):
         f = fars.reshape(-1, 1)
         nr = torch.zeros_like(f) if nears is None else nears.reshape(-1, 1)
