@@ -806,7 +806,9 @@ class NeuRADModel(nn.Module):
         the library -- the per-module API of SURVEY 8b; additionally returns the reference's training-side extras
         `weights_list` / `ray_samples_list` (neurad.py:404-405)."""
         be = self._bind()
-        wants_grad = torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())
+        # only the parameters of THIS path count (the rgb decoder's nn.Conv2d weights require grad by default, but it is
+        # evaluated after this function and is inference-only)
+        wants_grad = torch.is_grad_enabled() and any(getattr(self, n).requires_grad for n, _ in self._names)
         if fused is None:
             fused = not wants_grad  # the fused kernels are forward-only; training walks the modules (autograd operators)
         if fused:

@@ -49,3 +49,29 @@ def test_rgb_decoder_mirror_has_the_reference_state_dict_keys():
     if not torch.cuda.is_available():
         with pytest.raises(RuntimeError):
             dec(g["in"]["features"])
+
+
+def test_fused_path_is_the_default_without_trainable_parameters(monkeypatch):
+    """A freshly constructed / loaded model (hot-path parameters frozen, rgb decoder's nn.Conv2d weights requiring grad
+    by default) must take the fused kernels even outside torch.no_grad(); the module walk is for training only."""
+    from neurad_studio_b200 import nerfstudio_api
+    from neurad_studio_b200.nerfstudio_api import NeuRADModel, RayBundle
+    from tests.fake_backend import FakeBackend
+
+    be = FakeBackend()
+    calls = []
+    orig = be.render
+    be.render = lambda *a, **k: (calls.append("fused"), orig(*a, **k))[1]
+    monkeypatch.setattr(nerfstudio_api, "get_backend", lambda device: be)
+    meta, g = load_golden("nff_static.npz")
+    model = NeuRADModel(cfg_from_meta(meta))
+    model.load_reference_state_dict(g["param"])
+    assert any(p.requires_grad for p in model.rgb_decoder.parameters())
+    r = g["ray"]
+    rb = RayBundle(origins=r["origins"][:8], directions=r["directions"][:8], pixel_area=r["pixel_area"][:8], times=r["times"][:8],
+                   metadata={"is_lidar": r["is_lidar"][:8], "sensor_idxs": r["sensor_idx"][:8]})
+    out = model.get_nff_outputs(rb)
+    assert calls == ["fused"] and "weights_list" not in out
+    model.requires_grad_(True)
+    out = model.get_nff_outputs(rb)
+    assert calls == ["fused"] and "weights_list" in out
