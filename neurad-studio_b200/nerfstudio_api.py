@@ -503,9 +503,10 @@ class DepthRenderer(nn.Module):
 
 
 class ProposalNetworkSampler:
-    """model_components/ray_samplers.py:569-666, eval mode: initial sampler, then per proposal level density_fns[i] ->
-    RaySamples.get_weights -> PDFSampler.  Every step is one of the library's stage kernels; the fused
-    `b200nerf_nff_render_fwd` does the same work without materialising any of these tensors."""
+    """model_components/ray_samplers.py:569-666: initial sampler, then per proposal level density_fns[i] ->
+    RaySamples.get_weights -> PDFSampler (stratified in training mode, `train()`); `step_cb` / `update_sched` gate the
+    proposal networks' gradients.  Every step is one of the library's stage kernels; the fused `b200nerf_nff_render_fwd`
+    does the same work (eval mode) without materialising any of these tensors."""
 
     def __init__(self, num_proposal_samples_per_ray: Tuple[int, ...] = (64,), num_nerf_samples_per_ray: int = 32,
                  num_proposal_network_iterations: int = 2, single_jitter: bool = False, update_sched=lambda x: 1,
