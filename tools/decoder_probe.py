@@ -4,12 +4,12 @@ import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from neurad_studio_b200.backend import B200Backend
-from oracle import decoder_oracle as D
+from neurad_studio_b200 import scene
 
 B, H, W = (int(v) for v in (sys.argv[1:4] if len(sys.argv) > 3 else (6, 360, 640)))
 reps = int(sys.argv[4]) if len(sys.argv) > 4 else 3
 be = B200Backend(torch.device("cuda", 0))
-be.set_rgb_decoder(D.random_decoder_params(seed=1))
+be.set_rgb_decoder(scene.make_rgb_decoder_params(seed=1))
 feats = torch.randn(B, H, W, 48, device="cuda") * 0.7
 for impl in os.environ.get("DEC_IMPLS", "tc,tc_ldgsts,ref").split(","):
     out = be.rgb_decode(feats, impl)

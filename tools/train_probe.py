@@ -1,8 +1,9 @@
 """Device-side timing of one TRAINING step of the NFF path (development aid, not the bench):
 NeuRAD's train batch (40 960 camera + 16 384 lidar rays, datamanagers/ad_datamanager.py:38-41) through the module walk
 with the hand-written backward operators, the two regularisers, loss.backward().  Prints one JSON line with the
-per-phase CUDA-event times (forward, losses, backward) and rays/s; `--cpu-reference N` also times torch autograd through
-the oracle (the reference's torch-mode step) on N rays of the same batch on the host cores.
+per-phase CUDA-event times (forward + losses, backward) and rays/s.  (The CPU reference of a training step -- torch
+autograd through the oracle -- belongs to bench.py's cpu_baseline leg once a training metric is benched: only tests/,
+smoke() and that leg may execute oracle/.)
 
   python tools/train_probe.py [--cam-rays 40960] [--lidar-rays 16384] [--actors 0] [--steps 5] [--small-tables]
   ncu --set full --clock-control none -k regex:neurad_encoding_bwd -c 2 python tools/train_probe.py --steps 1
@@ -13,7 +14,6 @@ import argparse
 import json
 import os
 import sys
-import time
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch  # noqa: E402
@@ -55,7 +55,6 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=2)
     ap.add_argument("--small-tables", action="store_true", help="2^14 / 2^13 slot tables instead of NeuRAD's 2^22 / 2^20")
-    ap.add_argument("--cpu-reference", type=int, default=0, help="also time the oracle's autograd step on this many rays")
     a = ap.parse_args()
     dev = "cuda"
     cfg = nsb.small_config(n_actors=a.actors, log2_main=14, log2_prop=13) if a.small_tables else nsb.NeuRADConfig(n_actors=a.actors)
@@ -91,22 +90,6 @@ def main():
     res = {"what": "NFF training step (module walk + hand-written backward operators), device time", "rays": n,
            "cam_rays": a.cam_rays, "lidar_rays": a.lidar_rays, "actors": a.actors, "tables": "small" if a.small_tables else "neurad-default",
            "ms": med, "ms_total": total, "rays_per_s": n / total * 1e3, "loss": float(loss.detach())}
-    if a.cpu_reference:
-        from oracle import neurad_oracle as O
-        from oracle.convert import to_oracle_cfg
-
-        m = a.cpu_reference
-        p = {k: v.clone() for k, v in params.items()}
-        for k, v in p.items():
-            if v.dtype.is_floating_point and not k.startswith("dynamic_actors.") and not k.endswith("scalings") and k != "static_scale":
-                v.requires_grad_(True)
-        t0 = time.perf_counter()
-        o = O.nff_outputs(p, to_oracle_cfg(cfg), rays["origins"][:m], rays["directions"][:m], rays["pixel_area"][:m].reshape(-1, 1),
-                          rays["times"][:m].reshape(-1, 1), rays["sensor_idx"][:m].reshape(-1, 1), rays["is_lidar"][:m].reshape(-1, 1))
-        (o["features"].pow(2).mean() + 0.01 * o["depth"].abs().mean()).backward()
-        dt = time.perf_counter() - t0
-        res["cpu_reference"] = {"rays": m, "seconds": dt, "rays_per_s": m / dt, "threads": torch.get_num_threads(),
-                                "what": "torch autograd through the oracle (reference torch-mode step) on the host cores"}
     print(json.dumps(res))
 
 
