@@ -20,7 +20,15 @@ Third-party arithmetic that is NOT in the reference tree and is therefore restat
 definition (nerfacc==0.5.2, ``pyproject.toml:36``):
   * ``nerfacc.render_weight_from_alpha`` (call site neurad.py:717): w_i = alpha_i * prod_{j<i}(1 - alpha_j)
   * ``nerfacc.accumulate_along_rays``    (call site neurad.py:734): sum_i w_i * v_i over the sample axis
-The reference's CPU debugging branch that returns constant 0.5 weights (neurad.py:713-715) is bypassed.
+These two are PARITY UNPINNED: nerfacc cannot be installed here (no network) and neither the reference's tests nor its
+tree hold a vector for them, so they follow nerfacc's documented dense-tensor semantics; the in-tree twins of the same
+formulas (cameras/rays.py:188-210, model_components/renderers.py:85,412) agree with them.  Everything else in this file is
+pinned against the reference run.  The reference's CPU debugging branch that returns constant 0.5 weights
+(neurad.py:713-715) is bypassed.
+
+Backward pass: torch autograd through these functions is pinned against the reference's own autograd
+(oracle/make_golden_grads.py -> tests/golden/grads_*.npz); the backward of ``render_weight_from_alpha`` is therefore
+autograd of the cumprod restatement above, not nerfacc's CUDA backward (unpinned for the same reason).
 """
 from __future__ import annotations
 
