@@ -64,3 +64,33 @@ def test_get_outputs_and_decode_features_glue():
 
 def test_train_mode_encoding_glue():
     C.train_mode_encoding_matches_reference_golden("cpu")
+
+
+def test_train_probe_step_glue():
+    """tools/train_probe.py's training step (module walk, both regularisers, carving terms, backward) over the fake
+    backend: keeps the round-2 measurement script from rotting."""
+    import os
+    import sys
+
+    import torch
+
+    import neurad_studio_b200 as nsb
+    from neurad_studio_b200 import scene
+    from neurad_studio_b200.nerfstudio_api import NeuRADModel
+
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
+    import train_probe as T
+
+    cfg = nsb.small_config(n_actors=2, log2_main=10, log2_prop=10)
+    trajs = scene.make_trajectories(2, cfg.duration)
+    model = NeuRADModel(cfg, trajs)
+    model.load_reference_state_dict(scene.make_params(cfg, seed=1, beta=3.0, sdf_bias=0.6, trajectories=trajs))
+    model.requires_grad_(True)
+    model.train()
+    rays, rb = T.make_batch(cfg, 40, 24, trajs, "cpu")
+    with torch.no_grad():
+        ref = model.get_nff_outputs(rb, fused=True)
+    out, loss = T.step(model, rb, {"features": ref["features"] + 0.1, "depth": ref["depth"] * 1.1})
+    loss.backward()
+    assert torch.isfinite(loss) and model._param("field.mlp_geo.layers.0.weight").grad.abs().max().item() > 0
+    assert model._param("proposal_fields.1.density_decoder.weight").grad.abs().max().item() > 0
