@@ -301,6 +301,12 @@ int b200nerf_field_heads_bwd(b200nerf_ctx* ctx, const float* geo_out, const floa
 int b200nerf_linear_wgrad(b200nerf_ctx* ctx, const float* x, const float* dy, int64_t n_rows, int in_dim, int out_dim,
                           int relu_x, float* dweight, float* dbias, void* stream);
 int b200nerf_relu_bwd(b200nerf_ctx* ctx, const float* z, float* dz, int64_t n, void* stream);
+/* EXPERIMENTAL twin of b200nerf_linear_wgrad on the tcgen05 tensor cores (split-K GEMM, output rows in the TMEM lanes,
+ * 48 input rows per MMA chunk, 3xTF32): same arguments and semantics.  Written after the round's GPU budget was spent; the
+ * CUDA-core operator stays the default until this one has been validated and timed on a B200 (a tensor-core barrier
+ * time-out raises the b200nerf_check_status flag instead of hanging). */
+int b200nerf_linear_wgrad_tc(b200nerf_ctx* ctx, const float* x, const float* dy, int64_t n_rows, int in_dim, int out_dim,
+                             int relu_x, float* dweight, float* dbias, void* stream);
 
 /* NeuRAD's per-ray training regularisers (models/neurad.py:262,524,541-545) on the `weights_list` / `ray_samples_list`
  * of get_nff_outputs; spacing-domain edges ("sdist", losses.py:119-125) and weights as [N,S+1] / [N,S].  Per-ray losses

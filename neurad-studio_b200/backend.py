@@ -5,6 +5,7 @@ is in libb200nerf.so.  There is no CPU path: constructing a `B200Backend` withou
 from __future__ import annotations
 
 import ctypes
+import os
 from typing import Dict, Optional, Sequence, Tuple
 
 import torch
@@ -510,11 +511,16 @@ class B200Backend:
                                                       _ptr(f(dx2, p, gdim + 16)), p, gdim, self._beta, _ptr(dgeo), _ptr(dbeta), self._stream))
         return dgeo, dbeta
 
-    def linear_wgrad(self, x: torch.Tensor, dy: torch.Tensor, relu_x: bool, dweight: torch.Tensor, dbias: Optional[torch.Tensor]) -> None:
-        """dweight [out,in] += dY^T act(X); dbias [out] += sum dY (act = ReLU when X is a hidden pre-activation)."""
+    def linear_wgrad(self, x: torch.Tensor, dy: torch.Tensor, relu_x: bool, dweight: torch.Tensor, dbias: Optional[torch.Tensor],
+                     impl: Optional[str] = None) -> None:
+        """dweight [out,in] += dY^T act(X); dbias [out] += sum dY (act = ReLU when X is a hidden pre-activation).
+        impl "cuda" (default: CUDA cores, GPU-validated) or "tc" (experimental tcgen05 split-K twin; also selected by the
+        environment variable B200NERF_WGRAD=tc)."""
         xs, ds = self._dev(x), self._dev(dy)
-        self._check(self.lib.b200nerf_linear_wgrad(self._h, _ptr(xs), _ptr(ds), xs.shape[0], xs.shape[1], ds.shape[1], int(relu_x),
-                                                   _ptr(dweight), _ptr(dbias), self._stream))
+        impl = impl or os.environ.get("B200NERF_WGRAD", "cuda")
+        fn = {"cuda": self.lib.b200nerf_linear_wgrad, "tc": self.lib.b200nerf_linear_wgrad_tc}[impl]
+        self._check(fn(self._h, _ptr(xs), _ptr(ds), xs.shape[0], xs.shape[1], ds.shape[1], int(relu_x), _ptr(dweight), _ptr(dbias),
+                       self._stream))
 
     def relu_bwd(self, z: torch.Tensor, dz: torch.Tensor) -> torch.Tensor:
         """dz *= (z > 0), in place."""

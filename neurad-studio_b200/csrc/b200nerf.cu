@@ -1580,6 +1580,21 @@ int b200nerf_zipnerf_interlevel_loss(b200nerf_ctx* c, const float* sdist, const 
   return 0;
 }
 
+int b200nerf_linear_wgrad_tc(b200nerf_ctx* c, const float* x, const float* dy, int64_t n_rows, int in_dim, int out_dim,
+                             int relu_x, float* dweight, float* dbias, void* stream) {
+  REQUIRE(c, "ctx is NULL");
+  REQUIRE(n_rows >= 0, "bad shape");
+  REQUIRE(in_dim >= 1 && in_dim <= 64 && out_dim >= 1 && out_dim <= 64, "layer widths must be <= 64");
+  if (n_rows == 0) return 0;
+  REQUIRE(x && dy && dweight, "NULL argument");
+  DeviceGuard g(c->device);
+  const int64_t chunks = (n_rows + kWgTcRows - 1) / kWgTcRows;
+  const int grid = (int)(chunks < (int64_t)c->sm_count ? chunks : (int64_t)c->sm_count);
+  linear_wgrad_tc_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(x, dy, n_rows, in_dim, out_dim, relu_x, dweight, dbias, c->d_status);
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
 int b200nerf_lidar_carving_mask(b200nerf_ctx* c, const float* bins_e, const uint8_t* is_lidar, const float* directions_norm,
                                 const uint8_t* did_return, float carving_epsilon, float non_return_distance, int64_t n_rays,
                                 int n_samples, uint8_t* mask, void* stream) {

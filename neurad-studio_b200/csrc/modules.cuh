@@ -341,4 +341,113 @@ __global__ void lidar_carving_mask_kernel(const float* __restrict__ bins_e, cons
   mask[i] = m;
 }
 
+// ---------------------------------------------------------------------------------- weight gradient on tcgen05
+// dW[o][i] += sum_r dY[r][o] * act(X[r][i]) as a split-K GEMM on the tensor cores, built from the pieces of
+// mlp_tc_kernel (tc_mlp.cuh): the 128 TMEM lanes are the OUTPUT rows o (lanes >= N hold zeros), a chunk of 48 input
+// rows r is the K dimension.  Per chunk, thread o gathers its column dY[r0..r0+48)[o] (coalesced across threads for a
+// fixed r) into A (TMEM, hi/lo TF32 split), the CTA stages X^T for the chunk as the B tile (shared memory, K-major
+// no-swizzle layout, hi/lo), and one elected lane issues 6 k-steps x 3 MMAs that ACCUMULATE into the same TMEM columns
+// across all chunks of the CTA.  At the end every thread reads its row of D and adds it to global dW (one atomic per
+// output and CTA).  EXPERIMENTAL: written after the round's GPU budget was spent; b200nerf_linear_wgrad (CUDA cores) stays
+// the default until this variant has been validated and timed on a B200.
+constexpr int kWgTcRows = 48;  // rows per chunk = K of the chunk's MMAs (TileCols K_MAX)
+__device__ __forceinline__ void wg_stage_xt(float* hi, float* lo, const float* __restrict__ x, int64_t r0, int64_t n_rows, int K, int n_pad,
+                                            bool relu_x, int tid, int nthreads) {
+  // B(n = i, k = r) = act(X[r0 + r][i]); i runs fastest so that the global reads are contiguous
+  for (int e = tid; e < n_pad * kWgTcRows; e += nthreads) {
+    const int r = e / n_pad, i = e - r * n_pad;
+    float v = (i < K && r0 + r < n_rows) ? x[(r0 + r) * K + i] : 0.0f;
+    if (relu_x) v = fmaxf(v, 0.0f);
+    const float h = tc::tf32_hi(v);
+    const uint32_t off = tc::b_elem_offset(i, r, kWgTcRows);
+    hi[off] = h;
+    lo[off] = v - h;
+  }
+}
+// tc::issue_layer with a caller-chosen accumulate flag for the first k-step (chunks after the first keep adding to D)
+template <int K_MAX>
+__device__ __forceinline__ void wg_issue_chunk(uint32_t tmem_base, int d_col, const float* b_hi, const float* b_lo, int n_pad,
+                                               uint32_t accumulate_first, uint64_t* bar) {
+  const uint32_t leader = tc::elect_one();
+  const uint32_t idesc = tc::idesc_tf32(128, n_pad);
+  const uint32_t h32 = ((tc::smem_u32(b_hi) & 0x3ffffu) >> 4) | ((128u >> 4) << 16);
+  const uint32_t l32 = ((tc::smem_u32(b_lo) & 0x3ffffu) >> 4) | ((128u >> 4) << 16);
+  const uint32_t hi32 = (uint32_t)(((kWgTcRows >> 2) * 128) >> 4) | (1u << 14);
+  const uint32_t d = tmem_base + (uint32_t)d_col;
+  for (int ks = 0; ks < kWgTcRows / 8; ++ks) {
+    const uint32_t adv = (uint32_t)(ks * 2 * 128) >> 4;
+    const uint32_t a_hi = tmem_base + (uint32_t)(ks * 8), a_lo = tmem_base + (uint32_t)(K_MAX + ks * 8);
+    const uint64_t dh = ((uint64_t)hi32 << 32) | (h32 + adv), dl = ((uint64_t)hi32 << 32) | (l32 + adv);
+    if (leader) {
+      tc::mma_tf32_ts(d, a_hi, dh, idesc, ks != 0 ? 1u : accumulate_first);
+      tc::mma_tf32_ts(d, a_lo, dh, idesc, 1);
+      tc::mma_tf32_ts(d, a_hi, dl, idesc, 1);
+    }
+  }
+  if (leader) tc::mma_commit(bar);
+  __syncwarp();
+}
+__global__ void __launch_bounds__(128) linear_wgrad_tc_kernel(const float* __restrict__ x, const float* __restrict__ dy, int64_t n_rows,
+                                                              int K, int N, int relu_x, float* __restrict__ dW, float* __restrict__ db,
+                                                              int* __restrict__ status) {
+  using Cols = tc::TileCols<kWgTcRows, 64>;
+  __shared__ __align__(128) float b_tile[2 * 64 * kWgTcRows];  // hi | lo, 24 KB
+  __shared__ uint32_t tmem_base_s;
+  __shared__ __align__(8) uint64_t bar;
+  const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
+  const int n_pad = (K + 15) / 16 * 16;  // the MMA's N = input width of the layer
+  float* b_hi = b_tile;
+  float* b_lo = b_tile + n_pad * kWgTcRows;
+  if (warp == 0) tc::tmem_alloc(&tmem_base_s, 256);
+  if (tid == 0) tc::mbar_init(&bar, 1);
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, tmem_base_s, 0);
+  const uint32_t lane_base = tmem_base + ((uint32_t)(32 * (warp & 3)) << 16);
+  uint32_t parity = 0, acc = 0;
+  float bacc = 0.f;
+  const int64_t n_chunks = (n_rows + kWgTcRows - 1) / kWgTcRows;
+  for (int64_t ch = blockIdx.x; ch < n_chunks; ch += gridDim.x) {
+    const int64_t r0 = ch * kWgTcRows;
+    float v[kWgTcRows];
+#pragma unroll
+    for (int r = 0; r < kWgTcRows; ++r) {
+      v[r] = (tid < N && r0 + r < n_rows) ? dy[(r0 + r) * N + tid] : 0.f;
+      bacc += v[r];
+    }
+    tc::store_a<kWgTcRows>(lane_base, 0, v, kWgTcRows);
+    wg_stage_xt(b_hi, b_lo, x, r0, n_rows, K, n_pad, relu_x != 0, tid, 128);
+    tc::fence_async_smem();
+    tc::wait_st();
+    tc::fence_before_sync();
+    __syncthreads();
+    if (warp == 0) {
+      tc::fence_after_sync();
+      wg_issue_chunk<kWgTcRows>(tmem_base, Cols::d, b_hi, b_lo, n_pad, acc, &bar);
+    }
+    if (!tc::mbar_wait(&bar, parity)) atomicExch(status, 1);  // A (TMEM) and the B tile may be overwritten after this
+    parity ^= 1u;
+    acc = 1u;
+    tc::fence_after_sync();
+  }
+  if (acc) {  // this CTA contributed: drain its accumulator
+    uint32_t d[64];
+    tc::tmem_ld16(lane_base + Cols::d, d);
+    if (n_pad > 16) tc::tmem_ld16(lane_base + Cols::d + 16, d + 16);
+    if (n_pad > 32) tc::tmem_ld16(lane_base + Cols::d + 32, d + 32);
+    if (n_pad > 48) tc::tmem_ld16(lane_base + Cols::d + 48, d + 48);
+    tc::wait_ld();
+    if (tid < N) {
+#pragma unroll
+      for (int i = 0; i < 64; ++i)
+        if (i < K) atomicAdd(dW + tid * K + i, __uint_as_float(d[i]));
+      if (db) atomicAdd(db + tid, bacc);
+    }
+  }
+  tc::fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tc::tmem_dealloc(tmem_base, 256);
+}
+
 }  // namespace nff
