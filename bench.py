@@ -12,6 +12,10 @@ reference: rays / time between device synchronisations (nerfstudio/pipelines/ad_
 N > 1 is launched by torchrun, one rank per GPU.  Rays shard with no data-path collective (every rank renders
 its own time step = weak scaling); the only communication is the per-step NCCL all-gather of the per-ray
 outputs, into which the kernel's epilogue writes directly.
+
+Beside the headline keys the N = 1 line carries two secondary figures: "with_rgb_decoder" (the step followed by the
+camera rgb decoder) and "train_step" (one NFF training step through the hand-written backward operators,
+SURVEY 8f f2, measured by tools/train_probe.py in a child process once every headline measurement is done).
 """
 from __future__ import annotations
 
@@ -270,6 +274,27 @@ def oracle_rays_per_sec(cfg, n_sample: int, repeats: int = 1, _threads_fixed: bo
 _SAVED_STDOUT = None
 
 
+def train_step_probe(timeout_s: float = 240.0) -> dict:
+    """Secondary figure for SURVEY 8(f) row f2: one NFF TRAINING step (NeuRAD's 40 960 camera + 16 384 lidar ray batch
+    through the module walk, both regularisers, loss.backward() through the hand-written backward operators), timed
+    with CUDA events by tools/train_probe.py in a CHILD process after every headline measurement is finished -- a
+    failure, crash or time-out of that young code path can only turn this entry into {"error": ...}, never the line."""
+    import subprocess
+
+    cmd = [sys.executable, os.path.join(ROOT, "tools", "train_probe.py"), "--steps", "5", "--warmup", "2"]
+    try:
+        res = subprocess.run(cmd, cwd=ROOT, capture_output=True, text=True, timeout=timeout_s)
+        lines = [ln for ln in res.stdout.splitlines() if ln.startswith("{")]
+        if res.returncode != 0 or not lines:
+            tail = (res.stderr or res.stdout).strip().splitlines()[-3:]
+            return {"error": f"tools/train_probe.py rc={res.returncode}: " + " | ".join(tail)[:400]}
+        out = json.loads(lines[-1])
+        out["note"] = "secondary figure (not the headline metric); measured in a child process after the timed arms"
+        return out
+    except Exception as e:  # time-out, missing file, malformed output ...
+        return {"error": f"{type(e).__name__}: {e}"[:400]}
+
+
 def _emit(line: dict):
     sys.stdout.flush()
     if _SAVED_STDOUT is not None:
@@ -285,6 +310,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--cpu-sample", type=int, default=16384)
     ap.add_argument("--no-decoder", action="store_true", help="skip the extra 'with_rgb_decoder' measurement (N = 1)")
+    ap.add_argument("--no-train", action="store_true", help="skip the extra 'train_step' measurement (N = 1, child process)")
     ap.add_argument("--gather", default="p2p", choices=["p2p", "nccl"],
                     help="N>1: p2p = render epilogue stores rows into every peer's buffer over NVLink (default); "
                          "nccl = all_gather_into_tensor after the render")
@@ -446,6 +472,10 @@ def main():
         line["roofline"]["traffic"] = json.load(open(traffic_file)).get("dram_bytes_per_launch")
     if dec_line is not None:
         line["with_rgb_decoder"] = dec_line
+    if world == 1 and not args.no_train:
+        torch.cuda.synchronize()
+        torch.cuda.empty_cache()  # the child process needs ~3 GB of its own
+        line["train_step"] = train_step_probe()
     if world == 1 and args.cpu_sample > 0:
         v, n, dt = oracle_rays_per_sec(cfg, args.cpu_sample)
         line["cpu_baseline"] = {"value": v, "unit": "rays/s", "cores": torch.get_num_threads(), "kind": "port",
