@@ -271,6 +271,18 @@ int b200nerf_neurad_encoding_bwd(b200nerf_ctx* ctx, int field, const float* mean
                                  const float* density, const float* ddensity, float* grad_static_table,
                                  float* const* grad_actor_tables_host, float* grad_decoder, void* stream);
 
+/* Gradient of a field's features with respect to the ACTOR TRAJECTORIES (DynamicActors.actor_positions [T,A,3] /
+ * actor_rotations_6d [T,A,6], optimize_trajectories model_components/dynamic_actors.py:37): for every sample inside an
+ * actor box, the position gradient of the actor-grid lookup chained through the box transform, rotation_6d_to_matrix,
+ * the keyframe interpolation and the keyframes' Gram-Schmidt (utils/poses.py:90-150, cameras/camera_utils.py:422-443).
+ * The reference does this for the main field only (require_actor_grad, fields/neurad_field.py:50,177); the box-frame
+ * directions carry no gradient in torch mode (SHEncoding.pytorch_fwd is no_grad, field_components/encodings.py:797).
+ * `rotations_6d` / `positions` are the raw parameters; grad_* are accumulated (+=). */
+int b200nerf_neurad_encoding_pose_bwd(b200nerf_ctx* ctx, int field, const float* mean, const float* std, const float* times,
+                                      const float* flip, int64_t n_rays, int n_samples, const float* dfeatures,
+                                      const float* rotations_6d, const float* positions, float* grad_rotations_6d,
+                                      float* grad_positions, void* stream);
+
 /* nerfacc.render_weight_from_alpha backward (call site models/neurad.py:717): alphas, dweights [N,S] -> dalphas. */
 int b200nerf_alpha_to_weights_bwd(b200nerf_ctx* ctx, const float* alphas, const float* dweights, int64_t n_rays, int s,
                                   float* dalphas, void* stream);

@@ -4,9 +4,10 @@ mirror (NeuRADField / NeuRADProposalField / RaySamples.get_weights / renderers, 
 the hash tables, density decoders, MLPs and beta without any torch reference math in between.
 
 The reference gets these gradients from torch autograd (implementation="torch") or tiny-cuda-nn's backward kernels
-(field_components/encodings.py:386-404, mlp.py:116-140).  Sample positions carry no gradient: PDFSampler detaches its
-bins (ray_samplers.py:363-364), NeuRADHashEncoding computes the actor split under no_grad (neurad_encoding.py:166-168),
-and pose / camera optimisation is outside this row."""
+(field_components/encodings.py:386-404, mlp.py:116-140).  Sample positions carry no gradient (PDFSampler detaches its
+bins, ray_samplers.py:363-364); the actor trajectories do, through the main field's box-frame positions
+(require_actor_grad, neurad_encoding.py:174; EncodingFn); the box-frame directions do not (torch-mode SHEncoding is
+no_grad, encodings.py:797-800); camera optimisation is off in NeuRAD's config."""
 from __future__ import annotations
 
 from typing import List, Optional
@@ -17,14 +18,16 @@ from torch.autograd import Function
 
 
 class EncodingFn(Function):
-    """NeuRADHashEncoding.forward: (features [N*S,D], directions [N,S,3]); gradients go to the hash tables."""
+    """NeuRADHashEncoding.forward: (features [N*S,D], directions [N,S,3]); gradients go to the hash tables and -- for a
+    field built with require_actor_grad (the main field, fields/neurad_field.py:50) -- to the actor trajectories
+    `actor_rotations_6d` [T,A,6] / `actor_positions` [T,A,3] (pass None for a field without trajectory gradients)."""
 
     @staticmethod
-    def forward(ctx, be, field: int, mean, std, times, directions, flip, static_table, *actor_tables):
+    def forward(ctx, be, field: int, mean, std, times, directions, flip, rotations_6d, positions, static_table, *actor_tables):
         out = be.neurad_encoding(field, mean, std, times, directions, flip=flip)
         ctx.be, ctx.field = be, field
         ctx.table_shapes = [static_table.shape] + [t.shape for t in actor_tables]
-        ctx.save_for_backward(mean, std, times, flip)
+        ctx.save_for_backward(mean, std, times, flip, rotations_6d, positions)
         dirs = out.get("directions")
         if dirs is None:
             dirs = mean.new_zeros(0)
@@ -33,14 +36,19 @@ class EncodingFn(Function):
 
     @staticmethod
     def backward(ctx, dfeatures, _ddirs):
-        mean, std, times, flip = ctx.saved_tensors
-        needs = ctx.needs_input_grad[7:]
+        mean, std, times, flip, rot6, pos = ctx.saved_tensors
+        needs = ctx.needs_input_grad[9:]
         shapes, dev = ctx.table_shapes, dfeatures.device
+        dfeatures = dfeatures.contiguous()
         g_static = torch.zeros(shapes[0], device=dev) if needs[0] else None
         g_actors: List[Optional[Tensor]] = [torch.zeros(shapes[1 + a], device=dev) if nd else None for a, nd in enumerate(needs[1:])]
-        ctx.be.neurad_encoding_bwd(ctx.field, mean, std, times, {"static": g_static, "actors": g_actors},
-                                   dfeatures=dfeatures.contiguous(), flip=flip)
-        return (None,) * 7 + (g_static, *g_actors)
+        if g_static is not None or any(g is not None for g in g_actors):
+            ctx.be.neurad_encoding_bwd(ctx.field, mean, std, times, {"static": g_static, "actors": g_actors}, dfeatures=dfeatures, flip=flip)
+        g_rot = g_pos = None
+        if rot6 is not None and pos is not None and (ctx.needs_input_grad[7] or ctx.needs_input_grad[8]):
+            g_rot, g_pos = torch.zeros_like(rot6), torch.zeros_like(pos)
+            ctx.be.neurad_encoding_pose_bwd(ctx.field, mean, std, times, dfeatures, rot6, pos, g_rot, g_pos, flip=flip)
+        return (None,) * 7 + (g_rot if ctx.needs_input_grad[7] else None, g_pos if ctx.needs_input_grad[8] else None, g_static, *g_actors)
 
 
 class DensityFn(Function):

@@ -468,6 +468,24 @@ class B200Backend:
         self._check(self.lib.b200nerf_neurad_encoding_bwd(self._h, field, _ptr(m), _ptr(sd), _ptr(t), _ptr(fl), n, s, _ptr(df), _ptr(de), _ptr(dd),
                                                           _ptr(grads.get("static")), arr, _ptr(grads.get("decoder")), self._stream))
 
+    def neurad_encoding_pose_bwd(self, field: int, mean: torch.Tensor, std: torch.Tensor, times: torch.Tensor, dfeatures: torch.Tensor,
+                                 rotations_6d: torch.Tensor, positions: torch.Tensor, grad_rotations_6d: torch.Tensor,
+                                 grad_positions: torch.Tensor, flip: Optional[torch.Tensor] = None) -> None:
+        """Accumulates dL/d(actor_rotations_6d [T,A,6], actor_positions [T,A,3]) of a field's features (the reference
+        does this for the main field only: require_actor_grad)."""
+        m = self._dev(mean)
+        n, s = m.shape[0], m.shape[1]
+        m = m.reshape(n, s, 3)
+        sd = self._dev(std).reshape(n, s)
+        t = self._dev(times.reshape(n, -1)[:, 0] if times.numel() != n else times.reshape(n))
+        fl = None if flip is None else self._dev(flip).reshape(n)
+        df = self._dev(dfeatures).reshape(n * s, -1)
+        r6, ps = self._dev(rotations_6d), self._dev(positions)
+        for g_ in (grad_rotations_6d, grad_positions):
+            assert g_.is_contiguous() and g_.dtype == torch.float32 and g_.device == self.device
+        self._check(self.lib.b200nerf_neurad_encoding_pose_bwd(self._h, field, _ptr(m), _ptr(sd), _ptr(t), _ptr(fl), n, s, _ptr(df), _ptr(r6),
+                                                               _ptr(ps), _ptr(grad_rotations_6d), _ptr(grad_positions), self._stream))
+
     def alpha_to_weights_bwd(self, alphas: torch.Tensor, dweights: torch.Tensor) -> torch.Tensor:
         a, dw = self._dev(alphas), self._dev(dweights)
         out = torch.empty_like(a)

@@ -1466,6 +1466,25 @@ int b200nerf_neurad_encoding_bwd(b200nerf_ctx* c, int field, const float* mean, 
   return 0;
 }
 
+int b200nerf_neurad_encoding_pose_bwd(b200nerf_ctx* c, int field, const float* mean, const float* std, const float* times,
+                                      const float* flip, int64_t n_rays, int n_samples, const float* dfeatures,
+                                      const float* rotations_6d, const float* positions, float* grad_rotations_6d,
+                                      float* grad_positions, void* stream) {
+  REQUIRE(c, "ctx is NULL");
+  REQUIRE(field >= 0 && field < 3, "field must be B200NERF_FIELD_MAIN / PROP0 / PROP1");
+  if (!c->have_field[field]) return fail(B200NERF_ERR_STATE, "b200nerf_set_field_grids was not called for this field");
+  REQUIRE(n_rays >= 0 && n_samples >= 1, "bad sample grid");
+  if (c->actors.n_actors > kModMaxActors) return fail(B200NERF_ERR_UNSUPPORTED, "more than 64 actors");
+  if (n_rays == 0 || c->actors.n_actors == 0) return 0;
+  REQUIRE(mean && std && times && dfeatures && rotations_6d && positions && grad_rotations_6d && grad_positions, "NULL argument");
+  DeviceGuard g(c->device);
+  PoseBwdArgs a{mean, std, times, flip, dfeatures, rotations_6d, positions, grad_rotations_6d, grad_positions, n_rays, n_samples};
+  const unsigned grid = (unsigned)((n_rays + kModWarps - 1) / kModWarps);
+  neurad_encoding_pose_bwd_kernel<<<grid, kModWarps * 32, 0, (cudaStream_t)stream>>>(c->fields[field], c->actors, a);
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
 int b200nerf_alpha_to_weights_bwd(b200nerf_ctx* c, const float* alphas, const float* dweights, int64_t n_rays, int s,
                                   float* dalphas, void* stream) {
   REQUIRE(c, "ctx is NULL");

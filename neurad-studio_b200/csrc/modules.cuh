@@ -450,4 +450,42 @@ __global__ void __launch_bounds__(128) linear_wgrad_tc_kernel(const float* __res
   if (warp == 0) tc::tmem_dealloc(tmem_base, 256);
 }
 
+// Gradient of the main field's features with respect to the actor trajectories (DynamicActors.actor_positions /
+// actor_rotations_6d; require_actor_grad, fields/neurad_field.py:50): a second walk over the samples that only does work
+// for the (few) samples inside an actor box -- position gradient of the actor grid lookup, then the pose chain
+// (nff_modules.h: neurad_encode_point_pose_bwd), accumulated with atomics into the two bracketing keyframes.
+struct PoseBwdArgs {
+  const float* mean;       // [N,S,3]
+  const float* std;        // [N,S]
+  const float* times;      // [N]
+  const float* flip;       // [N] or NULL
+  const float* dfeatures;  // [N*S, D]
+  const float* rot6;       // [T,A,6] raw parameters
+  const float* pos;        // [T,A,3]
+  float* grad_rot6;        // [T,A,6] accumulated
+  float* grad_pos;         // [T,A,3] accumulated
+  int64_t n_rays;
+  int32_t S;
+};
+__global__ void __launch_bounds__(kModWarps * 32) neurad_encoding_pose_bwd_kernel(const FieldGrids fg, const Actors A,
+                                                                                   const PoseBwdArgs a) {
+  __shared__ ActorFrame frames[kModWarps][kModMaxActors];
+  const int warp = threadIdx.x >> 5, ln = threadIdx.x & 31;
+  const int64_t ray = (int64_t)blockIdx.x * kModWarps + warp;
+  if (ray >= a.n_rays || A.n_actors == 0) return;
+  int left, right;
+  float frac;
+  keyframe_bracket(A, a.times[ray], left, right, frac);
+  for (int k = ln; k < A.n_actors; k += 32) actor_frame(A, k, left, right, frac, frames[warp][k]);
+  __syncwarp();
+  const int D = fg.stat.L * fg.stat.F;
+  const float flip = a.flip ? a.flip[ray] : 1.0f;
+  for (int s = ln; s < a.S; s += 32) {
+    const int64_t i = ray * a.S + s;
+    Gauss g = {a.mean[3 * i], a.mean[3 * i + 1], a.mean[3 * i + 2], a.std[i]};
+    neurad_encode_point_pose_bwd(fg, A, frames[warp], a.rot6, a.pos, left, right, frac, g, flip, a.dfeatures + i * D, a.grad_rot6,
+                                 a.grad_pos);
+  }
+}
+
 }  // namespace nff

@@ -233,6 +233,167 @@ NFF_D void density_weights_bwd_ray(const float* delta, const float* density, con
   }
 }
 
+// ------------------------------------------------------------------------------ gradients to the actor trajectories
+// The main field's grid is built with require_actor_grad (fields/neurad_field.py:50), so in the reference the box-frame
+// POSITIONS of actor samples carry a gradient back to DynamicActors.actor_positions / actor_rotations_6d
+// (optimize_trajectories, model_components/dynamic_actors.py:37).  The box-frame DIRECTIONS do not: in torch mode the SH
+// encoding runs under no_grad (field_components/encodings.py:797-800).
+//
+// d trilerp / d (ox, oy, oz) for one feature's 8 corner values (corner order of cell_rows()).
+NFF_D void trilerp_grad(const float f[8], const Cell& c, float g[3]) {
+  const float ox = c.ox, oy = c.oy, oz = c.oz, ix = 1.0f - ox, iy = 1.0f - oy, iz = 1.0f - oz;
+  const float f03 = f[0] * ox + f[3] * ix, f12 = f[1] * ox + f[2] * ix;
+  const float f56 = f[5] * ox + f[6] * ix, f47 = f[4] * ox + f[7] * ix;
+  g[0] = ((f[0] - f[3]) * oy + (f[1] - f[2]) * iy) * oz + ((f[4] - f[7]) * oy + (f[5] - f[6]) * iy) * iz;
+  g[1] = (f03 - f12) * oz + (f47 - f56) * iz;
+  g[2] = (f03 * oy + f12 * iy) - (f47 * oy + f56 * iy);
+}
+
+// dL/d(grid coordinate in [0,1]^3) of one contracted gaussian: sum_l res_l * level_weight_l * sum_f dfeat[l,f] *
+// d trilerp_f / d offset  (HashEncoding.pytorch_fwd: offset = x * res_l - floor(x * res_l), encodings.py:430-434).
+NFF_D void encode_levels_pos_grad(const float* NFF_RESTRICT table, const Grid& gr, const Gauss& g, const float* dfeat, float gu[3]) {
+  gu[0] = gu[1] = gu[2] = 0.0f;
+  for (int l = 0; l < gr.L; ++l) {
+    Cell c = grid_cell(g.x, g.y, g.z, gr.res[l]);
+    uint32_t r[8];
+    cell_rows(c, gr.mask, r);
+    const float* base = table + (size_t)l * gr.T * gr.F;
+    const float w = level_weight(gr.res[l], g.std) * gr.res[l];
+    for (int f = 0; f < gr.F; ++f) {
+      const float df = dfeat[l * gr.F + f];
+      if (df == 0.0f) continue;
+      float v[8], dt[3];
+      for (int k = 0; k < 8; ++k) v[k] = ldg(base + (size_t)r[k] * gr.F + f);
+      trilerp_grad(v, c, dt);
+      gu[0] = fmaf(df * w, dt[0], gu[0]);
+      gu[1] = fmaf(df * w, dt[1], gu[1]);
+      gu[2] = fmaf(df * w, dt[2], gu[2]);
+    }
+  }
+}
+
+NFF_D float dot3(const float a[3], const float b[3]) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; }
+// backward of y = x / max(|x|, 1e-12) (F.normalize): gx = (gy - y (y . gy)) / |x|
+NFF_D void normalize_bwd(const float x[3], const float gy[3], float gx[3]) {
+  const float n = fmaxf(sqrtf(dot3(x, x)), 1e-12f);
+  const float y[3] = {x[0] / n, x[1] / n, x[2] / n};
+  const float d = dot3(y, gy);
+  for (int i = 0; i < 3; ++i) gx[i] = (gy[i] - y[i] * d) / n;
+}
+// backward of the Gram-Schmidt pair  u1 = normalize(r1), u2 = normalize(r2 - (u1 . r2) u1)  (rotation_6d_to_matrix
+// cameras/camera_utils.py:438-441 and the per-keyframe orthogonalisation of interpolate_trajectories_6d, utils/poses.py:
+// 117-120): given dL/du1, dL/du2 -> dL/dr1, dL/dr2.
+NFF_D void gram_schmidt_bwd(const float r1[3], const float r2[3], const float gu1[3], const float gu2[3], float gr1[3], float gr2[3]) {
+  const float n1 = fmaxf(sqrtf(dot3(r1, r1)), 1e-12f);
+  const float u1[3] = {r1[0] / n1, r1[1] / n1, r1[2] / n1};
+  const float s = dot3(u1, r2);
+  const float c2[3] = {r2[0] - s * u1[0], r2[1] - s * u1[1], r2[2] - s * u1[2]};
+  float gc2[3];
+  normalize_bwd(c2, gu2, gc2);
+  const float t = dot3(gc2, u1);
+  float g1[3];
+  for (int i = 0; i < 3; ++i) {
+    gr2[i] = gc2[i] - t * u1[i];
+    g1[i] = gu1[i] - t * r2[i] - s * gc2[i];
+  }
+  normalize_bwd(r1, g1, gr1);
+}
+
+// Chain from dL/d(box-frame position) of ONE actor sample to the trajectory parameters of its actor:
+//   q = B^T (p - t),  B = rows (b1, b2, b3) = rotation_6d_to_matrix(lerp of the Gram-Schmidt'ed keyframes),  t = lerp of
+//   the keyframe positions  (dynamic_actors.py:251-262, utils/poses.py:90-150, 42-55).
+// rot6 / pos are the RAW parameters [T,A,6] / [T,A,3]; grad_rot6 / grad_pos are accumulated with atomics (two keyframes).
+NFF_D void actor_pose_bwd(const float* NFF_RESTRICT rot6, const float* NFF_RESTRICT pos, int n_actors, int a, int left, int right,
+                          float frac, const float p[3], const float gq[3], float* grad_rot6, float* grad_pos) {
+  // forward recompute: keyframe Gram-Schmidt, lerp, rotation_6d_to_matrix
+  float A1[2][3], A2[2][3], P[2][3];
+  const int kf[2] = {left, right};
+  for (int e = 0; e < 2; ++e) {
+    const float* r = rot6 + ((size_t)kf[e] * n_actors + a) * 6;
+    const float* t = pos + ((size_t)kf[e] * n_actors + a) * 3;
+    float r1[3] = {ldg(r), ldg(r + 1), ldg(r + 2)}, r2[3] = {ldg(r + 3), ldg(r + 4), ldg(r + 5)};
+    const float n1 = fmaxf(sqrtf(dot3(r1, r1)), 1e-12f);
+    for (int i = 0; i < 3; ++i) A1[e][i] = r1[i] / n1;
+    const float s = dot3(A1[e], r2);
+    float c2[3] = {r2[0] - s * A1[e][0], r2[1] - s * A1[e][1], r2[2] - s * A1[e][2]};
+    const float n2 = fmaxf(sqrtf(dot3(c2, c2)), 1e-12f);
+    for (int i = 0; i < 3; ++i) {
+      A2[e][i] = c2[i] / n2;
+      P[e][i] = ldg(t + i);
+    }
+  }
+  float a1[3], a2[3], tt[3];
+  for (int i = 0; i < 3; ++i) {
+    a1[i] = A1[0][i] + (A1[1][i] - A1[0][i]) * frac;
+    a2[i] = A2[0][i] + (A2[1][i] - A2[0][i]) * frac;
+    tt[i] = P[0][i] + (P[1][i] - P[0][i]) * frac;
+  }
+  const float m1 = fmaxf(sqrtf(dot3(a1, a1)), 1e-12f);
+  const float b1[3] = {a1[0] / m1, a1[1] / m1, a1[2] / m1};
+  const float s2 = dot3(b1, a2);
+  const float c2[3] = {a2[0] - s2 * b1[0], a2[1] - s2 * b1[1], a2[2] - s2 * b1[2]};
+  const float m2 = fmaxf(sqrtf(dot3(c2, c2)), 1e-12f);
+  const float b2[3] = {c2[0] / m2, c2[1] / m2, c2[2] / m2};
+  const float b3[3] = {b1[1] * b2[2] - b1[2] * b2[1], b1[2] * b2[0] - b1[0] * b2[2], b1[0] * b2[1] - b1[1] * b2[0]};
+  // q_i = sum_j b_j[i] v_j, v = p - t
+  const float v[3] = {p[0] - tt[0], p[1] - tt[1], p[2] - tt[2]};
+  float gt[3] = {-dot3(b1, gq), -dot3(b2, gq), -dot3(b3, gq)};
+  float gb1[3], gb2[3], gb3[3];
+  for (int i = 0; i < 3; ++i) {
+    gb1[i] = v[0] * gq[i];
+    gb2[i] = v[1] * gq[i];
+    gb3[i] = v[2] * gq[i];
+  }
+  // b3 = b1 x b2
+  gb1[0] += b2[1] * gb3[2] - b2[2] * gb3[1];
+  gb1[1] += b2[2] * gb3[0] - b2[0] * gb3[2];
+  gb1[2] += b2[0] * gb3[1] - b2[1] * gb3[0];
+  gb2[0] += gb3[1] * b1[2] - gb3[2] * b1[1];
+  gb2[1] += gb3[2] * b1[0] - gb3[0] * b1[2];
+  gb2[2] += gb3[0] * b1[1] - gb3[1] * b1[0];
+  float ga1[3], ga2[3];
+  gram_schmidt_bwd(a1, a2, gb1, gb2, ga1, ga2);
+  // lerp: left gets (1 - frac), right gets frac; then the keyframes' own Gram-Schmidt back to the raw 6-D parameters
+  for (int e = 0; e < 2; ++e) {
+    const float w = e == 0 ? 1.0f - frac : frac;
+    if (w == 0.0f) continue;
+    const float* r = rot6 + ((size_t)kf[e] * n_actors + a) * 6;
+    const float r1[3] = {ldg(r), ldg(r + 1), ldg(r + 2)}, r2[3] = {ldg(r + 3), ldg(r + 4), ldg(r + 5)};
+    const float gA1[3] = {w * ga1[0], w * ga1[1], w * ga1[2]}, gA2[3] = {w * ga2[0], w * ga2[1], w * ga2[2]};
+    float gr1[3], gr2[3];
+    gram_schmidt_bwd(r1, r2, gA1, gA2, gr1, gr2);
+    float* go = grad_rot6 + ((size_t)kf[e] * n_actors + a) * 6;
+    float* gp = grad_pos + ((size_t)kf[e] * n_actors + a) * 3;
+    for (int i = 0; i < 3; ++i) {
+      atomic_add(go + i, gr1[i]);
+      atomic_add(go + 3 + i, gr2[i]);
+      atomic_add(gp + i, w * gt[i]);
+    }
+  }
+}
+
+// Trajectory gradient of one sample of the main field (if it lies inside an actor): position gradient of the actor grid
+// lookup -> box frame (scene contraction is the identity inside the unit ball: |q| / actor_scale < 1 for every padded box)
+// -> actor_pose_bwd.  Returns the actor index or -1.
+NFF_D int neurad_encode_point_pose_bwd(const FieldGrids& fg, const Actors& A, const ActorFrame* frames, const float* rot6,
+                                       const float* pos, int left, int right, float frac, const Gauss& g, float flip,
+                                       const float* dfeat, float* grad_rot6, float* grad_pos) {
+  float pb[3];
+  const int a = A.n_actors > 0 ? actor_containing(frames, A.n_actors, g.x, g.y, g.z, pb) : -1;
+  if (a < 0) return a;
+  Gauss ga = {flip < 0.0f ? -pb[0] : pb[0], pb[1], pb[2], g.std};
+  const float inv = frcp(fg.actor_scale);
+  if (!(fmaxf(fmaxf(fabsf(ga.x), fabsf(ga.y)), fabsf(ga.z)) * inv < 1.0f)) return a;  // contracted region: never for a padded box
+  ga = contract(ga, fg.actor_scale);
+  float gu[3];
+  encode_levels_pos_grad(fg.actor_tables[a], fg.act, ga, dfeat, gu);
+  const float k = 0.25f * inv;  // u = (q / scale + 2) / 4
+  float gq[3] = {gu[0] * k * (flip < 0.0f ? -1.0f : 1.0f), gu[1] * k, gu[2] * k};
+  const float p[3] = {g.x, g.y, g.z};
+  actor_pose_bwd(rot6, pos, A.n_actors, a, left, right, frac, p, gq, grad_rot6, grad_pos);
+  return a;
+}
+
 // ------------------------------------------------------------------------------------------------ training losses
 // The two per-ray regularisers NeuRAD trains with (models/neurad.py:262,524,541-545), one thread per ray; both are
 // functions of the `weights_list` / `ray_samples_list` the module walk returns.

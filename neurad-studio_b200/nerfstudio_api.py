@@ -653,9 +653,11 @@ class NeuRADField:
         geo_wb = m._mlp_params("field.mlp_geo", 2)
         feat_wb = m._mlp_params("field.mlp_feature", 3)
         beta = m._param("field.sdf_to_density.beta")
-        if torch.is_grad_enabled() and any(t.requires_grad for t in tables + geo_wb + feat_wb + [beta]):
+        # the main field's grid has require_actor_grad (neurad_field.py:50): its features also train the trajectories
+        traj = [m._param("dynamic_actors.actor_rotations_6d"), m._param("dynamic_actors.actor_positions")] if m.config.n_actors else [None, None]
+        if torch.is_grad_enabled() and any(t.requires_grad for t in tables + geo_wb + feat_wb + [beta] + [t for t in traj if t is not None]):
             feats, dirs = AG.EncodingFn.apply(be, 0, g.mean, g.std, ray_samples.times, ray_samples.frustums.directions, flip,
-                                              tables[0], *tables[1:])
+                                              traj[0], traj[1], tables[0], *tables[1:])
             geo = AG.MlpFn.apply(be, feats, *geo_wb)
             h = AG.MlpFn.apply(be, AG.FieldMidFn.apply(be, geo, dirs), *feat_wb)
             feature, sdf, alpha = AG.FieldTailFn.apply(be, geo, h, beta)
@@ -737,7 +739,8 @@ class NeuRADModel(nn.Module):
                 continue
             name = k.replace(".", "__")
             self._names.append((name, k))
-            if v.dtype.is_floating_point and not k.startswith("dynamic_actors.") and not k.endswith("scalings"):
+            trainable = not k.startswith("dynamic_actors.") or k in ("dynamic_actors.actor_positions", "dynamic_actors.actor_rotations_6d")
+            if v.dtype.is_floating_point and trainable and not k.endswith("scalings"):  # optimize_trajectories (dynamic_actors.py:37)
                 self.register_parameter(name, nn.Parameter(v, requires_grad=False))
             else:
                 self.register_buffer(name, v)

@@ -43,8 +43,11 @@ def loss_weights(shapes, seed=7):
     return {k: torch.randn(shapes[k], generator=gen) * LOSS_SCALE[k] for k in OUT_KEYS}
 
 
+POSE_KEYS = ("dynamic_actors.actor_positions", "dynamic_actors.actor_rotations_6d")  # optimize_trajectories (dynamic_actors.py:37)
+
+
 def trainable_keys(params):
-    return [k for k, v in params.items() if v.dtype.is_floating_point and not k.startswith("dynamic_actors.")
+    return [k for k, v in params.items() if v.dtype.is_floating_point and (not k.startswith("dynamic_actors.") or k in POSE_KEYS)
             and not k.endswith("scalings") and k != "static_scale"]
 
 

@@ -415,6 +415,7 @@ def hashgrid_forward(
     directions: Optional[Tensor],
     trace: Optional[dict] = None,
     flip: Optional[Tensor] = None,
+    require_actor_grad: bool = True,
 ) -> Tuple[Tensor, Optional[Tensor]]:
     """neurad_encoding.py:150-223, 265-304.  mean [N,S,M,3], std [N,S,M,1], times [N,S,1], directions [N,S,3] or None.
     `flip` [N] (+1 / -1 per ray) is the training-mode random actor flip (:212-219, drawn with torch.bernoulli there);
@@ -434,23 +435,28 @@ def hashgrid_forward(
     if cfg.n_actors == 0:
         return features.view(-1, out_dim), directions
 
-    b2w, valid = boxes2world_at(params, times[:, 0].squeeze(-1))
-    w2b_all = pose_inverse(b2w)
-    bounds = params["dynamic_actors.actor_sizes"] / 2 + params["dynamic_actors.actor_padding"]
-    ray_idx, sample_idx, actor_idx = actor_indices(mean, b2w, valid, w2b_all, bounds)
-    w2b = w2b_all[ray_idx, actor_idx]
-    pos = transform_points_pairwise(mean[ray_idx, sample_idx], w2b.unsqueeze(-3))
-    if directions is not None:
-        directions = directions.clone()
-        dirs = transform_points_pairwise(directions[ray_idx, sample_idx], w2b, with_translation=False).squeeze(1)
-        dirs = dirs / (torch.linalg.norm(dirs, dim=-1, keepdim=True) + EPS)
-        directions[ray_idx, sample_idx] = dirs
-    if flip is not None:  # neurad_encoding.py:212-219
-        fl = torch.ones_like(pos[..., 0:1, :])
-        fl[..., 0] = flip[ray_idx].unsqueeze(-1)
-        pos = pos * fl
+    # neurad_encoding.py:174: the actor split runs under no_grad unless `require_actor_grad` (True for the main field's
+    # grid, fields/neurad_field.py:50; False for the proposal fields', :177) -- only then do the actor trajectories
+    # receive gradients through the box-frame positions and directions
+    with torch.enable_grad() if require_actor_grad else torch.no_grad():
+        b2w, valid = boxes2world_at(params, times[:, 0].squeeze(-1))
+        w2b_all = pose_inverse(b2w)
+        bounds = params["dynamic_actors.actor_sizes"] / 2 + params["dynamic_actors.actor_padding"]
+        with torch.no_grad():  # _get_actor_indices is decorated @torch.no_grad() (neurad_encoding.py:224)
+            ray_idx, sample_idx, actor_idx = actor_indices(mean, b2w, valid, w2b_all, bounds)
+        w2b = w2b_all[ray_idx, actor_idx]
+        pos = transform_points_pairwise(mean[ray_idx, sample_idx], w2b.unsqueeze(-3))
         if directions is not None:
-            directions[ray_idx, sample_idx, 0] = directions[ray_idx, sample_idx, 0] * fl[..., 0].squeeze(-1)
+            directions = directions.clone()
+            dirs = transform_points_pairwise(directions[ray_idx, sample_idx], w2b, with_translation=False).squeeze(1)
+            dirs = dirs / (torch.linalg.norm(dirs, dim=-1, keepdim=True) + EPS)
+            directions[ray_idx, sample_idx] = dirs
+        if flip is not None:  # neurad_encoding.py:212-219
+            fl = torch.ones_like(pos[..., 0:1, :])
+            fl[..., 0] = flip[ray_idx].unsqueeze(-1)
+            pos = pos * fl
+            if directions is not None:
+                directions[ray_idx, sample_idx, 0] = directions[ray_idx, sample_idx, 0] * fl[..., 0].squeeze(-1)
     if actor_idx.shape[0] == 0:
         return features.view(-1, out_dim), directions
     a_mean, a_std = scaled_contraction(pos, std[ray_idx, sample_idx], fcfg.actor_scale)
@@ -481,7 +487,7 @@ def proposal_density(params, k: int, cfg: NeuRADCfg, o, d, area, times, starts, 
     N, S = starts.shape
     mean, std = fast_isotropic_gaussian(o[:, None, :], d[:, None, :], area[:, None, None], starts[..., None], ends[..., None])
     t = times[:, None, None].expand(N, S, 1)
-    feats, _ = hashgrid_forward(params, f"proposal_fields.{k}", cfg.prop[k], cfg, mean, std, t, None, trace)
+    feats, _ = hashgrid_forward(params, f"proposal_fields.{k}", cfg.prop[k], cfg, mean, std, t, None, trace, require_actor_grad=False)
     dens = F.linear(feats, params[f"proposal_fields.{k}.density_decoder.weight"])
     return torch.exp(dens).view(N, S)
 
@@ -529,7 +535,9 @@ def main_field(params, cfg: NeuRADCfg, o, d, area, times, starts, ends, trace=No
     h = mlp_forward(params, "field.mlp_geo", 2, feats)
     geo_out, geo_embedding = torch.split(h, [1, cfg.nff_out_dim], dim=-1)
     sdf = geo_out.view(N, S, 1)
-    direction_embedding = sh_components_l4(((dirs + 1.0) / 2.0).reshape(-1, 3))  # base_field.py:136-142
+    with torch.no_grad():  # SHEncoding.pytorch_fwd is decorated @torch.no_grad() (encodings.py:797-800): in torch mode
+        # no gradient reaches the directions, hence none reaches the actor rotations through this path
+        direction_embedding = sh_components_l4(((dirs + 1.0) / 2.0).reshape(-1, 3))  # base_field.py:136-142
     feature = geo_embedding + mlp_forward(
         params, "field.mlp_feature", 3, torch.cat([geo_embedding, direction_embedding], dim=-1)
     )

@@ -52,6 +52,10 @@ class FakeBackend(B200Backend):
     def neurad_encoding_bwd(self, field, mean, std, times, grads, dfeatures=None, density=None, ddensity=None, flip=None):
         emul.encoding_bwd(self.cfg, self.params, O.pdf_u, field, mean, std, times, grads, dfeatures, density, ddensity, flip)
 
+    def neurad_encoding_pose_bwd(self, field, mean, std, times, dfeatures, rotations_6d, positions, grad_rotations_6d, grad_positions,
+                                 flip=None):
+        emul.encoding_pose_bwd(self.cfg, self.params, O.pdf_u, field, mean, std, times, dfeatures, grad_rotations_6d, grad_positions, flip)
+
     def alpha_to_weights_bwd(self, alphas, dweights):
         return emul.weights_bwd(True, alphas, None, dweights)
 

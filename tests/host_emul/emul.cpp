@@ -344,4 +344,40 @@ int emul_zipnerf_interlevel(const float* c, const float* w, int S, const float* 
                                      dwp ? dwp + r * Sp : nullptr);
   return 0;
 }
+
+// Trajectory gradients of the main field's features (nff_modules.h: neurad_encode_point_pose_bwd; loop structure of
+// neurad_encoding_pose_bwd_kernel).  extra = {mean, std, times, flip|NULL, dfeatures, rot6 [T,A,6], pos [T,A,3],
+// grad_rot6, grad_pos}
+int emul_encoding_pose_bwd(const void* const* ptrs, const int* ints, const float* floats, const void* const* extra, long long n_rays,
+                           int S, int field) {
+  Parsed Q;
+  parse_params(ptrs, ints, floats, Q);
+  const FieldGrids& fg = Q.P.fields[field];
+  const Actors& A = Q.P.actors;
+  if (A.n_actors == 0) return 0;
+  const float* mean = (const float*)extra[0];
+  const float* std_ = (const float*)extra[1];
+  const float* times = (const float*)extra[2];
+  const float* flips = (const float*)extra[3];
+  const float* dfeatures = (const float*)extra[4];
+  const float* rot6 = (const float*)extra[5];
+  const float* pos = (const float*)extra[6];
+  float* grad_rot6 = (float*)extra[7];
+  float* grad_pos = (float*)extra[8];
+  const int D = fg.stat.L * fg.stat.F;
+  std::vector<ActorFrame> frames(A.n_actors);
+  for (long long r = 0; r < n_rays; ++r) {
+    int left, right;
+    float frac;
+    keyframe_bracket(A, times[r], left, right, frac);
+    for (int a = 0; a < A.n_actors; ++a) actor_frame(A, a, left, right, frac, frames[a]);
+    const float flip = flips ? flips[r] : 1.0f;
+    for (int s = 0; s < S; ++s) {
+      const long long i = r * S + s;
+      Gauss g = {mean[3 * i], mean[3 * i + 1], mean[3 * i + 2], std_[i]};
+      neurad_encode_point_pose_bwd(fg, A, frames.data(), rot6, pos, left, right, frac, g, flip, dfeatures + i * D, grad_rot6, grad_pos);
+    }
+  }
+  return 0;
+}
 }

@@ -258,3 +258,28 @@ def zipnerf_interlevel(sdist, weights, prop_sdist, prop_weights, pulse_width, wa
                                      ctypes.c_float(pulse_width), ctypes.c_longlong(c.shape[0]), p(loss), p(dwp))
     assert rc == 0
     return loss, dwp
+
+
+def encoding_pose_bwd(cfg, params, pdf_u, field, mean, std, times, dfeatures, grad_rot6, grad_pos, flip=None):
+    """Trajectory gradients (csrc/nff_modules.h: neurad_encode_point_pose_bwd): accumulates dL/d(actor_rotations_6d,
+    actor_positions) into grad_rot6 [T,A,6] / grad_pos [T,A,3] (same contract as B200Backend.neurad_encoding_pose_bwd)."""
+    lib = ctypes.CDLL(build())
+    lib.emul_encoding_pose_bwd.restype = ctypes.c_int
+    pk = _Pack()
+    _pack_params(pk, cfg, params, pdf_u, (2, 2))
+    n, s = mean.shape[0], mean.shape[1]
+    ex = _Pack()
+    ex.P(mean.float().reshape(n, s, 3))
+    ex.P(std.float().reshape(n, s))
+    ex.P(times.float().reshape(n, -1)[:, 0])
+    ex.P(None if flip is None else flip.float().reshape(n))
+    ex.P(dfeatures.float().reshape(n * s, -1))
+    ex.P(params["dynamic_actors.actor_rotations_6d"].detach().float())
+    ex.P(params["dynamic_actors.actor_positions"].detach().float())
+    for t in (grad_rot6, grad_pos):
+        assert t.is_contiguous() and t.dtype == torch.float32
+        ex.ptrs.append(ctypes.c_void_p(t.data_ptr()))
+    c_ptrs, c_ints, c_floats = pk.c_arrays()
+    c_extra = (ctypes.c_void_p * len(ex.ptrs))(*ex.ptrs)
+    rc = lib.emul_encoding_pose_bwd(c_ptrs, c_ints, c_floats, c_extra, ctypes.c_longlong(n), ctypes.c_int(s), ctypes.c_int(field))
+    assert rc == 0

@@ -146,6 +146,14 @@ def load_golden_grads(name):
     return meta, g["grad"]
 
 
+# tests/golden/nff_actors.npz holds exactly one sample inside actor 4 (ray 26, sample 29), and that sample sits on a ReLU
+# kink of mlp_geo's first layer: one hidden pre-activation is -1.6e-6 in the reference.  A forward that differs by 1e-6
+# (sampler transcendental functions, 3xTF32) flips that unit, and the sample's gradient -- the only contribution to actor
+# 4's grid table and trajectory -- changes by ~25 %.  The reference's own gradient there is one side of a discontinuity,
+# not a target: actor 4's trajectory entries are left out of the comparison (its table is compared on the field's scale).
+KINK_ACTOR = 4
+
+
 def check_grads(got, want, min_checked=15):
     """got / want: {reference parameter name: gradient}.  Hash tables of one field (static + per-actor; one "hashgrids"
     parameter group, neurad_encoding.py:140-142) are compared on a common scale: a single occluded sample inside an actor
@@ -163,7 +171,10 @@ def check_grads(got, want, min_checked=15):
             continue
         assert gk is not None, k
         ref_scale = scale[k.split(".hashgrid.")[0]] if ".hashgrid." in k else w.abs().max().item()
-        err = (gk.detach().cpu().reshape(w.shape) - w).abs().max().item() / ref_scale
+        diff = (gk.detach().cpu().reshape(w.shape) - w).abs()
+        if k.startswith("dynamic_actors.") and w.shape[1] > KINK_ACTOR:  # [T,A,...]: see KINK_ACTOR
+            diff[:, KINK_ACTOR] = 0
+        err = diff.max().item() / ref_scale
         assert err < 2e-3, (k, err)
         checked += 1
     assert checked >= min_checked
@@ -185,7 +196,7 @@ def training_gradients_match_reference_golden(name, dev):
     sum((out[k] * G[k].to(dev)).sum() for k in OUT_KEYS).backward()
     sd = model.reference_state_dict()
     got = {k: v.grad for k, v in sd.items() if v.dtype.is_floating_point and v.grad is not None}
-    check_grads(got, want, min_checked=15 if meta["n_actors"] == 0 else 20)
+    check_grads(got, want, min_checked=15 if meta["n_actors"] == 0 else 22)  # incl. actor_positions / actor_rotations_6d
     with pytest.raises(RuntimeError):
         model.get_nff_outputs(rb, fused=True)  # the fused kernels are forward-only
     with torch.no_grad():

@@ -129,3 +129,38 @@ def test_training_losses_match_reference_golden():
         # away from a float64 evaluation, and so is this one (cumulative sums in double, like torch's CPU cumsum)
         assert rel_to_max(dwp * 3 / n, g["ref"][f"grad_{i}"]) < 5e-4, i
     assert abs(total - g["ref"]["interlevel"].item()) < 5e-4 * abs(g["ref"]["interlevel"].item())
+
+
+@pytest.mark.parametrize("with_flip", [False, True])
+def test_encoding_backward_to_actor_trajectories(with_flip):
+    """dL/d(actor_positions, actor_rotations_6d) of the main field's grid features (require_actor_grad): the device chain
+    (position gradient of the lookup -> box transform -> rotation_6d_to_matrix -> keyframe lerp -> keyframe Gram-Schmidt)
+    against torch autograd through the oracle's NeuRADHashEncoding restatement."""
+    meta, g = load_golden("nff_actors.npz")
+    cfg = cfg_from_meta(meta)
+    ocfg = to_oracle_cfg(cfg)
+    p, r, ref = dict(g["param"]), g["ray"], g["ref"]
+    n = r["origins"].shape[0]
+    starts, ends = ref["starts"].reshape(n, -1), ref["ends"].reshape(n, -1)
+    s = starts.shape[1]
+    lidar = r["is_lidar"].reshape(-1).bool()
+    area = r["pixel_area"].reshape(-1) * torch.where(lidar, 1.0, float(cfg.rgb_upsample_factor**2))
+    for k in ("dynamic_actors.actor_positions", "dynamic_actors.actor_rotations_6d"):
+        p[k] = p[k].clone().requires_grad_(True)
+    mean, std = O.fast_isotropic_gaussian(r["origins"][:, None, :], r["directions"][:, None, :], area[:, None, None],
+                                          starts[..., None], ends[..., None])
+    t = r["times"].reshape(n, 1, 1).expand(n, s, 1)
+    flip = None
+    if with_flip:
+        flip = torch.where(torch.arange(n) % 2 == 0, -1.0, 1.0)
+    feats, _ = O.hashgrid_forward(p, "field", ocfg.main, ocfg, mean, std, t, None, flip=flip)
+    G = torch.randn(feats.shape, generator=torch.Generator().manual_seed(4))
+    (feats * G).sum().backward()
+    want_pos, want_rot = p["dynamic_actors.actor_positions"].grad, p["dynamic_actors.actor_rotations_6d"].grad
+    assert want_pos.abs().max().item() > 0 and want_rot.abs().max().item() > 0
+    em_mean, em_std = emul.gaussian(r["origins"], r["directions"], area, torch.cat([starts, ends[:, -1:]], 1))
+    g_rot, g_pos = torch.zeros_like(want_rot), torch.zeros_like(want_pos)
+    q = {k: v.detach() for k, v in p.items()}
+    emul.encoding_pose_bwd(cfg, q, O.pdf_u, 0, em_mean, em_std, r["times"], G, g_rot, g_pos, flip=flip)
+    assert rel_to_max(g_pos, want_pos) < 2e-4, rel_to_max(g_pos, want_pos)
+    assert rel_to_max(g_rot, want_rot) < 2e-4, rel_to_max(g_rot, want_rot)

@@ -119,7 +119,8 @@ def test_oracle_autograd_matches_reference_gradients(name):
     cfg = cfg_from_meta(meta)
     n = gmeta["n_rays"]
     p = {k: v.clone() for k, v in g["param"].items()}
-    keys = [k for k, v in p.items() if v.dtype.is_floating_point and not k.startswith("dynamic_actors.")
+    pose = ("dynamic_actors.actor_positions", "dynamic_actors.actor_rotations_6d")  # optimize_trajectories (dynamic_actors.py:37)
+    keys = [k for k, v in p.items() if v.dtype.is_floating_point and (not k.startswith("dynamic_actors.") or k in pose)
             and not k.endswith("scalings") and k != "static_scale"]
     for k in keys:
         p[k].requires_grad_(True)
