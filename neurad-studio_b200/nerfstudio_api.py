@@ -687,7 +687,9 @@ class BasicBlock(nn.Module):
         self.final_activation = nn.ReLU(inplace=True)
 
     def forward(self, x: Tensor) -> Tensor:
-        raise RuntimeError("BasicBlock is evaluated by RGBDecoder.forward (fused tcgen05 convolutions)")
+        """cnns.py:45-46.  Only reached through RGBDecoder.forward(impl="torch") (training): the inference path evaluates
+        the whole decoder with the fused tcgen05 convolutions and never calls the blocks one by one."""
+        return self.final_activation(self.res_branch(x) + self.main_branch(x))
 
 
 class RGBDecoder(nn.Sequential):
@@ -707,10 +709,25 @@ class RGBDecoder(nn.Sequential):
             nn.Conv2d(hidden_dim, 3, kernel_size=1, padding=0), nn.Sigmoid())
         self._bound = None
 
-    @torch.no_grad()
     def forward(self, features: Tensor, impl: str = "tc") -> Tensor:
+        """impl "tc" / "tc_ldgsts" / "ref": the library's decoder kernels (inference: BatchNorm folded from its running
+        statistics).  impl "torch": the nn.Sequential itself on torch's convolution library, differentiable and with
+        BatchNorm batch statistics in training mode -- exactly what the reference runs (neurad.py:362-365).  It exists so
+        that a model can TRAIN end to end (the NFF path through this library's backward operators, the decoder through
+        torch) until the decoder has a native backward; it is never chosen implicitly."""
+        if impl == "torch":
+            x = features if features.dim() == 4 else features[None]
+            x = x.permute(0, 3, 1, 2)
+            for module in self:
+                x = module(x)
+            return x.permute(0, 2, 3, 1)
         if self.training:
-            raise RuntimeError("the b200 rgb decoder is inference-only (BatchNorm in eval mode); call .eval()")
+            raise RuntimeError("the b200 rgb decoder kernels are inference-only (BatchNorm in eval mode); call .eval(), "
+                               "or pass impl='torch' to train through torch's convolutions")
+        with torch.no_grad():
+            return self._forward_kernels(features, impl)
+
+    def _forward_kernels(self, features: Tensor, impl: str) -> Tensor:
         be = get_backend(features.device)
         sd = self.state_dict()
         ver = tuple(v._version for v in sd.values()) + (id(be),)
@@ -997,7 +1014,9 @@ class NeuRADModel(nn.Module):
         rgb = None
         if cam_features.numel() > 0:
             patches = cam_features.reshape(-1, *patch_size, cam_features.shape[-1])
-            rgb = self.rgb_decoder(patches)  # eval mode only: raises in training mode (BatchNorm batch statistics)
+            # inference: the tcgen05 decoder kernels.  Training (BatchNorm batch statistics + autograd): explicitly the torch
+            # modules, as the reference does -- the native decoder has no backward yet
+            rgb = self.rgb_decoder(patches, impl="torch" if (self.rgb_decoder.training and torch.is_grad_enabled()) else "tc")
         return rgb, intensity, ray_drop_logit
 
     def get_outputs(self, ray_bundle: RayBundle, patch_size: Tuple[int, int], intensity_for_cam: bool = False,

@@ -75,3 +75,24 @@ def test_fused_path_is_the_default_without_trainable_parameters(monkeypatch):
     model.requires_grad_(True)
     out = model.get_nff_outputs(rb)
     assert calls == ["fused"] and "weights_list" in out
+
+
+def test_rgb_decoder_torch_impl_matches_reference_golden_and_trains():
+    """RGBDecoder.forward(impl="torch"): the mirror's nn.Sequential itself (the reference's training path for the decoder,
+    models/neurad.py:362-365) reproduces the reference's eval output bit for bit and is differentiable."""
+    from neurad_studio_b200.nerfstudio_api import RGBDecoder
+
+    _, g = load_golden("rgb_decoder.npz")
+    dec = RGBDecoder(48, 32, 3)
+    dec.load_state_dict({k[len("rgb_decoder."):]: v for k, v in g["param"].items()}, strict=False)
+    dec.eval()
+    with torch.no_grad():
+        rgb = dec(g["in"]["features"], impl="torch")
+    assert torch.equal(rgb, g["ref"]["rgb"])
+    dec.train()
+    feats = g["in"]["features"].clone().requires_grad_(True)
+    with pytest.raises(RuntimeError):
+        dec(feats)  # the kernels are inference-only and are never swapped for torch implicitly
+    out = dec(feats, impl="torch")
+    out.sum().backward()
+    assert feats.grad.abs().max().item() > 0 and dec[0].weight.grad.abs().max().item() > 0
