@@ -265,7 +265,8 @@ int b200nerf_pdf_resample_stratified(b200nerf_ctx* ctx, const float* weights, co
  *   density mode : density [N,S] (the forward output) and ddensity [N,S] = dL/d density; folds in the proposal head
  *                  (trunc_exp, Linear(L*F,1,bias=False)); grad_decoder [L*F] receives dL/d density_decoder.weight.
  * grad_static_table [L*T, F] (or NULL); grad_actor_tables_host = HOST array of n_actors device pointers
- * [La*Ta, F] (entries or the array may be NULL). */
+ * [La*Ta, F] (entries or the array may be NULL); it is copied, stream-ordered, into ONE context-owned device array, so
+ * calls that pass it must not run concurrently on different streams of the same context. */
 int b200nerf_neurad_encoding_bwd(b200nerf_ctx* ctx, int field, const float* mean, const float* std, const float* times,
                                  const float* flip, int64_t n_rays, int n_samples, const float* dfeatures,
                                  const float* density, const float* ddensity, float* grad_static_table,

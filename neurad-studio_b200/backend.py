@@ -74,6 +74,12 @@ class B200Backend:
             t = t.detach().to(device=self.device, dtype=dtype).contiguous()
         return t
 
+    def _ray_times(self, times: Optional[torch.Tensor], n: int) -> Optional[torch.Tensor]:
+        """Per-ray times [N] from [N], [N,1] or the reference's expanded [N,S,1] (it reads times[:, 0], neurad_encoding.py:194)."""
+        if times is None:
+            return None
+        return self._dev(times.reshape(n, -1)[:, 0] if times.numel() != n else times.reshape(n))
+
     def _check(self, rc: int):
         _lib.check(self.lib, rc)
 
@@ -376,10 +382,7 @@ class B200Backend:
         n, s = m.shape[0], m.shape[1]
         m = m.reshape(n, s, 3)
         sd = self._dev(std).reshape(n, s)
-        t = None
-        if times is not None:
-            t = times.reshape(n, -1)[:, 0] if times.numel() != n else times.reshape(n)
-            t = self._dev(t)
+        t = self._ray_times(times, n)
         d = per_ray = None
         if directions is not None:
             per_ray = directions.numel() == 3 * n and s != 1
@@ -452,9 +455,7 @@ class B200Backend:
         n, s = m.shape[0], m.shape[1]
         m = m.reshape(n, s, 3)
         sd = self._dev(std).reshape(n, s)
-        t = None
-        if times is not None:
-            t = self._dev(times.reshape(n, -1)[:, 0] if times.numel() != n else times.reshape(n))
+        t = self._ray_times(times, n)
         fl = None if flip is None else self._dev(flip).reshape(n)
         df = None if dfeatures is None else self._dev(dfeatures).reshape(n * s, -1)
         de = None if density is None else self._dev(density).reshape(n, s)
@@ -477,7 +478,7 @@ class B200Backend:
         n, s = m.shape[0], m.shape[1]
         m = m.reshape(n, s, 3)
         sd = self._dev(std).reshape(n, s)
-        t = self._dev(times.reshape(n, -1)[:, 0] if times.numel() != n else times.reshape(n))
+        t = self._ray_times(times, n)
         fl = None if flip is None else self._dev(flip).reshape(n)
         df = self._dev(dfeatures).reshape(n * s, -1)
         r6, ps = self._dev(rotations_6d), self._dev(positions)
