@@ -16,6 +16,11 @@ import torch
 from torch import Tensor
 from torch.autograd import Function
 
+# The reference trains under AMP (mixed_precision, configs/method_configs.py:401).  The operators here are fp32: under
+# autocast their tensor arguments are cast to fp32 and autocast is switched off inside forward / backward.
+_fwd = torch.amp.custom_fwd(device_type="cuda", cast_inputs=torch.float32)
+_bwd = torch.amp.custom_bwd(device_type="cuda")
+
 
 class EncodingFn(Function):
     """NeuRADHashEncoding.forward: (features [N*S,D], directions [N,S,3]); gradients go to the hash tables and -- for a
@@ -23,6 +28,7 @@ class EncodingFn(Function):
     `actor_rotations_6d` [T,A,6] / `actor_positions` [T,A,3] (pass None for a field without trajectory gradients)."""
 
     @staticmethod
+    @_fwd
     def forward(ctx, be, field: int, mean, std, times, directions, flip, rotations_6d, positions, static_table, *actor_tables):
         out = be.neurad_encoding(field, mean, std, times, directions, flip=flip)
         ctx.be, ctx.field = be, field
@@ -35,6 +41,7 @@ class EncodingFn(Function):
         return out["features"], dirs
 
     @staticmethod
+    @_bwd
     def backward(ctx, dfeatures, _ddirs):
         mean, std, times, flip, rot6, pos = ctx.saved_tensors
         needs = ctx.needs_input_grad[9:]
@@ -55,6 +62,7 @@ class DensityFn(Function):
     """NeuRADProposalField.get_density: density [N,S]; gradients go to the hash tables and the density decoder."""
 
     @staticmethod
+    @_fwd
     def forward(ctx, be, field: int, mean, std, times, flip, static_table, decoder_weight, *actor_tables):
         out = be.neurad_encoding(field, mean, std, times, None, want_features=False, want_density=True, flip=flip)
         ctx.be, ctx.field = be, field
@@ -64,6 +72,7 @@ class DensityFn(Function):
         return out["density"]
 
     @staticmethod
+    @_bwd
     def backward(ctx, ddensity):
         mean, std, times, flip, density = ctx.saved_tensors
         needs = ctx.needs_input_grad[6:]
@@ -80,6 +89,7 @@ class MlpFn(Function):
     """MLP.forward (ReLU hidden layers, linear output) on the tcgen05 operator; args: x, then weight_0, bias_0, ..."""
 
     @staticmethod
+    @_fwd
     def forward(ctx, be, x, *wb):
         ws, bs = list(wb[0::2]), list(wb[1::2])
         ctx.be = be
@@ -87,6 +97,7 @@ class MlpFn(Function):
         return be.mlp_fwd(x, ws, bs)
 
     @staticmethod
+    @_bwd
     def backward(ctx, dy):
         x, *wb = ctx.saved_tensors
         ws, bs = list(wb[0::2]), list(wb[1::2])
@@ -104,12 +115,14 @@ class FieldMidFn(Function):
     """[geo_embedding | SH4((d+1)/2)] (fields/neurad_field.py:139-141); gradient to geo_out only."""
 
     @staticmethod
+    @_fwd
     def forward(ctx, be, geo_out, directions):
         ctx.be = be
         ctx.save_for_backward(geo_out)
         return be._field_mid(geo_out, directions)
 
     @staticmethod
+    @_bwd
     def backward(ctx, dx2):
         (geo,) = ctx.saved_tensors
         dgeo, _ = ctx.be.field_heads_bwd(geo, None, None, None, dx2.contiguous())
@@ -120,12 +133,14 @@ class FieldTailFn(Function):
     """feature = geo_embedding + mlp_feature_out, sdf, alpha = sigmoid(-sdf (|beta| + 1e-4)) (neurad_field.py:141-149)."""
 
     @staticmethod
+    @_fwd
     def forward(ctx, be, geo_out, mlp_out, beta_param):
         ctx.be = be
         ctx.save_for_backward(geo_out, beta_param)
         return be._field_tail(geo_out, mlp_out)
 
     @staticmethod
+    @_bwd
     def backward(ctx, dfeature, dsdf, dalpha):
         geo, beta_param = ctx.saved_tensors
         dgeo, dbeta = ctx.be.field_heads_bwd(geo, dfeature.contiguous(), dsdf, dalpha, None)
@@ -138,12 +153,14 @@ class AlphaToWeightsFn(Function):
     """nerfacc.render_weight_from_alpha on dense [N,S] (models/neurad.py:717)."""
 
     @staticmethod
+    @_fwd
     def forward(ctx, be, alphas):
         ctx.be = be
         ctx.save_for_backward(alphas)
         return be.alpha_to_weights(alphas)
 
     @staticmethod
+    @_bwd
     def backward(ctx, dw):
         (alphas,) = ctx.saved_tensors
         return None, ctx.be.alpha_to_weights_bwd(alphas, dw.contiguous())
@@ -153,12 +170,14 @@ class DensityToWeightsFn(Function):
     """RaySamples.get_weights (cameras/rays.py:188-210); gradient to the densities (bin widths are detached)."""
 
     @staticmethod
+    @_fwd
     def forward(ctx, be, deltas, densities):
         ctx.be = be
         ctx.save_for_backward(deltas, densities)
         return be.density_to_weights(deltas, densities)
 
     @staticmethod
+    @_bwd
     def backward(ctx, dw):
         deltas, densities = ctx.saved_tensors
         return None, None, ctx.be.density_to_weights_bwd(deltas, densities, dw.contiguous())
@@ -169,6 +188,7 @@ class CompositeFn(Function):
     [N,1], depth [N,1]); tensors that were not asked for come back empty."""
 
     @staticmethod
+    @_fwd
     def forward(ctx, be, weights, values, starts, ends, want_acc: bool, want_depth: bool):
         out = be.composite(weights, values, starts, ends, "simple" if want_depth else None, want_accumulation=want_acc)
         ctx.be = be
@@ -180,6 +200,7 @@ class CompositeFn(Function):
         return out.get("values", e), out.get("accumulation", e), out.get("depth", e)
 
     @staticmethod
+    @_bwd
     def backward(ctx, dvalues_out, dacc, ddepth):
         weights, values, starts, ends = ctx.saved_tensors
         has_v, has_a, has_d = ctx.has
@@ -198,12 +219,14 @@ class DistortionLossFn(Function):
     """lossfun_distortion per ray (losses.py:160-172): gradient to the weights; the spacing edges are detached."""
 
     @staticmethod
+    @_fwd
     def forward(ctx, be, sdist, weights):
         loss, dw = be.distortion_loss(sdist, weights, want_grad=True)
         ctx.save_for_backward(dw)
         return loss
 
     @staticmethod
+    @_bwd
     def backward(ctx, dloss):
         (dw,) = ctx.saved_tensors
         return None, None, dw * dloss[:, None]
@@ -213,12 +236,14 @@ class InterlevelLossFn(Function):
     """zipnerf_interlevel_loss for one proposal level, per ray (losses.py:645-705): gradient to the proposal weights."""
 
     @staticmethod
+    @_fwd
     def forward(ctx, be, sdist, weights, prop_sdist, prop_weights, pulse_width: float):
         loss, dwp = be.zipnerf_interlevel_loss(sdist, weights, prop_sdist, prop_weights, pulse_width, want_grad=True)
         ctx.save_for_backward(dwp)
         return loss
 
     @staticmethod
+    @_bwd
     def backward(ctx, dloss):
         (dwp,) = ctx.saved_tensors
         return None, None, None, None, dwp * dloss[:, None], None
