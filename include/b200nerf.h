@@ -284,6 +284,11 @@ int b200nerf_neurad_encoding_pose_bwd(b200nerf_ctx* ctx, int field, const float*
                                       const float* rotations_6d, const float* positions, float* grad_rotations_6d,
                                       float* grad_positions, void* stream);
 
+/* HashEncoding.forward backward (autograd of encodings.py:425-466 / tcnn's grid backward) for the stand-alone grid operator
+ * b200nerf_hashgrid_fwd: x [P,3], dout [P, L*F] -> grad_table [L*T, F] accumulated (+=).  L*F <= 64. */
+int b200nerf_hashgrid_bwd(b200nerf_ctx* ctx, const b200nerf_grid_desc* desc, const float* x, const float* dout,
+                          int64_t n_points, float* grad_table, void* stream);
+
 /* nerfacc.render_weight_from_alpha backward (call site models/neurad.py:717): alphas, dweights [N,S] -> dalphas. */
 int b200nerf_alpha_to_weights_bwd(b200nerf_ctx* ctx, const float* alphas, const float* dweights, int64_t n_rays, int s,
                                   float* dalphas, void* stream);

@@ -247,3 +247,24 @@ class InterlevelLossFn(Function):
     def backward(ctx, dloss):
         (dwp,) = ctx.saved_tensors
         return None, None, None, None, dwp * dloss[:, None], None
+
+
+class HashGridFn(Function):
+    """HashEncoding.forward (the stand-alone grid, encodings.py:425-471): gradient to the hash table (the reference also
+    differentiates with respect to the positions; the path never asks for that on a stand-alone grid)."""
+
+    @staticmethod
+    @_fwd
+    def forward(ctx, be, settings, scalings, x, table):
+        ctx.be, ctx.settings, ctx.scalings = be, settings, scalings
+        ctx.save_for_backward(x)
+        ctx.table_shape = table.shape
+        return be.hashgrid_fwd(settings, table, x, scalings)
+
+    @staticmethod
+    @_bwd
+    def backward(ctx, dout):
+        (x,) = ctx.saved_tensors
+        g = torch.zeros(ctx.table_shape, device=dout.device)
+        ctx.be.hashgrid_bwd(ctx.settings, x, dout.contiguous(), g, ctx.scalings)
+        return None, None, None, None, g

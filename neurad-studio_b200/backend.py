@@ -487,6 +487,15 @@ class B200Backend:
         self._check(self.lib.b200nerf_neurad_encoding_pose_bwd(self._h, field, _ptr(m), _ptr(sd), _ptr(t), _ptr(fl), n, s, _ptr(df), _ptr(r6),
                                                                _ptr(ps), _ptr(grad_rotations_6d), _ptr(grad_positions), self._stream))
 
+    def hashgrid_bwd(self, g: HashGridSettings, x: torch.Tensor, dout: torch.Tensor, grad_table: torch.Tensor,
+                     scalings: Optional[torch.Tensor] = None) -> None:
+        """Backward of hashgrid_fwd: accumulates dL/d hash_table [L*T,F] from dL/d out [P, L*F]."""
+        xs = self._dev(x).reshape(-1, 3)
+        d = self._dev(dout).reshape(xs.shape[0], -1)
+        assert grad_table.is_contiguous() and grad_table.dtype == torch.float32 and grad_table.device == self.device
+        desc = grid_desc(g, scalings)
+        self._check(self.lib.b200nerf_hashgrid_bwd(self._h, ctypes.byref(desc), _ptr(xs), _ptr(d), xs.shape[0], _ptr(grad_table), self._stream))
+
     def alpha_to_weights_bwd(self, alphas: torch.Tensor, dweights: torch.Tensor) -> torch.Tensor:
         a, dw = self._dev(alphas), self._dev(dweights)
         out = torch.empty_like(a)

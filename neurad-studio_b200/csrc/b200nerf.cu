@@ -1485,6 +1485,21 @@ int b200nerf_neurad_encoding_pose_bwd(b200nerf_ctx* c, int field, const float* m
   return 0;
 }
 
+int b200nerf_hashgrid_bwd(b200nerf_ctx* c, const b200nerf_grid_desc* desc, const float* x, const float* dout, int64_t n_points,
+                          float* grad_table, void* stream) {
+  REQUIRE(c, "ctx is NULL");
+  REQUIRE(n_points >= 0, "bad shape");
+  Grid g{};
+  if (int e = make_grid(desc, nullptr, &g)) return e;
+  REQUIRE(g.L * g.F <= kModMaxDim, "encoding rows wider than 64 features are not supported");
+  if (n_points == 0) return 0;
+  REQUIRE(x && dout && grad_table, "NULL argument");
+  DeviceGuard gd(c->device);
+  hashgrid_bwd_kernel<<<(unsigned)((n_points + 127) / 128), 128, 0, (cudaStream_t)stream>>>(g, x, dout, n_points, grad_table);
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
 int b200nerf_alpha_to_weights_bwd(b200nerf_ctx* c, const float* alphas, const float* dweights, int64_t n_rays, int s,
                                   float* dalphas, void* stream) {
   REQUIRE(c, "ctx is NULL");

@@ -488,4 +488,17 @@ __global__ void __launch_bounds__(kModWarps * 32) neurad_encoding_pose_bwd_kerne
   }
 }
 
+// HashEncoding.forward backward (the stand-alone grid of field_components/encodings.py:425-466, no anti-aliasing rescale):
+// grad_table[row] += dout[p, l*F+f] * trilinear corner weight; one thread per point.
+__global__ void hashgrid_bwd_kernel(Grid g, const float* __restrict__ x, const float* __restrict__ dout, int64_t n_points,
+                                    float* __restrict__ grad_table) {
+  const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n_points) return;
+  const Gauss q = {x[3 * p], x[3 * p + 1], x[3 * p + 2], 0.0f};  // std = 0: level_weight() == 1
+  float d[kModMaxDim];
+  const int D = g.L * g.F;
+  for (int k = 0; k < D; ++k) d[k] = dout[p * D + k];
+  encode_levels_bwd(grad_table, g, q, d);
+}
+
 }  // namespace nff

@@ -53,6 +53,17 @@ def get_backend(device: torch.device) -> B200Backend:
     return _BACKENDS[idx]
 
 
+def _needs_grad(*tensors) -> bool:
+    return torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in tensors)
+
+
+def _no_backward(what: str, *tensors) -> None:
+    """Operators without a backward fail loudly rather than detach silently."""
+    if _needs_grad(*tensors):
+        raise NotImplementedError(f"{what} has no backward operator (NeuRAD does not train through it); detach its inputs "
+                                  "or call it under torch.no_grad()")
+
+
 @dataclass
 class RayBundle:
     """cameras/rays.py:252-275 (the tensors the hot path reads; shapes [*batch, k])."""
@@ -126,11 +137,13 @@ class HashEncoding(nn.Module):
     def get_out_dim(self) -> int:
         return self.num_levels * self.features_per_level
 
-    @torch.no_grad()
     def forward(self, in_tensor: Tensor) -> Tensor:
         assert in_tensor.shape[-1] == 3  # encodings.py:428
         be = get_backend(self.hash_table.device)
-        return be.hashgrid_fwd(self._g, self.hash_table, in_tensor, self.scalings)
+        if torch.is_grad_enabled() and self.hash_table.requires_grad:  # trains the table (hand-written scatter backward)
+            return AG.HashGridFn.apply(be, self._g, self.scalings, in_tensor.detach(), self.hash_table)
+        with torch.no_grad():
+            return be.hashgrid_fwd(self._g, self.hash_table, in_tensor, self.scalings)
 
 
 class SHEncoding(nn.Module):
@@ -174,10 +187,14 @@ class MLP(nn.Module):
     def get_out_dim(self) -> int:
         return self.out_dim
 
-    @torch.no_grad()
     def forward(self, in_tensor: Tensor) -> Tensor:
         be = get_backend(in_tensor.device)
-        y = be.mlp_fwd(in_tensor, [l.weight for l in self.layers], [l.bias for l in self.layers])
+        wb = [t for l in self.layers for t in (l.weight, l.bias)]
+        if _needs_grad(in_tensor, *wb):  # MLP backward operators (dX on tcgen05, dW / db)
+            y = AG.MlpFn.apply(be, in_tensor.reshape(-1, in_tensor.shape[-1]).contiguous(), *wb).reshape(*in_tensor.shape[:-1], self.out_dim)
+        else:
+            with torch.no_grad():
+                y = be.mlp_fwd(in_tensor, wb[0::2], wb[1::2])
         return y if self.out_activation is None else self.out_activation(y)
 
 
@@ -444,12 +461,16 @@ class PowerSampler(SpacedSampler):
 
 
 class FeatureRenderer(nn.Module):
-    """model_components/renderers.py:59-90, unpacked branch: sum_s w_s * f_s."""
+    """model_components/renderers.py:59-90, unpacked branch: sum_s w_s * f_s (differentiable: composite backward operator)."""
 
     @classmethod
-    @torch.no_grad()
     def forward(cls, features: Tensor, weights: Tensor) -> Tensor:
-        return get_backend(weights.device).composite(weights, features, want_accumulation=False)["values"]
+        be = get_backend(weights.device)
+        if _needs_grad(features, weights):
+            w = weights.reshape(weights.shape[0], weights.shape[1]).contiguous()
+            return AG.CompositeFn.apply(be, w, features.contiguous(), None, None, False, False)[0]
+        with torch.no_grad():
+            return be.composite(weights, features, want_accumulation=False)["values"]
 
 
 class RGBRenderer(nn.Module):
@@ -466,7 +487,7 @@ class RGBRenderer(nn.Module):
         self.background_color = background_color
 
     @torch.no_grad()
-    def forward(self, rgb: Tensor, weights: Tensor) -> Tensor:
+    def _forward(self, rgb: Tensor, weights: Tensor) -> Tensor:
         bg = self.background_color
         if isinstance(bg, str):
             bg = None if bg == "random" else self.COLORS[bg]
@@ -475,14 +496,22 @@ class RGBRenderer(nn.Module):
         be = get_backend(weights.device)
         return be.composite(weights, rgb, background=bg, value_nan_to_num=True, want_accumulation=False)["values"]
 
+    def forward(self, rgb: Tensor, weights: Tensor) -> Tensor:
+        _no_backward("RGBRenderer", rgb, weights)
+        return self._forward(rgb, weights)
+
 
 class AccumulationRenderer(nn.Module):
-    """model_components/renderers.py:322-350, unpacked branch."""
+    """model_components/renderers.py:322-350, unpacked branch (differentiable: composite backward operator)."""
 
     @classmethod
-    @torch.no_grad()
     def forward(cls, weights: Tensor) -> Tensor:
-        return get_backend(weights.device).composite(weights)["accumulation"]
+        be = get_backend(weights.device)
+        if _needs_grad(weights):
+            w = weights.reshape(weights.shape[0], weights.shape[1]).contiguous()
+            return AG.CompositeFn.apply(be, w, None, None, None, True, False)[1]
+        with torch.no_grad():
+            return be.composite(weights)["accumulation"]
 
 
 class DepthRenderer(nn.Module):
@@ -494,12 +523,13 @@ class DepthRenderer(nn.Module):
             raise NotImplementedError(f"Method {method} not implemented")
         self.method = method
 
-    @torch.no_grad()
     def forward(self, weights: Tensor, ray_samples: RaySamples) -> Tensor:
+        _no_backward(f"DepthRenderer({self.method!r})", weights)  # NeuRAD trains with render_depth_simple (NeuRADModel.renderer_depth)
         fr = ray_samples.frustums
         be = get_backend(weights.device)
-        return be.composite(weights, starts=fr.starts.contiguous(), ends=fr.ends.contiguous(), depth_method=self.method,
-                            want_accumulation=False)["depth"]
+        with torch.no_grad():
+            return be.composite(weights, starts=fr.starts.contiguous(), ends=fr.ends.contiguous(), depth_method=self.method,
+                                want_accumulation=False)["depth"]
 
 
 class ProposalNetworkSampler:
@@ -594,10 +624,22 @@ class NeuRADHashEncoding:
     def get_out_dim(self) -> int:
         return self.scene_repr_dim
 
-    @torch.no_grad()
     def forward(self, positions: GaussiansStd, times: Tensor, directions: Optional[Tensor] = None) -> Tuple[Tensor, Optional[Tensor]]:
-        """(features [N*S, D], directions [N,S,3] in the actor frame where a sample is inside an actor | None)."""
-        out = self._model._bind().neurad_encoding(self._field, positions.mean, positions.std, times, directions)
+        """(features [N*S, D], directions [N,S,3] in the actor frame where a sample is inside an actor | None); trains the
+        tables (and, for the main field's grid, the actor trajectories) when they require grad."""
+        m = self._model
+        be = m._bind()
+        flip = m._draw_actor_flip(positions.mean.shape[0], self._field)
+        tables = m._grid_params("field" if self._field == 0 else f"proposal_fields.{self._field - 1}")
+        traj = [None, None]
+        if self._field == 0 and m.config.n_actors:  # require_actor_grad: the main field's grid only (neurad_field.py:50,177)
+            traj = [m._param("dynamic_actors.actor_rotations_6d"), m._param("dynamic_actors.actor_positions")]
+        if _needs_grad(*tables, *traj):
+            feats, dirs = AG.EncodingFn.apply(be, self._field, positions.mean, positions.std, times, directions, flip, traj[0], traj[1],
+                                              tables[0], *tables[1:])
+            return feats, (dirs if directions is not None else None)
+        with torch.no_grad():
+            out = be.neurad_encoding(self._field, positions.mean, positions.std, times, directions, flip=flip)
         return out["features"], out.get("directions")
 
     __call__ = forward

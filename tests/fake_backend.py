@@ -134,6 +134,10 @@ class FakeBackend(B200Backend):
         y = O.hash_encode(x.reshape(-1, 3), table, sc, 2 ** g.log2_hashmap_size)
         return y.reshape(*x.shape[:-1], y.shape[-1])
 
+    def hashgrid_bwd(self, g, x, dout, grad_table, scalings=None):
+        sc = g.scalings() if scalings is None else scalings
+        emul.hashgrid_bwd(g.num_levels, g.hashgrid_dim, g.log2_hashmap_size, sc, x.detach(), dout, grad_table)
+
     @torch.no_grad()
     def sh4_fwd(self, dirs):
         return O.sh_components_l4(dirs)
@@ -206,9 +210,12 @@ class FakeBackend(B200Backend):
             out["values"] = (w * values.reshape(n, s, -1)).sum(dim=-2)
         if want_accumulation:
             out["accumulation"] = w.sum(dim=-2)
-        if depth_method is not None:
-            assert depth_method == "simple"
+        if depth_method == "simple":
             out["depth"] = (w * (starts.reshape(n, s, 1) + ends.reshape(n, s, 1)) / 2).sum(dim=-2)
+        elif depth_method == "median":
+            out["depth"] = S.depth_median(w, starts.reshape(n, s, 1), ends.reshape(n, s, 1))
+        elif depth_method is not None:
+            raise NotImplementedError(depth_method)
         return out
 
     def render(self, rays, want_trace=False, want_intensity=False, out=None, image_width=0):

@@ -380,4 +380,16 @@ int emul_encoding_pose_bwd(const void* const* ptrs, const int* ints, const float
   }
   return 0;
 }
+
+// stand-alone HashEncoding backward (modules.cuh: hashgrid_bwd_kernel = encode_levels_bwd with unit level weights)
+int emul_hashgrid_bwd(int L, int F, int log2T, const float* res, const float* x, const float* dout, long long n_points, float* grad_table) {
+  Grid g{};
+  g.L = L; g.F = F; g.T = 1u << log2T; g.mask = g.T - 1u;
+  for (int l = 0; l < L; ++l) g.res[l] = res[l];
+  for (long long p = 0; p < n_points; ++p) {
+    const Gauss q = {x[3 * p], x[3 * p + 1], x[3 * p + 2], 0.0f};
+    encode_levels_bwd(grad_table, g, q, dout + p * L * F);
+  }
+  return 0;
+}
 }

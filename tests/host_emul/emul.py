@@ -283,3 +283,14 @@ def encoding_pose_bwd(cfg, params, pdf_u, field, mean, std, times, dfeatures, gr
     c_extra = (ctypes.c_void_p * len(ex.ptrs))(*ex.ptrs)
     rc = lib.emul_encoding_pose_bwd(c_ptrs, c_ints, c_floats, c_extra, ctypes.c_longlong(n), ctypes.c_int(s), ctypes.c_int(field))
     assert rc == 0
+
+
+def hashgrid_bwd(num_levels, features_per_level, log2_hashmap_size, scalings, x, dout, grad_table):
+    """encode_levels_bwd with unit level weights: accumulates dL/d hash_table from dL/d out [P, L*F]."""
+    lib = ctypes.CDLL(build())
+    sc = scalings.float().contiguous()
+    xs, d = x.float().reshape(-1, 3).contiguous(), dout.float().contiguous()
+    p = lambda t: ctypes.c_void_p(t.data_ptr())  # noqa: E731
+    rc = lib.emul_hashgrid_bwd(ctypes.c_int(num_levels), ctypes.c_int(features_per_level), ctypes.c_int(log2_hashmap_size), p(sc), p(xs),
+                               p(d), ctypes.c_longlong(xs.shape[0]), p(grad_table))
+    assert rc == 0

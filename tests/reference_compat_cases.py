@@ -134,3 +134,40 @@ def mlp(dev):
 
 
 SPACED = {"uniform": UniformSampler, "lin_disp": LinearDisparitySampler, "sqrt": SqrtSampler, "log": LogSampler}
+
+
+def standalone_modules_train(dev):
+    """The stand-alone HashEncoding / MLP mirrors are differentiable like the reference's torch modules (hand-written
+    backward operators), FeatureRenderer / AccumulationRenderer too; operators without a backward refuse to run on
+    inputs that require grad instead of detaching them silently."""
+    from neurad_studio_b200.nerfstudio_api import DepthRenderer, FeatureRenderer, RaySamples
+    from oracle import neurad_oracle as O
+
+    torch.manual_seed(0)
+    enc = HashEncoding(num_levels=4, min_res=16, max_res=128, log2_hashmap_size=8, features_per_level=4, hash_init_scale=1.0).to(dev)
+    m = MLP(in_dim=16, num_layers=2, layer_width=32, out_dim=3).to(dev)
+    x = torch.rand(200, 3, device=dev)
+    g = torch.randn(200, 3, device=dev)
+    (m(enc(x)) * g).sum().backward()
+    table = enc.hash_table.detach().cpu().clone().requires_grad_(True)
+    ws = [l.weight.detach().cpu().clone().requires_grad_(True) for l in m.layers]
+    bs = [l.bias.detach().cpu().clone().requires_grad_(True) for l in m.layers]
+    f = O.hash_encode(x.cpu(), table, enc.scalings.cpu(), 2**8)
+    y = torch.nn.functional.linear(torch.relu(torch.nn.functional.linear(f, ws[0], bs[0])), ws[1], bs[1])
+    (y * g.cpu()).sum().backward()
+
+    def rel(a, b):
+        return (a.detach().cpu() - b).abs().max().item() / (b.abs().max().item() + 1e-30)
+
+    assert rel(enc.hash_table.grad, table.grad) < 1e-4
+    for l, w, b in zip(m.layers, ws, bs):
+        assert rel(l.weight.grad, w.grad) < 1e-4 and rel(l.bias.grad, b.grad) < 1e-4
+    w = torch.rand(6, 10, 1, device=dev).requires_grad_(True)
+    v = torch.randn(6, 10, 5, device=dev).requires_grad_(True)
+    (FeatureRenderer()(v, w).sum() + 2 * AccumulationRenderer()(w).sum()).backward()
+    assert rel(w.grad, (v.detach().cpu().sum(-1, keepdim=True) + 2)) < 1e-5 and rel(v.grad, w.detach().cpu().expand(6, 10, 5)) < 1e-6
+    rs = RaySamples(Frustums(torch.zeros(6, 3, device=dev), torch.ones(6, 3, device=dev), torch.linspace(0, 1, 11, device=dev).repeat(6, 1)),
+                    torch.linspace(0, 1, 11, device=dev))
+    with pytest.raises(NotImplementedError):
+        DepthRenderer("median")(w, rs)
+    assert DepthRenderer("median")(w.detach(), rs).shape == (6, 1)

@@ -43,3 +43,7 @@ def test_tensor_hash_encoder():
 
 def test_mlp():
     R.mlp("cpu")
+
+
+def test_standalone_modules_train():
+    R.standalone_modules_train("cpu")

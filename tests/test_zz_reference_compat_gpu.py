@@ -39,3 +39,7 @@ def test_tensor_hash_encoder():
 
 def test_mlp():
     R.mlp("cuda")
+
+
+def test_standalone_modules_train():
+    R.standalone_modules_train("cuda")
