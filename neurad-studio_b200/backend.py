@@ -56,6 +56,10 @@ class B200Backend:
         self._h = h
         self._keep: Dict[str, object] = {}  # tensors the library references zero-copy
         self.cfg: Optional[NeuRADConfig] = None
+        # Who bound the context last: (model uid, parameter versions).  The backend is a per-device singleton shared by every
+        # model in the process, so a model must re-bind whenever ANOTHER model (or a direct load_params call) came in between.
+        self._owner = None
+        self._dec_owner = None
 
     def close(self):
         if getattr(self, "_h", None) is not None and self._h.value:
@@ -92,8 +96,16 @@ class B200Backend:
         """Bind a full parameter set.  `density_field_of_round` defaults to the reference's effective behaviour:
         both proposal rounds evaluate proposal_fields[1] (late-binding closures at models/neurad.py:248)."""
         self.cfg = cfg
+        self._owner = None  # a model that binds through NeuRADModel._bind() records itself after this call
         p = params
         n_act = cfg.n_actors
+        # dynamic_actors.actor_to_id (dynamic_actors.py:161, read at neurad_encoding.py:181): actor index -> hash-grid index;
+        # identity unless a closed-loop server re-assigned it (scripts/closed_loop/server.py:143)
+        a2i = p.get("dynamic_actors.actor_to_id")
+        grid_of_actor = list(range(n_act)) if a2i is None else [int(v) for v in a2i.detach().cpu().reshape(-1).tolist()]
+        if n_act > 0 and (len(grid_of_actor) != n_act or min(grid_of_actor) < 0 or max(grid_of_actor) >= n_act):
+            raise ValueError("dynamic_actors.actor_to_id must hold one grid index in [0, n_actors) per actor")
+        self.actor_grids_remapped = grid_of_actor != list(range(n_act))
         prefixes = {FIELD_MAIN: "field", FIELD_PROP0: "proposal_fields.0", FIELD_PROP1: "proposal_fields.1"}
         gcfgs = {FIELD_MAIN: cfg.grid, FIELD_PROP0: cfg.proposal_grid_1, FIELD_PROP1: cfg.proposal_grid_2}
         static_scale = float(p["static_scale"]) if "static_scale" in p else float(cfg.static_scale)
@@ -104,7 +116,7 @@ class B200Backend:
             sd = grid_desc(g.static, p.get(f"{pre}.hashgrid.static_grid.scalings"))
             ad, arr = None, None
             if n_act > 0:
-                tabs = [self._dev(p[f"{pre}.hashgrid.actor_grids.{a}.hash_table"]) for a in range(n_act)]
+                tabs = [self._dev(p[f"{pre}.hashgrid.actor_grids.{grid_of_actor[a]}.hash_table"]) for a in range(n_act)]
                 self._keep[f"{pre}.actors"] = tabs
                 arr = (ctypes.c_void_p * n_act)(*[t.data_ptr() for t in tabs])
                 ad = grid_desc(g.actor, p.get(f"{pre}.hashgrid.actor_grids.0.scalings"))
@@ -685,6 +697,7 @@ class B200Backend:
         `{prefix}.0.weight`, `{prefix}.2.main_branch.0.weight`, `{prefix}.2.main_branch.1.running_mean`, ...
         BatchNorms are folded into the 7x7 convolutions inside the library (eval-mode semantics)."""
         keep = []
+        self._dec_owner = None
         pre = prefix + "." if prefix else ""
 
         def t(key):

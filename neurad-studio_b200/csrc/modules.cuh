@@ -158,7 +158,8 @@ __global__ void __launch_bounds__(kModWarps * 32) neurad_encoding_bwd_kernel(con
       Gauss g = {a.mean[3 * i], a.mean[3 * i + 1], a.mean[3 * i + 2], a.std[i]};
       float dfeat[kModMaxDim];
       if (density_mode) {
-        const float gd = a.ddensity[i] * a.density[i];
+        // trunc_exp backward (field_components/activations.py:38-41): g * exp(clamp(x, -15, 15)); density = exp(x), exp is monotonic
+        const float gd = a.ddensity[i] * fminf(fmaxf(a.density[i], 3.0590232e-07f), 3269017.372f);
         if (a.grad_decoder) {
           float feat[kModMaxDim];
           neurad_encode_point(fg, frames[warp], A.n_actors, g, feat, nullptr, flip);

@@ -28,6 +28,14 @@
 #ifndef NFF_FAST_RCP
 #define NFF_FAST_RCP 1  // anti-aliasing weights via MUFU.RCP (smooth factor, <= 1 ulp)
 #endif
+#ifndef NFF_PARITY_STD
+#define NFF_PARITY_STD 0  // gaussian std / contraction scaling / level weight with the reference's own op sequence (pow(x, 1/3) as
+                          // powf(x, 0.33333334f), true divisions); 0: cbrtf + reciprocal multiplies (<= 3e-7 relative, faster)
+#endif
+#ifndef NFF_PARITY_LERP
+#define NFF_PARITY_LERP 0  // trilinear blend with the reference's separate products (encodings.py:454-466); 0: one product per
+                           // blend folded into an FMA
+#endif
 #define NFF_STR2(x) #x
 #define NFF_STR(x) NFF_STR2(x)
 
@@ -102,8 +110,12 @@ NFF_D Gauss sample_gaussian(const float o[3], const float d[3], float area, floa
   g.z = fadd(o[2], fmul(d[2], t));
   float cs = fmul(area, fmul(t, t));
   // reference: pow(x, 1/3) with the fp32 exponent 0.33333334f; cbrtf differs from it by < 3e-7 relative
-  // (|ln x| * 1e-8), far inside the 1e-4 budget, and costs ~12 instead of ~75 instructions
+  // (|ln x| * 1e-8) and costs ~12 instead of ~75 instructions
+#if NFF_PARITY_STD
+  g.std = powf(fmul(cs, md), 0.33333334f);
+#else
   g.std = cbrtf(fmul(cs, md));
+#endif
   return g;
 }
 // ScaledSceneContraction(order=inf) on a GaussiansStd (field_components/spatial_distortions.py:103-114,132-136)
@@ -112,14 +124,22 @@ NFF_D Gauss contract(Gauss g, float scale) {
   // difference in x by its resolution (4096 / 8191 cells), so one ulp here is ~1e-4 in a feature.  The std only
   // scales the smooth anti-aliasing weights, so it uses reciprocals and cbrt (<= 3e-7 relative).
   float x = fdiv(g.x, scale), y = fdiv(g.y, scale), z = fdiv(g.z, scale);
+#if NFF_PARITY_STD
+  float sd = fdiv(g.std, scale);
+#else
   float sd = fmul(g.std, frcp(scale));
+#endif
   float mag = fmaxf(fmaxf(fabsf(x), fabsf(y)), fabsf(z));
   if (!(mag < 1.0f)) {
     const float a = fsub(2.0f, frcp(mag));
     x = fmul(a, fdiv(x, mag));
     y = fmul(a, fdiv(y, mag));
     z = fmul(a, fdiv(z, mag));
+#if NFF_PARITY_STD
+    float q = fdiv(powf(fsub(fmul(2.0f, mag), 1.0f), 0.33333334f), mag);
+#else
     float q = fmul(cbrtf(fsub(fmul(2.0f, mag), 1.0f)), frcp(mag));
+#endif
     sd = fmul(sd, fmul(q, q));
   }
   Gauss r;
@@ -180,11 +200,15 @@ NFF_D float trilerp(const float f[8], const Cell& c) {
 
 // Fused-path variant: same blend tree with the second product folded into an FMA (one rounding fewer per blend,
 // 14 instead of 24 instructions); the stage operator b200nerf_hashgrid_fwd keeps the bit-exact form above.
+#if NFF_PARITY_LERP
+NFF_D float blend_f(float a, float wa, float b, float wb) { return fadd(fmul(a, wa), fmul(b, wb)); }
+#else
 NFF_D float blend_f(float a, float wa, float b, float wb) { return fmaf(a, wa, b * wb); }
+#endif
 // anti-aliasing weight 1/max(1, 2*res*std) (neurad_encoding.py:302)
 NFF_D float level_weight(float res, float std) {
   const float t = fmaxf(fmul(fmul(res, 2.0f), std), 1.0f);
-#if NFF_FAST_RCP && defined(__CUDACC__)
+#if NFF_FAST_RCP && !NFF_PARITY_STD && defined(__CUDACC__)
   return __fdividef(1.0f, t);  // MUFU.RCP, <= 1 ulp for t in [1, 2^126)
 #else
   return frcp(t);

@@ -27,6 +27,8 @@ decoder is inference-only.  There is no CPU path: modules raise at call time if 
 """
 from __future__ import annotations
 
+import itertools
+
 import math
 from dataclasses import dataclass, field
 from enum import Enum
@@ -40,6 +42,7 @@ from .backend import B200Backend
 from .config import HashGridSettings, NeuRADConfig
 
 _BACKENDS: Dict[int, B200Backend] = {}
+_UIDS = itertools.count(1)  # one token per model instance (id() can be reused after garbage collection)
 
 
 def get_backend(device: torch.device) -> B200Backend:
@@ -140,6 +143,8 @@ class HashEncoding(nn.Module):
     def forward(self, in_tensor: Tensor) -> Tensor:
         assert in_tensor.shape[-1] == 3  # encodings.py:428
         be = get_backend(self.hash_table.device)
+        # the reference also differentiates w.r.t. the positions (encodings.py:425-471); this operator only trains the table
+        _no_backward("HashEncoding (d / d positions)", in_tensor)
         if torch.is_grad_enabled() and self.hash_table.requires_grad:  # trains the table (hand-written scatter backward)
             return AG.HashGridFn.apply(be, self._g, self.scalings, in_tensor.detach(), self.hash_table)
         with torch.no_grad():
@@ -749,7 +754,7 @@ class RGBDecoder(nn.Sequential):
             BasicBlock(hidden_dim, hidden_dim, kernel_size=7, padding=3, use_bn=True),
             BasicBlock(hidden_dim, hidden_dim, kernel_size=7, padding=3, use_bn=True),
             nn.Conv2d(hidden_dim, 3, kernel_size=1, padding=0), nn.Sigmoid())
-        self._bound = None
+        self._uid = next(_UIDS)
 
     def forward(self, features: Tensor, impl: str = "tc") -> Tensor:
         """impl "tc" / "tc_ldgsts" / "ref": the library's decoder kernels (inference: BatchNorm folded from its running
@@ -772,16 +777,21 @@ class RGBDecoder(nn.Sequential):
     def _forward_kernels(self, features: Tensor, impl: str) -> Tensor:
         be = get_backend(features.device)
         sd = self.state_dict()
-        ver = tuple(v._version for v in sd.values()) + (id(be),)
-        if ver != self._bound:
+        # the context is shared by every model on the device: re-bind unless THIS decoder, at these parameter versions,
+        # is what the context holds (two decoders alternating would otherwise run with each other's weights)
+        token = (self._uid, tuple(v._version for v in sd.values()), tuple(v.data_ptr() for v in sd.values()))
+        if getattr(be, "_dec_owner", None) != token:
             be.set_rgb_decoder(sd, prefix="", bn_eps=self[2].main_branch[1].eps)
-            self._bound = ver
+            be._dec_owner = token
         return be.rgb_decode(features, impl)
 
 
 class NeuRADModel(nn.Module):
-    """models/neurad.py:165 -- the forward (eval) half, with the reference's parameter names so that
-    `load_state_dict(reference_checkpoint["pipeline"], strict=False)` binds the tensors the path uses.
+    """models/neurad.py:165 with the reference's parameter names: `state_dict()` / `load_state_dict()` speak the reference's
+    dotted keys (`field.hashgrid.static_grid.hash_table`, ...; a `_model.` prefix as in `checkpoint["pipeline"]` is accepted),
+    so `load_state_dict(reference_checkpoint["pipeline"], strict=False)` binds the tensors the path uses and raises if a
+    hot-path tensor is missing.  Internally the tensors are registered under mangled names (dots are not allowed in
+    parameter names); hooks translate in both directions.
 
     `get_nff_outputs` is ONE fused kernel launch (ray sampling, both proposal rounds, main field, compositing); the
     reference's 32 768-ray chunk loop (neurad.py:650-659) is unnecessary because nothing per-sample goes to HBM."""
@@ -803,9 +813,12 @@ class NeuRADModel(nn.Module):
                 self.register_parameter(name, nn.Parameter(v, requires_grad=False))
             else:
                 self.register_buffer(name, v)
-        self.register_buffer("static_scale", torch.tensor(float(config.static_scale)))
+        # not part of the reference's state dict (a float passed to field.setup, neurad.py:180-184): non-persistent
+        self.register_buffer("static_scale", torch.tensor(float(config.static_scale)), persistent=False)
         self.rgb_decoder = RGBDecoder(config.nff_out_dim + config.appearance_dim, config.rgb_hidden_dim, config.rgb_upsample_factor)
-        self._bound_version = None
+        self._uid = next(_UIDS)
+        self.register_state_dict_post_hook(NeuRADModel._state_dict_out_hook)
+        self.register_load_state_dict_pre_hook(NeuRADModel._state_dict_in_hook)
         # the reference's sub-modules (neurad.py:180-254), as views onto this model's parameters
         self.field = NeuRADField(self)
         self.proposal_fields = [NeuRADProposalField(self, 1), NeuRADProposalField(self, 2)]
@@ -824,6 +837,36 @@ class NeuRADModel(nn.Module):
         self.density_fns = [lambda ray_samples: last.get_density(ray_samples)[0] for _ in self.proposal_fields]
         self.renderer_feat = FeatureRenderer()
         self.renderer_accumulation = AccumulationRenderer()
+
+    # -- nn.Module state dict in the reference's key format --------------------------------------------------------
+    @staticmethod
+    def _state_dict_out_hook(module, state_dict, prefix, local_metadata):
+        for name, key in module._names:
+            if prefix + name in state_dict:
+                state_dict[prefix + key] = state_dict.pop(prefix + name)
+
+    @staticmethod
+    def _state_dict_in_hook(module, state_dict, prefix, local_metadata, strict, missing_keys, unexpected_keys, error_msgs):
+        pipeline_prefix = prefix + "_model."
+        if any(k.startswith(pipeline_prefix) for k in state_dict):  # checkpoint["pipeline"]: `_model.<key>` (+ datamanager keys)
+            for k in [k for k in state_dict if k.startswith(prefix)]:
+                v = state_dict.pop(k)
+                if k.startswith(pipeline_prefix):
+                    state_dict[prefix + k[len(pipeline_prefix):]] = v
+        for name, key in module._names:
+            if prefix + key in state_dict:
+                state_dict[prefix + name] = state_dict.pop(prefix + key)
+
+    def load_state_dict(self, state_dict, strict: bool = True, assign: bool = False):
+        """nn.Module.load_state_dict on the reference's keys.  Even with strict=False a missing tensor of THIS path (grids,
+        MLPs, decoders, appearance embedding, actor trajectories) raises: silently keeping a random init is never wanted.
+        The rgb decoder stays optional in a hot-path-only state dict; keys of other subsystems are ignored when not strict."""
+        res = super().load_state_dict(dict(state_dict), strict=strict, assign=assign)
+        back = {n: k for n, k in self._names}
+        missing = [back[k] for k in res.missing_keys if k in back]
+        if missing:
+            raise KeyError(f"state dict lacks hot-path tensors: {missing[:6]}{' ...' if len(missing) > 6 else ''}")
+        return res
 
     def train(self, mode: bool = True) -> "NeuRADModel":
         """nn.Module.train, also reaching the samplers (nn.Modules in the reference): stratified jitter and the random
@@ -848,16 +891,19 @@ class NeuRADModel(nn.Module):
         dec = {k[len("rgb_decoder."):]: v for k, v in sd.items() if k.startswith("rgb_decoder.")}
         if dec:  # the camera decoder is optional in a hot-path-only state dict
             self.rgb_decoder.load_state_dict(dec, strict=False)
-        self._bound_version = None
 
     def _bind(self) -> B200Backend:
         be = get_backend(self.static_scale.device)
-        ver = tuple(getattr(self, n)._version for n, _ in self._names) + (id(be), str(self.static_scale.device))
-        if ver != self._bound_version or be.cfg is not self.config:
+        # The backend is a per-device singleton shared by every model of the process (EMA / teacher-student pairs, two
+        # checkpoints side by side): the context records WHO bound it, and a model re-binds unless it is the owner at the
+        # current parameter versions and storage (in-place updates bump _version; .to() / load_state_dict may swap storage).
+        tensors = [getattr(self, n) for n, _ in self._names] + [self.static_scale]
+        token = (self._uid, tuple(t._version for t in tensors), tuple(t.data_ptr() for t in tensors))
+        if getattr(be, "_owner", None) != token:
             params = self.reference_state_dict()
             params["static_scale"] = self.static_scale
             be.load_params(self.config, params)
-            self._bound_version = ver
+            be._owner = token
         return be
 
     # -- forward API --------------------------------------------------------------------------------------------

@@ -482,6 +482,19 @@ def hashgrid_forward(
 # ----------------------------------------------------------------------------------------------------------------------
 # fields
 # ----------------------------------------------------------------------------------------------------------------------
+class _TruncExp(torch.autograd.Function):
+    """field_components/activations.py:28-41: exp forward, backward g * exp(clamp(x, -15, 15))."""
+
+    @staticmethod
+    def forward(ctx, x):
+        ctx.save_for_backward(x)
+        return torch.exp(x)
+
+    @staticmethod
+    def backward(ctx, g):
+        return g * torch.exp(ctx.saved_tensors[0].clamp(-15, 15))
+
+
 def proposal_density(params, k: int, cfg: NeuRADCfg, o, d, area, times, starts, ends, trace=None) -> Tensor:
     """NeuRADProposalField.get_density (neurad_field.py:208-213).  starts/ends [N,S]; returns [N,S]."""
     N, S = starts.shape
@@ -489,7 +502,7 @@ def proposal_density(params, k: int, cfg: NeuRADCfg, o, d, area, times, starts, 
     t = times[:, None, None].expand(N, S, 1)
     feats, _ = hashgrid_forward(params, f"proposal_fields.{k}", cfg.prop[k], cfg, mean, std, t, None, trace, require_actor_grad=False)
     dens = F.linear(feats, params[f"proposal_fields.{k}.density_decoder.weight"])
-    return torch.exp(dens).view(N, S)
+    return _TruncExp.apply(dens).view(N, S)
 
 
 def sh_components_l4(directions: Tensor) -> Tensor:

@@ -280,7 +280,7 @@ int emul_encoding_bwd(const void* const* ptrs, const int* ints, const float* flo
       Gauss g = {mean[3 * i], mean[3 * i + 1], mean[3 * i + 2], std_[i]};
       float dfeat[kModMaxDim];
       if (ddensity) {
-        const float gd = ddensity[i] * density[i];
+        const float gd = ddensity[i] * std::fmin(std::fmax(density[i], 3.0590232e-07f), 3269017.372f);  // trunc_exp backward clamp
         if (grad_decoder) {
           float feat[kModMaxDim];
           neurad_encode_point(fg, frames.data(), A.n_actors, g, feat, nullptr, flip);

@@ -96,3 +96,62 @@ def test_rgb_decoder_torch_impl_matches_reference_golden_and_trains():
     out = dec(feats, impl="torch")
     out.sum().backward()
     assert feats.grad.abs().max().item() > 0 and dec[0].weight.grad.abs().max().item() > 0
+
+
+def test_two_models_sharing_one_backend_never_render_with_each_others_weights(monkeypatch):
+    """The backend is a per-device singleton: two models built from the SAME config object (EMA / teacher-student, two
+    checkpoints side by side) must each re-bind their own parameters when they alternate (round-1 advisor finding)."""
+    from neurad_studio_b200 import nerfstudio_api
+    from neurad_studio_b200.nerfstudio_api import NeuRADModel, RayBundle
+    from tests.fake_backend import FakeBackend
+
+    be = FakeBackend()
+    monkeypatch.setattr(nerfstudio_api, "get_backend", lambda device: be)
+    meta, g = load_golden("nff_static.npz")
+    cfg = cfg_from_meta(meta)
+    a, b = NeuRADModel(cfg), NeuRADModel(cfg)
+    a.load_reference_state_dict(g["param"])
+    pb = {k: (v * 1.5 if v.dtype.is_floating_point and "hash_table" in k else v) for k, v in g["param"].items()}
+    b.load_reference_state_dict(pb)
+    r = g["ray"]
+    rb = RayBundle(origins=r["origins"][:8], directions=r["directions"][:8], pixel_area=r["pixel_area"][:8], times=r["times"][:8],
+                   metadata={"is_lidar": r["is_lidar"][:8], "sensor_idxs": r["sensor_idx"][:8]})
+    fa1 = a.get_nff_outputs(rb)["features"].clone()
+    fb = b.get_nff_outputs(rb)["features"].clone()
+    fa2 = a.get_nff_outputs(rb)["features"].clone()
+    assert (fa1 - fb).abs().max().item() > 1e-3  # the two models really differ
+    assert torch.equal(fa1, fa2)  # ... and A's second render is A's again, not B's
+    # an in-place parameter update of the owner is noticed too
+    with torch.no_grad():
+        a._param("field.hashgrid.static_grid.hash_table").mul_(0.5)
+    assert (a.get_nff_outputs(rb)["features"] - fa1).abs().max().item() > 1e-4
+
+
+def test_state_dict_speaks_the_reference_keys(monkeypatch):
+    """state_dict() / load_state_dict() use the reference's dotted keys (optionally under checkpoint["pipeline"]'s `_model.`
+    prefix); strict=False ignores other subsystems' keys but a missing hot-path tensor always raises."""
+    from neurad_studio_b200.nerfstudio_api import NeuRADModel
+
+    meta, g = load_golden("nff_actors.npz")
+    cfg = cfg_from_meta(meta)
+    model = NeuRADModel(cfg)
+    sd = model.state_dict()
+    assert "field.hashgrid.static_grid.hash_table" in sd and "proposal_fields.1.density_decoder.weight" in sd
+    assert "rgb_decoder.0.weight" in sd and not any("__" in k for k in sd) and "static_scale" not in sd
+    # a reference pipeline checkpoint: `_model.` prefix, extra keys of other subsystems
+    ckpt = {"_model." + k: v for k, v in g["param"].items() if k != "static_scale"}
+    ckpt["_model.camera_optimizer.pose_adjustment"] = torch.zeros(3, 6)
+    ckpt["datamanager.train_ray_generator.image_coords"] = torch.zeros(2, 2)
+    res = model.load_state_dict(ckpt, strict=False)
+    assert all(k.startswith("rgb_decoder.") for k in res.missing_keys)
+    for k in ("field.hashgrid.static_grid.hash_table", "field.mlp_geo.layers.1.weight", "dynamic_actors.actor_positions"):
+        assert torch.equal(model.state_dict()[k].float(), g["param"][k].float()), k
+    with pytest.raises(RuntimeError):
+        model.load_state_dict(ckpt, strict=True)  # unexpected keys, like torch
+    del ckpt["_model.field.mlp_geo.layers.0.weight"]
+    with pytest.raises(KeyError):
+        model.load_state_dict(ckpt, strict=False)
+    # round trip through the mirror's own state dict
+    other = NeuRADModel(cfg)
+    other.load_state_dict(model.state_dict())
+    assert torch.equal(other.state_dict()["field.hashgrid.actor_grids.3.hash_table"], model.state_dict()["field.hashgrid.actor_grids.3.hash_table"])

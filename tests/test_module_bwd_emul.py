@@ -111,6 +111,33 @@ def test_encoding_backward_density_mode(name):
         assert (grads["actors"][a] - want).abs().max().item() <= 1e-4 * max(want.abs().max().item(), 1e-6)
 
 
+def test_encoding_backward_density_mode_clamps_like_trunc_exp():
+    """Pre-activations outside [-15, 15]: the reference's trunc_exp backward is g * exp(clamp(x, -15, 15))
+    (field_components/activations.py:38-41), not g * exp(x)."""
+    meta, g = load_golden("nff_static.npz")
+    cfg = cfg_from_meta(meta)
+    ocfg = to_oracle_cfg(cfg)
+    p, r, ref = dict(g["param"]), g["ray"], g["ref"]
+    key = "proposal_fields.1.density_decoder.weight"
+    p[key] = p[key] * 400.0  # drives |x| far beyond 15 on many samples
+    n = r["origins"].shape[0]
+    edges = ref["bins_e_1"].reshape(n, -1)
+    lidar = r["is_lidar"].reshape(-1).bool()
+    area = r["pixel_area"].reshape(-1) * torch.where(lidar, 1.0, float(cfg.rgb_upsample_factor**2))
+    q, keys = _grad_params(p, "proposal_fields.1", 0)
+    dens = O.proposal_density(q, 1, ocfg, r["origins"], r["directions"], area, r["times"].reshape(-1), edges[:, :-1], edges[:, 1:])
+    x = dens.detach().log()
+    assert (x > 15).any() and (x < -15).any()
+    G = torch.randn(dens.shape, generator=torch.Generator().manual_seed(2))
+    (dens * G).sum().backward()
+    em_mean, em_std = emul.gaussian(r["origins"], r["directions"], area, edges)
+    grads = {"static": torch.zeros_like(p[keys[0]]), "actors": [], "decoder": torch.zeros(p[keys[-1]].numel())}
+    emul.encoding_bwd(cfg, p, O.pdf_u, 2, em_mean, em_std, r["times"], grads, density=dens.detach(), ddensity=G)
+    assert torch.isfinite(grads["static"]).all()
+    assert rel_to_max(grads["static"], q[keys[0]].grad) < 1e-4
+    assert rel_to_max(grads["decoder"], q[keys[-1]].grad.reshape(-1)) < 1e-4
+
+
 def test_training_losses_match_reference_golden():
     """distortion_loss_ray / zipnerf_interlevel_ray (csrc/nff_modules.h) against the reference's own loss values and
     autograd gradients (tests/golden/losses.npz, oracle/make_golden_losses.py: loss = 3 * interlevel + 5 * distortion)."""

@@ -37,6 +37,10 @@ def test_training_gradients_glue(name):
     C.training_gradients_match_reference_golden(name, "cpu")
 
 
+def test_proposal_density_backward_clamp_glue():
+    C.proposal_density_backward_clamps_like_trunc_exp("cpu")
+
+
 def test_backward_stage_operators_glue():
     C.backward_stage_operators_match_torch_autograd("cpu")
 

@@ -4,10 +4,17 @@ Tolerances (north_star: "within 1e-4 rel fp32, bit-exact for sample indices/coun
   * integer work with identical inputs (hash rows, searchsorted indices of the stage operator fed the oracle's own
     weights) is compared bit-exactly;
   * final outputs are compared as  max|a-b| <= 1e-4 * max|ref|  (relative to the tensor's scale);
-  * inside the fused pipeline indices depend on transcendental functions (exp/pow differ by ulps between the CPU's
-    SLEEF and CUDA's libdevice), so there we assert an agreement RATE (>= 99.9 %) instead -- a flipped index only
-    moves a sample edge by a few ulp because the inverse cdf is continuous.
-  * `depth` under the raw beta=20 init is ill-conditioned (d alpha / d sdf = 5) and gets 5e-4.
+  * sample indices / actor ids of the fused pipeline are compared EXACTLY on the three reference goldens; only the
+    live-oracle cases (fresh random scenes, thousands of rays) keep an agreement rate, because there an index can
+    flip when exp/pow differ by an ulp between the CPU's SLEEF and CUDA's libdevice (a flipped index moves a sample
+    edge by a few ulp: the inverse cdf is continuous).
+  * per-sample traces (sdf / alpha / field_feature) are held to 1e-5 on the samples whose two edges are bit-identical
+    to the reference's, and to 2e-3 elsewhere: an edge that differs by one ulp moves the sample by ~1e-7 of the ray
+    length, which the finest grid level (8191 cells) turns into a ~1e-4 change of that sample's features -- in the
+    reference's own arithmetic too (tests/test_reference_noise_floor.py).
+  * `depth` under the raw beta=20 init (d alpha / d sdf = 5) gets 2e-4: the reference's own math evaluated with a
+    correctly rounded exp() instead of SLEEF's already sits 0.7e-4 from the golden (same test file).
+  "rel" everywhere = max|a-b| / max|ref| (relative to the tensor's scale, not elementwise).
 """
 import pytest
 import torch
@@ -34,17 +41,27 @@ def backend():
     return B200Backend(torch.device("cuda", 0))
 
 
-def _check_against(out, ref, beta, index_rate=1e-3):
+def _check_against(out, ref, beta):
     for k in ("inds_1", "inds_2", "actor_id_0", "actor_id_1", "actor_id_main"):
-        mism = (out[k].cpu().long() != ref[k].long()).float().mean().item()
-        assert mism <= index_rate, (k, mism)
+        n_mism = int((out[k].cpu().long() != ref[k].long()).sum())
+        assert n_mism == 0, (k, n_mism)  # bit-exact sample indices / actor assignment on the reference goldens
     for k in ("features", "accumulation", "prop_depth_0", "prop_depth_1", "prop_weights_0"):
         assert rel_to_max(out[k], ref[k]) < 1e-4, (k, rel_to_max(out[k], ref[k]))
-    assert rel_to_max(out["depth"], ref["depth"]) < (5e-4 if beta >= 20 else 1e-4)
+    assert rel_to_max(out["depth"], ref["depth"]) < (2e-4 if beta >= 20 else 1e-4)
     for k in ("bins_s_1", "bins_s_2"):
-        assert (out[k].cpu() - ref[k]).abs().max().item() < 1e-5, k
+        assert (out[k].cpu() - ref[k]).abs().max().item() < 3e-6, k
+    # per-sample traces: tight where the sample sits exactly where the reference's does
+    edges_equal = out["bins_s_2"].cpu() == ref["bins_s_2"]
+    same_sample = edges_equal[:, :-1] & edges_equal[:, 1:]
+    assert same_sample.float().mean().item() > 0.05
     for k in ("sdf", "alpha", "field_feature"):
-        assert rel_to_max(out[k], ref[k]) < 2e-3, (k, rel_to_max(out[k], ref[k]))
+        a, b = out[k].cpu().float(), ref[k].float()
+        a = a.reshape(b.shape)
+        scale = b.abs().max().item()
+        err = (a - b).abs()
+        err = err.reshape(*same_sample.shape, -1).amax(-1)
+        assert err[same_sample].max().item() < 1e-5 * scale, (k, err[same_sample].max().item() / scale)
+        assert err.max().item() < 2e-3 * scale, (k, err.max().item() / scale)
 
 
 @pytest.mark.parametrize("mode", ["lane", "split", "tc", "ffma"])
@@ -82,21 +99,19 @@ def _live_case(backend, cfg, n_rays, seed, beta, sdf_bias, table_scale=1.0, n_ch
 
 
 def test_fused_render_vs_oracle_16_actors(backend):
-    """Config 3: 16 rigid actors, rays aimed at the boxes; discrete decisions must agree on >= 99.9 % of samples and
-    the rendered outputs on rays whose decisions agree must match to 1e-4."""
+    """Config 3: 16 rigid actors, rays aimed at the boxes.  Fresh random scene vs the live oracle: discrete decisions
+    must agree on >= 99.9 % of samples, and the rendered outputs of ALL rays (no agreement mask) must match to 1e-4."""
     cfg = nsb.small_config(n_actors=16, log2_main=16, log2_prop=14)
     out, ref = _live_case(backend, cfg, 2048, seed=21, beta=4.0, sdf_bias=0.5)
     n_hit = int((ref["actor_id_main"] >= 0).sum())
     assert n_hit > 100, n_hit  # the actor branch is really exercised
-    same = torch.ones(2048, dtype=torch.bool)
-    for k in ("inds_1", "inds_2", "actor_id_0", "actor_id_1", "actor_id_main"):
+    for k in ("actor_id_0", "actor_id_1", "actor_id_main"):  # actor assignment: exact
+        assert int((out[k].cpu().long() != ref[k].long()).sum()) == 0, k
+    for k in ("inds_1", "inds_2"):
         neq = out[k].cpu().long() != ref[k].long()
         assert neq.float().mean().item() <= 1e-3, (k, neq.float().mean().item())
-        same &= ~neq.any(dim=-1)
-    assert same.float().mean().item() > 0.98
     for k in ("features", "accumulation", "depth", "prop_depth_0", "prop_depth_1"):
-        a, b = out[k].cpu()[same], ref[k][same]
-        assert rel_to_max(a, b) < 1e-4, (k, rel_to_max(a, b))
+        assert rel_to_max(out[k], ref[k]) < 1e-4, (k, rel_to_max(out[k], ref[k]))
 
 
 def test_fused_render_vs_oracle_default_tables(backend):

@@ -37,6 +37,10 @@ def test_training_gradients_match_reference_golden(name):
     C.training_gradients_match_reference_golden(name, "cuda")
 
 
+def test_proposal_density_backward_clamps_like_trunc_exp():
+    C.proposal_density_backward_clamps_like_trunc_exp("cuda")
+
+
 def test_backward_stage_operators_match_torch_autograd():
     C.backward_stage_operators_match_torch_autograd("cuda")
 
