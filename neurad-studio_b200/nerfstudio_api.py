@@ -887,7 +887,8 @@ class NeuRADModel(nn.Module):
         for n, k in self._names:
             if k not in sd:
                 raise KeyError(f"reference state dict lacks {k}")
-            getattr(self, n).data.copy_(sd[k].to(getattr(self, n).dtype))
+            with torch.no_grad():  # in place on the tensor itself (not .data): bumps _version, which _bind() watches
+                getattr(self, n).copy_(sd[k].to(getattr(self, n).dtype))
         dec = {k[len("rgb_decoder."):]: v for k, v in sd.items() if k.startswith("rgb_decoder.")}
         if dec:  # the camera decoder is optional in a hot-path-only state dict
             self.rgb_decoder.load_state_dict(dec, strict=False)
