@@ -47,5 +47,25 @@ def build(force: bool = False, verbose: bool = False) -> str:
     return LIB_PATH
 
 
+def build_variant(name: str, defines=(), verbose: bool = False) -> str:
+    """A/B builds for GPU experiments (tools/perf_probe.py picks one with NFF_LIB=...): the same sources with extra -D
+    switches, written to lib/variants/libb200nerf_<name>.so.  Never loaded by the product."""
+    out_dir = os.path.join(LIB_DIR, "variants")
+    os.makedirs(out_dir, exist_ok=True)
+    out = os.path.join(out_dir, f"libb200nerf_{name}.so")
+    cmd = [_nvcc()] + NVCC_FLAGS + [f"-D{d}" for d in defines] + (["-Xptxas", "-v"] if verbose else []) + ["-o", out] + SOURCES
+    res = subprocess.run(cmd, cwd=CSRC, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
+    if verbose:
+        print(res.stderr)
+    return out
+
+
 if __name__ == "__main__":
-    print(build(force=True, verbose=True))
+    import sys
+
+    if len(sys.argv) > 1:  # python build.py <variant-name> [DEFINE=VALUE ...]
+        print(build_variant(sys.argv[1], sys.argv[2:], verbose=True))
+    else:
+        print(build(force=True, verbose=True))

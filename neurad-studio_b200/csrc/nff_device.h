@@ -209,7 +209,10 @@ NFF_D float blend_f(float a, float wa, float b, float wb) { return fmaf(a, wa, b
 NFF_D float level_weight(float res, float std) {
   const float t = fmaxf(fmul(fmul(res, 2.0f), std), 1.0f);
 #if NFF_FAST_RCP && !NFF_PARITY_STD && defined(__CUDACC__)
-  return __fdividef(1.0f, t);  // MUFU.RCP, <= 1 ulp for t in [1, 2^126)
+  float r;  // bare MUFU.RCP (<= 1 ulp; t >= 1, so neither the denormal guard of __fdividef nor a Newton step is needed;
+            // the value is the one __fdividef(1.0f, t) returns for t in [1, 2^126))
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(t));
+  return r;
 #else
   return frcp(t);
 #endif
@@ -224,32 +227,111 @@ NFF_D float trilerp_f(const float f[8], const Cell& c, float ix, float iy, float
   return blend_f(f0312, c.oz, f4756, iz);
 }
 
+// ---- fused-path addressing: byte offsets straight out of the hash --------------------------------------------------
+// The stage operator above exposes the reference's row indices; the fused kernels only need the ADDRESSES, and the
+// index arithmetic was a quarter of their instructions (profiles/r01_ncu_render_v10_split.txt: per corner xor3 + and +
+// zero-extend + 64-bit scale-and-add).  Here every hash term is pre-multiplied by the row size (a shift distributes over
+// xor, and (h & mask) << s == (h << s) & (mask << s) while log2(T) + s <= 32), so a corner costs one LOP3
+// ((hx ^ a) & maskb) and one 64-bit add.  The "ceil" corner is always floor + 1: where the reference's ceil equals its
+// floor (p integral) the interpolation offset is exactly 0, so the value read there is multiplied by 0 either way
+// (finite tables) -- same result, three compare/select pairs fewer per level.
+template <int SH>  // log2(bytes per table row): F = 1 -> 2, F = 4 -> 4
+struct CellB {
+  uint32_t hx, hy, hz;  // floor corner, pre-scaled
+  float ox, oy, oz;
+};
+template <int SH>
+NFF_D CellB<SH> grid_cell_b(float x, float y, float z, float res) {
+  const float px = fmul(x, res), py = fmul(y, res), pz = fmul(z, res);
+  const float fx = floorf(px), fy = floorf(py), fz = floorf(pz);
+  CellB<SH> c;
+  c.hx = (uint32_t)(int32_t)fx << SH;
+  c.hy = (uint32_t)(int32_t)fy * (2654435761u << SH);
+  c.hz = (uint32_t)(int32_t)fz * (805459861u << SH);
+  c.ox = fsub(px, fx);
+  c.oy = fsub(py, fy);
+  c.oz = fsub(pz, fz);
+  return c;
+}
+// byte offsets of the 8 corners in the reference's order (ccc, cfc, ffc, fcc, ccf, cff, fff, fcf)
+NFF_D uint32_t xor_and(uint32_t a, uint32_t b, uint32_t m) {  // (a ^ b) & m: one LOP3
+#if defined(__CUDACC__)
+  uint32_t d;
+  asm("lop3.b32 %0, %1, %2, %3, 0x28;" : "=r"(d) : "r"(a), "r"(b), "r"(m));
+  return d;
+#else
+  return (a ^ b) & m;
+#endif
+}
+template <int SH>
+NFF_D void cell_offsets_b(const CellB<SH>& c, uint32_t maskb, uint32_t r[8]) {
+  const uint32_t hx1 = c.hx + (1u << SH), hy1 = c.hy + (2654435761u << SH), hz1 = c.hz + (805459861u << SH);
+  const uint32_t a11 = hy1 ^ hz1, a01 = c.hy ^ hz1, a10 = hy1 ^ c.hz, a00 = c.hy ^ c.hz;
+  r[0] = xor_and(hx1, a11, maskb);
+  r[1] = xor_and(hx1, a01, maskb);
+  r[2] = xor_and(c.hx, a01, maskb);
+  r[3] = xor_and(c.hx, a11, maskb);
+  r[4] = xor_and(hx1, a10, maskb);
+  r[5] = xor_and(hx1, a00, maskb);
+  r[6] = xor_and(c.hx, a00, maskb);
+  r[7] = xor_and(c.hx, a10, maskb);
+}
+// base + zero-extended 32-bit byte offset as ONE instruction (IMAD.WIDE.U32 off * 1 + base)
+template <class T>
+NFF_D T ldg_at(const char* base, uint32_t byte_off) {
+#if defined(__CUDACC__)
+  uint64_t addr;
+  asm("mad.wide.u32 %0, %1, 1, %2;" : "=l"(addr) : "r"(byte_off), "l"((uint64_t)base));
+  return ldg(reinterpret_cast<const T*>(addr));
+#else
+  return ldg(reinterpret_cast<const T*>(base + byte_off));
+#endif
+}
+// byte address of level l's first row, opaque to the compiler so that it is formed once per level and not re-associated
+// into every corner's offset
+NFF_D const char* level_base(const void* table, uint32_t l, uint32_t T, int row_bytes) {
+  const char* p = reinterpret_cast<const char*>(table) + (size_t)l * T * (size_t)row_bytes;
+#if defined(__CUDACC__)
+  asm("" : "+l"(p));
+#endif
+  return p;
+}
+template <int SH>
+NFF_D float trilerp_b(const float f[8], const CellB<SH>& c, float ix, float iy, float iz) {
+  float f03 = blend_f(f[0], c.ox, f[3], ix);
+  float f12 = blend_f(f[1], c.ox, f[2], ix);
+  float f56 = blend_f(f[5], c.ox, f[6], ix);
+  float f47 = blend_f(f[4], c.ox, f[7], ix);
+  float f0312 = blend_f(f03, c.oy, f12, iy);
+  float f4756 = blend_f(f47, c.oy, f56, iy);
+  return blend_f(f0312, c.oz, f4756, iz);
+}
+
 // One grid, all levels, F = 1, fused with the proposal field's Linear(L,1) decoder:
 //   sum_l dec[l] * interp_l * 1/max(1, 2*res_l*std)      (neurad_encoding.py:297-304, neurad_field.py:201,211)
-// The level loop stays rolled (one copy of the ~90-instruction body) so the kernel fits the instruction cache.
 template <int L, int G>
 NFF_D float encode_f1_dot(const float* NFF_RESTRICT table, const Grid& gr, Gauss g, const float* NFF_RESTRICT dec) {
   // levels in groups of G: the 8*G gathers of a group are issued back to back before the first is consumed
-  // (the kernel is latency-bound on these loads: profiles/r01_ncu_render_v3.txt, stall_long_sb)
   static_assert(L % G == 0, "group size must divide the level count");
   float acc = 0.0f;
+  const uint32_t maskb = gr.mask << 2;
 #pragma unroll
   for (int l0 = 0; l0 < L; l0 += G) {
-    Cell c[G];
+    CellB<2> c[G];
     float f[G][8];
 #pragma unroll
     for (int j = 0; j < G; ++j) {
-      c[j] = grid_cell(g.x, g.y, g.z, gr.res[l0 + j]);
+      c[j] = grid_cell_b<2>(g.x, g.y, g.z, gr.res[l0 + j]);
       uint32_t r[8];
-      cell_rows(c[j], gr.mask, r);
-      const float* base = table + (size_t)(l0 + j) * gr.T;
+      cell_offsets_b<2>(c[j], maskb, r);
+      const char* base = level_base(table, l0 + j, gr.T, 4);
 #pragma unroll
-      for (int k = 0; k < 8; ++k) f[j][k] = ldg(base + r[k]);
+      for (int k = 0; k < 8; ++k) f[j][k] = ldg_at<float>(base, r[k]);
     }
 #pragma unroll
     for (int j = 0; j < G; ++j) {
       float w = level_weight(gr.res[l0 + j], g.std);
-      float v = trilerp_f(f[j], c[j], 1.0f - c[j].ox, 1.0f - c[j].oy, 1.0f - c[j].oz);
+      float v = trilerp_b<2>(f[j], c[j], 1.0f - c[j].ox, 1.0f - c[j].oy, 1.0f - c[j].oz);
       acc = fmaf(fmul(v, w), ldg(dec + l0 + j), acc);
     }
   }

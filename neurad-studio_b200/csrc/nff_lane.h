@@ -154,31 +154,32 @@ NFF_D float lane_proposal_density(const FieldGrids& fg, const LaneScratch& sc, i
 
 // F = 4 grid into the CTA's shared panel column [4l+f][tid] (rolled level loop: small code)
 NFF_D void encode_f4_col(const float* NFF_RESTRICT table, const Grid& gr, int L, Gauss g, float* x /* = panel + tid */) {
+  const uint32_t maskb = gr.mask << 4;
 #pragma unroll 2
   for (int l = 0; l < L; ++l) {
     const float res = gr.res[l];
-    Cell c = grid_cell(g.x, g.y, g.z, res);
+    const CellB<4> c = grid_cell_b<4>(g.x, g.y, g.z, res);
     uint32_t r[8];
-    cell_rows(c, gr.mask, r);
-    const float4* base = reinterpret_cast<const float4*>(table) + (size_t)l * gr.T;
+    cell_offsets_b<4>(c, maskb, r);
+    const char* base = level_base(table, l, gr.T, 16);
     float4 v[8];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) v[k] = ldg(base + r[k]);
+    for (int k = 0; k < 8; ++k) v[k] = ldg_at<float4>(base, r[k]);
     float w = level_weight(res, g.std);
     const float ix = 1.0f - c.ox, iy = 1.0f - c.oy, iz = 1.0f - c.oz;
     float f[8];
 #pragma unroll
     for (int k = 0; k < 8; ++k) f[k] = v[k].x;
-    x[(4 * l + 0) * kLaneThreads] = fmul(trilerp_f(f, c, ix, iy, iz), w);
+    x[(4 * l + 0) * kLaneThreads] = fmul(trilerp_b<4>(f, c, ix, iy, iz), w);
 #pragma unroll
     for (int k = 0; k < 8; ++k) f[k] = v[k].y;
-    x[(4 * l + 1) * kLaneThreads] = fmul(trilerp_f(f, c, ix, iy, iz), w);
+    x[(4 * l + 1) * kLaneThreads] = fmul(trilerp_b<4>(f, c, ix, iy, iz), w);
 #pragma unroll
     for (int k = 0; k < 8; ++k) f[k] = v[k].z;
-    x[(4 * l + 2) * kLaneThreads] = fmul(trilerp_f(f, c, ix, iy, iz), w);
+    x[(4 * l + 2) * kLaneThreads] = fmul(trilerp_b<4>(f, c, ix, iy, iz), w);
 #pragma unroll
     for (int k = 0; k < 8; ++k) f[k] = v[k].w;
-    x[(4 * l + 3) * kLaneThreads] = fmul(trilerp_f(f, c, ix, iy, iz), w);
+    x[(4 * l + 3) * kLaneThreads] = fmul(trilerp_b<4>(f, c, ix, iy, iz), w);
   }
 }
 

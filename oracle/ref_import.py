@@ -29,6 +29,17 @@ _STUBS = [
 ]
 
 
+# further absent third-party packages that only the FULL method registry (nerfstudio.configs.method_configs: every
+# dataparser and model of the reference) pulls in; needed by tests/test_reference_plugin.py, not by the golden generators
+_STUBS_FULL = [
+    "av2", "av2.utils", "av2.utils.io", "av2.datasets", "av2.datasets.sensor", "av2.datasets.sensor.av2_sensor_dataloader",
+    "av2.datasets.sensor.constants", "av2.geometry", "av2.geometry.geometry", "av2.structures", "av2.structures.sweep",
+    "nuscenes", "nuscenes.nuscenes", "pandaset", "zod", "zod.constants", "zod.data_classes", "zod.data_classes.box",
+    "zod.data_classes.sensor", "pathos", "pathos.helpers", "gsplat.strategy", "gsplat.strategy.ops", "splines",
+    "splines.quaternion", "imageio", "imageio.v3", "torchmetrics.image.fid",
+]
+
+
 class _Anything:
     """Attribute sink: any attribute / call / subscript returns another sink (enough for import-time use)."""
 
@@ -61,11 +72,12 @@ def reference_available() -> bool:
     return os.path.isdir(os.path.join(REFERENCE_ROOT, "nerfstudio"))
 
 
-def install() -> None:
-    """Install the stubs and make ``import nerfstudio`` resolve to the reference tree."""
+def install(full: bool = False) -> None:
+    """Install the stubs and make ``import nerfstudio`` resolve to the reference tree.  ``full``: also the packages the
+    complete method registry imports (``nerfstudio.configs.method_configs`` / ``nerfstudio.plugins.registry``)."""
     if not reference_available():
         raise RuntimeError(f"reference tree not found at {REFERENCE_ROOT} (only present in the build container)")
-    for name in _STUBS:
+    for name in _STUBS + (_STUBS_FULL if full else []):
         if name in sys.modules:
             continue
         if name == "tinycudann":
