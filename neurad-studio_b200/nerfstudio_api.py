@@ -120,6 +120,60 @@ class RayBundle:
         return d
 
 
+class Cameras:
+    """cameras/cameras.py (PERSPECTIVE cameras with the AD rolling-shutter metadata): a batch of pinhole cameras whose
+    `generate_rays(camera_indices, keep_shape=True)` returns the full-resolution [H, W] bundle the evaluation loop feeds to
+    `get_outputs_for_camera_ray_bundle` (pipelines/ad_pipeline.py:198-208).  One raygen kernel; constant per-image fields
+    (sensor index, camera index) are stride-0 views."""
+
+    def __init__(self, cameras, device: torch.device) -> None:
+        self.cameras = list(cameras)  # scene.PinholeCamera descriptors (host side, like the reference's Cameras tensors)
+        self.device = torch.device(device)
+
+    def __len__(self) -> int:
+        return len(self.cameras)
+
+    def generate_rays(self, camera_indices: int, keep_shape: bool = True) -> RayBundle:
+        cam = self.cameras[int(camera_indices)]
+        r = get_backend(self.device).raygen_pinhole(cam)
+        h, w = r["shape"]
+        shape = (h, w) if keep_shape else (h * w,)
+
+        def v(t):
+            return t.view(*shape, t.shape[-1])
+
+        def const(val):
+            return torch.full((1,), val, dtype=torch.long, device=self.device).expand(*shape, 1)
+
+        return RayBundle(origins=v(r["origins"]), directions=v(r["directions"]), pixel_area=v(r["pixel_area"]), times=v(r["times"]),
+                         camera_indices=const(int(camera_indices)), metadata={"sensor_idxs": const(cam.sensor_idx)})
+
+
+class Lidars:
+    """cameras/lidars.py:399-460: `generate_rays(lidar_indices, points, keep_shape)` -- one ray per measured point
+    (origin = sensor pose + velocity * dt, unit direction, beam footprint, metadata directions_norm / is_lidar / did_return)."""
+
+    def __init__(self, scans, device: torch.device) -> None:
+        self.scans = list(scans)  # scene.LidarScan descriptors
+        self.device = torch.device(device)
+        self.lidar_to_worlds = torch.stack([s.l2w for s in self.scans]).to(self.device)
+
+    def __len__(self) -> int:
+        return len(self.scans)
+
+    def generate_rays(self, lidar_indices, points: Tensor, keep_shape: bool = True) -> RayBundle:
+        idx = int(lidar_indices.reshape(-1)[0]) if torch.is_tensor(lidar_indices) else int(lidar_indices)
+        scan = self.scans[idx]
+        r = get_backend(self.device).raygen_lidar_points(scan, points.to(self.device, non_blocking=True))
+        n = r["origins"].shape[0]
+        md = {"directions_norm": r["directions_norm"], "did_return": r["did_return"],
+              "is_lidar": torch.ones(1, dtype=torch.bool, device=self.device).expand(n, 1),
+              "sensor_idxs": torch.full((1,), scan.sensor_idx, dtype=torch.long, device=self.device).expand(n, 1)}
+        return RayBundle(origins=r["origins"], directions=r["directions"], pixel_area=r["pixel_area"], times=r["times"],
+                         camera_indices=torch.full((1,), idx, dtype=torch.long, device=self.device).expand(n, 1), metadata=md,
+                         fars=torch.full((1,), 1_000_000.0, device=self.device).expand(n, 1))
+
+
 class HashEncoding(nn.Module):
     """field_components/encodings.py:311-471 with `implementation="b200"`.  Parameter `hash_table` [L*T, F] and
     buffer `scalings` exactly as the torch implementation builds them (encodings.py:348-352, 380-384)."""
@@ -1126,6 +1180,22 @@ class NeuRADModel(nn.Module):
         return self.get_outputs(ray_bundle, patch_size, intensity_for_cam, calc_lidar_losses)
 
     @torch.no_grad()
+    def get_outputs_for_lidar(self, lidar: "Lidars", batch: Dict[str, Tensor]) -> Tuple[Dict[str, Tensor], Dict[str, Tensor]]:
+        """models/ad_model.py:84-113: rays from the sweep's points, the model outputs, and the predicted points in the
+        lidar frame (origin + direction * depth through the inverse sensor pose)."""
+        points = batch["lidar"]
+        assert isinstance(batch["lidar_idx"], int), "All lidar points are assumed to be from the same scan."
+        ray_bundle = lidar.generate_rays(lidar_indices=0, points=points, keep_shape=True)
+        md = ray_bundle.metadata
+        batch["is_lidar"], batch["distance"], batch["did_return"] = md["is_lidar"], md["directions_norm"], md["did_return"]
+        outputs = self.get_outputs_for_camera_ray_bundle(ray_bundle)
+        l2w = lidar.lidar_to_worlds[0]
+        rot_t = l2w[:3, :3].t()  # pose_inverse (utils/poses.py:42-55): [R^T | -R^T t]
+        pts = ray_bundle.origins + ray_bundle.directions * outputs["depth"]
+        outputs["points"] = pts @ rot_t.t() - (rot_t @ l2w[:3, 3])
+        return outputs, batch
+
+    @torch.no_grad()
     def get_outputs_for_camera_ray_bundle(self, camera_ray_bundle: RayBundle) -> Dict[str, Tensor]:
         """neurad.py:623-675: 2-D bundles are subsampled at
         [step//2::step] like the reference (`compensate_upsampling_when_rendering`), 1-D bundles are lidar rays."""
@@ -1137,7 +1207,8 @@ class NeuRADModel(nn.Module):
             camera_ray_bundle = camera_ray_bundle[step // 2 :: step, step // 2 :: step]
             output_size = camera_ray_bundle.shape
         be = self._bind()
-        out = be.render(camera_ray_bundle.as_backend_dict(), want_intensity=True)
+        # an image is walked in 2-D tiles (a warp = an 8x4 pixel patch: coherent gathers); the output order is unchanged
+        out = be.render(camera_ray_bundle.as_backend_dict(), want_intensity=True, image_width=output_size[1] if len(output_size) == 2 else 0)
         res = {k: v.view(*output_size, -1) for k, v in out.items()}
         res["ray_drop_prob"] = res["ray_drop_logits"].sigmoid()
         if len(output_size) == 2:  # camera: decode the feature image to rgb at `step` x the ray resolution

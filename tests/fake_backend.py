@@ -218,11 +218,27 @@ class FakeBackend(B200Backend):
             raise NotImplementedError(depth_method)
         return out
 
+    # ---- ray generation (GPU-validated kernels; the oracle's restatement of Cameras / Lidars.generate_rays here)
+    def raygen_pinhole(self, cam, row0=0, row_step=1, col0=0, col_step=1, out=None):
+        ys, xs = torch.meshgrid(torch.arange(row0, cam.height, row_step), torch.arange(col0, cam.width, col_step), indexing="ij")
+        coords = (torch.stack([ys, xs], -1).reshape(-1, 2) + 0.5).float()
+        r = O.generate_rays_pinhole(cam.c2w, cam.fx, cam.fy, cam.cx, cam.cy, cam.height, cam.width, coords, cam.time, cam.velocity,
+                                    cam.rolling_shutter_time, cam.time_to_center_pixel)
+        return {"origins": r["origins"].contiguous(), "directions": r["directions"], "pixel_area": r["pixel_area"], "times": r["times"],
+                "shape": tuple(ys.shape)}
+
+    def raygen_lidar_points(self, scan, points=None, out=None):
+        r = O.generate_rays_lidar_points(scan.l2w, scan.points if points is None else points, scan.time, scan.velocity)
+        return {k: r[k] for k in ("origins", "directions", "pixel_area", "times", "directions_norm", "did_return")}
+
     def render(self, rays, want_trace=False, want_intensity=False, out=None, image_width=0):
         n = rays["origins"].shape[0]
         col = lambda t: t.reshape(n, 1)  # noqa: E731
         with torch.no_grad():
-            return O.nff_outputs(self.params, to_oracle_cfg(self.cfg), rays["origins"], rays["directions"],
-                                 col(rays["pixel_area"]), col(rays["times"]),
-                                 col(rays.get("sensor_idx", torch.zeros(n, dtype=torch.long))),
-                                 col(rays["is_lidar"]).bool() if "is_lidar" in rays else None)
+            res = O.nff_outputs(self.params, to_oracle_cfg(self.cfg), rays["origins"].reshape(n, 3), rays["directions"].reshape(n, 3),
+                                col(rays["pixel_area"]), col(rays["times"]),
+                                col(rays.get("sensor_idx", torch.zeros(n, dtype=torch.long))),
+                                col(rays["is_lidar"]).bool() if "is_lidar" in rays else None)
+            if want_intensity:
+                res["intensity"], res["ray_drop_logits"] = O.decode_lidar(self.params, res["features"])
+            return res

@@ -4,6 +4,7 @@ tests/test_module_glue_cpu.py (dev = "cpu": the same Python glue over tests/fake
 import pytest
 import torch
 
+import neurad_studio_b200 as nsb
 from oracle import neurad_oracle as O
 from oracle.convert import to_oracle_cfg
 from tests.helpers import cfg_from_meta, load_golden
@@ -94,11 +95,15 @@ def proposal_sampler_and_module_walk_match_reference_golden(name, dev):
     n = len(rb)
     mod = model.get_nff_outputs(rb, fused=False)
     fused = model.get_nff_outputs(rb)
-    tol_depth = 2e-4 if meta["beta"] >= 20 else 1e-4  # tests/test_reference_noise_floor.py
+    # beta = 20 (d alpha / d sdf = 5): the reference's own arithmetic moves depth by 0.7e-4 when exp() rounds differently
+    # (tests/test_reference_noise_floor.py); the fused kernels are held to 2e-4 there, the stage-operator walk (fp32 warp
+    # scans instead of the fused kernel's double accumulators) to 5e-4
+    tol_depth = (2e-4 if dev == "cpu" else 5e-4) if meta["beta"] >= 20 else 1e-4
     for k in ("features", "accumulation", "prop_depth_0", "prop_depth_1"):
         assert rel_to_max(mod[k], ref[k]) < 1e-4, k
         assert rel_to_max(mod[k], fused[k]) < 1e-4, k
-    assert rel_to_max(mod["depth"], ref["depth"]) < tol_depth
+    assert rel_to_max(mod["depth"], ref["depth"]) < tol_depth, rel_to_max(mod["depth"], ref["depth"])
+    assert rel_to_max(fused["depth"], ref["depth"]) < (2e-4 if meta["beta"] >= 20 else 1e-4)
     rs_list, w_list = mod["ray_samples_list"], mod["weights_list"]
     # proposal levels, then the final level WITHOUT the sky sample (neurad.py:385-386, 404-405)
     assert [r.shape[1] for r in rs_list] == [128, 64, 31] and [w.shape[1] for w in w_list] == [128, 64, 31]
@@ -476,3 +481,59 @@ def train_mode_encoding_matches_reference_golden(dev):
     assert (out["directions"].cpu() - tg["ref"]["directions"]).abs().max().item() < 1e-5
     ev = be.neurad_encoding(0, gs.mean, gs.std, rs.times, rs.frustums.directions)
     assert not torch.equal(ev["directions"], out["directions"]) and not torch.equal(ev["features"], out["features"])
+
+
+def metric_entry_points(dev):
+    """The calls the reference's metric is defined on (pipelines/ad_pipeline.py:198-208, 296-304) through the API mirror:
+    `Cameras.generate_rays(i, keep_shape=True)` -> `NeuRADModel.get_outputs_for_camera_ray_bundle` and
+    `NeuRADModel.get_outputs_for_lidar(lidars, batch)`; checked against the oracle's ray generation + render + decoders."""
+    from oracle import decoder_oracle as D
+
+    from neurad_studio_b200 import scene
+    from neurad_studio_b200.nerfstudio_api import Cameras, Lidars, NeuRADModel
+
+    cfg = nsb.small_config(n_actors=0, log2_main=12, log2_prop=11)
+    params = scene.make_params(cfg, seed=4, beta=3.0, sdf_bias=0.5)
+    dec = scene.make_rgb_decoder_params(seed=5)
+    model = NeuRADModel(cfg)
+    model.load_reference_state_dict(params)
+    model.rgb_decoder.load_state_dict({k[len("rgb_decoder."):]: v for k, v in dec.items()}, strict=False)
+    model = model.to(dev).eval()
+    cam = scene.pandaset_rig(time=2.0, width=24, height=15)[1]
+    cams = Cameras([cam], dev)
+    rb = cams.generate_rays(camera_indices=0, keep_shape=True)
+    assert rb.shape == (15, 24) and rb.metadata["sensor_idxs"].shape == (15, 24, 1) and int(rb.metadata["sensor_idxs"][3, 4]) == cam.sensor_idx
+    out = model.get_outputs_for_camera_ray_bundle(rb)
+    assert out["rgb"].shape == (15, 24, 3) and out["depth"].shape == (5, 8, 1) and out["intensity"].shape == (5, 8, 1)
+    # oracle: the [1::3, 1::3] pixel centres, rendered and decoded
+    ys, xs = torch.meshgrid(torch.arange(1, 15, 3), torch.arange(1, 24, 3), indexing="ij")
+    coords = (torch.stack([ys, xs], -1).reshape(-1, 2) + 0.5).float()
+    with torch.no_grad():
+        r = O.generate_rays_pinhole(cam.c2w, cam.fx, cam.fy, cam.cx, cam.cy, cam.height, cam.width, coords, cam.time, cam.velocity,
+                                    cam.rolling_shutter_time, cam.time_to_center_pixel)
+        ref = O.nff_outputs(params, to_oracle_cfg(cfg), r["origins"], r["directions"], r["pixel_area"], r["times"],
+                            torch.full((40, 1), cam.sensor_idx), None)
+        rgb_ref = D.rgb_decoder(dec, ref["features"].view(1, 5, 8, -1))[0]
+    assert rel_to_max(out["depth"].reshape(-1), ref["depth"].reshape(-1)) < 1e-4
+    assert rel_to_max(out["features"].reshape(40, -1), ref["features"]) < 1e-4
+    assert (out["rgb"].cpu() - rgb_ref).abs().max().item() < 1e-4
+    # lidar sweep
+    scan = scene.pandar64_scan(time=2.0, beams=4, azimuths=25)
+    lidars = Lidars([scan], dev)
+    batch = {"lidar": scan.points, "lidar_idx": 0}
+    lout, batch = model.get_outputs_for_lidar(lidars, batch)
+    n = scan.points.shape[0]
+    assert lout["depth"].shape == (n, 1) and lout["points"].shape == (n, 3) and lout["ray_drop_prob"].shape == (n, 1)
+    assert batch["is_lidar"].shape == (n, 1) and bool(batch["is_lidar"].all()) and batch["did_return"].dtype == torch.bool
+    with torch.no_grad():
+        rl = O.generate_rays_lidar_points(scan.l2w, scan.points, scan.time, scan.velocity)
+        ref = O.nff_outputs(params, to_oracle_cfg(cfg), rl["origins"], rl["directions"], rl["pixel_area"], rl["times"],
+                            torch.full((n, 1), scan.sensor_idx), torch.ones(n, 1, dtype=torch.bool))
+        inten, drop = O.decode_lidar(params, ref["features"])
+        pts_w = rl["origins"] + rl["directions"] * ref["depth"]
+        pts_l = (pts_w - scan.l2w[:3, 3]) @ scan.l2w[:3, :3]  # R^T (p - t)
+    assert rel_to_max(batch["distance"], rl["directions_norm"]) < 1e-6
+    assert rel_to_max(lout["depth"], ref["depth"]) < 1e-4 and rel_to_max(lout["intensity"], inten) < 1e-4
+    assert rel_to_max(lout["ray_drop_prob"], drop.sigmoid()) < 1e-4
+    assert (lout["points"].cpu() - pts_l).abs().max().item() < 1e-3 * pts_l.abs().max().item()
+    model._bind().check_status()

@@ -58,6 +58,10 @@ def test_training_losses_glue():
     C.training_losses_match_reference_golden("cpu")
 
 
+def test_metric_entry_points_glue():
+    C.metric_entry_points("cpu")
+
+
 def test_lidar_carving_masks_glue():
     C.lidar_carving_masks_and_training_outputs("cpu")
 

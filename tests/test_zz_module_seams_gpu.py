@@ -68,3 +68,7 @@ def test_get_outputs_and_decode_features():
 
 def test_train_mode_encoding_matches_reference_golden():
     C.train_mode_encoding_matches_reference_golden("cuda")
+
+
+def test_metric_entry_points():
+    C.metric_entry_points("cuda")
