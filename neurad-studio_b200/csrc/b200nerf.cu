@@ -193,6 +193,22 @@ __device__ __forceinline__ bool lane_unit_ray(const RenderParams& P, int64_t uni
   return active;
 }
 
+// Work distribution of the two-stage kernels.  The unit of work is a PATCH = the 32 rays of one warp (an 8x4 pixel patch of a
+// 32x16 tile when the caller passes image_width, else 32 consecutive rays); patches are numbered tile by tile, so consecutive
+// patches are spatial neighbours.  Every CTA owns a contiguous, balanced range of patches (sizes differ by at most one) and
+// hands them out round-robin to its warps (sampling: no CTA-level synchronisation at all) or to its 128-ray warp groups
+// (shading: one tensor-core tile = 4 consecutive patches).  With whole 512-ray CTA units, a 230 400-ray image is 460 units
+// on 148 (x2) resident CTAs: a few SMs got 4 units where the others got 3 and the launch lasted 4/3.1 of its balanced time;
+// with patches every SM gets 48.6 +- 0.5 of them.
+__device__ __forceinline__ int64_t lane_patches(const RenderParams& P) {
+  return P.rays.image_width > 0 ? lane_units(P) * (kLaneThreads / 32) : (P.n_rays + 31) / 32;
+}
+__device__ __forceinline__ bool lane_patch_ray(const RenderParams& P, int64_t patch, int lane_, int64_t* ray_out) {
+  constexpr int kPatchesPerUnit = kLaneThreads / 32;
+  // same mapping as lane_unit_ray with (unit, warp) = (patch / 16, patch % 16)
+  return lane_unit_ray(P, patch / kPatchesPerUnit, (int)(patch % kPatchesPerUnit) * 32 + lane_, ray_out);
+}
+
 // Two-stage variant of the ray-per-lane path.  Stage 1 (sampling: both proposal rounds) needs neither TMEM nor shared
 // memory and fits 64 registers, so it runs at 32 warps/SM with the whole 228 KB as L1; stage 2 (main field + MLPs +
 // compositing) is the tensor-core kernel at 16 warps/SM.  The hand-over is 33 spacing edges per ray ([edge][ray],
@@ -203,11 +219,13 @@ __device__ __forceinline__ bool lane_unit_ray(const RenderParams& P, int64_t uni
 __global__ void __launch_bounds__(kLaneThreads, NFF_SAMPLE_CTAS) nff_sample_lane_kernel(const __grid_constant__ RenderParams P,
                                                                                         float* __restrict__ scratch,
                                                                                         float* __restrict__ handoff) {
-  const int tid = threadIdx.x;
+  const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane_ = tid & 31;
   const LaneScratch sc = lane_scratch_of(scratch, blockIdx.x);
-  for (int64_t unit = blockIdx.x; unit < lane_units(P); unit += gridDim.x) {
+  const int64_t n_patches = lane_patches(P);
+  const int64_t p0 = n_patches * blockIdx.x / gridDim.x, p1 = n_patches * (blockIdx.x + 1) / gridDim.x;
+  for (int64_t patch = p0 + warp; patch < p1; patch += kLaneThreads / 32) {
     int64_t ray;
-    const bool active = lane_unit_ray(P, unit, tid, &ray);
+    const bool active = lane_patch_ray(P, patch, lane_, &ray);
     const LaneRay R = lane_ray_setup(P, sc, tid, ray);
     // inactive lanes write their (discarded) edges into the slab column instead of another ray's hand-over column
     float* col = active ? handoff + ray : sc.bins2 + tid;
@@ -243,9 +261,13 @@ __global__ void __launch_bounds__(kLaneThreads, kLaneCtasPerSm) nff_shade_lane_k
   mlp.core.status = P.status;
   const LaneScratch sc = lane_scratch_of(scratch, blockIdx.x);
   mlp.geo_park = NFF_PANEL_GLOBAL ? sc.panel : geo_park;
-  for (int64_t unit = blockIdx.x; unit < lane_units(P); unit += gridDim.x) {
+  // a warp group (one 128-row tensor-core tile) renders 4 consecutive patches; the groups of a CTA only meet at the two
+  // block barriers around the loop, inside it they synchronise among their own 4 warps (named barriers, mbarriers)
+  const int64_t n_groups = (lane_patches(P) + 3) / 4;
+  const int64_t g0 = n_groups * blockIdx.x / gridDim.x, g1 = n_groups * (blockIdx.x + 1) / gridDim.x;
+  for (int64_t gu = g0 + group; gu < g1; gu += kLaneThreads / 128) {
     int64_t ray;
-    const bool active = lane_unit_ray(P, unit, tid, &ray);
+    const bool active = lane_patch_ray(P, gu * 4 + (warp & 3), tid & 31, &ray);
     const LaneRay R = lane_ray_setup(P, sc, tid, ray);
     shade_ray_lane(P, sc, R, mlp, tid, ray, active, handoff + ray, P.n_rays);
   }
@@ -1219,9 +1241,13 @@ int b200nerf_nff_render_fwd(b200nerf_ctx* c, const b200nerf_rays* rays, int64_t 
         const int64_t W = rays->image_width, H = (cnt + W - 1) / W;
         need = ((W + 31) / 32) * ((H + kLaneThreads / 32 - 1) / (kLaneThreads / 32));
       }
+      // persistent grids: every resident CTA gets a balanced share of the patches (see lane_patches); bundles with fewer
+      // patches than warps still spread over all SMs
       const int64_t max_a = (int64_t)c->sm_count * NFF_SAMPLE_CTAS, max_b = (int64_t)c->sm_count * kLaneCtasPerSm;
-      nff_sample_lane_kernel<<<(int)(need < max_a ? need : max_a), kLaneThreads, 0, st>>>(Q, c->d_lane_scratch, c->d_handoff);
-      nff_shade_lane_kernel<<<(int)(need < max_b ? need : max_b), kLaneThreads, smem, st>>>(Q, c->d_lane_scratch, c->d_handoff);
+      const int64_t patches = rays->image_width > 0 ? need * (kLaneThreads / 32) : (cnt + 31) / 32, groups = (patches + 3) / 4;
+      const int64_t grid_a = patches < max_a ? patches : max_a, grid_b = groups < max_b ? groups : max_b;
+      nff_sample_lane_kernel<<<(int)grid_a, kLaneThreads, 0, st>>>(Q, c->d_lane_scratch, c->d_handoff);
+      nff_shade_lane_kernel<<<(int)grid_b, kLaneThreads, smem, st>>>(Q, c->d_lane_scratch, c->d_handoff);
     }
   } else if (c->mlp_mode == 2) {
     const size_t smem = (sizeof(TcShared) + 127) / 128 * 128 + (NFF_PANEL_GLOBAL ? 0 : sizeof(float) * kNff * kLaneThreads);

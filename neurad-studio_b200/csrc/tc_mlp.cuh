@@ -11,6 +11,10 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#ifndef NFF_MBAR_HINT
+#define NFF_MBAR_HINT 0  // ns; 0 = plain try_wait
+#endif
+
 namespace tc {
 
 // ------------------------------------------------------------------------------------------------ PTX wrappers
@@ -41,10 +45,18 @@ __device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity) {
     uint32_t ok;
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
+#if NFF_MBAR_HINT
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"  // suspend-time hint: sleep in hardware, not in the loop
+#else
         "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+#endif
         "selp.b32 %0, 1, 0, p;\n\t}"
         : "=r"(ok)
+#if NFF_MBAR_HINT
+        : "r"(addr), "r"(parity), "r"((uint32_t)NFF_MBAR_HINT)
+#else
         : "r"(addr), "r"(parity)
+#endif
         : "memory");
     if (ok) return true;
   }

@@ -148,7 +148,9 @@ _LIB = None
 
 
 def library_path() -> str:
-    return _build.LIB_PATH
+    """The in-tree library; B200NERF_LIB selects an A/B build of the same sources (neurad-studio_b200/build.py
+    build_variant) for GPU experiments."""
+    return os.environ.get("B200NERF_LIB") or _build.LIB_PATH
 
 
 def load(build_if_missing: bool = True) -> ctypes.CDLL:

@@ -1,5 +1,6 @@
 """torchrun --nproc-per-node N tools/check_peer_gather.py -- the fused render+gather (peer stores over NVLink from the
-render epilogue) must produce exactly what render + NCCL all_gather produces."""
+render epilogue) must produce exactly what render + NCCL all_gather produces, and both must equal the single-GPU render
+of the whole bundle (strong scaling: contiguous shards of one batch)."""
 import os
 import sys
 
@@ -46,6 +47,22 @@ def main():
     be.check_status()
     ok = all(torch.equal(pg.buf[k], ref[k]) for k in ref)
     be.set_peer_outputs(None)
+    # strong scaling: the gathered shards ARE the single-GPU render of the whole bundle (rays are independent and the
+    # kernels are batch-composition independent), bit for bit -- also through ShardedOutputs (NCCL gather into the
+    # buffer the kernel wrote its slice of)
+    from neurad_studio_b200.dist import ShardedOutputs
+
+    whole = be.render(rays)
+    torch.cuda.synchronize()
+    for k in ref:
+        ok = ok and torch.equal(pg.buf[k].reshape(n_total, -1), whole[k].reshape(n_total, -1))
+    so = ShardedOutputs(n_total, {"features": cfg.feature_dim, "depth": 1, "accumulation": 1}, dev)
+    loc2 = so.local()
+    loc2.update({k: torch.empty(b - a, 1, device=dev) for k in ("prop_depth_0", "prop_depth_1")})
+    be.render(mine, out=loc2)
+    gathered = so.gather()
+    for k in ref:
+        ok = ok and torch.equal(gathered[k], whole[k].reshape(n_total, -1))
     flag = torch.tensor([1 if ok else 0], device=dev)
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     if rank == 0:

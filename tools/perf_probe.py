@@ -33,6 +33,8 @@ r = {k: r[k] for k in ("origins", "directions", "pixel_area", "times")}
 r["sensor_idx"] = torch.full((n, 1), 6, dtype=torch.long, device="cuda")
 r["is_lidar"] = torch.ones(n, 1, dtype=torch.uint8, device="cuda")
 rays_list.append(r)
+if os.environ.get("ONE_IMAGE"):  # one 640x360 image (230 400 rays): the per-call size of get_outputs_for_camera_ray_bundle
+    rays_list = rays_list[:1]
 rays = {k: torch.cat([x[k] for x in rays_list]) for k in rays_list[0]}
 N = rays["origins"].shape[0]
 print("rays", N)
