@@ -51,6 +51,25 @@ typedef struct {
   float scalings[B200NERF_MAX_LEVELS];
 } b200nerf_grid_desc;
 
+/* tiny-cuda-nn `HashGrid` encoding layout -- what `HashEncoding(implementation="tcnn")` instantiates (encoding_config at
+ * field_components/encodings.py:386-401: n_levels, n_features_per_level, log2_hashmap_size, base_resolution = min_res,
+ * per_level_scale = growth_factor; `n_input_dims` 3, or 4 for the shared actor grid, neurad_encoding.py:110-131).  The caller
+ * computes the per-level constants (neurad-studio_b200/tcnn_compat.py: grid_layout): position scale (pos = fma(x, scale,
+ * 0.5)), vertices per axis, first entry and entry count in the flat parameter vector, and whether the level indexes linearly
+ * (res^n_dims fits) or hashes.  `scalings` is HashEncoding.scalings, which NeuRAD's anti-aliasing weights use in both modes
+ * (neurad_encoding.py:297-304).  PARITY UNPINNED: tiny-cuda-nn is absent here (oracle/tcnn_oracle.py). */
+typedef struct {
+  int32_t num_levels;
+  int32_t features_per_level;
+  int32_t n_input_dims;
+  float scale[B200NERF_MAX_LEVELS];
+  uint32_t resolution[B200NERF_MAX_LEVELS];
+  uint32_t offset[B200NERF_MAX_LEVELS];
+  uint32_t size[B200NERF_MAX_LEVELS];
+  uint8_t dense[B200NERF_MAX_LEVELS];
+  float scalings[B200NERF_MAX_LEVELS];
+} b200nerf_tcnn_grid_desc;
+
 const char* b200nerf_last_error(void);
 int b200nerf_version(void);
 
@@ -67,6 +86,21 @@ int b200nerf_set_field_grids(b200nerf_ctx* ctx, int field, const b200nerf_grid_d
                              const float* static_table, const b200nerf_grid_desc* actor_desc,
                              const float* const* actor_tables_host, int n_actors, float static_scale,
                              float actor_scale);
+
+/* The same field from a tcnn-trained checkpoint: `static_params` is `hashgrid.static_grid.tcnn_encoding
+ * .params` (flat fp32 master copy, rounded to fp16-representable values by the caller: tiny-cuda-nn casts to half at forward
+ * time), `actor_params` the ONE 4-D grid `hashgrid.actor_grids[0].tcnn_encoding.params` shared by all actors
+ * (neurad_encoding.py:270-281; NULL when n_actors == 0).  Selects the tcnn kernels for the fused renderer: the main field and
+ * the proposal fields used for sampling must then all be bound through this entry point; the SH basis follows tiny-cuda-nn's
+ * convention (evaluated at the direction, Condon-Shortley signs).  Bias-free FullyFusedMLP weights are passed to
+ * b200nerf_set_main_mlps / b200nerf_set_lidar_decoder with zero biases (tcnn_compat.py unpacks and un-pads them). */
+int b200nerf_set_field_grids_tcnn(b200nerf_ctx* ctx, int field, const b200nerf_tcnn_grid_desc* static_desc,
+                                  const float* static_params, const b200nerf_tcnn_grid_desc* actor_desc,
+                                  const float* actor_params, int n_actors, float static_scale, float actor_scale);
+
+/* Stage operator: tcnn.Encoding{HashGrid}.forward, x [P, n_input_dims] in [0,1] -> out [P, L*F] (level-major). */
+int b200nerf_tcnn_hashgrid_fwd(b200nerf_ctx* ctx, const b200nerf_tcnn_grid_desc* desc, const float* params, const float* x,
+                               float* out, int64_t n_points, void* stream);
 
 /* NeuRADProposalField.density_decoder = nn.Linear(L*F, 1, bias=False) (fields/neurad_field.py:201). */
 int b200nerf_set_proposal_decoder(b200nerf_ctx* ctx, int field, const float* weight, int in_dim);

@@ -11,6 +11,7 @@ from typing import Dict, Optional, Sequence, Tuple
 import torch
 
 from . import lib as _lib
+from . import tcnn_compat
 from .config import HashGridSettings, NeuRADConfig
 from .lib import ConvBnParams, ConvParams, RgbDecoderParams, FIELD_MAIN, FIELD_PROP0, FIELD_PROP1, GridDesc, Outputs, PeerOutputs, Rays, Trace, TRACE_FIELDS
 
@@ -109,8 +110,39 @@ class B200Backend:
         prefixes = {FIELD_MAIN: "field", FIELD_PROP0: "proposal_fields.0", FIELD_PROP1: "proposal_fields.1"}
         gcfgs = {FIELD_MAIN: cfg.grid, FIELD_PROP0: cfg.proposal_grid_1, FIELD_PROP1: cfg.proposal_grid_2}
         static_scale = float(p["static_scale"]) if "static_scale" in p else float(cfg.static_scale)
+        # a tcnn-trained checkpoint (implementation="tcnn", the reference's default): flat `tcnn_encoding.params` vectors in
+        # tiny-cuda-nn's layout instead of the torch twins' tensors (tcnn_compat.py)
+        tcnn = tcnn_compat.is_tcnn_state(p)
+        self.layout = "tcnn" if tcnn else "torch"
+        if tcnn and self.actor_grids_remapped:
+            raise NotImplementedError("dynamic_actors.actor_to_id re-assignment is not supported with the tiny-cuda-nn layout")
+        sizes = tcnn_compat.n_grid_params(cfg) if tcnn else {}
         for f, pre in prefixes.items():
             g = gcfgs[f]
+            if f != FIELD_MAIN:
+                w = self._dev(p[f"{pre}.density_decoder.weight"]).reshape(-1)
+                self._check(self.lib.b200nerf_set_proposal_decoder(self._h, f, _ptr(w), w.numel()))
+            if tcnn:
+                def flat(key):
+                    t = p[key].reshape(-1)
+                    if t.numel() != sizes[key]:
+                        raise ValueError(f"{key} has {t.numel()} parameters, the configured grid needs {sizes[key]}")
+                    return self._dev(tcnn_compat.half_round(t))
+
+                tab = flat(f"{pre}.hashgrid.static_grid.{tcnn_compat.TCNN_SUFFIX}")
+                self._keep[f"{pre}.static"] = tab
+                sc = p.get(f"{pre}.hashgrid.static_grid.scalings")
+                sd = tcnn_compat.grid_desc(tcnn_compat.layout_of(g.static, 3), sc if sc is not None else g.static.scalings())
+                ad = atab = None
+                if n_act > 0:
+                    atab = flat(f"{pre}.hashgrid.actor_grids.0.{tcnn_compat.TCNN_SUFFIX}")
+                    self._keep[f"{pre}.actors"] = atab
+                    sc = p.get(f"{pre}.hashgrid.actor_grids.0.scalings")
+                    ad = tcnn_compat.grid_desc(tcnn_compat.layout_of(g.actor, 4), sc if sc is not None else g.actor.scalings())
+                self._check(self.lib.b200nerf_set_field_grids_tcnn(
+                    self._h, f, ctypes.byref(sd), _ptr(tab), ctypes.byref(ad) if ad is not None else None, _ptr(atab), n_act,
+                    static_scale, float(g.actor_scale)))
+                continue
             tab = self._dev(p[f"{pre}.hashgrid.static_grid.hash_table"])
             self._keep[f"{pre}.static"] = tab
             sd = grid_desc(g.static, p.get(f"{pre}.hashgrid.static_grid.scalings"))
@@ -120,26 +152,32 @@ class B200Backend:
                 self._keep[f"{pre}.actors"] = tabs
                 arr = (ctypes.c_void_p * n_act)(*[t.data_ptr() for t in tabs])
                 ad = grid_desc(g.actor, p.get(f"{pre}.hashgrid.actor_grids.0.scalings"))
-            if f != FIELD_MAIN:
-                w = self._dev(p[f"{pre}.density_decoder.weight"]).reshape(-1)
-                self._check(self.lib.b200nerf_set_proposal_decoder(self._h, f, _ptr(w), w.numel()))
             self._check(
                 self.lib.b200nerf_set_field_grids(
                     self._h, f, ctypes.byref(sd), _ptr(tab), ctypes.byref(ad) if ad is not None else None,
                     arr, n_act, static_scale, float(g.actor_scale),
                 )
             )
-        names = ["field.mlp_geo.layers.0", "field.mlp_geo.layers.1", "field.mlp_feature.layers.0",
-                 "field.mlp_feature.layers.1", "field.mlp_feature.layers.2"]
-        ts = []
-        for nme in names:
-            ts += [self._dev(p[nme + ".weight"]), self._dev(p[nme + ".bias"])]
+        if tcnn and f"field.mlp_geo.{tcnn_compat.TCNN_SUFFIX}" in p:
+            # FullyFusedMLP: bias-free, widths padded to 16 (field_components/mlp.py:116-140) -> nn.Linear shapes, zero biases
+            hid, nff = cfg.geo_hidden_dim, cfg.nff_out_dim
+            ts = (tcnn_compat.mlp_tensors(p, "field.mlp_geo", cfg.grid.static.out_dim, hid, 2, nff + 1, self.device)
+                  + tcnn_compat.mlp_tensors(p, "field.mlp_feature", nff + 16, cfg.nff_hidden_dim, 3, nff, self.device))
+        else:
+            names = ["field.mlp_geo.layers.0", "field.mlp_geo.layers.1", "field.mlp_feature.layers.0",
+                     "field.mlp_feature.layers.1", "field.mlp_feature.layers.2"]
+            ts = []
+            for nme in names:
+                ts += [self._dev(p[nme + ".weight"]), self._dev(p[nme + ".bias"])]
         beta = float(p["field.sdf_to_density.beta"].abs().item() + 0.0001)  # model_components/utils.py:38-41
         self._check(self.lib.b200nerf_set_main_mlps(self._h, *[_ptr(t) for t in ts], beta))
         # the module-level NeuRADField.forward runs the same MLPs through b200nerf_mlp_fwd
         self._field_mlps = {"geo": (ts[0:4:2], ts[1:4:2]), "feature": (ts[4::2], ts[5::2])}
         self._beta = beta
-        if "lidar_decoder.layers.0.weight" in p:
+        if tcnn and f"lidar_decoder.{tcnn_compat.TCNN_SUFFIX}" in p:
+            ts = tcnn_compat.mlp_tensors(p, "lidar_decoder", cfg.feature_dim, 32, 3, 2, self.device)
+            self._check(self.lib.b200nerf_set_lidar_decoder(self._h, *[_ptr(t) for t in ts]))
+        elif "lidar_decoder.layers.0.weight" in p:
             ts = []
             for i in range(3):
                 ts += [self._dev(p[f"lidar_decoder.layers.{i}.weight"]), self._dev(p[f"lidar_decoder.layers.{i}.bias"])]
@@ -268,6 +306,16 @@ class B200Backend:
         self._check(self.lib.b200nerf_hashgrid_fwd(self._h, ctypes.byref(d), _ptr(table), _ptr(xs), _ptr(out), _ptr(idx), n, self._stream))
         out = out.reshape(*x.shape[:-1], -1)
         return (out, idx.reshape(*x.shape[:-1], g.num_levels, 8)) if want_indices else out
+
+    def tcnn_hashgrid_fwd(self, layout: Dict[str, list], params: torch.Tensor, x: torch.Tensor, scalings: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """tcnn.Encoding{HashGrid}.forward for a tiny-cuda-nn layout (tcnn_compat.grid_layout): flat params (values already
+        fp16-rounded), x [P, n_dims] in [0,1] -> [P, L*F] level-major.  Parity unpinned (tcnn_compat.py)."""
+        sc = scalings if scalings is not None else torch.ones(layout["n_levels"])
+        d = tcnn_compat.grid_desc(layout, sc)
+        pr, xs = self._dev(params).reshape(-1), self._dev(x).reshape(-1, layout["n_dims"])
+        out = torch.empty(xs.shape[0], layout["n_levels"] * layout["n_features"], device=self.device)
+        self._check(self.lib.b200nerf_tcnn_hashgrid_fwd(self._h, ctypes.byref(d), _ptr(pr), _ptr(xs), _ptr(out), xs.shape[0], self._stream))
+        return out
 
     def sh4_fwd(self, dirs: torch.Tensor) -> torch.Tensor:
         """SHEncoding(levels=4).forward (encodings.py:797-805)."""

@@ -41,6 +41,8 @@ struct b200nerf_ctx {
   float* d_decoder[3] = {nullptr, nullptr, nullptr};
   float* d_main_mlp = nullptr;
   float* d_main_mlp_nn = nullptr;
+  int layout = 0;    // 0: torch-mode grids (b200nerf_set_field_grids); 1: tiny-cuda-nn layout (b200nerf_set_field_grids_tcnn)
+  int field_layout[3] = {0, 0, 0};
   int mlp_mode = 3;  // 3 = ray-per-lane in two kernels (sampling | shading + tcgen05), 2 = the same as one fused kernel, 1 = warp-per-ray + tcgen05 (3xTF32), 0 = warp-per-ray + CUDA-core fp32 FFMA
   float* d_lane_scratch = nullptr;
   int lane_ctas = 0;
@@ -195,11 +197,13 @@ __device__ __forceinline__ bool lane_unit_ray(const RenderParams& P, int64_t uni
 
 // Work distribution of the two-stage kernels.  The unit of work is a PATCH = the 32 rays of one warp (an 8x4 pixel patch of a
 // 32x16 tile when the caller passes image_width, else 32 consecutive rays); patches are numbered tile by tile, so consecutive
-// patches are spatial neighbours.  Every CTA owns a contiguous, balanced range of patches (sizes differ by at most one) and
-// hands them out round-robin to its warps (sampling: no CTA-level synchronisation at all) or to its 128-ray warp groups
-// (shading: one tensor-core tile = 4 consecutive patches).  With whole 512-ray CTA units, a 230 400-ray image is 460 units
-// on 148 (x2) resident CTAs: a few SMs got 4 units where the others got 3 and the launch lasted 4/3.1 of its balanced time;
-// with patches every SM gets 48.6 +- 0.5 of them.
+// patches are spatial neighbours.  Whole tiles (16 patches = one per warp) are taken grid-stride, tile k * gridDim + blockIdx,
+// for as many FULL rounds as there are -- all resident CTAs then work on adjacent tiles, which keeps their common working
+// set of grid cells compact in L2 (giving every CTA one long contiguous range instead cost 4 % on the 1.5 M-ray batch:
+// profiles/r02_ab_work_distribution_v1.txt).  The last, partial round is split evenly over ALL CTAs at patch granularity
+// (sampling: round-robin over a CTA's warps, there is no CTA-level synchronisation at all; shading: over its 128-ray warp
+// groups, one tensor-core tile = 4 consecutive patches).  With whole 512-ray CTA units a 230 400-ray image is 460 units on
+// 148 (x2) resident CTAs: a few SMs got 4 units where the others got 3 and the launch lasted 4 / 3.1 of its balanced time.
 __device__ __forceinline__ int64_t lane_patches(const RenderParams& P) {
   return P.rays.image_width > 0 ? lane_units(P) * (kLaneThreads / 32) : (P.n_rays + 31) / 32;
 }
@@ -216,23 +220,38 @@ __device__ __forceinline__ bool lane_patch_ray(const RenderParams& P, int64_t pa
 #ifndef NFF_SAMPLE_CTAS
 #define NFF_SAMPLE_CTAS 2
 #endif
+template <int LAYOUT>  // 0: the reference's torch-mode grids; 1: tiny-cuda-nn layout (tcnn-trained checkpoints)
 __global__ void __launch_bounds__(kLaneThreads, NFF_SAMPLE_CTAS) nff_sample_lane_kernel(const __grid_constant__ RenderParams P,
                                                                                         float* __restrict__ scratch,
                                                                                         float* __restrict__ handoff) {
   const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane_ = tid & 31;
   const LaneScratch sc = lane_scratch_of(scratch, blockIdx.x);
+  constexpr int kPPU = kLaneThreads / 32;  // patches per tile
   const int64_t n_patches = lane_patches(P);
-  const int64_t p0 = n_patches * blockIdx.x / gridDim.x, p1 = n_patches * (blockIdx.x + 1) / gridDim.x;
-  for (int64_t patch = p0 + warp; patch < p1; patch += kLaneThreads / 32) {
+  // full rounds: tile k * gridDim + blockIdx (the resident CTAs sweep over ADJACENT tiles together: their working set of
+  // grid cells stays compact in L2); the last, partial round is dealt out patch by patch so that every SM ends together.
+  // One loop (one copy of the body: the kernel has to stay inside the instruction cache).
+  const int64_t full_rounds = n_patches / kPPU / gridDim.x;
+  const int64_t r0 = full_rounds * gridDim.x * kPPU, rest = n_patches - r0;
+  const int64_t p0 = r0 + rest * blockIdx.x / gridDim.x, p1 = r0 + rest * (blockIdx.x + 1) / gridDim.x;
+  for (int64_t it = 0;; ++it) {
+    int64_t patch;
+    if (it < full_rounds) {
+      patch = (it * gridDim.x + blockIdx.x) * kPPU + warp;
+    } else {
+      patch = p0 + warp + (it - full_rounds) * kPPU;
+      if (patch >= p1) break;
+    }
     int64_t ray;
     const bool active = lane_patch_ray(P, patch, lane_, &ray);
     const LaneRay R = lane_ray_setup(P, sc, tid, ray);
     // inactive lanes write their (discarded) edges into the slab column instead of another ray's hand-over column
     float* col = active ? handoff + ray : sc.bins2 + tid;
-    sample_ray_lane(P, sc, R, tid, ray, active, col, active ? P.n_rays : (int64_t)kLaneThreads);
+    sample_ray_lane<LAYOUT>(P, sc, R, tid, ray, active, col, active ? P.n_rays : (int64_t)kLaneThreads);
   }
 }
 
+template <int LAYOUT>
 __global__ void __launch_bounds__(kLaneThreads, kLaneCtasPerSm) nff_shade_lane_kernel(const __grid_constant__ RenderParams P,
                                                                                       float* __restrict__ scratch,
                                                                                       const float* __restrict__ handoff) {
@@ -261,15 +280,29 @@ __global__ void __launch_bounds__(kLaneThreads, kLaneCtasPerSm) nff_shade_lane_k
   mlp.core.status = P.status;
   const LaneScratch sc = lane_scratch_of(scratch, blockIdx.x);
   mlp.geo_park = NFF_PANEL_GLOBAL ? sc.panel : geo_park;
+  mlp.sh_tcnn = LAYOUT;
   // a warp group (one 128-row tensor-core tile) renders 4 consecutive patches; the groups of a CTA only meet at the two
-  // block barriers around the loop, inside it they synchronise among their own 4 warps (named barriers, mbarriers)
-  const int64_t n_groups = (lane_patches(P) + 3) / 4;
-  const int64_t g0 = n_groups * blockIdx.x / gridDim.x, g1 = n_groups * (blockIdx.x + 1) / gridDim.x;
-  for (int64_t gu = g0 + group; gu < g1; gu += kLaneThreads / 128) {
+  // block barriers around the loop, inside it they synchronise among their own 4 warps (named barriers, mbarriers).
+  // Full rounds sweep adjacent tiles like the sampling kernel; the partial last round is dealt out group-unit by group-unit.
+  constexpr int kPPU = kLaneThreads / 32;
+  const int64_t n_patches = lane_patches(P);
+  const int64_t full_rounds = n_patches / kPPU / gridDim.x;
+  const int64_t r0 = full_rounds * gridDim.x * kPPU;
+  const int64_t rest_groups = (n_patches - r0 + 3) / 4;
+  const int64_t g0 = rest_groups * blockIdx.x / gridDim.x, g1 = rest_groups * (blockIdx.x + 1) / gridDim.x;
+  for (int64_t it = 0;; ++it) {
+    int64_t patch;
+    if (it < full_rounds) {
+      patch = (it * gridDim.x + blockIdx.x) * kPPU + warp;
+    } else {
+      const int64_t gu = g0 + group + (it - full_rounds) * (kLaneThreads / 128);
+      if (gu >= g1) break;
+      patch = r0 + gu * 4 + (warp & 3);
+    }
     int64_t ray;
-    const bool active = lane_patch_ray(P, gu * 4 + (warp & 3), tid & 31, &ray);
+    const bool active = lane_patch_ray(P, patch, tid & 31, &ray);
     const LaneRay R = lane_ray_setup(P, sc, tid, ray);
-    shade_ray_lane(P, sc, R, mlp, tid, ray, active, handoff + ray, P.n_rays);
+    shade_ray_lane<MlpLaneTc, LAYOUT>(P, sc, R, mlp, tid, ray, active, handoff + ray, P.n_rays);
   }
   tc::fence_before_sync();
   __syncthreads();
@@ -353,6 +386,25 @@ __global__ void hashgrid_fwd_kernel(Grid g, const float* __restrict__ x, float* 
 #pragma unroll
     for (int k = 0; k < 8; ++k) v[k] = __ldg(base + (size_t)r[k] * g.F + f);
     out[p * g.L * g.F + l * g.F + f] = trilerp(v, c);
+  }
+}
+
+// tcnn.Encoding{HashGrid}.forward (stage operator of the tiny-cuda-nn layout): one thread per point.
+template <int D>
+__global__ void tcnn_hashgrid_fwd_kernel(Grid g, const float* __restrict__ x, float* __restrict__ out, int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float p[D];
+  for (int d = 0; d < D; ++d) p[d] = x[i * D + d];
+  for (int l = 0; l < g.L; ++l) {
+    uint32_t idx[1 << D];
+    float frac[D];
+    tcnn_corners<D>(g, l, p, idx, frac);
+    for (int f = 0; f < g.F; ++f) {
+      float v = 0.f;
+      for (int c = 0; c < (1 << D); ++c) v = fmaf(tcnn_corner_weight<D>(c, frac), g.table[(size_t)idx[c] * g.F + f], v);
+      out[i * (g.L * g.F) + l * g.F + f] = v;
+    }
   }
 }
 
@@ -953,9 +1005,12 @@ int b200nerf_create(int device_ordinal, b200nerf_ctx** out) {
                                 (int)((sizeof(TcShared) + 127) / 128 * 128 + (NFF_PANEL_GLOBAL ? 0 : sizeof(float) * kNff * kLaneThreads))));
   c->lane_ctas = c->sm_count * (kLaneCtasPerSm > NFF_SAMPLE_CTAS ? kLaneCtasPerSm : NFF_SAMPLE_CTAS);
   CUDA_TRY(cudaMalloc((void**)&c->d_lane_scratch, sizeof(float) * lane_scratch_floats_per_cta() * c->lane_ctas));
-  CUDA_TRY(cudaFuncSetAttribute(nff_shade_lane_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  CUDA_TRY(cudaFuncSetAttribute(nff_shade_lane_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 (int)((sizeof(TcShared) + 127) / 128 * 128 + (NFF_PANEL_GLOBAL ? 0 : sizeof(float) * kNff * kLaneThreads))));
-  CUDA_TRY(cudaFuncSetAttribute(nff_sample_lane_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 0));  // all L1
+  CUDA_TRY(cudaFuncSetAttribute(nff_shade_lane_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)((sizeof(TcShared) + 127) / 128 * 128 + (NFF_PANEL_GLOBAL ? 0 : sizeof(float) * kNff * kLaneThreads))));
+  CUDA_TRY(cudaFuncSetAttribute(nff_sample_lane_kernel<0>, cudaFuncAttributePreferredSharedMemoryCarveout, 0));  // all L1
+  CUDA_TRY(cudaFuncSetAttribute(nff_sample_lane_kernel<1>, cudaFuncAttributePreferredSharedMemoryCarveout, 0));
   CUDA_TRY(cudaMalloc((void**)&c->d_minmax, 2 * sizeof(unsigned)));
   c->handoff_rays = (int64_t)1 << 21;
   CUDA_TRY(cudaMalloc((void**)&c->d_handoff, sizeof(float) * (kS2 + 1) * c->handoff_rays));
@@ -1025,6 +1080,64 @@ int b200nerf_set_field_grids(b200nerf_ctx* c, int field, const b200nerf_grid_des
   fg.decoder = c->d_decoder[field];
   c->fields[field] = fg;
   c->have_field[field] = true;
+  c->field_layout[field] = 0;
+  if (field == B200NERF_FIELD_MAIN) c->layout = 0;
+  return 0;
+}
+
+namespace {
+int make_tcnn_grid(const b200nerf_tcnn_grid_desc* d, const float* params, int want_dims, Grid* g) {
+  REQUIRE(d != nullptr && params != nullptr, "tcnn grid descriptor / parameters are NULL");
+  REQUIRE(d->num_levels >= 1 && d->num_levels <= kMaxLevels, "num_levels must be in [1,16]");
+  REQUIRE(d->n_input_dims == want_dims, "tcnn grid has the wrong number of input dimensions (static: 3, actors: 4)");
+  *g = Grid{};
+  g->table = params;
+  g->L = d->num_levels;
+  g->F = d->features_per_level;
+  g->n_dims = d->n_input_dims;
+  for (int l = 0; l < d->num_levels; ++l) {
+    g->res[l] = d->scalings[l];
+    g->pos_scale[l] = d->scale[l];
+    g->lvl_res[l] = d->resolution[l];
+    g->lvl_off[l] = d->offset[l];
+    REQUIRE(d->size[l] >= 1, "empty tcnn grid level");
+    if (d->dense[l]) {
+      g->dense_bits |= 1u << l;
+      g->lvl_mask[l] = d->size[l];
+    } else {
+      REQUIRE((d->size[l] & (d->size[l] - 1)) == 0, "a hashed tcnn level must hold a power-of-two number of entries");
+      g->lvl_mask[l] = d->size[l] - 1;
+    }
+  }
+  return 0;
+}
+}  // namespace
+
+int b200nerf_set_field_grids_tcnn(b200nerf_ctx* c, int field, const b200nerf_tcnn_grid_desc* sd, const float* sparams,
+                                  const b200nerf_tcnn_grid_desc* ad, const float* aparams, int n_actors, float static_scale,
+                                  float actor_scale) {
+  REQUIRE(c, "ctx is NULL");
+  REQUIRE(field >= 0 && field < 3, "field selector out of range");
+  DeviceGuard g(c->device);
+  FieldGrids fg{};
+  if (int e = make_tcnn_grid(sd, sparams, 3, &fg.stat)) return e;
+  const int wantL = field == B200NERF_FIELD_MAIN ? 8 : 6, wantF = field == B200NERF_FIELD_MAIN ? 4 : 1;
+  if (fg.stat.L != wantL || fg.stat.F != wantF)
+    return fail(B200NERF_ERR_UNSUPPORTED,
+                "fused kernel is specialised for NeuRAD's grid shapes (main: 8 levels x 4 features, proposal: 6 x 1)");
+  if (n_actors > 0) {
+    if (int e = make_tcnn_grid(ad, aparams, 4, &fg.act)) return e;
+    if (fg.act.L != 4 || fg.act.F != wantF)
+      return fail(B200NERF_ERR_UNSUPPORTED, "the 4-D actor grid must have 4 levels and the static grid's feature width");
+  }
+  fg.n_actors_f = (float)(n_actors > 0 ? n_actors : 1);
+  fg.static_scale = static_scale;
+  fg.actor_scale = actor_scale;
+  fg.decoder = c->d_decoder[field];
+  c->fields[field] = fg;
+  c->have_field[field] = true;
+  c->field_layout[field] = 1;
+  if (field == B200NERF_FIELD_MAIN) c->layout = 1;
   return 0;
 }
 
@@ -1184,10 +1297,10 @@ int b200nerf_nff_render_fwd(b200nerf_ctx* c, const b200nerf_rays* rays, int64_t 
     int f = c->samp.field_of_round[i];
     if (!c->have_field[f] || !c->fields[f].decoder)
       return fail(B200NERF_ERR_STATE, "proposal field used by a sampling round has no grids / decoder set");
-    if (c->actors.n_actors > 0 && !c->fields[f].actor_tables)
+    if (c->actors.n_actors > 0 && !c->fields[f].actor_tables && !c->fields[f].act.table)
       return fail(B200NERF_ERR_STATE, "actors are set but a proposal field has no actor grids");
   }
-  if (c->actors.n_actors > 0 && !c->fields[0].actor_tables)
+  if (c->actors.n_actors > 0 && !c->fields[0].actor_tables && !c->fields[0].act.table)
     return fail(B200NERF_ERR_STATE, "actors are set but the main field has no actor grids");
   if (n_rays == 0) return 0;
   REQUIRE(rays->origins && rays->directions && rays->pixel_area && rays->times, "NULL ray tensor");
@@ -1215,6 +1328,18 @@ int b200nerf_nff_render_fwd(b200nerf_ctx* c, const b200nerf_rays* rays, int64_t 
   if (c->peers.n_peers > 0 && ((kNff + c->app.dim) & 3) != 0)
     return fail(B200NERF_ERR_UNSUPPORTED, "peer outputs need a feature width that is a multiple of 4");
   P.n_rays = n_rays;
+  P.layout = c->layout;
+  if (c->layout == 1) {
+    if (c->mlp_mode != 3)
+      return fail(B200NERF_ERR_UNSUPPORTED, "the tiny-cuda-nn layout is implemented by the two-stage renderer (mode 3) only");
+    for (int i = 0; i < 2; ++i)
+      if (c->field_layout[c->samp.field_of_round[i]] != 1)
+        return fail(B200NERF_ERR_STATE, "main field has the tiny-cuda-nn layout but a proposal field used for sampling does not");
+  } else {
+    for (int i = 0; i < 2; ++i)
+      if (c->field_layout[c->samp.field_of_round[i]] != 0)
+        return fail(B200NERF_ERR_STATE, "a proposal field has the tiny-cuda-nn layout but the main field does not");
+  }
   constexpr int WARPS = kRenderWarps;
   int64_t blocks_needed = (n_rays + WARPS - 1) / WARPS;
   int64_t max_blocks = (int64_t)c->sm_count * (16 / WARPS);  // persistent: resident CTAs only, grid-stride over rays
@@ -1246,8 +1371,13 @@ int b200nerf_nff_render_fwd(b200nerf_ctx* c, const b200nerf_rays* rays, int64_t 
       const int64_t max_a = (int64_t)c->sm_count * NFF_SAMPLE_CTAS, max_b = (int64_t)c->sm_count * kLaneCtasPerSm;
       const int64_t patches = rays->image_width > 0 ? need * (kLaneThreads / 32) : (cnt + 31) / 32, groups = (patches + 3) / 4;
       const int64_t grid_a = patches < max_a ? patches : max_a, grid_b = groups < max_b ? groups : max_b;
-      nff_sample_lane_kernel<<<(int)grid_a, kLaneThreads, 0, st>>>(Q, c->d_lane_scratch, c->d_handoff);
-      nff_shade_lane_kernel<<<(int)grid_b, kLaneThreads, smem, st>>>(Q, c->d_lane_scratch, c->d_handoff);
+      if (c->layout == 1) {
+        nff_sample_lane_kernel<1><<<(int)grid_a, kLaneThreads, 0, st>>>(Q, c->d_lane_scratch, c->d_handoff);
+        nff_shade_lane_kernel<1><<<(int)grid_b, kLaneThreads, smem, st>>>(Q, c->d_lane_scratch, c->d_handoff);
+      } else {
+        nff_sample_lane_kernel<0><<<(int)grid_a, kLaneThreads, 0, st>>>(Q, c->d_lane_scratch, c->d_handoff);
+        nff_shade_lane_kernel<0><<<(int)grid_b, kLaneThreads, smem, st>>>(Q, c->d_lane_scratch, c->d_handoff);
+      }
     }
   } else if (c->mlp_mode == 2) {
     const size_t smem = (sizeof(TcShared) + 127) / 128 * 128 + (NFF_PANEL_GLOBAL ? 0 : sizeof(float) * kNff * kLaneThreads);
@@ -1960,6 +2090,25 @@ int b200nerf_hashgrid_fwd(b200nerf_ctx* c, const b200nerf_grid_desc* desc, const
   if (int e = make_grid(desc, table, &gr)) return e;
   int64_t n = n_points * gr.L;
   hashgrid_fwd_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(gr, x, out, indices, n_points);
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+int b200nerf_tcnn_hashgrid_fwd(b200nerf_ctx* c, const b200nerf_tcnn_grid_desc* desc, const float* params, const float* x,
+                               float* out, int64_t n_points, void* stream) {
+  REQUIRE(c && desc, "NULL argument");
+  REQUIRE(desc->features_per_level >= 1 && desc->features_per_level <= 8, "features_per_level must be in [1,8]");
+  REQUIRE(desc->n_input_dims == 3 || desc->n_input_dims == 4, "n_input_dims must be 3 or 4");
+  if (n_points == 0) return 0;
+  REQUIRE(params && x && out, "NULL argument");
+  DeviceGuard g(c->device);
+  Grid gr{};
+  if (int e = make_tcnn_grid(desc, params, desc->n_input_dims, &gr)) return e;
+  const unsigned blocks = (unsigned)((n_points + 127) / 128);
+  if (desc->n_input_dims == 3)
+    tcnn_hashgrid_fwd_kernel<3><<<blocks, 128, 0, (cudaStream_t)stream>>>(gr, x, out, n_points);
+  else
+    tcnn_hashgrid_fwd_kernel<4><<<blocks, 128, 0, (cudaStream_t)stream>>>(gr, x, out, n_points);
   CUDA_TRY(cudaGetLastError());
   return 0;
 }

@@ -337,6 +337,144 @@ NFF_D float encode_f1_dot(const float* NFF_RESTRICT table, const Grid& gr, Gauss
   }
   return acc;
 }
+// ---- tiny-cuda-nn HashGrid layout (tcnn-trained checkpoints) ---------------------------------------
+// tcnn::GridEncoding (encodings/grid.h; configuration built at field_components/encodings.py:386-401) differs from the
+// torch twin in four ways: the position is pos = fma(x, grid_scale(l), 0.5) with grid_scale = base * growth^l - 1 (vertex-
+// centred), levels whose res^n vertices fit their share of the table index LINEARLY (x + y*res + z*res^2, no hash), every
+// level has its own entry offset / size, and the actors share ONE 4-D grid whose 4th coordinate is actor_index / n_actors
+// (neurad_encoding.py:270-281; a 4th prime, 3674653429, joins the hash).  Parameters are the fp16-rounded values of the
+// checkpoint held as floats, the arithmetic is fp32 (tiny-cuda-nn itself accumulates in half: parity unpinned, see
+// oracle/tcnn_oracle.py).  The anti-aliasing weights still use HashEncoding.scalings (neurad_encoding.py:300-302).
+//
+// Entry indices of the 2^D corners of level l, in the order bit d of the corner number = "ceil" along dimension d, and the
+// interpolation offsets.
+template <int D>
+NFF_D void tcnn_corners(const Grid& gr, int l, const float* x, uint32_t* idx /* [1 << D] */, float* frac /* [D] */) {
+  uint32_t pg[D];
+#pragma unroll
+  for (int d = 0; d < D; ++d) {
+    const float p = fmaf(x[d], gr.pos_scale[l], 0.5f);
+    const float f = floorf(p);
+    pg[d] = (uint32_t)(int32_t)f;
+    frac[d] = fsub(p, f);
+  }
+  const uint32_t res = gr.lvl_res[l];
+  if ((gr.dense_bits >> l) & 1u) {
+    uint32_t base = 0, stride = 1, st[D];
+#pragma unroll
+    for (int d = 0; d < D; ++d) {
+      st[d] = stride;
+      base += pg[d] * stride;
+      stride *= res;
+    }
+#pragma unroll
+    for (int c = 0; c < (1 << D); ++c) {
+      uint32_t i = base;
+#pragma unroll
+      for (int d = 0; d < D; ++d)
+        if (c & (1 << d)) i += st[d];
+      // tiny-cuda-nn takes `index % entries` and never clamps: the "+1" vertex of the last cell (pos >= res - 1, i.e. x
+      // within half a cell of 1) wraps into the next row / the start of the level.  i < 2 * entries always.
+      if (i >= gr.lvl_mask[l]) i -= gr.lvl_mask[l];
+      idx[c] = gr.lvl_off[l] + i;
+    }
+  } else {
+    constexpr uint32_t kPrimes[4] = {1u, 2654435761u, 805459861u, 3674653429u};
+    uint32_t h0[D], h1[D];
+#pragma unroll
+    for (int d = 0; d < D; ++d) {
+      h0[d] = pg[d] * kPrimes[d];
+      h1[d] = h0[d] + kPrimes[d];
+    }
+#pragma unroll
+    for (int c = 0; c < (1 << D); ++c) {
+      uint32_t h = 0;
+#pragma unroll
+      for (int d = 0; d < D; ++d) h ^= (c & (1 << d)) ? h1[d] : h0[d];
+      idx[c] = gr.lvl_off[l] + (h & gr.lvl_mask[l]);
+    }
+  }
+}
+// N-linear interpolation weight of corner c
+template <int D>
+NFF_D float tcnn_corner_weight(int c, const float* frac) {
+  float w = 1.0f;
+#pragma unroll
+  for (int d = 0; d < D; ++d) w = fmul(w, (c & (1 << d)) ? frac[d] : fsub(1.0f, frac[d]));
+  return w;
+}
+// F = 1 grid fused with the proposal decoder (the tcnn twin of encode_f1_dot); `x` has D coordinates in [0,1]
+template <int D>
+NFF_D float tcnn_encode_f1_dot(const Grid& gr, int L, const float* x, float std, const float* NFF_RESTRICT dec) {
+  float acc = 0.0f;
+#pragma unroll 1
+  for (int l = 0; l < L; ++l) {
+    uint32_t idx[1 << D];
+    float frac[D];
+    tcnn_corners<D>(gr, l, x, idx, frac);
+    float f[1 << D];
+#pragma unroll
+    for (int c = 0; c < (1 << D); ++c) f[c] = ldg(gr.table + idx[c]);
+    float v = 0.0f;
+#pragma unroll
+    for (int c = 0; c < (1 << D); ++c) v = fmaf(tcnn_corner_weight<D>(c, frac), f[c], v);
+    acc = fmaf(fmul(v, level_weight(gr.res[l], std)), ldg(dec + l), acc);
+  }
+  return acc;
+}
+// F = 4 grid into a strided column (the tcnn twin of encode_f4_col / encode_f4_panel): out[(4l+f) * stride]
+template <int D>
+NFF_D void tcnn_encode_f4(const Grid& gr, int L, const float* x, float std, float* out, int stride) {
+#pragma unroll 1
+  for (int l = 0; l < L; ++l) {
+    uint32_t idx[1 << D];
+    float frac[D];
+    tcnn_corners<D>(gr, l, x, idx, frac);
+    const float4* t4 = reinterpret_cast<const float4*>(gr.table);
+    float4 v[1 << D];
+#pragma unroll
+    for (int c = 0; c < (1 << D); ++c) v[c] = ldg(t4 + idx[c]);
+    float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f, a3 = 0.0f;
+#pragma unroll
+    for (int c = 0; c < (1 << D); ++c) {
+      const float w = tcnn_corner_weight<D>(c, frac);
+      a0 = fmaf(w, v[c].x, a0);
+      a1 = fmaf(w, v[c].y, a1);
+      a2 = fmaf(w, v[c].z, a2);
+      a3 = fmaf(w, v[c].w, a3);
+    }
+    const float lw = level_weight(gr.res[l], std);
+    out[(4 * l + 0) * stride] = fmul(a0, lw);
+    out[(4 * l + 1) * stride] = fmul(a1, lw);
+    out[(4 * l + 2) * stride] = fmul(a2, lw);
+    out[(4 * l + 3) * stride] = fmul(a3, lw);
+  }
+}
+// tcnn SphericalHarmonics, degree 4 (encodings/spherical_harmonics.h): the reference passes (d + 1) / 2
+// (fields/base_field.py:136-142) and tiny-cuda-nn maps it back with x * 2 - 1, i.e. the basis is evaluated at the direction
+// itself, with the Condon-Shortley signs the torch twin (utils/math.py:31-94) does not have.
+NFF_D void sh4_tcnn(float dx, float dy, float dz, float* c) {
+  const float x = fsub(fmul(fmul(fadd(dx, 1.0f), 0.5f), 2.0f), 1.0f), y = fsub(fmul(fmul(fadd(dy, 1.0f), 0.5f), 2.0f), 1.0f),
+              z = fsub(fmul(fmul(fadd(dz, 1.0f), 0.5f), 2.0f), 1.0f);
+  const float xy = x * y, xz = x * z, yz = y * z, x2 = x * x, y2 = y * y, z2 = z * z;
+  c[0] = 0.28209479177387814f;
+  c[1] = -0.48860251190291987f * y;
+  c[2] = 0.48860251190291987f * z;
+  c[3] = -0.48860251190291987f * x;
+  c[4] = 1.0925484305920792f * xy;
+  c[5] = -1.0925484305920792f * yz;
+  c[6] = 0.94617469575755997f * z2 - 0.31539156525251999f;
+  c[7] = -1.0925484305920792f * xz;
+  c[8] = 0.54627421529603959f * x2 - 0.54627421529603959f * y2;
+  c[9] = 0.59004358992664352f * y * (-3.0f * x2 + y2);
+  c[10] = 2.8906114426405538f * xy * z;
+  c[11] = 0.45704579946446572f * y * (1.0f - 5.0f * z2);
+  c[12] = 0.3731763325901154f * z * (5.0f * z2 - 3.0f);
+  c[13] = 0.45704579946446572f * x * (1.0f - 5.0f * z2);
+  c[14] = 1.4453057213202769f * z * (x2 - y2);
+  c[15] = 0.59004358992664352f * x * (-x2 + 3.0f * y2);
+}
+
 // F = 4 (16-byte rows, one LDG.128 per corner); writes feature 4l+f of this lane's sample to panel[4l+f][lane].
 NFF_D void encode_f4_panel(const float* NFF_RESTRICT table, const Grid& gr, int L, Gauss g, float (*panel)[33]) {
   const int ln = lane();

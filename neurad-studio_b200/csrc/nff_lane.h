@@ -138,6 +138,8 @@ NFF_D int lane_actor_of_sample(const LaneScratch& sc, int tid, int n_cand, const
   return hit;
 }
 
+// LAYOUT 0: the reference's torch layout (hashed [L*T,F] tables, one 3-D grid per actor); 1: tiny-cuda-nn layout (nff_device.h)
+template <int LAYOUT = 0>
 NFF_D float lane_proposal_density(const FieldGrids& fg, const LaneScratch& sc, int tid, int n_cand, const Gauss& g,
                                   int* actor_id) {
   float pb[3], M[12];
@@ -146,10 +148,20 @@ NFF_D float lane_proposal_density(const FieldGrids& fg, const LaneScratch& sc, i
   if (a >= 0) {
     Gauss ga = {pb[0], pb[1], pb[2], g.std};
     ga = contract(ga, fg.actor_scale);
-    acc = encode_f1_dot<4, NFF_G_ACT>(fg.actor_tables[a], fg.act, ga, fg.decoder);
+    if (LAYOUT == 1) {
+      const float x4[4] = {ga.x, ga.y, ga.z, fdiv((float)a, fg.n_actors_f)};  // neurad_encoding.py:273-275
+      acc = tcnn_encode_f1_dot<4>(fg.act, 4, x4, ga.std, fg.decoder);
+    } else {
+      acc = encode_f1_dot<4, NFF_G_ACT>(fg.actor_tables[a], fg.act, ga, fg.decoder);
+    }
   } else {
     Gauss gs = contract(g, fg.static_scale);
-    acc = encode_f1_dot<6, NFF_G_PROP>(fg.stat.table, fg.stat, gs, fg.decoder);
+    if (LAYOUT == 1) {
+      const float x3[3] = {gs.x, gs.y, gs.z};
+      acc = tcnn_encode_f1_dot<3>(fg.stat, 6, x3, gs.std, fg.decoder);
+    } else {
+      acc = encode_f1_dot<6, NFF_G_PROP>(fg.stat.table, fg.stat, gs, fg.decoder);
+    }
   }
   *actor_id = a;
   return expf(acc);
@@ -222,6 +234,7 @@ struct LaneRoundIO {
   int32_t* tr_inds;
 };
 // `bins_in` == nullptr: level-0 edges torch.linspace(0, 1, S+1); else the scratch column written by the previous round.
+template <int LAYOUT = 0>
 NFF_D float lane_proposal_round(const RenderParams& P, const FieldGrids& fg, const LaneScratch& sc, int tid, int n_cand,
                                 const LaneRoundIO& io, const float* bins_in, const float o[3], const float d[3], float area,
                                 float s_near, float s_far, int64_t ray) {
@@ -246,7 +259,7 @@ NFF_D float lane_proposal_round(const RenderParams& P, const FieldGrids& fg, con
       e_prev = e1;
       Gauss g = sample_gaussian(o, d, area, e0, e1);
       int aid;
-      float dens = lane_proposal_density(fg, sc, tid, n_cand, g, &aid);
+      float dens = lane_proposal_density<LAYOUT>(fg, sc, tid, n_cand, g, &aid);
       float dd = fmul(fsub(e1, e0), dens);
       float alpha = fsub(1.0f, expf(-dd));
       excl += (double)dd;  // torch.cumsum order
@@ -299,6 +312,7 @@ NFF_D float lane_proposal_round(const RenderParams& P, const FieldGrids& fg, con
 struct MlpLaneFfma {
   const float* w;  // packed transposed weights (nff_params.h)
   float* panel_;   // [kNff][kLaneThreads]
+  int sh_tcnn = 0;  // 1: tiny-cuda-nn's SphericalHarmonics convention (nff_device.h: sh4_tcnn)
   NFF_D float* panel() const { return panel_; }
   NFF_D void run(const float* x, const float dir[3], float& sdf, float* feat, int /*tid*/) const {
     float h[kHidden], go[kNff + 1], in2[kNff + kSh], h2[kHidden];
@@ -307,7 +321,7 @@ struct MlpLaneFfma {
     sdf = go[0];
 #pragma unroll
     for (int i = 0; i < kNff; ++i) in2[i] = go[i + 1];
-    sh4(dir[0], dir[1], dir[2], in2 + kNff);
+    if (sh_tcnn) sh4_tcnn(dir[0], dir[1], dir[2], in2 + kNff); else sh4(dir[0], dir[1], dir[2], in2 + kNff);
     dense<kNff + kSh, kHidden, kHidden, true>(w + kOffFeatW0, w + kOffFeatB0, in2, h);
     dense<kHidden, kHidden, kHidden, true>(w + kOffFeatW1, w + kOffFeatB1, h, h2);
     dense<kHidden, kNff, kNff, false>(w + kOffFeatW2, w + kOffFeatB2, h2, h);
@@ -321,6 +335,7 @@ struct MlpLaneFfma {
 struct MlpLaneTc {
   MlpTc core;
   float* geo_park;  // [kNff][kLaneThreads] shared memory: grid-feature panel first, then the parked geo_embedding
+  int sh_tcnn = 0;  // 1: tiny-cuda-nn's SphericalHarmonics convention
   NFF_D float* panel() const { return geo_park; }
   NFF_D void run(const float* x, const float dir[3], float& sdf, float* feat, int tid) {
     float h[kHidden], in2[kNff + kSh];
@@ -335,7 +350,7 @@ struct MlpLaneTc {
     core.layer<32>(1, h, in2);
 #pragma unroll
     for (int i = 0; i < kNff; ++i) geo_park[i * kLaneThreads + tid] = in2[i];
-    sh4(dir[0], dir[1], dir[2], in2 + kNff);
+    if (sh_tcnn) sh4_tcnn(dir[0], dir[1], dir[2], in2 + kNff); else sh4(dir[0], dir[1], dir[2], in2 + kNff);
     core.layer<48>(2, in2, h);
 #pragma unroll
     for (int i = 0; i < kHidden; ++i) h[i] = fmaxf(h[i], 0.0f);
@@ -383,6 +398,7 @@ NFF_D LaneRay lane_ray_setup(const RenderParams& P, const LaneScratch& sc, int t
 
 // Sampling stage: both proposal rounds (ProposalNetworkSampler.generate_ray_samples, ray_samplers.py:623-666).  The
 // final spacing edges go to this lane's column `bins2` (element i at bins2[i * bins2_stride]); prop depths to P.out.
+template <int LAYOUT = 0>
 NFF_D void sample_ray_lane(const RenderParams& P, const LaneScratch& sc, const LaneRay& R, int tid, int64_t ray, bool active,
                            float* bins2, int64_t bins2_stride) {
   const Sampling& sp = P.samp;
@@ -400,7 +416,7 @@ NFF_D void sample_ray_lane(const RenderParams& P, const LaneScratch& sc, const L
     io.tr_bins_s = !active ? nullptr : rd == 0 ? P.trace.bins_s_1 : P.trace.bins_s_2;
     io.tr_bins_e = !active ? nullptr : rd == 0 ? P.trace.bins_e_1 : P.trace.bins_e_2;
     io.tr_inds = !active ? nullptr : rd == 0 ? P.trace.inds_1 : P.trace.inds_2;
-    prop_depth[rd] = lane_proposal_round(P, P.fields[sp.field_of_round[rd]], sc, tid, R.n_cand, io,
+    prop_depth[rd] = lane_proposal_round<LAYOUT>(P, P.fields[sp.field_of_round[rd]], sc, tid, R.n_cand, io,
                                          rd == 0 ? nullptr : sc.bins1 + tid, R.o, R.d, R.area, R.s_near, R.s_far, ray);
   }
   if (active) {
@@ -410,7 +426,7 @@ NFF_D void sample_ray_lane(const RenderParams& P, const LaneScratch& sc, const L
 }
 
 // Shading stage: main field on the 32 resampled intervals + compositing + outputs (neurad.py:368-401).
-template <class Mlp>
+template <class Mlp, int LAYOUT = 0>
 NFF_D void shade_ray_lane(const RenderParams& P, const LaneScratch& sc, const LaneRay& R, Mlp& mlp, int tid, int64_t ray,
                           bool active, const float* bins2, int64_t bins2_stride) {
   const Sampling& sp = P.samp;
@@ -445,7 +461,12 @@ NFF_D void shade_ray_lane(const RenderParams& P, const LaneScratch& sc, const La
         ga = contract(ga, fm.actor_scale);
 #pragma unroll
         for (int i = 16; i < 32; ++i) col[i * kLaneThreads] = 0.0f;  // F.pad(actor_features, (0, 32-16))
-        encode_f4_col(fm.actor_tables[aid], fm.act, 4, ga, col);
+        if (LAYOUT == 1) {
+          const float x4[4] = {ga.x, ga.y, ga.z, fdiv((float)aid, fm.n_actors_f)};
+          tcnn_encode_f4<4>(fm.act, 4, x4, ga.std, col, kLaneThreads);
+        } else {
+          encode_f4_col(fm.actor_tables[aid], fm.act, 4, ga, col);
+        }
         float q0 = fadd(fadd(fmul(M[0], d[0]), fmul(M[1], d[1])), fmul(M[2], d[2]));
         float q1 = fadd(fadd(fmul(M[4], d[0]), fmul(M[5], d[1])), fmul(M[6], d[2]));
         float q2 = fadd(fadd(fmul(M[8], d[0]), fmul(M[9], d[1])), fmul(M[10], d[2]));
@@ -453,7 +474,12 @@ NFF_D void shade_ray_lane(const RenderParams& P, const LaneScratch& sc, const La
         dir[0] = fdiv(q0, n); dir[1] = fdiv(q1, n); dir[2] = fdiv(q2, n);
       } else {
         Gauss gs = contract(g, fm.static_scale);
-        encode_f4_col(fm.stat.table, fm.stat, 8, gs, col);
+        if (LAYOUT == 1) {
+          const float x3[3] = {gs.x, gs.y, gs.z};
+          tcnn_encode_f4<3>(fm.stat, 8, x3, gs.std, col, kLaneThreads);
+        } else {
+          encode_f4_col(fm.stat.table, fm.stat, 8, gs, col);
+        }
       }
     }
     float x[kGeoIn];
@@ -567,11 +593,11 @@ NFF_D void shade_ray_lane(const RenderParams& P, const LaneScratch& sc, const La
 
 // NeuRADModel.get_nff_outputs (models/neurad.py:368-421), eval mode, for the ray owned by this lane: both stages back to
 // back with the resampled edges handed over through the CTA's scratch slab.
-template <class Mlp>
+template <class Mlp, int LAYOUT = 0>
 NFF_D void render_ray_lane(const RenderParams& P, const LaneScratch& sc, Mlp& mlp, int tid, int64_t ray, bool active) {
   const LaneRay R = lane_ray_setup(P, sc, tid, ray);
-  sample_ray_lane(P, sc, R, tid, ray, active, sc.bins2 + tid, kLaneThreads);
-  shade_ray_lane(P, sc, R, mlp, tid, ray, active, sc.bins2 + tid, kLaneThreads);
+  sample_ray_lane<LAYOUT>(P, sc, R, tid, ray, active, sc.bins2 + tid, kLaneThreads);
+  shade_ray_lane<Mlp, LAYOUT>(P, sc, R, mlp, tid, ray, active, sc.bins2 + tid, kLaneThreads);
 }
 
 }  // namespace nff

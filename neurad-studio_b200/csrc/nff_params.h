@@ -56,18 +56,26 @@ constexpr int kNnFeatB2 = kNnFeatW2 + kNff * kHidden;
 constexpr int kNnMlpFloats = kNnFeatB2 + kNff;
 
 struct Grid {
-  const float* table;  // [L*T, F]
+  const float* table;  // torch layout: [L*T, F]; tcnn layout: the flat parameter vector (fp16-representable values)
   uint32_t mask;       // T-1
   uint32_t T;
   int32_t L, F;
-  float res[kMaxLevels];
+  float res[kMaxLevels];  // HashEncoding.scalings: position scale of the torch layout AND the anti-aliasing weights of both
+  // tiny-cuda-nn HashGrid layout (LAYOUT == 1 kernels only; zero otherwise)
+  float pos_scale[kMaxLevels];    // grid_scale(level): pos = fma(x, pos_scale, 0.5)
+  uint32_t lvl_res[kMaxLevels];   // vertices per axis
+  uint32_t lvl_off[kMaxLevels];   // first entry of the level
+  uint32_t lvl_mask[kMaxLevels];  // hashed levels: entries - 1 (entries is a power of two); dense levels: entries
+  uint32_t dense_bits;            // bit l: level l indexes linearly (x + y*res + z*res^2 [+ w*res^3])
+  int32_t n_dims;                 // 3, or 4 for the shared actor grid (4th coordinate = actor index / n_actors)
 };
 
 struct FieldGrids {
   Grid stat;
-  Grid act;                          // .table unused; per-actor tables below
-  const float* const* actor_tables;  // device array [n_actors]
+  Grid act;                          // torch layout: .table unused, per-actor tables below; tcnn layout: the one 4-D grid
+  const float* const* actor_tables;  // device array [n_actors] (torch layout)
   float static_scale, actor_scale;
+  float n_actors_f;                  // tcnn layout: the 4-D actor grid's 4th coordinate is actor_index / n_actors
   const float* decoder;              // proposal fields: density_decoder.weight [L*F]; main: nullptr
 };
 
@@ -102,6 +110,7 @@ struct RenderParams {
   int* status;             // device-side failure flag (tensor-core barrier timeout)
   float beta;
   int32_t nff_dim;
+  int32_t layout;          // 0: the reference's torch layout; 1: tiny-cuda-nn layout (grids, SH convention)
   Actors actors;
   Sampling samp;
   Appearance app;

@@ -21,6 +21,22 @@ class GridDesc(ctypes.Structure):
     ]
 
 
+class TcnnGridDesc(ctypes.Structure):
+    """b200nerf_tcnn_grid_desc: tiny-cuda-nn HashGrid layout (per-level constants from tcnn_compat.grid_layout)."""
+
+    _fields_ = [
+        ("num_levels", c_int32),
+        ("features_per_level", c_int32),
+        ("n_input_dims", c_int32),
+        ("scale", c_float * MAX_LEVELS),
+        ("resolution", ctypes.c_uint32 * MAX_LEVELS),
+        ("offset", ctypes.c_uint32 * MAX_LEVELS),
+        ("size", ctypes.c_uint32 * MAX_LEVELS),
+        ("dense", c_uint8 * MAX_LEVELS),
+        ("scalings", c_float * MAX_LEVELS),
+    ]
+
+
 class Rays(ctypes.Structure):
     _fields_ = [(n, c_void_p) for n in
                 ("origins", "directions", "pixel_area", "times", "nears", "fars", "sensor_idx", "is_lidar")] + [("image_width", c_int32)]
@@ -78,6 +94,9 @@ SIGNATURES = {
     "b200nerf_set_sampling": (c_int, [c_void_p, c_int, c_int, c_int, c_float, c_float, c_float, c_float,
                                       POINTER(c_float), POINTER(c_float), POINTER(c_int), c_float]),
     "b200nerf_nff_render_fwd": (c_int, [c_void_p, POINTER(Rays), c_int64, POINTER(Outputs), POINTER(Trace), c_void_p]),
+    "b200nerf_set_field_grids_tcnn": (c_int, [c_void_p, c_int, POINTER(TcnnGridDesc), c_void_p, POINTER(TcnnGridDesc), c_void_p, c_int,
+                                              c_float, c_float]),
+    "b200nerf_tcnn_hashgrid_fwd": (c_int, [c_void_p, POINTER(TcnnGridDesc), c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
     "b200nerf_hashgrid_fwd": (c_int, [c_void_p, POINTER(GridDesc), c_void_p, c_void_p, c_void_p, c_void_p, c_int64,
                                       c_void_p]),
     "b200nerf_sh4_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),

@@ -850,12 +850,20 @@ class NeuRADModel(nn.Module):
     `get_nff_outputs` is ONE fused kernel launch (ray sampling, both proposal rounds, main field, compositing); the
     reference's 32 768-ray chunk loop (neurad.py:650-659) is unnecessary because nothing per-sample goes to HBM."""
 
-    def __init__(self, config: NeuRADConfig, trajectories: Optional[List[dict]] = None) -> None:
+    def __init__(self, config: NeuRADConfig, trajectories: Optional[List[dict]] = None, implementation: str = "torch") -> None:
+        """`implementation`: which of the reference's two parameter layouts the model holds (models/neurad.py:146) --
+        "torch" (per-level hashed tables, nn.Linear MLPs; trainable here) or "tcnn" (the reference's default: flat
+        `tcnn_encoding.params` vectors in tiny-cuda-nn's layout, so that a tcnn-trained checkpoint loads with
+        `load_state_dict`; inference through the fused kernels only -- SURVEY 8f row f3, tcnn_compat.py)."""
         super().__init__()
         from . import scene  # synthetic init = the reference's random init shapes
 
+        if implementation not in ("torch", "tcnn"):
+            raise ValueError("implementation must be 'torch' or 'tcnn'")
         self.config = config
-        p = scene.make_params(config, seed=0, table_scale=1e-3, trajectories=trajectories)
+        self.implementation = implementation
+        make = scene.make_params if implementation == "torch" else scene.make_params_tcnn
+        p = make(config, seed=0, table_scale=1e-3, trajectories=trajectories)
         self._names = []
         for k, v in p.items():
             if k == "static_scale":
@@ -969,10 +977,13 @@ class NeuRADModel(nn.Module):
         (sampler with density_fns -> field -> _render_weights -> renderers -> appearance), every step a stage kernel of
         the library -- the per-module API of SURVEY 8b; additionally returns the reference's training-side extras
         `weights_list` / `ray_samples_list` (neurad.py:404-405)."""
-        be = self._bind()
         # only the parameters of THIS path count (the rgb decoder's nn.Conv2d weights require grad by default, but it is
         # evaluated after this function and is inference-only)
         wants_grad = torch.is_grad_enabled() and any(getattr(self, n).requires_grad for n, _ in self._names)
+        if self.implementation == "tcnn" and (wants_grad or fused is False):
+            raise NotImplementedError("tiny-cuda-nn-layout parameters render through the fused kernels only (inference of "
+                                      "tcnn-trained checkpoints); the module walk and training use the torch layout")
+        be = self._bind()
         if fused is None:
             fused = not wants_grad  # the fused kernels are forward-only; training walks the modules (autograd operators)
         if fused:

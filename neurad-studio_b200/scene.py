@@ -141,6 +141,52 @@ def make_params(
     return p
 
 
+def make_params_tcnn(cfg: NeuRADConfig, seed: int = 0, table_scale: float = 1.0, beta: float = 20.0, device="cpu",
+                     trajectories: Optional[List[dict]] = None, mlp_gain: float = 1.0) -> Dict[str, torch.Tensor]:
+    """Random-init parameters of the same architecture under the state_dict names of a checkpoint trained with the
+    reference's default `implementation="tcnn"`: one flat `tcnn_encoding.params` per HashEncoding / MLP in tiny-cuda-nn's
+    layout (tcnn_compat.py), one 4-D grid shared by the actors, bias-free MLPs with padded widths.  fp32 master values like
+    the torch binding stores them (the binding casts to half at forward time; so does `B200Backend.load_params`)."""
+    from . import tcnn_compat as T
+
+    gen = torch.Generator(device=device).manual_seed(seed)
+    p: Dict[str, torch.Tensor] = {}
+
+    def rnd(n, scale):
+        return (torch.rand(n, generator=gen, device=device) * 2 - 1) * scale
+
+    def grids(prefix: str, gcfg):
+        ls = T.layout_of(gcfg.static, 3)
+        p[f"{prefix}.hashgrid.static_grid.{T.TCNN_SUFFIX}"] = rnd(ls["n_entries"] * ls["n_features"], table_scale)
+        p[f"{prefix}.hashgrid.static_grid.scalings"] = gcfg.static.scalings().to(device)
+        if cfg.n_actors > 0:
+            la = T.layout_of(gcfg.actor, 4)
+            p[f"{prefix}.hashgrid.actor_grids.0.{T.TCNN_SUFFIX}"] = rnd(la["n_entries"] * la["n_features"], table_scale)
+            p[f"{prefix}.hashgrid.actor_grids.0.scalings"] = gcfg.actor.scalings().to(device)
+
+    def mlp(prefix, in_dim, width, n_layers, out_dim):
+        n = sum(o * k for o, k in T.mlp_shapes(in_dim, width, n_layers - 1, out_dim))
+        p[f"{prefix}.{T.TCNN_SUFFIX}"] = rnd(n, mlp_gain * (3.0 / width) ** 0.5)
+
+    grids("field", cfg.grid)
+    mlp("field.mlp_geo", cfg.grid.static.out_dim, cfg.geo_hidden_dim, 2, cfg.nff_out_dim + 1)
+    mlp("field.mlp_feature", 16 + cfg.nff_out_dim, cfg.nff_hidden_dim, 3, cfg.nff_out_dim)
+    p["field.sdf_to_density.beta"] = torch.full((1,), float(beta), device=device)
+    for k, g in enumerate(cfg.proposal_grids):
+        grids(f"proposal_fields.{k}", g)
+        w, _ = _linear(gen, 1, g.static.out_dim, bias=False, device=device)
+        p[f"proposal_fields.{k}.density_decoder.weight"] = w
+    n_emb = cfg.num_sensors * cfg.embeds_per_sensor
+    p["appearance_embedding.weight"] = torch.randn(n_emb, cfg.appearance_dim, generator=gen, device=device)
+    mlp("lidar_decoder", cfg.feature_dim, 32, 3, 2)
+    if cfg.n_actors > 0:
+        trajs = trajectories if trajectories is not None else make_trajectories(cfg.n_actors, cfg.duration, seed=seed)
+        for k_, v in actors_state_from_trajectories(trajs, cfg.actor_bbox_padding).items():
+            p[k_] = v.to(device)
+    p["static_scale"] = torch.tensor(float(cfg.static_scale), device=device)
+    return p
+
+
 # ----------------------------------------------------------------------------------------------------------------------
 # sensors
 # ----------------------------------------------------------------------------------------------------------------------

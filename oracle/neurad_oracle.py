@@ -423,7 +423,18 @@ def hashgrid_forward(
     sg, ag = fcfg.static, fcfg.actor
     s_scal = params[f"{prefix}.hashgrid.static_grid.scalings"]
     c_mean, c_std = scaled_contraction(mean, std, params["static_scale"])
-    feats = hash_encode(c_mean.view(-1, 3), params[f"{prefix}.hashgrid.static_grid.hash_table"], s_scal, sg.table_size)
+    tcnn = f"{prefix}.hashgrid.static_grid.tcnn_encoding.params" in params  # SURVEY 8f row f3 (parity unpinned)
+    if tcnn:
+        from . import tcnn_oracle as T
+
+        def tcnn_grid(g: GridCfg, key: str, x: Tensor, n_dims: int) -> Tensor:
+            growth = float(np.exp((np.log(g.max_res) - np.log(g.min_res)) / (g.num_levels - 1))) if g.num_levels > 1 else 1.0
+            lay = T.grid_layout(g.num_levels, g.features_per_level, g.log2_hashmap_size, g.min_res, growth, n_dims)
+            return T.hashgrid_encode(lay, T.half_round(params[key].reshape(-1)), x)
+
+        feats = tcnn_grid(sg, f"{prefix}.hashgrid.static_grid.tcnn_encoding.params", c_mean.view(-1, 3), 3)
+    else:
+        feats = hash_encode(c_mean.view(-1, 3), params[f"{prefix}.hashgrid.static_grid.hash_table"], s_scal, sg.table_size)
     feats = rescale_grid_features(feats, c_mean, c_std, s_scal, sg.features_per_level)
     out_dim = sg.num_levels * sg.features_per_level
     features = feats.reshape(*times[..., 0].shape, out_dim)
@@ -461,6 +472,17 @@ def hashgrid_forward(
         return features.view(-1, out_dim), directions
     a_mean, a_std = scaled_contraction(pos, std[ray_idx, sample_idx], fcfg.actor_scale)
     a_scal = params[f"{prefix}.hashgrid.actor_grids.0.scalings"]
+    if tcnn:
+        # _get_actor_features_fast (neurad_encoding.py:270-281): ONE 4-D grid, 4th coordinate = actor index / n_actors
+        pos4 = torch.cat([a_mean.view(-1, 3), (actor_idx / cfg.n_actors).view(-1, 1).to(a_mean.dtype)], dim=-1)
+        afe = tcnn_grid(ag, f"{prefix}.hashgrid.actor_grids.0.tcnn_encoding.params", pos4, 4)
+        afe = rescale_grid_features(afe, a_mean, a_std, a_scal, ag.features_per_level)
+        padded = F.pad(afe, (0, out_dim - afe.shape[-1]))
+        features[ray_idx, sample_idx] = padded
+        if trace is not None:
+            trace["actor_id"][ray_idx, sample_idx] = actor_idx
+            trace["actor_triples"] = torch.stack([ray_idx, sample_idx, actor_idx], -1)
+        return features.view(-1, out_dim), directions
     # _get_actor_features_slow (neurad_encoding.py:283-295): one 3-D grid per actor
     afe = None
     for i_actor in actor_idx.unique():
@@ -529,8 +551,15 @@ def sh_components_l4(directions: Tensor) -> Tensor:
     return comp
 
 
-def mlp_forward(params, prefix: str, n_layers: int, x: Tensor) -> Tensor:
-    """MLP.pytorch_fwd with ReLU hidden activations, no output activation (field_components/mlp.py:142-178)."""
+def mlp_forward(params, prefix: str, n_layers: int, x: Tensor, out_dim: Optional[int] = None, width: int = 32) -> Tensor:
+    """MLP.pytorch_fwd with ReLU hidden activations, no output activation (field_components/mlp.py:142-178); with a
+    tcnn-layout parameter set (`<prefix>.tcnn_encoding.params`) the bias-free FullyFusedMLP restated in
+    oracle/tcnn_oracle.py (parity unpinned)."""
+    if f"{prefix}.tcnn_encoding.params" in params:
+        from . import tcnn_oracle as T
+
+        ws = T.mlp_unpack(params[f"{prefix}.tcnn_encoding.params"].reshape(-1), x.shape[-1], width, n_layers - 1, out_dim)
+        return T.mlp_forward(ws, x)
     for i in range(n_layers):
         x = F.linear(x, params[f"{prefix}.layers.{i}.weight"], params[f"{prefix}.layers.{i}.bias"])
         if i < n_layers - 1:
@@ -545,14 +574,19 @@ def main_field(params, cfg: NeuRADCfg, o, d, area, times, starts, ends, trace=No
     t = times[:, None, None].expand(N, S, 1)
     dirs_in = d[:, None, :].expand(N, S, 3)
     feats, dirs = hashgrid_forward(params, "field", cfg.main, cfg, mean, std, t, dirs_in, trace)
-    h = mlp_forward(params, "field.mlp_geo", 2, feats)
+    h = mlp_forward(params, "field.mlp_geo", 2, feats, out_dim=cfg.nff_out_dim + 1, width=cfg.geo_hidden_dim)
     geo_out, geo_embedding = torch.split(h, [1, cfg.nff_out_dim], dim=-1)
     sdf = geo_out.view(N, S, 1)
     with torch.no_grad():  # SHEncoding.pytorch_fwd is decorated @torch.no_grad() (encodings.py:797-800): in torch mode
         # no gradient reaches the directions, hence none reaches the actor rotations through this path
         direction_embedding = sh_components_l4(((dirs + 1.0) / 2.0).reshape(-1, 3))  # base_field.py:136-142
+        if "field.hashgrid.static_grid.tcnn_encoding.params" in params:  # tcnn's SH: x * 2 - 1 inside, its own signs
+            from . import tcnn_oracle as T
+
+            direction_embedding = T.sh4((((dirs + 1.0) / 2.0) * 2.0 - 1.0).reshape(-1, 3))
     feature = geo_embedding + mlp_forward(
-        params, "field.mlp_feature", 3, torch.cat([geo_embedding, direction_embedding], dim=-1)
+        params, "field.mlp_feature", 3, torch.cat([geo_embedding, direction_embedding], dim=-1), out_dim=cfg.nff_out_dim,
+        width=cfg.nff_hidden_dim
     )
     feature = feature.view(N, S, cfg.nff_out_dim)
     beta = params["field.sdf_to_density.beta"].abs() + 0.0001  # model_components/utils.py:24-41
@@ -703,7 +737,7 @@ def nff_outputs(
 
 def decode_lidar(params, features: Tensor) -> Tuple[Tensor, Tensor]:
     """decode_features, lidar half (neurad.py:350-357): intensity = sigmoid(o[0]), ray_drop_logit = o[1]."""
-    o = mlp_forward(params, "lidar_decoder", 3, features)
+    o = mlp_forward(params, "lidar_decoder", 3, features, out_dim=2)
     intensity, ray_drop_logit = o.split(1, dim=-1)
     return intensity.sigmoid(), ray_drop_logit
 

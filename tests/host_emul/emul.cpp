@@ -111,6 +111,38 @@ static void parse_params(const void* const* ptrs, const int* ints, const float* 
 
 extern "C" {
 
+// tiny-cuda-nn layout: after the ordinary parameter block the caller appends, per field and per grid
+// (static 3-D, actor 4-D): tcnn_ints {n_dims, dense_bits, then per level res, off, mask} and tcnn_floats {per level scale};
+// tcnn_ptrs {static params, actor params} per field.  lane_mode = 2 selects the LAYOUT = 1 instantiation.
+static const void* const* g_tcnn_ptrs = nullptr;
+static const int* g_tcnn_ints = nullptr;
+static const float* g_tcnn_floats = nullptr;
+int emul_set_tcnn(const void* const* ptrs, const int* ints, const float* floats) {
+  g_tcnn_ptrs = ptrs; g_tcnn_ints = ints; g_tcnn_floats = floats;
+  return 0;
+}
+static void apply_tcnn(RenderParams& P, int n_actors) {
+  int pi = 0, ii = 0, fi = 0;
+  for (int f = 0; f < 3; ++f) {
+    FieldGrids& fg = P.fields[f];
+    Grid* gs[2] = {&fg.stat, &fg.act};
+    for (int k = 0; k < 2; ++k) {
+      Grid& g = *gs[k];
+      g.n_dims = g_tcnn_ints[ii++];
+      g.dense_bits = (uint32_t)g_tcnn_ints[ii++];
+      for (int l = 0; l < kMaxLevels; ++l) {
+        g.lvl_res[l] = (uint32_t)g_tcnn_ints[ii++];
+        g.lvl_off[l] = (uint32_t)g_tcnn_ints[ii++];
+        g.lvl_mask[l] = (uint32_t)g_tcnn_ints[ii++];
+        g.pos_scale[l] = g_tcnn_floats[fi++];
+      }
+      g.table = (const float*)g_tcnn_ptrs[pi++];
+    }
+    fg.n_actors_f = (float)(n_actors > 0 ? n_actors : 1);
+  }
+  P.layout = 1;
+}
+
 int emul_render(const void* const* ptrs, const int* ints, const float* floats, long long n_rays, int lane_mode) {
   Parsed Q;
   parse_params(ptrs, ints, floats, Q);
@@ -156,6 +188,12 @@ int emul_render(const void* const* ptrs, const int* ints, const float* floats, l
     LaneScratch sc = lane_scratch_of(scratch.data(), 0);
     std::vector<float> panel((size_t)kNff * kLaneThreads);
     MlpLaneFfma pol{mlp.data(), panel.data()};
+    if (lane_mode == 2) {
+      apply_tcnn(P, P.actors.n_actors);
+      pol.sh_tcnn = 1;
+      for (long long r = 0; r < n_rays; ++r) render_ray_lane<MlpLaneFfma, 1>(P, sc, pol, (int)(r % kLaneThreads), r, true);
+      return 0;
+    }
     for (long long r = 0; r < n_rays; ++r) render_ray_lane(P, sc, pol, (int)(r % kLaneThreads), r, true);
     return 0;
   }
@@ -176,6 +214,33 @@ int emul_render(const void* const* ptrs, const int* ints, const float* floats, l
         for (long long r = w; r < n_rays; r += n_warps) render_ray(P, shared[w], pol, r, true);
       });
   for (auto& th : threads) th.join();
+  return 0;
+}
+
+// tcnn.Encoding{HashGrid}.forward through the device functions (tcnn_corners / tcnn_corner_weight), D = 3 or 4.
+int emul_tcnn_hashgrid(const int* ints, const float* scales, const float* params, const float* x, long long n, float* out) {
+  Grid g{};
+  int ii = 0;
+  g.n_dims = ints[ii++]; g.L = ints[ii++]; g.F = ints[ii++]; g.dense_bits = (uint32_t)ints[ii++];
+  for (int l = 0; l < g.L; ++l) {
+    g.lvl_res[l] = (uint32_t)ints[ii++]; g.lvl_off[l] = (uint32_t)ints[ii++]; g.lvl_mask[l] = (uint32_t)ints[ii++];
+    g.pos_scale[l] = scales[l];
+  }
+  g.table = params;
+  for (long long i = 0; i < n; ++i)
+    for (int l = 0; l < g.L; ++l) {
+      uint32_t idx[16];
+      float frac[4];
+      if (g.n_dims == 3) tcnn_corners<3>(g, l, x + 3 * i, idx, frac); else tcnn_corners<4>(g, l, x + 4 * i, idx, frac);
+      for (int f = 0; f < g.F; ++f) {
+        float v = 0.f;
+        for (int c = 0; c < (1 << g.n_dims); ++c) {
+          const float w = g.n_dims == 3 ? tcnn_corner_weight<3>(c, frac) : tcnn_corner_weight<4>(c, frac);
+          v = std::fmaf(w, params[(size_t)idx[c] * g.F + f], v);
+        }
+        out[i * (g.L * g.F) + l * g.F + f] = v;
+      }
+    }
   return 0;
 }
 

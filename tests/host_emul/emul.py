@@ -90,11 +90,66 @@ def _pack_params(pk, cfg, params, pdf_u, field_of_round):
     floats.append(cfg.duration)
 
 
+def _tcnn_level_ints(layout):
+    out, dense_bits = [], 0
+    for l in range(16):
+        if l < layout["n_levels"]:
+            dense_bits |= (1 << l) if layout["dense"][l] else 0
+            out += [layout["resolution"][l], layout["offset"][l], layout["size"][l] if layout["dense"][l] else layout["size"][l] - 1]
+        else:
+            out += [0, 0, 0]
+    return dense_bits, out
+
+
+def _torch_shaped_standin(cfg, params):
+    """A torch-layout dict with the same non-grid tensors (MLPs unpacked from the tcnn vectors, zero biases) and dummy hash
+    tables, so that the ordinary parameter block can be packed; the grids are then overridden with the tcnn layout."""
+    from neurad_studio_b200 import tcnn_compat as T
+
+    q = {k: v for k, v in params.items() if T.TCNN_SUFFIX not in k}
+    for pre, g in (("field", cfg.grid), ("proposal_fields.0", cfg.proposal_grid_1), ("proposal_fields.1", cfg.proposal_grid_2)):
+        q[f"{pre}.hashgrid.static_grid.hash_table"] = torch.zeros(8, g.static.hashgrid_dim)
+        for a in range(cfg.n_actors):
+            q[f"{pre}.hashgrid.actor_grids.{a}.hash_table"] = torch.zeros(8, g.actor.hashgrid_dim)
+    for pre, dims in (("field.mlp_geo", (cfg.grid.static.out_dim, cfg.geo_hidden_dim, 2, cfg.nff_out_dim + 1)),
+                      ("field.mlp_feature", (cfg.nff_out_dim + 16, cfg.nff_hidden_dim, 3, cfg.nff_out_dim)),
+                      ("lidar_decoder", (cfg.feature_dim, 32, 3, 2))):
+        ts = T.mlp_tensors(params, pre, *dims, "cpu")
+        for i in range(dims[2]):
+            q[f"{pre}.layers.{i}.weight"], q[f"{pre}.layers.{i}.bias"] = ts[2 * i], ts[2 * i + 1]
+    return q
+
+
 def render(cfg, params, rays, pdf_u, field_of_round=(2, 2), lane_mode=False):
-    """cfg: neurad_studio_b200.NeuRADConfig; params: reference-named tensors (CPU); rays: dict of CPU tensors."""
+    """cfg: neurad_studio_b200.NeuRADConfig; params: reference-named tensors (CPU); rays: dict of CPU tensors.  A
+    tcnn-layout parameter set (tcnn_compat.is_tcnn_state) runs the LAYOUT = 1 instantiation of the ray-per-lane code."""
+    from neurad_studio_b200 import tcnn_compat as T
+
     lib = ctypes.CDLL(build())
     lib.emul_render.restype = ctypes.c_int
     pk = _Pack()
+    tcnn_keep = None
+    if T.is_tcnn_state(params):
+        assert lane_mode, "the tcnn layout exists in the ray-per-lane kernels only"
+        t_ptrs, t_ints, t_floats, tcnn_keep = [], [], [], []
+        for pre, g in (("field", cfg.grid), ("proposal_fields.0", cfg.proposal_grid_1), ("proposal_fields.1", cfg.proposal_grid_2)):
+            for name, gs, nd in (("static_grid", g.static, 3), ("actor_grids.0", g.actor, 4)):
+                lay = T.layout_of(gs, nd)
+                bits, li = _tcnn_level_ints(lay)
+                t_ints += [nd, bits] + li
+                t_floats += lay["scale"] + [0.0] * (16 - lay["n_levels"])
+                key = f"{pre}.hashgrid.{name}.{T.TCNN_SUFFIX}"
+                if key in params:
+                    t = T.half_round(params[key].reshape(-1)).contiguous()
+                    tcnn_keep.append(t)
+                    t_ptrs.append(ctypes.c_void_p(t.data_ptr()))
+                else:
+                    t_ptrs.append(None)
+        arrs = ((ctypes.c_void_p * len(t_ptrs))(*t_ptrs), (ctypes.c_int * len(t_ints))(*t_ints), (ctypes.c_float * len(t_floats))(*t_floats))
+        tcnn_keep.append(arrs)
+        lib.emul_set_tcnn(*arrs)
+        params = _torch_shaped_standin(cfg, params)
+        lane_mode = 2
     _pack_params(pk, cfg, params, pdf_u, field_of_round)
     keep, P = pk.keep, pk.P
     sp = cfg.sampling
@@ -125,7 +180,23 @@ def render(cfg, params, rays, pdf_u, field_of_round=(2, 2), lane_mode=False):
         P(out[k])
         out[k] = keep[-1]
     c_ptrs, c_ints, c_floats = pk.c_arrays()
-    rc = lib.emul_render(c_ptrs, c_ints, c_floats, ctypes.c_longlong(n), ctypes.c_int(1 if lane_mode else 0))
+    rc = lib.emul_render(c_ptrs, c_ints, c_floats, ctypes.c_longlong(n), ctypes.c_int(int(lane_mode)))
+    assert rc == 0
+    del tcnn_keep
+    return out
+
+
+def tcnn_hashgrid(layout, params, x):
+    """tcnn.Encoding{HashGrid}.forward through the device functions: x [P, n_dims] -> [P, L*F]."""
+    lib = ctypes.CDLL(build())
+    bits, li = _tcnn_level_ints(layout)
+    ints = [layout["n_dims"], layout["n_levels"], layout["n_features"], bits] + li[: 3 * layout["n_levels"]]
+    c_ints = (ctypes.c_int * len(ints))(*ints)
+    c_sc = (ctypes.c_float * layout["n_levels"])(*layout["scale"])
+    p, xs = params.contiguous().float(), x.contiguous().float()
+    out = torch.zeros(xs.shape[0], layout["n_levels"] * layout["n_features"])
+    rc = lib.emul_tcnn_hashgrid(c_ints, c_sc, ctypes.c_void_p(p.data_ptr()), ctypes.c_void_p(xs.data_ptr()), ctypes.c_longlong(xs.shape[0]),
+                                ctypes.c_void_p(out.data_ptr()))
     assert rc == 0
     return out
 
