@@ -463,7 +463,11 @@ def main():
         global _SAVED_STDOUT
         _SAVED_STDOUT = os.dup(1)
         os.dup2(2, 1)
-        dist.init_process_group("nccl", device_id=dev)
+        import datetime
+
+        # a mis-ordered collective or a wedged kernel should cost minutes, not NCCL's 10-minute default plus its debug dump
+        os.environ.setdefault("TORCH_NCCL_DUMP_ON_TIMEOUT", "0")
+        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=180))
     from neurad_studio_b200 import scene
     from neurad_studio_b200.nerfstudio_api import NeuRADModel
 
@@ -517,6 +521,8 @@ def main():
     ms_e2e = timed(step.run_e2e, args.steps)
     e2e_launches = step.e2e_launches // args.steps
     # the host buffers the e2e arm filled must hold what the API returns on the device (last image + the sweep re-rendered)
+    if step.p2p:
+        be.set_peer_outputs(None)  # the check re-renders locally only (run_device / run_e2e bind their own row offsets)
     with torch.no_grad():
         chk = model.get_outputs_for_camera_ray_bundle(step.cameras.generate_rays(len(cams) - 1))
         chk_l, _ = model.get_outputs_for_lidar(step.lidars, {"lidar": step.points_pinned, "lidar_idx": 0})

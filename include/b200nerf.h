@@ -78,6 +78,12 @@ int b200nerf_destroy(b200nerf_ctx* ctx);
 
 /* ---- parameters --------------------------------------------------------------------------------------- */
 
+/* The stream the b200nerf_set_* entry points issue their packing kernels and device-to-device copies on (default: the
+ * legacy default stream).  Bind the stream the parameters were last written on -- e.g. torch's current stream after an
+ * optimizer step -- and renders launched on the same stream see the new parameters in order; nothing synchronises the
+ * device (b200nerf_set_rgb_decoder alone waits for this stream before it returns). */
+int b200nerf_set_param_stream(b200nerf_ctx* ctx, void* stream);
+
 /* NeuRADHashEncoding of one field (field_components/neurad_encoding.py:85-131): the static grid
  * `static_grid.hash_table` [L*T, F] and, in torch mode, one 3-D grid per actor `actor_grids[i].hash_table`.
  * `actor_tables_host` is a HOST array of `n_actors` device pointers (NULL when n_actors == 0).

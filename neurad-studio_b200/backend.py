@@ -98,6 +98,9 @@ class B200Backend:
         both proposal rounds evaluate proposal_fields[1] (late-binding closures at models/neurad.py:248)."""
         self.cfg = cfg
         self._owner = None  # a model that binds through NeuRADModel._bind() records itself after this call
+        # packing kernels / copies of the set_* calls go on torch's current stream: ordered after the optimizer step that
+        # wrote the parameters and before the renders that read the packed copies (no device-wide synchronisation)
+        self._check(self.lib.b200nerf_set_param_stream(self._h, self._stream))
         p = params
         n_act = cfg.n_actors
         # dynamic_actors.actor_to_id (dynamic_actors.py:161, read at neurad_encoding.py:181): actor index -> hash-grid index;
@@ -746,6 +749,7 @@ class B200Backend:
         BatchNorms are folded into the 7x7 convolutions inside the library (eval-mode semantics)."""
         keep = []
         self._dec_owner = None
+        self._check(self.lib.b200nerf_set_param_stream(self._h, self._stream))
         pre = prefix + "." if prefix else ""
 
         def t(key):

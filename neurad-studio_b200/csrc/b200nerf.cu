@@ -41,6 +41,8 @@ struct b200nerf_ctx {
   float* d_decoder[3] = {nullptr, nullptr, nullptr};
   float* d_main_mlp = nullptr;
   float* d_main_mlp_nn = nullptr;
+  cudaStream_t param_stream = 0;  // stream of the set_* packing kernels / copies (b200nerf_set_param_stream)
+  int act_alloc_actors = 0, act_alloc_times = 0;  // sizes the actor arrays are currently allocated for
   int layout = 0;    // 0: torch-mode grids (b200nerf_set_field_grids); 1: tiny-cuda-nn layout (b200nerf_set_field_grids_tcnn)
   int field_layout[3] = {0, 0, 0};
   int mlp_mode = 3;  // 3 = ray-per-lane in two kernels (sampling | shading + tcgen05), 2 = the same as one fused kernel, 1 = warp-per-ray + tcgen05 (3xTF32), 0 = warp-per-ray + CUDA-core fp32 FFMA
@@ -1147,14 +1149,14 @@ int b200nerf_set_proposal_decoder(b200nerf_ctx* c, int field, const float* weigh
   REQUIRE(weight && in_dim == 6, "density_decoder must be Linear(6, 1)");
   DeviceGuard g(c->device);
   if (!c->d_decoder[field]) CUDA_TRY(cudaMalloc((void**)&c->d_decoder[field], sizeof(float) * 8));
-  CUDA_TRY(cudaMemcpy(c->d_decoder[field], weight, sizeof(float) * in_dim, cudaMemcpyDeviceToDevice));
+  CUDA_TRY(cudaMemcpyAsync(c->d_decoder[field], weight, sizeof(float) * in_dim, cudaMemcpyDeviceToDevice, c->param_stream));
   c->fields[field].decoder = c->d_decoder[field];
   return 0;
 }
 
-static int pack(const float* w, const float* b, int out_f, int in_f, int outp, float* dw, float* db) {
+static int pack(cudaStream_t st, const float* w, const float* b, int out_f, int in_f, int outp, float* dw, float* db) {
   int n = in_f * outp > outp ? in_f * outp : outp;
-  pack_linear_kernel<<<(n + 255) / 256, 256>>>(w, b, out_f, in_f, outp, dw, db);
+  pack_linear_kernel<<<(n + 255) / 256, 256, 0, st>>>(w, b, out_f, in_f, outp, dw, db);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return fail(B200NERF_ERR_CUDA, std::string("pack_linear: ") + cudaGetErrorString(e));
   return 0;
@@ -1168,11 +1170,11 @@ int b200nerf_set_main_mlps(b200nerf_ctx* c, const float* gw0, const float* gb0, 
   DeviceGuard g(c->device);
   if (!c->d_main_mlp) CUDA_TRY(cudaMalloc((void**)&c->d_main_mlp, sizeof(float) * kMainMlpFloats));
   float* m = c->d_main_mlp;
-  if (int e = pack(gw0, gb0, kHidden, kGeoIn, kHidden, m + kOffGeoW0, m + kOffGeoB0)) return e;
-  if (int e = pack(gw1, gb1, kNff + 1, kHidden, kGeoOutP, m + kOffGeoW1, m + kOffGeoB1)) return e;
-  if (int e = pack(fw0, fb0, kHidden, kNff + kSh, kHidden, m + kOffFeatW0, m + kOffFeatB0)) return e;
-  if (int e = pack(fw1, fb1, kHidden, kHidden, kHidden, m + kOffFeatW1, m + kOffFeatB1)) return e;
-  if (int e = pack(fw2, fb2, kNff, kHidden, kNff, m + kOffFeatW2, m + kOffFeatB2)) return e;
+  if (int e = pack(c->param_stream, gw0, gb0, kHidden, kGeoIn, kHidden, m + kOffGeoW0, m + kOffGeoB0)) return e;
+  if (int e = pack(c->param_stream, gw1, gb1, kNff + 1, kHidden, kGeoOutP, m + kOffGeoW1, m + kOffGeoB1)) return e;
+  if (int e = pack(c->param_stream, fw0, fb0, kHidden, kNff + kSh, kHidden, m + kOffFeatW0, m + kOffFeatB0)) return e;
+  if (int e = pack(c->param_stream, fw1, fb1, kHidden, kHidden, kHidden, m + kOffFeatW1, m + kOffFeatB1)) return e;
+  if (int e = pack(c->param_stream, fw2, fb2, kNff, kHidden, kNff, m + kOffFeatW2, m + kOffFeatB2)) return e;
   if (!c->d_main_mlp_nn) CUDA_TRY(cudaMalloc((void**)&c->d_main_mlp_nn, sizeof(float) * kNnMlpFloats));
   {
     float* n = c->d_main_mlp_nn;
@@ -1181,9 +1183,9 @@ int b200nerf_set_main_mlps(b200nerf_ctx* c, const float* gw0, const float* gb0, 
     const int cnt[10] = {kHidden * kGeoIn, kHidden, (kNff + 1) * kHidden, kNff + 1, kHidden * (kNff + kSh), kHidden,
                          kHidden * kHidden, kHidden, kNff * kHidden, kNff};
     for (int i = 0; i < 10; ++i)
-      CUDA_TRY(cudaMemcpy(n + off[i], src[i], sizeof(float) * cnt[i], cudaMemcpyDeviceToDevice));
+      CUDA_TRY(cudaMemcpyAsync(n + off[i], src[i], sizeof(float) * cnt[i], cudaMemcpyDeviceToDevice, c->param_stream));
   }
-  CUDA_TRY(cudaDeviceSynchronize());
+  // no synchronisation: the packing runs on the parameter stream (the caller's), render launches on it follow in order
   c->beta = beta;
   c->have_main_mlp = true;
   return 0;
@@ -1196,10 +1198,9 @@ int b200nerf_set_lidar_decoder(b200nerf_ctx* c, const float* w0, const float* b0
   DeviceGuard g(c->device);
   if (!c->d_lidar_mlp) CUDA_TRY(cudaMalloc((void**)&c->d_lidar_mlp, sizeof(float) * kLidarMlpFloats));
   float* m = c->d_lidar_mlp;
-  if (int e = pack(w0, b0, kHidden, kNff + kApp, kHidden, m + kOffLidW0, m + kOffLidB0)) return e;
-  if (int e = pack(w1, b1, kHidden, kHidden, kHidden, m + kOffLidW1, m + kOffLidB1)) return e;
-  if (int e = pack(w2, b2, 2, kHidden, kLidOutP, m + kOffLidW2, m + kOffLidB2)) return e;
-  CUDA_TRY(cudaDeviceSynchronize());
+  if (int e = pack(c->param_stream, w0, b0, kHidden, kNff + kApp, kHidden, m + kOffLidW0, m + kOffLidB0)) return e;
+  if (int e = pack(c->param_stream, w1, b1, kHidden, kHidden, kHidden, m + kOffLidW1, m + kOffLidB1)) return e;
+  if (int e = pack(c->param_stream, w2, b2, 2, kHidden, kLidOutP, m + kOffLidW2, m + kOffLidB2)) return e;
   c->have_lidar = true;
   return 0;
 }
@@ -1221,26 +1222,32 @@ int b200nerf_set_actors(b200nerf_ctx* c, int n_actors, int n_times, const float*
                         const float* pos, const uint8_t* present, const float* sizes, const float* padding_host) {
   REQUIRE(c, "ctx is NULL");
   DeviceGuard g(c->device);
-  cudaFree(c->d_act_times); cudaFree(c->d_act_kf); cudaFree(c->d_act_bounds); cudaFree(c->d_act_radii);
-  cudaFree(c->d_act_present);
-  c->d_act_times = c->d_act_kf = c->d_act_bounds = c->d_act_radii = nullptr;
-  c->d_act_present = nullptr;
+  if (n_actors <= 0 || n_actors != c->act_alloc_actors || n_times != c->act_alloc_times) {  // (re)allocate only on a shape change
+    cudaFree(c->d_act_times); cudaFree(c->d_act_kf); cudaFree(c->d_act_bounds); cudaFree(c->d_act_radii);
+    cudaFree(c->d_act_present);
+    c->d_act_times = c->d_act_kf = c->d_act_bounds = c->d_act_radii = nullptr;
+    c->d_act_present = nullptr;
+    c->act_alloc_actors = c->act_alloc_times = 0;
+  }
   c->actors = Actors{};
   if (n_actors <= 0) return 0;
   REQUIRE(n_times >= 1 && timestamps && rot6 && pos && present && sizes && padding_host, "NULL actor tensor");
   size_t ta = (size_t)n_times * n_actors;
-  CUDA_TRY(cudaMalloc((void**)&c->d_act_times, sizeof(float) * n_times));
-  CUDA_TRY(cudaMalloc((void**)&c->d_act_kf, sizeof(float) * 9 * ta));
-  CUDA_TRY(cudaMalloc((void**)&c->d_act_bounds, sizeof(float) * 3 * n_actors));
-  CUDA_TRY(cudaMalloc((void**)&c->d_act_radii, sizeof(float) * n_actors));
-  CUDA_TRY(cudaMalloc((void**)&c->d_act_present, ta));
-  CUDA_TRY(cudaMemcpy(c->d_act_times, timestamps, sizeof(float) * n_times, cudaMemcpyDeviceToDevice));
-  CUDA_TRY(cudaMemcpy(c->d_act_present, present, ta, cudaMemcpyDeviceToDevice));
+  if (c->act_alloc_actors == 0) {
+    CUDA_TRY(cudaMalloc((void**)&c->d_act_times, sizeof(float) * n_times));
+    CUDA_TRY(cudaMalloc((void**)&c->d_act_kf, sizeof(float) * 9 * ta));
+    CUDA_TRY(cudaMalloc((void**)&c->d_act_bounds, sizeof(float) * 3 * n_actors));
+    CUDA_TRY(cudaMalloc((void**)&c->d_act_radii, sizeof(float) * n_actors));
+    CUDA_TRY(cudaMalloc((void**)&c->d_act_present, ta));
+    c->act_alloc_actors = n_actors;
+    c->act_alloc_times = n_times;
+  }
+  CUDA_TRY(cudaMemcpyAsync(c->d_act_times, timestamps, sizeof(float) * n_times, cudaMemcpyDeviceToDevice, c->param_stream));
+  CUDA_TRY(cudaMemcpyAsync(c->d_act_present, present, ta, cudaMemcpyDeviceToDevice, c->param_stream));
   int n = (int)(ta > (size_t)n_actors ? ta : n_actors);
-  actors_prep_kernel<<<(n + 127) / 128, 128>>>(n_times, n_actors, rot6, pos, sizes, padding_host[0], padding_host[1],
-                                               padding_host[2], c->d_act_kf, c->d_act_bounds, c->d_act_radii);
+  actors_prep_kernel<<<(n + 127) / 128, 128, 0, c->param_stream>>>(n_times, n_actors, rot6, pos, sizes, padding_host[0], padding_host[1],
+                                                                  padding_host[2], c->d_act_kf, c->d_act_bounds, c->d_act_radii);
   CUDA_TRY(cudaGetLastError());
-  CUDA_TRY(cudaDeviceSynchronize());
   c->actors.n_actors = n_actors;
   c->actors.n_times = n_times;
   c->actors.times = c->d_act_times;
@@ -1944,19 +1951,19 @@ int b200nerf_set_rgb_decoder(b200nerf_ctx* c, const b200nerf_rgb_decoder_params*
       const b200nerf_conv_bn_params& q = p->block[b][k];
       REQUIRE(q.conv_weight && q.conv_bias && q.bn_weight && q.bn_bias && q.bn_running_mean && q.bn_running_var, "NULL BasicBlock tensor");
       const int i = 2 * b + k, n = dec::kTaps * dec::kC * dec::kC;
-      dec::dec_fold_conv_kernel<<<(n + 255) / 256, 256>>>(q.conv_weight, q.conv_bias, q.bn_weight, q.bn_bias, q.bn_running_mean,
+      dec::dec_fold_conv_kernel<<<(n + 255) / 256, 256, 0, c->param_stream>>>(q.conv_weight, q.conv_bias, q.bn_weight, q.bn_bias, q.bn_running_mean,
                                                           q.bn_running_var, p->bn_eps, c->d_dec_wimg[i], c->d_dec_wf32[i],
                                                           c->d_dec_bias + i * dec::kC);
       CUDA_TRY(cudaGetLastError());
     }
   const DecSmall d = dec_small(c->d_dec_small);
-  CUDA_TRY(cudaMemcpy(d.in_w, p->in_conv.weight, sizeof(float) * dec::kC * p->in_dim, cudaMemcpyDeviceToDevice));
-  CUDA_TRY(cudaMemcpy(d.in_b, p->in_conv.bias, sizeof(float) * dec::kC, cudaMemcpyDeviceToDevice));
-  CUDA_TRY(cudaMemcpy(d.up_w, p->up_conv.weight, sizeof(float) * dec::kC * dec::kC * 9, cudaMemcpyDeviceToDevice));
-  CUDA_TRY(cudaMemcpy(d.up_b, p->up_conv.bias, sizeof(float) * dec::kC, cudaMemcpyDeviceToDevice));
-  CUDA_TRY(cudaMemcpy(d.out_w, p->out_conv.weight, sizeof(float) * 3 * dec::kC, cudaMemcpyDeviceToDevice));
-  CUDA_TRY(cudaMemcpy(d.out_b, p->out_conv.bias, sizeof(float) * 3, cudaMemcpyDeviceToDevice));
-  CUDA_TRY(cudaDeviceSynchronize());
+  CUDA_TRY(cudaMemcpyAsync(d.in_w, p->in_conv.weight, sizeof(float) * dec::kC * p->in_dim, cudaMemcpyDeviceToDevice, c->param_stream));
+  CUDA_TRY(cudaMemcpyAsync(d.in_b, p->in_conv.bias, sizeof(float) * dec::kC, cudaMemcpyDeviceToDevice, c->param_stream));
+  CUDA_TRY(cudaMemcpyAsync(d.up_w, p->up_conv.weight, sizeof(float) * dec::kC * dec::kC * 9, cudaMemcpyDeviceToDevice, c->param_stream));
+  CUDA_TRY(cudaMemcpyAsync(d.up_b, p->up_conv.bias, sizeof(float) * dec::kC, cudaMemcpyDeviceToDevice, c->param_stream));
+  CUDA_TRY(cudaMemcpyAsync(d.out_w, p->out_conv.weight, sizeof(float) * 3 * dec::kC, cudaMemcpyDeviceToDevice, c->param_stream));
+  CUDA_TRY(cudaMemcpyAsync(d.out_b, p->out_conv.bias, sizeof(float) * 3, cudaMemcpyDeviceToDevice, c->param_stream));
+  CUDA_TRY(cudaStreamSynchronize(c->param_stream));  // the caller may release its parameter tensors when this returns
   c->dec_in_dim = p->in_dim;
   c->have_rgb_decoder = true;
   return 0;
@@ -2056,6 +2063,12 @@ int b200nerf_set_peer_outputs(b200nerf_ctx* c, const b200nerf_peer_outputs* peer
     REQUIRE(peers->features[p] && peers->depth[p] && peers->accumulation[p], "NULL peer buffer");
   }
   c->peers = *peers;
+  return 0;
+}
+
+int b200nerf_set_param_stream(b200nerf_ctx* c, void* stream) {
+  REQUIRE(c, "ctx is NULL");
+  c->param_stream = (cudaStream_t)stream;
   return 0;
 }
 

@@ -94,6 +94,7 @@ SIGNATURES = {
     "b200nerf_set_sampling": (c_int, [c_void_p, c_int, c_int, c_int, c_float, c_float, c_float, c_float,
                                       POINTER(c_float), POINTER(c_float), POINTER(c_int), c_float]),
     "b200nerf_nff_render_fwd": (c_int, [c_void_p, POINTER(Rays), c_int64, POINTER(Outputs), POINTER(Trace), c_void_p]),
+    "b200nerf_set_param_stream": (c_int, [c_void_p, c_void_p]),
     "b200nerf_set_field_grids_tcnn": (c_int, [c_void_p, c_int, POINTER(TcnnGridDesc), c_void_p, POINTER(TcnnGridDesc), c_void_p, c_int,
                                               c_float, c_float]),
     "b200nerf_tcnn_hashgrid_fwd": (c_int, [c_void_p, POINTER(TcnnGridDesc), c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),

@@ -4,8 +4,8 @@ set -u
 N=${1:-2}
 mkdir -p gpurun_out
 nvidia-smi topo -m > gpurun_out/r02e_topo_n$N.txt 2>&1
-python -m pytest tests/test_multi_gpu.py -q > gpurun_out/r02e_mgpu_test_n$N.log 2>&1; tail -3 gpurun_out/r02e_mgpu_test_n$N.log
-python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29533 bench.py --gpus $N --steps 10 --warmup 3 \
+timeout -k 10 300 python -m pytest tests/test_multi_gpu.py -q > gpurun_out/r02e_mgpu_test_n$N.log 2>&1; tail -3 gpurun_out/r02e_mgpu_test_n$N.log
+timeout -k 10 420 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29533 bench.py --gpus $N --steps 10 --warmup 3 \
   > gpurun_out/r02e_bench_n$N.json 2> gpurun_out/r02e_bench_n$N.err
 echo "bench rc=$?"; tail -4 gpurun_out/r02e_bench_n$N.err | cut -c1-300
 python - <<PY
