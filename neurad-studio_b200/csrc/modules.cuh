@@ -137,23 +137,36 @@ __global__ void __launch_bounds__(kModWarps * 32) neurad_encoding_bwd_kernel(con
                                                                               const EncodingBwdArgs a) {
   __shared__ ActorFrame frames[kModWarps][kModMaxActors];
   __shared__ float dec_part[kModWarps][kModMaxDim];
+  static_assert((kModWarps & (kModWarps - 1)) == 0, "rays per CTA must be a power of two");
   const int warp = threadIdx.x >> 5, ln = threadIdx.x & 31;
-  const int64_t ray = (int64_t)blockIdx.x * kModWarps + warp;
+  // A CTA owns kModWarps rays.  Thread t works on ray slot t % kModWarps and walks that ray's samples with stride
+  // blockDim / kModWarps, so one warp instruction carries 4 consecutive samples of each of 8 DIFFERENT rays.  (The forward
+  // kernel's mapping -- a warp = 32 consecutive samples of ONE ray -- makes most lanes of a scatter instruction hit the same
+  // coarse-level rows: after resampling, neighbouring samples of a ray share their cells, and same-address reductions
+  // serialise.  profiles/r02_train_step_launches.txt: 176 M reductions of round 1 took as long as round 0's 352 M.)
+  const int slot = threadIdx.x & (kModWarps - 1), sub = threadIdx.x / kModWarps, sub_n = (kModWarps * 32) / kModWarps;
+  const int64_t ray = (int64_t)blockIdx.x * kModWarps + slot;
   const int D = fg.stat.L * fg.stat.F;
   const bool density_mode = a.ddensity != nullptr;
   float dec_acc[kModMaxDim];
   if (density_mode && a.grad_decoder)
     for (int k = 0; k < D; ++k) dec_acc[k] = 0.f;
-  if (ray < a.n_rays) {
-    if (A.n_actors > 0) {
-      int left, right;
-      float frac;
-      keyframe_bracket(A, a.times[ray], left, right, frac);
-      for (int k = ln; k < A.n_actors; k += 32) actor_frame(A, k, left, right, frac, frames[warp][k]);
+  if (A.n_actors > 0) {  // the CTA's rays x actors frames, built cooperatively
+    for (int i = threadIdx.x; i < kModWarps * A.n_actors; i += kModWarps * 32) {
+      const int sl = i / A.n_actors, k = i - sl * A.n_actors;
+      const int64_t r = (int64_t)blockIdx.x * kModWarps + sl;
+      if (r < a.n_rays) {
+        int left, right;
+        float frac;
+        keyframe_bracket(A, a.times[r], left, right, frac);
+        actor_frame(A, k, left, right, frac, frames[sl][k]);
+      }
     }
-    __syncwarp();
+    __syncthreads();
+  }
+  if (ray < a.n_rays) {
     const float flip = a.flip ? a.flip[ray] : 1.0f;
-    for (int s = ln; s < a.S; s += 32) {
+    for (int s = sub; s < a.S; s += sub_n) {
       const int64_t i = ray * a.S + s;
       Gauss g = {a.mean[3 * i], a.mean[3 * i + 1], a.mean[3 * i + 2], a.std[i]};
       float dfeat[kModMaxDim];
@@ -162,14 +175,14 @@ __global__ void __launch_bounds__(kModWarps * 32) neurad_encoding_bwd_kernel(con
         const float gd = a.ddensity[i] * fminf(fmaxf(a.density[i], 3.0590232e-07f), 3269017.372f);
         if (a.grad_decoder) {
           float feat[kModMaxDim];
-          neurad_encode_point(fg, frames[warp], A.n_actors, g, feat, nullptr, flip);
+          neurad_encode_point(fg, frames[slot], A.n_actors, g, feat, nullptr, flip);
           for (int k = 0; k < D; ++k) dec_acc[k] = fmaf(gd, feat[k], dec_acc[k]);
         }
         for (int k = 0; k < D; ++k) dfeat[k] = gd * __ldg(fg.decoder + k);
       } else {
         for (int k = 0; k < D; ++k) dfeat[k] = a.dfeatures[i * D + k];
       }
-      neurad_encode_point_bwd(fg, a.grad_static, a.grad_actor_tables, frames[warp], A.n_actors, g, flip, dfeat);
+      neurad_encode_point_bwd(fg, a.grad_static, a.grad_actor_tables, frames[slot], A.n_actors, g, flip, dfeat);
     }
   }
   if (density_mode && a.grad_decoder) {  // warp, then block reduction; one atomic per CTA and decoder weight
