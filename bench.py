@@ -88,13 +88,17 @@ def measured_peaks():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+RENDER_KERNEL_SOURCES = ("b200nerf.cu", "nff_device.h", "nff_lane.h", "nff_params.h", "simt.h", "tc_mlp.cuh")
+
+
 def kernel_sources_sha() -> str:
-    """Hash of the CUDA sources the timed kernels are built from: profiles/traffic.json records the one it was captured
-    at, and a capture of a different binary is not reported as this run's traffic."""
+    """Hash of the CUDA sources the two timed render kernels are built from (the entry-point file and the headers they
+    include; the decoder / training-operator headers are not part of them): profiles/traffic.json records the one it was
+    captured at, and a capture of a different binary is not reported as this run's traffic."""
     h = hashlib.sha256()
-    for f in sorted(glob.glob(os.path.join(ROOT, "neurad-studio_b200", "csrc", "*"))):
-        h.update(os.path.basename(f).encode())
-        h.update(open(f, "rb").read())
+    for name in RENDER_KERNEL_SOURCES:
+        h.update(name.encode())
+        h.update(open(os.path.join(ROOT, "neurad-studio_b200", "csrc", name), "rb").read())
     return h.hexdigest()[:16]
 
 
