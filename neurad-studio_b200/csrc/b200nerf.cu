@@ -1624,7 +1624,8 @@ int b200nerf_neurad_encoding_bwd(b200nerf_ctx* c, int field, const float* mean, 
   EncodingBwdArgs a{mean, std, times, flip, dfeatures, density, ddensity, grad_static_table, d_ptrs, grad_decoder, n_rays,
                     n_samples};
   const unsigned grid = (unsigned)((n_rays + kModWarps - 1) / kModWarps);
-  neurad_encoding_bwd_kernel<<<grid, kModWarps * 32, 0, (cudaStream_t)stream>>>(fg, c->actors, a);
+  if (!launch_neurad_encoding_bwd(fg, c->actors, a, grid, (cudaStream_t)stream))
+    return fail(B200NERF_ERR_UNSUPPORTED, "encoding backward: features mode needs 4 features / level, density mode 1 (<= 8 levels)");
   CUDA_TRY(cudaGetLastError());
   return 0;
 }

@@ -133,6 +133,10 @@ struct EncodingBwdArgs {
 
 // Backward of neurad_encoding_fwd_kernel: scatter-add into the hash tables (RED.ADD.F32).  Density mode folds the
 // proposal head in: g = dL/d density * density (trunc_exp' = exp), dfeat_k = g * decoder_k, d decoder_k += g * feat_k.
+// MODE 1: features (F = 4, L <= 8), MODE 2: density (F = 1, L <= 8) -- the shapes b200nerf_set_field_grids admits; everything
+// stays in registers (nff_modules.h: encode_levels_bwd_t).  The generic any-shape device function (neurad_encode_point_bwd,
+// per-sample rows in local memory) is what round 1 ran here; it remains the cross-check of tests/test_module_bwd_emul.py.
+template <int MODE>
 __global__ void __launch_bounds__(kModWarps * 32) neurad_encoding_bwd_kernel(const FieldGrids fg, const Actors A,
                                                                               const EncodingBwdArgs a) {
   __shared__ ActorFrame frames[kModWarps][kModMaxActors];
@@ -147,10 +151,11 @@ __global__ void __launch_bounds__(kModWarps * 32) neurad_encoding_bwd_kernel(con
   const int slot = threadIdx.x & (kModWarps - 1), sub = threadIdx.x / kModWarps, sub_n = (kModWarps * 32) / kModWarps;
   const int64_t ray = (int64_t)blockIdx.x * kModWarps + slot;
   const int D = fg.stat.L * fg.stat.F;
-  const bool density_mode = a.ddensity != nullptr;
-  float dec_acc[kModMaxDim];
-  if (density_mode && a.grad_decoder)
-    for (int k = 0; k < D; ++k) dec_acc[k] = 0.f;
+  constexpr bool density_mode = MODE == 2;
+  static_assert(MODE == 1 || MODE == 2, "features or density mode");
+  float dec_acc[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) dec_acc[k] = 0.f;
   if (A.n_actors > 0) {  // the CTA's rays x actors frames, built cooperatively
     for (int i = threadIdx.x; i < kModWarps * A.n_actors; i += kModWarps * 32) {
       const int sl = i / A.n_actors, k = i - sl * A.n_actors;
@@ -164,31 +169,35 @@ __global__ void __launch_bounds__(kModWarps * 32) neurad_encoding_bwd_kernel(con
     }
     __syncthreads();
   }
+  // fast paths (nff_modules.h: encode_levels_bwd_t): NeuRAD's grid shapes, everything in registers
   if (ray < a.n_rays) {
     const float flip = a.flip ? a.flip[ray] : 1.0f;
     for (int s = sub; s < a.S; s += sub_n) {
       const int64_t i = ray * a.S + s;
       Gauss g = {a.mean[3 * i], a.mean[3 * i + 1], a.mean[3 * i + 2], a.std[i]};
-      float dfeat[kModMaxDim];
-      if (density_mode) {
+      if (MODE == 1) {
+        neurad_encode_point_bwd_t<8, 4, false>(fg, a.grad_static, a.grad_actor_tables, frames[slot], A.n_actors, g, flip,
+                                               a.dfeatures + i * D, 1.0f, nullptr);
+        continue;
+      }
+      if (MODE == 2) {
         // trunc_exp backward (field_components/activations.py:38-41): g * exp(clamp(x, -15, 15)); density = exp(x), exp is monotonic
         const float gd = a.ddensity[i] * fminf(fmaxf(a.density[i], 3.0590232e-07f), 3269017.372f);
-        if (a.grad_decoder) {
-          float feat[kModMaxDim];
-          neurad_encode_point(fg, frames[slot], A.n_actors, g, feat, nullptr, flip);
-          for (int k = 0; k < D; ++k) dec_acc[k] = fmaf(gd, feat[k], dec_acc[k]);
-        }
-        for (int k = 0; k < D; ++k) dfeat[k] = gd * __ldg(fg.decoder + k);
-      } else {
-        for (int k = 0; k < D; ++k) dfeat[k] = a.dfeatures[i * D + k];
+        if (a.grad_decoder)
+          neurad_encode_point_bwd_t<8, 1, true>(fg, a.grad_static, a.grad_actor_tables, frames[slot], A.n_actors, g, flip,
+                                                fg.decoder, gd, dec_acc);
+        else
+          neurad_encode_point_bwd_t<8, 1, false>(fg, a.grad_static, a.grad_actor_tables, frames[slot], A.n_actors, g, flip,
+                                                 fg.decoder, gd, nullptr);
+        continue;
       }
-      neurad_encode_point_bwd(fg, a.grad_static, a.grad_actor_tables, frames[slot], A.n_actors, g, flip, dfeat);
     }
   }
   if (density_mode && a.grad_decoder) {  // warp, then block reduction; one atomic per CTA and decoder weight
-    for (int k = 0; k < D; ++k) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {  // static indices: dec_acc stays in registers
       const float t = warp_sum(ray < a.n_rays ? dec_acc[k] : 0.f);
-      if (ln == 0) dec_part[warp][k] = t;
+      if (ln == 0 && k < D) dec_part[warp][k] = t;
     }
     __syncthreads();
     if (threadIdx.x < D) {
@@ -197,6 +206,19 @@ __global__ void __launch_bounds__(kModWarps * 32) neurad_encoding_bwd_kernel(con
       atomicAdd(a.grad_decoder + threadIdx.x, t);
     }
   }
+}
+
+// Host dispatch; false when the bound grids do not have the shapes the variants are written for (cannot happen behind
+// b200nerf_set_field_grids, which admits NeuRAD's shapes only -- the caller turns it into an error instead of guessing).
+inline bool launch_neurad_encoding_bwd(const FieldGrids& fg, const Actors& A, const EncodingBwdArgs& a, unsigned grid,
+                                       cudaStream_t stream) {
+  if (!a.ddensity && encode_bwd_fast_ok(fg, A.n_actors, 4))
+    neurad_encoding_bwd_kernel<1><<<grid, kModWarps * 32, 0, stream>>>(fg, A, a);
+  else if (a.ddensity && encode_bwd_fast_ok(fg, A.n_actors, 1))
+    neurad_encoding_bwd_kernel<2><<<grid, kModWarps * 32, 0, stream>>>(fg, A, a);
+  else
+    return false;
+  return true;
 }
 
 // nerfacc.render_weight_from_alpha / RaySamples.get_weights backward: one thread per ray, sequential scans (S is at

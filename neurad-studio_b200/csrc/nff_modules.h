@@ -177,6 +177,113 @@ NFF_D void encode_levels_bwd(float* grad_table, const Grid& gr, const Gauss& g, 
   }
 }
 
+// ---- register-resident fast paths of the scatter backward (round 2) -------------------------------------------------
+// ncu on the first version (profiles/r02_ncu_encoding_bwd.txt) showed the backward kernel issuing 1-9 % of its slots with
+// 80 % of the stall samples on the long scoreboard: every sample staged its dL/dfeature row in a `float[64]` LOCAL-memory
+// array (dynamic level index), and the density mode ran a separate forward (another local array) for the decoder gradient.
+// Here the level loop is unrolled over a compile-time bound, the upstream gradient is read straight from its source
+// (the dL/dfeatures row in global memory, or decoder weight * g in density mode) with read-only loads the scheduler can
+// hoist, and the density mode computes the interpolated feature for the decoder gradient in the SAME pass as the scatter.
+//   grad_table[row] += scale * src[l*F + f] * level_weight_l * corner_weight_k
+//   dec_acc[l]      += scale * feature_l                 (F == 1, density mode; feature_l = trilerp * level_weight)
+template <int LMAX, int F, bool WANT_DEC>
+NFF_D void encode_levels_bwd_t(float* grad_table, const float* NFF_RESTRICT table, const Grid& gr, const Gauss& g,
+                               const float* NFF_RESTRICT src, float scale, float* dec_acc /* [LMAX] registers, WANT_DEC */) {
+  static_assert(F == 1 || F == 4, "fast paths exist for NeuRAD's feature widths");
+#pragma unroll
+  for (int l = 0; l < LMAX; ++l) {
+    if (l < gr.L) {
+      Cell c = grid_cell(g.x, g.y, g.z, gr.res[l]);
+      uint32_t r[8];
+      cell_rows(c, gr.mask, r);
+      float cw[8];
+      corner_weights(c, cw);
+      const float w = level_weight(gr.res[l], g.std);
+      float* base = grad_table + (size_t)l * gr.T * F;
+      if (F == 4) {
+        const float4 d4 = ldg(reinterpret_cast<const float4*>(src) + l);
+        const float g0 = scale * d4.x * w, g1 = scale * d4.y * w, g2 = scale * d4.z * w, g3 = scale * d4.w * w;
+        if (!(g0 == 0.0f && g1 == 0.0f && g2 == 0.0f && g3 == 0.0f)) {
+#pragma unroll
+          for (int k = 0; k < 8; ++k) atomic_add4(base + (size_t)r[k] * 4, g0 * cw[k], g1 * cw[k], g2 * cw[k], g3 * cw[k]);
+        }
+      } else {
+        if (WANT_DEC) {
+          const float* tb = table + (size_t)l * gr.T;
+          float v[8];
+#pragma unroll
+          for (int k = 0; k < 8; ++k) v[k] = ldg(tb + r[k]);
+          dec_acc[l] = fmaf(scale, fmul(trilerp(v, c), w), dec_acc[l]);
+        }
+        const float gs = scale * ldg(src + l) * w;
+        if (gs != 0.0f) {
+#pragma unroll
+          for (int k = 0; k < 8; ++k) atomic_add(base + r[k], gs * cw[k]);
+        }
+      }
+    }
+  }
+}
+// neurad_encode_point_bwd with the fast paths: static table or the containing actor's table (LMAX covers both).
+template <int LMAX, int F, bool WANT_DEC>
+NFF_D int neurad_encode_point_bwd_t(const FieldGrids& fg, float* grad_static, float* const* grad_actor_tables,
+                                    const ActorFrame* frames, int n_actors, const Gauss& g, float flip, const float* src,
+                                    float scale, float* dec_acc) {
+  float pb[3];
+  const int a = n_actors > 0 ? actor_containing(frames, n_actors, g.x, g.y, g.z, pb) : -1;
+  if (a >= 0) {
+    Gauss ga = {flip < 0.0f ? -pb[0] : pb[0], pb[1], pb[2], g.std};
+    ga = contract(ga, fg.actor_scale);
+    float* gt = grad_actor_tables ? grad_actor_tables[a] : nullptr;
+    if (gt) {
+      encode_levels_bwd_t<LMAX, F, WANT_DEC>(gt, fg.actor_tables[a], fg.act, ga, src, scale, dec_acc);
+    } else if (WANT_DEC) {  // no table gradient wanted for this actor, the decoder still sees its features
+      float dummy[LMAX];
+#pragma unroll
+      for (int l = 0; l < LMAX; ++l) dummy[l] = 0.0f;
+      Grid gz = fg.act;
+      (void)gz;
+#pragma unroll
+      for (int l = 0; l < LMAX; ++l) {
+        if (l < fg.act.L) {
+          Cell c = grid_cell(ga.x, ga.y, ga.z, fg.act.res[l]);
+          uint32_t r[8];
+          cell_rows(c, fg.act.mask, r);
+          const float* tb = fg.actor_tables[a] + (size_t)l * fg.act.T;
+          float v[8];
+#pragma unroll
+          for (int k = 0; k < 8; ++k) v[k] = ldg(tb + r[k]);
+          dec_acc[l] = fmaf(scale, fmul(trilerp(v, c), level_weight(fg.act.res[l], ga.std)), dec_acc[l]);
+        }
+      }
+    }
+  } else {
+    Gauss gs = contract(g, fg.static_scale);
+    if (grad_static) {
+      encode_levels_bwd_t<LMAX, F, WANT_DEC>(grad_static, fg.stat.table, fg.stat, gs, src, scale, dec_acc);
+    } else if (WANT_DEC) {
+#pragma unroll
+      for (int l = 0; l < LMAX; ++l) {
+        if (l < fg.stat.L) {
+          Cell c = grid_cell(gs.x, gs.y, gs.z, fg.stat.res[l]);
+          uint32_t r[8];
+          cell_rows(c, fg.stat.mask, r);
+          const float* tb = fg.stat.table + (size_t)l * fg.stat.T;
+          float v[8];
+#pragma unroll
+          for (int k = 0; k < 8; ++k) v[k] = ldg(tb + r[k]);
+          dec_acc[l] = fmaf(scale, fmul(trilerp(v, c), level_weight(fg.stat.res[l], gs.std)), dec_acc[l]);
+        }
+      }
+    }
+  }
+  return a;
+}
+// the grids the fast paths cover: NeuRAD's shapes (and anything up to 8 levels of width 1 / 4)
+NFF_HD bool encode_bwd_fast_ok(const FieldGrids& fg, int n_actors, int F) {
+  return fg.stat.F == F && fg.stat.L <= 8 && (n_actors == 0 || (fg.act.F == F && fg.act.L <= 8));
+}
+
 // Backward of neurad_encode_point(): routes dfeat to the static table or to the containing actor's table (the zero
 // padded tail of an actor sample's feature row has no parameter behind it).  `flip` is the per-ray actor flip of
 // training mode (+1 / -1, neurad_encoding.py:212-219).

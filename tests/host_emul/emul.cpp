@@ -117,6 +117,8 @@ extern "C" {
 static const void* const* g_tcnn_ptrs = nullptr;
 static const int* g_tcnn_ints = nullptr;
 static const float* g_tcnn_floats = nullptr;
+static int g_bwd_generic = 0;  // 1: run the generic (MODE 0) scatter backward even where a fast path applies
+int emul_set_bwd_generic(int on) { g_bwd_generic = on; return 0; }
 int emul_set_tcnn(const void* const* ptrs, const int* ints, const float* floats) {
   g_tcnn_ptrs = ptrs; g_tcnn_ints = ints; g_tcnn_floats = floats;
   return 0;
@@ -340,9 +342,27 @@ int emul_encoding_bwd(const void* const* ptrs, const int* ints, const float* flo
       for (int a = 0; a < A.n_actors; ++a) actor_frame(A, a, left, right, frac, frames[a]);
     }
     const float flip = flips ? flips[r] : 1.0f;
+    const bool fast_feat = !g_bwd_generic && !ddensity && encode_bwd_fast_ok(fg, A.n_actors, 4);   // same dispatch as neurad_encoding_bwd_kernel
+    const bool fast_dens = !g_bwd_generic && ddensity && encode_bwd_fast_ok(fg, A.n_actors, 1);
     for (int s = 0; s < S; ++s) {
       const long long i = r * S + s;
       Gauss g = {mean[3 * i], mean[3 * i + 1], mean[3 * i + 2], std_[i]};
+      if (fast_feat) {
+        neurad_encode_point_bwd_t<8, 4, false>(fg, grad_static, grad_actors, frames.data(), A.n_actors, g, flip, dfeatures + i * D, 1.0f,
+                                               nullptr);
+        continue;
+      }
+      if (fast_dens) {
+        const float gd = ddensity[i] * std::fmin(std::fmax(density[i], 3.0590232e-07f), 3269017.372f);  // trunc_exp backward clamp
+        float dec8[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        if (grad_decoder) {
+          neurad_encode_point_bwd_t<8, 1, true>(fg, grad_static, grad_actors, frames.data(), A.n_actors, g, flip, fg.decoder, gd, dec8);
+          for (int k = 0; k < D && k < 8; ++k) grad_decoder[k] += dec8[k];
+        } else {
+          neurad_encode_point_bwd_t<8, 1, false>(fg, grad_static, grad_actors, frames.data(), A.n_actors, g, flip, fg.decoder, gd, nullptr);
+        }
+        continue;
+      }
       float dfeat[kModMaxDim];
       if (ddensity) {
         const float gd = ddensity[i] * std::fmin(std::fmax(density[i], 3.0590232e-07f), 3269017.372f);  // trunc_exp backward clamp

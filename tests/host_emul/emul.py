@@ -247,6 +247,11 @@ def encoding(cfg, params, pdf_u, field, mean, std, times, directions=None, want_
     return out
 
 
+def set_bwd_generic(on: bool) -> None:
+    """Run the generic (any L x F, MODE 0) variant of the scatter backward instead of the register-resident fast paths."""
+    ctypes.CDLL(build()).emul_set_bwd_generic(ctypes.c_int(1 if on else 0))
+
+
 def encoding_bwd(cfg, params, pdf_u, field, mean, std, times, grads, dfeatures=None, density=None, ddensity=None, flip=None):
     """Backward of `encoding` (csrc/nff_modules.h: neurad_encode_point_bwd).  `grads` = {"static": tensor | None,
     "actors": [tensor | None] * n_actors | None, "decoder": tensor | None}, accumulated in place (same contract as

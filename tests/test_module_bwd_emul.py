@@ -55,8 +55,17 @@ def _grad_params(p, prefix, n_actors):
     return q, keys
 
 
+@pytest.fixture(params=["fast", "generic"])
+def bwd_variant(request):
+    """Both variants of neurad_encoding_bwd_kernel: the register-resident fast paths (NeuRAD's grid shapes) and the generic
+    one (any L x F)."""
+    emul.set_bwd_generic(request.param == "generic")
+    yield request.param
+    emul.set_bwd_generic(False)
+
+
 @pytest.mark.parametrize("name", ["nff_static.npz", "nff_actors.npz"])
-def test_encoding_backward_features_mode(name):
+def test_encoding_backward_features_mode(name, bwd_variant):
     meta, g = load_golden(name)
     cfg = cfg_from_meta(meta)
     ocfg = to_oracle_cfg(cfg)
@@ -86,7 +95,7 @@ def test_encoding_backward_features_mode(name):
 
 
 @pytest.mark.parametrize("name", ["nff_static.npz", "nff_actors.npz"])
-def test_encoding_backward_density_mode(name):
+def test_encoding_backward_density_mode(name, bwd_variant):
     meta, g = load_golden(name)
     cfg = cfg_from_meta(meta)
     ocfg = to_oracle_cfg(cfg)
