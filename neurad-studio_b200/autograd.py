@@ -64,9 +64,12 @@ class DensityFn(Function):
     @staticmethod
     @_fwd
     def forward(ctx, be, field: int, mean, std, times, flip, static_table, decoder_weight, *actor_tables):
-        out = be.neurad_encoding(field, mean, std, times, None, want_features=False, want_density=True, flip=flip)
+        # the decoder's gradient is sum_i g_i * features_i: keep the forward's features ([N*S, 6] floats) instead of
+        # re-gathering 48 table entries per sample in the backward kernel
+        want_feats = bool(ctx.needs_input_grad[7])
+        out = be.neurad_encoding(field, mean, std, times, None, want_features=want_feats, want_density=True, flip=flip)
         ctx.be, ctx.field = be, field
-        ctx.save_for_backward(mean, std, times, flip, out["density"])
+        ctx.save_for_backward(mean, std, times, flip, out["density"], out.get("features"))
         ctx.decoder_shape = decoder_weight.shape
         ctx.table_shapes = [static_table.shape] + [t.shape for t in actor_tables]
         return out["density"]
@@ -74,14 +77,20 @@ class DensityFn(Function):
     @staticmethod
     @_bwd
     def backward(ctx, ddensity):
-        mean, std, times, flip, density = ctx.saved_tensors
+        mean, std, times, flip, density, feats = ctx.saved_tensors
         needs = ctx.needs_input_grad[6:]
         shapes, dev = ctx.table_shapes, ddensity.device
+        ddensity = ddensity.contiguous()
         g_static = torch.zeros(shapes[0], device=dev) if needs[0] else None
-        g_dec = torch.zeros(ctx.decoder_shape, device=dev) if needs[1] else None
         g_actors = [torch.zeros(shapes[1 + a], device=dev) if nd else None for a, nd in enumerate(needs[2:])]
-        ctx.be.neurad_encoding_bwd(ctx.field, mean, std, times, {"static": g_static, "actors": g_actors, "decoder": g_dec},
-                                   density=density, ddensity=ddensity.contiguous(), flip=flip)
+        g_dec = None
+        if needs[1]:
+            # trunc_exp backward (field_components/activations.py:38-41): g * exp(clamp(x, -15, 15)), density = exp(x)
+            g = ddensity.reshape(1, -1) * density.reshape(1, -1).clamp(3.0590232e-07, 3269017.372)
+            g_dec = (g @ feats).reshape(ctx.decoder_shape)
+        if g_static is not None or any(t is not None for t in g_actors):
+            ctx.be.neurad_encoding_bwd(ctx.field, mean, std, times, {"static": g_static, "actors": g_actors, "decoder": None},
+                                       density=density, ddensity=ddensity, flip=flip)
         return (None,) * 6 + (g_static, g_dec, *g_actors)
 
 

@@ -750,6 +750,7 @@ struct MlpArgs {
   int k_real[3], n_real[3], k_pad[3], n_pad[3];
   int smem_off[3];  // float offsets of each layer's (hi) tile; lo follows at +n_pad*k_pad
   int bias_off;
+  int stage_off;  // [128][max(kTcKMax, kTcNMax) + 1] row tile (input rows in, output rows out)
 };
 template <int kTcKMax, int kTcNMax>
 __global__ void __launch_bounds__(128) mlp_tc_kernel(const MlpArgs a, const float* __restrict__ x, float* __restrict__ y,
@@ -774,11 +775,29 @@ __global__ void __launch_bounds__(128) mlp_tc_kernel(const MlpArgs a, const floa
   const uint32_t lane_base = tmem_base + ((uint32_t)(32 * (warp & 3)) << 16);
   uint32_t parity = 0;
   const int out_dim = a.n_real[a.n_layers - 1];
+  // Rows travel through a shared-memory tile with an odd pitch: the CTA's 128 rows are one contiguous block of global
+  // memory, read / written with coalesced accesses by all threads, while thread = row reads its own row from shared memory
+  // without bank conflicts.  (Thread = row straight from global memory touches 32 different lines per load instruction:
+  // 48 loads + 48 stores x 32 wavefronts made the LSU, not HBM, the limit -- 1.3 TB/s, profiles/r02_train_step_launches.txt.)
+  constexpr int kPitch = (kTcKMax > kTcNMax ? kTcKMax : kTcNMax) + 1;
+  float* stage = sm_mlp + a.stage_off;
   for (int64_t tile = blockIdx.x; tile * 128 < n_rows; tile += gridDim.x) {
     const int64_t row = tile * 128 + tid;
+    const int rows_here = (int)(n_rows - tile * 128 < 128 ? n_rows - tile * 128 : 128);
+    {
+      const float* src = x + tile * 128 * a.in_dim;
+      const int n_el = rows_here * a.in_dim, qstep = 128 / a.in_dim, rstep = 128 - qstep * a.in_dim;
+      int r = tid / a.in_dim, cidx = tid - r * a.in_dim;
+      for (int e = tid; e < n_el; e += 128) {
+        stage[r * kPitch + cidx] = __ldg(src + e);
+        r += qstep, cidx += rstep;
+        if (cidx >= a.in_dim) cidx -= a.in_dim, ++r;
+      }
+    }
+    __syncthreads();
     float v[kTcKMax];
 #pragma unroll
-    for (int k = 0; k < kTcKMax; ++k) v[k] = (row < n_rows && k < a.in_dim) ? x[row * a.in_dim + k] : 0.f;
+    for (int k = 0; k < kTcKMax; ++k) v[k] = (row < n_rows && k < a.in_dim) ? stage[tid * kPitch + k] : 0.f;
     for (int l = 0; l < a.n_layers; ++l) {
       tc::store_a<kTcKMax>(lane_base, 0, v, a.k_pad[l]);
       tc::wait_st();
@@ -808,11 +827,22 @@ __global__ void __launch_bounds__(128) mlp_tc_kernel(const MlpArgs a, const floa
         v[k] = last ? o : fmaxf(o, 0.f);
       }
     }
-    if (row < n_rows) {
+    // every thread passed the layer loop's barriers after reading its input row: the tile can take the output rows
 #pragma unroll
-      for (int k = 0; k < kTcNMax; ++k)
-        if (k < out_dim) y[row * out_dim + k] = v[k];
+    for (int k = 0; k < kTcNMax; ++k)
+      if (k < out_dim) stage[tid * kPitch + k] = v[k];
+    __syncthreads();
+    {
+      float* dst = y + tile * 128 * out_dim;
+      const int n_el = rows_here * out_dim, qstep = 128 / out_dim, rstep = 128 - qstep * out_dim;
+      int r = tid / out_dim, cidx = tid - r * out_dim;
+      for (int e = tid; e < n_el; e += 128) {
+        dst[e] = stage[r * kPitch + cidx];
+        r += qstep, cidx += rstep;
+        if (cidx >= out_dim) cidx -= out_dim, ++r;
+      }
     }
+    __syncthreads();  // before the next tile's rows overwrite the stage
   }
   tc::fence_before_sync();
   __syncthreads();
@@ -1445,12 +1475,13 @@ int b200nerf_mlp_fwd(b200nerf_ctx* c, const float* x, int64_t n_rows, int in_dim
   a.bias_off = off;
   // NeuRAD's own MLPs (<= 48 wide) use the 48-column tile; wider ones (config 1's 32 -> 64 -> 4) the 64-column tile
   const int tile_w = wmax <= 48 ? 48 : kWide;
-  size_t smem = sizeof(float) * (off + 3 * tile_w);
+  a.stage_off = off + 3 * tile_w;
+  size_t smem = sizeof(float) * (a.stage_off + 128 * (tile_w + 1));
   // function attributes are per device: one flag per context (several contexts, one per GPU, may share the process)
   bool& attr_set = c->mlp_attr_set;
   if (!attr_set) {
     CUDA_TRY(cudaFuncSetAttribute(mlp_tc_kernel<48, 48>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-    CUDA_TRY(cudaFuncSetAttribute(mlp_tc_kernel<64, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    CUDA_TRY(cudaFuncSetAttribute(mlp_tc_kernel<64, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 136 * 1024));
     attr_set = true;
   }
   int64_t tiles = (n_rows + 127) / 128;
@@ -1623,8 +1654,7 @@ int b200nerf_neurad_encoding_bwd(b200nerf_ctx* c, int field, const float* mean, 
   }
   EncodingBwdArgs a{mean, std, times, flip, dfeatures, density, ddensity, grad_static_table, d_ptrs, grad_decoder, n_rays,
                     n_samples};
-  const unsigned grid = (unsigned)((n_rays + kModWarps - 1) / kModWarps);
-  if (!launch_neurad_encoding_bwd(fg, c->actors, a, grid, (cudaStream_t)stream))
+  if (!launch_neurad_encoding_bwd(fg, c->actors, a, (cudaStream_t)stream))
     return fail(B200NERF_ERR_UNSUPPORTED, "encoding backward: features mode needs 4 features / level, density mode 1 (<= 8 levels)");
   CUDA_TRY(cudaGetLastError());
   return 0;

@@ -87,30 +87,50 @@ __global__ void __launch_bounds__(kModWarps * 32) neurad_encoding_fwd_kernel(con
 // NeuRADField.forward between its two MLPs (fields/neurad_field.py:139-141): geo_out [P, G+1] (sdf | geo_embedding)
 // and directions [P,3] -> the feature MLP's input [P, G+16] = [geo_embedding | SH4((d + 1) / 2)]
 // (get_normalized_directions base_field.py:136-142, SHEncoding encodings.py:797-805).
-__global__ void field_mid_kernel(const float* __restrict__ geo_out, const float* __restrict__ dirs, int64_t n, int G,
-                                 float* __restrict__ x2) {
-  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  const int W = G + kSh;
-  for (int k = 0; k < G; ++k) x2[i * W + k] = geo_out[i * (G + 1) + 1 + k];
-  float c[16];
-  sh4(dirs[3 * i], dirs[3 * i + 1], dirs[3 * i + 2], c);
+// One CTA = 128 consecutive rows.  Per-row values (SH, sdf, alpha) are computed thread = row; the [rows, W] blocks are
+// moved by all threads element-wise, so global accesses are coalesced (thread = row over a 47-float row touches 32
+// different lines per instruction and made these copies LSU-bound).
+__global__ void __launch_bounds__(128) field_mid_kernel(const float* __restrict__ geo_out, const float* __restrict__ dirs, int64_t n,
+                                                        int G, float* __restrict__ x2) {
+  __shared__ float sh[128 * 17];
+  const int64_t r0 = (int64_t)blockIdx.x * 128, row = r0 + threadIdx.x;
+  const int rows = (int)(n - r0 < 128 ? n - r0 : 128);
+  if (row < n) {
+    float c[16];
+    sh4(dirs[3 * row], dirs[3 * row + 1], dirs[3 * row + 2], c);
 #pragma unroll
-  for (int k = 0; k < 16; ++k) x2[i * W + G + k] = c[k];
+    for (int k = 0; k < 16; ++k) sh[threadIdx.x * 17 + k] = c[k];
+  }
+  __syncthreads();
+  const int W = G + kSh, n_el = rows * W, qstep = 128 / W, rstep = 128 - qstep * W;
+  int i = threadIdx.x / W, k = threadIdx.x - i * W;
+  for (int e = threadIdx.x; e < n_el; e += 128) {
+    x2[r0 * W + e] = k < G ? geo_out[(r0 + i) * (G + 1) + 1 + k] : sh[i * 17 + k - G];
+    i += qstep, k += rstep;
+    if (k >= W) k -= W, ++i;
+  }
 }
 
 // ... and after them (neurad_field.py:141-149): feature = geo_embedding + mlp_feature(...); sdf = geo_out[0];
 // alpha = SigmoidDensity(sdf) = sigmoid(-sdf * (|beta| + 1e-4)) (model_components/utils.py:29-41; `beta` here is the
 // already offset value the context holds).
-__global__ void field_tail_kernel(const float* __restrict__ geo_out, const float* __restrict__ mlp_out, int64_t n,
-                                  int G, float beta, float* __restrict__ feature, float* __restrict__ sdf,
-                                  float* __restrict__ alpha) {
-  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  for (int k = 0; k < G; ++k) feature[i * G + k] = geo_out[i * (G + 1) + 1 + k] + mlp_out[i * G + k];
-  const float sd = geo_out[i * (G + 1)];
-  if (sdf) sdf[i] = sd;
-  if (alpha) alpha[i] = frcp(fadd(1.0f, expf(fmul(sd, beta))));
+__global__ void __launch_bounds__(128) field_tail_kernel(const float* __restrict__ geo_out, const float* __restrict__ mlp_out,
+                                                         int64_t n, int G, float beta, float* __restrict__ feature,
+                                                         float* __restrict__ sdf, float* __restrict__ alpha) {
+  const int64_t r0 = (int64_t)blockIdx.x * 128, row = r0 + threadIdx.x;
+  const int rows = (int)(n - r0 < 128 ? n - r0 : 128);
+  const int n_el = rows * G, qstep = 128 / G, rstep = 128 - qstep * G;
+  int i = threadIdx.x / G, k = threadIdx.x - i * G;
+  for (int e = threadIdx.x; e < n_el; e += 128) {
+    feature[r0 * G + e] = geo_out[(r0 + i) * (G + 1) + 1 + k] + mlp_out[r0 * G + e];
+    i += qstep, k += rstep;
+    if (k >= G) k -= G, ++i;
+  }
+  if (row < n) {
+    const float sd = geo_out[row * (G + 1)];
+    if (sdf) sdf[row] = sd;
+    if (alpha) alpha[row] = frcp(fadd(1.0f, expf(fmul(sd, beta))));
+  }
 }
 
 // =============================================================================================== backward operators
@@ -131,93 +151,86 @@ struct EncodingBwdArgs {
   int32_t S;
 };
 
-// Backward of neurad_encoding_fwd_kernel: scatter-add into the hash tables (RED.ADD.F32).  Density mode folds the
+// Backward of neurad_encoding_fwd_kernel: scatter-add into the hash tables (RED.ADD.F32 / .v4).  Density mode folds the
 // proposal head in: g = dL/d density * density (trunc_exp' = exp), dfeat_k = g * decoder_k, d decoder_k += g * feat_k.
-// MODE 1: features (F = 4, L <= 8), MODE 2: density (F = 1, L <= 8) -- the shapes b200nerf_set_field_grids admits; everything
-// stays in registers (nff_modules.h: encode_levels_bwd_t).  The generic any-shape device function (neurad_encode_point_bwd,
-// per-sample rows in local memory) is what round 1 ran here; it remains the cross-check of tests/test_module_bwd_emul.py.
+// MODE 1: features (F = 4, L <= 8), MODE 2: density (F = 1, L <= 8) -- the shapes b200nerf_set_field_grids admits.
+// A CTA of 128 threads owns 16 rays; a ray's samples are cut into kBwdSegments = 8 contiguous segments, one per thread
+// (lanes 8r..8r+7 = the segments of ray r), so a thread sees CONSECUTIVE samples and can run-length aggregate the coarse
+// levels' reductions in registers (nff_modules.h: encoding_bwd_segment has the why and the measurements behind it).
+constexpr int kBwdThreads = 128, kBwdRays = kBwdThreads / kBwdSegments;
+#ifndef NFF_BWD_MINB_F4
+#define NFF_BWD_MINB_F4 2  // resident CTAs the features-mode variant is compiled for (register budget of its 8 * 4 * K sums)
+#endif
 template <int MODE>
-__global__ void __launch_bounds__(kModWarps * 32) neurad_encoding_bwd_kernel(const FieldGrids fg, const Actors A,
-                                                                              const EncodingBwdArgs a) {
-  __shared__ ActorFrame frames[kModWarps][kModMaxActors];
-  __shared__ float dec_part[kModWarps][kModMaxDim];
-  static_assert((kModWarps & (kModWarps - 1)) == 0, "rays per CTA must be a power of two");
-  const int warp = threadIdx.x >> 5, ln = threadIdx.x & 31;
-  // A CTA owns kModWarps rays.  Thread t works on ray slot t % kModWarps and walks that ray's samples with stride
-  // blockDim / kModWarps, so one warp instruction carries 4 consecutive samples of each of 8 DIFFERENT rays.  (The forward
-  // kernel's mapping -- a warp = 32 consecutive samples of ONE ray -- makes most lanes of a scatter instruction hit the same
-  // coarse-level rows: after resampling, neighbouring samples of a ray share their cells, and same-address reductions
-  // serialise.  profiles/r02_train_step_launches.txt: 176 M reductions of round 1 took as long as round 0's 352 M.)
-  const int slot = threadIdx.x & (kModWarps - 1), sub = threadIdx.x / kModWarps, sub_n = (kModWarps * 32) / kModWarps;
-  const int64_t ray = (int64_t)blockIdx.x * kModWarps + slot;
-  const int D = fg.stat.L * fg.stat.F;
-  constexpr bool density_mode = MODE == 2;
+__global__ void __launch_bounds__(kBwdThreads, MODE == 1 ? NFF_BWD_MINB_F4 : 4) neurad_encoding_bwd_kernel(const FieldGrids fg, const Actors A, const EncodingBwdArgs a) {
   static_assert(MODE == 1 || MODE == 2, "features or density mode");
-  float dec_acc[8];
-#pragma unroll
-  for (int k = 0; k < 8; ++k) dec_acc[k] = 0.f;
+  extern __shared__ __align__(16) unsigned char bwd_smem[];
+  ActorFrame* frames = reinterpret_cast<ActorFrame*>(bwd_smem);  // [kBwdRays][n_actors]
+  __shared__ float dec_part[kBwdThreads / 32][8];
+  const int warp = threadIdx.x >> 5, ln = threadIdx.x & 31;
+  const int slot = threadIdx.x / kBwdSegments, seg = threadIdx.x % kBwdSegments;
+  const int64_t ray = (int64_t)blockIdx.x * kBwdRays + slot;
   if (A.n_actors > 0) {  // the CTA's rays x actors frames, built cooperatively
-    for (int i = threadIdx.x; i < kModWarps * A.n_actors; i += kModWarps * 32) {
+    for (int i = threadIdx.x; i < kBwdRays * A.n_actors; i += kBwdThreads) {
       const int sl = i / A.n_actors, k = i - sl * A.n_actors;
-      const int64_t r = (int64_t)blockIdx.x * kModWarps + sl;
+      const int64_t r = (int64_t)blockIdx.x * kBwdRays + sl;
       if (r < a.n_rays) {
         int left, right;
         float frac;
         keyframe_bracket(A, a.times[r], left, right, frac);
-        actor_frame(A, k, left, right, frac, frames[sl][k]);
+        actor_frame(A, k, left, right, frac, frames[sl * A.n_actors + k]);
       }
     }
     __syncthreads();
   }
-  // fast paths (nff_modules.h: encode_levels_bwd_t): NeuRAD's grid shapes, everything in registers
+  float dec_acc[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) dec_acc[k] = 0.f;
   if (ray < a.n_rays) {
     const float flip = a.flip ? a.flip[ray] : 1.0f;
-    for (int s = sub; s < a.S; s += sub_n) {
-      const int64_t i = ray * a.S + s;
-      Gauss g = {a.mean[3 * i], a.mean[3 * i + 1], a.mean[3 * i + 2], a.std[i]};
-      if (MODE == 1) {
-        neurad_encode_point_bwd_t<8, 4, false>(fg, a.grad_static, a.grad_actor_tables, frames[slot], A.n_actors, g, flip,
-                                               a.dfeatures + i * D, 1.0f, nullptr);
-        continue;
-      }
-      if (MODE == 2) {
-        // trunc_exp backward (field_components/activations.py:38-41): g * exp(clamp(x, -15, 15)); density = exp(x), exp is monotonic
-        const float gd = a.ddensity[i] * fminf(fmaxf(a.density[i], 3.0590232e-07f), 3269017.372f);
-        if (a.grad_decoder)
-          neurad_encode_point_bwd_t<8, 1, true>(fg, a.grad_static, a.grad_actor_tables, frames[slot], A.n_actors, g, flip,
-                                                fg.decoder, gd, dec_acc);
-        else
-          neurad_encode_point_bwd_t<8, 1, false>(fg, a.grad_static, a.grad_actor_tables, frames[slot], A.n_actors, g, flip,
-                                                 fg.decoder, gd, nullptr);
-        continue;
-      }
-    }
+    const int seg_len = (a.S + kBwdSegments - 1) / kBwdSegments;
+    const int s0 = seg * seg_len, n = min(a.S, s0 + seg_len) - s0;
+    const ActorFrame* fr = frames + slot * A.n_actors;
+    if (MODE == 1)
+      encoding_bwd_segment<4, false, NFF_BWD_AGG_F4>(fg, a.grad_static, a.grad_actor_tables, fr, A.n_actors, a.mean, a.std, a.dfeatures,
+                                                     nullptr, nullptr, ray * a.S + s0, n, flip, dec_acc);
+    else if (a.grad_decoder)
+      encoding_bwd_segment<1, true, NFF_BWD_AGG_F1>(fg, a.grad_static, a.grad_actor_tables, fr, A.n_actors, a.mean, a.std, nullptr,
+                                                    a.density, a.ddensity, ray * a.S + s0, n, flip, dec_acc);
+    else
+      encoding_bwd_segment<1, false, NFF_BWD_AGG_F1>(fg, a.grad_static, a.grad_actor_tables, fr, A.n_actors, a.mean, a.std, nullptr,
+                                                     a.density, a.ddensity, ray * a.S + s0, n, flip, dec_acc);
   }
-  if (density_mode && a.grad_decoder) {  // warp, then block reduction; one atomic per CTA and decoder weight
+  if (MODE == 2 && a.grad_decoder) {  // warp, then block reduction; one atomic per CTA and decoder weight
+    const int D = fg.stat.L * fg.stat.F;
 #pragma unroll
     for (int k = 0; k < 8; ++k) {  // static indices: dec_acc stays in registers
-      const float t = warp_sum(ray < a.n_rays ? dec_acc[k] : 0.f);
-      if (ln == 0 && k < D) dec_part[warp][k] = t;
+      const float t = warp_sum(dec_acc[k]);
+      if (ln == 0) dec_part[warp][k] = t;
     }
     __syncthreads();
     if (threadIdx.x < D) {
       float t = 0.f;
-      for (int w = 0; w < kModWarps; ++w) t += dec_part[w][threadIdx.x];
+      for (int w = 0; w < kBwdThreads / 32; ++w) t += dec_part[w][threadIdx.x];
       atomicAdd(a.grad_decoder + threadIdx.x, t);
     }
   }
 }
-
 // Host dispatch; false when the bound grids do not have the shapes the variants are written for (cannot happen behind
 // b200nerf_set_field_grids, which admits NeuRAD's shapes only -- the caller turns it into an error instead of guessing).
-inline bool launch_neurad_encoding_bwd(const FieldGrids& fg, const Actors& A, const EncodingBwdArgs& a, unsigned grid,
-                                       cudaStream_t stream) {
-  if (!a.ddensity && encode_bwd_fast_ok(fg, A.n_actors, 4))
-    neurad_encoding_bwd_kernel<1><<<grid, kModWarps * 32, 0, stream>>>(fg, A, a);
-  else if (a.ddensity && encode_bwd_fast_ok(fg, A.n_actors, 1))
-    neurad_encoding_bwd_kernel<2><<<grid, kModWarps * 32, 0, stream>>>(fg, A, a);
-  else
+inline bool launch_neurad_encoding_bwd(const FieldGrids& fg, const Actors& A, const EncodingBwdArgs& a, cudaStream_t stream) {
+  const unsigned grid = (unsigned)((a.n_rays + kBwdRays - 1) / kBwdRays);
+  const size_t smem = sizeof(ActorFrame) * kBwdRays * (size_t)A.n_actors;  // <= 64 KB at kModMaxActors
+  if (grid == 0) return true;
+  if (!a.ddensity && encode_bwd_fast_ok(fg, A.n_actors, 4)) {
+    if (smem > 48 * 1024) cudaFuncSetAttribute(neurad_encoding_bwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    neurad_encoding_bwd_kernel<1><<<grid, kBwdThreads, smem, stream>>>(fg, A, a);
+  } else if (a.ddensity && encode_bwd_fast_ok(fg, A.n_actors, 1)) {
+    if (smem > 48 * 1024) cudaFuncSetAttribute(neurad_encoding_bwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    neurad_encoding_bwd_kernel<2><<<grid, kBwdThreads, smem, stream>>>(fg, A, a);
+  } else {
     return false;
+  }
   return true;
 }
 
@@ -263,24 +276,38 @@ __global__ void composite_bwd_kernel(const float* __restrict__ weights, const fl
 //   d geo_out[:,0]  = dsdf + dalpha * (-beta * alpha * (1 - alpha))
 //   d geo_out[:,1:] = dfeature + dx2[:, :G]              d mlp_feature_out = dfeature (the caller reuses the tensor)
 //   d beta         += sum dalpha * (-sdf * alpha * (1 - alpha))
-__global__ void field_heads_bwd_kernel(const float* __restrict__ geo_out, const float* __restrict__ dfeature,
-                                       const float* __restrict__ dsdf, const float* __restrict__ dalpha,
-                                       const float* __restrict__ dx2, int64_t n, int G, float beta, float* __restrict__ dgeo,
-                                       float* __restrict__ dbeta) {
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void __launch_bounds__(128) field_heads_bwd_kernel(const float* __restrict__ geo_out, const float* __restrict__ dfeature,
+                                                              const float* __restrict__ dsdf, const float* __restrict__ dalpha,
+                                                              const float* __restrict__ dx2, int64_t n, int G, float beta,
+                                                              float* __restrict__ dgeo, float* __restrict__ dbeta) {
+  __shared__ float g0s[128];
+  const int64_t r0 = (int64_t)blockIdx.x * 128, row = r0 + threadIdx.x;
+  const int rows = (int)(n - r0 < 128 ? n - r0 : 128);
   float db = 0.f;
-  if (i < n) {
-    const float sd = geo_out[i * (G + 1)];
-    float g0 = dsdf ? dsdf[i] : 0.f;
+  if (row < n) {  // thread = row: the sdf column
+    const float sd = geo_out[row * (G + 1)];
+    float g0 = dsdf ? dsdf[row] : 0.f;
     if (dalpha) {
       const float al = frcp(fadd(1.0f, expf(fmul(sd, beta))));
-      const float t = dalpha[i] * al * (1.0f - al);
+      const float t = dalpha[row] * al * (1.0f - al);
       g0 -= beta * t;
       db = -sd * t;
     }
-    dgeo[i * (G + 1)] = g0;
-    for (int k = 0; k < G; ++k)
-      dgeo[i * (G + 1) + 1 + k] = (dfeature ? dfeature[i * G + k] : 0.f) + (dx2 ? dx2[i * (G + kSh) + k] : 0.f);
+    g0s[threadIdx.x] = g0;
+  }
+  __syncthreads();
+  // all threads, element-wise over the CTA's [rows, G+1] block of dgeo (coalesced)
+  const int W = G + 1, n_el = rows * W, qstep = 128 / W, rstep = 128 - qstep * W;
+  int i = threadIdx.x / W, k = threadIdx.x - i * W;
+  for (int e = threadIdx.x; e < n_el; e += 128) {
+    float v;
+    if (k == 0)
+      v = g0s[i];
+    else
+      v = (dfeature ? dfeature[(r0 + i) * G + k - 1] : 0.f) + (dx2 ? dx2[(r0 + i) * (G + kSh) + k - 1] : 0.f);
+    dgeo[r0 * W + e] = v;
+    i += qstep, k += rstep;
+    if (k >= W) k -= W, ++i;
   }
   if (dbeta) {
     db = warp_sum(db);
@@ -303,7 +330,8 @@ __global__ void __launch_bounds__(kWgradThreads) linear_wgrad_kernel(const float
                                                                      int64_t n_rows, int K, int N, int relu_x,
                                                                      float* __restrict__ dW, float* __restrict__ db) {
   __shared__ float xs[kWgradRows * 64];
-  __shared__ float dys[kWgradRows * 64];
+  __shared__ __align__(16) float dys[kWgradRows * 64];
+  const int ldy = (N + 3) & ~3;  // dY rows padded to whole quads (pad columns zero)
   float acc[kWgradMaxOut];
 #pragma unroll
   for (int j = 0; j < kWgradMaxOut; ++j) acc[j] = 0.f;
@@ -313,18 +341,17 @@ __global__ void __launch_bounds__(kWgradThreads) linear_wgrad_kernel(const float
     const int64_t r0 = t * kWgradRows;
     const int rows = (int)(n_rows - r0 < kWgradRows ? n_rows - r0 : kWgradRows);
     for (int e = threadIdx.x; e < rows * K; e += kWgradThreads) xs[e] = x[r0 * K + e];
-    for (int e = threadIdx.x; e < rows * N; e += kWgradThreads) dys[e] = dy[r0 * N + e];
+    for (int e = threadIdx.x; e < rows * ldy; e += kWgradThreads) {
+      const int r = e / ldy, c = e - r * ldy;
+      dys[e] = c < N ? dy[(r0 + r) * N + c] : 0.f;
+    }
     __syncthreads();
-    wgrad_tile(threadIdx.x, kWgradThreads, xs, dys, rows, K, N, relu_x != 0, acc);
+    wgrad_tile(threadIdx.x, kWgradThreads, xs, dys, rows, K, N, ldy, relu_x != 0, acc);
     if (db && threadIdx.x < N)
-      for (int r = 0; r < rows; ++r) bacc += dys[r * N + threadIdx.x];
+      for (int r = 0; r < rows; ++r) bacc += dys[r * ldy + threadIdx.x];
     __syncthreads();
   }
-#pragma unroll
-  for (int j = 0; j < kWgradMaxOut; ++j) {
-    const int e = threadIdx.x + j * kWgradThreads;
-    if (e < N * K) atomicAdd(dW + e, acc[j]);
-  }
+  wgrad_flush(threadIdx.x, kWgradThreads, K, N, ldy, acc, [&](int e, float v) { atomicAdd(dW + e, v); });
   if (db && threadIdx.x < N) atomicAdd(db + threadIdx.x, bacc);
 }
 

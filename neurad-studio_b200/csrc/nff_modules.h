@@ -177,109 +177,188 @@ NFF_D void encode_levels_bwd(float* grad_table, const Grid& gr, const Gauss& g, 
   }
 }
 
-// ---- register-resident fast paths of the scatter backward (round 2) -------------------------------------------------
-// ncu on the first version (profiles/r02_ncu_encoding_bwd.txt) showed the backward kernel issuing 1-9 % of its slots with
-// 80 % of the stall samples on the long scoreboard: every sample staged its dL/dfeature row in a `float[64]` LOCAL-memory
-// array (dynamic level index), and the density mode ran a separate forward (another local array) for the decoder gradient.
-// Here the level loop is unrolled over a compile-time bound, the upstream gradient is read straight from its source
-// (the dL/dfeatures row in global memory, or decoder weight * g in density mode) with read-only loads the scheduler can
-// hoist, and the density mode computes the interpolated feature for the decoder gradient in the SAME pass as the scatter.
+// ---- scatter backward, round 2: registers only + run-length aggregation of the coarse levels ---------------------------
+// What bounds the scatter (profiles/r02_ncu_encoding_bwd.txt): not instructions and not DRAM but the L2 atomic units of a
+// FEW slices -- lts__t_tag_requests is 80 % of peak on the busiest slice and 25 % on average.  Every ray starts at the
+// sensor, so the coarse levels' cells around the sensors receive a reduction from every near-range sample of every ray,
+// and same-address reductions serialise in the slice that owns the row.  Consecutive samples of a ray share their coarse
+// cells, so a thread that walks a CONTIGUOUS segment of one ray keeps the current cell's 8 corner sums of the first K
+// levels in registers and issues the reductions only when the cell changes (flush): the hot rows see one reduction per
+// cell crossing instead of one per sample.  Fine levels (and levels whose resolution does not fit the 10-bit cell key) go
+// straight to RED.  The first version's other cost is gone as well: the level loop is unrolled over a compile-time bound
+// and the upstream gradient is read from its source (the dL/dfeatures row, or decoder weight * g in density mode), so no
+// per-sample row lives in local memory, and density mode computes the interpolated feature for the decoder gradient in
+// the same pass.
 //   grad_table[row] += scale * src[l*F + f] * level_weight_l * corner_weight_k
 //   dec_acc[l]      += scale * feature_l                 (F == 1, density mode; feature_l = trilerp * level_weight)
-template <int LMAX, int F, bool WANT_DEC>
+#ifndef NFF_BWD_SEGMENTS
+#define NFF_BWD_SEGMENTS 4
+#endif
+constexpr int kBwdSegments = NFF_BWD_SEGMENTS;  // threads per ray: each walks ceil(S / kBwdSegments) consecutive samples
+constexpr uint32_t kAggEmpty = 0xffffffffu;
+template <int K, int F>
+struct ScatterAgg {
+  int tab;                                // table the pending sums belong to: -1 static, >= 0 actor, -2 none yet
+  uint32_t key[K > 0 ? K : 1];            // ix | iy << 10 | iz << 20 of the pending cell, per aggregated level
+  float acc[K > 0 ? K : 1][8 * F];
+};
+template <int K, int F>
+NFF_D void agg_init(ScatterAgg<K, F>& ag) {
+  ag.tab = -2;
+#pragma unroll
+  for (int l = 0; l < K; ++l) {
+    ag.key[l] = kAggEmpty;
+#pragma unroll
+    for (int j = 0; j < 8 * F; ++j) ag.acc[l][j] = 0.0f;
+  }
+}
+template <int F>
+NFF_D void scatter_cell(float* base, const uint32_t r[8], const float* v /* [8*F] corner-major */) {
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    if (F == 4) {
+      if (!(v[4 * k] == 0.0f && v[4 * k + 1] == 0.0f && v[4 * k + 2] == 0.0f && v[4 * k + 3] == 0.0f))
+        atomic_add4(base + (size_t)r[k] * 4, v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
+    } else {
+      if (v[k] != 0.0f) atomic_add(base + r[k], v[k]);
+    }
+  }
+}
+template <int F>
+NFF_D void agg_flush_level(float* base, uint32_t mask, uint32_t& key, float* acc) {
+  if (key == kAggEmpty) return;
+  const uint32_t ix = key & 1023u, iy = (key >> 10) & 1023u, iz = key >> 20;
+  Cell c;  // rows of the cell's 8 vertices (a sample on an exact integer coordinate gave its "ceil" corners weight 0)
+  c.hx[0] = ix, c.hx[1] = ix + 1u;
+  c.hy[0] = iy * 2654435761u, c.hy[1] = (iy + 1u) * 2654435761u;
+  c.hz[0] = iz * 805459861u, c.hz[1] = (iz + 1u) * 805459861u;
+  c.ox = c.oy = c.oz = 0.0f;
+  uint32_t r[8];
+  cell_rows(c, mask, r);
+  scatter_cell<F>(base, r, acc);
+  key = kAggEmpty;
+#pragma unroll
+  for (int j = 0; j < 8 * F; ++j) acc[j] = 0.0f;
+}
+template <int K, int F>
+NFF_D void agg_flush_all(const FieldGrids& fg, float* grad_static, float* const* grad_actor_tables, ScatterAgg<K, F>& ag) {
+  if (K == 0 || ag.tab == -2) return;
+  float* gt = ag.tab < 0 ? grad_static : grad_actor_tables[ag.tab];
+  const Grid& gr = ag.tab < 0 ? fg.stat : fg.act;
+#pragma unroll
+  for (int l = 0; l < K; ++l)
+    if (gt) agg_flush_level<F>(gt + (size_t)l * gr.T * F, gr.mask, ag.key[l], ag.acc[l]);
+}
+// one sample against one table (grad_table may be NULL: no table gradient wanted, the decoder gradient still is)
+template <int LMAX, int F, bool WANT_DEC, int K>
 NFF_D void encode_levels_bwd_t(float* grad_table, const float* NFF_RESTRICT table, const Grid& gr, const Gauss& g,
-                               const float* NFF_RESTRICT src, float scale, float* dec_acc /* [LMAX] registers, WANT_DEC */) {
-  static_assert(F == 1 || F == 4, "fast paths exist for NeuRAD's feature widths");
+                               const float* NFF_RESTRICT src, float scale, float* dec_acc /* [LMAX] registers */,
+                               ScatterAgg<K, F>& ag) {
+  static_assert(F == 1 || F == 4, "NeuRAD's feature widths");
 #pragma unroll
   for (int l = 0; l < LMAX; ++l) {
     if (l < gr.L) {
-      Cell c = grid_cell(g.x, g.y, g.z, gr.res[l]);
+      const float res = gr.res[l];
+      Cell c = grid_cell(g.x, g.y, g.z, res);
       uint32_t r[8];
       cell_rows(c, gr.mask, r);
-      float cw[8];
-      corner_weights(c, cw);
-      const float w = level_weight(gr.res[l], g.std);
-      float* base = grad_table + (size_t)l * gr.T * F;
-      if (F == 4) {
-        const float4 d4 = ldg(reinterpret_cast<const float4*>(src) + l);
-        const float g0 = scale * d4.x * w, g1 = scale * d4.y * w, g2 = scale * d4.z * w, g3 = scale * d4.w * w;
-        if (!(g0 == 0.0f && g1 == 0.0f && g2 == 0.0f && g3 == 0.0f)) {
+      const float w = level_weight(res, g.std);
+      if (WANT_DEC) {
+        const float* tb = table + (size_t)l * gr.T;
+        float v[8];
 #pragma unroll
-          for (int k = 0; k < 8; ++k) atomic_add4(base + (size_t)r[k] * 4, g0 * cw[k], g1 * cw[k], g2 * cw[k], g3 * cw[k]);
+        for (int k = 0; k < 8; ++k) v[k] = ldg(tb + r[k]);
+        dec_acc[l] = fmaf(scale, fmul(trilerp(v, c), w), dec_acc[l]);
+      }
+      if (grad_table) {
+        float gv[F];
+        if (F == 4) {
+          const float4 d4 = ldg(reinterpret_cast<const float4*>(src) + l);
+          gv[0] = scale * d4.x * w, gv[1] = scale * d4.y * w, gv[2] = scale * d4.z * w, gv[3] = scale * d4.w * w;
+        } else {
+          gv[0] = scale * ldg(src + l) * w;
         }
-      } else {
-        if (WANT_DEC) {
-          const float* tb = table + (size_t)l * gr.T;
-          float v[8];
+        float cw[8];
+        corner_weights(c, cw);
+        float* base = grad_table + (size_t)l * gr.T * F;
+        const int la = l < K ? l : 0;  // compile-time after unrolling
+        const uint32_t ix = c.hx[0], iy = (uint32_t)(int32_t)floorf(fmul(g.y, res)), iz = (uint32_t)(int32_t)floorf(fmul(g.z, res));
+        if (l < K && (ix | iy | iz) < 1023u) {  // the cell fits the key (always, for contracted coordinates on a coarse level)
+          const uint32_t key = ix | (iy << 10) | (iz << 20);
+          if (key != ag.key[la]) {
+            agg_flush_level<F>(base, gr.mask, ag.key[la], ag.acc[la]);
+            ag.key[la] = key;
+          }
 #pragma unroll
-          for (int k = 0; k < 8; ++k) v[k] = ldg(tb + r[k]);
-          dec_acc[l] = fmaf(scale, fmul(trilerp(v, c), w), dec_acc[l]);
-        }
-        const float gs = scale * ldg(src + l) * w;
-        if (gs != 0.0f) {
+          for (int k = 0; k < 8; ++k)
 #pragma unroll
-          for (int k = 0; k < 8; ++k) atomic_add(base + r[k], gs * cw[k]);
+            for (int f = 0; f < F; ++f) ag.acc[la][k * F + f] = fmaf(gv[f], cw[k], ag.acc[la][k * F + f]);
+        } else {
+          float v[8 * F];
+#pragma unroll
+          for (int k = 0; k < 8; ++k)
+#pragma unroll
+            for (int f = 0; f < F; ++f) v[k * F + f] = gv[f] * cw[k];
+          scatter_cell<F>(base, r, v);
         }
       }
     }
   }
 }
-// neurad_encode_point_bwd with the fast paths: static table or the containing actor's table (LMAX covers both).
-template <int LMAX, int F, bool WANT_DEC>
+// one sample: static table or the containing actor's table (LMAX covers both grids)
+template <int LMAX, int F, bool WANT_DEC, int K>
 NFF_D int neurad_encode_point_bwd_t(const FieldGrids& fg, float* grad_static, float* const* grad_actor_tables,
                                     const ActorFrame* frames, int n_actors, const Gauss& g, float flip, const float* src,
-                                    float scale, float* dec_acc) {
+                                    float scale, float* dec_acc, ScatterAgg<K, F>& ag) {
   float pb[3];
   const int a = n_actors > 0 ? actor_containing(frames, n_actors, g.x, g.y, g.z, pb) : -1;
+  if (K > 0 && a != ag.tab) {  // pending sums belong to another table
+    agg_flush_all(fg, grad_static, grad_actor_tables, ag);
+    ag.tab = a;
+  }
   if (a >= 0) {
     Gauss ga = {flip < 0.0f ? -pb[0] : pb[0], pb[1], pb[2], g.std};
     ga = contract(ga, fg.actor_scale);
-    float* gt = grad_actor_tables ? grad_actor_tables[a] : nullptr;
-    if (gt) {
-      encode_levels_bwd_t<LMAX, F, WANT_DEC>(gt, fg.actor_tables[a], fg.act, ga, src, scale, dec_acc);
-    } else if (WANT_DEC) {  // no table gradient wanted for this actor, the decoder still sees its features
-      float dummy[LMAX];
-#pragma unroll
-      for (int l = 0; l < LMAX; ++l) dummy[l] = 0.0f;
-      Grid gz = fg.act;
-      (void)gz;
-#pragma unroll
-      for (int l = 0; l < LMAX; ++l) {
-        if (l < fg.act.L) {
-          Cell c = grid_cell(ga.x, ga.y, ga.z, fg.act.res[l]);
-          uint32_t r[8];
-          cell_rows(c, fg.act.mask, r);
-          const float* tb = fg.actor_tables[a] + (size_t)l * fg.act.T;
-          float v[8];
-#pragma unroll
-          for (int k = 0; k < 8; ++k) v[k] = ldg(tb + r[k]);
-          dec_acc[l] = fmaf(scale, fmul(trilerp(v, c), level_weight(fg.act.res[l], ga.std)), dec_acc[l]);
-        }
-      }
-    }
+    encode_levels_bwd_t<LMAX, F, WANT_DEC, K>(grad_actor_tables ? grad_actor_tables[a] : nullptr, fg.actor_tables[a], fg.act, ga, src,
+                                              scale, dec_acc, ag);
   } else {
-    Gauss gs = contract(g, fg.static_scale);
-    if (grad_static) {
-      encode_levels_bwd_t<LMAX, F, WANT_DEC>(grad_static, fg.stat.table, fg.stat, gs, src, scale, dec_acc);
-    } else if (WANT_DEC) {
-#pragma unroll
-      for (int l = 0; l < LMAX; ++l) {
-        if (l < fg.stat.L) {
-          Cell c = grid_cell(gs.x, gs.y, gs.z, fg.stat.res[l]);
-          uint32_t r[8];
-          cell_rows(c, fg.stat.mask, r);
-          const float* tb = fg.stat.table + (size_t)l * fg.stat.T;
-          float v[8];
-#pragma unroll
-          for (int k = 0; k < 8; ++k) v[k] = ldg(tb + r[k]);
-          dec_acc[l] = fmaf(scale, fmul(trilerp(v, c), level_weight(fg.stat.res[l], gs.std)), dec_acc[l]);
-        }
-      }
-    }
+    const Gauss gs = contract(g, fg.static_scale);
+    encode_levels_bwd_t<LMAX, F, WANT_DEC, K>(grad_static, fg.stat.table, fg.stat, gs, src, scale, dec_acc, ag);
   }
   return a;
 }
-// the grids the fast paths cover: NeuRAD's shapes (and anything up to 8 levels of width 1 / 4)
+// `n` consecutive samples [i0, i0 + n) of one ray.  F == 4: features mode (src = the sample's dL/dfeatures row);
+// F == 1: density mode, g = dL/d density * exp(clamp(x, -15, 15)) (trunc_exp backward, field_components/activations.py:38-41;
+// density = exp(x) and exp is monotonic, so the clamp is applied to the stored density), src = the decoder weights.
+template <int F, bool WANT_DEC, int K>
+NFF_D void encoding_bwd_segment(const FieldGrids& fg, float* grad_static, float* const* grad_actor_tables, const ActorFrame* frames,
+                                int n_actors, const float* mean, const float* std_, const float* dfeatures, const float* density,
+                                const float* ddensity, int64_t i0, int n, float flip, float* dec_acc /* [8] */) {
+  ScatterAgg<K, F> ag;
+  agg_init(ag);
+  const int D = fg.stat.L * fg.stat.F;
+  for (int t = 0; t < n; ++t) {
+    const int64_t i = i0 + t;
+    const Gauss g = {mean[3 * i], mean[3 * i + 1], mean[3 * i + 2], std_[i]};
+    if (F == 4) {
+      neurad_encode_point_bwd_t<8, F, false, K>(fg, grad_static, grad_actor_tables, frames, n_actors, g, flip, dfeatures + i * D, 1.0f,
+                                                dec_acc, ag);
+    } else {
+      const float gd = ddensity[i] * fminf(fmaxf(density[i], 3.0590232e-07f), 3269017.372f);
+      neurad_encode_point_bwd_t<8, F, WANT_DEC, K>(fg, grad_static, grad_actor_tables, frames, n_actors, g, flip, fg.decoder, gd, dec_acc,
+                                                   ag);
+    }
+  }
+  agg_flush_all(fg, grad_static, grad_actor_tables, ag);
+}
+// levels aggregated per feature width (registers: 8 * F sums + a key per level)
+#ifndef NFF_BWD_AGG_F1
+#define NFF_BWD_AGG_F1 6
+#endif
+#ifndef NFF_BWD_AGG_F4
+#define NFF_BWD_AGG_F4 4
+#endif
+// the grids these variants cover: NeuRAD's shapes (and anything up to 8 levels of width 1 / 4)
 NFF_HD bool encode_bwd_fast_ok(const FieldGrids& fg, int n_actors, int F) {
   return fg.stat.F == F && fg.stat.L <= 8 && (n_actors == 0 || (fg.act.F == F && fg.act.L <= 8));
 }
@@ -605,26 +684,49 @@ NFF_D float zipnerf_interlevel_ray(const float* c, const float* w, int S, const 
 }
 
 // One tile of the weight gradient of a Linear layer, dW[o][i] += sum_r dY[r][o] * act(X[r][i]) (act = ReLU when the
-// layer's input is a hidden activation stored as its pre-activation).  Thread `tid` of `nthreads` owns the outputs
-// e = tid + j * nthreads (e = o*K + i), j < MAXOUT, and keeps them in acc[] (registers: the j loop is unrolled).
-// xs [rows][K], dys [rows][N] are the staged tiles.
+// layer's input is a hidden activation stored as its pre-activation).  Outputs are owned in QUADS of four consecutive o
+// for one input i: quad q = tid + j * nthreads (q = og*K + i, o = 4*og + c), j < MAXOUT / 4, kept in acc[4*j + c]
+// (registers: the j loop is unrolled).  Per staged row a quad costs one shared-memory read of X[r][i] and one 16-byte
+// read of dY[r][4*og .. 4*og+3] (a broadcast when the warp's lanes share og) for four FMAs; the first version read two
+// words per FMA and was bound by shared-memory bandwidth.  xs [rows][K]; dys [rows][ldy] with ldy = N rounded up to a
+// multiple of 4, the pad columns zero, 16-byte aligned.
 template <int MAXOUT>
-NFF_D void wgrad_tile(int tid, int nthreads, const float* xs, const float* dys, int rows, int K, int N, bool relu_x,
+NFF_D void wgrad_tile(int tid, int nthreads, const float* xs, const float* dys, int rows, int K, int N, int ldy, bool relu_x,
                       float (&acc)[MAXOUT]) {
+  const int n_quads = (ldy >> 2) * K;
 #if defined(__CUDACC__)
 #pragma unroll
 #endif
-  for (int j = 0; j < MAXOUT; ++j) {
-    const int e = tid + j * nthreads;
-    if (e >= N * K) continue;
-    const int o = e / K, i = e - o * K;
-    float a = acc[j];
+  for (int j = 0; j < MAXOUT / 4; ++j) {
+    const int q = tid + j * nthreads;
+    if (q >= n_quads) continue;
+    const int og = q / K, i = q - og * K;
+    float a0 = acc[4 * j], a1 = acc[4 * j + 1], a2 = acc[4 * j + 2], a3 = acc[4 * j + 3];
     for (int r = 0; r < rows; ++r) {
       float x = xs[r * K + i];
       if (relu_x) x = fmaxf(x, 0.0f);
-      a = fmaf(dys[r * N + o], x, a);
+      const float4 d = *reinterpret_cast<const float4*>(dys + r * ldy + 4 * og);
+      a0 = fmaf(d.x, x, a0), a1 = fmaf(d.y, x, a1), a2 = fmaf(d.z, x, a2), a3 = fmaf(d.w, x, a3);
     }
-    acc[j] = a;
+    acc[4 * j] = a0, acc[4 * j + 1] = a1, acc[4 * j + 2] = a2, acc[4 * j + 3] = a3;
+  }
+}
+// where thread `tid`'s accumulators go: dW[o*K + i] += acc[4*j + c] for o = 4*og + c < N
+template <int MAXOUT, class Add>
+NFF_D void wgrad_flush(int tid, int nthreads, int K, int N, int ldy, const float (&acc)[MAXOUT], Add add) {
+  const int n_quads = (ldy >> 2) * K;
+#if defined(__CUDACC__)
+#pragma unroll
+#endif
+  for (int j = 0; j < MAXOUT / 4; ++j) {
+    const int q = tid + j * nthreads;
+    if (q >= n_quads) continue;
+    const int og = q / K, i = q - og * K;
+#if defined(__CUDACC__)
+#pragma unroll
+#endif
+    for (int c = 0; c < 4; ++c)
+      if (4 * og + c < N) add((4 * og + c) * K + i, acc[4 * j + c]);
   }
 }
 

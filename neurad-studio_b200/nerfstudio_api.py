@@ -1128,9 +1128,16 @@ class NeuRADModel(nn.Module):
         before = t.floor().clamp(0, eps - 1)
         after = (before + 1).clamp(0, eps - 1)
         frac = (t - before)[:, None]
-        e0 = emb[(before + sensor * eps).long()]
-        e1 = emb[(after + sensor * eps).long()]
-        return e0 * (1 - frac) + e1 * frac
+        i0, i1 = (before + sensor * eps).long(), (after + sensor * eps).long()
+        if emb.requires_grad and emb.shape[0] <= 4096:
+            # training: the same two-term interpolation as one [N, E] @ [E, 16] product (E = sensors x embeds_per_sensor = 56).
+            # Autograd's backward of `emb[i]` with ~1000 duplicates per row is a serialised index_put (1.3 ms per step for
+            # 57 k rays, profiles/r02_train_step_launches.txt); the product's backward is a 56 x N x 16 GEMM.
+            m = torch.zeros(n, emb.shape[0], device=emb.device, dtype=emb.dtype)
+            m.scatter_add_(1, i0[:, None], 1 - frac)
+            m.scatter_add_(1, i1[:, None], frac)
+            return m @ emb
+        return emb[i0] * (1 - frac) + emb[i1] * frac
 
     def decode_features(self, features: Tensor, patch_size: Optional[Tuple[int, int]] = None, is_lidar: Optional[Tensor] = None,
                         intensity_for_cam: bool = False):

@@ -342,27 +342,31 @@ int emul_encoding_bwd(const void* const* ptrs, const int* ints, const float* flo
       for (int a = 0; a < A.n_actors; ++a) actor_frame(A, a, left, right, frac, frames[a]);
     }
     const float flip = flips ? flips[r] : 1.0f;
-    const bool fast_feat = !g_bwd_generic && !ddensity && encode_bwd_fast_ok(fg, A.n_actors, 4);   // same dispatch as neurad_encoding_bwd_kernel
+    // same dispatch and the same thread -> (ray, segment) cut as neurad_encoding_bwd_kernel (modules.cuh)
+    const bool fast_feat = !g_bwd_generic && !ddensity && encode_bwd_fast_ok(fg, A.n_actors, 4);
     const bool fast_dens = !g_bwd_generic && ddensity && encode_bwd_fast_ok(fg, A.n_actors, 1);
+    if (fast_feat || fast_dens) {
+      const int seg_len = (S + kBwdSegments - 1) / kBwdSegments;
+      for (int seg = 0; seg < kBwdSegments; ++seg) {
+        const int s0 = seg * seg_len, n = std::min(S, s0 + seg_len) - s0;
+        float dec8[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        if (fast_feat)
+          encoding_bwd_segment<4, false, NFF_BWD_AGG_F4>(fg, grad_static, grad_actors, frames.data(), A.n_actors, mean, std_, dfeatures, nullptr,
+                                                         nullptr, r * S + s0, n, flip, dec8);
+        else if (grad_decoder)
+          encoding_bwd_segment<1, true, NFF_BWD_AGG_F1>(fg, grad_static, grad_actors, frames.data(), A.n_actors, mean, std_, nullptr, density,
+                                                        ddensity, r * S + s0, n, flip, dec8);
+        else
+          encoding_bwd_segment<1, false, NFF_BWD_AGG_F1>(fg, grad_static, grad_actors, frames.data(), A.n_actors, mean, std_, nullptr, density,
+                                                         ddensity, r * S + s0, n, flip, dec8);
+        if (fast_dens && grad_decoder)
+          for (int k = 0; k < D && k < 8; ++k) grad_decoder[k] += dec8[k];
+      }
+      continue;
+    }
     for (int s = 0; s < S; ++s) {
       const long long i = r * S + s;
       Gauss g = {mean[3 * i], mean[3 * i + 1], mean[3 * i + 2], std_[i]};
-      if (fast_feat) {
-        neurad_encode_point_bwd_t<8, 4, false>(fg, grad_static, grad_actors, frames.data(), A.n_actors, g, flip, dfeatures + i * D, 1.0f,
-                                               nullptr);
-        continue;
-      }
-      if (fast_dens) {
-        const float gd = ddensity[i] * std::fmin(std::fmax(density[i], 3.0590232e-07f), 3269017.372f);  // trunc_exp backward clamp
-        float dec8[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-        if (grad_decoder) {
-          neurad_encode_point_bwd_t<8, 1, true>(fg, grad_static, grad_actors, frames.data(), A.n_actors, g, flip, fg.decoder, gd, dec8);
-          for (int k = 0; k < D && k < 8; ++k) grad_decoder[k] += dec8[k];
-        } else {
-          neurad_encode_point_bwd_t<8, 1, false>(fg, grad_static, grad_actors, frames.data(), A.n_actors, g, flip, fg.decoder, gd, nullptr);
-        }
-        continue;
-      }
       float dfeat[kModMaxDim];
       if (ddensity) {
         const float gd = ddensity[i] * std::fmin(std::fmax(density[i], 3.0590232e-07f), 3269017.372f);  // trunc_exp backward clamp
@@ -397,6 +401,8 @@ int emul_linear_wgrad(const float* x, const float* dy, long long n_rows, int K, 
                       float* db) {
   constexpr int kThreads = 256, kRows = 32, kMaxOut = 64 * 64 / kThreads;
   const long long n_tiles = (n_rows + kRows - 1) / kRows;
+  const int ldy = (N + 3) & ~3;
+  alignas(16) float dys[kRows * 64];  // the staged dY tile: rows padded to whole quads, pad columns zero
   for (int cta = 0; cta < n_ctas; ++cta)
     for (int tid = 0; tid < kThreads; ++tid) {
       float acc[kMaxOut] = {};
@@ -404,14 +410,13 @@ int emul_linear_wgrad(const float* x, const float* dy, long long n_rows, int K, 
       for (long long t = cta; t < n_tiles; t += n_ctas) {
         const long long r0 = t * kRows;
         const int rows = (int)(n_rows - r0 < kRows ? n_rows - r0 : kRows);
-        wgrad_tile(tid, kThreads, x + r0 * K, dy + r0 * N, rows, K, N, relu_x != 0, acc);
+        for (int r = 0; r < rows; ++r)
+          for (int c = 0; c < ldy; ++c) dys[r * ldy + c] = c < N ? dy[(r0 + r) * N + c] : 0.f;
+        wgrad_tile(tid, kThreads, x + r0 * K, dys, rows, K, N, ldy, relu_x != 0, acc);
         if (db && tid < N)
-          for (int r = 0; r < rows; ++r) bacc += dy[(r0 + r) * N + tid];
+          for (int r = 0; r < rows; ++r) bacc += dys[r * ldy + tid];
       }
-      for (int j = 0; j < kMaxOut; ++j) {
-        const int e = tid + j * kThreads;
-        if (e < N * K) dW[e] += acc[j];
-      }
+      wgrad_flush(tid, kThreads, K, N, ldy, acc, [&](int e, float v) { dW[e] += v; });
       if (db && tid < N) db[tid] += bacc;
     }
   return 0;
