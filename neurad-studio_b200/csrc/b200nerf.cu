@@ -750,7 +750,7 @@ struct MlpArgs {
   int k_real[3], n_real[3], k_pad[3], n_pad[3];
   int smem_off[3];  // float offsets of each layer's (hi) tile; lo follows at +n_pad*k_pad
   int bias_off;
-  int stage_off;  // [128][max(kTcKMax, kTcNMax) + 1] row tile (input rows in, output rows out)
+  int stage_off;  // 2 x [128][max(kTcKMax, kTcNMax) + 1] row tiles (input rows in / output rows out, double buffered)
 };
 template <int kTcKMax, int kTcNMax>
 __global__ void __launch_bounds__(128) mlp_tc_kernel(const MlpArgs a, const float* __restrict__ x, float* __restrict__ y,
@@ -775,24 +775,39 @@ __global__ void __launch_bounds__(128) mlp_tc_kernel(const MlpArgs a, const floa
   const uint32_t lane_base = tmem_base + ((uint32_t)(32 * (warp & 3)) << 16);
   uint32_t parity = 0;
   const int out_dim = a.n_real[a.n_layers - 1];
-  // Rows travel through a shared-memory tile with an odd pitch: the CTA's 128 rows are one contiguous block of global
-  // memory, read / written with coalesced accesses by all threads, while thread = row reads its own row from shared memory
+  // Rows travel through shared-memory tiles with an odd pitch: the CTA's 128 rows are one contiguous block of global
+  // memory, moved with coalesced accesses by all threads, while thread = row reads its own row from shared memory
   // without bank conflicts.  (Thread = row straight from global memory touches 32 different lines per load instruction:
-  // 48 loads + 48 stores x 32 wavefronts made the LSU, not HBM, the limit -- 1.3 TB/s, profiles/r02_train_step_launches.txt.)
+  // 48 loads + 48 stores x 32 wavefronts made the LSU the limit.)  The NEXT tile's rows are fetched with cp.async into
+  // the other buffer while this tile goes through the layers: with 8 warps per SM (TMEM allows two CTAs) nothing else
+  // would hide the DRAM latency (ncu: 12 % warps active, 60 % of the stall samples on the long scoreboard).
   constexpr int kPitch = (kTcKMax > kTcNMax ? kTcKMax : kTcNMax) + 1;
-  float* stage = sm_mlp + a.stage_off;
-  for (int64_t tile = blockIdx.x; tile * 128 < n_rows; tile += gridDim.x) {
+  float* stage0 = sm_mlp + a.stage_off;
+  auto fetch_rows = [&](int64_t tile, float* buf) {  // asynchronous: 4-byte cp.async per element, no registers held
+    const int rows_here = (int)(n_rows - tile * 128 < 128 ? n_rows - tile * 128 : 128);
+    const float* src = x + tile * 128 * a.in_dim;
+    const int n_el = rows_here * a.in_dim, qstep = 128 / a.in_dim, rstep = 128 - qstep * a.in_dim;
+    int r = tid / a.in_dim, cidx = tid - r * a.in_dim;
+    for (int e = tid; e < n_el; e += 128) {
+      const uint32_t dst = (uint32_t)__cvta_generic_to_shared(buf + r * kPitch + cidx);
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src + e) : "memory");
+      r += qstep, cidx += rstep;
+      if (cidx >= a.in_dim) cidx -= a.in_dim, ++r;
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  if ((int64_t)blockIdx.x * 128 < n_rows) fetch_rows(blockIdx.x, stage0);
+  int it = 0;
+  for (int64_t tile = blockIdx.x; tile * 128 < n_rows; tile += gridDim.x, ++it) {
     const int64_t row = tile * 128 + tid;
     const int rows_here = (int)(n_rows - tile * 128 < 128 ? n_rows - tile * 128 : 128);
-    {
-      const float* src = x + tile * 128 * a.in_dim;
-      const int n_el = rows_here * a.in_dim, qstep = 128 / a.in_dim, rstep = 128 - qstep * a.in_dim;
-      int r = tid / a.in_dim, cidx = tid - r * a.in_dim;
-      for (int e = tid; e < n_el; e += 128) {
-        stage[r * kPitch + cidx] = __ldg(src + e);
-        r += qstep, cidx += rstep;
-        if (cidx >= a.in_dim) cidx -= a.in_dim, ++r;
-      }
+    float* stage = stage0 + (it & 1) * (128 * kPitch);
+    const int64_t next = tile + gridDim.x;
+    if (next * 128 < n_rows) {
+      fetch_rows(next, stage0 + ((it + 1) & 1) * (128 * kPitch));
+      asm volatile("cp.async.wait_group 1;" ::: "memory");
+    } else {
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
     }
     __syncthreads();
     float v[kTcKMax];
@@ -842,7 +857,7 @@ __global__ void __launch_bounds__(128) mlp_tc_kernel(const MlpArgs a, const floa
         if (cidx >= out_dim) cidx -= out_dim, ++r;
       }
     }
-    __syncthreads();  // before the next tile's rows overwrite the stage
+    __syncthreads();  // this buffer is the prefetch target of the next iteration
   }
   tc::fence_before_sync();
   __syncthreads();
@@ -1476,12 +1491,12 @@ int b200nerf_mlp_fwd(b200nerf_ctx* c, const float* x, int64_t n_rows, int in_dim
   // NeuRAD's own MLPs (<= 48 wide) use the 48-column tile; wider ones (config 1's 32 -> 64 -> 4) the 64-column tile
   const int tile_w = wmax <= 48 ? 48 : kWide;
   a.stage_off = off + 3 * tile_w;
-  size_t smem = sizeof(float) * (a.stage_off + 128 * (tile_w + 1));
+  size_t smem = sizeof(float) * (a.stage_off + 2 * 128 * (tile_w + 1));
   // function attributes are per device: one flag per context (several contexts, one per GPU, may share the process)
   bool& attr_set = c->mlp_attr_set;
   if (!attr_set) {
-    CUDA_TRY(cudaFuncSetAttribute(mlp_tc_kernel<48, 48>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-    CUDA_TRY(cudaFuncSetAttribute(mlp_tc_kernel<64, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 136 * 1024));
+    CUDA_TRY(cudaFuncSetAttribute(mlp_tc_kernel<48, 48>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
+    CUDA_TRY(cudaFuncSetAttribute(mlp_tc_kernel<64, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 172 * 1024));
     attr_set = true;
   }
   int64_t tiles = (n_rows + 127) / 128;
@@ -1561,8 +1576,8 @@ int b200nerf_neurad_encoding_fwd(b200nerf_ctx* c, int field, const float* mean, 
   DeviceGuard g(c->device);
   EncodingArgs a{mean, std, times, directions, flip, features, density, directions_out, actor_id, n_rays, n_samples,
                  directions_per_ray ? 1 : 0};
-  const unsigned grid = (unsigned)((n_rays + kModWarps - 1) / kModWarps);
-  neurad_encoding_fwd_kernel<<<grid, kModWarps * 32, 0, (cudaStream_t)stream>>>(fg, c->actors, a);
+  if (!launch_neurad_encoding_fwd(fg, c->actors, a, (cudaStream_t)stream))
+    return fail(B200NERF_ERR_UNSUPPORTED, "encoding forward: 4 or 1 features per level, at most 8 levels");
   CUDA_TRY(cudaGetLastError());
   return 0;
 }

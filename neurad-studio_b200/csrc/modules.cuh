@@ -41,47 +41,93 @@ struct EncodingArgs {
 };
 
 // NeuRADHashEncoding.forward (neurad_encoding.py:150-187), optionally followed by the proposal field's density head.
-// One warp per ray: the lanes first build the ray's actor frames (lane = actor) in shared memory, then stride over
-// the ray's samples.
+// One warp per ray: the lanes first build the ray's actor frames (lane = actor) in shared memory, then take 32 consecutive
+// samples at a time.  F = 4 (main field) / F = 1 (proposal fields), at most 8 levels: a sample's feature row stays in
+// registers (neurad_encode_point_t), and the warp's 32 rows -- one contiguous block of `features` -- go out through a
+// shared-memory tile with an odd pitch so that the global stores are coalesced (lane = row wrote 32 different lines per
+// store instruction: 85 % LSU-wavefront utilisation, profiles/r02_ncu_train_kernels.txt).
+template <int F>
 __global__ void __launch_bounds__(kModWarps * 32) neurad_encoding_fwd_kernel(const FieldGrids fg, const Actors A,
                                                                               const EncodingArgs a) {
-  __shared__ ActorFrame frames[kModWarps][kModMaxActors];
+  constexpr int kRow = 8 * F, kPitch = kRow + 1;
+  extern __shared__ __align__(16) unsigned char fwd_smem[];
+  float* stage_all = reinterpret_cast<float*>(fwd_smem);  // [kModWarps][32][kPitch]
+  ActorFrame* frames_all = reinterpret_cast<ActorFrame*>(stage_all + kModWarps * 32 * kPitch);  // [kModWarps][n_actors]
   const int warp = threadIdx.x >> 5, ln = threadIdx.x & 31;
   const int64_t ray = (int64_t)blockIdx.x * kModWarps + warp;
   if (ray >= a.n_rays) return;
+  float* stage = stage_all + warp * 32 * kPitch;
+  ActorFrame* frames = frames_all + warp * A.n_actors;
   if (A.n_actors > 0) {
     int left, right;
     float frac;
     keyframe_bracket(A, a.times[ray], left, right, frac);
-    for (int k = ln; k < A.n_actors; k += 32) actor_frame(A, k, left, right, frac, frames[warp][k]);
+    for (int k = ln; k < A.n_actors; k += 32) actor_frame(A, k, left, right, frac, frames[k]);
   }
   __syncwarp();
   const int D = fg.stat.L * fg.stat.F;
   const float flip = a.flip ? a.flip[ray] : 1.0f;
-  for (int s = ln; s < a.S; s += 32) {
-    const int64_t i = ray * a.S + s;
-    Gauss g = {a.mean[3 * i], a.mean[3 * i + 1], a.mean[3 * i + 2], a.std[i]};
-    float dir[3] = {0.f, 0.f, 0.f};
-    if (a.dirs) {
-      const float* dp = a.dirs + 3 * (a.dirs_per_ray ? ray : i);
-      dir[0] = dp[0]; dir[1] = dp[1]; dir[2] = dp[2];
+  for (int s0 = 0; s0 < a.S; s0 += 32) {
+    const int s = s0 + ln;
+    if (s < a.S) {
+      const int64_t i = ray * a.S + s;
+      Gauss g = {a.mean[3 * i], a.mean[3 * i + 1], a.mean[3 * i + 2], a.std[i]};
+      float dir[3] = {0.f, 0.f, 0.f};
+      if (a.dirs) {
+        const float* dp = a.dirs + 3 * (a.dirs_per_ray ? ray : i);
+        dir[0] = dp[0]; dir[1] = dp[1]; dir[2] = dp[2];
+      }
+      float feat[kRow];
+      const int aid = neurad_encode_point_t<8, F>(fg, frames, A.n_actors, g, feat, a.dirs ? dir : nullptr, flip);
+      if (a.features) {
+#pragma unroll
+        for (int k = 0; k < kRow; ++k)
+          if (k < D) stage[ln * kPitch + k] = feat[k];
+      }
+      if (a.density) {
+        float acc = 0.f;
+#pragma unroll
+        for (int k = 0; k < kRow; ++k)
+          if (k < D) acc = fmaf(feat[k], __ldg(fg.decoder + k), acc);
+        a.density[i] = expf(acc);
+      }
+      if (a.dirs_out) {
+        a.dirs_out[3 * i] = dir[0];
+        a.dirs_out[3 * i + 1] = dir[1];
+        a.dirs_out[3 * i + 2] = dir[2];
+      }
+      if (a.actor_id) a.actor_id[i] = aid;
     }
-    float feat[kModMaxDim];
-    const int aid = neurad_encode_point(fg, frames[warp], A.n_actors, g, feat, a.dirs ? dir : nullptr, flip);
-    if (a.features)
-      for (int k = 0; k < D; ++k) a.features[i * D + k] = feat[k];
-    if (a.density) {
-      float acc = 0.f;
-      for (int k = 0; k < D; ++k) acc = fmaf(feat[k], __ldg(fg.decoder + k), acc);
-      a.density[i] = expf(acc);
+    if (a.features) {
+      __syncwarp();
+      const int rows = a.S - s0 < 32 ? a.S - s0 : 32, n_el = rows * D, qstep = 32 / D, rstep = 32 - qstep * D;
+      float* dst = a.features + (ray * a.S + s0) * D;
+      int r = ln / D, c = ln - r * D;
+      for (int e = ln; e < n_el; e += 32) {
+        dst[e] = stage[r * kPitch + c];
+        r += qstep, c += rstep;
+        if (c >= D) c -= D, ++r;
+      }
+      __syncwarp();
     }
-    if (a.dirs_out) {
-      a.dirs_out[3 * i] = dir[0];
-      a.dirs_out[3 * i + 1] = dir[1];
-      a.dirs_out[3 * i + 2] = dir[2];
-    }
-    if (a.actor_id) a.actor_id[i] = aid;
   }
+}
+// Host dispatch (false: grid shapes b200nerf_set_field_grids does not admit).
+inline bool launch_neurad_encoding_fwd(const FieldGrids& fg, const Actors& A, const EncodingArgs& a, cudaStream_t stream) {
+  const unsigned grid = (unsigned)((a.n_rays + kModWarps - 1) / kModWarps);
+  if (grid == 0) return true;
+  auto launch = [&](auto kernel, int F) {
+    const size_t smem = sizeof(float) * kModWarps * 32 * (8 * F + 1) + sizeof(ActorFrame) * kModWarps * (size_t)A.n_actors;
+    if (smem > 48 * 1024) cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    kernel<<<grid, kModWarps * 32, smem, stream>>>(fg, A, a);
+  };
+  if (encode_bwd_fast_ok(fg, A.n_actors, 4))
+    launch(neurad_encoding_fwd_kernel<4>, 4);
+  else if (encode_bwd_fast_ok(fg, A.n_actors, 1))
+    launch(neurad_encoding_fwd_kernel<1>, 1);
+  else
+    return false;
+  return true;
 }
 
 // NeuRADField.forward between its two MLPs (fields/neurad_field.py:139-141): geo_out [P, G+1] (sdf | geo_embedding)
@@ -154,13 +200,49 @@ struct EncodingBwdArgs {
 // Backward of neurad_encoding_fwd_kernel: scatter-add into the hash tables (RED.ADD.F32 / .v4).  Density mode folds the
 // proposal head in: g = dL/d density * density (trunc_exp' = exp), dfeat_k = g * decoder_k, d decoder_k += g * feat_k.
 // MODE 1: features (F = 4, L <= 8), MODE 2: density (F = 1, L <= 8) -- the shapes b200nerf_set_field_grids admits.
-// A CTA of 128 threads owns 16 rays; a ray's samples are cut into kBwdSegments = 8 contiguous segments, one per thread
-// (lanes 8r..8r+7 = the segments of ray r), so a thread sees CONSECUTIVE samples and can run-length aggregate the coarse
-// levels' reductions in registers (nff_modules.h: encoding_bwd_segment has the why and the measurements behind it).
+// A CTA of 128 threads owns 128 / kBwdSegments rays; a ray's samples are cut into kBwdSegments (4) contiguous segments, one
+// per thread (adjacent lanes = the segments of one ray), so a thread sees CONSECUTIVE samples and can run-length aggregate
+// the coarse levels' reductions in registers (nff_modules.h: encoding_bwd_segment has the why and the measurements).
 constexpr int kBwdThreads = 128, kBwdRays = kBwdThreads / kBwdSegments;
 #ifndef NFF_BWD_MINB_F4
 #define NFF_BWD_MINB_F4 2  // resident CTAs the features-mode variant is compiled for (register budget of its 8 * 4 * K sums)
 #endif
+#ifndef NFF_BWD_WARP_MERGE
+#define NFF_BWD_WARP_MERGE 3  // coarsest levels whose pending sums are merged across the warp before they are flushed
+#endif
+// What is still pending when a thread finishes its segment is, on the coarsest levels, the SAME cell for most lanes of a
+// warp (every ray starts at the sensors; a level-0 cell is tens of metres wide): lanes holding the same (table, cell)
+// add their 8 * F sums with shuffles and one of them issues the reductions.  At most kMergeRounds distinct cells are
+// merged per level; lanes left over flush their own sums afterwards (agg_flush_all).  All 32 lanes must call this.
+template <int K, int F>
+__device__ __forceinline__ void warp_merge_pending(const FieldGrids& fg, float* grad_static, float* const* grad_actor_tables,
+                                                   ScatterAgg<K, F>& ag) {
+  constexpr int kMergeRounds = 4, KW = NFF_BWD_WARP_MERGE < K ? NFF_BWD_WARP_MERGE : K;
+  const int lane = threadIdx.x & 31;
+  float* gt = ag.tab == -2 ? nullptr : (ag.tab < 0 ? grad_static : (grad_actor_tables ? grad_actor_tables[ag.tab] : nullptr));
+  const Grid& gr = ag.tab < 0 ? fg.stat : fg.act;
+#pragma unroll
+  for (int l = 0; l < KW; ++l) {
+    const unsigned long long id = ((unsigned long long)(unsigned)ag.tab << 32) | ag.key[l];
+    unsigned todo = __ballot_sync(0xffffffffu, gt != nullptr && ag.key[l] != kAggEmpty);
+    for (int round = 0; round < kMergeRounds && todo; ++round) {
+      const int src = __ffs(todo) - 1;
+      const unsigned long long want = __shfl_sync(0xffffffffu, id, src);
+      const bool mine = ((todo >> lane) & 1u) && id == want;
+      const unsigned group = __ballot_sync(0xffffffffu, mine);
+      if (group != (1u << src)) {  // somebody shares the leader's cell (warp-uniform branch)
+#pragma unroll
+        for (int j = 0; j < 8 * F; ++j) {
+          const float t = warp_sum(mine ? ag.acc[l][j] : 0.0f);
+          ag.acc[l][j] = lane == src ? t : (mine ? 0.0f : ag.acc[l][j]);
+        }
+        if (mine && lane != src) ag.key[l] = kAggEmpty;
+      }
+      if (lane == src) agg_flush_level<F>(gt + (size_t)l * gr.T * F, gr.mask, ag.key[l], ag.acc[l]);
+      todo &= ~group;
+    }
+  }
+}
 template <int MODE>
 __global__ void __launch_bounds__(kBwdThreads, MODE == 1 ? NFF_BWD_MINB_F4 : 4) neurad_encoding_bwd_kernel(const FieldGrids fg, const Actors A, const EncodingBwdArgs a) {
   static_assert(MODE == 1 || MODE == 2, "features or density mode");
@@ -186,20 +268,29 @@ __global__ void __launch_bounds__(kBwdThreads, MODE == 1 ? NFF_BWD_MINB_F4 : 4) 
   float dec_acc[8];
 #pragma unroll
   for (int k = 0; k < 8; ++k) dec_acc[k] = 0.f;
-  if (ray < a.n_rays) {
-    const float flip = a.flip ? a.flip[ray] : 1.0f;
-    const int seg_len = (a.S + kBwdSegments - 1) / kBwdSegments;
-    const int s0 = seg * seg_len, n = min(a.S, s0 + seg_len) - s0;
-    const ActorFrame* fr = frames + slot * A.n_actors;
-    if (MODE == 1)
-      encoding_bwd_segment<4, false, NFF_BWD_AGG_F4>(fg, a.grad_static, a.grad_actor_tables, fr, A.n_actors, a.mean, a.std, a.dfeatures,
-                                                     nullptr, nullptr, ray * a.S + s0, n, flip, dec_acc);
-    else if (a.grad_decoder)
-      encoding_bwd_segment<1, true, NFF_BWD_AGG_F1>(fg, a.grad_static, a.grad_actor_tables, fr, A.n_actors, a.mean, a.std, nullptr,
-                                                    a.density, a.ddensity, ray * a.S + s0, n, flip, dec_acc);
+  // (no early exit: the warp-wide merge below needs all 32 lanes)
+  const bool live = ray < a.n_rays;
+  const float flip = live && a.flip ? a.flip[ray] : 1.0f;
+  const int seg_len = (a.S + kBwdSegments - 1) / kBwdSegments;
+  const int s0 = seg * seg_len, n = live ? max(min(a.S, s0 + seg_len) - s0, 0) : 0;
+  const ActorFrame* fr = frames + slot * A.n_actors;
+  const int64_t i0 = live ? ray * a.S + s0 : 0;
+  if (MODE == 1) {
+    ScatterAgg<NFF_BWD_AGG_F4, 4> ag;
+    encoding_bwd_segment_pending<4, false, NFF_BWD_AGG_F4>(fg, a.grad_static, a.grad_actor_tables, fr, A.n_actors, a.mean, a.std,
+                                                           a.dfeatures, nullptr, nullptr, i0, n, flip, dec_acc, ag);
+    warp_merge_pending(fg, a.grad_static, a.grad_actor_tables, ag);
+    agg_flush_all(fg, a.grad_static, a.grad_actor_tables, ag);
+  } else {
+    ScatterAgg<NFF_BWD_AGG_F1, 1> ag;
+    if (a.grad_decoder)
+      encoding_bwd_segment_pending<1, true, NFF_BWD_AGG_F1>(fg, a.grad_static, a.grad_actor_tables, fr, A.n_actors, a.mean, a.std, nullptr,
+                                                            a.density, a.ddensity, i0, n, flip, dec_acc, ag);
     else
-      encoding_bwd_segment<1, false, NFF_BWD_AGG_F1>(fg, a.grad_static, a.grad_actor_tables, fr, A.n_actors, a.mean, a.std, nullptr,
-                                                     a.density, a.ddensity, ray * a.S + s0, n, flip, dec_acc);
+      encoding_bwd_segment_pending<1, false, NFF_BWD_AGG_F1>(fg, a.grad_static, a.grad_actor_tables, fr, A.n_actors, a.mean, a.std, nullptr,
+                                                             a.density, a.ddensity, i0, n, flip, dec_acc, ag);
+    warp_merge_pending(fg, a.grad_static, a.grad_actor_tables, ag);
+    agg_flush_all(fg, a.grad_static, a.grad_actor_tables, ag);
   }
   if (MODE == 2 && a.grad_decoder) {  // warp, then block reduction; one atomic per CTA and decoder weight
     const int D = fg.stat.L * fg.stat.F;

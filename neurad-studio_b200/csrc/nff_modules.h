@@ -132,6 +132,69 @@ NFF_D int neurad_encode_point(const FieldGrids& fg, const ActorFrame* frames, in
   return a;
 }
 
+// The same two functions for NeuRAD's shapes (F = 4 or 1 features, at most LMAX levels) with the level loop unrolled, so
+// the feature row lives in REGISTERS (the generic versions index a local-memory array) and an F = 4 row is one 16-byte
+// load per corner.  Same operations in the same order: bit-identical to encode_levels / neurad_encode_point.  Levels past
+// gr.L are written as zeros (the F.pad of an actor sample's row).
+template <int LMAX, int F>
+NFF_D void encode_levels_t(const float* NFF_RESTRICT table, const Grid& gr, const Gauss& g, float* out /* [LMAX*F] */) {
+  static_assert(F == 1 || F == 4, "NeuRAD's feature widths");
+#pragma unroll
+  for (int l = 0; l < LMAX; ++l) {
+    if (l < gr.L) {
+      Cell c = grid_cell(g.x, g.y, g.z, gr.res[l]);
+      uint32_t r[8];
+      cell_rows(c, gr.mask, r);
+      const float* base = table + (size_t)l * gr.T * F;
+      const float w = level_weight(gr.res[l], g.std);
+      if (F == 4) {
+        float vx[8], vy[8], vz[8], vw[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const float4 q = ldg(reinterpret_cast<const float4*>(base) + r[k]);
+          vx[k] = q.x, vy[k] = q.y, vz[k] = q.z, vw[k] = q.w;
+        }
+        out[l * F] = fmul(trilerp(vx, c), w);
+        out[l * F + (F > 1 ? 1 : 0)] = fmul(trilerp(vy, c), w);
+        out[l * F + (F > 2 ? 2 : 0)] = fmul(trilerp(vz, c), w);
+        out[l * F + (F > 3 ? 3 : 0)] = fmul(trilerp(vw, c), w);
+      } else {
+        float v[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) v[k] = ldg(base + r[k]);
+        out[l * F] = fmul(trilerp(v, c), w);
+      }
+    } else {
+#pragma unroll
+      for (int f = 0; f < F; ++f) out[l * F + f] = 0.0f;
+    }
+  }
+}
+template <int LMAX, int F>
+NFF_D int neurad_encode_point_t(const FieldGrids& fg, const ActorFrame* frames, int n_actors, const Gauss& g, float* feat /* [LMAX*F] */,
+                                float dir[3], float flip = 1.0f) {
+  float pb[3];
+  const int a = n_actors > 0 ? actor_containing(frames, n_actors, g.x, g.y, g.z, pb) : -1;
+  if (a >= 0) {
+    Gauss ga = {flip < 0.0f ? -pb[0] : pb[0], pb[1], pb[2], g.std};
+    ga = contract(ga, fg.actor_scale);
+    encode_levels_t<LMAX, F>(fg.actor_tables[a], fg.act, ga, feat);
+    if (dir) {
+      const float* M = frames[a].w2b;
+      float q0 = fadd(fadd(fmul(M[0], dir[0]), fmul(M[1], dir[1])), fmul(M[2], dir[2]));
+      float q1 = fadd(fadd(fmul(M[4], dir[0]), fmul(M[5], dir[1])), fmul(M[6], dir[2]));
+      float q2 = fadd(fadd(fmul(M[8], dir[0]), fmul(M[9], dir[1])), fmul(M[10], dir[2]));
+      float n = fadd(fsqrt(fadd(fadd(fmul(q0, q0), fmul(q1, q1)), fmul(q2, q2))), 1.0e-7f);
+      dir[0] = fdiv(q0, n); dir[1] = fdiv(q1, n); dir[2] = fdiv(q2, n);
+      if (flip < 0.0f) dir[0] = -dir[0];
+    }
+  } else {
+    Gauss gs = contract(g, fg.static_scale);
+    encode_levels_t<LMAX, F>(fg.stat.table, fg.stat, gs, feat);
+  }
+  return a;
+}
+
 // --------------------------------------------------------------------------------------------- backward pieces
 // SURVEY 8f row f2.  Gradients flow to the parameters the reference trains through this path (hash tables, proposal
 // density decoders, MLPs, beta); sample positions carry no gradient (PDFSampler detaches its bins,
@@ -330,16 +393,23 @@ NFF_D int neurad_encode_point_bwd_t(const FieldGrids& fg, float* grad_static, fl
 // `n` consecutive samples [i0, i0 + n) of one ray.  F == 4: features mode (src = the sample's dL/dfeatures row);
 // F == 1: density mode, g = dL/d density * exp(clamp(x, -15, 15)) (trunc_exp backward, field_components/activations.py:38-41;
 // density = exp(x) and exp is monotonic, so the clamp is applied to the stored density), src = the decoder weights.
+#ifndef NFF_BWD_PREFETCH
+#define NFF_BWD_PREFETCH 1
+#endif
 template <int F, bool WANT_DEC, int K>
-NFF_D void encoding_bwd_segment(const FieldGrids& fg, float* grad_static, float* const* grad_actor_tables, const ActorFrame* frames,
-                                int n_actors, const float* mean, const float* std_, const float* dfeatures, const float* density,
-                                const float* ddensity, int64_t i0, int n, float flip, float* dec_acc /* [8] */) {
-  ScatterAgg<K, F> ag;
+NFF_D void encoding_bwd_segment_pending(const FieldGrids& fg, float* grad_static, float* const* grad_actor_tables,
+                                        const ActorFrame* frames, int n_actors, const float* mean, const float* std_,
+                                        const float* dfeatures, const float* density, const float* ddensity, int64_t i0, int n,
+                                        float flip, float* dec_acc /* [8] */, ScatterAgg<K, F>& ag /* pending sums out */) {
   agg_init(ag);
   const int D = fg.stat.L * fg.stat.F;
   for (int t = 0; t < n; ++t) {
     const int64_t i = i0 + t;
     const Gauss g = {mean[3 * i], mean[3 * i + 1], mean[3 * i + 2], std_[i]};
+    if (NFF_BWD_PREFETCH && t + 1 < n) {  // the walk is sequential and few warps are resident: fetch the next sample's inputs now
+      if (F == 4) prefetch_l1(dfeatures + (i + 1) * D);
+      prefetch_l1(mean + 3 * (i + 2)), prefetch_l1(std_ + i + 2);  // (a 128-byte line past the array's end is a dropped hint)
+    }
     if (F == 4) {
       neurad_encode_point_bwd_t<8, F, false, K>(fg, grad_static, grad_actor_tables, frames, n_actors, g, flip, dfeatures + i * D, 1.0f,
                                                 dec_acc, ag);
@@ -349,6 +419,16 @@ NFF_D void encoding_bwd_segment(const FieldGrids& fg, float* grad_static, float*
                                                    ag);
     }
   }
+}
+// ... and with the pending sums flushed by the thread itself (the host emulation; the kernel merges the coarsest levels'
+// pending sums across the warp first, modules.cuh: warp_merge_pending)
+template <int F, bool WANT_DEC, int K>
+NFF_D void encoding_bwd_segment(const FieldGrids& fg, float* grad_static, float* const* grad_actor_tables, const ActorFrame* frames,
+                                int n_actors, const float* mean, const float* std_, const float* dfeatures, const float* density,
+                                const float* ddensity, int64_t i0, int n, float flip, float* dec_acc /* [8] */) {
+  ScatterAgg<K, F> ag;
+  encoding_bwd_segment_pending<F, WANT_DEC, K>(fg, grad_static, grad_actor_tables, frames, n_actors, mean, std_, dfeatures, density,
+                                               ddensity, i0, n, flip, dec_acc, ag);
   agg_flush_all(fg, grad_static, grad_actor_tables, ag);
 }
 // levels aggregated per feature width (registers: 8 * F sums + a key per level)

@@ -46,6 +46,8 @@ NFF_D void atomic_add(float* p, float v) { atomicAdd(p, v); }
 NFF_D void atomic_add4(float* p, float a, float b, float c, float d) {
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
+// hint: bring the line at p into L1 (no register, no scoreboard entry) -- the next sample's inputs of a sequential walk
+NFF_D void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 }  // namespace simt
 
 #else
@@ -109,6 +111,7 @@ template <typename T>
 inline T ldg(const T* p) { return *p; }
 inline void atomic_add(float* p, float v) { *p += v; }  // the backward emulation runs its "threads" one after the other
 inline void atomic_add4(float* p, float a, float b, float c, float d) { p[0] += a; p[1] += b; p[2] += c; p[3] += d; }
+inline void prefetch_l1(const void*) {}
 }  // namespace simt
 
 inline float fminf_(float a, float b) { return std::fmin(a, b); }

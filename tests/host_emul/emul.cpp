@@ -297,7 +297,13 @@ int emul_encoding(const void* const* ptrs, const int* ints, const float* floats,
         dir[0] = dp[0]; dir[1] = dp[1]; dir[2] = dp[2];
       }
       float feat[kModMaxDim];
-      const int aid = neurad_encode_point(fg, frames.data(), A.n_actors, g, feat, dirs ? dir : nullptr, flip);
+      int aid;  // same dispatch as launch_neurad_encoding_fwd (modules.cuh); g_bwd_generic also selects the generic forward
+      if (!g_bwd_generic && encode_bwd_fast_ok(fg, A.n_actors, 4))
+        aid = neurad_encode_point_t<8, 4>(fg, frames.data(), A.n_actors, g, feat, dirs ? dir : nullptr, flip);
+      else if (!g_bwd_generic && encode_bwd_fast_ok(fg, A.n_actors, 1))
+        aid = neurad_encode_point_t<8, 1>(fg, frames.data(), A.n_actors, g, feat, dirs ? dir : nullptr, flip);
+      else
+        aid = neurad_encode_point(fg, frames.data(), A.n_actors, g, feat, dirs ? dir : nullptr, flip);
       if (features)
         for (int k = 0; k < D; ++k) features[i * D + k] = feat[k];
       if (density) {

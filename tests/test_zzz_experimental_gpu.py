@@ -27,7 +27,11 @@ def test_linear_wgrad_tensor_core_twin(k, n, relu, rows):
     be.check_status()
     xa = torch.relu(x) if relu else x
     want = (dy.double().t() @ xa.double()).float()
-    assert rel_to_max(dW, want) < 2e-5 and rel_to_max(db, dy.double().sum(0).float()) < 2e-5
+    assert rel_to_max(dW, want) < 2e-5
+    # a column sum of N(0,1) draws cancels (|sum| ~ sqrt(rows) while sum|dy| ~ rows): the fp32 bound is relative to sum|dy|,
+    # and the atomics' order changes from run to run
+    db_err = (db - dy.double().sum(0).float()).abs().max().item()
+    assert db_err <= 2e-6 * dy.abs().sum(0).max().item() + 1e-6
     dW2, db2 = torch.zeros_like(dW), torch.zeros_like(db)
     be.linear_wgrad(x, dy, relu, dW2, db2, impl="cuda")
     assert rel_to_max(dW, dW2) < 2e-5
