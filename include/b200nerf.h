@@ -239,6 +239,13 @@ int b200nerf_sh4_fwd(b200nerf_ctx* ctx, const float* dirs, float* out, int64_t n
 int b200nerf_mlp_fwd(b200nerf_ctx* ctx, const float* x, int64_t n_rows, int in_dim, int n_layers,
                      const float* const* weights_host, const float* const* biases_host, const int* out_dims_host,
                      float* y, void* stream);
+/* The same forward for TRAINING: additionally stores the pre-activations of the hidden layers, hidden_pre_host[l]
+ * [n_rows, out_dims[l]] for l < n_layers - 1 (a HOST array of device pointers; entries may be NULL), which the backward
+ * (b200nerf_linear_wgrad on ReLU(pre-activation), b200nerf_relu_bwd) needs -- what torch autograd keeps for
+ * MLP.forward (mlp.py:142-183) instead of recomputing it. */
+int b200nerf_mlp_fwd_train(b200nerf_ctx* ctx, const float* x, int64_t n_rows, int in_dim, int n_layers,
+                           const float* const* weights_host, const float* const* biases_host, const int* out_dims_host,
+                           float* y, float* const* hidden_pre_host, void* stream);
 
 /* ---- module-level seams: the reference's Field / Sampler / Encoding nn.Modules as stand-alone operators ----
  * (SURVEY.md 8b).  The fused b200nerf_nff_render_fwd never materialises a per-sample tensor; these do, because the

@@ -102,18 +102,26 @@ class MlpFn(Function):
     def forward(ctx, be, x, *wb):
         ws, bs = list(wb[0::2]), list(wb[1::2])
         ctx.be = be
-        ctx.save_for_backward(x, *wb)
-        return be.mlp_fwd(x, ws, bs)
+        if any(ctx.needs_input_grad[1:]) and len(ws) > 1:
+            # like autograd keeps them for MLP.forward: the hidden pre-activations, stored by the same launch
+            y, zs = be.mlp_fwd(x, ws, bs, want_hidden=True)
+        else:
+            y, zs = be.mlp_fwd(x, ws, bs), []
+        ctx.n_hidden = len(zs)
+        ctx.save_for_backward(x, *wb, *zs)
+        return y
 
     @staticmethod
     @_bwd
     def backward(ctx, dy):
-        x, *wb = ctx.saved_tensors
+        x, *rest = ctx.saved_tensors
+        wb = rest[: len(rest) - ctx.n_hidden]
+        zs = rest[len(rest) - ctx.n_hidden:] if ctx.n_hidden else None
         ws, bs = list(wb[0::2]), list(wb[1::2])
         needs = ctx.needs_input_grad
         dws = [torch.zeros_like(w) if needs[2 + 2 * l] or needs[3 + 2 * l] else None for l, w in enumerate(ws)]
         dbs = [torch.zeros_like(b) if dws[l] is not None else None for l, b in enumerate(bs)]
-        dx = ctx.be.mlp_bwd(x, ws, bs, dy.contiguous(), dws, dbs, need_dx=needs[1])
+        dx = ctx.be.mlp_bwd(x, ws, bs, dy.contiguous(), dws, dbs, need_dx=needs[1], hidden=zs)
         grads = []
         for l in range(len(ws)):
             grads += [dws[l] if needs[2 + 2 * l] else None, dbs[l] if needs[3 + 2 * l] else None]

@@ -327,9 +327,11 @@ class B200Backend:
         self._check(self.lib.b200nerf_sh4_fwd(self._h, _ptr(d), _ptr(out), d.shape[0], self._stream))
         return out.reshape(*dirs.shape[:-1], 16)
 
-    def mlp_fwd(self, x: torch.Tensor, weights: Sequence[torch.Tensor], biases: Optional[Sequence[Optional[torch.Tensor]]] = None) -> torch.Tensor:
+    def mlp_fwd(self, x: torch.Tensor, weights: Sequence[torch.Tensor], biases: Optional[Sequence[Optional[torch.Tensor]]] = None,
+                want_hidden: bool = False):
         """MLP.forward (field_components/mlp.py:142-183) on the tcgen05 tensor cores (3xTF32): ReLU hidden
-        activations, no output activation.  weights[i] is nn.Linear's [out_i, in_i]."""
+        activations, no output activation.  weights[i] is nn.Linear's [out_i, in_i].  `want_hidden` (training): returns
+        (y, [pre-activation of hidden layer l, [n_rows, out_l]]) -- what the backward needs, stored by the same launch."""
         xs = self._dev(x).reshape(-1, x.shape[-1])
         ws = [self._dev(w) for w in weights]
         bs = [None if (biases is None or b is None) else self._dev(b) for b in (biases if biases is not None else [None] * len(ws))]
@@ -339,6 +341,11 @@ class B200Backend:
         cw = (ctypes.c_void_p * nl)(*[w.data_ptr() for w in ws])
         cb = (ctypes.c_void_p * nl)(*[(b.data_ptr() if b is not None else None) for b in bs])
         co = (ctypes.c_int * nl)(*out_dims)
+        if want_hidden:
+            zs = [torch.empty(n, d, device=self.device) for d in out_dims[:-1]]
+            ch = (ctypes.c_void_p * max(nl - 1, 1))(*[z.data_ptr() for z in zs])
+            self._check(self.lib.b200nerf_mlp_fwd_train(self._h, _ptr(xs), n, xs.shape[1], nl, cw, cb, co, _ptr(y), ch, self._stream))
+            return y.reshape(*x.shape[:-1], out_dims[-1]), zs
         self._check(self.lib.b200nerf_mlp_fwd(self._h, _ptr(xs), n, xs.shape[1], nl, cw, cb, co, _ptr(y), self._stream))
         return y.reshape(*x.shape[:-1], out_dims[-1])
 
@@ -619,14 +626,16 @@ class B200Backend:
         return dz
 
     def mlp_bwd(self, x: torch.Tensor, weights: Sequence[torch.Tensor], biases: Optional[Sequence[Optional[torch.Tensor]]], dy: torch.Tensor,
-                dweights: Sequence[Optional[torch.Tensor]], dbiases: Sequence[Optional[torch.Tensor]], need_dx: bool = True) -> Optional[torch.Tensor]:
+                dweights: Sequence[Optional[torch.Tensor]], dbiases: Sequence[Optional[torch.Tensor]], need_dx: bool = True,
+                hidden: Optional[Sequence[torch.Tensor]] = None) -> Optional[torch.Tensor]:
         """MLP.forward backward (field_components/mlp.py:142-178): accumulates into dweights[l] / dbiases[l] (entries may
         be None) and returns dL/dx.  Hidden pre-activations are recomputed with prefix forward passes (tcgen05); dX = dY W
         runs through the same tensor-core operator with the transposed weight; dW through linear_wgrad."""
         x2 = self._dev(x).reshape(-1, x.shape[-1])
         nl = len(weights)
         bs = list(biases) if biases is not None else [None] * nl
-        zs = [self.mlp_fwd(x2, weights[: l + 1], bs[: l + 1]) for l in range(nl - 1)]  # pre-activation of hidden layer l
+        # pre-activation of hidden layer l: kept by the training forward (mlp_fwd(want_hidden=True)), else recomputed
+        zs = list(hidden) if hidden is not None else [self.mlp_fwd(x2, weights[: l + 1], bs[: l + 1]) for l in range(nl - 1)]
         g = self._dev(dy).reshape(x2.shape[0], -1)
         for l in range(nl - 1, -1, -1):
             inp = x2 if l == 0 else zs[l - 1]

@@ -751,6 +751,7 @@ struct MlpArgs {
   int smem_off[3];  // float offsets of each layer's (hi) tile; lo follows at +n_pad*k_pad
   int bias_off;
   int stage_off;  // 2 x [128][max(kTcKMax, kTcNMax) + 1] row tiles (input rows in / output rows out, double buffered)
+  float* hidden_pre[2];  // training: pre-activation rows [n_rows, n_real[l]] of hidden layer l, or NULL
 };
 template <int kTcKMax, int kTcNMax>
 __global__ void __launch_bounds__(128) mlp_tc_kernel(const MlpArgs a, const float* __restrict__ x, float* __restrict__ y,
@@ -836,10 +837,24 @@ __global__ void __launch_bounds__(128) mlp_tc_kernel(const MlpArgs a, const floa
       tc::wait_ld();
       const float* bias = sm_mlp + a.bias_off + l * kTcNMax;
       const bool last = l == a.n_layers - 1;
+      float* hid = last ? nullptr : a.hidden_pre[l];  // warp-uniform
 #pragma unroll
       for (int k = 0; k < kTcNMax; ++k) {
         float o = k < a.n_pad[l] ? __uint_as_float(d[k]) + bias[k] : 0.f;
+        if (hid && k < a.n_real[l]) stage[tid * kPitch + k] = o;  // (the input rows were consumed before this layer's barrier)
         v[k] = last ? o : fmaxf(o, 0.f);
+      }
+      if (hid) {  // the hidden pre-activation rows leave through the same tile, coalesced
+        __syncthreads();
+        const int W = a.n_real[l], n_el = rows_here * W, qstep = 128 / W, rstep = 128 - qstep * W;
+        float* dst = hid + tile * 128 * W;
+        int r = tid / W, cidx = tid - r * W;
+        for (int e = tid; e < n_el; e += 128) {
+          dst[e] = stage[r * kPitch + cidx];
+          r += qstep, cidx += rstep;
+          if (cidx >= W) cidx -= W, ++r;
+        }
+        __syncthreads();
       }
     }
     // every thread passed the layer loop's barriers after reading its input row: the tile can take the output rows
@@ -1458,9 +1473,22 @@ int b200nerf_nff_render_fwd(b200nerf_ctx* c, const b200nerf_rays* rays, int64_t 
 }
 
 
+static int mlp_fwd_impl(b200nerf_ctx* c, const float* x, int64_t n_rows, int in_dim, int n_layers,
+                        const float* const* weights_host, const float* const* biases_host, const int* out_dims_host,
+                        float* y, float* const* hidden_pre_host, void* stream);
 int b200nerf_mlp_fwd(b200nerf_ctx* c, const float* x, int64_t n_rows, int in_dim, int n_layers,
                      const float* const* weights_host, const float* const* biases_host, const int* out_dims_host,
                      float* y, void* stream) {
+  return mlp_fwd_impl(c, x, n_rows, in_dim, n_layers, weights_host, biases_host, out_dims_host, y, nullptr, stream);
+}
+int b200nerf_mlp_fwd_train(b200nerf_ctx* c, const float* x, int64_t n_rows, int in_dim, int n_layers,
+                           const float* const* weights_host, const float* const* biases_host, const int* out_dims_host,
+                           float* y, float* const* hidden_pre_host, void* stream) {
+  return mlp_fwd_impl(c, x, n_rows, in_dim, n_layers, weights_host, biases_host, out_dims_host, y, hidden_pre_host, stream);
+}
+static int mlp_fwd_impl(b200nerf_ctx* c, const float* x, int64_t n_rows, int in_dim, int n_layers,
+                        const float* const* weights_host, const float* const* biases_host, const int* out_dims_host,
+                        float* y, float* const* hidden_pre_host, void* stream) {
   REQUIRE(c && weights_host && out_dims_host, "NULL argument");
   REQUIRE(n_layers >= 1 && n_layers <= 3, "MLP depth must be 1..3 Linear layers");
   constexpr int kWide = 64;
@@ -1488,6 +1516,7 @@ int b200nerf_mlp_fwd(b200nerf_ctx* c, const float* x, int64_t n_rows, int in_dim
     k = n;
   }
   a.bias_off = off;
+  for (int l = 0; l + 1 < n_layers && l < 2; ++l) a.hidden_pre[l] = hidden_pre_host ? hidden_pre_host[l] : nullptr;
   // NeuRAD's own MLPs (<= 48 wide) use the 48-column tile; wider ones (config 1's 32 -> 64 -> 4) the 64-column tile
   const int tile_w = wmax <= 48 ? 48 : kWide;
   a.stage_off = off + 3 * tile_w;

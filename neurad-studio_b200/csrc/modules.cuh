@@ -416,33 +416,50 @@ __global__ void relu_bwd_kernel(const float* __restrict__ z, float* __restrict__
 // db[o] += sum_p dY[p][o]; K, N <= 64.  A CTA walks row tiles of 32, stages X / dY in shared memory and keeps its
 // share of the N*K outputs in registers (first version on the CUDA cores: K = rows is the long GEMM dimension here and
 // the output is at most 64 x 64; a split-K tcgen05 version is the next step for this operator).
-constexpr int kWgradThreads = 256, kWgradRows = 32, kWgradMaxOut = 64 * 64 / kWgradThreads;
+constexpr int kWgradThreads = 256, kWgradRows = 64;
 __global__ void __launch_bounds__(kWgradThreads) linear_wgrad_kernel(const float* __restrict__ x, const float* __restrict__ dy,
                                                                      int64_t n_rows, int K, int N, int relu_x,
                                                                      float* __restrict__ dW, float* __restrict__ db) {
-  __shared__ float xs[kWgradRows * 64];
+  __shared__ __align__(16) float xs[kWgradRows * 64];
   __shared__ __align__(16) float dys[kWgradRows * 64];
-  const int ldy = (N + 3) & ~3;  // dY rows padded to whole quads (pad columns zero)
-  float acc[kWgradMaxOut];
+  const int ldx = (K + 3) & ~3, ldy = (N + 3) & ~3;  // rows padded to whole quads (pad columns zero)
+  const WgradMap m = wgrad_map(K, N, kWgradThreads);
+  float acc[16];
 #pragma unroll
-  for (int j = 0; j < kWgradMaxOut; ++j) acc[j] = 0.f;
+  for (int j = 0; j < 16; ++j) acc[j] = 0.f;
   float bacc = 0.f;  // thread o < N accumulates db[o]
   const int64_t n_tiles = (n_rows + kWgradRows - 1) / kWgradRows;
   for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
     const int64_t r0 = t * kWgradRows;
     const int rows = (int)(n_rows - r0 < kWgradRows ? n_rows - r0 : kWgradRows);
-    for (int e = threadIdx.x; e < rows * K; e += kWgradThreads) xs[e] = x[r0 * K + e];
+    for (int e = threadIdx.x; e < rows * ldx; e += kWgradThreads) {
+      const int r = e / ldx, c = e - r * ldx;
+      xs[e] = c < K ? x[(r0 + r) * K + c] : 0.f;
+    }
     for (int e = threadIdx.x; e < rows * ldy; e += kWgradThreads) {
       const int r = e / ldy, c = e - r * ldy;
       dys[e] = c < N ? dy[(r0 + r) * N + c] : 0.f;
     }
     __syncthreads();
-    wgrad_tile(threadIdx.x, kWgradThreads, xs, dys, rows, K, N, ldy, relu_x != 0, acc);
+    wgrad_tile(threadIdx.x, m, xs, dys, rows, ldx, ldy, relu_x != 0, acc);
     if (db && threadIdx.x < N)
       for (int r = 0; r < rows; ++r) bacc += dys[r * ldy + threadIdx.x];
     __syncthreads();
   }
-  wgrad_flush(threadIdx.x, kWgradThreads, K, N, ldy, acc, [&](int e, float v) { atomicAdd(dW + e, v); });
+  // the row groups' partial blocks are summed through shared memory (xs is free now), then one atomic per output and CTA
+  const int g = threadIdx.x / m.blocks, b = threadIdx.x - g * m.blocks;
+  float* part = xs;  // [(G - 1) * blocks][16] <= 15 * 256 floats
+  if (g > 0 && g < m.G) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) part[((g - 1) * m.blocks + b) * 16 + j] = acc[j];
+  }
+  __syncthreads();
+  if (g == 0) {
+    for (int gg = 1; gg < m.G; ++gg)
+#pragma unroll
+      for (int j = 0; j < 16; ++j) acc[j] += part[((gg - 1) * m.blocks + b) * 16 + j];
+    wgrad_flush(b, m, K, N, acc, [&](int e, float v) { atomicAdd(dW + e, v); });
+  }
   if (db && threadIdx.x < N) atomicAdd(db + threadIdx.x, bacc);
 }
 

@@ -764,50 +764,52 @@ NFF_D float zipnerf_interlevel_ray(const float* c, const float* w, int S, const 
 }
 
 // One tile of the weight gradient of a Linear layer, dW[o][i] += sum_r dY[r][o] * act(X[r][i]) (act = ReLU when the
-// layer's input is a hidden activation stored as its pre-activation).  Outputs are owned in QUADS of four consecutive o
-// for one input i: quad q = tid + j * nthreads (q = og*K + i, o = 4*og + c), j < MAXOUT / 4, kept in acc[4*j + c]
-// (registers: the j loop is unrolled).  Per staged row a quad costs one shared-memory read of X[r][i] and one 16-byte
-// read of dY[r][4*og .. 4*og+3] (a broadcast when the warp's lanes share og) for four FMAs; the first version read two
-// words per FMA and was bound by shared-memory bandwidth.  xs [rows][K]; dys [rows][ldy] with ldy = N rounded up to a
-// multiple of 4, the pad columns zero, 16-byte aligned.
-template <int MAXOUT>
-NFF_D void wgrad_tile(int tid, int nthreads, const float* xs, const float* dys, int rows, int K, int N, int ldy, bool relu_x,
-                      float (&acc)[MAXOUT]) {
-  const int n_quads = (ldy >> 2) * K;
-#if defined(__CUDACC__)
-#pragma unroll
-#endif
-  for (int j = 0; j < MAXOUT / 4; ++j) {
-    const int q = tid + j * nthreads;
-    if (q >= n_quads) continue;
-    const int og = q / K, i = q - og * K;
-    float a0 = acc[4 * j], a1 = acc[4 * j + 1], a2 = acc[4 * j + 2], a3 = acc[4 * j + 3];
-    for (int r = 0; r < rows; ++r) {
-      float x = xs[r * K + i];
-      if (relu_x) x = fmaxf(x, 0.0f);
-      const float4 d = *reinterpret_cast<const float4*>(dys + r * ldy + 4 * og);
-      a0 = fmaf(d.x, x, a0), a1 = fmaf(d.y, x, a1), a2 = fmaf(d.z, x, a2), a3 = fmaf(d.w, x, a3);
-    }
-    acc[4 * j] = a0, acc[4 * j + 1] = a1, acc[4 * j + 2] = a2, acc[4 * j + 3] = a3;
+// layer's input is a hidden activation stored as its pre-activation).  The N x K outputs are cut into 4 x 4 blocks
+// (NB = ceil(N/4) x KB = ceil(K/4) of them, at most 256); with fewer blocks than threads the tile's rows are split
+// over G = nthreads / blocks row groups.  Thread tid = g * blocks + b owns block b = ob * KB + ib for the rows
+// r = g, g + G, ...: one 16-byte read of act(X[r][4ib..4ib+3]) and one of dY[r][4ob..4ob+3] feed 16 FMAs (the first
+// version read two words per FMA and was bound by shared-memory bandwidth; a 1 x 4 blocking still spent half its
+// issue slots on loads).  xs [rows][ldx], dys [rows][ldy]: pitches = K / N rounded up to a multiple of 4, the pad
+// columns zero, 16-byte aligned.  acc[4*c + d] belongs to dW[4*ob + c][4*ib + d].
+struct WgradMap {
+  int KB, blocks, G;  // blocks = NB * KB; G row groups
+};
+NFF_HD WgradMap wgrad_map(int K, int N, int nthreads) {
+  WgradMap m;
+  m.KB = (K + 3) >> 2;
+  m.blocks = ((N + 3) >> 2) * m.KB;
+  m.G = nthreads / m.blocks;
+  if (m.G < 1) m.G = 1;
+  return m;
+}
+NFF_D void wgrad_tile(int tid, const WgradMap& m, const float* xs, const float* dys, int rows, int ldx, int ldy, bool relu_x,
+                      float (&acc)[16]) {
+  const int g = tid / m.blocks, b = tid - g * m.blocks;
+  if (g >= m.G) return;  // threads past G * blocks idle
+  const int ob = b / m.KB, ib = b - ob * m.KB;
+  for (int r = g; r < rows; r += m.G) {
+    float4 x = *reinterpret_cast<const float4*>(xs + r * ldx + 4 * ib);
+    if (relu_x) x.x = fmaxf(x.x, 0.0f), x.y = fmaxf(x.y, 0.0f), x.z = fmaxf(x.z, 0.0f), x.w = fmaxf(x.w, 0.0f);
+    const float4 d = *reinterpret_cast<const float4*>(dys + r * ldy + 4 * ob);
+    acc[0] = fmaf(d.x, x.x, acc[0]), acc[1] = fmaf(d.x, x.y, acc[1]), acc[2] = fmaf(d.x, x.z, acc[2]), acc[3] = fmaf(d.x, x.w, acc[3]);
+    acc[4] = fmaf(d.y, x.x, acc[4]), acc[5] = fmaf(d.y, x.y, acc[5]), acc[6] = fmaf(d.y, x.z, acc[6]), acc[7] = fmaf(d.y, x.w, acc[7]);
+    acc[8] = fmaf(d.z, x.x, acc[8]), acc[9] = fmaf(d.z, x.y, acc[9]), acc[10] = fmaf(d.z, x.z, acc[10]), acc[11] = fmaf(d.z, x.w, acc[11]);
+    acc[12] = fmaf(d.w, x.x, acc[12]), acc[13] = fmaf(d.w, x.y, acc[13]), acc[14] = fmaf(d.w, x.z, acc[14]), acc[15] = fmaf(d.w, x.w, acc[15]);
   }
 }
-// where thread `tid`'s accumulators go: dW[o*K + i] += acc[4*j + c] for o = 4*og + c < N
-template <int MAXOUT, class Add>
-NFF_D void wgrad_flush(int tid, int nthreads, int K, int N, int ldy, const float (&acc)[MAXOUT], Add add) {
-  const int n_quads = (ldy >> 2) * K;
+// where block b's accumulators go: add(o * K + i, acc[4*c + d]) for o = 4*ob + c < N, i = 4*ib + d < K
+template <class Add>
+NFF_D void wgrad_flush(int b, const WgradMap& m, int K, int N, const float (&acc)[16], Add add) {
+  const int ob = b / m.KB, ib = b - ob * m.KB;
 #if defined(__CUDACC__)
 #pragma unroll
 #endif
-  for (int j = 0; j < MAXOUT / 4; ++j) {
-    const int q = tid + j * nthreads;
-    if (q >= n_quads) continue;
-    const int og = q / K, i = q - og * K;
+  for (int c = 0; c < 4; ++c)
 #if defined(__CUDACC__)
 #pragma unroll
 #endif
-    for (int c = 0; c < 4; ++c)
-      if (4 * og + c < N) add((4 * og + c) * K + i, acc[4 * j + c]);
-  }
+    for (int d = 0; d < 4; ++d)
+      if (4 * ob + c < N && 4 * ib + d < K) add((4 * ob + c) * K + 4 * ib + d, acc[4 * c + d]);
 }
 
 }  // namespace nff

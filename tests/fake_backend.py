@@ -114,13 +114,16 @@ class FakeBackend(B200Backend):
 
     # ---- leaves that exist (and are GPU-validated) since earlier commits: the oracle's restatements
     @torch.no_grad()
-    def mlp_fwd(self, x, weights, biases=None):
+    def mlp_fwd(self, x, weights, biases=None, want_hidden=False):
         y = x.reshape(-1, x.shape[-1])
+        zs = []
         for i, w in enumerate(weights):
             y = torch.nn.functional.linear(y, w, None if biases is None else biases[i])
             if i < len(weights) - 1:
+                zs.append(y)
                 y = torch.relu(y)
-        return y.reshape(*x.shape[:-1], y.shape[-1])
+        y = y.reshape(*x.shape[:-1], y.shape[-1])
+        return (y, zs) if want_hidden else y
 
     @torch.no_grad()
     def frustum_positions(self, origins, directions, bins_e, aabb=None):

@@ -405,24 +405,29 @@ int emul_weights_bwd(int from_alpha, const float* a, const float* b, const float
 // linear_wgrad_kernel's tiling (modules.cuh) with `n_ctas` CTAs of 256 "threads" run one after the other.
 int emul_linear_wgrad(const float* x, const float* dy, long long n_rows, int K, int N, int relu_x, int n_ctas, float* dW,
                       float* db) {
-  constexpr int kThreads = 256, kRows = 32, kMaxOut = 64 * 64 / kThreads;
+  constexpr int kThreads = 256, kRows = 64;
   const long long n_tiles = (n_rows + kRows - 1) / kRows;
-  const int ldy = (N + 3) & ~3;
-  alignas(16) float dys[kRows * 64];  // the staged dY tile: rows padded to whole quads, pad columns zero
+  const int ldx = (K + 3) & ~3, ldy = (N + 3) & ~3;
+  const WgradMap m = wgrad_map(K, N, kThreads);
+  alignas(16) float xs[kRows * 64];   // the staged tiles: rows padded to whole quads, pad columns zero
+  alignas(16) float dys[kRows * 64];
   for (int cta = 0; cta < n_ctas; ++cta)
     for (int tid = 0; tid < kThreads; ++tid) {
-      float acc[kMaxOut] = {};
+      float acc[16] = {};
       float bacc = 0.f;
       for (long long t = cta; t < n_tiles; t += n_ctas) {
         const long long r0 = t * kRows;
         const int rows = (int)(n_rows - r0 < kRows ? n_rows - r0 : kRows);
-        for (int r = 0; r < rows; ++r)
+        for (int r = 0; r < rows; ++r) {
+          for (int c = 0; c < ldx; ++c) xs[r * ldx + c] = c < K ? x[(r0 + r) * K + c] : 0.f;
           for (int c = 0; c < ldy; ++c) dys[r * ldy + c] = c < N ? dy[(r0 + r) * N + c] : 0.f;
-        wgrad_tile(tid, kThreads, x + r0 * K, dys, rows, K, N, ldy, relu_x != 0, acc);
+        }
+        wgrad_tile(tid, m, xs, dys, rows, ldx, ldy, relu_x != 0, acc);
         if (db && tid < N)
           for (int r = 0; r < rows; ++r) bacc += dys[r * ldy + tid];
       }
-      wgrad_flush(tid, kThreads, K, N, ldy, acc, [&](int e, float v) { dW[e] += v; });
+      const int g = tid / m.blocks, b = tid - g * m.blocks;
+      if (g < m.G) wgrad_flush(b, m, K, N, acc, [&](int e, float v) { dW[e] += v; });  // (the kernel sums the row groups in shared memory first)
       if (db && tid < N) db[tid] += bacc;
     }
   return 0;

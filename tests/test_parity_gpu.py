@@ -382,6 +382,15 @@ def test_mlp_fwd_tensor_core_vs_fp32(backend, dims, n_rows):
     for i, (w, b) in enumerate(zip(ws, bs)):
         p[f"m.layers.{i}.weight"], p[f"m.layers.{i}.bias"] = w, b
     assert rel_to_max(y, O.mlp_forward(p, "m", len(ws), x)) < 5e-6
+    # the training forward (b200nerf_mlp_fwd_train): the same output bit for bit, plus the hidden pre-activations
+    y2, zs = backend.mlp_fwd(x, ws, bs, want_hidden=True)
+    backend.check_status()
+    assert torch.equal(y2, y) and len(zs) == len(ws) - 1
+    h = x.double()
+    for i, z in enumerate(zs):
+        pre = h @ ws[i].double().T + bs[i].double()
+        assert z.shape == (n_rows, dims[i + 1]) and rel_to_max(z, pre.float()) < 5e-6, i
+        h = torch.relu(pre)
 
 
 def test_mlp_fwd_no_bias_and_empty(backend):
