@@ -246,6 +246,12 @@ int b200nerf_mlp_fwd(b200nerf_ctx* ctx, const float* x, int64_t n_rows, int in_d
 int b200nerf_mlp_fwd_train(b200nerf_ctx* ctx, const float* x, int64_t n_rows, int in_dim, int n_layers,
                            const float* const* weights_host, const float* const* biases_host, const int* out_dims_host,
                            float* y, float* const* hidden_pre_host, void* stream);
+/* Input gradient of one Linear layer of those MLPs (autograd of F.linear + ReLU, mlp.py:170-178):
+ *   dx [n_rows, dx_dim] = dy [n_rows, dy_dim] @ weight_t^T,   weight_t = the layer's nn.Linear weight TRANSPOSED, [dx_dim, dy_dim]
+ * and, when relu_z [n_rows, dx_dim] (the pre-activation that fed this layer through ReLU) is given, dx *= (relu_z > 0).
+ * Same tcgen05 3xTF32 operator as b200nerf_mlp_fwd. */
+int b200nerf_mlp_dgrad(b200nerf_ctx* ctx, const float* dy, int64_t n_rows, int dy_dim, const float* weight_t, int dx_dim,
+                       const float* relu_z, float* dx, void* stream);
 
 /* ---- module-level seams: the reference's Field / Sampler / Encoding nn.Modules as stand-alone operators ----
  * (SURVEY.md 8b).  The fused b200nerf_nff_render_fwd never materialises a per-sample tensor; these do, because the
@@ -361,7 +367,7 @@ int b200nerf_field_heads_bwd(b200nerf_ctx* ctx, const float* geo_out, const floa
 /* MLP backward pieces (field_components/mlp.py:142-178).  For layer l with input X (a hidden pre-activation Z when
  * relu_x != 0, so act = ReLU) and output gradient dY:
  *   b200nerf_linear_wgrad : dweight [out,in] += dY^T act(X), dbias [out] += sum dY            (widths <= 64)
- *   dX = dY W runs through b200nerf_mlp_fwd with the transposed weight (tcgen05), then
+ *   dX = dY W: b200nerf_mlp_dgrad (above; tcgen05, ReLU mask fused), or b200nerf_mlp_fwd with the transposed weight and
  *   b200nerf_relu_bwd     : dZ *= (Z > 0) in place. */
 int b200nerf_linear_wgrad(b200nerf_ctx* ctx, const float* x, const float* dy, int64_t n_rows, int in_dim, int out_dim,
                           int relu_x, float* dweight, float* dbias, void* stream);

@@ -620,6 +620,18 @@ class B200Backend:
         self._check(fn(self._h, _ptr(xs), _ptr(ds), xs.shape[0], xs.shape[1], ds.shape[1], int(relu_x), _ptr(dweight), _ptr(dbias),
                        self._stream))
 
+    def mlp_dgrad(self, dy: torch.Tensor, weight: torch.Tensor, relu_z: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """dX = dY W of one Linear layer (weight = nn.Linear's [out, in]) on the tcgen05 operator; with `relu_z` (the
+        pre-activation that fed the layer through ReLU) the result is masked by (relu_z > 0) in the same launch."""
+        g = self._dev(dy).reshape(-1, dy.shape[-1]).contiguous()
+        wt = self._dev(weight).t().contiguous()  # [in, out]
+        dx = torch.empty(g.shape[0], wt.shape[0], device=self.device)
+        if g.shape[0] == 0:
+            return dx
+        z = None if relu_z is None else self._dev(relu_z).reshape(g.shape[0], wt.shape[0]).contiguous()
+        self._check(self.lib.b200nerf_mlp_dgrad(self._h, _ptr(g), g.shape[0], g.shape[1], _ptr(wt), wt.shape[0], _ptr(z), _ptr(dx), self._stream))
+        return dx
+
     def relu_bwd(self, z: torch.Tensor, dz: torch.Tensor) -> torch.Tensor:
         """dz *= (z > 0), in place."""
         self._check(self.lib.b200nerf_relu_bwd(self._h, _ptr(z), _ptr(dz), dz.numel(), self._stream))
@@ -643,9 +655,7 @@ class B200Backend:
                 self.linear_wgrad(inp, g, l > 0, dweights[l], dbiases[l])
             if l == 0 and not need_dx:
                 return None
-            g = self.mlp_fwd(g, [weights[l].t().contiguous()], None)
-            if l > 0:
-                g = self.relu_bwd(zs[l - 1], g)
+            g = self.mlp_dgrad(g, weights[l], zs[l - 1] if l > 0 else None)
         return g.reshape(*x.shape)
 
     def lidar_carving_mask(self, bins_e: torch.Tensor, is_lidar: torch.Tensor, directions_norm: torch.Tensor,

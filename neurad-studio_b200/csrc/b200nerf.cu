@@ -752,6 +752,7 @@ struct MlpArgs {
   int bias_off;
   int stage_off;  // 2 x [128][max(kTcKMax, kTcNMax) + 1] row tiles (input rows in / output rows out, double buffered)
   float* hidden_pre[2];  // training: pre-activation rows [n_rows, n_real[l]] of hidden layer l, or NULL
+  const float* relu_mask;  // backward: rows [n_rows, out_dim] of a pre-activation Z; the output is multiplied by (Z > 0), or NULL
 };
 template <int kTcKMax, int kTcNMax>
 __global__ void __launch_bounds__(128) mlp_tc_kernel(const MlpArgs a, const float* __restrict__ x, float* __restrict__ y,
@@ -784,6 +785,7 @@ __global__ void __launch_bounds__(128) mlp_tc_kernel(const MlpArgs a, const floa
   // would hide the DRAM latency (ncu: 12 % warps active, 60 % of the stall samples on the long scoreboard).
   constexpr int kPitch = (kTcKMax > kTcNMax ? kTcKMax : kTcNMax) + 1;
   float* stage0 = sm_mlp + a.stage_off;
+  float* mask_tile = stage0 + 2 * 128 * kPitch;  // [128 * out_dim], present when a.relu_mask
   auto fetch_rows = [&](int64_t tile, float* buf) {  // asynchronous: 4-byte cp.async per element, no registers held
     const int rows_here = (int)(n_rows - tile * 128 < 128 ? n_rows - tile * 128 : 128);
     const float* src = x + tile * 128 * a.in_dim;
@@ -804,12 +806,21 @@ __global__ void __launch_bounds__(128) mlp_tc_kernel(const MlpArgs a, const floa
     const int rows_here = (int)(n_rows - tile * 128 < 128 ? n_rows - tile * 128 : 128);
     float* stage = stage0 + (it & 1) * (128 * kPitch);
     const int64_t next = tile + gridDim.x;
-    if (next * 128 < n_rows) {
-      fetch_rows(next, stage0 + ((it + 1) & 1) * (128 * kPitch));
-      asm volatile("cp.async.wait_group 1;" ::: "memory");
-    } else {
-      asm volatile("cp.async.wait_group 0;" ::: "memory");
+    // one cp.async group per iteration: the NEXT tile's input rows and (dgrad) THIS tile's mask rows, which are only needed
+    // by the store loop at the end of the iteration
+    const bool more = next * 128 < n_rows;
+    if (a.relu_mask) {
+      const float* src = a.relu_mask + tile * 128 * out_dim;
+      const uint32_t dst0 = (uint32_t)__cvta_generic_to_shared(mask_tile);
+      for (int e = tid; e < rows_here * out_dim; e += 128)
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst0 + 4u * e), "l"(src + e) : "memory");
+      if (!more) asm volatile("cp.async.commit_group;" ::: "memory");
     }
+    if (more) fetch_rows(next, stage0 + ((it + 1) & 1) * (128 * kPitch));  // commits the group
+    if (more || a.relu_mask)
+      asm volatile("cp.async.wait_group 1;" ::: "memory");  // everything but this iteration's group: this tile's rows are in
+    else
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncthreads();
     float v[kTcKMax];
 #pragma unroll
@@ -861,15 +872,31 @@ __global__ void __launch_bounds__(128) mlp_tc_kernel(const MlpArgs a, const floa
 #pragma unroll
     for (int k = 0; k < kTcNMax; ++k)
       if (k < out_dim) stage[tid * kPitch + k] = v[k];
+    if (a.relu_mask) asm volatile("cp.async.wait_group 0;" ::: "memory");  // this tile's mask rows (and the next tile's input)
     __syncthreads();
     {
       float* dst = y + tile * 128 * out_dim;
+      const float* mask = a.relu_mask ? mask_tile : nullptr;
       const int n_el = rows_here * out_dim, qstep = 128 / out_dim, rstep = 128 - qstep * out_dim;
       int r = tid / out_dim, cidx = tid - r * out_dim;
-      for (int e = tid; e < n_el; e += 128) {
-        dst[e] = stage[r * kPitch + cidx];
-        r += qstep, cidx += rstep;
-        if (cidx >= out_dim) cidx -= out_dim, ++r;
+      // 16 elements per thread at a time; the mask values (dgrad: the pre-activation rows, fetched into shared memory by
+      // cp.async at the top of the iteration) are read as a batch before the stores that depend on them
+      for (int e0 = tid; e0 < n_el; e0 += 128 * 16) {
+        float mk[16];
+#pragma unroll
+        for (int u = 0; u < 16; ++u) {
+          const int e = e0 + 128 * u;
+          mk[u] = (mask && e < n_el) ? mask[e] : 1.0f;
+        }
+#pragma unroll
+        for (int u = 0; u < 16; ++u) {
+          const int e = e0 + 128 * u;
+          if (e < n_el) {
+            dst[e] = mk[u] > 0.f ? stage[r * kPitch + cidx] : 0.f;
+            r += qstep, cidx += rstep;
+            if (cidx >= out_dim) cidx -= out_dim, ++r;
+          }
+        }
       }
     }
     __syncthreads();  // this buffer is the prefetch target of the next iteration
@@ -1475,7 +1502,7 @@ int b200nerf_nff_render_fwd(b200nerf_ctx* c, const b200nerf_rays* rays, int64_t 
 
 static int mlp_fwd_impl(b200nerf_ctx* c, const float* x, int64_t n_rows, int in_dim, int n_layers,
                         const float* const* weights_host, const float* const* biases_host, const int* out_dims_host,
-                        float* y, float* const* hidden_pre_host, void* stream);
+                        float* y, float* const* hidden_pre_host, void* stream, const float* relu_mask = nullptr);
 int b200nerf_mlp_fwd(b200nerf_ctx* c, const float* x, int64_t n_rows, int in_dim, int n_layers,
                      const float* const* weights_host, const float* const* biases_host, const int* out_dims_host,
                      float* y, void* stream) {
@@ -1486,9 +1513,15 @@ int b200nerf_mlp_fwd_train(b200nerf_ctx* c, const float* x, int64_t n_rows, int 
                            float* y, float* const* hidden_pre_host, void* stream) {
   return mlp_fwd_impl(c, x, n_rows, in_dim, n_layers, weights_host, biases_host, out_dims_host, y, hidden_pre_host, stream);
 }
+int b200nerf_mlp_dgrad(b200nerf_ctx* c, const float* dy, int64_t n_rows, int dy_dim, const float* weight_t, int dx_dim,
+                       const float* relu_z, float* dx, void* stream) {
+  const float* w[1] = {weight_t};
+  const int od[1] = {dx_dim};
+  return mlp_fwd_impl(c, dy, n_rows, dy_dim, 1, w, nullptr, od, dx, nullptr, stream, relu_z);
+}
 static int mlp_fwd_impl(b200nerf_ctx* c, const float* x, int64_t n_rows, int in_dim, int n_layers,
                         const float* const* weights_host, const float* const* biases_host, const int* out_dims_host,
-                        float* y, float* const* hidden_pre_host, void* stream) {
+                        float* y, float* const* hidden_pre_host, void* stream, const float* relu_mask) {
   REQUIRE(c && weights_host && out_dims_host, "NULL argument");
   REQUIRE(n_layers >= 1 && n_layers <= 3, "MLP depth must be 1..3 Linear layers");
   constexpr int kWide = 64;
@@ -1517,10 +1550,11 @@ static int mlp_fwd_impl(b200nerf_ctx* c, const float* x, int64_t n_rows, int in_
   }
   a.bias_off = off;
   for (int l = 0; l + 1 < n_layers && l < 2; ++l) a.hidden_pre[l] = hidden_pre_host ? hidden_pre_host[l] : nullptr;
+  a.relu_mask = relu_mask;
   // NeuRAD's own MLPs (<= 48 wide) use the 48-column tile; wider ones (config 1's 32 -> 64 -> 4) the 64-column tile
   const int tile_w = wmax <= 48 ? 48 : kWide;
   a.stage_off = off + 3 * tile_w;
-  size_t smem = sizeof(float) * (a.stage_off + 2 * 128 * (tile_w + 1));
+  size_t smem = sizeof(float) * (a.stage_off + 2 * 128 * (tile_w + 1) + (relu_mask ? 128 * out_dims_host[n_layers - 1] : 0));
   // function attributes are per device: one flag per context (several contexts, one per GPU, may share the process)
   bool& attr_set = c->mlp_attr_set;
   if (!attr_set) {

@@ -416,12 +416,31 @@ __global__ void relu_bwd_kernel(const float* __restrict__ z, float* __restrict__
 // db[o] += sum_p dY[p][o]; K, N <= 64.  A CTA walks row tiles of 32, stages X / dY in shared memory and keeps its
 // share of the N*K outputs in registers (first version on the CUDA cores: K = rows is the long GEMM dimension here and
 // the output is at most 64 x 64; a split-K tcgen05 version is the next step for this operator).
-constexpr int kWgradThreads = 256, kWgradRows = 64;
+constexpr int kWgradThreads = 256, kWgradRows = 32;
+// global -> shared copy of one [rows][W] row block into a tile of pitch ld (>= W, pad columns zero-filled), asynchronous
+// (cp.async: no registers, completion through commit / wait groups).  16-byte copies when the rows are whole quads.
+__device__ __forceinline__ void wgrad_fetch(const float* __restrict__ src, int rows, int W, int ld, float* tile, int tid) {
+  const uint32_t dst0 = (uint32_t)__cvta_generic_to_shared(tile);
+  if (ld == W && (reinterpret_cast<uintptr_t>(src) & 15) == 0) {
+    for (int e = tid; e < rows * (W >> 2); e += kWgradThreads)
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst0 + 16u * e), "l"(src + 4 * e) : "memory");
+  } else {
+    for (int e = tid; e < rows * ld; e += kWgradThreads) {
+      const int r = e / ld, c = e - r * ld;
+      const int ok = c < W;
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst0 + 4u * e), "l"(src + (int64_t)r * W + (ok ? c : 0)),
+                   "r"(ok ? 4 : 0)
+                   : "memory");
+    }
+  }
+}
 __global__ void __launch_bounds__(kWgradThreads) linear_wgrad_kernel(const float* __restrict__ x, const float* __restrict__ dy,
                                                                      int64_t n_rows, int K, int N, int relu_x,
                                                                      float* __restrict__ dW, float* __restrict__ db) {
-  __shared__ __align__(16) float xs[kWgradRows * 64];
-  __shared__ __align__(16) float dys[kWgradRows * 64];
+  // two stages: the next tile's rows are in flight while this one is multiplied (a CTA that waited for its own loads
+  // spent half its time at the first shared-memory store after them: profiles/r02_ncu_train_kernels.txt)
+  __shared__ __align__(16) float xs2[2][kWgradRows * 64];
+  __shared__ __align__(16) float dys2[2][kWgradRows * 64];
   const int ldx = (K + 3) & ~3, ldy = (N + 3) & ~3;  // rows padded to whole quads (pad columns zero)
   const WgradMap m = wgrad_map(K, N, kWgradThreads);
   float acc[16];
@@ -429,26 +448,36 @@ __global__ void __launch_bounds__(kWgradThreads) linear_wgrad_kernel(const float
   for (int j = 0; j < 16; ++j) acc[j] = 0.f;
   float bacc = 0.f;  // thread o < N accumulates db[o]
   const int64_t n_tiles = (n_rows + kWgradRows - 1) / kWgradRows;
-  for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+  auto fetch = [&](int64_t t, int buf) {
     const int64_t r0 = t * kWgradRows;
     const int rows = (int)(n_rows - r0 < kWgradRows ? n_rows - r0 : kWgradRows);
-    for (int e = threadIdx.x; e < rows * ldx; e += kWgradThreads) {
-      const int r = e / ldx, c = e - r * ldx;
-      xs[e] = c < K ? x[(r0 + r) * K + c] : 0.f;
-    }
-    for (int e = threadIdx.x; e < rows * ldy; e += kWgradThreads) {
-      const int r = e / ldy, c = e - r * ldy;
-      dys[e] = c < N ? dy[(r0 + r) * N + c] : 0.f;
+    wgrad_fetch(x + r0 * K, rows, K, ldx, xs2[buf], threadIdx.x);
+    wgrad_fetch(dy + r0 * N, rows, N, ldy, dys2[buf], threadIdx.x);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  if ((int64_t)blockIdx.x < n_tiles) fetch(blockIdx.x, 0);
+  int it = 0;
+  for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it) {
+    const int64_t r0 = t * kWgradRows;
+    const int rows = (int)(n_rows - r0 < kWgradRows ? n_rows - r0 : kWgradRows);
+    if (t + gridDim.x < n_tiles) {
+      fetch(t + gridDim.x, (it + 1) & 1);
+      asm volatile("cp.async.wait_group 1;" ::: "memory");
+    } else {
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
     }
     __syncthreads();
+    const float* xs = xs2[it & 1];
+    const float* dys = dys2[it & 1];
     wgrad_tile(threadIdx.x, m, xs, dys, rows, ldx, ldy, relu_x != 0, acc);
     if (db && threadIdx.x < N)
       for (int r = 0; r < rows; ++r) bacc += dys[r * ldy + threadIdx.x];
-    __syncthreads();
+    __syncthreads();  // this stage is the fetch target of the next iteration
   }
-  // the row groups' partial blocks are summed through shared memory (xs is free now), then one atomic per output and CTA
+  // the row groups' partial blocks are summed through shared memory (both x stages are free now: 4096 floats), then one
+  // atomic per output and CTA
   const int g = threadIdx.x / m.blocks, b = threadIdx.x - g * m.blocks;
-  float* part = xs;  // [(G - 1) * blocks][16] <= 15 * 256 floats
+  float* part = &xs2[0][0];  // [(G - 1) * blocks][16] <= 255 * 16 floats
   if (g > 0 && g < m.G) {
 #pragma unroll
     for (int j = 0; j < 16; ++j) part[((g - 1) * m.blocks + b) * 16 + j] = acc[j];

@@ -259,6 +259,12 @@ NFF_D void encode_levels_bwd(float* grad_table, const Grid& gr, const Gauss& g, 
 #endif
 constexpr int kBwdSegments = NFF_BWD_SEGMENTS;  // threads per ray: each walks ceil(S / kBwdSegments) consecutive samples
 constexpr uint32_t kAggEmpty = 0xffffffffu;
+#ifndef NFF_BWD_PAIR_X
+#define NFF_BWD_PAIR_X 1  // F = 1: x-adjacent corners that are adjacent rows share one 8-byte vector reduction
+#endif
+#ifndef NFF_BWD_PROBE_SKIP
+#define NFF_BWD_PROBE_SKIP 0  // MEASUREMENT PROBE ONLY (wrong gradients): drop the scatter of the first n levels to see what they cost
+#endif
 template <int K, int F>
 struct ScatterAgg {
   int tab;                                // table the pending sums belong to: -1 static, >= 0 actor, -2 none yet
@@ -282,8 +288,27 @@ NFF_D void scatter_cell(float* base, const uint32_t r[8], const float* v /* [8*F
     if (F == 4) {
       if (!(v[4 * k] == 0.0f && v[4 * k + 1] == 0.0f && v[4 * k + 2] == 0.0f && v[4 * k + 3] == 0.0f))
         atomic_add4(base + (size_t)r[k] * 4, v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
-    } else {
+    } else if (!NFF_BWD_PAIR_X) {
       if (v[k] != 0.0f) atomic_add(base + r[k], v[k]);
+    }
+  }
+  if (F == 1 && NFF_BWD_PAIR_X) {
+    // The x prime of the hash is 1, so the floor-x and ceil-x corners of an edge (same y, z) are rows h ^ ix and
+    // h ^ (ix + 1): for even ix they differ in bit 0 only, i.e. they are the two halves of one aligned 8-byte pair and
+    // take ONE vector reduction.  What limits this kernel is the number of L2 reduction requests (~85 G/s whether they
+    // carry 4 or 16 bytes), and half of all edges qualify.  Corner order (cell_rows): floor-x / ceil-x pairs are
+    // (2,1) (3,0) (6,5) (7,4).
+    constexpr int kF[4] = {2, 3, 6, 7}, kC[4] = {1, 0, 5, 4};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const uint32_t rf = r[kF[e]], rc = r[kC[e]];
+      const float vf = v[kF[e]], vc = v[kC[e]];
+      if ((rf ^ rc) == 1u) {
+        if (vf != 0.0f || vc != 0.0f) atomic_add2(base + (rf & ~1u), (rf & 1u) ? vc : vf, (rf & 1u) ? vf : vc);
+      } else {
+        if (vf != 0.0f) atomic_add(base + rf, vf);
+        if (vc != 0.0f) atomic_add(base + rc, vc);
+      }
     }
   }
 }
@@ -333,7 +358,7 @@ NFF_D void encode_levels_bwd_t(float* grad_table, const float* NFF_RESTRICT tabl
         for (int k = 0; k < 8; ++k) v[k] = ldg(tb + r[k]);
         dec_acc[l] = fmaf(scale, fmul(trilerp(v, c), w), dec_acc[l]);
       }
-      if (grad_table) {
+      if (grad_table && l >= NFF_BWD_PROBE_SKIP) {
         float gv[F];
         if (F == 4) {
           const float4 d4 = ldg(reinterpret_cast<const float4*>(src) + l);

@@ -46,6 +46,10 @@ NFF_D void atomic_add(float* p, float v) { atomicAdd(p, v); }
 NFF_D void atomic_add4(float* p, float a, float b, float c, float d) {
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
+// 8-byte vector reduction (REDG.E.ADD.F32x2) for two ADJACENT floats; p must be 8-byte aligned
+NFF_D void atomic_add2(float* p, float a, float b) {
+  asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(p), "f"(a), "f"(b) : "memory");
+}
 // hint: bring the line at p into L1 (no register, no scoreboard entry) -- the next sample's inputs of a sequential walk
 NFF_D void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 }  // namespace simt
@@ -111,6 +115,7 @@ template <typename T>
 inline T ldg(const T* p) { return *p; }
 inline void atomic_add(float* p, float v) { *p += v; }  // the backward emulation runs its "threads" one after the other
 inline void atomic_add4(float* p, float a, float b, float c, float d) { p[0] += a; p[1] += b; p[2] += c; p[3] += d; }
+inline void atomic_add2(float* p, float a, float b) { p[0] += a; p[1] += b; }
 inline void prefetch_l1(const void*) {}
 }  // namespace simt
 

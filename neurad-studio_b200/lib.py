@@ -105,6 +105,7 @@ SIGNATURES = {
                                  POINTER(c_int), c_void_p, c_void_p]),
     "b200nerf_mlp_fwd_train": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int, POINTER(c_void_p), POINTER(c_void_p),
                                        POINTER(c_int), c_void_p, POINTER(c_void_p), c_void_p]),
+    "b200nerf_mlp_dgrad": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
     "b200nerf_check_status": (c_int, [c_void_p]),
     "b200nerf_set_mlp_mode": (c_int, [c_void_p, c_int]),
     "b200nerf_set_peer_outputs": (c_int, [c_void_p, POINTER(PeerOutputs)]),

@@ -70,6 +70,13 @@ class FakeBackend(B200Backend):
         dz[~(z > 0)] = 0
         return dz
 
+    @torch.no_grad()
+    def mlp_dgrad(self, dy, weight, relu_z=None):
+        dx = dy.reshape(-1, dy.shape[-1]) @ weight
+        if relu_z is not None:
+            dx[~(relu_z.reshape(dx.shape) > 0)] = 0
+        return dx
+
     def field_heads_bwd(self, geo, dfeature, dsdf, dalpha, dx2):
         p, gdim = geo.shape[0], geo.shape[1] - 1
         dgeo = torch.zeros(p, gdim + 1)

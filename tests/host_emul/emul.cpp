@@ -405,7 +405,7 @@ int emul_weights_bwd(int from_alpha, const float* a, const float* b, const float
 // linear_wgrad_kernel's tiling (modules.cuh) with `n_ctas` CTAs of 256 "threads" run one after the other.
 int emul_linear_wgrad(const float* x, const float* dy, long long n_rows, int K, int N, int relu_x, int n_ctas, float* dW,
                       float* db) {
-  constexpr int kThreads = 256, kRows = 64;
+  constexpr int kThreads = 256, kRows = 32;
   const long long n_tiles = (n_rows + kRows - 1) / kRows;
   const int ldx = (K + 3) & ~3, ldy = (N + 3) & ~3;
   const WgradMap m = wgrad_map(K, N, kThreads);

@@ -391,6 +391,15 @@ def test_mlp_fwd_tensor_core_vs_fp32(backend, dims, n_rows):
         pre = h @ ws[i].double().T + bs[i].double()
         assert z.shape == (n_rows, dims[i + 1]) and rel_to_max(z, pre.float()) < 5e-6, i
         h = torch.relu(pre)
+    # the input gradient of the last layer through the same operator (b200nerf_mlp_dgrad), with and without the ReLU mask
+    dy = torch.randn(n_rows, dims[-1], generator=gen)
+    want = dy.double() @ ws[-1].double()
+    dx = backend.mlp_dgrad(dy, ws[-1])
+    assert rel_to_max(dx, want.float()) < 5e-6
+    if zs:
+        dxm = backend.mlp_dgrad(dy, ws[-1], zs[-1])
+        backend.check_status()
+        assert torch.equal(dxm, torch.where(zs[-1] > 0, dx, torch.zeros_like(dx)))
 
 
 def test_mlp_fwd_no_bias_and_empty(backend):
