@@ -9,16 +9,18 @@ def summarise(raw_csv, src_csv, n_rays, title):
     for h,u,v in zip(hdr,units,vals):
         if h in keys: out.append(f"{h:75s} {u:16s} {v}")
     rows = list(csv.reader(open(src_csv)))
-    hdr = rows[1]; idx = {h:i for i,h in enumerate(hdr)}
+    hi = next(i for i, r in enumerate(rows) if "Source" in r and "Instructions Executed" in r)  # header row (position varies with ncu options)
+    hdr = rows[hi]; rows = [None, hdr] + rows[hi + 1:]; idx = {h:i for i,h in enumerate(hdr)}
     stall_cols = [h for h in hdr if h.startswith("stall_") and "Not Issued" not in h]
-    tot = collections.Counter(); ops = collections.Counter(); n_inst=0
+    tot = collections.Counter(); ops = collections.Counter(); n_inst=0; n_sass=0
     for r in rows[2:]:
+        if r == hdr: break  # the page repeats itself (second view): one section is the kernel
         if len(r) < len(hdr): continue
-        ie = int(r[idx["Instructions Executed"]] or 0); n_inst += ie
+        ie = int(r[idx["Instructions Executed"]] or 0); n_inst += ie; n_sass += 1
         m = re.match(r"\s*(@!?U?P\d+\s+)?([A-Z0-9_.]+)", r[idx["Source"]]); op = m.group(2).split(".")[0] if m else "?"
         ops[op] += ie
         for c in stall_cols: tot[c] += int(r[idx[c]] or 0)
-    out += ["", f"SASS instructions in kernel: {len(rows)-2}; warp instructions executed: {n_inst} ({n_inst/n_rays:.0f} per ray)", "", "warp stall samples:"]
+    out += ["", f"SASS instructions in kernel: {n_sass}; warp instructions executed: {n_inst} ({n_inst/n_rays:.0f} per ray)", "", "warp stall samples:"]
     s = sum(tot.values())
     for k,v in tot.most_common(9): out.append(f"  {k:26s} {100*v/s:5.1f}%")
     out += ["", "executed instruction mix:"]
