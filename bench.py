@@ -243,11 +243,14 @@ class Step:
                 dist.all_gather_into_tensor(buf.view(-1), buf[self.rank].reshape(-1))
 
     # ------------------------------------------------------------------------------------- API / host-buffer arm
-    def _to_host(self, pairs, keep):
-        """D2H on the copy stream (copy engine) once the main stream has produced the tensors."""
+    def _to_host(self, pairs, keep, ready=None):
+        """D2H on the copy stream (copy engine) once the main stream (and, with a decoder stream, the image's decoder) has
+        produced the tensors."""
         ev = torch.cuda.Event()
         ev.record()
         self.copy_stream.wait_event(ev)
+        if ready is not None:
+            self.copy_stream.wait_event(ready)
         with torch.cuda.stream(self.copy_stream):
             for dst, src in pairs:
                 dst.copy_(src.reshape(dst.shape), non_blocking=True)
@@ -263,7 +266,7 @@ class Step:
                 be.set_peer_outputs(self._dev_peers, self_rank=self.rank, row_offset=self.rank * self.n + row)
             rb = self.cameras.generate_rays(camera_indices=i, keep_shape=True)
             out = model.get_outputs_for_camera_ray_bundle(rb)
-            self._to_host([(host[k], out[k]) for k in host], keep)
+            self._to_host([(host[k], out[k]) for k in host], keep, ready=out.get("rgb_ready"))
             row += CAM_RAYS
             self.e2e_launches += 1 + 5 + 3 + 10  # raygen, subsample copies, render pair + lidar head, decoder
         if self.p2p:
@@ -272,6 +275,8 @@ class Step:
         self._to_host([(self.host_lidar[k], out[k]) for k in self.host_lidar], keep)
         self.e2e_launches += 1 + 3
         self._finish_gather()
+        if getattr(model, "decoder_stream", None) is not None:
+            model.decoder_stream.synchronize()
         self.copy_stream.synchronize()
         torch.cuda.current_stream(self.dev).synchronize()
         return out
@@ -522,6 +527,11 @@ def main():
     kern_ms = sorted(a.elapsed_time(b) for a, b in step.kernel_events)
     kern_ms = sum(kern_ms) / len(kern_ms)
     step.e2e_launches = 0
+    # the API arm pipelines image i's rgb decoder (side stream) under image i + 1's render (NeuRADModel.set_decoder_stream);
+    # B200_E2E_DECODER_STREAM=0 keeps everything on one stream
+    dec_stream = os.environ.get("B200_E2E_DECODER_STREAM", "1") != "0"
+    if dec_stream:
+        model.set_decoder_stream(torch.cuda.Stream(device=dev))
     ms_e2e = timed(step.run_e2e, args.steps)
     e2e_launches = step.e2e_launches // args.steps
     # the host buffers the e2e arm filled must hold what the API returns on the device (last image + the sweep re-rendered)
@@ -531,6 +541,7 @@ def main():
         chk = model.get_outputs_for_camera_ray_bundle(step.cameras.generate_rays(len(cams) - 1))
         chk_l, _ = model.get_outputs_for_lidar(step.lidars, {"lidar": step.points_pinned, "lidar_idx": 0})
     torch.cuda.synchronize()
+    model.set_decoder_stream(None)
     e2e_ok = all(torch.equal(step.host_cam[-1][k], chk[k].cpu().reshape(step.host_cam[-1][k].shape)) for k in step.host_cam[-1]) and \
         all(torch.equal(step.host_lidar[k], chk_l[k].cpu().reshape(step.host_lidar[k].shape)) for k in step.host_lidar)
     # multi-GPU: every peer's slice of the fused gather against an NCCL all-gather of the local slices
@@ -646,10 +657,12 @@ def main():
     line = dict(base, value=value, ms_per_step=ms / args.steps, clocks=clocks, gpu_launches=launches,
                 e2e={"value": e2e_value, "unit": "rays/s", "h2d_bytes_per_step": step.h2d_bytes, "d2h_bytes_per_step": step.d2h_bytes,
                      "ms_per_step": ms_e2e / args.steps, "host_buffers_verified": bool(e2e_ok), "gpu_launches": e2e_launches,
+                     "decoder_stream": dec_stream,
                      "how": "per sensor through the API mirror, as pipelines/ad_pipeline.py:198-208,296-304 does: Cameras.generate_rays -> "
                             "NeuRADModel.get_outputs_for_camera_ray_bundle (render + lidar head + rgb CNN decoder), NeuRADModel.get_outputs_for_lidar "
                             "(sweep points from pinned host memory); rgb / depth / accumulation images and the lidar outputs copied to pinned host "
-                            "memory by the copy engine on a second stream; _bind() and all Python inside the timed region"},
+                            "memory by the copy engine on a second stream; with decoder_stream the rgb decoder of image i runs on a side stream under the render "
+                            "of image i + 1 (NeuRADModel.set_decoder_stream); _bind() and all Python inside the timed region"},
                 roofline=roof, numa=numa)
     if gather_ok is not None:
         line["gather_verified"] = gather_ok

@@ -1230,5 +1230,27 @@ class NeuRADModel(nn.Module):
         res = {k: v.view(*output_size, -1) for k, v in out.items()}
         res["ray_drop_prob"] = res["ray_drop_logits"].sigmoid()
         if len(output_size) == 2:  # camera: decode the feature image to rgb at `step` x the ray resolution
-            res["rgb"] = self.rgb_decoder(res["features"][None])[0]
+            ds = getattr(self, "decoder_stream", None)
+            if ds is None:
+                res["rgb"] = self.rgb_decoder(res["features"][None])[0]
+            else:
+                # opt-in pipelining (set_decoder_stream): this image's decoder runs on `ds` while the caller's stream goes on
+                # to the next image's render -- the sampling kernel (CUDA cores, issue-bound) and the convolutions (tensor
+                # pipe) use different parts of an SM.  `rgb` is ready when res["rgb_ready"] (a CUDA event) has completed.
+                feats = res["features"]
+                ev = torch.cuda.Event()
+                ev.record()
+                with torch.cuda.stream(ds):
+                    ds.wait_event(ev)
+                    res["rgb"] = self.rgb_decoder(feats[None])[0]
+                    feats.record_stream(ds)
+                    done = torch.cuda.Event()
+                    done.record(ds)
+                res["rgb_ready"] = done
         return res
+
+    def set_decoder_stream(self, stream: Optional["torch.cuda.Stream"]) -> None:
+        """Run the rgb decoder of `get_outputs_for_camera_ray_bundle` on a side stream (None: on the caller's stream, the
+        default and the reference's behaviour).  With a stream, outputs["rgb"] must not be consumed before
+        outputs["rgb_ready"] has completed (`stream.wait_event(outputs["rgb_ready"])` or `.synchronize()`)."""
+        self.decoder_stream = stream

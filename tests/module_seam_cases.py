@@ -517,6 +517,16 @@ def metric_entry_points(dev):
     assert rel_to_max(out["depth"].reshape(-1), ref["depth"].reshape(-1)) < 1e-4
     assert rel_to_max(out["features"].reshape(40, -1), ref["features"]) < 1e-4
     assert (out["rgb"].cpu() - rgb_ref).abs().max().item() < 1e-4
+    if torch.device(dev).type == "cuda":
+        # opt-in pipelining: the decoder on a side stream (three images back to back, like the bench's API arm) gives the same bits
+        model.set_decoder_stream(torch.cuda.Stream(device=dev))
+        outs = [model.get_outputs_for_camera_ray_bundle(rb) for _ in range(3)]
+        for o in outs:
+            assert "rgb_ready" in o
+            o["rgb_ready"].synchronize()
+            assert torch.equal(o["rgb"], out["rgb"]) and torch.equal(o["depth"], out["depth"])
+        model.set_decoder_stream(None)
+        assert "rgb_ready" not in model.get_outputs_for_camera_ray_bundle(rb)
     # lidar sweep
     scan = scene.pandar64_scan(time=2.0, beams=4, azimuths=25)
     lidars = Lidars([scan], dev)
