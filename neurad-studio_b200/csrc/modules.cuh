@@ -8,6 +8,8 @@
 namespace nff {
 
 constexpr int kModWarps = 8;
+// dynamic shared memory above which a launch opts in (the 48 KB default limit also counts a kernel's static shared memory)
+constexpr size_t kSmemOptIn = 47 * 1024;
 
 // Frustums.get_fast_isotropic_gaussian(num_multisamples=1) (cameras/rays.py:109-124): one thread per sample.
 __global__ void isotropic_gaussian_kernel(const float* __restrict__ origins, const float* __restrict__ dirs,
@@ -118,7 +120,7 @@ inline bool launch_neurad_encoding_fwd(const FieldGrids& fg, const Actors& A, co
   if (grid == 0) return true;
   auto launch = [&](auto kernel, int F) {
     const size_t smem = sizeof(float) * kModWarps * 32 * (8 * F + 1) + sizeof(ActorFrame) * kModWarps * (size_t)A.n_actors;
-    if (smem > 48 * 1024) cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (smem > kSmemOptIn) cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     kernel<<<grid, kModWarps * 32, smem, stream>>>(fg, A, a);
   };
   if (encode_bwd_fast_ok(fg, A.n_actors, 4))
@@ -314,10 +316,10 @@ inline bool launch_neurad_encoding_bwd(const FieldGrids& fg, const Actors& A, co
   const size_t smem = sizeof(ActorFrame) * kBwdRays * (size_t)A.n_actors;  // <= 64 KB at kModMaxActors
   if (grid == 0) return true;
   if (!a.ddensity && encode_bwd_fast_ok(fg, A.n_actors, 4)) {
-    if (smem > 48 * 1024) cudaFuncSetAttribute(neurad_encoding_bwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (smem > kSmemOptIn) cudaFuncSetAttribute(neurad_encoding_bwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     neurad_encoding_bwd_kernel<1><<<grid, kBwdThreads, smem, stream>>>(fg, A, a);
   } else if (a.ddensity && encode_bwd_fast_ok(fg, A.n_actors, 1)) {
-    if (smem > 48 * 1024) cudaFuncSetAttribute(neurad_encoding_bwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (smem > kSmemOptIn) cudaFuncSetAttribute(neurad_encoding_bwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     neurad_encoding_bwd_kernel<2><<<grid, kBwdThreads, smem, stream>>>(fg, A, a);
   } else {
     return false;
