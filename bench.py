@@ -425,7 +425,9 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     args.warmup = max(args.warmup, 3)
-    numa = bind_to_gpu_numa_node(local_rank) if args.impl == "b200" and world > 1 else {"node": None, "cpus": None}
+    # every rank (also the single one at N = 1: the API arm's pinned buffers and launch latencies otherwise depend on which
+    # socket the scheduler happened to start the process on -- 38.7 vs 44.4 ms per e2e step between two fresh boxes)
+    numa = bind_to_gpu_numa_node(local_rank) if args.impl == "b200" else {"node": None, "cpus": None}
 
     import neurad_studio_b200 as nsb
 
@@ -527,9 +529,10 @@ def main():
     kern_ms = sorted(a.elapsed_time(b) for a, b in step.kernel_events)
     kern_ms = sum(kern_ms) / len(kern_ms)
     step.e2e_launches = 0
-    # the API arm pipelines image i's rgb decoder (side stream) under image i + 1's render (NeuRADModel.set_decoder_stream);
-    # B200_E2E_DECODER_STREAM=0 keeps everything on one stream
-    dec_stream = os.environ.get("B200_E2E_DECODER_STREAM", "1") != "0"
+    # B200_E2E_DECODER_STREAM=1: the API arm pipelines image i's rgb decoder (side stream) under image i + 1's render
+    # (NeuRADModel.set_decoder_stream; +2 % in back-to-back A/B runs).  Off by default: two of three full bench runs with it
+    # showed a much slower e2e arm (44 / 61 ms per step instead of 38; the single-stream arm never did), not understood yet.
+    dec_stream = os.environ.get("B200_E2E_DECODER_STREAM", "0") != "0"
     if dec_stream:
         model.set_decoder_stream(torch.cuda.Stream(device=dev))
     ms_e2e = timed(step.run_e2e, args.steps)

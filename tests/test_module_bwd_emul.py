@@ -120,6 +120,47 @@ def test_encoding_backward_density_mode(name, bwd_variant):
         assert (grads["actors"][a] - want).abs().max().item() <= 1e-4 * max(want.abs().max().item(), 1e-6)
 
 
+@pytest.mark.parametrize("field,mode", [(0, "features"), (2, "density")])
+def test_encoding_backward_aggregation_equals_per_sample_scatter(field, mode):
+    """The kernel's device functions (contiguous ray segments, run-length aggregation of the coarse cells, x-pair vector
+    reductions) against the per-sample generic scatter on rays whose consecutive samples SHARE coarse cells (5 cm steps):
+    the same sums in a different order."""
+    meta, g = load_golden("nff_actors.npz")
+    cfg = cfg_from_meta(meta)
+    p, r = g["param"], g["ray"]
+    n, s = 24, 64
+    gen = torch.Generator().manual_seed(11)
+    o, d = r["origins"][:n], r["directions"][:n]
+    t = 0.5 + 0.05 * torch.arange(s + 1).float()[None, :] + torch.rand(n, 1, generator=gen)
+    area = r["pixel_area"].reshape(-1)[:n]
+    mean, std = emul.gaussian(o, d, area, t)
+    prefix = "field" if field == 0 else "proposal_fields.1"
+    keys = [f"{prefix}.hashgrid.static_grid.hash_table"] + [f"{prefix}.hashgrid.actor_grids.{a}.hash_table" for a in range(meta["n_actors"])]
+    width = p[keys[0]].shape[-1] * (8 if field == 0 else 6)
+    kw = {}
+    if mode == "features":
+        kw["dfeatures"] = torch.randn(n * s, width, generator=gen)
+    else:
+        kw["density"] = torch.rand(n, s, generator=gen) + 0.1
+        kw["ddensity"] = torch.randn(n, s, generator=gen)
+    out = {}
+    for variant in ("fast", "generic"):
+        emul.set_bwd_generic(variant == "generic")
+        grads = {"static": torch.zeros_like(p[keys[0]]), "actors": [torch.zeros_like(p[k]) for k in keys[1:]]}
+        if mode == "density":
+            grads["decoder"] = torch.zeros(6)
+        emul.encoding_bwd(cfg, p, O.pdf_u, field, mean, std, r["times"][:n], grads, **kw)
+        out[variant] = grads
+    emul.set_bwd_generic(False)
+    a, b = out["fast"], out["generic"]
+    assert b["static"].abs().max().item() > 0
+    assert rel_to_max(a["static"], b["static"]) < 2e-6
+    for x, y in zip(a["actors"], b["actors"]):
+        assert (x - y).abs().max().item() <= 2e-6 * max(y.abs().max().item(), 1e-6)
+    if mode == "density":
+        assert rel_to_max(a["decoder"], b["decoder"]) < 1e-5  # 1536 terms per weight, summed per segment vs per sample
+
+
 def test_encoding_backward_density_mode_clamps_like_trunc_exp():
     """Pre-activations outside [-15, 15]: the reference's trunc_exp backward is g * exp(clamp(x, -15, 15))
     (field_components/activations.py:38-41), not g * exp(x)."""
